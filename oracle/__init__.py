@@ -1,0 +1,196 @@
+"""ctypes binding of the CPU oracle (oracle/oracle.cpp) — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The shipped path (rust_debruijn_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "oracle.cpp")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        u64p, u32p, u16p, u8p = (C.POINTER(t) for t in (C.c_uint64, C.c_uint32, C.c_uint16, C.c_uint8))
+        L.orc_kmer_rc.restype = C.c_uint64
+        L.orc_kmer_rc.argtypes = [C.c_int, C.c_uint64]
+        L.orc_kmer_rc128.argtypes = [C.c_int, u64p, u64p]
+        L.orc_kmer_extend_left.restype = C.c_uint64
+        L.orc_kmer_extend_left.argtypes = [C.c_int, C.c_uint64, C.c_int]
+        L.orc_kmer_extend_right.restype = C.c_uint64
+        L.orc_kmer_extend_right.argtypes = [C.c_int, C.c_uint64, C.c_int]
+        L.orc_pack_bases.argtypes = [u8p, C.c_uint64, u64p]
+        L.orc_filter_kmers.restype = C.c_void_p
+        L.orc_filter_kmers.argtypes = [C.c_int, u64p, u64p, u32p, u8p, C.c_uint64, C.c_uint32, C.c_int, C.c_int,
+                                       C.c_uint64, C.c_int]
+        for f in ("orc_table_len", "orc_table_all_len", "orc_table_n_input"):
+            getattr(L, f).restype = C.c_uint64
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_table_passes.argtypes = [C.c_void_p]
+        L.orc_table_copy.argtypes = [C.c_void_p, u64p, u64p, u8p, u16p, u64p, u64p]
+        L.orc_table_free.argtypes = [C.c_void_p]
+        L.orc_compress_kmers.restype = C.c_void_p
+        L.orc_compress_kmers.argtypes = [C.c_int, C.c_uint64, u64p, u64p, u8p, u16p, C.c_int, C.c_int, u32p]
+        L.orc_graph_error.argtypes = [C.c_void_p]
+        for f in ("orc_graph_n_nodes", "orc_graph_n_bases"):
+            getattr(L, f).restype = C.c_uint64
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_graph_copy.argtypes = [C.c_void_p, u64p, u64p, u32p, u8p, u16p]
+        L.orc_graph_free.argtypes = [C.c_void_p]
+        L.orc_msp_scan.restype = C.c_int64
+        L.orc_msp_scan.argtypes = [C.c_int, C.c_int, u8p, C.c_uint32, u64p, C.c_int, u32p, u32p, u32p, u64p, u64p, u8p]
+        L.orc_synth_genome_bases.restype = C.c_uint64
+        L.orc_synth_genome_bases.argtypes = [C.c_uint64]
+        L.orc_synth_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, u64p]
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+SAT_ADD, WRAP_ADD, ADD_MOD_65535, MAX = 0, 1, 2, 3
+ERR_THR_NOISY = 83886
+
+
+def pack_bases(bases):
+    """0..3 bases (uint8 array) -> DnaString words (src/dna_string.rs:383-399)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    words = np.zeros((len(bases) + 31) // 32, dtype=np.uint64)
+    if len(bases):
+        lib().orc_pack_bases(_p(bases, C.c_uint8), len(bases), _p(words, C.c_uint64))
+    return words
+
+
+def seqset_from_lists(seqs):
+    """list of uint8 base arrays -> (words, start, length) in PackedDnaStringSet layout."""
+    length = np.array([len(s) for s in seqs], dtype=np.uint32)
+    start = np.zeros(len(seqs), dtype=np.uint64)
+    if len(seqs):
+        start[1:] = np.cumsum(length.astype(np.uint64))[:-1]
+    cat = np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs]) if len(seqs) else np.zeros(0, np.uint8)
+    return pack_bases(cat), start, length
+
+
+def synth_reads(R, seed=1, err_thr=0):
+    """synth-v1: R reads x 150 bases, packed contiguously."""
+    words = np.zeros((150 * R + 31) // 32, dtype=np.uint64)
+    lib().orc_synth_reads(R, seed, err_thr, _p(words, C.c_uint64))
+    start = np.arange(R, dtype=np.uint64) * np.uint64(150)
+    length = np.full(R, 150, dtype=np.uint32)
+    return words, start, length
+
+
+def filter_kmers(k, words, start, length, seq_exts=None, min_obs=1, stranded=False, report_all=False, memory_gb=4,
+                 threads=1):
+    """src/filter.rs:139-231 with CountFilter.  Returns dict(kmers_lo, kmers_hi, exts, counts, all_lo, all_hi, ...)."""
+    L = lib()
+    words = np.ascontiguousarray(words, np.uint64)
+    start = np.ascontiguousarray(start, np.uint64)
+    length = np.ascontiguousarray(length, np.uint32)
+    if seq_exts is not None:
+        seq_exts = np.ascontiguousarray(seq_exts, np.uint8)
+    h = L.orc_filter_kmers(k, _p(words, C.c_uint64), _p(start, C.c_uint64), _p(length, C.c_uint32),
+                           _p(seq_exts, C.c_uint8), len(start), min_obs, int(stranded), int(report_all), memory_gb,
+                           threads)
+    n, na = L.orc_table_len(h), L.orc_table_all_len(h)
+    two = k > 32
+    out = dict(k=k, lo=np.zeros(n, np.uint64), hi=np.zeros(n if two else 0, np.uint64), exts=np.zeros(n, np.uint8),
+               counts=np.zeros(n, np.uint16), all_lo=np.zeros(na, np.uint64),
+               all_hi=np.zeros(na if two else 0, np.uint64), n_input=L.orc_table_n_input(h),
+               passes=L.orc_table_passes(h))
+    L.orc_table_copy(h, _p(out["lo"], C.c_uint64), _p(out["hi"], C.c_uint64), _p(out["exts"], C.c_uint8),
+                     _p(out["counts"], C.c_uint16), _p(out["all_lo"], C.c_uint64), _p(out["all_hi"], C.c_uint64))
+    L.orc_table_free(h)
+    return out
+
+
+def compress_kmers(k, lo, hi, exts, counts, stranded=False, reduce_op=SAT_ADD, seed_order=None):
+    """src/compression.rs:545-583 (CompressFromHash + SimpleCompress).  Returns BaseGraph arrays."""
+    L = lib()
+    lo = np.ascontiguousarray(lo, np.uint64)
+    hi = np.ascontiguousarray(hi, np.uint64) if k > 32 else None
+    exts = np.ascontiguousarray(exts, np.uint8)
+    counts = np.ascontiguousarray(counts, np.uint16)
+    if seed_order is not None:
+        seed_order = np.ascontiguousarray(seed_order, np.uint32)
+    h = L.orc_compress_kmers(k, len(lo), _p(lo, C.c_uint64), _p(hi, C.c_uint64), _p(exts, C.c_uint8),
+                             _p(counts, C.c_uint16), int(stranded), reduce_op, _p(seed_order, C.c_uint32))
+    err = L.orc_graph_error(h)
+    m, nb = L.orc_graph_n_nodes(h), L.orc_graph_n_bases(h)
+    g = dict(error=err, n_nodes=m, n_bases=nb, words=np.zeros((nb + 31) // 32, np.uint64), start=np.zeros(m, np.uint64),
+             length=np.zeros(m, np.uint32), exts=np.zeros(m, np.uint8), data=np.zeros(m, np.uint16), stranded=stranded)
+    L.orc_graph_copy(h, _p(g["words"], C.c_uint64), _p(g["start"], C.c_uint64), _p(g["length"], C.c_uint32),
+                     _p(g["exts"], C.c_uint8), _p(g["data"], C.c_uint16))
+    L.orc_graph_free(h)
+    return g
+
+
+def msp_scan(k, p, seq, perm=None, rc=True):
+    """src/msp.rs:207-324.  seq: uint8 0..3.  Returns dict of interval arrays."""
+    L = lib()
+    seq = np.ascontiguousarray(seq, np.uint8)
+    m = len(seq)
+    cap = max(m - k + 1, 1)
+    o = dict(start=np.zeros(cap, np.uint32), len=np.zeros(cap, np.uint32), minpos=np.zeros(cap, np.uint32),
+             minimizer=np.zeros(cap, np.uint64), bucket=np.zeros(cap, np.uint64), exts=np.zeros(cap, np.uint8))
+    if perm is not None:
+        perm = np.ascontiguousarray(perm, np.uint64)
+    n = L.orc_msp_scan(k, p, _p(seq, C.c_uint8), m, _p(perm, C.c_uint64), int(rc), _p(o["start"], C.c_uint32),
+                       _p(o["len"], C.c_uint32), _p(o["minpos"], C.c_uint32), _p(o["minimizer"], C.c_uint64),
+                       _p(o["bucket"], C.c_uint64), _p(o["exts"], C.c_uint8))
+    return {kk: v[:n] for kk, v in o.items()}
+
+
+# ---- checksums used by the golden anchors ---------------------------------
+def xor_valid(t):
+    lo = int(np.bitwise_xor.reduce(t["lo"])) if len(t["lo"]) else 0
+    if t["k"] > 32:
+        hi = int(np.bitwise_xor.reduce(t["hi"])) if len(t["hi"]) else 0
+        return (hi << 64) | lo
+    return lo
+
+
+def mix_valid(t):
+    e = t["exts"].astype(np.uint64)
+    s = (t["lo"] * (e + np.uint64(1)) + t["counts"].astype(np.uint64))
+    if t["k"] > 32:
+        s = s + t["hi"] * (e + np.uint64(3))
+    return int(np.add.reduce(s, dtype=np.uint64)) if len(s) else 0
+
+
+def unpack_bases(words, start, n):
+    idx = np.arange(start, start + n, dtype=np.uint64)
+    return ((words[(idx >> np.uint64(5)).astype(np.int64)] >> (np.uint64(62) - np.uint64(2) * (idx & np.uint64(31)))) & np.uint64(3)).astype(np.uint8)
+
+
+def fnv_nodes(g):
+    """FNV-1a-64 over, per node in order: one byte per base, then exts, data lo, data hi."""
+    parts = []
+    for i in range(g["n_nodes"]):
+        parts.append(unpack_bases(g["words"], int(g["start"][i]), int(g["length"][i])))
+        d = int(g["data"][i])
+        parts.append(np.array([g["exts"][i], d & 0xff, d >> 8], dtype=np.uint8))
+    buf = np.concatenate(parts).tobytes() if parts else b""
+    h = 0xcbf29ce484222325
+    for b in buf:
+        h = ((h ^ b) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return h

@@ -1,0 +1,664 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
+//
+// CPU restatement (C++17, single thread unless told otherwise) of the read -> unitig hot path of
+// 10XGenomics/rust-debruijn (crate `debruijn` 0.3.4).  Every function cites the reference
+// file:line it follows (paths relative to /root/reference/).  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load this library.
+//
+// PARITY STATUS: "parity unpinned" against the real crate for node ORDER / STRAND / cycle
+// break-point: those are decided by boomphf 0.6.x (un-vendored, un-pinned third-party MPHF) slot
+// order (src/compression.rs:574-580) and the reference's tests never pin them
+// (src/test.rs:388-413 compare k-mer sets).  The crate cannot be built here (no rustc/cargo).
+// What IS pinned: the arithmetic (KATs from src/kmer.rs:14-34, src/dna_string.rs:937-951,
+// 1061-1068, src/lib.rs Exts), the filter_kmers output before the MPHF permutation (fully
+// determined by src/filter.rs:205-219: ascending, unique), and the model-derived anchors of
+// SURVEY.md Appendix B (an independent second restatement).  Seed order used here: ascending
+// canonical k-mer (= order of valid_kmers before BoomHashMap2::new permutes them).
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <thread>
+#include <vector>
+
+typedef unsigned __int128 u128;
+
+// ---------------------------------------------------------------------------------------------
+// k-mer arithmetic — src/kmer.rs
+// ---------------------------------------------------------------------------------------------
+// reverse_by_twos: src/kmer.rs:140-159 (u64), :104-132 (u128)
+static inline uint64_t rev2(uint64_t x) {
+    x = ((x & 0x3333333333333333ull) << 2) | ((x >> 2) & 0x3333333333333333ull);
+    x = ((x & 0x0F0F0F0F0F0F0F0Full) << 4) | ((x >> 4) & 0x0F0F0F0F0F0F0F0Full);
+    x = ((x & 0x00FF00FF00FF00FFull) << 8) | ((x >> 8) & 0x00FF00FF00FF00FFull);
+    x = ((x & 0x0000FFFF0000FFFFull) << 16) | ((x >> 16) & 0x0000FFFF0000FFFFull);
+    x = ((x & 0x00000000FFFFFFFFull) << 32) | ((x >> 32) & 0x00000000FFFFFFFFull);
+    return x;
+}
+static inline u128 rev2(u128 x) {
+    uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+    return ((u128)rev2(lo) << 64) | (u128)rev2(hi);
+}
+
+template <typename T>
+struct KOps {
+    int k;
+    T mask;  // low 2k bits
+    explicit KOps(int k_) : k(k_) {
+        int tb = (int)sizeof(T) * 8;
+        mask = (2 * k == tb) ? ~(T)0 : ((((T)1) << (2 * k)) - 1);
+    }
+    // VarIntKmer::rc src/kmer.rs:620-634; IntKmer::rc :346-352
+    T rc(T x) const {
+        T r = ~rev2(x);
+        int half = (int)sizeof(T) * 4;
+        if (k < half) r >>= 2 * (half - k);
+        return r;
+    }
+    // extend_right src/kmer.rs:479-487 (mask unused top bits, set last base)
+    T ext_right(T x, uint8_t v) const { return ((x << 2) & mask) | (T)v; }
+    // extend_left src/kmer.rs:469-477
+    T ext_left(T x, uint8_t v) const { return (x >> 2) | ((T)v << (2 * (k - 1))); }
+    // get src/kmer.rs:574-577, bit address :515-518
+    uint8_t get(T x, int pos) const { return (uint8_t)((x >> (2 * (k - 1 - pos))) & 3); }
+    // min_rc_flip src/lib.rs:224-231 — equality goes to the flipped branch
+    T min_rc_flip(T x, bool& flip) const {
+        T r = rc(x);
+        if (x < r) { flip = false; return x; }
+        flip = true;
+        return r;
+    }
+    // is_palindrome src/lib.rs:244-246
+    bool is_pal(T x) const { return (k % 2 == 0) && x == rc(x); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Exts — src/lib.rs:577-749
+// ---------------------------------------------------------------------------------------------
+static inline uint8_t exts_complement(uint8_t v) {  // lib.rs:729-738
+    uint8_t r = (uint8_t)(((v & 0x55) << 1) | ((v >> 1) & 0x55));
+    r = (uint8_t)(((r & 0x33) << 2) | ((r >> 2) & 0x33));
+    return r;
+}
+static inline uint8_t exts_reverse(uint8_t v) { return (uint8_t)(((v & 0xf) << 4) | (v >> 4)); }  // :740-744
+static inline uint8_t exts_rc(uint8_t v) { return exts_complement(exts_reverse(v)); }            // :746-748
+static inline uint8_t exts_dir_bits(uint8_t v, int dir) { return dir ? (v >> 4) : (v & 0xf); }    // :621-626
+static inline int exts_num_dir(uint8_t v, int dir) {                                              // :687-690
+    uint8_t e = exts_dir_bits(v, dir);
+    return (e & 1) + ((e & 2) >> 1) + ((e & 4) >> 2) + ((e & 8) >> 3);
+}
+static inline int exts_unique(uint8_t v, int dir) {  // :704-717
+    uint8_t e = exts_dir_bits(v, dir);
+    for (int i = 0; i < 4; i++)
+        if (e & (1 << i)) return i;
+    return -1;
+}
+// single_dir :719-726 (Right => val>>4 ; Left => val & 0xf)
+static inline uint8_t exts_single_dir(uint8_t v, int dir) { return dir ? (v >> 4) : (v & 0xf); }
+
+enum { LEFT = 0, RIGHT = 1 };
+
+// ---------------------------------------------------------------------------------------------
+// DnaString layout — src/dna_string.rs:383-399 (32 bases / u64, first base in bits 63..62)
+// ---------------------------------------------------------------------------------------------
+static inline uint8_t dna_get(const uint64_t* w, uint64_t i) { return (uint8_t)((w[i >> 5] >> (62 - 2 * (i & 31))) & 3); }
+struct DnaStr {  // DnaString::push src/dna_string.rs:303-310
+    std::vector<uint64_t> storage;
+    uint64_t len = 0;
+    void push(uint8_t v) {
+        uint64_t blk = len >> 5;
+        int bit = (int)(2 * (len & 31));
+        if (bit == 0 && blk >= storage.size()) storage.push_back(0);
+        uint64_t m = 3ull << (62 - bit);
+        storage[blk] = (storage[blk] & ~m) | ((uint64_t)(v & 3) << (62 - bit));
+        len++;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// filter_kmers + CountFilter — src/filter.rs:18-23, 52-63, 138-231 ; KmerExtsIter src/lib.rs:812-841
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Obs {
+    T key;
+    uint8_t exts;
+};
+
+template <typename T>
+struct FilterOut {
+    std::vector<T> kmers;
+    std::vector<uint8_t> exts;
+    std::vector<uint16_t> counts;
+    std::vector<T> all_kmers;
+    uint64_t n_input = 0;
+    int passes = 0;
+};
+
+template <typename T>
+static void extract_range(const KOps<T>& K, const uint64_t* words, const uint64_t* start, const uint32_t* length,
+                          const uint8_t* seq_exts, uint64_t s0, uint64_t s1, bool stranded, int b_lo, int b_hi,
+                          std::vector<std::vector<Obs<T>>>& buckets) {
+    const int k = K.k;
+    for (uint64_t s = s0; s < s1; s++) {
+        uint64_t len = length[s], st = start[s];
+        if (len < (uint64_t)k) continue;  // lib.rs:783,813 : shorter => nothing
+        uint8_t sx = seq_exts ? seq_exts[s] : 0;
+        T kmer = 0;
+        for (int i = 0; i < k; i++) kmer = K.ext_right(kmer, dna_get(words, st + i));  // first_kmer lib.rs:409-411
+        for (uint64_t pos = k; pos <= len; pos++) {                                    // lib.rs:813
+            uint8_t next_base = pos < len ? dna_get(words, st + pos) : 0;              // :814-818
+            uint8_t left = (pos == (uint64_t)k) ? sx : (uint8_t)(1u << dna_get(words, st + pos - k - 1));  // :820-824
+            uint8_t right = (pos < len) ? (uint8_t)(1u << (4 + next_base)) : sx;       // :826-830
+            uint8_t e = (uint8_t)((left & 0x0f) | (right & 0xf0));                     // merge :597-601
+            T mk = kmer;
+            uint8_t me = e;
+            if (!stranded) {  // filter.rs:190-196
+                bool flip;
+                mk = K.min_rc_flip(kmer, flip);
+                if (flip) me = exts_rc(e);
+            }
+            // bucket(): first 4 bases — filter.rs:18-23
+            int b = (K.get(mk, 0) << 6) | (K.get(mk, 1) << 4) | (K.get(mk, 2) << 2) | K.get(mk, 3);
+            if (b >= b_lo && b < b_hi) buckets[b].push_back({mk, me});  // :199-201
+            kmer = K.ext_right(kmer, next_base);                        // lib.rs:835
+        }
+    }
+}
+
+template <typename T>
+static FilterOut<T> filter_kmers(int k, const uint64_t* words, const uint64_t* start, const uint32_t* length,
+                                 const uint8_t* seq_exts, uint64_t n_seqs, uint32_t min_obs, bool stranded,
+                                 bool report_all, uint64_t memory_gb, int threads) {
+    KOps<T> K(k);
+    FilterOut<T> out;
+    // pass planning — filter.rs:151-168.  size_of::<(K,D1)>() with D1 = u8: 16 B (u64) / 32 B (u128).
+    uint64_t input_kmers = 0;
+    for (uint64_t s = 0; s < n_seqs; s++) input_kmers += length[s] >= (uint32_t)(k - 1) ? length[s] - (k - 1) : 0;
+    out.n_input = input_kmers;
+    uint64_t kmer_mem = input_kmers * (sizeof(T) == 8 ? 16 : 32);
+    uint64_t max_mem = (memory_gb ? memory_gb : 1) * 1000000000ull;
+    uint64_t slices = kmer_mem / max_mem + 1;
+    int sz = (int)(256 / slices + 1);
+    if (threads < 1) threads = 1;
+    for (int b0 = 0; b0 < 256; b0 += sz) {
+        out.passes++;
+        int b1 = b0 + sz;
+        std::vector<std::vector<Obs<T>>> buckets(256);  // filter.rs:186
+        if (threads == 1) {
+            extract_range(K, words, start, length, seq_exts, 0, n_seqs, stranded, b0, b1, buckets);
+        } else {
+            // Baseline-only parallel variant: per-thread bucket sets over contiguous sequence ranges,
+            // concatenated in sequence order so the per-bucket observation order (and hence the stable
+            // sort's result) is identical to the single-thread loop.
+            std::vector<std::vector<std::vector<Obs<T>>>> tb(threads, std::vector<std::vector<Obs<T>>>(256));
+            std::vector<std::thread> th;
+            for (int t = 0; t < threads; t++)
+                th.emplace_back([&, t]() {
+                    uint64_t s0 = n_seqs * t / threads, s1 = n_seqs * (t + 1) / threads;
+                    extract_range(K, words, start, length, seq_exts, s0, s1, stranded, b0, b1, tb[t]);
+                });
+            for (auto& x : th) x.join();
+            std::vector<std::thread> th2;
+            for (int t = 0; t < threads; t++)
+                th2.emplace_back([&, t]() {
+                    for (int b = t; b < 256; b += threads)
+                        for (int u = 0; u < threads; u++)
+                            buckets[b].insert(buckets[b].end(), tb[u][b].begin(), tb[u][b].end());
+                });
+            for (auto& x : th2) x.join();
+        }
+        // per-bucket stable sort + group + CountFilter::summarize — filter.rs:205-219, 52-63
+        struct BOut {
+            std::vector<T> k, all;
+            std::vector<uint8_t> e;
+            std::vector<uint16_t> c;
+        };
+        std::vector<BOut> bo(256);
+        auto do_bucket = [&](int b) {
+            auto& v = buckets[b];
+            std::stable_sort(v.begin(), v.end(), [](const Obs<T>& a, const Obs<T>& c) { return a.key < c.key; });
+            size_t i = 0;
+            while (i < v.size()) {
+                size_t j = i;
+                uint8_t all_exts = 0;
+                uint16_t count = 0;
+                while (j < v.size() && v[j].key == v[i].key) {
+                    if (count != 65535) count++;  // saturating_add filter.rs:57
+                    all_exts |= v[j].exts;        // Exts::add :58
+                    j++;
+                }
+                if (report_all) bo[b].all.push_back(v[i].key);
+                if ((uint64_t)count >= (uint64_t)min_obs) {  // :61
+                    bo[b].k.push_back(v[i].key);
+                    bo[b].e.push_back(all_exts);
+                    bo[b].c.push_back(count);
+                }
+                i = j;
+            }
+            std::vector<Obs<T>>().swap(v);
+        };
+        if (threads == 1) {
+            for (int b = 0; b < 256; b++) do_bucket(b);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < threads; t++)
+                th.emplace_back([&, t]() {
+                    for (int b = t; b < 256; b += threads) do_bucket(b);
+                });
+            for (auto& x : th) x.join();
+        }
+        for (int b = 0; b < 256; b++) {
+            out.kmers.insert(out.kmers.end(), bo[b].k.begin(), bo[b].k.end());
+            out.exts.insert(out.exts.end(), bo[b].e.begin(), bo[b].e.end());
+            out.counts.insert(out.counts.end(), bo[b].c.begin(), bo[b].c.end());
+            out.all_kmers.insert(out.all_kmers.end(), bo[b].all.begin(), bo[b].all.end());
+        }
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// compress_kmers (CompressFromHash + SimpleCompress) — src/compression.rs:355-594
+// ---------------------------------------------------------------------------------------------
+enum ReduceOp { RED_SAT_ADD = 0, RED_WRAP_ADD = 1, RED_ADD_MOD_65535 = 2, RED_MAX = 3 };
+static inline uint16_t reduce_data(int op, uint16_t a, uint16_t b) {
+    switch (op) {
+        case RED_SAT_ADD: { uint32_t s = (uint32_t)a + b; return (uint16_t)(s > 65535 ? 65535 : s); }  // test.rs:383
+        case RED_WRAP_ADD: return (uint16_t)(a + b);                                                   // test.rs:265 (release wraps)
+        case RED_ADD_MOD_65535: return (uint16_t)(((uint32_t)a + (uint32_t)b) % 65535);                // test.rs:247
+        default: return a > b ? a : b;                                                                 // test.rs:469
+    }
+}
+
+template <typename T>
+struct KeyIndex {  // stands in for BoomHashMap2::get_key_id — exact key lookup (boomphf checks key equality)
+    std::vector<T> keys;
+    std::vector<uint32_t> ids;
+    uint64_t msk;
+    static uint64_t mix(T x) {
+        uint64_t h = (uint64_t)x;
+        if (sizeof(T) == 16) h ^= (uint64_t)((u128)x >> 64) * 0xC2B2AE3D27D4EB4Full;
+        h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+        return h;
+    }
+    void build(const T* k, uint64_t n) {
+        uint64_t cap = 16;
+        while (cap < 2 * n + 1) cap <<= 1;
+        msk = cap - 1;
+        keys.assign(cap, 0);
+        ids.assign(cap, 0xffffffffu);
+        for (uint64_t i = 0; i < n; i++) {
+            uint64_t s = mix(k[i]) & msk;
+            while (ids[s] != 0xffffffffu) s = (s + 1) & msk;
+            keys[s] = k[i];
+            ids[s] = (uint32_t)i;
+        }
+    }
+    int64_t find(T k) const {
+        uint64_t s = mix(k) & msk;
+        while (ids[s] != 0xffffffffu) {
+            if (keys[s] == k) return ids[s];
+            s = (s + 1) & msk;
+        }
+        return -1;
+    }
+};
+
+struct GraphOut {
+    DnaStr seq;
+    std::vector<uint64_t> start;
+    std::vector<uint32_t> length;
+    std::vector<uint8_t> exts;
+    std::vector<uint16_t> data;
+    int error = 0;  // 1 = "unreachable" inconsistent exts (compression.rs:428-434), 2 = missing k-mer
+};
+
+template <typename T>
+struct Compressor {
+    KOps<T> K;
+    bool stranded;
+    int op;
+    const T* kmers;
+    const uint8_t* exts;
+    const uint16_t* data;
+    uint64_t n;
+    KeyIndex<T> index;
+    std::vector<uint8_t> avail;
+    int error = 0;
+    struct Step { T kmer; int dir; };
+
+    Compressor(int k, bool s, int o, const T* km, const uint8_t* e, const uint16_t* d, uint64_t n_)
+        : K(k), stranded(s), op(o), kmers(km), exts(e), data(d), n(n_) {
+        index.build(km, n_);
+        avail.assign(n_, 1);
+    }
+    // try_extend_kmer — compression.rs:382-444.  Returns true for Unique (sets next,next_dir),
+    // false for Terminal (sets term).
+    bool try_extend(T kmer, int dir, T& next, int& next_dir, uint8_t& term) {
+        int64_t id = index.find(kmer);
+        if (id < 0) { error = 2; term = 0; return false; }  // get_kmer_data panic :369
+        uint8_t e = exts[id];
+        if (exts_num_dir(e, dir) != 1 || (!stranded && K.is_pal(kmer))) {  // :386
+            term = exts_single_dir(e, dir);
+            return false;
+        }
+        int base = exts_unique(e, dir);                                          // :390
+        T nk = dir == LEFT ? K.ext_left(kmer, (uint8_t)base) : K.ext_right(kmer, (uint8_t)base);  // :392
+        bool flip = false;
+        if (!stranded) nk = K.min_rc_flip(nk, flip);                             // :396-400
+        int nd = flip ? (dir ^ 1) : dir;                                         // :402
+        bool pal = !stranded && K.is_pal(nk);                                    // :403
+        int64_t nid = index.find(nk);                                            // :410
+        if (nid < 0 || !avail[nid]) { term = exts_single_dir(e, dir); return false; }  // :411-415
+        int incoming = flip ? dir : (dir ^ 1);                                   // dir.flip().cond_flip(flip) :419
+        uint8_t ne = exts[nid];
+        int incoming_count = exts_num_dir(ne, incoming);                         // :422
+        if (incoming_count == 0 && !pal) {                                       // :428-434 panic!("unreachable")
+            error = 1;
+            term = exts_single_dir(e, dir);
+            return false;
+        } else if (incoming_count == 1 && !pal) {  // join_test == true for SimpleCompress (:62-64)
+            next = nk;
+            next_dir = nd;
+            return true;
+        }
+        term = exts_single_dir(e, dir);  // :441
+        return false;
+    }
+    // extend_kmer — compression.rs:450-479
+    uint8_t extend(T kmer, int start_dir, std::vector<Step>& path) {
+        int cur_dir = start_dir;
+        T cur = kmer;
+        path.clear();
+        int64_t id = index.find(kmer);
+        avail[id] = 0;  // :457-458
+        for (;;) {
+            T nk = 0;
+            int nd = 0;
+            uint8_t term = 0;
+            if (try_extend(cur, cur_dir, nk, nd, term)) {
+                path.push_back({nk, nd});
+                avail[index.find(nk)] = 0;  // :466-467
+                cur = nk;
+                cur_dir = nd;
+            } else {
+                return term;
+            }
+            if (error) return 0;
+        }
+    }
+    // build_node — compression.rs:483-541
+    void build_node(uint64_t seed_id, std::vector<Step>& path, std::deque<uint8_t>& edge, uint8_t& node_exts,
+                    uint16_t& node_data) {
+        T seed = kmers[seed_id];
+        edge.clear();
+        for (int i = 0; i < K.k; i++) edge.push_back(K.get(seed, i));  // :491-493
+        node_data = data[seed_id];                                      // :495
+        uint8_t l_ext = extend(seed, LEFT, path);                       // :497
+        for (auto& st : path) {                                         // :500-511
+            T km = st.dir == LEFT ? st.kmer : K.rc(st.kmer);
+            edge.push_front(K.get(km, 0));
+            node_data = reduce_data(op, node_data, data[index.find(st.kmer)]);
+        }
+        uint8_t left_extend = l_ext;  // :513-517
+        if (!path.empty() && path.back().dir == RIGHT) left_extend = exts_complement(l_ext);
+        uint8_t r_ext = extend(seed, RIGHT, path);  // :519
+        for (auto& st : path) {                     // :522-532
+            T km = st.dir == LEFT ? K.rc(st.kmer) : st.kmer;
+            edge.push_back(K.get(km, K.k - 1));
+            node_data = reduce_data(op, node_data, data[index.find(st.kmer)]);
+        }
+        uint8_t right_extend = r_ext;  // :534-538
+        if (!path.empty() && path.back().dir == LEFT) right_extend = exts_complement(r_ext);
+        node_exts = (uint8_t)((right_extend << 4) | (left_extend & 0xf));  // from_single_dirs lib.rs:591-595
+    }
+    // compress_kmers — compression.rs:545-583.  seed_order == nullptr => slot order = input order.
+    void run(const uint32_t* seed_order, GraphOut& g) {
+        std::vector<Step> path;
+        std::deque<uint8_t> edge;
+        for (uint64_t c = 0; c < n; c++) {
+            uint64_t id = seed_order ? seed_order[c] : c;
+            if (!avail[id]) continue;  // :575
+            uint8_t ne;
+            uint16_t nd;
+            build_node(id, path, edge, ne, nd);
+            if (error) { g.error = error; return; }
+            // BaseGraph::add graph.rs:104-113 ; PackedDnaStringSet::add dna_string.rs:811-821
+            g.start.push_back(g.seq.len);
+            for (uint8_t b : edge) g.seq.push(b);
+            g.length.push_back((uint32_t)edge.size());
+            g.exts.push_back(ne);
+            g.data.push_back(nd);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// MSP — src/msp.rs:115-157, 207-324 ; Exts::from_slice_bounds src/lib.rs:645-660
+// ---------------------------------------------------------------------------------------------
+struct MspIv {
+    uint32_t start, len, min_pos;
+    uint64_t minimizer;  // p-mer value as found in the sequence (not canonicalised)
+    uint64_t bucket;     // min_rc(minimizer).to_u64()  msp.rs:115-117
+    uint8_t exts;        // from_slice_bounds
+};
+
+struct MspScanner {
+    const uint8_t* seq;
+    uint32_t m;
+    int k, p;
+    const uint64_t* perm;  // nullptr => identity (msp.rs:298-301)
+    bool rc;
+    KOps<uint64_t> P;
+    struct MinPos { uint64_t val; uint32_t pos; uint64_t kmer; };
+    MspScanner(const uint8_t* s, uint32_t m_, int k_, int p_, const uint64_t* perm_, bool rc_)
+        : seq(s), m(m_), k(k_), p(p_), perm(perm_), rc(rc_), P(p_) {}
+    uint64_t score(uint64_t pm) const {  // msp.rs:305-311
+        uint64_t a = perm ? perm[pm] : pm;
+        if (!rc) return a;
+        uint64_t r = P.rc(pm);
+        uint64_t b = perm ? perm[r] : r;
+        return a < b ? a : b;
+    }
+    MinPos mp(uint32_t pos) const {  // :194-198
+        uint64_t km = 0;
+        for (int i = 0; i < p; i++) km = P.ext_right(km, seq[pos + i]);
+        return {score(km), pos, km};
+    }
+    MinPos incr(const MinPos& a) const {  // :200-205
+        uint32_t pos = a.pos + 1;
+        uint64_t km = P.ext_right(a.kmer, seq[pos + p - 1]);
+        return {score(km), pos, km};
+    }
+    // MinPos::cmp :127-140 — smaller val wins; on ties the LARGER position is "less"
+    static bool less(const MinPos& a, const MinPos& b) {
+        if (a.val != b.val) return a.val < b.val;
+        return a.pos > b.pos;
+    }
+    MinPos find_min(uint32_t start, uint32_t stop) const {  // :218-228  (std::cmp::min returns first arg on Equal)
+        MinPos mn = mp(start), cur = mn;
+        while (cur.pos < stop) {
+            cur = incr(cur);
+            if (less(cur, mn)) mn = cur;
+        }
+        return mn;
+    }
+    std::vector<MspIv> scan() const {  // :207-276
+        std::vector<std::pair<uint32_t, MinPos>> mps;
+        MinPos min_pos = find_min(0, k - p);
+        MinPos end_pos = mp(k - p);
+        mps.push_back({0, min_pos});
+        for (uint32_t i = 1; i < m - k + 1; i++) {
+            end_pos = incr(end_pos);
+            if (i > min_pos.pos) {
+                min_pos = find_min(i, i + k - p);
+                mps.push_back({i, min_pos});
+            } else if (end_pos.val < min_pos.val) {
+                min_pos = end_pos;
+                mps.push_back({i, min_pos});
+            }
+        }
+        std::vector<MspIv> out;
+        for (size_t q = 0; q < mps.size(); q++) {
+            uint32_t st = mps[q].first;
+            uint32_t len = (q + 1 < mps.size()) ? (mps[q + 1].first + k - 1 - st) : (m - st);
+            uint64_t mz = mps[q].second.kmer;
+            uint64_t r = P.rc(mz);
+            uint8_t l = st > 0 ? (uint8_t)(1u << seq[st - 1]) : 0;                 // lib.rs:646-650
+            uint8_t rr = (st + len < m) ? (uint8_t)(1u << seq[st + len]) : 0;      // :651-655
+            out.push_back({st, len, mps[q].second.pos, mz, mz < r ? mz : r, (uint8_t)((rr << 4) | l)});
+        }
+        return out;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// synth-v1 generator — SURVEY.md Appendix B
+// ---------------------------------------------------------------------------------------------
+static inline uint64_t sm64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline uint64_t rnd(uint64_t seed, uint64_t stream, uint64_t ctr) { return sm64(sm64(4 * seed + stream) + ctr); }
+
+// =============================================================================================
+// C ABI for ctypes
+// =============================================================================================
+struct OrcTable {
+    int k;
+    std::vector<uint64_t> lo, hi;  // hi empty for k <= 32
+    std::vector<uint8_t> exts;
+    std::vector<uint16_t> counts;
+    std::vector<uint64_t> all_lo, all_hi;
+    uint64_t n_input;
+    int passes;
+};
+
+extern "C" {
+
+uint64_t orc_kmer_rc(int k, uint64_t x) { return KOps<uint64_t>(k).rc(x); }
+void orc_kmer_rc128(int k, const uint64_t* in, uint64_t* out) {
+    u128 x = ((u128)in[1] << 64) | in[0];
+    u128 r = KOps<u128>(k).rc(x);
+    out[0] = (uint64_t)r;
+    out[1] = (uint64_t)(r >> 64);
+}
+uint64_t orc_kmer_extend_left(int k, uint64_t x, int v) { return KOps<uint64_t>(k).ext_left(x, (uint8_t)v); }
+uint64_t orc_kmer_extend_right(int k, uint64_t x, int v) { return KOps<uint64_t>(k).ext_right(x, (uint8_t)v); }
+int orc_exts_rc(int v) { return exts_rc((uint8_t)v); }
+int orc_exts_complement(int v) { return exts_complement((uint8_t)v); }
+
+// Pack 0..3 bases into DnaString words (DnaString::push).  words must hold ceil(n/32) u64.
+void orc_pack_bases(const uint8_t* bases, uint64_t n, uint64_t* words) {
+    DnaStr d;
+    for (uint64_t i = 0; i < n; i++) d.push(bases[i]);
+    memcpy(words, d.storage.data(), d.storage.size() * 8);
+}
+
+void* orc_filter_kmers(int k, const uint64_t* words, const uint64_t* start, const uint32_t* length,
+                       const uint8_t* seq_exts, uint64_t n_seqs, uint32_t min_obs, int stranded, int report_all,
+                       uint64_t memory_gb, int threads) {
+    OrcTable* t = new OrcTable();
+    t->k = k;
+    if (k <= 32) {
+        auto o = filter_kmers<uint64_t>(k, words, start, length, seq_exts, n_seqs, min_obs, stranded, report_all, memory_gb, threads);
+        t->lo = std::move(o.kmers);
+        t->all_lo = std::move(o.all_kmers);
+        t->exts = std::move(o.exts);
+        t->counts = std::move(o.counts);
+        t->n_input = o.n_input;
+        t->passes = o.passes;
+    } else {
+        auto o = filter_kmers<u128>(k, words, start, length, seq_exts, n_seqs, min_obs, stranded, report_all, memory_gb, threads);
+        for (u128 x : o.kmers) { t->lo.push_back((uint64_t)x); t->hi.push_back((uint64_t)(x >> 64)); }
+        for (u128 x : o.all_kmers) { t->all_lo.push_back((uint64_t)x); t->all_hi.push_back((uint64_t)(x >> 64)); }
+        t->exts = std::move(o.exts);
+        t->counts = std::move(o.counts);
+        t->n_input = o.n_input;
+        t->passes = o.passes;
+    }
+    return t;
+}
+uint64_t orc_table_len(void* h) { return ((OrcTable*)h)->lo.size(); }
+uint64_t orc_table_all_len(void* h) { return ((OrcTable*)h)->all_lo.size(); }
+uint64_t orc_table_n_input(void* h) { return ((OrcTable*)h)->n_input; }
+int orc_table_passes(void* h) { return ((OrcTable*)h)->passes; }
+void orc_table_copy(void* h, uint64_t* lo, uint64_t* hi, uint8_t* exts, uint16_t* counts, uint64_t* all_lo, uint64_t* all_hi) {
+    OrcTable* t = (OrcTable*)h;
+    if (lo) memcpy(lo, t->lo.data(), t->lo.size() * 8);
+    if (hi && !t->hi.empty()) memcpy(hi, t->hi.data(), t->hi.size() * 8);
+    if (exts) memcpy(exts, t->exts.data(), t->exts.size());
+    if (counts) memcpy(counts, t->counts.data(), t->counts.size() * 2);
+    if (all_lo) memcpy(all_lo, t->all_lo.data(), t->all_lo.size() * 8);
+    if (all_hi && !t->all_hi.empty()) memcpy(all_hi, t->all_hi.data(), t->all_hi.size() * 8);
+}
+void orc_table_free(void* h) { delete (OrcTable*)h; }
+
+// compress_kmers: kmers given as lo[] (+hi[] when k > 32), in SEED ORDER = array order unless seed_order given.
+void* orc_compress_kmers(int k, uint64_t n, const uint64_t* lo, const uint64_t* hi, const uint8_t* exts,
+                         const uint16_t* counts, int stranded, int reduce_op, const uint32_t* seed_order) {
+    GraphOut* g = new GraphOut();
+    if (k <= 32) {
+        Compressor<uint64_t> c(k, stranded, reduce_op, lo, exts, counts, n);
+        c.run(seed_order, *g);
+    } else {
+        std::vector<u128> km(n);
+        for (uint64_t i = 0; i < n; i++) km[i] = ((u128)hi[i] << 64) | lo[i];
+        Compressor<u128> c(k, stranded, reduce_op, km.data(), exts, counts, n);
+        c.run(seed_order, *g);
+    }
+    return g;
+}
+int orc_graph_error(void* h) { return ((GraphOut*)h)->error; }
+uint64_t orc_graph_n_nodes(void* h) { return ((GraphOut*)h)->start.size(); }
+uint64_t orc_graph_n_bases(void* h) { return ((GraphOut*)h)->seq.len; }
+void orc_graph_copy(void* h, uint64_t* words, uint64_t* start, uint32_t* length, uint8_t* exts, uint16_t* data) {
+    GraphOut* g = (GraphOut*)h;
+    if (words) memcpy(words, g->seq.storage.data(), g->seq.storage.size() * 8);
+    if (start) memcpy(start, g->start.data(), g->start.size() * 8);
+    if (length) memcpy(length, g->length.data(), g->length.size() * 4);
+    if (exts) memcpy(exts, g->exts.data(), g->exts.size());
+    if (data) memcpy(data, g->data.data(), g->data.size() * 2);
+}
+void orc_graph_free(void* h) { delete (GraphOut*)h; }
+
+// MSP scan of one sequence of 0..3 bases.  out arrays sized >= m-k+1.  Returns #intervals (0 if m < k).
+int64_t orc_msp_scan(int k, int p, const uint8_t* seq, uint32_t m, const uint64_t* perm, int rc, uint32_t* o_start,
+                     uint32_t* o_len, uint32_t* o_minpos, uint64_t* o_minimizer, uint64_t* o_bucket, uint8_t* o_exts) {
+    if (m < (uint32_t)k) return 0;  // msp.rs:294-296
+    MspScanner sc(seq, m, k, p, perm, rc != 0);
+    auto v = sc.scan();
+    for (size_t i = 0; i < v.size(); i++) {
+        o_start[i] = v[i].start; o_len[i] = v[i].len; o_minpos[i] = v[i].min_pos;
+        o_minimizer[i] = v[i].minimizer; o_bucket[i] = v[i].bucket; o_exts[i] = v[i].exts;
+    }
+    return (int64_t)v.size();
+}
+
+// synth-v1: genome words (G = 3R bases) and packed reads (R x 150 bases, contiguous).  SURVEY.md App. B.
+uint64_t orc_synth_genome_bases(uint64_t R) { return (150 * R + 49) / 50; }
+void orc_synth_reads(uint64_t R, uint64_t seed, uint32_t err_thr, uint64_t* read_words /* ceil(150R/32) */) {
+    uint64_t G = orc_synth_genome_bases(R);
+    uint64_t gw = (G + 31) / 32;
+    std::vector<uint64_t> genome(gw);
+    for (uint64_t j = 0; j < gw; j++) genome[j] = rnd(seed, 0, j);
+    uint64_t nw = (150 * R + 31) / 32;
+    memset(read_words, 0, nw * 8);
+    for (uint64_t i = 0; i < R; i++) {
+        uint64_t st = rnd(seed, 1, i) % (G - 149);
+        uint64_t strand = rnd(seed, 2, i) >> 63;
+        for (int b = 0; b < 150; b++) {
+            uint8_t base = strand ? (uint8_t)(3 - dna_get(genome.data(), st + 149 - b)) : dna_get(genome.data(), st + b);
+            uint64_t h = rnd(seed, 3, 256 * i + b);
+            if ((h & 0xFFFFFF) < err_thr) base = (uint8_t)((base + 1 + ((h >> 24) % 3)) & 3);
+            uint64_t pos = 150 * i + b;
+            read_words[pos >> 5] |= (uint64_t)base << (62 - 2 * (pos & 31));
+        }
+    }
+}
+
+}  // extern "C"

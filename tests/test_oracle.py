@@ -1,0 +1,311 @@
+"""CPU tests pinning the oracle (oracle/oracle.cpp) before anything is compared against it.
+
+Sources of truth, in order: (1) known-answer vectors held by the reference's own tests/doctests,
+(2) the properties the reference's integration tests assert (src/test.rs P1-P6, src/msp.rs (1)-(4)),
+(3) SURVEY.md Appendix B anchors from an independent restatement."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (canon, dec, enc, kmers_of, node_bases, random_contigs, random_dna, rc_int, simple_random_contigs,
+                     small_k_contigs)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---- (1) KATs from the reference ----------------------------------------------------------------
+def test_kmer_doctest_kat(orc):
+    """src/kmer.rs:14-34 (Kmer16 doctest) + SURVEY §7.1 K31 KAT."""
+    L = orc.lib()
+    k1 = kmers_of(enc("ACGTACGTACGTACGT"), 16)[0]
+    assert L.orc_kmer_rc(16, L.orc_kmer_rc(16, k1)) == k1
+    assert L.orc_kmer_extend_left(16, k1, 3) == kmers_of(enc("TACGTACGTACGTACG"), 16)[0]
+    ks = sorted(kmers_of(enc("TACGTACGTACGTACGTT"), 16))
+    assert ks == [kmers_of(enc(s), 16)[0] for s in ("ACGTACGTACGTACGT", "CGTACGTACGTACGTT", "TACGTACGTACGTACG")]
+    s31 = ("ACGT" * 8)[:31]
+    x = kmers_of(enc(s31), 31)[0]
+    assert x == 0x06c6c6c6c6c6c6c6
+    assert L.orc_kmer_rc(31, x) == 0x1b1b1b1b1b1b1b1b == kmers_of(enc(("CGTA" * 8)[:31]), 31)[0]
+
+
+@pytest.mark.parametrize("k", [4, 5, 6, 8, 10, 12, 14, 15, 16, 20, 24, 31, 32])
+def test_kmer_ops_property(orc, k):
+    """src/kmer.rs:848-905: rc∘rc = id, rc base identity, extend_left/right."""
+    L = orc.lib()
+    rng = np.random.default_rng(k)
+    for _ in range(300):
+        b = random_dna(rng, k)
+        x = kmers_of(b, k)[0]
+        r = L.orc_kmer_rc(k, x)
+        assert r == rc_int(x, k) and L.orc_kmer_rc(k, r) == x
+        v = int(rng.integers(0, 4))
+        assert L.orc_kmer_extend_right(k, x, v) == kmers_of(np.append(b[1:], v), k)[0]
+        assert L.orc_kmer_extend_left(k, x, v) == kmers_of(np.insert(b[:-1], 0, v), k)[0]
+
+
+@pytest.mark.parametrize("k", [33, 40, 48, 63, 64])
+def test_kmer_rc128(orc, k):
+    import ctypes as C
+    L = orc.lib()
+    rng = np.random.default_rng(k)
+    for _ in range(100):
+        x = kmers_of(random_dna(rng, k), k)[0]
+        i = np.array([x & (2**64 - 1), x >> 64], dtype=np.uint64)
+        o = np.zeros(2, dtype=np.uint64)
+        L.orc_kmer_rc128(k, i.ctypes.data_as(C.POINTER(C.c_uint64)), o.ctypes.data_as(C.POINTER(C.c_uint64)))
+        assert (int(o[1]) << 64) | int(o[0]) == rc_int(x, k)
+
+
+def test_exts_kat(orc):
+    """src/lib.rs:729-748; SURVEY §7.1: Exts(0x12).rc() == 0x48."""
+    L = orc.lib()
+    assert L.orc_exts_rc(0x12) == 0x48
+    for v in range(256):
+        assert L.orc_exts_rc(L.orc_exts_rc(v)) == v
+        c = L.orc_exts_complement(v)
+        # complement reverses the 4 bits inside each nibble (A<->T, C<->G)
+        for nib in (0, 4):
+            for i in range(4):
+                assert ((v >> (nib + i)) & 1) == ((c >> (nib + 3 - i)) & 1)
+
+
+def test_dna_string_layout_kat(orc):
+    """Bases of src/dna_string.rs:937-951 test_push_bytes ([2,0,0,0,0,1,1,0]) in the storage layout
+    of :383-399: first base in bits 63..62 of word 0 => top 16 bits 10000000 00010100."""
+    w = orc.pack_bases(np.array([2, 0, 0, 0, 0, 1, 1, 0], dtype=np.uint8))
+    assert int(w[0]) >> 48 == 0x8014
+    b = np.arange(70, dtype=np.uint8) % 4
+    w = orc.pack_bases(b)
+    assert len(w) == 3 and np.array_equal(orc.unpack_bases(w, 0, 70), b)
+
+
+DNA142 = ("TGCATTAGAAAACTCCTTGCCTGTCAGCCCGACAGGTAGAAACTCATTAATCCACACATTGA"
+          "CTCTATTTCAGGTAAATATGACGTCAACTCCTGCATGTTGAAGGCAGTGAGTGGCTGAAACAGCATCAAGGCGTGAAGGC")
+
+
+def test_kmers_142(orc):
+    """src/dna_string.rs:1061-1068 test_kmers string; model-derived check from SURVEY App. B:
+    K=31, min_obs 1, unstranded => V=112, one node == input, exts 0, data 112."""
+    w, s, l = orc.seqset_from_lists([enc(DNA142)])
+    t = orc.filter_kmers(31, w, s, l, min_obs=1)
+    assert len(t["lo"]) == 112
+    assert int(t["lo"][0]) == 0x001d7e5ed25612b2 and int(t["exts"][0]) == 0x14
+    assert set(int(x) for x in t["lo"]) == set(canon(x, 31) for x in kmers_of(enc(DNA142), 31))
+    g = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], t["counts"])
+    assert g["n_nodes"] == 1 and dec(node_bases(orc, g, 0)) == DNA142
+    assert int(g["exts"][0]) == 0 and int(g["data"][0]) == 112
+
+
+def test_degen_seq_asm(orc):
+    """src/test.rs:169-180 input; expected output per SURVEY App. B model."""
+    ctg = enc("AAAAATAAAATAAAATAAAATAAAATAAAATAAAATAAAATAAAA")
+    w, s, l = orc.seqset_from_lists([ctg, ctg])
+    t = orc.filter_kmers(31, w, s, l, min_obs=2)
+    assert len(t["lo"]) == 6
+    g = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], t["counts"])
+    assert g["n_nodes"] == 2
+    assert dec(node_bases(orc, g, 0)) == "AAAAATAAAATAAAATAAAATAAAATAAAAT" and g["exts"][0] == 0x10 and g["data"][0] == 2
+    assert dec(node_bases(orc, g, 1)) == "AAAATAAAATAAAATAAAATAAAATAAAATAAAAT" and g["exts"][1] == 0x19 and g["data"][1] == 28
+
+
+# ---- (3) anchors --------------------------------------------------------------------------------
+with open(os.path.join(HERE, "golden", "anchors.json")) as f:
+    ANCHORS = json.load(f)["rows"]
+
+
+@pytest.mark.parametrize("row", ANCHORS, ids=lambda r: f"R{r[0]}-k{r[1]}-{'s' if r[2] else 'u'}-{'noisy' if r[3] else 'clean'}")
+def test_anchor(orc, row):
+    R, k, stranded, noisy, mo, N, U, V, M, Lb, mx, xv, mv, fn = row
+    w, s, l = orc.synth_reads(R, 1, orc.ERR_THR_NOISY if noisy else 0)
+    t = orc.filter_kmers(k, w, s, l, min_obs=mo, stranded=stranded, report_all=True)
+    assert (t["n_input"], len(t["all_lo"]), len(t["lo"])) == (N, U, V)
+    assert orc.xor_valid(t) == int(xv, 16) and orc.mix_valid(t) == int(mv, 16)
+    g = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], stranded=stranded)
+    assert g["error"] == 0
+    assert (g["n_nodes"], g["n_bases"], int(g["length"].max())) == (M, Lb, mx)
+    assert orc.fnv_nodes(g) == int(fn, 16)
+
+
+def test_first_bases(orc):
+    assert dec(orc.unpack_bases(orc.synth_reads(1000)[0], 0, 20)) == "GGTTCAGGTAACCTTCATTA"
+    assert dec(orc.unpack_bases(orc.synth_reads(10000)[0], 0, 20)) == "TTAAGGCGCTAATTGATTCC"
+
+
+# ---- (2) properties of the reference's integration tests ---------------------------------------
+def _check_graph_props(orc, k, contigs, t, g, stranded=False):
+    """P1, P3, P4 of src/test.rs:351-355, 388-413."""
+    cf = (lambda x: x) if stranded else (lambda x: canon(x, k))
+    kmer_set = set(cf(x) for c in contigs for x in kmers_of(c, k))
+    assert set(int(x) for x in t["lo"]) == kmer_set                              # P1
+    allc = set()
+    for i in range(g["n_nodes"]):
+        b = node_bases(orc, g, i)
+        ks = kmers_of(b, k)
+        cs = set(cf(x) for x in ks)
+        assert cs <= kmer_set and len(cs) == len(ks)
+        assert not (cs & allc)
+        allc |= cs
+        e = int(g["exts"][i])
+        mask = (1 << (2 * k)) - 1
+        for base in range(4):                                                     # P4
+            if e & (1 << base):
+                assert cf((ks[0] >> 2) | (base << (2 * (k - 1)))) in kmer_set
+            if e & (1 << (4 + base)):
+                assert cf(((ks[-1] << 2) & mask) | base) in kmer_set
+    assert allc == kmer_set                                                       # P3
+
+
+@pytest.mark.parametrize("k", [31, 32])
+def test_reassemble_contigs(orc, k):
+    """src/test.rs:299-414 (unsharded variant: whole contigs, each given twice, CountFilter(2))."""
+    rng = np.random.default_rng(100 + k)
+    for it in range(6):
+        contigs = simple_random_contigs(rng) if it == 0 else random_contigs(rng)
+        contigs = [c for c in contigs if len(c) >= k]
+        w, s, l = orc.seqset_from_lists(contigs + contigs)
+        t = orc.filter_kmers(k, w, s, l, min_obs=2)
+        g = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], reduce_op=orc.SAT_ADD)
+        assert g["error"] == 0
+        _check_graph_props(orc, k, contigs, t, g)
+        # P2: every k-mer reachable via Exts, none invented (test.rs:357-381)
+        kmer_set = set(int(x) for x in t["lo"])
+        ext_set = set()
+        mask = (1 << (2 * k)) - 1
+        for x, e in zip(t["lo"], t["exts"]):
+            x, e = int(x), int(e)
+            for base in range(4):
+                if e & (1 << base):
+                    ext_set.add(canon((x >> 2) | (base << (2 * (k - 1))), k))
+                if e & (1 << (4 + base)):
+                    ext_set.add(canon(((x << 2) & mask) | base, k))
+        assert ext_set <= kmer_set
+        # memory_size only changes the number of passes (filter.rs:151-168)
+        t1 = orc.filter_kmers(k, w, s, l, min_obs=2, memory_gb=1)
+        assert np.array_equal(t1["lo"], t["lo"]) and np.array_equal(t1["exts"], t["exts"])
+
+
+@pytest.mark.parametrize("k,stranded", [(4, False), (5, False), (6, False), (7, False), (5, True), (6, True)])
+def test_small_k_cycles_palindromes(orc, k, stranded):
+    rng = np.random.default_rng(k * 7 + stranded)
+    for it in range(60):
+        contigs = small_k_contigs(rng, alphabet=2 if it % 3 == 0 else 4)
+        contigs = [c for c in contigs if len(c) >= k]
+        if not contigs:
+            continue
+        w, s, l = orc.seqset_from_lists(contigs)
+        t = orc.filter_kmers(k, w, s, l, min_obs=1, stranded=stranded)
+        g = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], stranded=stranded)
+        assert g["error"] == 0
+        _check_graph_props(orc, k, contigs, t, g, stranded)
+
+
+def test_seed_order_changes_only_strand_and_cycle_breaks(orc):
+    """canonical form of the graph is invariant to seed (boomphf slot) order for
+    non-cyclic components."""
+    rng = np.random.default_rng(5)
+    k = 31
+    contigs = [c for c in random_contigs(rng) if len(c) >= k]
+    w, s, l = orc.seqset_from_lists(contigs)
+    t = orc.filter_kmers(k, w, s, l, min_obs=1)
+    g0 = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"])
+
+    def canon_form(g):
+        out = []
+        L = orc.lib()
+        for i in range(g["n_nodes"]):
+            b = node_bases(orc, g, i)
+            r = (3 - b[::-1]).astype(np.uint8)
+            e = int(g["exts"][i])
+            if bytes(r) < bytes(b):
+                b, e = r, L.orc_exts_rc(e)
+            out.append((bytes(b), e, int(g["data"][i])))
+        return sorted(out)
+
+    perm = rng.permutation(len(t["lo"])).astype(np.uint32)
+    g1 = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], seed_order=perm)
+    assert canon_form(g0) == canon_form(g1)
+
+
+def test_threads_variant_identical(orc):
+    w, s, l = orc.synth_reads(2000, 1, orc.ERR_THR_NOISY)
+    a = orc.filter_kmers(31, w, s, l, min_obs=2, report_all=True)
+    b = orc.filter_kmers(31, w, s, l, min_obs=2, report_all=True, threads=4)
+    for f in ("lo", "exts", "counts", "all_lo"):
+        assert np.array_equal(a[f], b[f])
+
+
+def test_edge_cases(orc):
+    """Empty input, reads shorter than K (lib.rs:783,813), min_obs=0, sequence-level exts (lib.rs:820-830)."""
+    e = np.zeros(0, np.uint64)
+    t = orc.filter_kmers(31, e, e, np.zeros(0, np.uint32))
+    assert len(t["lo"]) == 0
+    g = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], t["counts"])
+    assert g["n_nodes"] == 0 and g["n_bases"] == 0
+    w, s, l = orc.seqset_from_lists([enc("ACGT"), enc("A" * 30)])
+    assert len(orc.filter_kmers(31, w, s, l)["lo"]) == 0
+    # a length-K sequence takes both nibbles of seq_exts verbatim
+    seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")
+    w, s, l = orc.seqset_from_lists([seq])
+    t = orc.filter_kmers(31, w, s, l, seq_exts=np.array([0x5a], np.uint8), stranded=True)
+    assert len(t["lo"]) == 1 and int(t["exts"][0]) == 0x5a
+    t = orc.filter_kmers(31, w, s, l, seq_exts=np.array([0x5a], np.uint8), min_obs=0)
+    x = kmers_of(seq, 31)[0]
+    assert int(t["lo"][0]) == canon(x, 31)
+    assert int(t["exts"][0]) == (0x5a if x < rc_int(x, 31) else orc.lib().orc_exts_rc(0x5a))
+
+
+def test_count_saturation(orc):
+    """filter.rs:57: counts saturate at 65535."""
+    seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")
+    w, s, l = orc.seqset_from_lists([seq] * 70000)
+    t = orc.filter_kmers(31, w, s, l, min_obs=1)
+    assert len(t["lo"]) == 1 and int(t["counts"][0]) == 65535
+
+
+# ---- MSP properties — src/msp.rs:404-485 --------------------------------------------------------
+@pytest.mark.parametrize("k,p", [(16, 5), (31, 6), (31, 8), (35, 5), (50, 8), (63, 12)])
+def test_msp_scanner_properties(orc, k, p):
+    rng = np.random.default_rng(k * 100 + p)
+    for it in range(30):
+        m = int(rng.integers(k, 6 * k))
+        seq = random_dna(rng, m) if it % 5 else np.zeros(m, np.uint8)  # incl. DnaString::blank (msp.rs:517-528)
+        iv = orc.msp_scan(k, p, seq, rc=False)  # score = p.to_u64() as in test_new_slicer (msp.rs:494)
+        pm = kmers_of(seq, p)
+        covered = np.zeros(m - k + 1, bool)
+        for st, ln, mp, mz in zip(iv["start"], iv["len"], iv["minpos"], iv["minimizer"]):
+            st, ln, mp, mz = int(st), int(ln), int(mp), int(mz)
+            assert not covered[st:st + ln - k + 1].any()
+            covered[st:st + ln - k + 1] = True                      # (1)
+            assert p <= ln <= 2 * k - p                              # (2)
+            assert pm[mp] == mz and st <= mp <= st + ln - p          # (3)
+            assert min(pm[st:st + ln - p + 1]) >= mz
+        assert covered.all()
+        for i in range(len(iv["start"]) - 1):                        # (4) right-maximal
+            st, ln, mp, mz = (int(iv[f][i]) for f in ("start", "len", "minpos", "minimizer"))
+            nk = st + ln - k + 1
+            assert pm[st + ln - p + 1] < mz or not (nk <= mp)
+
+
+def test_msp_sharded_filter_equals_unsharded(orc):
+    """The reference's own sharded flow (src/test.rs:433-456): per-bucket filter_kmers over MSP
+    substrings with from_slice_bounds exts reproduces the unsharded (k-mer, exts, count) set."""
+    rng = np.random.default_rng(9)
+    k, p = 31, 6
+    contigs = [c for c in random_contigs(rng) if len(c) >= k]
+    w, s, l = orc.seqset_from_lists(contigs)
+    ref = orc.filter_kmers(k, w, s, l, min_obs=1)
+    shards = {}
+    for c in contigs:
+        iv = orc.msp_scan(k, p, c, rc=True)
+        for st, ln, b, e in zip(iv["start"], iv["len"], iv["bucket"], iv["exts"]):
+            shards.setdefault(int(b), []).append((c[int(st):int(st) + int(ln)], int(e)))
+    got = {}
+    for b, items in shards.items():
+        w2, s2, l2 = orc.seqset_from_lists([x[0] for x in items])
+        t = orc.filter_kmers(k, w2, s2, l2, seq_exts=np.array([x[1] for x in items], np.uint8), min_obs=1)
+        for x, e, c in zip(t["lo"], t["exts"], t["counts"]):
+            assert int(x) not in got
+            got[int(x)] = (int(e), int(c))
+    assert got == {int(x): (int(e), int(c)) for x, e, c in zip(ref["lo"], ref["exts"], ref["counts"])}
