@@ -1,0 +1,148 @@
+/* dbg_b200.h — C ABI of the B200-native read -> unitig path (libdbg_b200.so).
+ *
+ * Drop-in boundary for ONE path of the crate `debruijn` (10XGenomics/rust-debruijn 0.3.4):
+ *     filter::filter_kmers (CountFilter)  ->  compression::compress_kmers_with_hash (SimpleCompress)
+ * The reference has no FFI; the boundary is two generic Rust functions plus three public data
+ * layouts.  Every entry point below names the reference item it replaces (paths relative to the
+ * crate root).  Plain pointers and sizes only; no exceptions or unwinding cross this ABI; every call
+ * returns a dbg_status and leaves a message retrievable with dbg_last_error().
+ *
+ * Threading: calls block.  One dbg_ctx = one CUDA device + one stream; a ctx is used by one caller at
+ * a time; several ctxs (one per GPU / per process) may coexist.  There is NO CPU fallback: without a
+ * CUDA device dbg_ctx_create fails with DBG_E_CUDA.
+ *
+ * Data layouts (identical to the crate's):
+ *   sequences   PackedDnaStringSet image (src/dna_string.rs:763-767, 383-399): `words` = 2-bit bases,
+ *               32 per u64, base b of the concatenation at bits 62-2(b%32) of word b/32;
+ *               `start[i]` base offset, `length[i]` bases; `seq_exts[i]` = Exts.val of sequence i
+ *               (NULL => Exts::empty()).
+ *   k-mers      K<=32: u64, right-aligned, base 0 most significant (src/kmer.rs:429-437);
+ *               32<K<=64: {lo,hi} = Rust u128 little-endian halves.
+ *   Exts        u8, bits 0..3 left A,C,G,T, bits 4..7 right A,C,G,T (src/lib.rs:569-580).
+ *   BaseGraph   sequences (bit-contiguous, no per-node padding), start (base offset), length (u32),
+ *               exts (u8), data (u16), stranded (src/graph.rs:44-50).
+ */
+#ifndef DBG_B200_H
+#define DBG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    DBG_OK = 0,
+    DBG_E_BADARG = 1,
+    DBG_E_OOM = 2,
+    DBG_E_CUDA = 3,
+    DBG_E_INCONSISTENT_EXTS = 4, /* the reference's panic!("unreachable"), src/compression.rs:428-434 */
+    DBG_E_INTERNAL = 5
+} dbg_status;
+
+/* SimpleCompress reduce closures used by the reference's tests (src/compression.rs:40-65). */
+typedef enum {
+    DBG_REDUCE_SAT_ADD = 0,       /* |a,b| a.saturating_add(*b)              src/test.rs:383,459 */
+    DBG_REDUCE_WRAP_ADD = 1,      /* |a,b| a + b (release: wrapping)          src/test.rs:265,546 */
+    DBG_REDUCE_ADD_MOD_65535 = 2, /* |a,b| ((a as u32 + *b as u32) % 65535)   src/test.rs:247     */
+    DBG_REDUCE_MAX = 3            /* |a,b| max(a,*b)                          src/test.rs:469     */
+} dbg_reduce_op;
+
+typedef struct dbg_ctx dbg_ctx;
+typedef struct dbg_seqset dbg_seqset;      /* device-resident &[(V, Exts, D1)]            */
+typedef struct dbg_kmer_table dbg_kmer_table; /* device-resident BoomHashMap2<K,Exts,u16> (+ all_kmers) */
+typedef struct dbg_graph dbg_graph;        /* device-resident BaseGraph<K,u16>             */
+
+/* Counters and per-stage device times (ms, CUDA events) of the last filter/compress call. */
+typedef struct {
+    uint64_t n_seqs, n_input_kmers, n_records, n_buckets, n_distinct, n_valid, n_nodes, n_bases;
+    uint64_t n_bucket_splits; /* shared-memory table overflows resolved by hash-class splitting */
+    uint64_t rank_rounds;     /* pointer-doubling rounds in compress */
+    uint64_t n_cycle_kmers;   /* k-mers on cyclic unitigs */
+    uint64_t gpu_launches;    /* kernels launched by this ctx so far */
+    float ms_partition, ms_count, ms_sort, ms_table, ms_links, ms_rank, ms_emit;
+    uint32_t msp_p, bucket_bits;
+} dbg_stats;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int dbg_ctx_create(int device, dbg_ctx** out);
+void dbg_ctx_destroy(dbg_ctx* ctx);
+const char* dbg_last_error(const dbg_ctx* ctx);
+int dbg_stats_get(const dbg_ctx* ctx, dbg_stats* out);
+/* tunables: "msp_p" (minimizer length, 0 = auto), "bucket_occ" (target k-mer occurrences per MSP
+ * bucket, 0 = auto). */
+int dbg_ctx_set_param(dbg_ctx* ctx, const char* name, int64_t value);
+int dbg_ctx_synchronize(dbg_ctx* ctx);
+
+/* ---- sequences: the `seqs: &[(V, Exts, D1)]` argument of filter_kmers (src/filter.rs:139-140) ----
+ * D1 is not transported: CountFilter never reads it (src/filter.rs:56).  Host pointers are borrowed
+ * for the duration of the call only. */
+int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, const uint64_t* start,
+                      const uint32_t* length, const uint8_t* seq_exts, uint64_t n_seqs, dbg_seqset** out);
+/* Wrap caller-owned DEVICE buffers (e.g. torch tensors) without copying. */
+int dbg_seqset_wrap_device(dbg_ctx* ctx, const uint64_t* d_words, uint64_t n_words, const uint64_t* d_start,
+                           const uint32_t* d_length, const uint8_t* d_seq_exts, uint64_t n_seqs, uint32_t max_len,
+                           dbg_seqset** out);
+/* synth-v1 generator on the device: R reads x 150 bases. */
+int dbg_seqset_synth(dbg_ctx* ctx, uint64_t n_reads, uint64_t seed, uint32_t err_thr, dbg_seqset** out);
+uint64_t dbg_seqset_len(const dbg_seqset* s);
+uint64_t dbg_seqset_n_words(const dbg_seqset* s);
+int dbg_seqset_copy_out(const dbg_seqset* s, uint64_t* words, uint64_t* start, uint32_t* length);
+void dbg_seqset_free(dbg_seqset* s);
+
+/* ---- filter::filter_kmers with CountFilter::new(min_kmer_obs) — src/filter.rs:139-231, 40-63 -----
+ * Result = the (valid_kmers, valid_exts, valid_data) arrays in ascending k-mer order, i.e. exactly
+ * what the reference hands to BoomHashMap2::new (src/filter.rs:227-230), plus `all_kmers` when
+ * report_all_kmers != 0.  memory_size_gb mirrors the reference argument; it never changes results
+ * (src/filter.rs:151-168). */
+int dbg_filter_kmers(dbg_ctx* ctx, int k, const dbg_seqset* seqs, uint32_t min_kmer_obs, int stranded,
+                     int report_all_kmers, uint64_t memory_size_gb, dbg_kmer_table** out);
+/* Same, host buffers in (upload + filter in one call; the e2e entry point). */
+int dbg_filter_kmers_host(dbg_ctx* ctx, int k, const uint64_t* words, uint64_t n_words, const uint64_t* start,
+                          const uint32_t* length, const uint8_t* seq_exts, uint64_t n_seqs, uint32_t min_kmer_obs,
+                          int stranded, int report_all_kmers, uint64_t memory_size_gb, dbg_kmer_table** out);
+uint64_t dbg_table_len(const dbg_kmer_table* t);      /* BoomHashMap2::len */
+uint64_t dbg_table_all_len(const dbg_kmer_table* t);  /* all_kmers.len()   */
+uint64_t dbg_table_n_input(const dbg_kmer_table* t);
+int dbg_table_k(const dbg_kmer_table* t);
+/* Any pointer may be NULL.  kmers_hi / all_hi are only written for k > 32. */
+int dbg_table_copy_out(const dbg_kmer_table* t, uint64_t* kmers_lo, uint64_t* kmers_hi, uint8_t* exts,
+                       uint16_t* counts, uint64_t* all_lo, uint64_t* all_hi);
+/* The `kmer_exts: &[(K,(Exts,D))]` argument of compression::compress_kmers (src/compression.rs:598-615):
+ * any order, distinct k-mers; sorted ascending on the device (seed order). */
+int dbg_table_from_host(dbg_ctx* ctx, int k, uint64_t n, const uint64_t* kmers_lo, const uint64_t* kmers_hi,
+                        const uint8_t* exts, const uint16_t* counts, dbg_kmer_table** out);
+void dbg_table_free(dbg_kmer_table* t);
+
+/* ---- compression::compress_kmers_with_hash with SimpleCompress — src/compression.rs:588-594 -------
+ * Node order = ascending smallest k-mer of each unitig (seed order = ascending canonical k-mer). */
+int dbg_compress_kmers_with_hash(dbg_ctx* ctx, const dbg_kmer_table* index, int stranded, int reduce_op,
+                                 dbg_graph** out);
+uint64_t dbg_graph_len(const dbg_graph* g);      /* BaseGraph::len, src/graph.rs:63-65 */
+uint64_t dbg_graph_n_bases(const dbg_graph* g);  /* sequences.sequence.len()           */
+uint64_t dbg_graph_n_words(const dbg_graph* g);  /* ceil(n_bases / 32)                  */
+int dbg_graph_stranded(const dbg_graph* g);
+int dbg_graph_copy_out(const dbg_graph* g, uint64_t* words, uint64_t* start, uint32_t* length, uint8_t* exts,
+                       uint16_t* data);
+void dbg_graph_free(dbg_graph* g);
+
+/* ---- fused path: reads -> BaseGraph with the k-mer table kept device-resident ----------------------
+ * Equivalent to filter_kmers(...) followed by compress_kmers_with_hash(...) (src/test.rs:344-386).
+ * `table_out` may be NULL. */
+int dbg_reads_to_graph(dbg_ctx* ctx, int k, const dbg_seqset* seqs, uint32_t min_kmer_obs, int stranded,
+                       int reduce_op, dbg_kmer_table** table_out, dbg_graph** graph_out);
+int dbg_reads_to_graph_host(dbg_ctx* ctx, int k, const uint64_t* words, uint64_t n_words, const uint64_t* start,
+                            const uint32_t* length, const uint8_t* seq_exts, uint64_t n_seqs, uint32_t min_kmer_obs,
+                            int stranded, int reduce_op, dbg_kmer_table** table_out, dbg_graph** graph_out);
+
+/* ---- msp::msp_sequence bucket assignment — src/msp.rs:279-324, 115-117 -----------------------------
+ * For every k-mer start position j of every sequence: the MSP bucket of that k-mer under the
+ * reference's default (identity) permutation with rc = !stranded, i.e. the value
+ * MspIntervalP::bucket() of the interval that Scanner::scan places the k-mer in.
+ * out_bucket has sum_i max(length[i]-k+1, 0) entries, sequence-major. */
+int dbg_msp_kmer_buckets(dbg_ctx* ctx, int k, int p, const dbg_seqset* seqs, int stranded, uint32_t* out_bucket,
+                         uint64_t n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBG_B200_H */

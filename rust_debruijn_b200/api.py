@@ -1,0 +1,339 @@
+"""Host-side mirror of the reference interface for the read -> unitig path, over the C ABI.
+
+Names, argument meaning and error behaviour follow the crate:
+    filter::filter_kmers            src/filter.rs:139-231      -> filter_kmers()
+    filter::CountFilter             src/filter.rs:40-63        -> CountFilter
+    compression::SimpleCompress     src/compression.rs:40-65   -> SimpleCompress (fixed menu of reduce closures)
+    compression::compress_kmers_with_hash  :588-594            -> compress_kmers_with_hash()
+    compression::compress_kmers     :598-615                   -> compress_kmers()
+    graph::BaseGraph                src/graph.rs:44-114        -> BaseGraph (len / sequences / exts / data / stranded)
+    dna_string::PackedDnaStringSet  src/dna_string.rs:763-822  -> PackedDnaStringSet
+The reference panics on misuse; here the same conditions raise DbgError with the ABI status.
+All compute happens in libdbg_b200.so on the GPU; numpy is only used to hold host copies."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DbgError
+
+SAT_ADD, WRAP_ADD, ADD_MOD_65535, MAX = 0, 1, 2, 3
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One CUDA device + stream + memory pool (dbg_ctx)."""
+
+    def __init__(self, device=0):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        st = self._L.dbg_ctx_create(device, C.byref(h))
+        if st != 0:
+            raise DbgError(st, f"dbg_ctx_create(device={device}) failed: no usable CUDA device (there is no CPU fallback)")
+        self._h = h
+        self.device = device
+
+    def check(self, st):
+        if st != 0:
+            raise DbgError(st, self._L.dbg_last_error(self._h).decode())
+
+    def set_param(self, name, value):
+        self.check(self._L.dbg_ctx_set_param(self._h, name.encode(), int(value)))
+
+    def stats(self):
+        s = _lib.Stats()
+        self.check(self._L.dbg_stats_get(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def synchronize(self):
+        self.check(self._L.dbg_ctx_synchronize(self._h))
+
+    def close(self):
+        if self._h:
+            self._L.dbg_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class Exts:
+    """src/lib.rs:577-749 (value type; only what the path's callers touch)."""
+
+    def __init__(self, val=0):
+        self.val = int(val) & 0xff
+
+    @staticmethod
+    def empty():
+        return Exts(0)
+
+    def __eq__(self, o):
+        return isinstance(o, Exts) and o.val == self.val
+
+    def __repr__(self):
+        return "".join("ACGT"[i] for i in range(4) if self.val & (1 << i)) + "|" + \
+               "".join("ACGT"[i] for i in range(4) if self.val & (16 << i))
+
+
+class SeqSet:
+    """Device-resident `&[(V, Exts, D1)]` (dbg_seqset)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+
+    @staticmethod
+    def upload(ctx, words, start, length, seq_exts=None):
+        words = np.ascontiguousarray(words, np.uint64)
+        start = np.ascontiguousarray(start, np.uint64)
+        length = np.ascontiguousarray(length, np.uint32)
+        if seq_exts is not None:
+            seq_exts = np.ascontiguousarray(seq_exts, np.uint8)
+        h = C.c_void_p()
+        ctx.check(ctx._L.dbg_seqset_upload(ctx._h, _ptr(words), len(words), _ptr(start), _ptr(length), _ptr(seq_exts),
+                                           len(start), C.byref(h)))
+        return SeqSet(ctx, h)
+
+    @staticmethod
+    def synth(ctx, n_reads, seed=1, err_thr=0):
+        h = C.c_void_p()
+        ctx.check(ctx._L.dbg_seqset_synth(ctx._h, n_reads, seed, err_thr, C.byref(h)))
+        return SeqSet(ctx, h)
+
+    def __len__(self):
+        return self.ctx._L.dbg_seqset_len(self._h)
+
+    def copy_out(self):
+        n, nw = len(self), self.ctx._L.dbg_seqset_n_words(self._h)
+        words, start, length = np.zeros(nw, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+        self.ctx.check(self.ctx._L.dbg_seqset_copy_out(self._h, _ptr(words), _ptr(start), _ptr(length)))
+        return words, start, length
+
+    def free(self):
+        if self._h:
+            self.ctx._L.dbg_seqset_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CountFilter:
+    """src/filter.rs:40-63: keep k-mers observed at least `min_kmer_obs` times; data = count capped at 65535."""
+
+    def __init__(self, min_kmer_obs):
+        self.min_kmer_obs = int(min_kmer_obs)
+
+
+class SimpleCompress:
+    """src/compression.rs:40-65.  The closure cannot cross to the GPU: `func` is one of the four
+    reductions the reference's tests use (SAT_ADD, WRAP_ADD, ADD_MOD_65535, MAX); join_test is always true."""
+
+    def __init__(self, func=SAT_ADD):
+        if func not in (SAT_ADD, WRAP_ADD, ADD_MOD_65535, MAX):
+            raise ValueError("SimpleCompress: func must be one of SAT_ADD, WRAP_ADD, ADD_MOD_65535, MAX")
+        self.func = func
+
+
+class KmerTable:
+    """Device-resident stand-in for BoomHashMap2<K, Exts, u16>: ascending k-mers with exts and counts."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+
+    def __len__(self):  # BoomHashMap2::len
+        return self.ctx._L.dbg_table_len(self._h)
+
+    @property
+    def k(self):
+        return self.ctx._L.dbg_table_k(self._h)
+
+    @property
+    def n_input(self):
+        return self.ctx._L.dbg_table_n_input(self._h)
+
+    def to_host(self):
+        L = self.ctx._L
+        n, na, k = len(self), L.dbg_table_all_len(self._h), self.k
+        two = k > 32
+        out = dict(k=k, lo=np.zeros(n, np.uint64), hi=np.zeros(n if two else 0, np.uint64), exts=np.zeros(n, np.uint8),
+                   counts=np.zeros(n, np.uint16), all_lo=np.zeros(na, np.uint64),
+                   all_hi=np.zeros(na if two else 0, np.uint64), n_input=self.n_input)
+        self.ctx.check(L.dbg_table_copy_out(self._h, _ptr(out["lo"]), _ptr(out["hi"]) if two else None,
+                                            _ptr(out["exts"]), _ptr(out["counts"]), _ptr(out["all_lo"]),
+                                            _ptr(out["all_hi"]) if two else None))
+        return out
+
+    def iter(self):
+        """(kmer, exts, count) in table order, like BoomHashMap2::iter (order here: ascending k-mer)."""
+        t = self.to_host()
+        for i in range(len(t["lo"])):
+            km = int(t["lo"][i]) | ((int(t["hi"][i]) << 64) if t["k"] > 32 else 0)
+            yield km, Exts(t["exts"][i]), int(t["counts"][i])
+
+    def free(self):
+        if self._h:
+            self.ctx._L.dbg_table_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PackedDnaStringSet:
+    """src/dna_string.rs:763-822: `sequence` words + `start` + `length`."""
+
+    def __init__(self, words, start, length, n_bases):
+        self.sequence, self.start, self.length, self.n_bases = words, start, length, n_bases
+
+    def __len__(self):
+        return len(self.start)
+
+    def get(self, i):
+        """Bases (0..3, uint8) of sequence i."""
+        idx = np.arange(int(self.start[i]), int(self.start[i]) + int(self.length[i]), dtype=np.uint64)
+        w = self.sequence[(idx >> np.uint64(5)).astype(np.int64)]
+        return ((w >> (np.uint64(62) - np.uint64(2) * (idx & np.uint64(31)))) & np.uint64(3)).astype(np.uint8)
+
+
+class BaseGraph:
+    """src/graph.rs:44-114.  Device-resident (dbg_graph) until to_host() is called."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+        self._host = None
+
+    def __len__(self):  # BaseGraph::len, graph.rs:63-65
+        return self.ctx._L.dbg_graph_len(self._h)
+
+    def is_empty(self):
+        return len(self) == 0
+
+    @property
+    def stranded(self):
+        return bool(self.ctx._L.dbg_graph_stranded(self._h))
+
+    def to_host(self):
+        if self._host is None:
+            L = self.ctx._L
+            m, nb, nw = len(self), L.dbg_graph_n_bases(self._h), L.dbg_graph_n_words(self._h)
+            g = dict(n_nodes=m, n_bases=nb, words=np.zeros(nw, np.uint64), start=np.zeros(m, np.uint64),
+                     length=np.zeros(m, np.uint32), exts=np.zeros(m, np.uint8), data=np.zeros(m, np.uint16),
+                     stranded=self.stranded)
+            self.ctx.check(L.dbg_graph_copy_out(self._h, _ptr(g["words"]), _ptr(g["start"]), _ptr(g["length"]),
+                                                _ptr(g["exts"]), _ptr(g["data"])))
+            self._host = g
+        return self._host
+
+    @property
+    def sequences(self):
+        g = self.to_host()
+        return PackedDnaStringSet(g["words"], g["start"], g["length"], g["n_bases"])
+
+    @property
+    def exts(self):
+        return [Exts(v) for v in self.to_host()["exts"]]
+
+    @property
+    def data(self):
+        return self.to_host()["data"]
+
+    def free(self):
+        if self._h:
+            self.ctx._L.dbg_graph_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def filter_kmers(seqs, summarizer, stranded, report_all_kmers, memory_size, k=31, ctx=None):
+    """filter::filter_kmers (src/filter.rs:139-148).
+
+    seqs: a SeqSet, or (words, start, length[, seq_exts]) host arrays in PackedDnaStringSet layout.
+    summarizer: CountFilter.  Returns (KmerTable, all_kmers) — all_kmers is empty unless report_all_kmers."""
+    if not isinstance(summarizer, CountFilter):
+        raise TypeError("only CountFilter is on the accelerated path (SURVEY.md §8)")
+    own = None
+    if isinstance(seqs, SeqSet):
+        ss, ctx = seqs, seqs.ctx
+    else:
+        ctx = ctx or default_context()
+        ss = own = SeqSet.upload(ctx, *seqs)
+    try:
+        h = C.c_void_p()
+        ctx.check(ctx._L.dbg_filter_kmers(ctx._h, k, ss._h, summarizer.min_kmer_obs, int(bool(stranded)),
+                                          int(bool(report_all_kmers)), int(memory_size), C.byref(h)))
+    finally:
+        if own is not None:
+            own.free()
+    table = KmerTable(ctx, h)
+    all_kmers = np.zeros(0, np.uint64)
+    if report_all_kmers:
+        t = table.to_host()
+        all_kmers = t["all_lo"] if k <= 32 else np.stack([t["all_lo"], t["all_hi"]], axis=1)
+    return table, all_kmers
+
+
+def compress_kmers_with_hash(stranded, spec, index):
+    """compression::compress_kmers_with_hash (src/compression.rs:588-594)."""
+    if not isinstance(spec, SimpleCompress):
+        raise TypeError("only SimpleCompress is on the accelerated path (SURVEY.md §8)")
+    ctx = index.ctx
+    h = C.c_void_p()
+    ctx.check(ctx._L.dbg_compress_kmers_with_hash(ctx._h, index._h, int(bool(stranded)), spec.func, C.byref(h)))
+    return BaseGraph(ctx, h)
+
+
+def table_from_host(k, lo, hi, exts, counts, ctx=None):
+    ctx = ctx or default_context()
+    lo = np.ascontiguousarray(lo, np.uint64)
+    hi = np.ascontiguousarray(hi, np.uint64) if k > 32 else None
+    exts = np.ascontiguousarray(exts, np.uint8)
+    counts = np.ascontiguousarray(counts, np.uint16)
+    h = C.c_void_p()
+    ctx.check(ctx._L.dbg_table_from_host(ctx._h, k, len(lo), _ptr(lo), _ptr(hi), _ptr(exts), _ptr(counts), C.byref(h)))
+    return KmerTable(ctx, h)
+
+
+def compress_kmers(stranded, spec, kmer_exts, k=31, ctx=None):
+    """compression::compress_kmers (src/compression.rs:598-615): kmer_exts = (lo, hi, exts, data) arrays."""
+    lo, hi, exts, data = kmer_exts
+    t = table_from_host(k, lo, hi, exts, data, ctx)
+    try:
+        return compress_kmers_with_hash(stranded, spec, t)
+    finally:
+        t.free()
+
+
+def reads_to_graph(seqs, summarizer, spec, stranded=False, k=31, keep_table=False):
+    """Fused filter_kmers -> compress_kmers_with_hash with the table kept on the device."""
+    ctx = seqs.ctx
+    th, gh = C.c_void_p(), C.c_void_p()
+    ctx.check(ctx._L.dbg_reads_to_graph(ctx._h, k, seqs._h, summarizer.min_kmer_obs, int(bool(stranded)), spec.func,
+                                        C.byref(th) if keep_table else None, C.byref(gh)))
+    g = BaseGraph(ctx, gh)
+    return (KmerTable(ctx, th), g) if keep_table else g

@@ -1,0 +1,482 @@
+// extern "C" boundary (include/dbg_b200.h): opaque handles over the device-resident objects, host <->
+// device copies, the synth-v1 generator.  No torch types, no exceptions across the ABI.
+#include <new>
+
+#include "common.cuh"
+
+using namespace dbg;
+
+
+namespace dbg {
+
+void free_seqset(SeqSet* s) {
+    if (!s) return;
+    if (s->owned) {
+        cudaStream_t st = s->ctx->stream;
+        if (s->words) cudaFreeAsync(s->words, st);
+        if (s->start) cudaFreeAsync(s->start, st);
+        if (s->length) cudaFreeAsync(s->length, st);
+        if (s->seq_exts) cudaFreeAsync(s->seq_exts, st);
+    }
+    delete reinterpret_cast<dbg_seqset*>(s);
+}
+void free_table(Table* t) {
+    if (!t) return;
+    cudaStream_t st = t->ctx->stream;
+    if (t->lo) cudaFreeAsync(t->lo, st);
+    if (t->hi) cudaFreeAsync(t->hi, st);
+    if (t->exts) cudaFreeAsync(t->exts, st);
+    if (t->counts) cudaFreeAsync(t->counts, st);
+    if (t->all_lo) cudaFreeAsync(t->all_lo, st);
+    if (t->all_hi) cudaFreeAsync(t->all_hi, st);
+    delete reinterpret_cast<dbg_kmer_table*>(t);
+}
+void free_graph(Graph* g) {
+    if (!g) return;
+    cudaStream_t st = g->ctx->stream;
+    if (g->words) cudaFreeAsync(g->words, st);
+    if (g->start) cudaFreeAsync(g->start, st);
+    if (g->length) cudaFreeAsync(g->length, st);
+    if (g->exts) cudaFreeAsync(g->exts, st);
+    if (g->data) cudaFreeAsync(g->data, st);
+    delete reinterpret_cast<dbg_graph*>(g);
+}
+
+// ---- synth-v1: counter-based splitmix64, identical bits on CPU and GPU ----
+__host__ __device__ __forceinline__ u64 sm64(u64 x) {
+    u64 z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void synth_reads_kernel(u64 R, u64 s0, u64 s1, u64 s2, u64 s3, u32 err_thr, u64 G, u64* words, u64 n_words,
+                                   u64* start, u32* length) {
+    u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < R) { start[w] = 150 * w; length[w] = 150; }
+    if (w >= n_words) return;
+    u64 out = 0;
+    u64 cur_read = ~0ull, rstart = 0, strand = 0;
+    for (int t = 0; t < 32; t++) {
+        u64 pos = w * 32 + t;
+        u64 i = pos / 150;
+        if (i >= R) break;
+        u32 b = (u32)(pos - i * 150);
+        if (i != cur_read) {
+            cur_read = i;
+            rstart = sm64(s1 + i) % (G - 149);
+            strand = sm64(s2 + i) >> 63;
+        }
+        u64 gi = strand ? rstart + 149 - b : rstart + b;
+        u32 base = (u32)(sm64(s0 + (gi >> 5)) >> (62 - 2 * (gi & 31))) & 3u;
+        if (strand) base = 3u - base;
+        u64 h = sm64(s3 + 256 * i + b);
+        if ((u32)(h & 0xFFFFFF) < err_thr) base = (base + 1 + (u32)((h >> 24) % 3)) & 3u;
+        out |= (u64)base << (62 - 2 * t);
+    }
+    words[w] = out;
+}
+
+int synth_reads_dev(Ctx* c, u64 R, u64 seed, u32 err_thr, SeqSet** out) {
+    *out = nullptr;
+    if (R == 0) DBG_SET_ERR(c, DBG_E_BADARG, "n_reads == 0");
+    dbg_seqset* h = new (std::nothrow) dbg_seqset();
+    SeqSet* s = &h->s;
+    s->ctx = c;
+    s->n_seqs = R;
+    s->n_words = (150 * R + 31) / 32;
+    s->uniform_len = 150;
+    s->max_len = 150;
+    DBuf<u64> words, start;
+    DBuf<u32> length;
+    TRY(words.alloc(c, s->n_words + 2));
+    TRY(words.zero());
+    TRY(start.alloc(c, R));
+    TRY(length.alloc(c, R));
+    u64 G = (150 * R + 49) / 50;
+    u64 n = s->n_words > R ? s->n_words : R;
+    synth_reads_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(R, sm64(4 * seed + 0), sm64(4 * seed + 1), sm64(4 * seed + 2),
+                                                                sm64(4 * seed + 3), err_thr, G, words.p, s->n_words, start.p,
+                                                                length.p);
+    TRY(check_launch(c, "synth_reads"));
+    TRY(sync(c));
+    s->words = words.take(); s->start = start.take(); s->length = length.take();
+    *out = s;
+    return DBG_OK;
+}
+
+}  // namespace dbg
+
+#define CTX(ctx) (&(ctx)->c)
+#define NULLCHK(ctx, p) do { if (!(p)) DBG_SET_ERR(CTX(ctx), DBG_E_BADARG, "null argument: %s", #p); } while (0)
+
+extern "C" {
+
+int dbg_ctx_create(int device, dbg_ctx** out) {
+    if (!out) return DBG_E_BADARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return DBG_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return DBG_E_CUDA;
+    dbg_ctx* h = new (std::nothrow) dbg_ctx();
+    if (!h) return DBG_E_OOM;
+    Ctx* c = &h->c;
+    c->device = device;
+    memset(&c->stats, 0, sizeof(c->stats));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return DBG_E_CUDA; }
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DBG_E_CUDA; }
+    cudaMemPoolProps pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    if (cudaMemPoolCreate(&c->pool, &pp) != cudaSuccess) { cudaStreamDestroy(c->stream); delete h; return DBG_E_CUDA; }
+    unsigned long long thr = ~0ull;  // keep freed blocks: steady-state calls do no driver allocation
+    cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    if (cudaMallocHost((void**)&c->h_scratch, 64 * 8) != cudaSuccess) { cudaMemPoolDestroy(c->pool); cudaStreamDestroy(c->stream); delete h; return DBG_E_CUDA; }
+    for (int i = 0; i < 8; i++) cudaEventCreate(&c->ev[i]);
+    *out = h;
+    return DBG_OK;
+}
+
+void dbg_ctx_destroy(dbg_ctx* ctx) {
+    if (!ctx) return;
+    Ctx* c = CTX(ctx);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+    cudaFreeHost(c->h_scratch);
+    cudaMemPoolDestroy(c->pool);
+    cudaStreamDestroy(c->stream);
+    delete ctx;
+}
+
+const char* dbg_last_error(const dbg_ctx* ctx) { return ctx ? ctx->c.err.c_str() : "null ctx"; }
+
+int dbg_stats_get(const dbg_ctx* ctx, dbg_stats* out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    *out = ctx->c.stats;
+    out->gpu_launches = ctx->c.launches;
+    return DBG_OK;
+}
+
+int dbg_ctx_set_param(dbg_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return DBG_E_BADARG;
+    Ctx* c = CTX(ctx);
+    if (!strcmp(name, "msp_p")) {
+        if (value < 0 || value > 16) DBG_SET_ERR(c, DBG_E_BADARG, "msp_p must be in [0,16]");
+        c->msp_p = (int)value;
+    } else if (!strcmp(name, "bucket_occ")) {
+        if (value < 0) DBG_SET_ERR(c, DBG_E_BADARG, "bucket_occ must be >= 0");
+        c->target_bucket_occ = (int)value;
+    } else {
+        DBG_SET_ERR(c, DBG_E_BADARG, "unknown parameter %s", name);
+    }
+    return DBG_OK;
+}
+
+int dbg_ctx_synchronize(dbg_ctx* ctx) {
+    if (!ctx) return DBG_E_BADARG;
+    cudaSetDevice(ctx->c.device);
+    return sync(CTX(ctx));
+}
+
+// ---- sequences --------------------------------------------------------------------------------------
+int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, const uint64_t* start,
+                      const uint32_t* length, const uint8_t* seq_exts, uint64_t n_seqs, dbg_seqset** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    Ctx* c = CTX(ctx);
+    *out = nullptr;
+    cudaSetDevice(c->device);
+    if (n_seqs && (!start || !length)) DBG_SET_ERR(c, DBG_E_BADARG, "start/length are required");
+    if (n_words && !words) DBG_SET_ERR(c, DBG_E_BADARG, "words is null");
+    // validate extents and detect the uniform layout (start[i] = i*L, length[i] = L) on the host
+    u32 max_len = 0;
+    bool uniform = n_seqs > 0;
+    for (u64 i = 0; i < n_seqs; i++) {
+        u64 e = (u64)start[i] + length[i];
+        if (e > n_words * 32) DBG_SET_ERR(c, DBG_E_BADARG, "sequence %llu runs past the packed words", (unsigned long long)i);
+        if (length[i] > max_len) max_len = length[i];
+        if (uniform && (length[i] != length[0] || start[i] != i * (u64)length[0])) uniform = false;
+    }
+    dbg_seqset* h = new (std::nothrow) dbg_seqset();
+    if (!h) DBG_SET_ERR(c, DBG_E_OOM, "host allocation failed");
+    SeqSet* s = &h->s;
+    s->ctx = c; s->n_seqs = n_seqs; s->n_words = n_words; s->max_len = max_len;
+    s->uniform_len = uniform ? length[0] : 0;
+    DBuf<u64> dw, ds;
+    DBuf<u32> dl;
+    DBuf<u8> de;
+    int rc = DBG_OK;
+    do {
+        if ((rc = dw.alloc(c, n_words + 2)) != DBG_OK) break;
+        if ((rc = dw.zero()) != DBG_OK) break;
+        if (n_words && cudaMemcpyAsync(dw.p, words, n_words * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = DBG_E_CUDA; break; }
+        if (!uniform) {
+            if ((rc = ds.alloc(c, n_seqs)) != DBG_OK) break;
+            if ((rc = dl.alloc(c, n_seqs)) != DBG_OK) break;
+            if (n_seqs && cudaMemcpyAsync(ds.p, start, n_seqs * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = DBG_E_CUDA; break; }
+            if (n_seqs && cudaMemcpyAsync(dl.p, length, n_seqs * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = DBG_E_CUDA; break; }
+        }
+        if (seq_exts) {
+            if ((rc = de.alloc(c, n_seqs)) != DBG_OK) break;
+            if (n_seqs && cudaMemcpyAsync(de.p, seq_exts, n_seqs, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = DBG_E_CUDA; break; }
+        }
+    } while (0);
+    if (rc != DBG_OK) {
+        if (rc == DBG_E_CUDA) c->err = std::string("seqset upload: ") + cudaGetErrorString(cudaGetLastError());
+        delete h;
+        return rc;
+    }
+    s->words = dw.take();
+    if (!uniform) { s->start = ds.take(); s->length = dl.take(); }
+    if (seq_exts) s->seq_exts = de.take();
+    *out = h;
+    return DBG_OK;
+}
+
+int dbg_seqset_wrap_device(dbg_ctx* ctx, const uint64_t* d_words, uint64_t n_words, const uint64_t* d_start,
+                           const uint32_t* d_length, const uint8_t* d_seq_exts, uint64_t n_seqs, uint32_t max_len,
+                           dbg_seqset** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    Ctx* c = CTX(ctx);
+    *out = nullptr;
+    if (n_seqs && (!d_start || !d_length || !d_words)) DBG_SET_ERR(c, DBG_E_BADARG, "null device pointer");
+    dbg_seqset* h = new (std::nothrow) dbg_seqset();
+    if (!h) DBG_SET_ERR(c, DBG_E_OOM, "host allocation failed");
+    SeqSet* s = &h->s;
+    s->ctx = c; s->owned = false;
+    s->words = (u64*)d_words; s->n_words = n_words;
+    s->start = (u64*)d_start; s->length = (u32*)d_length; s->seq_exts = (u8*)d_seq_exts;
+    s->n_seqs = n_seqs; s->max_len = max_len; s->uniform_len = 0;
+    *out = h;
+    return DBG_OK;
+}
+
+int dbg_seqset_synth(dbg_ctx* ctx, uint64_t n_reads, uint64_t seed, uint32_t err_thr, dbg_seqset** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    cudaSetDevice(ctx->c.device);
+    SeqSet* s = nullptr;
+    int rc = synth_reads_dev(CTX(ctx), n_reads, seed, err_thr, &s);
+    *out = reinterpret_cast<dbg_seqset*>(s);
+    return rc;
+}
+
+uint64_t dbg_seqset_len(const dbg_seqset* s) { return s ? s->s.n_seqs : 0; }
+uint64_t dbg_seqset_n_words(const dbg_seqset* s) { return s ? s->s.n_words : 0; }
+
+int dbg_seqset_copy_out(const dbg_seqset* h, uint64_t* words, uint64_t* start, uint32_t* length) {
+    if (!h) return DBG_E_BADARG;
+    const SeqSet* s = &h->s;
+    Ctx* c = s->ctx;
+    cudaSetDevice(c->device);
+    if (words && s->n_words) CU(c, cudaMemcpyAsync(words, s->words, s->n_words * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (s->uniform_len && (!s->start || !s->length)) {
+        for (u64 i = 0; i < s->n_seqs; i++) {
+            if (start) start[i] = i * (u64)s->uniform_len;
+            if (length) length[i] = s->uniform_len;
+        }
+    } else {
+        if (start && s->n_seqs) CU(c, cudaMemcpyAsync(start, s->start, s->n_seqs * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (length && s->n_seqs) CU(c, cudaMemcpyAsync(length, s->length, s->n_seqs * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return sync(c);
+}
+
+void dbg_seqset_free(dbg_seqset* s) { if (s) { cudaSetDevice(s->s.ctx->device); free_seqset(&s->s); } }
+
+// ---- filter_kmers -------------------------------------------------------------------------------------
+int dbg_filter_kmers(dbg_ctx* ctx, int k, const dbg_seqset* seqs, uint32_t min_kmer_obs, int stranded,
+                     int report_all_kmers, uint64_t memory_size_gb, dbg_kmer_table** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    *out = nullptr;
+    NULLCHK(ctx, seqs);
+    cudaSetDevice(ctx->c.device);
+    Table* t = nullptr;
+    int rc = filter_kmers_dev(CTX(ctx), k, &seqs->s, min_kmer_obs, stranded != 0, report_all_kmers != 0, memory_size_gb, &t);
+    *out = reinterpret_cast<dbg_kmer_table*>(t);
+    return rc;
+}
+
+int dbg_filter_kmers_host(dbg_ctx* ctx, int k, const uint64_t* words, uint64_t n_words, const uint64_t* start,
+                          const uint32_t* length, const uint8_t* seq_exts, uint64_t n_seqs, uint32_t min_kmer_obs,
+                          int stranded, int report_all_kmers, uint64_t memory_size_gb, dbg_kmer_table** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    *out = nullptr;
+    dbg_seqset* s = nullptr;
+    int rc = dbg_seqset_upload(ctx, words, n_words, start, length, seq_exts, n_seqs, &s);
+    if (rc != DBG_OK) return rc;
+    rc = dbg_filter_kmers(ctx, k, s, min_kmer_obs, stranded, report_all_kmers, memory_size_gb, out);
+    dbg_seqset_free(s);
+    return rc;
+}
+
+uint64_t dbg_table_len(const dbg_kmer_table* t) { return t ? t->t.n : 0; }
+uint64_t dbg_table_all_len(const dbg_kmer_table* t) { return t ? t->t.n_all : 0; }
+uint64_t dbg_table_n_input(const dbg_kmer_table* t) { return t ? t->t.n_input : 0; }
+int dbg_table_k(const dbg_kmer_table* t) { return t ? t->t.k : 0; }
+
+int dbg_table_copy_out(const dbg_kmer_table* h, uint64_t* kmers_lo, uint64_t* kmers_hi, uint8_t* exts,
+                       uint16_t* counts, uint64_t* all_lo, uint64_t* all_hi) {
+    if (!h) return DBG_E_BADARG;
+    const Table* t = &h->t;
+    Ctx* c = t->ctx;
+    cudaSetDevice(c->device);
+    if (t->n) {
+        if (kmers_lo) CU(c, cudaMemcpyAsync(kmers_lo, t->lo, t->n * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (kmers_hi && t->hi) CU(c, cudaMemcpyAsync(kmers_hi, t->hi, t->n * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (exts) CU(c, cudaMemcpyAsync(exts, t->exts, t->n, cudaMemcpyDeviceToHost, c->stream));
+        if (counts) CU(c, cudaMemcpyAsync(counts, t->counts, t->n * 2, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (t->n_all) {
+        if (all_lo) CU(c, cudaMemcpyAsync(all_lo, t->all_lo, t->n_all * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (all_hi && t->all_hi) CU(c, cudaMemcpyAsync(all_hi, t->all_hi, t->n_all * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return sync(c);
+}
+
+__global__ void pack_vals_kernel(const u8* exts, const u16* counts, u32* val, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) val[i] = (u32)exts[i] | ((u32)counts[i] << 8);
+}
+__global__ void unpack_vals_kernel2(const u32* val, u8* exts, u16* counts, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { u32 v = val[i]; exts[i] = (u8)v; counts[i] = (u16)(v >> 8); }
+}
+__global__ void check_sorted_unique_kernel(const u64* lo, const u64* hi, u64 n, u32* bad) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    bool ok = hi ? (hi[i] < hi[i + 1] || (hi[i] == hi[i + 1] && lo[i] < lo[i + 1])) : lo[i] < lo[i + 1];
+    if (!ok) *bad = 1;
+}
+
+int dbg_table_from_host(dbg_ctx* ctx, int k, uint64_t n, const uint64_t* kmers_lo, const uint64_t* kmers_hi,
+                        const uint8_t* exts, const uint16_t* counts, dbg_kmer_table** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    Ctx* c = CTX(ctx);
+    *out = nullptr;
+    cudaSetDevice(c->device);
+    if (k < 2 || k > 64) DBG_SET_ERR(c, DBG_E_BADARG, "k=%d outside [2,64]", k);
+    if (n && (!kmers_lo || !exts || !counts || (k > 32 && !kmers_hi))) DBG_SET_ERR(c, DBG_E_BADARG, "null array");
+    const int W = k <= 32 ? 1 : 2;
+    dbg_kmer_table* h = new (std::nothrow) dbg_kmer_table();
+    if (!h) DBG_SET_ERR(c, DBG_E_OOM, "host allocation failed");
+    Table* t = &h->t;
+    t->ctx = c; t->k = k; t->n = n; t->n_input = 0;
+    *out = h;
+    if (n == 0) return DBG_OK;
+    DBuf<u64> alo, ahi, blo, bhi;
+    DBuf<u32> av, bv, bad;
+    DBuf<u8> de;
+    DBuf<u16> dc;
+    auto fail = [&](int rc) { free_table(t); *out = nullptr; return rc; };
+#define T2(x) do { int _r = (x); if (_r != DBG_OK) return fail(_r); } while (0)
+#define CU2(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { c->err = std::string("table_from_host: ") + cudaGetErrorString(_e); return fail(DBG_E_CUDA); } } while (0)
+    T2(alo.alloc(c, n)); T2(blo.alloc(c, n)); T2(av.alloc(c, n)); T2(bv.alloc(c, n)); T2(de.alloc(c, n)); T2(dc.alloc(c, n)); T2(bad.alloc(c, 1));
+    if (W == 2) { T2(ahi.alloc(c, n)); T2(bhi.alloc(c, n)); }
+    CU2(cudaMemcpyAsync(alo.p, kmers_lo, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (W == 2) CU2(cudaMemcpyAsync(ahi.p, kmers_hi, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU2(cudaMemcpyAsync(de.p, exts, n, cudaMemcpyHostToDevice, c->stream));
+    CU2(cudaMemcpyAsync(dc.p, counts, n * 2, cudaMemcpyHostToDevice, c->stream));
+    pack_vals_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(de.p, dc.p, av.p, n);
+    T2(check_launch(c, "pack_vals"));
+    u64 *rlo, *rhi;
+    u32* rv;
+    T2(radix_sort_pairs(c, W, 2 * k, n, alo.p, ahi.p, av.p, blo.p, bhi.p, bv.p, &rlo, &rhi, &rv));
+    unpack_vals_kernel2<<<grid_for(n, 256), 256, 0, c->stream>>>(rv, de.p, dc.p, n);
+    T2(check_launch(c, "unpack_vals"));
+    T2(bad.zero());
+    check_sorted_unique_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(rlo, W == 2 ? rhi : nullptr, n, bad.p);
+    T2(check_launch(c, "check_sorted_unique"));
+    u32 hbad = 0;
+    CU2(cudaMemcpyAsync(c->h_scratch, bad.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU2(cudaStreamSynchronize(c->stream));
+    hbad = *(u32*)c->h_scratch;
+    if (hbad) { c->err = "duplicate k-mers in table"; return fail(DBG_E_BADARG); }
+    t->lo = (rlo == alo.p) ? alo.take() : blo.take();
+    if (W == 2) t->hi = (rhi == ahi.p) ? ahi.take() : bhi.take();
+    t->exts = de.take();
+    t->counts = dc.take();
+#undef T2
+#undef CU2
+    return DBG_OK;
+}
+
+void dbg_table_free(dbg_kmer_table* t) { if (t) { cudaSetDevice(t->t.ctx->device); free_table(&t->t); } }
+
+// ---- compress ------------------------------------------------------------------------------------------
+int dbg_compress_kmers_with_hash(dbg_ctx* ctx, const dbg_kmer_table* index, int stranded, int reduce_op,
+                                 dbg_graph** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    *out = nullptr;
+    NULLCHK(ctx, index);
+    cudaSetDevice(ctx->c.device);
+    Graph* g = nullptr;
+    int rc = compress_dev(CTX(ctx), &index->t, stranded != 0, reduce_op, &g);
+    *out = reinterpret_cast<dbg_graph*>(g);
+    return rc;
+}
+
+uint64_t dbg_graph_len(const dbg_graph* g) { return g ? g->g.n_nodes : 0; }
+uint64_t dbg_graph_n_bases(const dbg_graph* g) { return g ? g->g.n_bases : 0; }
+uint64_t dbg_graph_n_words(const dbg_graph* g) { return g ? g->g.n_words : 0; }
+int dbg_graph_stranded(const dbg_graph* g) { return g ? g->g.stranded : 0; }
+
+int dbg_graph_copy_out(const dbg_graph* h, uint64_t* words, uint64_t* start, uint32_t* length, uint8_t* exts,
+                       uint16_t* data) {
+    if (!h) return DBG_E_BADARG;
+    const Graph* g = &h->g;
+    Ctx* c = g->ctx;
+    cudaSetDevice(c->device);
+    if (g->n_nodes) {
+        if (words && g->n_words) CU(c, cudaMemcpyAsync(words, g->words, g->n_words * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (start) CU(c, cudaMemcpyAsync(start, g->start, g->n_nodes * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (length) CU(c, cudaMemcpyAsync(length, g->length, g->n_nodes * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (exts) CU(c, cudaMemcpyAsync(exts, g->exts, g->n_nodes, cudaMemcpyDeviceToHost, c->stream));
+        if (data) CU(c, cudaMemcpyAsync(data, g->data, g->n_nodes * 2, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return sync(c);
+}
+
+void dbg_graph_free(dbg_graph* g) { if (g) { cudaSetDevice(g->g.ctx->device); free_graph(&g->g); } }
+
+// ---- fused ------------------------------------------------------------------------------------------------
+int dbg_reads_to_graph(dbg_ctx* ctx, int k, const dbg_seqset* seqs, uint32_t min_kmer_obs, int stranded,
+                       int reduce_op, dbg_kmer_table** table_out, dbg_graph** graph_out) {
+    if (!ctx || !graph_out) return DBG_E_BADARG;
+    *graph_out = nullptr;
+    if (table_out) *table_out = nullptr;
+    dbg_kmer_table* t = nullptr;
+    int rc = dbg_filter_kmers(ctx, k, seqs, min_kmer_obs, stranded, 0, 0, &t);
+    if (rc != DBG_OK) return rc;
+    dbg_stats s1 = ctx->c.stats;
+    rc = dbg_compress_kmers_with_hash(ctx, t, stranded, reduce_op, graph_out);
+    // keep the filter-stage timings next to the compress-stage ones
+    ctx->c.stats.ms_partition = s1.ms_partition; ctx->c.stats.ms_count = s1.ms_count; ctx->c.stats.ms_sort = s1.ms_sort;
+    if (rc != DBG_OK || !table_out) dbg_table_free(t);
+    else *table_out = t;
+    return rc;
+}
+
+int dbg_reads_to_graph_host(dbg_ctx* ctx, int k, const uint64_t* words, uint64_t n_words, const uint64_t* start,
+                            const uint32_t* length, const uint8_t* seq_exts, uint64_t n_seqs, uint32_t min_kmer_obs,
+                            int stranded, int reduce_op, dbg_kmer_table** table_out, dbg_graph** graph_out) {
+    if (!ctx || !graph_out) return DBG_E_BADARG;
+    *graph_out = nullptr;
+    dbg_seqset* s = nullptr;
+    int rc = dbg_seqset_upload(ctx, words, n_words, start, length, seq_exts, n_seqs, &s);
+    if (rc != DBG_OK) return rc;
+    rc = dbg_reads_to_graph(ctx, k, s, min_kmer_obs, stranded, reduce_op, table_out, graph_out);
+    dbg_seqset_free(s);
+    return rc;
+}
+
+int dbg_msp_kmer_buckets(dbg_ctx* ctx, int k, int p, const dbg_seqset* seqs, int stranded, uint32_t* out_bucket,
+                         uint64_t n_out) {
+    if (!ctx) return DBG_E_BADARG;
+    (void)k; (void)p; (void)seqs; (void)stranded; (void)out_bucket; (void)n_out;
+    DBG_SET_ERR(CTX(ctx), DBG_E_INTERNAL, "dbg_msp_kmer_buckets: not built yet");
+}
+
+}  // extern "C"

