@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — k-mers/sec through filter_kmers + compress_kmers (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # reference algorithm on the host cores
+
+One "step" = one pass of the whole hot path (reads -> valid k-mer table -> BaseGraph) over one batch of
+synthetic reads.  N=1 workload = BASELINE.json configs[1]: K=31, 10M x 150 bp synth-v1 reads (noisy,
+e=0.5%, 50x, CountFilter(2), SimpleCompress(sat_add), stranded=false), all MSP buckets on one GPU.
+`value`   : device-resident input (reads already in HBM) -> BaseGraph arrays in HBM.
+`e2e`     : same metric through the reference-facing C-ABI call with HOST (pinned) buffers: H2D of the
+            packed reads and D2H of the BaseGraph arrays inside the timed region.
+Timing: CUDA events recorded on the library's own stream (dbg_ctx_stream), barrier + synchronize on
+both sides, max over ranks.  Inputs (375 MB packed reads) and every intermediate are larger than the
+126 MB L2, so no L2 flush is needed between iterations (stated in config.l2).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 31
+MIN_OBS = 2
+ERR_THR_NOISY = 83886
+METRIC = "k-mers/sec filter_kmers+compress_kmers K=31 150bp reads"
+UNIT = "k-mers/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
+def cpu_baseline(sample_reads, threads):
+    """Reference algorithm restated in C++ (oracle/), timed on the host cores on a bounded sample."""
+    import oracle as O
+    words, start, length = O.synth_reads(sample_reads, 1, ERR_THR_NOISY)
+    t0 = time.perf_counter()
+    t = O.filter_kmers(K, words, start, length, min_obs=MIN_OBS, stranded=False, memory_gb=4, threads=threads)
+    t1 = time.perf_counter()
+    g = O.compress_kmers(K, t["lo"], t["hi"], t["exts"], t["counts"], stranded=False, reduce_op=O.SAT_ADD)
+    t2 = time.perf_counter()
+    n = t["n_input"]
+    return {"value": n / (t2 - t0), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"synth-v1 noisy, {sample_reads} x 150bp reads (N={n} k-mers), seed 1; "
+                      f"filter {t1 - t0:.2f}s + compress {t2 - t1:.2f}s; host has {os.cpu_count()} cpus",
+            "n_valid": int(len(t["lo"])), "n_nodes": int(g["n_nodes"])}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (C++ restatement — the crate is Rust and cannot be
+    built in this image) on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.ref_reads
+    for _ in range(args.warmup):
+        cpu_baseline(max(sample // 10, 1000), threads)
+    vals, ms = [], []
+    last = None
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        last = cpu_baseline(sample, threads)
+        ms.append((time.perf_counter() - t0) * 1e3)
+        vals.append(last["value"])
+    v = statistics.mean(vals)
+    last["value"] = v
+    last["sample"] += " per step; filter stage parallel over sequence ranges and the 256 prefix buckets, compress is serial by construction"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": statistics.mean(ms), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"K=31, {sample} x 150bp synth-v1 noisy reads per step (bounded sample of configs[1]), host cores",
+                   "k": K, "min_kmer_obs": MIN_OBS, "stranded": False},
+        "cpu_baseline": last,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU (configs[1]: 10M)")
+    ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
+    ap.add_argument("--ref-reads", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import rust_debruijn_b200 as D
+
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = D.Context(local)
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize(local)
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(local)
+
+    R = args.reads
+    # weak scaling: every rank owns R reads of the same synth-v1 family (seed = 1 + rank => independent shards)
+    ss = D.SeqSet.synth(ctx, R, 1 + rank, ERR_THR_NOISY)
+    filt, spec = D.CountFilter(MIN_OBS), D.SimpleCompress(D.SAT_ADD)
+
+    def step():
+        g = D.reads_to_graph(ss, filt, spec, stranded=False, k=K)
+        n = len(g)
+        g.free()
+        return n
+
+    for _ in range(args.warmup):
+        step()
+    st0 = ctx.stats()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        step()
+    e1.record(ext)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    st1 = ctx.stats()
+    n_kmers = st1["n_input_kmers"]
+
+    # ---- e2e: host pinned buffers in, BaseGraph arrays out, through the C-ABI host entry point ----
+    hw, hs, hl = ss.copy_out()
+    pw = torch.empty(len(hw), dtype=torch.int64, pin_memory=True)
+    pw.numpy()[:] = hw.view(np.int64)
+    words_pinned = pw.numpy().view(np.uint64)
+    M0, nb0 = st1["n_nodes"], st1["n_bases"]
+    cap_nodes, cap_words = int(M0 * 1.05) + 16, int(nb0 * 1.05) // 32 + 16
+    out_bufs = {
+        "words": torch.empty(cap_words, dtype=torch.int64, pin_memory=True),
+        "start": torch.empty(cap_nodes, dtype=torch.int64, pin_memory=True),
+        "length": torch.empty(cap_nodes, dtype=torch.int32, pin_memory=True),
+        "exts": torch.empty(cap_nodes, dtype=torch.uint8, pin_memory=True),
+        "data": torch.empty(cap_nodes, dtype=torch.int16, pin_memory=True),
+    }
+    import ctypes as C
+    L = ctx._L
+
+    def e2e_step():
+        gh = C.c_void_p()
+        ctx.check(L.dbg_reads_to_graph_host(ctx._h, K, C.c_void_p(words_pinned.ctypes.data), len(words_pinned),
+                                            C.c_void_p(hs.ctypes.data), C.c_void_p(hl.ctypes.data), None, len(hs),
+                                            MIN_OBS, 0, D.SAT_ADD, None, C.byref(gh)))
+        m, nw = L.dbg_graph_len(gh), L.dbg_graph_n_words(gh)
+        assert m <= cap_nodes and nw <= cap_words
+        ctx.check(L.dbg_graph_copy_out(gh, C.c_void_p(out_bufs["words"].data_ptr()), C.c_void_p(out_bufs["start"].data_ptr()),
+                                       C.c_void_p(out_bufs["length"].data_ptr()), C.c_void_p(out_bufs["exts"].data_ptr()),
+                                       C.c_void_p(out_bufs["data"].data_ptr())))
+        L.dbg_graph_free(gh)
+        return m, nw
+
+    e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(ext)
+    for _ in range(args.steps):
+        m_nodes, n_gw = e2e_step()
+    f1.record(ext)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    h2d = int(len(words_pinned) * 8)
+    d2h = int(n_gw * 8 + m_nodes * (8 + 4 + 1 + 2))
+
+    # ---- reduce over ranks: max time, sum of units ----
+    times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
+    units = torch.tensor([float(n_kmers)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(units, op=dist.ReduceOp.SUM)
+    ms_total, ms_e2e = float(times[0]), float(times[1])
+    total_kmers = float(units[0])
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = total_kmers / (ms_step * 1e-3)
+        e2e_value = total_kmers / (ms_e2e / args.steps * 1e-3)
+        # roofline of the dominant kernel (SURVEY.md §8(d) algorithmic bytes: S1 = 150R/4 + 9N, S2 = 9N + 11V)
+        N, V = st1["n_input_kmers"], st1["n_valid"]
+        cand = {"msp_partition_kernel": (st1["ms_k_partition"], 150 * R / 4 + 9 * N),
+                "count_kernel": (st1["ms_k_count"], 9 * N + 11 * V)}
+        dom = max(cand, key=lambda k_: cand[k_][0])
+        peak, peak_kind = hbm_peak()
+        ach = cand[dom][1] / (cand[dom][0] * 1e-3) / 1e9
+        tr = ncu_traffic()
+        step_bytes = 21.65 * N
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": f"configs[1]: K=31, {R} x 150bp synth-v1 noisy reads per GPU (e=0.5%, 50x), "
+                                   "CountFilter(2), SimpleCompress(sat_add), stranded=false, all MSP buckets on one GPU",
+                       "k": K, "reads_per_gpu": R, "input_kmers_per_gpu": N, "valid_kmers": V, "nodes": st1["n_nodes"],
+                       "node_bases": st1["n_bases"], "msp_p": st1["msp_p"], "bucket_bits": st1["bucket_bits"],
+                       "l2": "inputs and every intermediate exceed the 126 MB L2; no flush needed",
+                       "parallelism": "replicas" if world > 1 else "single"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(st1["gpu_launches"] - st0["gpu_launches"]),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "peak_kind": peak_kind, "traffic": tr.get(dom),
+                         "kernel_ms": cand[dom][0],
+                         "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                                        "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}},
+            "stage_ms": {k_: round(st1[k_], 3) for k_ in ("ms_partition", "ms_count", "ms_sort", "ms_table", "ms_links",
+                                                         "ms_rank", "ms_emit", "ms_k_partition", "ms_k_count",
+                                                         "ms_filter_total", "ms_compress_total")},
+            "counters": {k_: st1[k_] for k_ in ("n_records", "n_buckets", "n_distinct", "n_bucket_splits", "rank_rounds",
+                                                "n_cycle_kmers")},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args.cpu_sample_reads, 1)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,8 @@ typedef struct {
     uint64_t gpu_launches;    /* kernels launched by this ctx so far */
     float ms_partition, ms_count, ms_sort, ms_table, ms_links, ms_rank, ms_emit;
     uint32_t msp_p, bucket_bits;
+    float ms_k_partition, ms_k_count; /* the two dominant kernels alone (events right around the launch) */
+    float ms_filter_total, ms_compress_total;
 } dbg_stats;
 
 /* ---- context ------------------------------------------------------------------------------------ */
@@ -72,6 +74,8 @@ int dbg_stats_get(const dbg_ctx* ctx, dbg_stats* out);
  * bucket, 0 = auto). */
 int dbg_ctx_set_param(dbg_ctx* ctx, const char* name, int64_t value);
 int dbg_ctx_synchronize(dbg_ctx* ctx);
+/* The cudaStream_t every call of this ctx is ordered on (for event timing / interop with other runtimes). */
+void* dbg_ctx_stream(dbg_ctx* ctx);
 
 /* ---- sequences: the `seqs: &[(V, Exts, D1)]` argument of filter_kmers (src/filter.rs:139-140) ----
  * D1 is not transported: CountFilter never reads it (src/filter.rs:56).  Host pointers are borrowed

@@ -26,7 +26,8 @@ class Stats(C.Structure):
                                            "gpu_launches")] +
                 [(n, C.c_float) for n in ("ms_partition", "ms_count", "ms_sort", "ms_table", "ms_links", "ms_rank",
                                           "ms_emit")] +
-                [("msp_p", C.c_uint32), ("bucket_bits", C.c_uint32)])
+                [("msp_p", C.c_uint32), ("bucket_bits", C.c_uint32)] +
+                [(n, C.c_float) for n in ("ms_k_partition", "ms_k_count", "ms_filter_total", "ms_compress_total")])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -51,6 +52,7 @@ SIGNATURES = {
     "dbg_stats_get": (C.c_int, [vp, C.POINTER(Stats)]),
     "dbg_ctx_set_param": (C.c_int, [vp, C.c_char_p, C.c_int64]),
     "dbg_ctx_synchronize": (C.c_int, [vp]),
+    "dbg_ctx_stream": (C.c_void_p, [vp]),
     "dbg_seqset_upload": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vpp]),
     "dbg_seqset_wrap_device": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.c_uint32, vpp]),
     "dbg_seqset_synth": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint32, vpp]),

@@ -48,6 +48,9 @@ class Context:
         self.check(self._L.dbg_stats_get(self._h, C.byref(s)))
         return s.as_dict()
 
+    def stream_ptr(self):
+        return self._L.dbg_ctx_stream(self._h)
+
     def synchronize(self):
         self.check(self._L.dbg_ctx_synchronize(self._h))
 

@@ -135,7 +135,7 @@ int dbg_ctx_create(int device, dbg_ctx** out) {
     unsigned long long thr = ~0ull;  // keep freed blocks: steady-state calls do no driver allocation
     cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
     if (cudaMallocHost((void**)&c->h_scratch, 64 * 8) != cudaSuccess) { cudaMemPoolDestroy(c->pool); cudaStreamDestroy(c->stream); delete h; return DBG_E_CUDA; }
-    for (int i = 0; i < 8; i++) cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 12; i++) cudaEventCreate(&c->ev[i]);
     *out = h;
     return DBG_OK;
 }
@@ -145,7 +145,7 @@ void dbg_ctx_destroy(dbg_ctx* ctx) {
     Ctx* c = CTX(ctx);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 12; i++) cudaEventDestroy(c->ev[i]);
     cudaFreeHost(c->h_scratch);
     cudaMemPoolDestroy(c->pool);
     cudaStreamDestroy(c->stream);
@@ -181,6 +181,8 @@ int dbg_ctx_synchronize(dbg_ctx* ctx) {
     cudaSetDevice(ctx->c.device);
     return sync(CTX(ctx));
 }
+
+void* dbg_ctx_stream(dbg_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
 
 // ---- sequences --------------------------------------------------------------------------------------
 int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, const uint64_t* start,

@@ -26,7 +26,7 @@ struct Ctx {
     // pinned scratch for small D2H reads
     u64* h_scratch = nullptr;
     // timing events
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[12];
 };
 
 #define DBG_SET_ERR(ctx, code, ...)                            \

@@ -423,6 +423,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     cudaEventElapsedTime(&S.ms_links, c->ev[1], c->ev[2]);
     cudaEventElapsedTime(&S.ms_rank, c->ev[2], c->ev[3]);
     cudaEventElapsedTime(&S.ms_emit, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&S.ms_compress_total, c->ev[0], c->ev[4]);
     S.gpu_launches = c->launches;
     return DBG_OK;
 }

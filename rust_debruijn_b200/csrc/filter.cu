@@ -596,8 +596,10 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         a.p = p; a.stranded = stranded; a.bucket_mask = NB - 1; a.maxk = maxk;
         a.rec = stage_rec.p; a.rec_bucket = stage_bucket.p; a.capacity = capacity;
         a.cursor = ctr.p; a.bucket_count = bucket_count.p; a.overflow = (u32*)(ctr.p + 1);
+        CU(c, cudaEventRecord(c->ev[8], st));
         msp_partition_kernel<W><<<grid1, P1_THREADS, 0, st>>>(kp, a);
         TRY(check_launch(c, "msp_partition"));
+        CU(c, cudaEventRecord(c->ev[9], st));
         u64 h[2];
         TRY(read_u64(c, ctr.p, h, 2));
         n_slots = h[0];
@@ -643,8 +645,10 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         size_t smem = (sizeof(Kmer<W>) + 4) * P2Cfg<W>::CAP;
         CU(c, cudaFuncSetAttribute(count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         u32 grid2 = (u32)std::min<u64>(NB, (u64)c->sm_count * 2);
+        CU(c, cudaEventRecord(c->ev[10], st));
         count_kernel<W><<<grid2, P2_THREADS, smem, st>>>(kp, a);
         TRY(check_launch(c, "count_kernel"));
+        CU(c, cudaEventRecord(c->ev[11], st));
     }
     u64 h[5];
     TRY(read_u64(c, ctr.p, h, 5));
@@ -707,6 +711,9 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     cudaEventElapsedTime(&S.ms_partition, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&S.ms_count, c->ev[1], c->ev[2]);
     cudaEventElapsedTime(&S.ms_sort, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&S.ms_k_partition, c->ev[8], c->ev[9]);
+    cudaEventElapsedTime(&S.ms_k_count, c->ev[10], c->ev[11]);
+    cudaEventElapsedTime(&S.ms_filter_total, c->ev[0], c->ev[3]);
     S.gpu_launches = c->launches;
     return DBG_OK;
 }
