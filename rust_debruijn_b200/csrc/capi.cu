@@ -86,6 +86,9 @@ int synth_reads_dev(Ctx* c, u64 R, u64 seed, u32 err_thr, SeqSet** out) {
     s->n_words = (150 * R + 31) / 32;
     s->uniform_len = 150;
     s->max_len = 150;
+    s->contiguous = true;
+    s->base0 = 0;
+    s->total_end = 150 * R;
     DBuf<u64> words, start;
     DBuf<u32> length;
     TRY(words.alloc(c, s->n_words + 2));
@@ -195,18 +198,21 @@ int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, con
     if (n_words && !words) DBG_SET_ERR(c, DBG_E_BADARG, "words is null");
     // validate extents and detect the uniform layout (start[i] = i*L, length[i] = L) on the host
     u32 max_len = 0;
-    bool uniform = n_seqs > 0;
+    bool uniform = n_seqs > 0, contiguous = n_seqs > 0;
     for (u64 i = 0; i < n_seqs; i++) {
         u64 e = (u64)start[i] + length[i];
         if (e > n_words * 32) DBG_SET_ERR(c, DBG_E_BADARG, "sequence %llu runs past the packed words", (unsigned long long)i);
         if (length[i] > max_len) max_len = length[i];
         if (uniform && (length[i] != length[0] || start[i] != i * (u64)length[0])) uniform = false;
+        if (contiguous && i + 1 < n_seqs && start[i + 1] != e) contiguous = false;
     }
     dbg_seqset* h = new (std::nothrow) dbg_seqset();
     if (!h) DBG_SET_ERR(c, DBG_E_OOM, "host allocation failed");
     SeqSet* s = &h->s;
     s->ctx = c; s->n_seqs = n_seqs; s->n_words = n_words; s->max_len = max_len;
     s->uniform_len = uniform ? length[0] : 0;
+    s->contiguous = contiguous;
+    if (contiguous) { s->base0 = start[0]; s->total_end = (u64)start[n_seqs - 1] + length[n_seqs - 1]; }
     DBuf<u64> dw, ds;
     DBuf<u32> dl;
     DBuf<u8> de;

@@ -122,6 +122,8 @@ struct SeqSet {
     u64 n_seqs = 0;
     u32 uniform_len = 0;
     u32 max_len = 0;
+    bool contiguous = false;  // start[i+1] == start[i] + length[i] (PackedDnaStringSet::add layout)
+    u64 base0 = 0, total_end = 0;  // global base range [start[0], start[n-1] + length[n-1]) when contiguous
     bool owned = true;
 };
 

@@ -174,6 +174,251 @@ __global__ void __launch_bounds__(P1_THREADS) msp_partition_kernel(KP kp, P1Args
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// P1 fast path: tile-per-CTA partition for CONTIGUOUSLY packed sequences (PackedDnaStringSet::add
+// layout: start[i+1] = start[i] + length[i]; uniform-length reads are the arithmetic special case).
+// A tile is TP consecutive base positions of the concatenation.  Three position-parallel phases in
+// shared memory, no per-sequence control flow:
+//   A  scores     thread = 4 consecutive p-mers: 3 LDS.32 + funnel shifts, canonical + hash, STS.128
+//   B  buckets    thread = 4 consecutive k-mers: register-tiled window minimum (w/4 LDS.128 per 4 outputs)
+//   C  records    lane = position: validity from a sequence-boundary bitmap, run starts by ballot,
+//                 the lane that sees a run END emits the record(s)
+// ------------------------------------------------------------------------------------------------
+static const int T1_THREADS = 256;
+static const int T1_WARPS = T1_THREADS / 32;
+static const int TP = 4096;                          // k-mer start positions per tile
+static const int T1_SEG = TP / T1_WARPS;             // positions per warp in phase C
+static const int T1_NB = TP + 64 + 2 + 32;           // staged bases: left flank + tile + K + right flank + alignment slack
+static const int T1_S32 = T1_NB / 16 + 6;            // staged 2-bit data as u32 in base order
+static const int T1_SC = TP + 64 + 8;                // p-mer scores
+static const int T1_BM = T1_NB / 32 + 4;             // boundary bitmap words
+
+struct TileArgs {
+    u64 base0;      // global position of the first base (start[0])
+    u64 total_end;  // global position one past the last base
+    u64 n_tiles;
+};
+
+__device__ __forceinline__ u32 s32_bits(const u32* s32, u32 b) {  // 32 bits starting at staged base b
+    u32 i = b >> 4;
+    return __funnelshift_l(s32[i + 1], s32[i], 2 * (b & 15));
+}
+__device__ __forceinline__ u32 s32_base(const u32* s32, u32 b) { return (s32[b >> 4] >> (30 - 2 * (b & 15))) & 3u; }
+__device__ __forceinline__ u64 bm_bits(const u32* bm, u32 b) {  // 64 boundary bits starting at staged index b (LSB = b)
+    u32 i = b >> 5, sh = b & 31;
+    u32 lo = __funnelshift_r(bm[i], bm[i + 1], sh);
+    u32 hi = __funnelshift_r(bm[i + 1], bm[i + 2], sh);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 seq_lower_bound(const u64* __restrict__ start, u64 n, u64 g) {
+    u64 lo = 0, hi = n;
+    while (lo < hi) { u64 m = (lo + hi) >> 1; if (start[m] < g) lo = m + 1; else hi = m; }
+    return lo;
+}
+// index of the sequence holding base g: last i with start[i] <= g (skips zero-length sequences sharing a start)
+__device__ __forceinline__ u64 seq_index_of(const u64* __restrict__ start, u64 n, u64 g) {
+    u64 lo = 0, hi = n;
+    while (lo < hi) { u64 m = (lo + hi) >> 1; if (start[m] <= g) lo = m + 1; else hi = m; }
+    return lo - 1;
+}
+
+template <int W>
+__device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs& ta, int K, const u32* s_s32, const u32* s_bm,
+                                                 const u32* s_bk, u64 sb, u32 ofs, int ps, int nn, u64 slot) {
+    constexpr int RW = RecLayout<W>::WORDS;
+    u32 eb = ofs + (u32)ps;            // staged index of the run's first base
+    u32 nbase = (u32)nn + K - 1;
+    u64 gpos = sb + eb;
+    bool at_first = (bm_bits(s_bm, eb) & 1ull) != 0;                                           // run starts a sequence
+    bool at_last = (bm_bits(s_bm, eb + nbase) & 1ull) != 0 || (gpos + nbase >= ta.total_end);  // run ends a sequence
+    u32 ln, rn;
+    if (at_first) {  // KmerExtsIter: first k-mer takes the sequence-level left nibble (lib.rs:820-824)
+        u32 sx = 0;
+        if (a.seq_exts) {
+            u64 si = a.uniform_len ? (gpos - ta.base0) / a.uniform_len : seq_index_of(a.start, a.n_seqs, gpos);
+            sx = a.seq_exts[si];
+        }
+        ln = sx & 0xfu;
+    } else {
+        ln = 1u << s32_base(s_s32, eb - 1);
+    }
+    if (at_last) {   // last k-mer takes the sequence-level right nibble (lib.rs:826-830)
+        u32 sx = 0;
+        if (a.seq_exts) {
+            u64 ge = gpos + nbase;
+            u64 si = a.uniform_len ? (ge - 1 - ta.base0) / a.uniform_len : seq_index_of(a.start, a.n_seqs, ge - 1);
+            sx = a.seq_exts[si];
+        }
+        rn = (sx >> 4) & 0xfu;
+    } else {
+        rn = 1u << s32_base(s_s32, eb + nbase);
+    }
+    u64 hdr = ((u64)nn << 8) | (rn << 4) | ln;
+    u64 r[RW];
+#pragma unroll
+    for (int t = 0; t < RW; t++) {
+        u32 bt = eb + 32 * t;
+        r[t] = (32u * t < nbase) ? (((u64)s32_bits(s_s32, bt) << 32) | s32_bits(s_s32, bt + 16)) : 0;
+    }
+    int lastw = (int)((nbase - 1) >> 5);
+    int used = (int)(nbase - 32 * lastw);
+#pragma unroll
+    for (int t = 0; t < RW; t++) {
+        if (t == lastw && used < 32) r[t] &= ~0ull << (64 - 2 * used);
+        if (t > lastw) r[t] = 0;
+    }
+    r[RW - 1] |= hdr;
+    u32 bkt = s_bk[ps];
+    if constexpr (RW == 2) {
+        *reinterpret_cast<ulonglong2*>(a.rec + slot * 2) = make_ulonglong2(r[0], r[1]);
+    } else {
+        *reinterpret_cast<ulonglong2*>(a.rec + slot * 4) = make_ulonglong2(r[0], r[1]);
+        *reinterpret_cast<ulonglong2*>(a.rec + slot * 4 + 2) = make_ulonglong2(r[2], r[RW - 1]);
+    }
+    a.rec_bucket[slot] = bkt;
+    atomicAdd(&a.bucket_count[bkt], 1u);
+}
+
+template <int W>
+__global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, TileArgs ta) {
+    constexpr int RW = RecLayout<W>::WORDS;
+    __shared__ __align__(16) u32 s_s32[T1_S32];
+    __shared__ __align__(16) u32 s_sc[T1_SC];
+    __shared__ __align__(16) u32 s_bk[TP + 4];
+    __shared__ u32 s_bm[T1_BM];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 lt = (1u << lane) - 1;
+    const int K = kp.k, p = a.p, wlen = K - p + 1;
+    const u64 kmask = K >= 2 ? ((K - 1 >= 64) ? ~0ull : ((1ull << (K - 1)) - 1)) : 0;  // boundary bits (b+1 .. b+K-1)
+    u64 chunk_base = 0;
+    u32 chunk_used = WCHUNK;
+
+    for (u64 tile = blockIdx.x; tile < ta.n_tiles; tile += gridDim.x) {
+        const u64 g0 = ta.base0 + tile * (u64)TP;                 // global position of tile-relative x = 0
+        const u64 sb = (g0 > ta.base0 ? g0 - 1 : g0) & ~31ull;    // staged origin (32-base aligned), covers the left flank
+        const u32 ofs = (u32)(g0 - sb);                           // staged index of x = 0
+        const u32 nbits = ofs + TP + K + 2;                       // staged indices that may be touched
+        __syncthreads();
+        // ---- stage bases (u32, base order) and the sequence-boundary bitmap ----
+        for (u32 t = tid; t < (nbits + 31) / 32 + 2; t += T1_THREADS) {
+            u64 wi = (sb >> 5) + t;
+            u64 v = wi < a.n_words ? a.words[wi] : 0;
+            s_s32[2 * t] = (u32)(v >> 32);
+            s_s32[2 * t + 1] = (u32)v;
+        }
+        for (u32 t = tid; t < (u32)T1_BM; t += T1_THREADS) s_bm[t] = 0;
+        __syncthreads();
+        if (a.uniform_len) {
+            const u64 L = a.uniform_len;
+            u64 i0 = (sb - ta.base0 + L - 1) / L;
+            for (u64 i = i0 + tid; i <= a.n_seqs; i += T1_THREADS) {
+                u64 g = ta.base0 + i * L;
+                if (g >= sb + nbits) break;
+                atomicOr(&s_bm[(g - sb) >> 5], 1u << ((g - sb) & 31));
+            }
+        } else {
+            u64 i0 = seq_lower_bound(a.start, a.n_seqs, sb);
+            for (u64 i = i0 + tid; i < a.n_seqs; i += T1_THREADS) {
+                u64 g = a.start[i];
+                if (g >= sb + nbits) break;
+                atomicOr(&s_bm[(g - sb) >> 5], 1u << ((g - sb) & 31));
+            }
+            if (tid == 0 && ta.total_end >= sb && ta.total_end < sb + nbits)
+                atomicOr(&s_bm[(ta.total_end - sb) >> 5], 1u << ((ta.total_end - sb) & 31));
+        }
+        // ---- phase A: p-mer scores, 4 consecutive positions per thread ----
+        for (u32 q0 = 4 * tid; q0 < (u32)(TP + K - p + 1); q0 += 4 * T1_THREADS) {
+            u32 b = ofs + q0, i = b >> 4, sh = 2 * (b & 15);
+            u32 w0 = s_s32[i], w1 = s_s32[i + 1], w2 = s_s32[i + 2];
+            u32 hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+            uint4 sc;
+            sc.x = pmer_score(hi >> (32 - 2 * p), p, a.stranded != 0);
+            sc.y = pmer_score(__funnelshift_l(lo, hi, 2) >> (32 - 2 * p), p, a.stranded != 0);
+            sc.z = pmer_score(__funnelshift_l(lo, hi, 4) >> (32 - 2 * p), p, a.stranded != 0);
+            sc.w = pmer_score(__funnelshift_l(lo, hi, 6) >> (32 - 2 * p), p, a.stranded != 0);
+            *reinterpret_cast<uint4*>(&s_sc[q0]) = sc;
+        }
+        __syncthreads();
+        // ---- phase B: window minimum (w >= 4) for 4 consecutive k-mers per thread ----
+        for (u32 x0 = 4 * tid; x0 < (u32)TP; x0 += 4 * T1_THREADS) {
+            uint4 f = *reinterpret_cast<const uint4*>(&s_sc[x0]);
+            u32 c = f.w;  // running min over indices 3 .. wlen-1
+            int e = 4;
+            for (; e + 3 < wlen; e += 4) {
+                uint4 v = *reinterpret_cast<const uint4*>(&s_sc[x0 + e]);
+                c = min(min(c, v.x), min(v.y, min(v.z, v.w)));
+            }
+            for (; e < wlen; e++) c = min(c, s_sc[x0 + e]);
+            u32 t0 = s_sc[x0 + wlen], t1 = s_sc[x0 + wlen + 1], t2 = s_sc[x0 + wlen + 2];
+            uint4 o;
+            o.x = min(min(f.x, f.y), min(f.z, c)) & a.bucket_mask;
+            o.y = min(min(f.y, f.z), min(c, t0)) & a.bucket_mask;
+            o.z = min(min(f.z, c), min(t0, t1)) & a.bucket_mask;
+            o.w = min(min(c, t0), min(t1, t2)) & a.bucket_mask;
+            *reinterpret_cast<uint4*>(&s_bk[x0]) = o;
+        }
+        __syncthreads();
+        // ---- phase C: records.  Warp `warp` owns tile positions [seg0, seg1); position seg1 only closes. ----
+        const u32 seg0 = warp * T1_SEG, seg1 = seg0 + T1_SEG;
+        int last_start = (int)seg0;
+        u32 carry_valid = 0;  // valid(x-1) for lane 0 of the next group
+        for (u32 gx = seg0; gx <= seg1; gx += 32) {
+            const u32 x = gx + lane;
+            const u32 b = ofs + x;
+            bool inseg = x < seg1;
+            u64 bb = bm_bits(s_bm, b);  // bit 0: a sequence starts at x; bits 1..K-1: starts inside the k-mer
+            bool valid = inseg && (sb + b < ta.total_end) && ((bb >> 1) & kmask) == 0;
+            u32 vmask = __ballot_sync(0xffffffffu, valid);
+            bool prev_valid = lane ? ((vmask >> (lane - 1)) & 1u) : (carry_valid != 0);
+            carry_valid = vmask >> 31;
+            u32 bkx = inseg ? s_bk[x] : 0, bkp = x > seg0 ? s_bk[x - 1] : 0;
+            bool start = valid && (x == seg0 || !prev_valid || (bb & 1ull) || bkx != bkp);
+            bool closer = !valid && prev_valid && x <= seg1;
+            u32 smask = __ballot_sync(0xffffffffu, start || closer);
+            if (smask == 0) continue;
+            // lanes whose bit is set and whose left neighbour k-mer is valid close the run [prev, x)
+            bool closes = ((smask >> lane) & 1u) && prev_valid;
+            u32 lower = smask & lt;
+            int prev = lower ? (int)gx + 31 - __clz(lower) : last_start;
+            int n = closes ? (int)x - prev : 0;
+            u32 nrec = closes ? (u32)((n + a.maxk - 1) / a.maxk) : 0;
+            u32 cmask = __ballot_sync(0xffffffffu, closes);
+            u32 multi = __ballot_sync(0xffffffffu, nrec > 1);
+            u32 rank, total;
+            if (!multi) {
+                rank = __popc(cmask & lt);
+                total = __popc(cmask);
+            } else {  // rare: a run longer than one record
+                u32 inc = nrec;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                rank = inc - nrec;
+                total = __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (total) {   // total <= 32 + T1_SEG / maxk < WCHUNK
+                if (chunk_used + total > (u32)WCHUNK) {
+                    u64 cb = 0;
+                    if (lane == 0) cb = atomicAdd(a.cursor, (u64)WCHUNK);
+                    chunk_base = __shfl_sync(0xffffffffu, cb, 0);
+                    chunk_used = 0;
+                    if (chunk_base + WCHUNK > a.capacity && lane == 0) *a.overflow = 1;
+                }
+                if (closes) {
+                    u64 slot0 = chunk_base + chunk_used + rank;
+                    for (u32 r = 0; r < nrec; r++) {
+                        int ps = prev + (int)r * a.maxk;
+                        int nn = min(a.maxk, (int)x - ps);
+                        if (slot0 + r < a.capacity) tile_emit_record<W>(a, ta, K, s_s32, s_bm, s_bk, sb, ofs, ps, nn, slot0 + r);
+                    }
+                }
+                chunk_used += total;
+            }
+            last_start = (int)gx + 31 - __clz(smask);
+        }
+    }
+}
+
+
 // records (staging order) -> per-bucket contiguous ranges
 template <int RW>
 __global__ void scatter_records_kernel(const u64* __restrict__ rec, const u32* __restrict__ rec_bucket, u64 n_slots,
@@ -533,9 +778,11 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     }
     // ---- plan ----
     int p = c->msp_p > 0 ? c->msp_p : 12;
-    if (p > k) p = k;
+    if (p > k - 3) p = k - 3;  // window of K-p+1 >= 4 p-mers (register-tiled window minimum)
     if (p > 16) p = 16;
+    if (p < 1) p = 1;
     if (k - p > 63) p = k - 63;
+    const bool use_tiles = s->contiguous && s->total_end > s->base0;
     int maxk = rec_max_kmers(RW, k);
     u64 target = c->target_bucket_occ > 0 ? (u64)c->target_bucket_occ : 0;
     if (!target) {
@@ -553,7 +800,7 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     // ---- work items ----
     DBuf<u32> item_seq, item_j0;
     u64 n_items = s->n_seqs;
-    bool chunked = max_len >= (u32)k && (max_len - k + 1) > (u32)CHUNK;
+    bool chunked = !use_tiles && max_len >= (u32)k && (max_len - k + 1) > (u32)CHUNK;
     if (chunked) {
         DBuf<u32> cnt;
         DBuf<u64> off, tot;
@@ -577,7 +824,11 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     TRY(bucket_fill.alloc(c, NB));
     TRY(bucket_off.alloc(c, (u64)NB + 1));
     TRY(ctr.alloc(c, 8));
-    u32 grid1 = (u32)std::min<u64>((n_items + P1_WARPS - 1) / P1_WARPS, (u64)c->sm_count * 6);
+    TileArgs ta;
+    ta.base0 = s->base0; ta.total_end = s->total_end;
+    ta.n_tiles = use_tiles ? (s->total_end - s->base0 + TP - 1) / TP : 0;
+    u32 grid1 = use_tiles ? (u32)std::min<u64>(ta.n_tiles, (u64)c->sm_count * 6)
+                          : (u32)std::min<u64>((n_items + P1_WARPS - 1) / P1_WARPS, (u64)c->sm_count * 6);
     u64 n_warps = (u64)grid1 * P1_WARPS;
     u64 capacity = N / 4 + n_warps * WCHUNK + 1024;
     DBuf<u64> stage_rec;
@@ -597,7 +848,8 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         a.rec = stage_rec.p; a.rec_bucket = stage_bucket.p; a.capacity = capacity;
         a.cursor = ctr.p; a.bucket_count = bucket_count.p; a.overflow = (u32*)(ctr.p + 1);
         CU(c, cudaEventRecord(c->ev[8], st));
-        msp_partition_kernel<W><<<grid1, P1_THREADS, 0, st>>>(kp, a);
+        if (use_tiles) msp_tile_kernel<W><<<grid1, T1_THREADS, 0, st>>>(kp, a, ta);
+        else msp_partition_kernel<W><<<grid1, P1_THREADS, 0, st>>>(kp, a);
         TRY(check_launch(c, "msp_partition"));
         CU(c, cudaEventRecord(c->ev[9], st));
         u64 h[2];

@@ -130,6 +130,29 @@ def test_edge_cases(D, ctx, orc):
         D.filter_kmers(orc.seqset_from_lists(seqs), D.CountFilter(1), False, False, 4, k=65, ctx=ctx)
 
 
+def test_layouts(D, ctx, orc):
+    """Sequence-set layouts: uniform reads with sequence-level Exts, zero-length sequences sharing a start,
+    and a NON-contiguous / out-of-order layout (general warp-per-chunk kernel instead of the tile kernel)."""
+    rng = np.random.default_rng(21)
+    # uniform, with seq_exts
+    seqs = [random_dna(rng, 40) for _ in range(300)]
+    sx = rng.integers(0, 256, size=len(seqs)).astype(np.uint8)
+    run_both(D, ctx, orc, 31, orc.seqset_from_lists(seqs), 1, seq_exts=sx)
+    run_both(D, ctx, orc, 33, orc.seqset_from_lists(seqs), 1, seq_exts=sx, stranded=True)
+    # zero-length and shorter-than-K sequences between real ones
+    seqs = [random_dna(rng, n) for n in (0, 35, 0, 0, 31, 5, 0, 90, 31, 0)]
+    sx = rng.integers(0, 256, size=len(seqs)).astype(np.uint8)
+    run_both(D, ctx, orc, 31, orc.seqset_from_lists(seqs), 1, seq_exts=sx)
+    # non-contiguous: sequences are slices (with gaps, reversed order, one overlap) of one packed buffer
+    big = random_dna(rng, 6000)
+    words = orc.pack_bases(big)
+    start = np.array([5000, 3100, 1200, 1190, 40, 0], dtype=np.uint64)
+    length = np.array([1000, 700, 650, 31, 1000, 33], dtype=np.uint32)
+    sx = rng.integers(0, 256, size=len(start)).astype(np.uint8)
+    run_both(D, ctx, orc, 31, (words, start, length), 1, seq_exts=sx)
+    run_both(D, ctx, orc, 31, (words, start, length), 1, stranded=True)
+
+
 def test_count_saturation(D, ctx, orc):
     """filter.rs:57 counts saturate at 65535; compression.rs:495 single-k-mer node keeps raw data."""
     seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")
