@@ -192,6 +192,7 @@ static const int T1_NB = TP + 64 + 2 + 32;           // staged bases: left flank
 static const int T1_S32 = T1_NB / 16 + 6;            // staged 2-bit data as u32 in base order
 static const int T1_SC = TP + 64 + 8;                // p-mer scores
 static const int T1_BM = T1_NB / 32 + 4;             // boundary bitmap words
+static const int T1_QN = 128;                        // per-warp ring queue of closed runs (power of two)
 
 struct TileArgs {
     u64 base0;      // global position of the first base (start[0])
@@ -209,6 +210,10 @@ __device__ __forceinline__ u64 bm_bits(const u32* bm, u32 b) {  // 64 boundary b
     u32 lo = __funnelshift_r(bm[i], bm[i + 1], sh);
     u32 hi = __funnelshift_r(bm[i + 1], bm[i + 2], sh);
     return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u32 bm_bits32(const u32* bm, u32 b) {  // 32 bitmap bits starting at index b (LSB = b)
+    u32 i = b >> 5;
+    return __funnelshift_r(bm[i], bm[i + 1], b & 31);
 }
 __device__ __forceinline__ u64 seq_lower_bound(const u64* __restrict__ start, u64 n, u64 g) {
     u64 lo = 0, hi = n;
@@ -285,7 +290,9 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
     __shared__ __align__(16) u32 s_s32[T1_S32];
     __shared__ __align__(16) u32 s_sc[T1_SC];
     __shared__ __align__(16) u32 s_bk[TP + 4];
-    __shared__ u32 s_bm[T1_BM];
+    __shared__ u32 s_bm[T1_BM];   // bit b: a sequence starts at staged index b (or the data ends there)
+    __shared__ u32 s_vm[T1_BM];   // bit b: a valid k-mer starts at staged index b
+    __shared__ u32 s_queue[T1_WARPS][T1_QN];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lt = (1u << lane) - 1;
     const int K = kp.k, p = a.p, wlen = K - p + 1;
@@ -339,6 +346,14 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
             *reinterpret_cast<uint4*>(&s_sc[q0]) = sc;
         }
         __syncthreads();
+        // ---- validity bitmap: a k-mer at b is valid iff no boundary in (b, b+K) and b lies before the end of data ----
+        for (u32 j = tid; j < (u32)T1_BM - 3; j += T1_THREADS) {
+            u32 inv = 0;
+            for (int d = 1; d < K; d++) inv |= bm_bits32(s_bm, 32 * j + d);
+            u64 endi = ta.total_end - sb;  // staged index of the end of data
+            u32 in_range = (u64)32 * j + 32 <= endi ? 0xffffffffu : ((u64)32 * j >= endi ? 0u : ((1u << (endi - 32 * j)) - 1));
+            s_vm[j] = ~inv & in_range;
+        }
         // ---- phase B: window minimum (w >= 4) for 4 consecutive k-mers per thread ----
         for (u32 x0 = 4 * tid; x0 < (u32)TP; x0 += 4 * T1_THREADS) {
             uint4 f = *reinterpret_cast<const uint4*>(&s_sc[x0]);
@@ -359,65 +374,75 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
         }
         __syncthreads();
         // ---- phase C: records.  Warp `warp` owns tile positions [seg0, seg1); position seg1 only closes. ----
+        // Flags are warp-uniform 32-bit masks taken from the validity / boundary bitmaps; the only per-lane
+        // work is the bucket comparison.  Closed runs go to a per-warp ring queue and are turned into
+        // records 32 at a time, so the (long) record assembly always runs with full lanes.
         const u32 seg0 = warp * T1_SEG, seg1 = seg0 + T1_SEG;
         int last_start = (int)seg0;
-        u32 carry_valid = 0;  // valid(x-1) for lane 0 of the next group
+        u32 carry_valid = 0;
+        u32 qhead = 0, qtail = 0;
+        u32* queue = s_queue[warp];
         for (u32 gx = seg0; gx <= seg1; gx += 32) {
             const u32 x = gx + lane;
-            const u32 b = ofs + x;
-            bool inseg = x < seg1;
-            u64 bb = bm_bits(s_bm, b);  // bit 0: a sequence starts at x; bits 1..K-1: starts inside the k-mer
-            bool valid = inseg && (sb + b < ta.total_end) && ((bb >> 1) & kmask) == 0;
-            u32 vmask = __ballot_sync(0xffffffffu, valid);
-            bool prev_valid = lane ? ((vmask >> (lane - 1)) & 1u) : (carry_valid != 0);
-            carry_valid = vmask >> 31;
-            u32 bkx = inseg ? s_bk[x] : 0, bkp = x > seg0 ? s_bk[x - 1] : 0;
-            bool start = valid && (x == seg0 || !prev_valid || (bb & 1ull) || bkx != bkp);
-            bool closer = !valid && prev_valid && x <= seg1;
-            u32 smask = __ballot_sync(0xffffffffu, start || closer);
-            if (smask == 0) continue;
-            // lanes whose bit is set and whose left neighbour k-mer is valid close the run [prev, x)
-            bool closes = ((smask >> lane) & 1u) && prev_valid;
-            u32 lower = smask & lt;
-            int prev = lower ? (int)gx + 31 - __clz(lower) : last_start;
-            int n = closes ? (int)x - prev : 0;
-            u32 nrec = closes ? (u32)((n + a.maxk - 1) / a.maxk) : 0;
-            u32 cmask = __ballot_sync(0xffffffffu, closes);
-            u32 multi = __ballot_sync(0xffffffffu, nrec > 1);
-            u32 rank, total;
-            if (!multi) {
-                rank = __popc(cmask & lt);
-                total = __popc(cmask);
-            } else {  // rare: a run longer than one record
-                u32 inc = nrec;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                rank = inc - nrec;
-                total = __shfl_sync(0xffffffffu, inc, 31);
+            const u32 b0 = ofs + gx;
+            const bool lastg = gx == seg1;
+            u32 vm = lastg ? 0u : bm_bits32(s_vm, b0);
+            u32 fm = bm_bits32(s_bm, b0);
+            u32 pv = (vm << 1) | carry_valid;
+            carry_valid = vm >> 31;
+            bool diff = !lastg && x > seg0 && s_bk[x] != s_bk[x - 1];
+            u32 dm = __ballot_sync(0xffffffffu, diff);
+            u32 start = vm & (fm | ~pv | dm | (gx == seg0 ? 1u : 0u));
+            u32 closer = ~vm & pv & (lastg ? 1u : 0xffffffffu);
+            u32 smask = start | closer;
+            if (smask) {
+                u32 cmask = smask & pv;  // set bits whose left neighbour is a valid k-mer close the run [prev, x)
+                bool closes = (cmask >> lane) & 1u;
+                u32 lower = smask & lt;
+                int prev = lower ? (int)gx + 31 - __clz(lower) : last_start;
+                int n = closes ? (int)x - prev : 0;
+                u32 multi = __ballot_sync(0xffffffffu, n > a.maxk);
+                if (!multi) {
+                    if (closes) queue[(qtail + __popc(cmask & lt)) & (T1_QN - 1)] = (u32)prev | ((u32)n << 16);
+                    qtail += __popc(cmask);
+                } else {  // rare: a run longer than one record is cut into pieces of maxk k-mers
+                    u32 nrec = closes ? (u32)((n + a.maxk - 1) / a.maxk) : 0;
+                    u32 inc = nrec;
+    #pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                    u32 rank = inc - nrec;
+                    for (u32 r = 0; r < nrec; r++) {
+                        int ps = prev + (int)r * a.maxk;
+                        queue[(qtail + rank + r) & (T1_QN - 1)] = (u32)ps | ((u32)min(a.maxk, (int)x - ps) << 16);
+                    }
+                    qtail += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                last_start = (int)gx + 31 - __clz(smask);
             }
-            if (total) {   // total <= 32 + T1_SEG / maxk < WCHUNK
-                if (chunk_used + total > (u32)WCHUNK) {
+            __syncwarp();
+            // drain full batches (and everything at the end of the segment)
+            while (qtail - qhead >= 32 || (lastg && qtail != qhead)) {
+                u32 cnt = min(qtail - qhead, 32u);
+                if (chunk_used + cnt > (u32)WCHUNK) {
                     u64 cb = 0;
                     if (lane == 0) cb = atomicAdd(a.cursor, (u64)WCHUNK);
                     chunk_base = __shfl_sync(0xffffffffu, cb, 0);
                     chunk_used = 0;
                     if (chunk_base + WCHUNK > a.capacity && lane == 0) *a.overflow = 1;
                 }
-                if (closes) {
-                    u64 slot0 = chunk_base + chunk_used + rank;
-                    for (u32 r = 0; r < nrec; r++) {
-                        int ps = prev + (int)r * a.maxk;
-                        int nn = min(a.maxk, (int)x - ps);
-                        if (slot0 + r < a.capacity) tile_emit_record<W>(a, ta, K, s_s32, s_bm, s_bk, sb, ofs, ps, nn, slot0 + r);
-                    }
+                if ((u32)lane < cnt) {
+                    u32 ent = queue[(qhead + lane) & (T1_QN - 1)];
+                    u64 slot = chunk_base + chunk_used + lane;
+                    if (slot < a.capacity)
+                        tile_emit_record<W>(a, ta, K, s_s32, s_bm, s_bk, sb, ofs, (int)(ent & 0xffffu), (int)(ent >> 16), slot);
                 }
-                chunk_used += total;
+                chunk_used += cnt;
+                qhead += cnt;
+                __syncwarp();
             }
-            last_start = (int)gx + 31 - __clz(smask);
         }
     }
 }
-
 
 // records (staging order) -> per-bucket contiguous ranges
 template <int RW>
