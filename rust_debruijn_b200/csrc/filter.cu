@@ -466,6 +466,8 @@ __global__ void scatter_records_kernel(const u64* __restrict__ rec, const u32* _
 static const int P2_THREADS = 512;
 static const int MAX_PROBE = 96;
 static const int SPLIT_STACK = 64;
+static const int P2_RC = 2048;   // records per chunk (prefix sums in smem)
+static const int P2_SEG = 8;     // consecutive k-mers per thread
 
 template <int W> struct P2Cfg;
 template <> struct P2Cfg<1> { static const int CAP = 8192; };  // 8 B key + 4 B val = 96 KB
@@ -495,11 +497,11 @@ template <int W>
 struct SmemTable {
     Kmer<W>* keys;
     u32* vals;  // count << 8 | exts
-    __device__ __forceinline__ int find_or_insert(Kmer<W> key, u64 h, int cap);
+    __device__ __forceinline__ int find_or_insert(Kmer<W> key, u32 h, int cap);
 };
 template <>
-__device__ __forceinline__ int SmemTable<1>::find_or_insert(Kmer<1> key, u64 h, int cap) {
-    u32 slot = (u32)(h >> 40) & (cap - 1);
+__device__ __forceinline__ int SmemTable<1>::find_or_insert(Kmer<1> key, u32 h, int cap) {
+    u32 slot = (h >> 18) & (cap - 1);  // class selection uses the low <= 18 bits
     u64* k64 = reinterpret_cast<u64*>(keys);
     for (int pr = 0; pr < MAX_PROBE; pr++) {
         u64 cur = *reinterpret_cast<volatile u64*>(k64 + slot);
@@ -513,8 +515,8 @@ __device__ __forceinline__ int SmemTable<1>::find_or_insert(Kmer<1> key, u64 h, 
     return -1;
 }
 template <>
-__device__ __forceinline__ int SmemTable<2>::find_or_insert(Kmer<2> key, u64 h, int cap) {
-    u32 slot = (u32)(h >> 40) & (cap - 1);
+__device__ __forceinline__ int SmemTable<2>::find_or_insert(Kmer<2> key, u32 h, int cap) {
+    u32 slot = (h >> 18) & (cap - 1);
     const Kmer<2> empty{~0ull, ~0ull};
     for (int pr = 0; pr < MAX_PROBE; pr++) {
         volatile u64* kp = reinterpret_cast<volatile u64*>(keys + slot);
@@ -534,6 +536,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
     Kmer<W>* keys = reinterpret_cast<Kmer<W>*>(smem_raw);
     u32* vals = reinterpret_cast<u32*>(smem_raw + sizeof(Kmer<W>) * CAP);
     __shared__ u64 s_scan[33];
+    __shared__ u32 s_pref[P2_RC + 1];
+    __shared__ u32 s_wsum[32];
     __shared__ u32 s_bucket, s_overflow, s_sp_cnt, s_sp_exts, s_nstack;
     __shared__ u64 s_base_valid, s_base_all;
     __shared__ u32 s_stack[SPLIT_STACK];  // (residue << 6) | bits ; residue < 2^26 (deeper => error)
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
             __syncthreads();
             const u32 top = s_stack[s_nstack - 1];
             const u32 cbits = top & 63u, cres = top >> 6;
-            const u64 cmask = cbits ? ((1ull << cbits) - 1) : 0;
+            const u32 cmask = cbits ? ((1u << cbits) - 1) : 0;
             __syncthreads();
             for (int i = threadIdx.x; i < CAP; i += P2_THREADS) {
                 if (W == 1) reinterpret_cast<u64*>(keys)[i] = ~0ull;
@@ -567,68 +571,162 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
             }
             if (threadIdx.x == 0) { s_overflow = 0; s_sp_cnt = 0; s_sp_exts = 0; s_nstack--; }
             __syncthreads();
-            // ---- expand records, insert ----
-            for (u64 r = r0 + threadIdx.x; r < r1; r += P2_THREADS) {
-                if (*reinterpret_cast<volatile u32*>(&s_overflow)) break;
-                u64 s[RW];
-                {
-                    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.rec + r * RW);
-                    ulonglong2 v0 = __ldg(src);
-                    s[0] = v0.x; s[1] = v0.y;
-                    if constexpr (RW == 4) { ulonglong2 v1 = __ldg(src + 1); s[2] = v1.x; s[RW - 1] = v1.y; }
+            // ---- expand records, insert.  The bucket is processed in chunks of RC records; inside a chunk the
+            // k-mers are numbered consecutively (prefix sum of the per-record counts in smem) and every thread
+            // rolls a segment of SEG consecutive k-mers, crossing record boundaries as needed, so all lanes of a
+            // warp do the same amount of work whatever the record lengths are. ----
+            for (u64 c0 = r0; c0 < r1; c0 += P2_RC) {
+                const u32 nrc = (u32)min((u64)P2_RC, r1 - c0);
+                {   // prefix sums of k-mers per record
+                    u32 cnt[P2_RC / P2_THREADS];
+                    u32 sum = 0;
+#pragma unroll
+                    for (int j = 0; j < P2_RC / P2_THREADS; j++) {
+                        u32 idx = threadIdx.x * (P2_RC / P2_THREADS) + j;
+                        cnt[j] = idx < nrc ? ((u32)__ldg(a.rec + (c0 + idx) * RW + (RW - 1)) >> 8) & 63u : 0;
+                        sum += cnt[j];
+                    }
+                    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                    u32 inc = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                    if (lane == 31) s_wsum[warp] = inc;
+                    __syncthreads();
+                    if (warp == 0) {
+                        u32 w = lane < P2_THREADS / 32 ? s_wsum[lane] : 0, winc = w;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+                        s_wsum[lane] = winc - w;
+                        if (lane == 31) s_pref[P2_RC] = winc;
+                    }
+                    __syncthreads();
+                    u32 ex = s_wsum[warp] + inc - sum;
+#pragma unroll
+                    for (int j = 0; j < P2_RC / P2_THREADS; j++) {
+                        s_pref[threadIdx.x * (P2_RC / P2_THREADS) + j] = ex;
+                        ex += cnt[j];
+                    }
+                    __syncthreads();
                 }
-                const u32 hdr = (u32)s[RW - 1] & 0x3fffu;
-                const int n = (int)(hdr >> 8);
-                const u32 rn = (hdr >> 4) & 0xfu, ln = hdr & 0xfu;
-                Kmer<W> fwd;
-                if constexpr (W == 1) {
-                    fwd.lo = s[0] >> (64 - 2 * K);
-                } else {
-                    // first K (33..64) bases = top 2K bits of (s0:s1)
-                    int sh = 128 - 2 * K;  // 0..62
-                    fwd.hi = sh ? (s[0] >> sh) : s[0];
-                    fwd.lo = sh ? ((s[1] >> sh) | (s[0] << (64 - sh))) : s[1];
-                }
-                Kmer<W> rcv = Ops<W>::rc(kp, fwd);
-                u32 prev_first = 0;
-                for (int t = 0; t < n; t++) {
-                    u32 nb;  // base t+K (only meaningful when t < n-1)
-                    if constexpr (W == 1) nb = (u32)((nxt_word ? s[1] : s[0]) >> nxt_shift) & 3u;
-                    else nb = (u32)((nxt_word == 2 ? s[2] : s[1]) >> nxt_shift) & 3u;
-                    u32 left = t == 0 ? ln : (1u << prev_first);
-                    u32 right = t == n - 1 ? rn : (1u << nb);
-                    u32 e = left | (right << 4);
-                    Kmer<W> key = fwd;
-                    if (!a.stranded && !(fwd < rcv)) { key = rcv; e = exts_rc(e); }  // lib.rs:224-231, filter.rs:190-196
-                    u64 h = Ops<W>::mix(key);
-                    if ((h & cmask) == cres) {
-                        bool special;
-                        if constexpr (W == 1) special = key.lo == ~0ull;
-                        else special = key.lo == ~0ull && key.hi == ~0ull;
-                        if (special) {  // all-T k-mer at K = 32/64 stranded collides with the EMPTY sentinel
-                            atomicAdd(&s_sp_cnt, 1u);
-                            atomicOr(&s_sp_exts, e);
+                const u32 T = s_pref[P2_RC];
+                for (u32 k0 = threadIdx.x * P2_SEG; k0 < T; k0 += P2_THREADS * P2_SEG) {
+                    if (*reinterpret_cast<volatile u32*>(&s_overflow)) break;
+                    const u32 k1 = min(T, k0 + (u32)P2_SEG);
+                    // record holding k-mer k0: largest i with pref[i] <= k0
+                    u32 lo = 0, hi = nrc - 1;
+                    while (lo < hi) { u32 m = (lo + hi + 1) >> 1; if (s_pref[m] <= k0) lo = m; else hi = m - 1; }
+                    u32 ri = lo;
+                    int t = (int)(k0 - s_pref[ri]);
+                    // current record (shifted so that k-mer t is at the front) and the prefetched next one
+                    u64 s[RW], nx[RW];
+                    {
+                        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.rec + (c0 + ri) * RW);
+                        ulonglong2 v0 = __ldg(src);
+                        s[0] = v0.x; s[1] = v0.y;
+                        if constexpr (RW == 4) { ulonglong2 v1 = __ldg(src + 1); s[2] = v1.x; s[RW - 1] = v1.y; }
+                        const u64 rnx = min(c0 + ri + 1, r1 - 1);
+                        const ulonglong2* srn = reinterpret_cast<const ulonglong2*>(a.rec + rnx * RW);
+                        ulonglong2 n0 = __ldg(srn);
+                        nx[0] = n0.x; nx[1] = n0.y;
+                        if constexpr (RW == 4) { ulonglong2 n1 = __ldg(srn + 1); nx[2] = n1.x; nx[RW - 1] = n1.y; }
+                    }
+                    u32 hdr = (u32)s[RW - 1] & 0x3fffu;
+                    int n = (int)(hdr >> 8);
+                    u32 rn = (hdr >> 4) & 0xfu, ln = hdr & 0xfu;
+                    u32 prev_first = 0;
+                    if (t > 0) {  // start inside the record: drop t bases from the front (static register indices only)
+                        const int pb = t - 1, pw = pb >> 5;
+                        u64 wsel = s[0];
+                        if (pw == 1) wsel = s[1];
+                        if constexpr (RW == 4) { if (pw == 2) wsel = s[2]; if (pw == 3) wsel = s[3]; }
+                        prev_first = (u32)(wsel >> (62 - 2 * (pb & 31))) & 3u;
+                        const int ws = t >> 5, bs = 2 * (t & 31);
+                        if constexpr (RW == 2) {
+                            if (ws) { s[0] = s[1]; s[1] = 0; }
                         } else {
-                            int slot = tab.find_or_insert(key, h, CAP);
-                            if (slot < 0) { s_overflow = 1; break; }
-                            u32 v = *reinterpret_cast<volatile u32*>(vals + slot);
-                            if (e & ~v) atomicOr(vals + slot, e);
-                            if ((v >> 8) < 65535u) atomicAdd(vals + slot, 256u);  // saturating count, filter.rs:57
+                            if (ws & 1) { s[0] = s[1]; s[1] = s[2]; s[2] = s[3]; s[3] = 0; }
+                            if (ws & 2) { s[0] = s[2]; s[1] = s[3]; s[2] = 0; s[3] = 0; }
+                        }
+                        if (bs) {
+#pragma unroll
+                            for (int q = 0; q < RW - 1; q++) s[q] = (s[q] << bs) | (s[q + 1] >> (64 - bs));
+                            s[RW - 1] <<= bs;
                         }
                     }
-                    // roll to the next k-mer
-                    prev_first = (u32)(s[0] >> 62);
-                    fwd = Ops<W>::ext_right(kp, fwd, nb);
-                    rcv = Ops<W>::roll_rc(kp, rcv, nb);
+                    Kmer<W> fwd;
+                    if constexpr (W == 1) {
+                        fwd.lo = s[0] >> (64 - 2 * K);
+                    } else {
+                        const int sh = 128 - 2 * K;  // first K (33..64) bases = top 2K bits of (s0:s1)
+                        fwd.hi = sh ? (s[0] >> sh) : s[0];
+                        fwd.lo = sh ? ((s[1] >> sh) | (s[0] << (64 - sh))) : s[1];
+                    }
+                    Kmer<W> rcv = Ops<W>::rc(kp, fwd);
+                    // one uniform loop: every lane handles one k-mer per iteration; switching to the next record is a
+                    // short predicated block (registers only, the following record is prefetched)
+                    for (u32 k = k0; k < k1; k++) {
+                        u32 nb;  // base t+K (only meaningful when t < n-1)
+                        if constexpr (W == 1) nb = (u32)((nxt_word ? s[1] : s[0]) >> nxt_shift) & 3u;
+                        else nb = (u32)((nxt_word == 2 ? s[2] : s[1]) >> nxt_shift) & 3u;
+                        u32 left = t == 0 ? ln : (1u << prev_first);
+                        u32 right = t == n - 1 ? rn : (1u << nb);
+                        u32 e = left | (right << 4);
+                        Kmer<W> key = fwd;
+                        if (!a.stranded && !(fwd < rcv)) { key = rcv; e = exts_rc(e); }  // lib.rs:224-231, filter.rs:190-196
+                        u32 h = Ops<W>::hash32(key);
+                        if ((h & cmask) == cres) {
+                            bool special;
+                            if constexpr (W == 1) special = key.lo == ~0ull;
+                            else special = key.lo == ~0ull && key.hi == ~0ull;
+                            if (special) {  // all-T k-mer at K = 32/64 stranded collides with the EMPTY sentinel
+                                atomicAdd(&s_sp_cnt, 1u);
+                                atomicOr(&s_sp_exts, e);
+                            } else {
+                                int slot = tab.find_or_insert(key, h, CAP);
+                                if (slot < 0) { s_overflow = 1; break; }
+                                u32 v = *reinterpret_cast<volatile u32*>(vals + slot);
+                                if (e & ~v) atomicOr(vals + slot, e);
+                                if ((v >> 8) < 65535u) atomicAdd(vals + slot, 256u);  // saturating count, filter.rs:57
+                            }
+                        }
+                        t++;
+                        if (t < n) {  // roll to the next k-mer of this record
+                            prev_first = (u32)(s[0] >> 62);
+                            fwd = Ops<W>::ext_right(kp, fwd, nb);
+                            rcv = Ops<W>::roll_rc(kp, rcv, nb);
 #pragma unroll
-                    for (int q = 0; q < RW - 1; q++) s[q] = (s[q] << 2) | (s[q + 1] >> 62);
-                    s[RW - 1] <<= 2;
+                            for (int q = 0; q < RW - 1; q++) s[q] = (s[q] << 2) | (s[q + 1] >> 62);
+                            s[RW - 1] <<= 2;
+                        } else {      // next record
+                            ri++;
+                            t = 0;
+#pragma unroll
+                            for (int q = 0; q < RW; q++) s[q] = nx[q];
+                            hdr = (u32)s[RW - 1] & 0x3fffu;
+                            n = (int)(hdr >> 8);
+                            rn = (hdr >> 4) & 0xfu; ln = hdr & 0xfu;
+                            if constexpr (W == 1) {
+                                fwd.lo = s[0] >> (64 - 2 * K);
+                            } else {
+                                const int sh = 128 - 2 * K;
+                                fwd.hi = sh ? (s[0] >> sh) : s[0];
+                                fwd.lo = sh ? ((s[1] >> sh) | (s[0] << (64 - sh))) : s[1];
+                            }
+                            rcv = Ops<W>::rc(kp, fwd);
+                            const u64 rnx = min(c0 + ri + 1, r1 - 1);
+                            const ulonglong2* srn = reinterpret_cast<const ulonglong2*>(a.rec + rnx * RW);
+                            ulonglong2 n0 = __ldg(srn);
+                            nx[0] = n0.x; nx[1] = n0.y;
+                            if constexpr (RW == 4) { ulonglong2 n1 = __ldg(srn + 1); nx[2] = n1.x; nx[RW - 1] = n1.y; }
+                        }
+                    }
                 }
+                __syncthreads();
             }
             __syncthreads();
             if (s_overflow) {
                 if (threadIdx.x == 0) {
-                    if (cbits >= 26 || s_nstack + 2 > SPLIT_STACK) {
+                    if (cbits >= 18 || s_nstack + 2 > SPLIT_STACK) {
                         a.counters[4] = 1;  // cannot happen for distinct keys below 2^26 classes; reported as internal error
                     } else {
                         s_stack[s_nstack++] = ((cres | (1u << cbits)) << 6) | (cbits + 1);
