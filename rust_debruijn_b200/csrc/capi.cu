@@ -91,10 +91,10 @@ int synth_reads_dev(Ctx* c, u64 R, u64 seed, u32 err_thr, SeqSet** out) {
     s->total_end = 150 * R;
     DBuf<u64> words, start;
     DBuf<u32> length;
-    TRY(words.alloc(c, s->n_words + 2));
+    TRY(words.alloc_pool(c, s->n_words + 2));
     TRY(words.zero());
-    TRY(start.alloc(c, R));
-    TRY(length.alloc(c, R));
+    TRY(start.alloc_pool(c, R));
+    TRY(length.alloc_pool(c, R));
     u64 G = (150 * R + 49) / 50;
     u64 n = s->n_words > R ? s->n_words : R;
     synth_reads_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(R, sm64(4 * seed + 0), sm64(4 * seed + 1), sm64(4 * seed + 2),
@@ -150,6 +150,7 @@ void dbg_ctx_destroy(dbg_ctx* ctx) {
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 12; i++) cudaEventDestroy(c->ev[i]);
     cudaFreeHost(c->h_scratch);
+    if (c->arena) cudaFree(c->arena);
     cudaMemPoolDestroy(c->pool);
     cudaStreamDestroy(c->stream);
     delete ctx;
@@ -218,17 +219,17 @@ int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, con
     DBuf<u8> de;
     int rc = DBG_OK;
     do {
-        if ((rc = dw.alloc(c, n_words + 2)) != DBG_OK) break;
+        if ((rc = dw.alloc_pool(c, n_words + 2)) != DBG_OK) break;
         if ((rc = dw.zero()) != DBG_OK) break;
         if (n_words && cudaMemcpyAsync(dw.p, words, n_words * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = DBG_E_CUDA; break; }
         if (!uniform) {
-            if ((rc = ds.alloc(c, n_seqs)) != DBG_OK) break;
-            if ((rc = dl.alloc(c, n_seqs)) != DBG_OK) break;
+            if ((rc = ds.alloc_pool(c, n_seqs)) != DBG_OK) break;
+            if ((rc = dl.alloc_pool(c, n_seqs)) != DBG_OK) break;
             if (n_seqs && cudaMemcpyAsync(ds.p, start, n_seqs * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = DBG_E_CUDA; break; }
             if (n_seqs && cudaMemcpyAsync(dl.p, length, n_seqs * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = DBG_E_CUDA; break; }
         }
         if (seq_exts) {
-            if ((rc = de.alloc(c, n_seqs)) != DBG_OK) break;
+            if ((rc = de.alloc_pool(c, n_seqs)) != DBG_OK) break;
             if (n_seqs && cudaMemcpyAsync(de.p, seq_exts, n_seqs, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = DBG_E_CUDA; break; }
         }
     } while (0);
@@ -381,8 +382,9 @@ int dbg_table_from_host(dbg_ctx* ctx, int k, uint64_t n, const uint64_t* kmers_l
     auto fail = [&](int rc) { free_table(t); *out = nullptr; return rc; };
 #define T2(x) do { int _r = (x); if (_r != DBG_OK) return fail(_r); } while (0)
 #define CU2(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { c->err = std::string("table_from_host: ") + cudaGetErrorString(_e); return fail(DBG_E_CUDA); } } while (0)
-    T2(alo.alloc(c, n)); T2(blo.alloc(c, n)); T2(av.alloc(c, n)); T2(bv.alloc(c, n)); T2(de.alloc(c, n)); T2(dc.alloc(c, n)); T2(bad.alloc(c, 1));
-    if (W == 2) { T2(ahi.alloc(c, n)); T2(bhi.alloc(c, n)); }
+    T2(arena_begin(c));
+    T2(alo.alloc_pool(c, n)); T2(blo.alloc_pool(c, n)); T2(av.alloc(c, n)); T2(bv.alloc(c, n)); T2(de.alloc_pool(c, n)); T2(dc.alloc_pool(c, n)); T2(bad.alloc(c, 1));
+    if (W == 2) { T2(ahi.alloc_pool(c, n)); T2(bhi.alloc_pool(c, n)); }
     CU2(cudaMemcpyAsync(alo.p, kmers_lo, n * 8, cudaMemcpyHostToDevice, c->stream));
     if (W == 2) CU2(cudaMemcpyAsync(ahi.p, kmers_hi, n * 8, cudaMemcpyHostToDevice, c->stream));
     CU2(cudaMemcpyAsync(de.p, exts, n, cudaMemcpyHostToDevice, c->stream));

@@ -25,6 +25,10 @@ struct Ctx {
     u64 launches = 0;          // kernels launched by this ctx (gpu_launches in bench.py)
     // pinned scratch for small D2H reads
     u64* h_scratch = nullptr;
+    // scratch arena: one device slab, bump/LIFO allocated per top-level call, regrown between calls when a
+    // call needed more than it holds (the overflow of that call is served by the pool)
+    char* arena = nullptr;
+    u64 arena_size = 0, arena_off = 0, arena_want = 0;
     // timing events
     cudaEvent_t ev[12];
 };
@@ -52,26 +56,42 @@ struct Ctx {
         if (_s != DBG_OK) return _s; \
     } while (0)
 
-// Stream-ordered device buffer (cudaMallocAsync from the ctx pool; the pool keeps freed blocks so
-// steady-state calls do no driver allocation).
+// Device buffer.  alloc(): scratch from the ctx arena (no driver call in steady state; LIFO release).
+// alloc_pool(): result storage from the ctx memory pool (cudaMallocAsync), may be handed out with take().
 template <typename T>
 struct DBuf {
     T* p = nullptr;
     u64 n = 0;
     Ctx* ctx = nullptr;
+    u64 arena_prev = ~0ull;  // arena offset to restore on release; ~0 = not an arena buffer
     DBuf() {}
     DBuf(const DBuf&) = delete;
     DBuf& operator=(const DBuf&) = delete;
-    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), ctx(o.ctx) { o.p = nullptr; o.n = 0; }
-    DBuf& operator=(DBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; ctx = o.ctx; o.p = nullptr; o.n = 0; }
-        return *this;
-    }
     ~DBuf() { release(); }
     int alloc(Ctx* c, u64 count) {
         release();
         ctx = c;
         n = count;
+        u64 bytes = ((count ? count : 1) * sizeof(T) + 255) & ~255ull;
+        if (c->arena_off + bytes <= c->arena_size) {
+            arena_prev = c->arena_off;
+            p = reinterpret_cast<T*>(c->arena + c->arena_off);
+            c->arena_off += bytes;
+            if (c->arena_off > c->arena_want) c->arena_want = c->arena_off;
+            return DBG_OK;
+        }
+        // does not fit: remember the demand (as if it had been bump-allocated) and serve from the pool
+        u64 would = c->arena_off + bytes;
+        if (would > c->arena_want) c->arena_want = would;
+        arena_prev = ~0ull;
+        CU(c, cudaMallocAsync((void**)&p, bytes, c->pool, c->stream));
+        return DBG_OK;
+    }
+    int alloc_pool(Ctx* c, u64 count) {
+        release();
+        ctx = c;
+        n = count;
+        arena_prev = ~0ull;
         u64 bytes = (count ? count : 1) * sizeof(T);
         CU(c, cudaMallocAsync((void**)&p, bytes, c->pool, c->stream));
         return DBG_OK;
@@ -85,12 +105,40 @@ struct DBuf {
         return DBG_OK;
     }
     void release() {
-        if (p && ctx) cudaFreeAsync(p, ctx->stream);
+        if (p && ctx) {
+            if (arena_prev != ~0ull) {
+                // LIFO: give the space back only when this is the top of the arena (stream order keeps reuse safe)
+                u64 bytes = ((n ? n : 1) * sizeof(T) + 255) & ~255ull;
+                if (arena_prev + bytes == ctx->arena_off) ctx->arena_off = arena_prev;
+            } else {
+                cudaFreeAsync(p, ctx->stream);
+            }
+        }
         p = nullptr;
         n = 0;
+        arena_prev = ~0ull;
     }
-    T* take() { T* q = p; p = nullptr; n = 0; return q; }
+    T* take() {  // pool buffers only
+        if (arena_prev != ~0ull) { fprintf(stderr, "dbg: take() on an arena buffer\n"); abort(); }
+        T* q = p; p = nullptr; n = 0; return q;
+    }
 };
+
+// Called at the start of every top-level stage call: empty the arena, regrow it if the last call overflowed.
+inline int arena_begin(Ctx* c) {
+    c->arena_off = 0;
+    if (c->arena_want > c->arena_size) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        if (c->arena) CU(c, cudaFree(c->arena));
+        c->arena = nullptr;
+        c->arena_size = 0;
+        u64 want = c->arena_want + c->arena_want / 8 + (64ull << 20);
+        cudaError_t e = cudaMalloc((void**)&c->arena, want);
+        if (e == cudaSuccess) c->arena_size = want;
+        else { cudaGetLastError(); c->arena_want = 0; }  // stay on the pool
+    }
+    return DBG_OK;
+}
 
 inline int sync(Ctx* c) {
     CU(c, cudaStreamSynchronize(c->stream));

@@ -302,6 +302,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     *out = g;
     S.n_nodes = S.n_bases = 0; S.rank_rounds = 0; S.n_cycle_kmers = 0;
     if (V == 0) return DBG_OK;
+    TRY(arena_begin(c));
     if (V >= (1ull << 31)) DBG_SET_ERR(c, DBG_E_BADARG, "k-mer table too large for 32-bit port states (%llu)", (unsigned long long)V);
     CU(c, cudaEventRecord(c->ev[0], st));
     // ---- S3 ----
@@ -401,9 +402,9 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     DBuf<u32> olen, oextw;
     DBuf<u8> oexts;
     DBuf<u16> odata;
-    TRY(words.alloc(c, g->n_words + 3)); TRY(words.zero());
-    TRY(ostart.alloc(c, M)); TRY(olen.alloc(c, M)); TRY(oextw.alloc(c, M / 4 + 1)); TRY(oextw.zero());
-    TRY(acc.alloc(c, M)); TRY(acc.zero()); TRY(oexts.alloc(c, M)); TRY(odata.alloc(c, M));
+    TRY(words.alloc_pool(c, g->n_words + 3)); TRY(words.zero());
+    TRY(ostart.alloc_pool(c, M)); TRY(olen.alloc_pool(c, M)); TRY(oextw.alloc(c, M / 4 + 1)); TRY(oextw.zero());
+    TRY(acc.alloc(c, M)); TRY(acc.zero()); TRY(oexts.alloc_pool(c, M)); TRY(odata.alloc_pool(c, M));
     EmitArgs ea;
     ea.lo = t->lo; ea.hi = t->hi; ea.exts = t->exts; ea.counts = t->counts; ea.n = V;
     ea.seed = seed.p; ea.pos = pos.p; ea.nlen = nlen.p; ea.flags = flags.p;

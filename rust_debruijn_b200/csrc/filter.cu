@@ -869,6 +869,7 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     KP kp = make_kp(k);
     cudaStream_t st = c->stream;
     dbg_stats& S = c->stats;
+    TRY(arena_begin(c));
     CU(c, cudaEventRecord(c->ev[0], st));
 
     // ---- input size ----
@@ -1040,17 +1041,17 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     if (V) {
         DBuf<u64> b_lo, b_hi;
         DBuf<u32> b_val;
-        TRY(b_lo.alloc(c, V));
+        TRY(b_lo.alloc_pool(c, V));
         TRY(b_val.alloc(c, V));
-        if (W == 2) TRY(b_hi.alloc(c, V));
+        if (W == 2) TRY(b_hi.alloc_pool(c, V));
         u64 *rlo, *rhi;
         u32* rval;
         TRY(radix_sort_pairs(c, W, 2 * k, V, v_lo.p, v_hi.p, v_val.p, b_lo.p, b_hi.p, b_val.p, &rlo, &rhi, &rval));
         // keep right-sized arrays: take the V-sized buffer when the result landed there, else copy out of the bound-sized one
         DBuf<u8> d_exts;
         DBuf<u16> d_counts;
-        TRY(d_exts.alloc(c, V));
-        TRY(d_counts.alloc(c, V));
+        TRY(d_exts.alloc_pool(c, V));
+        TRY(d_counts.alloc_pool(c, V));
         unpack_vals_kernel<<<grid_for(V, 256), 256, 0, st>>>(rval, d_exts.p, d_counts.p, V);
         TRY(check_launch(c, "unpack_vals"));
         if (rlo != b_lo.p) {
@@ -1066,8 +1067,8 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         // all_kmers: every distinct k-mer, ascending (src/filter.rs:210-212)
         DBuf<u64> b_lo, b_hi;
         DBuf<u32> dummy_a, dummy_b;
-        TRY(b_lo.alloc(c, U));
-        if (W == 2) TRY(b_hi.alloc(c, U));
+        TRY(b_lo.alloc_pool(c, U));
+        if (W == 2) TRY(b_hi.alloc_pool(c, U));
         TRY(dummy_a.alloc(c, U));
         TRY(dummy_b.alloc(c, U));
         u64 *rlo, *rhi;
