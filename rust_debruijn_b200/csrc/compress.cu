@@ -61,13 +61,11 @@ __device__ __forceinline__ u32 table_find(const Kmer<W>* __restrict__ tkeys, con
     }
 }
 
-// ---- S4 (+ S5 init) ---------------------------------------------------------------------------------
-// rec = (ptr, len, minst, mindist): window of `len` consecutive states starting at s; minst = the
-// state at which the smallest-index k-mer of the window is traversed; mindist = steps from s to it.
+// ---- S4 -------------------------------------------------------------------------------------------
 template <int W>
 __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __restrict__ hi, const u8* __restrict__ exts,
                              u64 n, const Kmer<W>* __restrict__ tkeys, const u32* __restrict__ tidx, u64 mask,
-                             int stranded, u32* __restrict__ nxt, uint4* __restrict__ rec, u32* __restrict__ err) {
+                             int stranded, u32* __restrict__ nxt, u32* __restrict__ err) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Kmer<W> key = load_key<W>(lo, hi, i);
@@ -104,8 +102,65 @@ __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __res
         }
         u32 s = 2u * (u32)i + d;
         nxt[s] = succ;
-        rec[s] = make_uint4(succ, 1u, s, 0u);
     }
+}
+
+// ---- S5a: short unitigs by walking from their ends ------------------------------------------------------
+// Every k-mer with exactly one free side is a path end.  Its thread walks to the other end (<= lmax steps),
+// tracking the smallest index (the seed, compression.rs:574-575) and the port state in which the seed is
+// traversed; the walker that started at the smaller-index end then walks again and writes
+// (seed, position, length, orientation) for every k-mer of the unitig.  Paths longer than lmax and cycles
+// are left untouched (nlen stays 0) for the pointer-doubling fallback.
+__global__ void walk_kernel(const u32* __restrict__ nxt, u64 n, u32 lmax, u32* __restrict__ seed, u32* __restrict__ pos,
+                            u32* __restrict__ nlen, u8* __restrict__ flags, u64* __restrict__ written) {
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 wrote = 0;
+    if (v < n) {
+        u32 a0 = nxt[2 * v], a1 = nxt[2 * v + 1];
+        if (a0 == NIL && a1 == NIL) {
+            seed[v] = (u32)v; pos[v] = 0; nlen[v] = 1; flags[v] = 1;
+            wrote = 1;
+        } else if (a0 == NIL || a1 == NIL) {
+            const u32 d = a0 == NIL ? 1u : 0u;  // the linked side: walk inwards through it
+            u32 cur = 2u * (u32)v + d, cnt = 1, minv = (u32)v, minst = cur;
+            u32 t = d ? a1 : a0;
+            while (t != NIL && cnt <= lmax) {
+                cur = t;
+                cnt++;
+                if ((t >> 1) < minv) { minv = t >> 1; minst = t; }
+                t = nxt[cur];
+            }
+            if (t == NIL && (u32)v < (cur >> 1)) {  // complete, and this is the walker from the smaller-index end
+                const bool right = minst & 1u;     // the walk leaves the seed through R: it runs left -> right
+                cur = 2u * (u32)v + d;
+                for (u32 i = 0; i < cnt; i++) {
+                    u32 w = cur >> 1, dw = cur & 1u;
+                    u32 lp = right ? dw ^ 1u : dw;
+                    seed[w] = minv; pos[w] = right ? i : cnt - 1 - i; nlen[w] = cnt; flags[w] = (u8)((lp == 0) | (lp << 1));
+                    cur = nxt[cur];
+                }
+                wrote = cnt;
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) wrote += __shfl_xor_sync(0xffffffffu, wrote, o);
+    if ((threadIdx.x & 31) == 0 && wrote) atomicAdd(written, (u64)wrote);
+}
+
+// rec = (ptr, len, minst, mindist): window of `len` consecutive states starting at s; minst = the
+// state at which the smallest-index k-mer of the window is traversed; mindist = steps from s to it.
+__global__ void pd_init_kernel(const u32* __restrict__ nxt, uint4* __restrict__ rec, u64 n_states) {
+    u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_states) rec[s] = make_uint4(nxt[s], 1u, (u32)s, 0u);
+}
+
+__global__ void derive_seed_kernel(const u32* __restrict__ seed, const u32* __restrict__ nlen, u64 n, int K,
+                                   u32* __restrict__ is_seed, u64* __restrict__ node_len) {
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    bool issd = seed[v] == (u32)v;
+    is_seed[v] = issd;
+    node_len[v] = issd ? (u64)nlen[v] + K - 1 : 0;
 }
 
 __device__ __forceinline__ uint4 pd_combine(uint4 a, uint4 t) {
@@ -167,8 +222,8 @@ __global__ void cyc_round_kernel(const u32* __restrict__ list, u64 n, const uint
 // flags: bit0 fwd (k-mer appears in stored orientation), bit1 left_port (side of the k-mer facing the
 // node's left end: 0 = L, 1 = R).
 __global__ void assign_kernel(const uint4* __restrict__ rec, const u32* __restrict__ nxt, const u8* __restrict__ is_cyc,
-                              u64 n, int K, u32* __restrict__ seed, u32* __restrict__ pos, u32* __restrict__ nlen,
-                              u8* __restrict__ flags, u32* __restrict__ is_seed, u64* __restrict__ node_len) {
+                              u64 n, u32* __restrict__ seed, u32* __restrict__ pos, u32* __restrict__ nlen,
+                              u8* __restrict__ flags) {
     u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     uint4 rl = rec[2 * v], rr = rec[2 * v + 1];
@@ -198,9 +253,6 @@ __global__ void assign_kernel(const uint4* __restrict__ rec, const u32* __restri
         fw = lp == 0;
     }
     seed[v] = sd; pos[v] = ps; nlen[v] = nn; flags[v] = (u8)(fw | (lp << 1));
-    bool issd = sd == (u32)v;
-    is_seed[v] = issd;
-    node_len[v] = issd ? (u64)nn + K - 1 : 0;
 }
 
 // ---- S6 ---------------------------------------------------------------------------------------------------
@@ -319,78 +371,85 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     // ---- S4 ----
     const u64 NS = 2 * V;
     DBuf<u32> nxt;
-    DBuf<uint4> recA, recB;
     DBuf<u64> ctr;
     TRY(nxt.alloc(c, NS));
-    TRY(recA.alloc(c, NS));
-    TRY(recB.alloc(c, NS));
     TRY(ctr.alloc(c, 4));
     TRY(ctr.zero());
     links_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, V, tkeys.p, tidx.p, cap - 1, stranded, nxt.p,
-                                                      recA.p, (u32*)(ctr.p + 3));
+                                                      (u32*)(ctr.p + 3));
     TRY(check_launch(c, "links"));
-    tkeys.release();
-    tidx.release();
     CU(c, cudaEventRecord(c->ev[2], st));
-    // ---- S5: pointer doubling until only cycles stay active ----
-    uint4 *src = recA.p, *dst = recB.p;
-    u64 prev_active = ~0ull, active = 0;
-    int rounds = 0;
-    for (; rounds < 40; rounds++) {
-        CU(c, cudaMemsetAsync(ctr.p, 0, 8, st));
-        pd_round_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, dst, NS, ctr.p);
-        TRY(check_launch(c, "pd_round"));
-        std::swap(src, dst);
-        TRY(read_u64(c, ctr.p, &active));
-        if (active == 0 || active == prev_active) break;
-        prev_active = active;
-    }
-    // one more pass so that states finished in the last round exist in both buffers
-    {
-        CU(c, cudaMemsetAsync(ctr.p, 0, 8, st));
-        pd_round_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, dst, NS, ctr.p);
-        TRY(check_launch(c, "pd_round"));
-        // src stays the authoritative buffer for finished states (dst now mirrors them)
-    }
-    S.rank_rounds = rounds + 1;
-    DBuf<u8> is_cyc;
-    TRY(is_cyc.alloc(c, V));
-    TRY(is_cyc.zero());
-    {
-        u64 h[4];
-        TRY(read_u64(c, ctr.p, h, 4));
-        if (h[3] == 1) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extension points at a k-mer with no extension back (src/compression.rs:428-434)");
-        if (h[3] == 2) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extensions are not reciprocal");
-    }
-    if (active) {
-        DBuf<u32> list;
-        TRY(list.alloc(c, active));
-        CU(c, cudaMemsetAsync(ctr.p + 1, 0, 8, st));
-        cyc_collect_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, NS, nxt.p, list.p, ctr.p + 1, src, dst, is_cyc.p);
-        TRY(check_launch(c, "cyc_collect"));
-        u64 ncs = 0;
-        TRY(read_u64(c, ctr.p + 1, &ncs));
-        int cr = 1;
-        while ((1ull << cr) < ncs) cr++;
-        cr += 1;
-        for (int r = 0; r < cr; r++) {
-            cyc_round_kernel<<<grid_for(ncs, 256), 256, 0, st>>>(list.p, ncs, src, dst);
-            TRY(check_launch(c, "cyc_round"));
-            std::swap(src, dst);
-        }
-        S.n_cycle_kmers = ncs / 2;
-        S.rank_rounds += cr;
-    }
-    CU(c, cudaEventRecord(c->ev[3], st));
-    // ---- S6 ----
+    // ---- S5a: walks for short unitigs ----
     DBuf<u32> seed, pos, nlen, is_seed;
     DBuf<u8> flags;
     DBuf<u64> node_len, node_id, tot;
     TRY(seed.alloc(c, V)); TRY(pos.alloc(c, V)); TRY(nlen.alloc(c, V)); TRY(is_seed.alloc(c, V));
     TRY(flags.alloc(c, V)); TRY(node_len.alloc(c, V)); TRY(node_id.alloc(c, V)); TRY(tot.alloc(c, 2));
-    assign_kernel<<<grid_for(V, 256), 256, 0, st>>>(src, nxt.p, is_cyc.p, V, t->k, seed.p, pos.p, nlen.p, flags.p, is_seed.p, node_len.p);
-    TRY(check_launch(c, "assign"));
-    recA.release(); recB.release(); nxt.release();
+    TRY(nlen.zero());
+    walk_kernel<<<grid_for(V, 256), 256, 0, st>>>(nxt.p, V, 1024u, seed.p, pos.p, nlen.p, flags.p, ctr.p + 2);
+    TRY(check_launch(c, "walk"));
+    {
+        u64 h[4];
+        TRY(read_u64(c, ctr.p, h, 4));
+        if (h[3] == 1) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extension points at a k-mer with no extension back (src/compression.rs:428-434)");
+        if (h[3] == 2) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extensions are not reciprocal");
+        S.rank_rounds = 0;
+        if (h[2] != V) {
+            // ---- S5b: pointer doubling for what the walks left (long unitigs, cycles) ----
+            DBuf<uint4> recA, recB;
+            TRY(recA.alloc(c, NS));
+            TRY(recB.alloc(c, NS));
+            pd_init_kernel<<<grid_for(NS, 256), 256, 0, st>>>(nxt.p, recA.p, NS);
+            TRY(check_launch(c, "pd_init"));
+            uint4 *src = recA.p, *dst = recB.p;
+            u64 prev_active = ~0ull, active = 0;
+            int rounds = 0;
+            for (; rounds < 40; rounds++) {
+                CU(c, cudaMemsetAsync(ctr.p, 0, 8, st));
+                pd_round_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, dst, NS, ctr.p);
+                TRY(check_launch(c, "pd_round"));
+                std::swap(src, dst);
+                TRY(read_u64(c, ctr.p, &active));
+                if (active == 0 || active == prev_active) break;
+                prev_active = active;
+            }
+            // one more pass so that states finished in the last round exist in both buffers
+            CU(c, cudaMemsetAsync(ctr.p, 0, 8, st));
+            pd_round_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, dst, NS, ctr.p);
+            TRY(check_launch(c, "pd_round"));
+            S.rank_rounds = rounds + 1;
+            DBuf<u8> is_cyc;
+            TRY(is_cyc.alloc(c, V));
+            TRY(is_cyc.zero());
+            if (active) {
+                DBuf<u32> list;
+                TRY(list.alloc(c, active));
+                CU(c, cudaMemsetAsync(ctr.p + 1, 0, 8, st));
+                cyc_collect_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, NS, nxt.p, list.p, ctr.p + 1, src, dst, is_cyc.p);
+                TRY(check_launch(c, "cyc_collect"));
+                u64 ncs = 0;
+                TRY(read_u64(c, ctr.p + 1, &ncs));
+                int cr = 1;
+                while ((1ull << cr) < ncs) cr++;
+                cr += 1;
+                for (int r = 0; r < cr; r++) {
+                    cyc_round_kernel<<<grid_for(ncs, 256), 256, 0, st>>>(list.p, ncs, src, dst);
+                    TRY(check_launch(c, "cyc_round"));
+                    std::swap(src, dst);
+                }
+                S.n_cycle_kmers = ncs / 2;
+                S.rank_rounds += cr;
+            }
+            assign_kernel<<<grid_for(V, 256), 256, 0, st>>>(src, nxt.p, is_cyc.p, V, seed.p, pos.p, nlen.p, flags.p);
+            TRY(check_launch(c, "assign"));
+        }
+    }
+    tkeys.release();
+    tidx.release();
+    CU(c, cudaEventRecord(c->ev[3], st));
+    // ---- S6 ----
+    derive_seed_kernel<<<grid_for(V, 256), 256, 0, st>>>(seed.p, nlen.p, V, t->k, is_seed.p, node_len.p);
+    TRY(check_launch(c, "derive_seed"));
     TRY(exclusive_scan_u32_to_u64(c, is_seed.p, node_id.p, V, tot.p));
     TRY(exclusive_scan_u64(c, node_len.p, node_len.p, V, tot.p + 1));
     u64 h[2];
