@@ -192,7 +192,7 @@ static const int T1_NB = TP + 64 + 2 + 32;           // staged bases: left flank
 static const int T1_S32 = T1_NB / 16 + 6;            // staged 2-bit data as u32 in base order
 static const int T1_SC = TP + 64 + 8;                // p-mer scores
 static const int T1_BM = T1_NB / 32 + 4;             // boundary bitmap words
-static const int T1_QN = 128;                        // per-warp ring queue of closed runs (power of two)
+static const int T1_QCAP = TP;                       // CTA queue of closed runs (<= one per k-mer start)
 
 struct TileArgs {
     u64 base0;      // global position of the first base (start[0])
@@ -273,7 +273,7 @@ __device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs
         if (t > lastw) r[t] = 0;
     }
     r[RW - 1] |= hdr;
-    u32 bkt = s_bk[ps];
+    u32 bkt = s_bk[ps + (ps >> 4)];  // padded layout (bkpad)
     if constexpr (RW == 2) {
         *reinterpret_cast<ulonglong2*>(a.rec + slot * 2) = make_ulonglong2(r[0], r[1]);
     } else {
@@ -284,21 +284,20 @@ __device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs
     atomicAdd(&a.bucket_count[bkt], 1u);
 }
 
+__device__ __forceinline__ u32 bkpad(u32 x) { return x + (x >> 4); }  // padded index: lane stride 17 words, conflict-free
+
 template <int W>
 __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, TileArgs ta) {
-    constexpr int RW = RecLayout<W>::WORDS;
     __shared__ __align__(16) u32 s_s32[T1_S32];
     __shared__ __align__(16) u32 s_sc[T1_SC];
-    __shared__ __align__(16) u32 s_bk[TP + 4];
+    __shared__ u32 s_bk[TP + TP / 16 + 8];   // bucket of every k-mer start, padded (bkpad)
     __shared__ u32 s_bm[T1_BM];   // bit b: a sequence starts at staged index b (or the data ends there)
     __shared__ u32 s_vm[T1_BM];   // bit b: a valid k-mer starts at staged index b
-    __shared__ u32 s_queue[T1_WARPS][T1_QN];
+    u32* const s_queue = s_sc;    // closed runs of this tile (start | n << 16); reuses the score array after phase B
+    __shared__ u32 s_qn;
+    __shared__ u64 s_slot0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 lt = (1u << lane) - 1;
     const int K = kp.k, p = a.p, wlen = K - p + 1;
-    const u64 kmask = K >= 2 ? ((K - 1 >= 64) ? ~0ull : ((1ull << (K - 1)) - 1)) : 0;  // boundary bits (b+1 .. b+K-1)
-    u64 chunk_base = 0;
-    u32 chunk_used = WCHUNK;
 
     for (u64 tile = blockIdx.x; tile < ta.n_tiles; tile += gridDim.x) {
         const u64 g0 = ta.base0 + tile * (u64)TP;                 // global position of tile-relative x = 0
@@ -314,10 +313,12 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
             s_s32[2 * t + 1] = (u32)v;
         }
         for (u32 t = tid; t < (u32)T1_BM; t += T1_THREADS) s_bm[t] = 0;
+        if (tid == 0) s_qn = 0;
         __syncthreads();
         if (a.uniform_len) {
-            const u64 L = a.uniform_len;
-            u64 i0 = (sb - ta.base0 + L - 1) / L;
+            const u32 L = a.uniform_len;
+            const u64 rel = sb - ta.base0;
+            u64 i0 = (rel + L - 1) / L;
             for (u64 i = i0 + tid; i <= a.n_seqs; i += T1_THREADS) {
                 u64 g = ta.base0 + i * L;
                 if (g >= sb + nbits) break;
@@ -346,10 +347,26 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
             *reinterpret_cast<uint4*>(&s_sc[q0]) = sc;
         }
         __syncthreads();
-        // ---- validity bitmap: a k-mer at b is valid iff no boundary in (b, b+K) and b lies before the end of data ----
+        // ---- validity bitmap: a k-mer at b is valid iff no boundary in (b, b+K) and b lies before the end of data.
+        // OR over the K-1 following boundary bits by doubling on a 96-bit register window. ----
         for (u32 j = tid; j < (u32)T1_BM - 3; j += T1_THREADS) {
-            u32 inv = 0;
-            for (int d = 1; d < K; d++) inv |= bm_bits32(s_bm, 32 * j + d);
+            u32 w0 = s_bm[j], w1 = s_bm[j + 1], w2 = s_bm[j + 2];
+            // y = boundary bits shifted down by 1 (bit b of y = boundary at b+1)
+            u32 y0 = __funnelshift_r(w0, w1, 1), y1 = __funnelshift_r(w1, w2, 1), y2 = w2 >> 1;
+            int have = 1;            // y covers offsets 1 .. have
+            const int need = K - 1;  // offsets 1 .. K-1
+            while (have * 2 <= need) {
+                int sft = have;      // < 32
+                u32 z0 = __funnelshift_r(y0, y1, sft), z1 = __funnelshift_r(y1, y2, sft), z2 = y2 >> sft;
+                y0 |= z0; y1 |= z1; y2 |= z2;
+                have *= 2;
+            }
+            if (have < need) {
+                int sft = need - have;  // < have <= 32
+                u32 z0 = __funnelshift_r(y0, y1, sft), z1 = __funnelshift_r(y1, y2, sft);
+                y0 |= z0; y1 |= z1;
+            }
+            u32 inv = need > 0 ? y0 : 0;
             u64 endi = ta.total_end - sb;  // staged index of the end of data
             u32 in_range = (u64)32 * j + 32 <= endi ? 0xffffffffu : ((u64)32 * j >= endi ? 0u : ((1u << (endi - 32 * j)) - 1));
             s_vm[j] = ~inv & in_range;
@@ -365,81 +382,98 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
             }
             for (; e < wlen; e++) c = min(c, s_sc[x0 + e]);
             u32 t0 = s_sc[x0 + wlen], t1 = s_sc[x0 + wlen + 1], t2 = s_sc[x0 + wlen + 2];
-            uint4 o;
-            o.x = min(min(f.x, f.y), min(f.z, c)) & a.bucket_mask;
-            o.y = min(min(f.y, f.z), min(c, t0)) & a.bucket_mask;
-            o.z = min(min(f.z, c), min(t0, t1)) & a.bucket_mask;
-            o.w = min(min(c, t0), min(t1, t2)) & a.bucket_mask;
-            *reinterpret_cast<uint4*>(&s_bk[x0]) = o;
+            u32 pb = bkpad(x0);  // x0 % 4 == 0: the four padded indices are consecutive
+            s_bk[pb] = min(min(f.x, f.y), min(f.z, c)) & a.bucket_mask;
+            s_bk[pb + 1] = min(min(f.y, f.z), min(c, t0)) & a.bucket_mask;
+            s_bk[pb + 2] = min(min(f.z, c), min(t0, t1)) & a.bucket_mask;
+            s_bk[pb + 3] = min(min(c, t0), min(t1, t2)) & a.bucket_mask;
         }
         __syncthreads();
-        // ---- phase C: records.  Warp `warp` owns tile positions [seg0, seg1); position seg1 only closes. ----
-        // Flags are warp-uniform 32-bit masks taken from the validity / boundary bitmaps; the only per-lane
-        // work is the bucket comparison.  Closed runs go to a per-warp ring queue and are turned into
-        // records 32 at a time, so the (long) record assembly always runs with full lanes.
-        const u32 seg0 = warp * T1_SEG, seg1 = seg0 + T1_SEG;
-        int last_start = (int)seg0;
-        u32 carry_valid = 0;
-        u32 qhead = 0, qtail = 0;
-        u32* queue = s_queue[warp];
-        for (u32 gx = seg0; gx <= seg1; gx += 32) {
-            const u32 x = gx + lane;
-            const u32 b0 = ofs + gx;
-            const bool lastg = gx == seg1;
-            u32 vm = lastg ? 0u : bm_bits32(s_vm, b0);
-            u32 fm = bm_bits32(s_bm, b0);
-            u32 pv = (vm << 1) | carry_valid;
-            carry_valid = vm >> 31;
-            bool diff = !lastg && x > seg0 && s_bk[x] != s_bk[x - 1];
-            u32 dm = __ballot_sync(0xffffffffu, diff);
-            u32 start = vm & (fm | ~pv | dm | (gx == seg0 ? 1u : 0u));
-            u32 closer = ~vm & pv & (lastg ? 1u : 0xffffffffu);
+        // ---- phase C: runs.  Warp `warp` owns tile positions [seg0, seg0 + 512); lane owns 16 consecutive
+        // positions and works on 16/17-bit masks: valid, first-of-sequence, bucket-differs.  A set bit in
+        // `smask` starts a run or (first invalid position after a run) closes one; bit 16 of the last lane is
+        // the virtual closer at the segment end.  Closed runs go to the CTA queue. ----
+        {
+            const u32 seg0 = warp * T1_SEG;
+            const u32 x0 = seg0 + 16 * lane;
+            const u32 b0 = ofs + x0;
+            u32 vm = bm_bits32(s_vm, b0) & 0xffffu;
+            u32 fm = bm_bits32(s_bm, b0) & 0xffffu;
+            u32 dm = 0;
+            {
+                u32 prevb = s_bk[bkpad(x0 ? x0 - 1 : 0)];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    u32 cur = s_bk[bkpad(x0 + i)];
+                    dm |= (cur != prevb ? 1u : 0u) << i;
+                    prevb = cur;
+                }
+            }
+            u32 up = __shfl_up_sync(0xffffffffu, vm, 1);
+            u32 pv = (vm << 1) | (lane ? (up >> 15) & 1u : 0u);           // bits 0..16: valid(x-1)
+            u32 start = vm & (fm | ~pv | dm | (lane == 0 ? 1u : 0u));
+            u32 closer = ~vm & pv & (lane == 31 ? 0x1ffffu : 0xffffu);    // bit 16 (x = seg end) only for the last lane
             u32 smask = start | closer;
-            if (smask) {
-                u32 cmask = smask & pv;  // set bits whose left neighbour is a valid k-mer close the run [prev, x)
-                bool closes = (cmask >> lane) & 1u;
-                u32 lower = smask & lt;
-                int prev = lower ? (int)gx + 31 - __clz(lower) : last_start;
-                int n = closes ? (int)x - prev : 0;
-                u32 multi = __ballot_sync(0xffffffffu, n > a.maxk);
-                if (!multi) {
-                    if (closes) queue[(qtail + __popc(cmask & lt)) & (T1_QN - 1)] = (u32)prev | ((u32)n << 16);
-                    qtail += __popc(cmask);
-                } else {  // rare: a run longer than one record is cut into pieces of maxk k-mers
-                    u32 nrec = closes ? (u32)((n + a.maxk - 1) / a.maxk) : 0;
-                    u32 inc = nrec;
-    #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                    u32 rank = inc - nrec;
-                    for (u32 r = 0; r < nrec; r++) {
-                        int ps = prev + (int)r * a.maxk;
-                        queue[(qtail + rank + r) & (T1_QN - 1)] = (u32)ps | ((u32)min(a.maxk, (int)x - ps) << 16);
+            u32 cmask = smask & pv;
+            // carry: position of the last set bit of smask in any lower lane
+            int mylast = smask ? (int)x0 + 31 - __clz(smask) : -1;
+            int carry = mylast;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, carry, o); if (lane >= o) carry = max(carry, t); }
+            carry = __shfl_up_sync(0xffffffffu, carry, 1);
+            if (lane == 0) carry = (int)seg0;
+            // records this lane will push (runs longer than maxk are cut)
+            u32 nrec = 0;
+            {
+                u32 m = cmask;
+                int pr = carry;
+                u32 sm = smask;
+                while (m) {
+                    int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    u32 lower = sm & ((1u << bit) - 1);
+                    int prev = lower ? (int)x0 + 31 - __clz(lower) : pr;
+                    int n = (int)x0 + bit - prev;
+                    nrec += n <= a.maxk ? 1u : (u32)((n + a.maxk - 1) / a.maxk);
+                }
+            }
+            u32 inc = nrec;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            u32 wtotal = __shfl_sync(0xffffffffu, inc, 31);
+            u32 wbase = 0;
+            if (lane == 0 && wtotal) wbase = atomicAdd(&s_qn, wtotal);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            u32 qpos = wbase + inc - nrec;
+            {
+                u32 m = cmask;
+                while (m) {
+                    int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    u32 lower = smask & ((1u << bit) - 1);
+                    int prev = lower ? (int)x0 + 31 - __clz(lower) : carry;
+                    int xe = (int)x0 + bit;
+                    for (int ps = prev; ps < xe; ps += a.maxk) {
+                        if (qpos < (u32)T1_QCAP) s_queue[qpos] = (u32)ps | ((u32)min(a.maxk, xe - ps) << 16);
+                        qpos++;
                     }
-                    qtail += __shfl_sync(0xffffffffu, inc, 31);
                 }
-                last_start = (int)gx + 31 - __clz(smask);
             }
-            __syncwarp();
-            // drain full batches (and everything at the end of the segment)
-            while (qtail - qhead >= 32 || (lastg && qtail != qhead)) {
-                u32 cnt = min(qtail - qhead, 32u);
-                if (chunk_used + cnt > (u32)WCHUNK) {
-                    u64 cb = 0;
-                    if (lane == 0) cb = atomicAdd(a.cursor, (u64)WCHUNK);
-                    chunk_base = __shfl_sync(0xffffffffu, cb, 0);
-                    chunk_used = 0;
-                    if (chunk_base + WCHUNK > a.capacity && lane == 0) *a.overflow = 1;
-                }
-                if ((u32)lane < cnt) {
-                    u32 ent = queue[(qhead + lane) & (T1_QN - 1)];
-                    u64 slot = chunk_base + chunk_used + lane;
-                    if (slot < a.capacity)
-                        tile_emit_record<W>(a, ta, K, s_s32, s_bm, s_bk, sb, ofs, (int)(ent & 0xffffu), (int)(ent >> 16), slot);
-                }
-                chunk_used += cnt;
-                qhead += cnt;
-                __syncwarp();
-            }
+        }
+        __syncthreads();
+        // ---- phase D: one exact reservation per tile, then one thread per record ----
+        const u32 nq = s_qn;
+        if (tid == 0) {
+            u64 s0 = nq ? atomicAdd(a.cursor, (u64)nq) : 0;
+            s_slot0 = s0;
+            if (s0 + nq > a.capacity || nq > (u32)T1_QCAP) *a.overflow = 1;
+        }
+        __syncthreads();
+        const u64 slot0 = s_slot0;
+        for (u32 q = tid; q < nq && q < (u32)T1_QCAP; q += T1_THREADS) {
+            u32 ent = s_queue[q];
+            if (slot0 + q < a.capacity)
+                tile_emit_record<W>(a, ta, K, s_s32, s_bm, s_bk, sb, ofs, (int)(ent & 0xffffu), (int)(ent >> 16), slot0 + q);
         }
     }
 }
