@@ -174,6 +174,8 @@ int dbg_ctx_set_param(dbg_ctx* ctx, const char* name, int64_t value) {
     } else if (!strcmp(name, "bucket_occ")) {
         if (value < 0) DBG_SET_ERR(c, DBG_E_BADARG, "bucket_occ must be >= 0");
         c->target_bucket_occ = (int)value;
+    } else if (!strcmp(name, "dedup")) {
+        c->dedup = value != 0;
     } else {
         DBG_SET_ERR(c, DBG_E_BADARG, "unknown parameter %s", name);
     }

@@ -508,7 +508,8 @@ template <> struct P2Cfg<1> { static const int CAP = 8192; };  // 8 B key + 4 B 
 template <> struct P2Cfg<2> { static const int CAP = 4096; };  // 16 B key + 4 B val = 80 KB
 
 struct P2Args {
-    const u64* rec; const u64* bucket_off; u32 n_buckets;
+    u64* rec; u32* mult;  // records (deduplicated in place per bucket when mult != nullptr) and their multiplicities
+    const u64* bucket_off; u32 n_buckets;
     u32 min_obs; int stranded; int report_all;
     u64* out_lo; u64* out_hi; u32* out_val; u64 cap_valid;
     u64* all_lo; u64* all_hi; u64 cap_all;
@@ -590,8 +591,82 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
         __syncthreads();
         const u32 b = s_bucket;
         if (b >= a.n_buckets) break;
-        const u64 r0 = a.bucket_off[b], r1 = a.bucket_off[b + 1];
+        const u64 r0 = a.bucket_off[b];
+        u64 r1 = a.bucket_off[b + 1];
         if (r0 == r1) continue;
+        if constexpr (W == 1) {
+            if (a.mult) {
+                // ---- P2a: deduplicate this bucket's records.  At sequencing coverage c most super-k-mers of a
+                // genomic site occur ~c/2 times byte-identically; each distinct record is expanded once below and
+                // its k-mers are counted with the record's multiplicity.  The 16-byte records are hashed into a
+                // table that borrows the (not yet used) k-mer table memory; distinct records are written back
+                // over the front of the bucket's own range (never ahead of what has been read). ----
+                constexpr int RCAP = 4096;
+                Kmer<2>* rkeys = reinterpret_cast<Kmer<2>*>(smem_raw);
+                u32* rcnt = reinterpret_cast<u32*>(smem_raw + sizeof(Kmer<2>) * RCAP);
+                u64 dbase = 0;
+                for (u64 c0 = r0; c0 < r1; c0 += RCAP / 2) {
+                    const u32 nrc = (u32)min((u64)(RCAP / 2), r1 - c0);
+                    for (int i = threadIdx.x; i < RCAP; i += P2_THREADS) {
+                        reinterpret_cast<u64*>(rkeys)[2 * i] = ~0ull;
+                        reinterpret_cast<u64*>(rkeys)[2 * i + 1] = ~0ull;
+                        rcnt[i] = 0;
+                    }
+                    __syncthreads();
+                    for (u32 i = threadIdx.x; i < nrc; i += P2_THREADS) {
+                        ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(a.rec + (c0 + i) * 2));
+                        Kmer<2> key{v.x, v.y};
+                        u32 slot = Ops<2>::hash32(key) >> 8 & (RCAP - 1);
+                        const Kmer<2> empty{~0ull, ~0ull};
+                        for (;;) {
+                            volatile u64* kp2 = reinterpret_cast<volatile u64*>(rkeys + slot);
+                            if (kp2[0] == key.lo && kp2[1] == key.hi) break;
+                            Kmer<2> old = cas128_shared(rkeys + slot, empty, key);
+                            if ((old.lo == ~0ull && old.hi == ~0ull) || (old.lo == key.lo && old.hi == key.hi)) break;
+                            slot = (slot + 1) & (RCAP - 1);
+                        }
+                        atomicAdd(&rcnt[slot], 1u);
+                    }
+                    __syncthreads();
+                    // compact: RCAP / P2_THREADS consecutive slots per thread
+                    u32 mine = 0;
+#pragma unroll
+                    for (int j = 0; j < RCAP / P2_THREADS; j++) mine += rcnt[threadIdx.x * (RCAP / P2_THREADS) + j] != 0;
+                    {
+                        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                        u32 inc = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                        if (lane == 31) s_wsum[warp] = inc;
+                        __syncthreads();
+                        if (warp == 0) {
+                            u32 w = lane < P2_THREADS / 32 ? s_wsum[lane] : 0, winc = w;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+                            s_wsum[lane] = winc - w;
+                            if (lane == 31) s_pref[P2_RC] = winc;
+                        }
+                        __syncthreads();
+                        u64 o = r0 + dbase + s_wsum[warp] + inc - mine;
+#pragma unroll
+                        for (int j = 0; j < RCAP / P2_THREADS; j++) {
+                            int sl = threadIdx.x * (RCAP / P2_THREADS) + j;
+                            u32 cnt = rcnt[sl];
+                            if (cnt) {
+                                *reinterpret_cast<ulonglong2*>(a.rec + o * 2) = make_ulonglong2(rkeys[sl].lo, rkeys[sl].hi);
+                                a.mult[o] = cnt;
+                                o++;
+                            }
+                        }
+                        dbase += s_pref[P2_RC];
+                    }
+                    __syncthreads();
+                }
+                r1 = r0 + dbase;
+                __threadfence_block();
+                __syncthreads();
+            }
+        }
         while (s_nstack > 0) {
             __syncthreads();
             const u32 top = s_stack[s_nstack - 1];
@@ -617,7 +692,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
 #pragma unroll
                     for (int j = 0; j < P2_RC / P2_THREADS; j++) {
                         u32 idx = threadIdx.x * (P2_RC / P2_THREADS) + j;
-                        cnt[j] = idx < nrc ? ((u32)__ldg(a.rec + (c0 + idx) * RW + (RW - 1)) >> 8) & 63u : 0;
+                        cnt[j] = idx < nrc ? ((u32)__ldcg(a.rec + (c0 + idx) * RW + (RW - 1)) >> 8) & 63u : 0;
                         sum += cnt[j];
                     }
                     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -655,15 +730,17 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                     u64 s[RW], nx[RW];
                     {
                         const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.rec + (c0 + ri) * RW);
-                        ulonglong2 v0 = __ldg(src);
+                        ulonglong2 v0 = __ldcg(src);   // L2 path: records may have been rewritten by this CTA (dedup)
                         s[0] = v0.x; s[1] = v0.y;
-                        if constexpr (RW == 4) { ulonglong2 v1 = __ldg(src + 1); s[2] = v1.x; s[RW - 1] = v1.y; }
+                        if constexpr (RW == 4) { ulonglong2 v1 = __ldcg(src + 1); s[2] = v1.x; s[RW - 1] = v1.y; }
                         const u64 rnx = min(c0 + ri + 1, r1 - 1);
                         const ulonglong2* srn = reinterpret_cast<const ulonglong2*>(a.rec + rnx * RW);
-                        ulonglong2 n0 = __ldg(srn);
+                        ulonglong2 n0 = __ldcg(srn);
                         nx[0] = n0.x; nx[1] = n0.y;
-                        if constexpr (RW == 4) { ulonglong2 n1 = __ldg(srn + 1); nx[2] = n1.x; nx[RW - 1] = n1.y; }
+                        if constexpr (RW == 4) { ulonglong2 n1 = __ldcg(srn + 1); nx[2] = n1.x; nx[RW - 1] = n1.y; }
                     }
+                    u32 mcur = a.mult ? __ldcg(a.mult + c0 + ri) : 1u;
+                    u32 mnx = a.mult ? __ldcg(a.mult + min(c0 + ri + 1, r1 - 1)) : 1u;
                     u32 hdr = (u32)s[RW - 1] & 0x3fffu;
                     int n = (int)(hdr >> 8);
                     u32 rn = (hdr >> 4) & 0xfu, ln = hdr & 0xfu;
@@ -713,14 +790,22 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                             if constexpr (W == 1) special = key.lo == ~0ull;
                             else special = key.lo == ~0ull && key.hi == ~0ull;
                             if (special) {  // all-T k-mer at K = 32/64 stranded collides with the EMPTY sentinel
-                                atomicAdd(&s_sp_cnt, 1u);
+                                atomicAdd(&s_sp_cnt, mcur);
                                 atomicOr(&s_sp_exts, e);
                             } else {
                                 int slot = tab.find_or_insert(key, h, CAP);
                                 if (slot < 0) { s_overflow = 1; break; }
                                 u32 v = *reinterpret_cast<volatile u32*>(vals + slot);
                                 if (e & ~v) atomicOr(vals + slot, e);
-                                if ((v >> 8) < 65535u) atomicAdd(vals + slot, 256u);  // saturating count, filter.rs:57
+                                // saturating count (filter.rs:57): stop adding once 65535 is reached; steps of <= 255
+                                // keep the transient overshoot far below the 24-bit field
+                                for (u32 rem = mcur;;) {
+                                    u32 stp = min(rem, 255u);
+                                    if ((v >> 8) < 65535u) atomicAdd(vals + slot, stp << 8);
+                                    rem -= stp;
+                                    if (!rem) break;
+                                    v = *reinterpret_cast<volatile u32*>(vals + slot);
+                                }
                             }
                         }
                         t++;
@@ -734,6 +819,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                         } else {      // next record
                             ri++;
                             t = 0;
+                            mcur = mnx;
+                            mnx = a.mult ? __ldcg(a.mult + min(c0 + ri + 1, r1 - 1)) : 1u;
 #pragma unroll
                             for (int q = 0; q < RW; q++) s[q] = nx[q];
                             hdr = (u32)s[RW - 1] & 0x3fffu;
@@ -749,9 +836,9 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                             rcv = Ops<W>::rc(kp, fwd);
                             const u64 rnx = min(c0 + ri + 1, r1 - 1);
                             const ulonglong2* srn = reinterpret_cast<const ulonglong2*>(a.rec + rnx * RW);
-                            ulonglong2 n0 = __ldg(srn);
+                            ulonglong2 n0 = __ldcg(srn);
                             nx[0] = n0.x; nx[1] = n0.y;
-                            if constexpr (RW == 4) { ulonglong2 n1 = __ldg(srn + 1); nx[2] = n1.x; nx[RW - 1] = n1.y; }
+                            if constexpr (RW == 4) { ulonglong2 n1 = __ldcg(srn + 1); nx[2] = n1.x; nx[RW - 1] = n1.y; }
                         }
                     }
                 }
@@ -1044,10 +1131,12 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         TRY(a_lo.alloc(c, cap_all));
         if (W == 2) TRY(a_hi.alloc(c, cap_all));
     }
+    DBuf<u32> mult;
+    if (W == 1 && c->dedup) TRY(mult.alloc(c, n_rec));
     TRY(ctr.zero());
     {
         P2Args a;
-        a.rec = rec.p; a.bucket_off = bucket_off.p; a.n_buckets = NB;
+        a.rec = rec.p; a.mult = (W == 1 && c->dedup) ? mult.p : nullptr; a.bucket_off = bucket_off.p; a.n_buckets = NB;
         a.min_obs = min_obs; a.stranded = stranded; a.report_all = report_all;
         a.out_lo = v_lo.p; a.out_hi = v_hi.p; a.out_val = v_val.p; a.cap_valid = cap_valid;
         a.all_lo = a_lo.p; a.all_hi = a_hi.p; a.cap_all = cap_all;

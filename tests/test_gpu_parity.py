@@ -181,6 +181,17 @@ def test_bucket_split_path(D, ctx, orc):
     c2.close()
 
 
+def test_record_dedup_off(D, ctx, orc):
+    """The per-bucket super-k-mer deduplication is an optimisation only: same bits with it switched off."""
+    c2 = D.Context(0)
+    c2.set_param("dedup", 0)
+    ss = orc.synth_reads(3000, 1, orc.ERR_THR_NOISY)
+    run_both(D, c2, orc, 31, ss, 2, report_all=True)
+    seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")
+    run_both(D, c2, orc, 31, orc.seqset_from_lists([seq] * 70000), 1)
+    c2.close()
+
+
 def test_compress_kmers_slice_variant(D, ctx, orc):
     """compression::compress_kmers (src/compression.rs:598-615): unordered (k-mer, (exts, data)) slice."""
     ss = orc.synth_reads(1500, 1, orc.ERR_THR_NOISY)
