@@ -63,6 +63,7 @@ typedef struct {
     uint32_t msp_p, bucket_bits;
     float ms_k_partition, ms_k_count; /* the two dominant kernels alone (events right around the launch) */
     float ms_filter_total, ms_compress_total;
+    uint64_t n_records_distinct; /* super-k-mer records left after per-bucket deduplication (0 = dedup off) */
 } dbg_stats;
 
 /* ---- context ------------------------------------------------------------------------------------ */

@@ -27,7 +27,8 @@ class Stats(C.Structure):
                 [(n, C.c_float) for n in ("ms_partition", "ms_count", "ms_sort", "ms_table", "ms_links", "ms_rank",
                                           "ms_emit")] +
                 [("msp_p", C.c_uint32), ("bucket_bits", C.c_uint32)] +
-                [(n, C.c_float) for n in ("ms_k_partition", "ms_k_count", "ms_filter_total", "ms_compress_total")])
+                [(n, C.c_float) for n in ("ms_k_partition", "ms_k_count", "ms_filter_total", "ms_compress_total")] +
+                [("n_records_distinct", C.c_uint64)])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

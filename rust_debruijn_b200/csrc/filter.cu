@@ -662,6 +662,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                     }
                     __syncthreads();
                 }
+                if (threadIdx.x == 0) atomicAdd(&a.counters[5], dbase);
                 r1 = r0 + dbase;
                 __threadfence_block();
                 __syncthreads();
@@ -1149,8 +1150,9 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         TRY(check_launch(c, "count_kernel"));
         CU(c, cudaEventRecord(c->ev[11], st));
     }
-    u64 h[5];
-    TRY(read_u64(c, ctr.p, h, 5));
+    u64 h[6];
+    TRY(read_u64(c, ctr.p, h, 6));
+    S.n_records_distinct = h[5];
     if (h[4]) DBG_SET_ERR(c, DBG_E_INTERNAL, "count_kernel failed (code %llu)", (unsigned long long)h[4]);
     u64 V = h[1], U = h[2];
     S.n_valid = V;
