@@ -122,53 +122,74 @@ int exclusive_scan_u64(Ctx* c, const u64* in, u64* out, u64 n, u64* d_total) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// LSD radix sort, 8-bit digits.  Per pass: upsweep (per-tile digit counts, digit-major), one exclusive
-// scan over the 256 x ntiles count matrix (gives every (digit, tile) its global base directly), and a
-// downsweep that ranks with warp match_any (stable) and scatters.
+// LSD radix sort, 8-bit digits, "onesweep" form: one kernel computes the digit histograms of every
+// pass (they do not depend on the order), then each pass is a single kernel: tiles are taken in
+// order from an atomic counter, ranked with warp match_any (stable), their per-digit counts chained
+// through a decoupled look-back, and the tile is scattered through shared memory so that the global
+// stores of each digit run are contiguous.  2 x 12 bytes per key per pass instead of 3 reads + 1 write.
 // ------------------------------------------------------------------------------------------------
-static const int RS_THREADS = 256;
-static const int RS_WARPS = RS_THREADS / 32;
-static const int RS_ITEMS = 8;                       // rounds per warp
-static const int RS_TILE = RS_THREADS * RS_ITEMS;    // 2048 keys per CTA
-static const int RS_WARP_SEG = 32 * RS_ITEMS;        // contiguous keys per warp
+static const int OS_THREADS = 512;
+static const int OS_WARPS = OS_THREADS / 32;
+static const int OS_ITEMS = 8;
+static const int OS_TILE = OS_THREADS * OS_ITEMS;  // 4096 keys per CTA
+static const int OS_SEG = 32 * OS_ITEMS;           // contiguous keys per warp
+static const u64 OS_FLAG_AGG = 1ull << 62, OS_FLAG_PREFIX = 2ull << 62, OS_VAL_MASK = (1ull << 62) - 1;
 
-__device__ __forceinline__ u32 digit_of(const u64* __restrict__ lo, const u64* __restrict__ hi, u64 i, int d) {
-    return d < 8 ? (u32)(lo[i] >> (8 * d)) & 0xffu : (u32)(hi[i] >> (8 * (d - 8))) & 0xffu;
-}
-
-__global__ void __launch_bounds__(RS_THREADS) rs_upsweep(const u64* __restrict__ lo, const u64* __restrict__ hi, u64 n,
-                                                         u32 ntiles, int d, u32* __restrict__ counts) {
-    __shared__ u32 hist[256];
-    hist[threadIdx.x] = 0;
+__global__ void __launch_bounds__(512) rs_hist_kernel(const u64* __restrict__ lo, const u64* __restrict__ hi, u64 n, int passes,
+                                                      u64* __restrict__ ghist) {
+    __shared__ u32 h[16 * 256];
+    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) h[i] = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 wbase = (u64)blockIdx.x * RS_TILE + (u64)warp * RS_WARP_SEG;
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        u64 i = wbase + r * 32 + lane;
-        u32 dg = i < n ? digit_of(lo, hi, i, d) : 0xffffffffu;
-        u32 peers = __match_any_sync(0xffffffffu, dg);
-        if (dg != 0xffffffffu && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&hist[dg], __popc(peers));
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 l = lo[i], hh = passes > 8 ? hi[i] : 0;
+        for (int d = 0; d < passes; d++) {
+            u32 dg = d < 8 ? (u32)(l >> (8 * d)) & 0xffu : (u32)(hh >> (8 * (d - 8))) & 0xffu;
+            atomicAdd(&h[d * 256 + dg], 1u);
+        }
     }
     __syncthreads();
-    counts[(u64)threadIdx.x * ntiles + blockIdx.x] = hist[threadIdx.x];
+    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x)
+        if (h[i]) atomicAdd(&ghist[i], (u64)h[i]);
+}
+
+__global__ void rs_hist_scan_kernel(u64* ghist, int passes) {  // one warp per pass: exclusive scan of 256 counters
+    int d = blockIdx.x, lane = threadIdx.x;
+    if (d >= passes) return;
+    u64 carry = 0;
+    for (int c = 0; c < 8; c++) {
+        u64 v = ghist[d * 256 + c * 32 + lane], inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        ghist[d * 256 + c * 32 + lane] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
 }
 
 template <int W>
-__global__ void __launch_bounds__(RS_THREADS) rs_downsweep(const u64* __restrict__ lo, const u64* __restrict__ hi,
-                                                           const u32* __restrict__ val, u64* __restrict__ olo,
-                                                           u64* __restrict__ ohi, u32* __restrict__ oval, u64 n,
-                                                           u32 ntiles, int d, const u64* __restrict__ base) {
-    __shared__ u64 woff[RS_WARPS][256];
-    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&woff[0][0])[i] = 0;
+__global__ void __launch_bounds__(OS_THREADS) rs_onesweep(const u64* __restrict__ lo, const u64* __restrict__ hi,
+                                                          const u32* __restrict__ val, u64* __restrict__ olo,
+                                                          u64* __restrict__ ohi, u32* __restrict__ oval, u64 n, int d,
+                                                          const u64* __restrict__ gbase, u64* status, u32* tile_counter) {
+    extern __shared__ __align__(16) unsigned char os_smem[];
+    u64* s_lo = reinterpret_cast<u64*>(os_smem);
+    u64* s_hi = s_lo + (W == 2 ? OS_TILE : 0);
+    u32* s_val = reinterpret_cast<u32*>(s_hi + OS_TILE);
+    __shared__ u32 whist[OS_WARPS][256];
+    __shared__ u32 dstart[256];
+    __shared__ u64 gpos[256];
+    __shared__ u32 s_wsum[8];
+    __shared__ u32 s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    for (int i = threadIdx.x; i < OS_WARPS * 256; i += OS_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();
+    const u32 tile = s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = (1u << lane) - 1;
-    u64 wbase = (u64)blockIdx.x * RS_TILE + (u64)warp * RS_WARP_SEG;
-    u64 klo[RS_ITEMS], khi[RS_ITEMS];
-    u32 kv[RS_ITEMS], rank[RS_ITEMS], dgt[RS_ITEMS];
+    const u64 tbase = (u64)tile * OS_TILE, wbase = tbase + (u64)warp * OS_SEG;
+    u64 klo[OS_ITEMS], khi[OS_ITEMS];
+    u32 kv[OS_ITEMS], rank[OS_ITEMS], dgt[OS_ITEMS];
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
+    for (int r = 0; r < OS_ITEMS; r++) {
         u64 i = wbase + r * 32 + lane;
         bool act = i < n;
         klo[r] = act ? lo[i] : 0;
@@ -177,31 +198,67 @@ __global__ void __launch_bounds__(RS_THREADS) rs_downsweep(const u64* __restrict
         u32 dg = act ? (d < 8 ? (u32)(klo[r] >> (8 * d)) & 0xffu : (u32)(khi[r] >> (8 * (d - 8))) & 0xffu) : 0xffffffffu;
         dgt[r] = dg;
         u32 peers = __match_any_sync(0xffffffffu, dg);
-        u32 before = act ? (u32)woff[warp][dg] : 0;
+        u32 before = act ? whist[warp][dg] : 0;
         rank[r] = before + __popc(peers & lt);
         __syncwarp();
-        if (act && (peers & lt) == 0) woff[warp][dg] = before + __popc(peers);
+        if (act && (peers & lt) == 0) whist[warp][dg] = before + __popc(peers);
         __syncwarp();
     }
     __syncthreads();
-    {   // digit = threadIdx.x: exclusive prefix over the warps of this tile + global base
-        u64 run = base[(u64)threadIdx.x * ntiles + blockIdx.x];
+    // digit totals of the tile (thread = digit), per-warp exclusive offsets, tile-local digit starts
+    u32 cnt = 0;
+    if (threadIdx.x < 256) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) {
-            u64 cnt = woff[w][threadIdx.x];
-            woff[w][threadIdx.x] = run;
-            run += cnt;
+        for (int w = 0; w < OS_WARPS; w++) { u32 c = whist[w][threadIdx.x]; whist[w][threadIdx.x] = cnt; cnt += c; }
+        // publish the aggregate right away so later tiles can move on
+        u64 st = (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | cnt;
+        *reinterpret_cast<volatile u64*>(&status[(u64)tile * 256 + threadIdx.x]) = st;
+        u32 inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_wsum[warp] = inc;
+        dstart[threadIdx.x] = inc - cnt;  // warp-local exclusive; fixed up after the barrier
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        u32 add = 0;
+        for (int w = 0; w < warp; w++) add += s_wsum[w];
+        u32 ds = dstart[threadIdx.x] + add;
+        // decoupled look-back over the preceding tiles for this digit
+        u64 excl = 0;
+        if (tile > 0) {
+            for (long long tt = (long long)tile - 1; tt >= 0; tt--) {
+                u64 v;
+                do { v = *reinterpret_cast<volatile u64*>(&status[(u64)tt * 256 + threadIdx.x]); } while ((v >> 62) == 0);
+                excl += v & OS_VAL_MASK;
+                if ((v >> 62) == 2) break;
+            }
+            *reinterpret_cast<volatile u64*>(&status[(u64)tile * 256 + threadIdx.x]) = OS_FLAG_PREFIX | (excl + cnt);
+        }
+        __syncwarp();
+        dstart[threadIdx.x] = ds;
+        gpos[threadIdx.x] = gbase[threadIdx.x] + excl - ds;
+    }
+    __syncthreads();
+    // stage the tile in digit order
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; r++) {
+        if (dgt[r] != 0xffffffffu) {
+            u32 li = dstart[dgt[r]] + whist[warp][dgt[r]] + rank[r];
+            s_lo[li] = klo[r];
+            if (W == 2) s_hi[li] = khi[r];
+            s_val[li] = kv[r];
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        if (dgt[r] != 0xffffffffu) {
-            u64 pos = woff[warp][dgt[r]] + rank[r];
-            olo[pos] = klo[r];
-            if (W == 2) ohi[pos] = khi[r];
-            oval[pos] = kv[r];
-        }
+    const u32 tcount = (u32)min((u64)OS_TILE, n - tbase);
+    for (u32 i = threadIdx.x; i < tcount; i += OS_THREADS) {
+        u64 l = s_lo[i], h = W == 2 ? s_hi[i] : 0;
+        u32 dg = d < 8 ? (u32)(l >> (8 * d)) & 0xffu : (u32)(h >> (8 * (d - 8))) & 0xffu;
+        u64 pos = gpos[dg] + i;
+        olo[pos] = l;
+        if (W == 2) ohi[pos] = h;
+        oval[pos] = s_val[i];
     }
 }
 
@@ -210,22 +267,31 @@ int radix_sort_pairs(Ctx* c, int W, int key_bits, u64 n, u64* lo_a, u64* hi_a, u
     *res_lo = lo_a; *res_hi = hi_a; *res_val = val_a;
     if (n <= 1) return DBG_OK;
     int passes = (key_bits + 7) / 8;
-    u32 ntiles = (u32)((n + RS_TILE - 1) / RS_TILE);
-    DBuf<u32> counts;
-    DBuf<u64> base;
-    TRY(counts.alloc(c, (u64)256 * ntiles));
-    TRY(base.alloc(c, (u64)256 * ntiles));
+    u32 ntiles = (u32)((n + OS_TILE - 1) / OS_TILE);
+    DBuf<u64> ghist, status;
+    DBuf<u32> tctr;
+    TRY(ghist.alloc(c, 16 * 256));
+    TRY(ghist.zero());
+    TRY(status.alloc(c, (u64)ntiles * 256));
+    TRY(tctr.alloc(c, 16));
+    TRY(tctr.zero());
+    u32 hgrid = (u32)std::min<u64>((n + 511) / 512, (u64)c->sm_count * 4);
+    rs_hist_kernel<<<hgrid, 512, 0, c->stream>>>(lo_a, hi_a, n, passes, ghist.p);
+    TRY(check_launch(c, "rs_hist"));
+    rs_hist_scan_kernel<<<passes, 32, 0, c->stream>>>(ghist.p, passes);
+    TRY(check_launch(c, "rs_hist_scan"));
+    size_t smem = (size_t)OS_TILE * (W == 2 ? 20 : 12);
+    if (W == 1) CU(c, cudaFuncSetAttribute(rs_onesweep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CU(c, cudaFuncSetAttribute(rs_onesweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     u64 *slo = lo_a, *shi = hi_a, *dlo = lo_b, *dhi = hi_b;
     u32 *sv = val_a, *dv = val_b;
     for (int d = 0; d < passes; d++) {
-        rs_upsweep<<<ntiles, RS_THREADS, 0, c->stream>>>(slo, shi, n, ntiles, d, counts.p);
-        TRY(check_launch(c, "rs_upsweep"));
-        TRY(exclusive_scan_u32_to_u64(c, counts.p, base.p, (u64)256 * ntiles, nullptr));
+        TRY(status.zero());
         if (W == 1)
-            rs_downsweep<1><<<ntiles, RS_THREADS, 0, c->stream>>>(slo, shi, sv, dlo, dhi, dv, n, ntiles, d, base.p);
+            rs_onesweep<1><<<ntiles, OS_THREADS, smem, c->stream>>>(slo, shi, sv, dlo, dhi, dv, n, d, ghist.p + d * 256, status.p, tctr.p + d);
         else
-            rs_downsweep<2><<<ntiles, RS_THREADS, 0, c->stream>>>(slo, shi, sv, dlo, dhi, dv, n, ntiles, d, base.p);
-        TRY(check_launch(c, "rs_downsweep"));
+            rs_onesweep<2><<<ntiles, OS_THREADS, smem, c->stream>>>(slo, shi, sv, dlo, dhi, dv, n, d, ghist.p + d * 256, status.p, tctr.p + d);
+        TRY(check_launch(c, "rs_onesweep"));
         std::swap(slo, dlo);
         std::swap(shi, dhi);
         std::swap(sv, dv);
