@@ -233,9 +233,8 @@ def main():
 
     def e2e_step():
         gh = C.c_void_p()
-        ctx.check(L.dbg_reads_to_graph_host(ctx._h, K, C.c_void_p(words_pinned.ctypes.data), len(words_pinned),
-                                            C.c_void_p(hs.ctypes.data), C.c_void_p(hl.ctypes.data), None, len(hs),
-                                            MIN_OBS, 0, D.SAT_ADD, None, C.byref(gh)))
+        ctx.check(L.dbg_reads_to_graph_host_uniform(ctx._h, K, C.c_void_p(words_pinned.ctypes.data), len(words_pinned),
+                                                    len(hs), 150, None, MIN_OBS, 0, D.SAT_ADD, None, C.byref(gh)))
         m, nw = L.dbg_graph_len(gh), L.dbg_graph_n_words(gh)
         assert m <= cap_nodes and nw <= cap_words
         ctx.check(L.dbg_graph_copy_out(gh, C.c_void_p(out_bufs["words"].data_ptr()), C.c_void_p(out_bufs["start"].data_ptr()),

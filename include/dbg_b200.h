@@ -83,6 +83,10 @@ void* dbg_ctx_stream(dbg_ctx* ctx);
  * for the duration of the call only. */
 int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, const uint64_t* start,
                       const uint32_t* length, const uint8_t* seq_exts, uint64_t n_seqs, dbg_seqset** out);
+/* Fixed-length reads packed back to back (sequence i = bases [i*read_len, (i+1)*read_len)): the common
+ * sequencer layout; no start/length arrays to transfer or validate. */
+int dbg_seqset_upload_uniform(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, uint64_t n_seqs, uint32_t read_len,
+                              const uint8_t* seq_exts, dbg_seqset** out);
 /* Wrap caller-owned DEVICE buffers (e.g. torch tensors) without copying. */
 int dbg_seqset_wrap_device(dbg_ctx* ctx, const uint64_t* d_words, uint64_t n_words, const uint64_t* d_start,
                            const uint32_t* d_length, const uint8_t* d_seq_exts, uint64_t n_seqs, uint32_t max_len,
@@ -135,6 +139,10 @@ void dbg_graph_free(dbg_graph* g);
  * `table_out` may be NULL. */
 int dbg_reads_to_graph(dbg_ctx* ctx, int k, const dbg_seqset* seqs, uint32_t min_kmer_obs, int stranded,
                        int reduce_op, dbg_kmer_table** table_out, dbg_graph** graph_out);
+/* start == NULL && length == NULL: fixed-length reads of `uniform_len` bases (see dbg_seqset_upload_uniform). */
+int dbg_reads_to_graph_host_uniform(dbg_ctx* ctx, int k, const uint64_t* words, uint64_t n_words, uint64_t n_seqs,
+                                    uint32_t read_len, const uint8_t* seq_exts, uint32_t min_kmer_obs, int stranded,
+                                    int reduce_op, dbg_kmer_table** table_out, dbg_graph** graph_out);
 int dbg_reads_to_graph_host(dbg_ctx* ctx, int k, const uint64_t* words, uint64_t n_words, const uint64_t* start,
                             const uint32_t* length, const uint8_t* seq_exts, uint64_t n_seqs, uint32_t min_kmer_obs,
                             int stranded, int reduce_op, dbg_kmer_table** table_out, dbg_graph** graph_out);

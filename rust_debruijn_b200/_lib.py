@@ -55,6 +55,7 @@ SIGNATURES = {
     "dbg_ctx_synchronize": (C.c_int, [vp]),
     "dbg_ctx_stream": (C.c_void_p, [vp]),
     "dbg_seqset_upload": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vpp]),
+    "dbg_seqset_upload_uniform": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vpp]),
     "dbg_seqset_wrap_device": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.c_uint32, vpp]),
     "dbg_seqset_synth": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint32, vpp]),
     "dbg_seqset_len": (C.c_uint64, [vp]),
@@ -81,6 +82,8 @@ SIGNATURES = {
     "dbg_reads_to_graph": (C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_int, C.c_int, vpp, vpp]),
     "dbg_reads_to_graph_host": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_int,
                                           C.c_int, vpp, vpp]),
+    "dbg_reads_to_graph_host_uniform": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, C.c_uint32,
+                                                  C.c_int, C.c_int, vpp, vpp]),
     "dbg_msp_kmer_buckets": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_uint64]),
 }
 

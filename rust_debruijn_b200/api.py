@@ -112,6 +112,16 @@ class SeqSet:
         return SeqSet(ctx, h)
 
     @staticmethod
+    def upload_uniform(ctx, words, n_seqs, read_len, seq_exts=None):
+        words = np.ascontiguousarray(words, np.uint64)
+        if seq_exts is not None:
+            seq_exts = np.ascontiguousarray(seq_exts, np.uint8)
+        h = C.c_void_p()
+        ctx.check(ctx._L.dbg_seqset_upload_uniform(ctx._h, _ptr(words), len(words), n_seqs, read_len, _ptr(seq_exts),
+                                                   C.byref(h)))
+        return SeqSet(ctx, h)
+
+    @staticmethod
     def synth(ctx, n_reads, seed=1, err_thr=0):
         h = C.c_void_p()
         ctx.check(ctx._L.dbg_seqset_synth(ctx._h, n_reads, seed, err_thr, C.byref(h)))

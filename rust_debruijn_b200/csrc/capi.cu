@@ -247,6 +247,39 @@ int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, con
     return DBG_OK;
 }
 
+int dbg_seqset_upload_uniform(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, uint64_t n_seqs, uint32_t read_len,
+                              const uint8_t* seq_exts, dbg_seqset** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    Ctx* c = CTX(ctx);
+    *out = nullptr;
+    cudaSetDevice(c->device);
+    if (n_seqs == 0 || read_len == 0) DBG_SET_ERR(c, DBG_E_BADARG, "n_seqs and read_len must be > 0");
+    if (!words || n_seqs * (u64)read_len > n_words * 32) DBG_SET_ERR(c, DBG_E_BADARG, "reads run past the packed words");
+    dbg_seqset* h = new (std::nothrow) dbg_seqset();
+    if (!h) DBG_SET_ERR(c, DBG_E_OOM, "host allocation failed");
+    SeqSet* s = &h->s;
+    s->ctx = c; s->n_seqs = n_seqs; s->n_words = n_words; s->max_len = read_len; s->uniform_len = read_len;
+    s->contiguous = true; s->base0 = 0; s->total_end = n_seqs * (u64)read_len;
+    DBuf<u64> dw;
+    DBuf<u8> de;
+    int rc = dw.alloc_pool(c, n_words + 2);
+    if (rc == DBG_OK && cudaMemsetAsync(dw.p + n_words, 0, 16, c->stream) != cudaSuccess) rc = DBG_E_CUDA;
+    if (rc == DBG_OK && cudaMemcpyAsync(dw.p, words, n_words * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = DBG_E_CUDA;
+    if (rc == DBG_OK && seq_exts) {
+        rc = de.alloc_pool(c, n_seqs);
+        if (rc == DBG_OK && cudaMemcpyAsync(de.p, seq_exts, n_seqs, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = DBG_E_CUDA;
+    }
+    if (rc != DBG_OK) {
+        if (rc == DBG_E_CUDA) c->err = std::string("seqset upload: ") + cudaGetErrorString(cudaGetLastError());
+        delete h;
+        return rc;
+    }
+    s->words = dw.take();
+    if (seq_exts) s->seq_exts = de.take();
+    *out = h;
+    return DBG_OK;
+}
+
 int dbg_seqset_wrap_device(dbg_ctx* ctx, const uint64_t* d_words, uint64_t n_words, const uint64_t* d_start,
                            const uint32_t* d_length, const uint8_t* d_seq_exts, uint64_t n_seqs, uint32_t max_len,
                            dbg_seqset** out) {
@@ -478,6 +511,19 @@ int dbg_reads_to_graph_host(dbg_ctx* ctx, int k, const uint64_t* words, uint64_t
     *graph_out = nullptr;
     dbg_seqset* s = nullptr;
     int rc = dbg_seqset_upload(ctx, words, n_words, start, length, seq_exts, n_seqs, &s);
+    if (rc != DBG_OK) return rc;
+    rc = dbg_reads_to_graph(ctx, k, s, min_kmer_obs, stranded, reduce_op, table_out, graph_out);
+    dbg_seqset_free(s);
+    return rc;
+}
+
+int dbg_reads_to_graph_host_uniform(dbg_ctx* ctx, int k, const uint64_t* words, uint64_t n_words, uint64_t n_seqs,
+                                    uint32_t read_len, const uint8_t* seq_exts, uint32_t min_kmer_obs, int stranded,
+                                    int reduce_op, dbg_kmer_table** table_out, dbg_graph** graph_out) {
+    if (!ctx || !graph_out) return DBG_E_BADARG;
+    *graph_out = nullptr;
+    dbg_seqset* s = nullptr;
+    int rc = dbg_seqset_upload_uniform(ctx, words, n_words, n_seqs, read_len, seq_exts, &s);
     if (rc != DBG_OK) return rc;
     rc = dbg_reads_to_graph(ctx, k, s, min_kmer_obs, stranded, reduce_op, table_out, graph_out);
     dbg_seqset_free(s);

@@ -1032,9 +1032,12 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     int maxk = rec_max_kmers(RW, k);
     u64 target = c->target_bucket_occ > 0 ? (u64)c->target_bucket_occ : 0;
     if (!target) {
+        // k-mer occurrences per bucket such that the bucket's DISTINCT k-mers fit the shared-memory table
+        // (8192 slots for one-word keys, 4096 for two-word keys; longer k-mers are also more often distinct)
+        const u64 tmax = W == 1 ? 16384 : 2048;
         target = N / ((u64)c->sm_count * 8);
-        if (target < 2048) target = 2048;
-        if (target > 16384) target = 16384;
+        if (target < tmax / 8) target = tmax / 8;
+        if (target > tmax) target = tmax;
     }
     int bbits = 0;
     while (bbits < 20 && (N >> (bbits + 1)) >= target) bbits++;

@@ -153,6 +153,16 @@ def test_layouts(D, ctx, orc):
     run_both(D, ctx, orc, 31, (words, start, length), 1, stranded=True)
 
 
+def test_uniform_upload_entry_point(D, ctx, orc):
+    w, s, l = orc.synth_reads(2500, 1, orc.ERR_THR_NOISY)
+    ss = D.SeqSet.upload_uniform(ctx, w, 2500, 150)
+    table, _ = D.filter_kmers(ss, D.CountFilter(2), False, False, 4, k=31)
+    ot = orc.filter_kmers(31, w, s, l, min_obs=2)
+    assert_tables_equal(table.to_host(), ot)
+    with pytest.raises(D.DbgError):
+        D.SeqSet.upload_uniform(ctx, w, 2501, 150)
+
+
 def test_count_saturation(D, ctx, orc):
     """filter.rs:57 counts saturate at 65535; compression.rs:495 single-k-mer node keeps raw data."""
     seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")
