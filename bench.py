@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
     ap.add_argument("--ref-reads", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="debug: do not run the nvidia-smi sampler")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -202,14 +203,19 @@ def main():
     st0 = ctx.stats()
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if not args.no_clocks:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
+    walls = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         step()
+        walls.append(round((time.perf_counter() - t0) * 1e3, 2))
     e1.record(ext)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if not args.no_clocks else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler off"]}
+    print(f"[bench] rank {rank} per-step wall ms: {walls}", file=sys.stderr)
     ms_total = e0.elapsed_time(e1)
     st1 = ctx.stats()
     n_kmers = st1["n_input_kmers"]

@@ -147,6 +147,32 @@ int dbg_reads_to_graph_host(dbg_ctx* ctx, int k, const uint64_t* words, uint64_t
                             const uint32_t* length, const uint8_t* seq_exts, uint64_t n_seqs, uint32_t min_kmer_obs,
                             int stranded, int reduce_op, dbg_kmer_table** table_out, dbg_graph** graph_out);
 
+/* ---- multi-GPU building blocks: MSP-bucket sharding of the counting stage (the reference's sharded flow,
+ * src/test.rs:433-456: msp_sequence -> per-shard filter_kmers).  Every rank partitions its own reads with the
+ * same plan, the caller exchanges bucket ranges between ranks (one all-to-all of super-k-mer records over
+ * NCCL on the device pointers below), and each rank counts the buckets it owns.  See rust_debruijn_b200/sharded.py. */
+typedef struct dbg_partition dbg_partition;
+/* Minimizer length and log2(#buckets) for a job of n_input_kmers_total k-mer occurrences (same on every rank). */
+int dbg_plan_filter(dbg_ctx* ctx, int k, uint64_t n_input_kmers_total, int* msp_p, int* bucket_bits);
+uint64_t dbg_seqset_count_kmers(dbg_ctx* ctx, int k, const dbg_seqset* seqs);
+int dbg_partition_reads(dbg_ctx* ctx, int k, const dbg_seqset* seqs, int stranded, int msp_p, int bucket_bits,
+                        dbg_partition** out);
+uint64_t dbg_partition_n_records(const dbg_partition* p);
+uint64_t dbg_partition_n_input(const dbg_partition* p);
+uint32_t dbg_partition_record_bytes(const dbg_partition* p);       /* 16 (k <= 32) or 32 */
+void* dbg_partition_records_dev(const dbg_partition* p);          /* device pointer, records in bucket order */
+int dbg_partition_bucket_counts(const dbg_partition* p, uint32_t* host_counts /* 2^bucket_bits */);
+void dbg_partition_free(dbg_partition* p);
+/* d_records (device): n_src runs back to back; run s holds this rank's n_local_buckets buckets in bucket order;
+ * h_counts[s * n_local_buckets + b] (host) = records of local bucket b in run s. */
+int dbg_filter_from_records(dbg_ctx* ctx, int k, const void* d_records, uint64_t n_records, const uint32_t* h_counts,
+                            uint32_t n_src, uint32_t n_local_buckets, uint64_t n_input_kmers_total,
+                            uint32_t min_kmer_obs, int stranded, int report_all_kmers, dbg_kmer_table** out);
+/* Device pointers of a table's arrays (hi is NULL for k <= 32), and a table built from device arrays (any order). */
+int dbg_table_device_ptrs(const dbg_kmer_table* t, void** kmers_lo, void** kmers_hi, void** exts, void** counts);
+int dbg_table_from_device(dbg_ctx* ctx, int k, uint64_t n, const void* d_kmers_lo, const void* d_kmers_hi,
+                          const void* d_exts, const void* d_counts, dbg_kmer_table** out);
+
 /* ---- msp::msp_sequence bucket assignment — src/msp.rs:279-324, 115-117 -----------------------------
  * For every k-mer start position j of every sequence: the MSP bucket of that k-mer under the
  * reference's default (identity) permutation with rc = !stranded, i.e. the value

@@ -84,6 +84,19 @@ SIGNATURES = {
                                           C.c_int, vpp, vpp]),
     "dbg_reads_to_graph_host_uniform": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, C.c_uint32,
                                                   C.c_int, C.c_int, vpp, vpp]),
+    "dbg_plan_filter": (C.c_int, [vp, C.c_int, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dbg_seqset_count_kmers": (C.c_uint64, [vp, C.c_int, vp]),
+    "dbg_partition_reads": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vpp]),
+    "dbg_partition_n_records": (C.c_uint64, [vp]),
+    "dbg_partition_n_input": (C.c_uint64, [vp]),
+    "dbg_partition_record_bytes": (C.c_uint32, [vp]),
+    "dbg_partition_records_dev": (C.c_void_p, [vp]),
+    "dbg_partition_bucket_counts": (C.c_int, [vp, vp]),
+    "dbg_partition_free": (None, [vp]),
+    "dbg_filter_from_records": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
+                                          C.c_int, C.c_int, vpp]),
+    "dbg_table_device_ptrs": (C.c_int, [vp, vpp, vpp, vpp, vpp]),
+    "dbg_table_from_device": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, vp, vpp]),
     "dbg_msp_kmer_buckets": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_uint64]),
 }
 

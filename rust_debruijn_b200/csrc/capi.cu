@@ -395,8 +395,8 @@ __global__ void check_sorted_unique_kernel(const u64* lo, const u64* hi, u64 n, 
     if (!ok) *bad = 1;
 }
 
-int dbg_table_from_host(dbg_ctx* ctx, int k, uint64_t n, const uint64_t* kmers_lo, const uint64_t* kmers_hi,
-                        const uint8_t* exts, const uint16_t* counts, dbg_kmer_table** out) {
+static int table_from_arrays(dbg_ctx* ctx, int k, uint64_t n, const void* kmers_lo, const void* kmers_hi,
+                             const void* exts, const void* counts, cudaMemcpyKind kind, dbg_kmer_table** out) {
     if (!ctx || !out) return DBG_E_BADARG;
     Ctx* c = CTX(ctx);
     *out = nullptr;
@@ -420,10 +420,10 @@ int dbg_table_from_host(dbg_ctx* ctx, int k, uint64_t n, const uint64_t* kmers_l
     T2(arena_begin(c));
     T2(alo.alloc_pool(c, n)); T2(blo.alloc_pool(c, n)); T2(av.alloc(c, n)); T2(bv.alloc(c, n)); T2(de.alloc_pool(c, n)); T2(dc.alloc_pool(c, n)); T2(bad.alloc(c, 1));
     if (W == 2) { T2(ahi.alloc_pool(c, n)); T2(bhi.alloc_pool(c, n)); }
-    CU2(cudaMemcpyAsync(alo.p, kmers_lo, n * 8, cudaMemcpyHostToDevice, c->stream));
-    if (W == 2) CU2(cudaMemcpyAsync(ahi.p, kmers_hi, n * 8, cudaMemcpyHostToDevice, c->stream));
-    CU2(cudaMemcpyAsync(de.p, exts, n, cudaMemcpyHostToDevice, c->stream));
-    CU2(cudaMemcpyAsync(dc.p, counts, n * 2, cudaMemcpyHostToDevice, c->stream));
+    CU2(cudaMemcpyAsync(alo.p, kmers_lo, n * 8, kind, c->stream));
+    if (W == 2) CU2(cudaMemcpyAsync(ahi.p, kmers_hi, n * 8, kind, c->stream));
+    CU2(cudaMemcpyAsync(de.p, exts, n, kind, c->stream));
+    CU2(cudaMemcpyAsync(dc.p, counts, n * 2, kind, c->stream));
     pack_vals_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(de.p, dc.p, av.p, n);
     T2(check_launch(c, "pack_vals"));
     u64 *rlo, *rhi;
@@ -446,6 +446,78 @@ int dbg_table_from_host(dbg_ctx* ctx, int k, uint64_t n, const uint64_t* kmers_l
 #undef T2
 #undef CU2
     return DBG_OK;
+}
+
+int dbg_table_from_host(dbg_ctx* ctx, int k, uint64_t n, const uint64_t* kmers_lo, const uint64_t* kmers_hi,
+                        const uint8_t* exts, const uint16_t* counts, dbg_kmer_table** out) {
+    return table_from_arrays(ctx, k, n, kmers_lo, kmers_hi, exts, counts, cudaMemcpyHostToDevice, out);
+}
+int dbg_table_from_device(dbg_ctx* ctx, int k, uint64_t n, const void* d_kmers_lo, const void* d_kmers_hi,
+                          const void* d_exts, const void* d_counts, dbg_kmer_table** out) {
+    return table_from_arrays(ctx, k, n, d_kmers_lo, d_kmers_hi, d_exts, d_counts, cudaMemcpyDeviceToDevice, out);
+}
+int dbg_table_device_ptrs(const dbg_kmer_table* t, void** kmers_lo, void** kmers_hi, void** exts, void** counts) {
+    if (!t) return DBG_E_BADARG;
+    if (kmers_lo) *kmers_lo = t->t.lo;
+    if (kmers_hi) *kmers_hi = t->t.hi;
+    if (exts) *exts = t->t.exts;
+    if (counts) *counts = t->t.counts;
+    return DBG_OK;
+}
+
+// ---- multi-GPU building blocks ------------------------------------------------------------------------------
+int dbg_plan_filter(dbg_ctx* ctx, int k, uint64_t n_total, int* msp_p, int* bucket_bits) {
+    if (!ctx || !msp_p || !bucket_bits) return DBG_E_BADARG;
+    if (k < 4 || k > 64) DBG_SET_ERR(CTX(ctx), DBG_E_BADARG, "k=%d outside [4,64]", k);
+    plan_filter(CTX(ctx), k, n_total, msp_p, bucket_bits);
+    return DBG_OK;
+}
+uint64_t dbg_seqset_count_kmers(dbg_ctx* ctx, int k, const dbg_seqset* seqs) {
+    if (!ctx || !seqs) return 0;
+    const SeqSet* s = &seqs->s;
+    if (s->uniform_len) return s->uniform_len >= (u32)k ? (u64)(s->uniform_len - k + 1) * s->n_seqs : 0;
+    // general layouts: the partition stage counts on the device; do the same reduction here through a 0-bucket plan
+    Partition* P = nullptr;
+    cudaSetDevice(ctx->c.device);
+    if (partition_reads_dev(CTX(ctx), k, s, 0, k - 3 < 1 ? 1 : (k - 3 > 12 ? 12 : k - 3), 0, &P) != DBG_OK) return 0;
+    u64 n = P->n_input;
+    free_partition(P);
+    return n;
+}
+int dbg_partition_reads(dbg_ctx* ctx, int k, const dbg_seqset* seqs, int stranded, int msp_p, int bucket_bits,
+                        dbg_partition** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    *out = nullptr;
+    NULLCHK(ctx, seqs);
+    cudaSetDevice(ctx->c.device);
+    Partition* P = nullptr;
+    int rc = partition_reads_dev(CTX(ctx), k, &seqs->s, stranded != 0, msp_p, bucket_bits, &P);
+    *out = reinterpret_cast<dbg_partition*>(P);
+    return rc;
+}
+uint64_t dbg_partition_n_records(const dbg_partition* p) { return p ? p->p.n_rec : 0; }
+uint64_t dbg_partition_n_input(const dbg_partition* p) { return p ? p->p.n_input : 0; }
+uint32_t dbg_partition_record_bytes(const dbg_partition* p) { return p ? (uint32_t)p->p.rec_words * 8 : 0; }
+void* dbg_partition_records_dev(const dbg_partition* p) { return p ? (void*)p->p.rec : nullptr; }
+int dbg_partition_bucket_counts(const dbg_partition* p, uint32_t* host_counts) {
+    if (!p || !host_counts) return DBG_E_BADARG;
+    Ctx* c = p->p.ctx;
+    cudaSetDevice(c->device);
+    CU(c, cudaMemcpyAsync(host_counts, p->p.bucket_count, ((u64)1 << p->p.bbits) * 4, cudaMemcpyDeviceToHost, c->stream));
+    return sync(c);
+}
+void dbg_partition_free(dbg_partition* p) { if (p) { cudaSetDevice(p->p.ctx->device); free_partition(&p->p); } }
+int dbg_filter_from_records(dbg_ctx* ctx, int k, const void* d_records, uint64_t n_records, const uint32_t* h_counts,
+                            uint32_t n_src, uint32_t n_local_buckets, uint64_t n_input_kmers_total,
+                            uint32_t min_kmer_obs, int stranded, int report_all_kmers, dbg_kmer_table** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    *out = nullptr;
+    cudaSetDevice(ctx->c.device);
+    Table* t = nullptr;
+    int rc = filter_from_records_dev(CTX(ctx), k, (const u64*)d_records, n_records, h_counts, n_src, n_local_buckets,
+                                     n_input_kmers_total, min_kmer_obs, stranded != 0, report_all_kmers != 0, &t);
+    *out = reinterpret_cast<dbg_kmer_table*>(t);
+    return rc;
 }
 
 void dbg_table_free(dbg_kmer_table* t) { if (t) { cudaSetDevice(t->t.ctx->device); free_table(&t->t); } }

@@ -201,12 +201,23 @@ struct Graph {
     u16* data = nullptr;
 };
 
+// Bucket-contiguous super-k-mer records of one rank's reads (multi-GPU building block).
+struct Partition {
+    Ctx* ctx;
+    int k = 0, p = 0, bbits = 0, rec_words = 2;
+    u64 n_input = 0, n_rec = 0;
+    u64* rec = nullptr;          // n_rec * rec_words u64
+    u32* bucket_count = nullptr; // 2^bbits
+    u64* bucket_off = nullptr;   // 2^bbits + 1
+};
+
 }  // namespace dbg
 // the opaque C handles are thin wrappers (first member) so stage code can allocate them directly
 struct dbg_ctx { dbg::Ctx c; };
 struct dbg_seqset { dbg::SeqSet s; };
 struct dbg_kmer_table { dbg::Table t; };
 struct dbg_graph { dbg::Graph g; };
+struct dbg_partition { dbg::Partition p; };
 namespace dbg {
 
 // ---- primitives (scan_sort.cu) ------------------------------------------------------------------------
@@ -222,6 +233,11 @@ int radix_sort_pairs(Ctx* c, int W, int key_bits, u64 n, u64* lo_a, u64* hi_a, u
 int filter_kmers_dev(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, int report_all, u64 mem_gb,
                      Table** out);
 int compress_dev(Ctx* c, const Table* t, int stranded, int reduce_op, Graph** out);
+void plan_filter(const Ctx* c, int k, u64 N, int* p_out, int* bbits_out);
+int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int bbits, Partition** out);
+void free_partition(Partition* P);
+int filter_from_records_dev(Ctx* c, int k, const u64* d_records, u64 n_records, const u32* h_counts, u32 n_src, u32 n_local,
+                            u64 n_input_total, u32 min_obs, int stranded, int report_all, Table** out);
 int synth_reads_dev(Ctx* c, u64 R, u64 seed, u32 err_thr, SeqSet** out);
 void free_seqset(SeqSet* s);
 void free_table(Table* t);

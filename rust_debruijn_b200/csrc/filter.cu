@@ -985,51 +985,15 @@ __global__ void item_fill_kernel(const u32* __restrict__ cnt, const u64* __restr
 // ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
-template <int W>
-static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, int report_all, Table** out) {
-    constexpr int RW = RecLayout<W>::WORDS;
-    KP kp = make_kp(k);
-    cudaStream_t st = c->stream;
-    dbg_stats& S = c->stats;
-    TRY(arena_begin(c));
-    CU(c, cudaEventRecord(c->ev[0], st));
-
-    // ---- input size ----
-    u64 N = 0;
-    u32 max_len = s->max_len;
-    if (s->uniform_len) {
-        N = s->uniform_len >= (u32)k ? (u64)(s->uniform_len - k + 1) * s->n_seqs : 0;
-        max_len = s->uniform_len;
-    } else if (s->n_seqs) {
-        DBuf<u64> tmp;
-        TRY(tmp.alloc(c, 2));
-        TRY(tmp.zero());
-        count_input_kmers_kernel<<<grid_for(s->n_seqs, 256), 256, 0, st>>>(s->length, s->n_seqs, k, tmp.p, (u32*)(tmp.p + 1));
-        TRY(check_launch(c, "count_input_kmers"));
-        u64 h[2];
-        TRY(read_u64(c, tmp.p, h, 2));
-        N = h[0];
-        max_len = (u32)h[1];
-    }
-    Table* t = &(new dbg_kmer_table())->t;
-    t->ctx = c;
-    t->k = k;
-    t->n_input = N;
-    S.n_seqs = s->n_seqs;
-    S.n_input_kmers = N;
-    *out = t;
-    if (N == 0) {
-        S.n_records = S.n_buckets = S.n_distinct = S.n_valid = 0;
-        return DBG_OK;
-    }
-    // ---- plan ----
+// MSP plan shared by every rank of a sharded run: minimizer length and number of buckets from the
+// TOTAL number of input k-mers.
+void plan_filter(const Ctx* c, int k, u64 N, int* p_out, int* bbits_out) {
+    const int W = k <= 32 ? 1 : 2;
     int p = c->msp_p > 0 ? c->msp_p : 12;
     if (p > k - 3) p = k - 3;  // window of K-p+1 >= 4 p-mers (register-tiled window minimum)
     if (p > 16) p = 16;
     if (p < 1) p = 1;
     if (k - p > 63) p = k - 63;
-    const bool use_tiles = s->contiguous && s->total_end > s->base0;
-    int maxk = rec_max_kmers(RW, k);
     u64 target = c->target_bucket_occ > 0 ? (u64)c->target_bucket_occ : 0;
     if (!target) {
         // k-mer occurrences per bucket such that the bucket's DISTINCT k-mers fit the shared-memory table
@@ -1041,12 +1005,51 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     }
     int bbits = 0;
     while (bbits < 20 && (N >> (bbits + 1)) >= target) bbits++;
-    u32 NB = 1u << bbits;
-    S.msp_p = p;
-    S.bucket_bits = bbits;
-    S.n_buckets = NB;
+    *p_out = p;
+    *bbits_out = bbits;
+}
 
-    // ---- work items ----
+static int count_input(Ctx* c, int k, const SeqSet* s, u64* N_out, u32* max_len_out) {
+    u64 N = 0;
+    u32 max_len = s->max_len;
+    if (s->uniform_len) {
+        N = s->uniform_len >= (u32)k ? (u64)(s->uniform_len - k + 1) * s->n_seqs : 0;
+        max_len = s->uniform_len;
+    } else if (s->n_seqs) {
+        DBuf<u64> tmp;
+        TRY(tmp.alloc(c, 2));
+        TRY(tmp.zero());
+        count_input_kmers_kernel<<<grid_for(s->n_seqs, 256), 256, 0, c->stream>>>(s->length, s->n_seqs, k, tmp.p, (u32*)(tmp.p + 1));
+        TRY(check_launch(c, "count_input_kmers"));
+        u64 h[2];
+        TRY(read_u64(c, tmp.p, h, 2));
+        N = h[0];
+        max_len = (u32)h[1];
+    }
+    *N_out = N;
+    *max_len_out = max_len;
+    return DBG_OK;
+}
+
+// Output of the partition stage: super-k-mer records grouped by MSP bucket.
+struct PartOut {
+    DBuf<u64> rec;         // n_rec records of RW words, bucket-contiguous
+    DBuf<u64> bucket_off;  // NB + 1 exclusive offsets (device)
+    DBuf<u32> bucket_count;
+    u64 n_rec = 0;
+};
+
+// ---- P1 + P1b: sequences -> bucket-contiguous super-k-mer records ----
+template <int W>
+static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, u32 max_len, int p, int bbits, bool pool_out,
+                           PartOut& po) {
+    constexpr int RW = RecLayout<W>::WORDS;
+    KP kp = make_kp(k);
+    cudaStream_t st = c->stream;
+    const u32 NB = 1u << bbits;
+    const bool use_tiles = s->contiguous && s->total_end > s->base0;
+    const int maxk = rec_max_kmers(RW, k);
+    // work items (general kernel only)
     DBuf<u32> item_seq, item_j0;
     u64 n_items = s->n_seqs;
     bool chunked = !use_tiles && max_len >= (u32)k && (max_len - k + 1) > (u32)CHUNK;
@@ -1065,13 +1068,11 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         item_fill_kernel<<<grid_for(s->n_seqs, 256), 256, 0, st>>>(cnt.p, off.p, s->n_seqs, item_seq.p, item_j0.p);
         TRY(check_launch(c, "item_fill"));
     }
-
-    // ---- P1: partition into super-k-mer records ----
-    DBuf<u32> bucket_count, bucket_fill;
-    DBuf<u64> bucket_off, ctr;
-    TRY(bucket_count.alloc(c, NB));
+    DBuf<u32> bucket_fill;
+    DBuf<u64> ctr;
+    if (pool_out) { TRY(po.bucket_count.alloc_pool(c, NB)); TRY(po.bucket_off.alloc_pool(c, (u64)NB + 1)); }
+    else { TRY(po.bucket_count.alloc(c, NB)); TRY(po.bucket_off.alloc(c, (u64)NB + 1)); }
     TRY(bucket_fill.alloc(c, NB));
-    TRY(bucket_off.alloc(c, (u64)NB + 1));
     TRY(ctr.alloc(c, 8));
     TileArgs ta;
     ta.base0 = s->base0; ta.total_end = s->total_end;
@@ -1087,7 +1088,7 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         TRY(stage_rec.alloc(c, capacity * RW));
         TRY(stage_bucket.alloc(c, capacity));
         TRY(stage_bucket.fill_ff());
-        TRY(bucket_count.zero());
+        TRY(po.bucket_count.zero());
         TRY(ctr.zero());
         P1Args a;
         a.words = s->words; a.n_words = s->n_words; a.start = s->start; a.length = s->length; a.seq_exts = s->seq_exts;
@@ -1095,7 +1096,7 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         a.item_seq = chunked ? item_seq.p : nullptr; a.item_j0 = chunked ? item_j0.p : nullptr; a.n_items = n_items;
         a.p = p; a.stranded = stranded; a.bucket_mask = NB - 1; a.maxk = maxk;
         a.rec = stage_rec.p; a.rec_bucket = stage_bucket.p; a.capacity = capacity;
-        a.cursor = ctr.p; a.bucket_count = bucket_count.p; a.overflow = (u32*)(ctr.p + 1);
+        a.cursor = ctr.p; a.bucket_count = po.bucket_count.p; a.overflow = (u32*)(ctr.p + 1);
         CU(c, cudaEventRecord(c->ev[8], st));
         if (use_tiles) msp_tile_kernel<W><<<grid1, T1_THREADS, 0, st>>>(kp, a, ta);
         else msp_partition_kernel<W><<<grid1, P1_THREADS, 0, st>>>(kp, a);
@@ -1108,26 +1109,29 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         if (attempt == 1) DBG_SET_ERR(c, DBG_E_INTERNAL, "record staging overflow after retry (%llu slots)", (unsigned long long)h[0]);
         capacity = h[0] + 1024;  // the cursor says exactly how much was needed
     }
-    TRY(exclusive_scan_u32_to_u64(c, bucket_count.p, bucket_off.p, NB, bucket_off.p + NB));
-    u64 n_rec = 0;
-    TRY(read_u64(c, bucket_off.p + NB, &n_rec));
-    S.n_records = n_rec;
-    DBuf<u64> rec;
-    TRY(rec.alloc(c, n_rec * RW));
+    TRY(exclusive_scan_u32_to_u64(c, po.bucket_count.p, po.bucket_off.p, NB, po.bucket_off.p + NB));
+    TRY(read_u64(c, po.bucket_off.p + NB, &po.n_rec));
+    if (pool_out) TRY(po.rec.alloc_pool(c, po.n_rec * RW)); else TRY(po.rec.alloc(c, po.n_rec * RW));
     TRY(bucket_fill.zero());
     if (n_slots > capacity) n_slots = capacity;
-    scatter_records_kernel<RW><<<grid_for(n_slots, 256), 256, 0, st>>>(stage_rec.p, stage_bucket.p, n_slots, bucket_off.p,
-                                                                        bucket_fill.p, rec.p);
+    scatter_records_kernel<RW><<<grid_for(n_slots, 256), 256, 0, st>>>(stage_rec.p, stage_bucket.p, n_slots, po.bucket_off.p,
+                                                                        bucket_fill.p, po.rec.p);
     TRY(check_launch(c, "scatter_records"));
-    stage_rec.release();
-    stage_bucket.release();
-    CU(c, cudaEventRecord(c->ev[1], st));
+    return DBG_OK;
+}
 
-    // ---- P2: count per bucket in shared memory ----
+// ---- P2 + P3: bucket-contiguous records -> ascending (k-mer, exts, count) table ----
+template <int W>
+static int count_sort_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucket_off, u32 NB, u64 N, u32 min_obs, int stranded,
+                            int report_all, Table* t) {
+    KP kp = make_kp(k);
+    cudaStream_t st = c->stream;
+    dbg_stats& S = c->stats;
     u64 cap_valid = min_obs > 1 ? N / min_obs + 1 : N;
     u64 cap_all = report_all ? N : 0;
-    DBuf<u64> v_lo, v_hi, a_lo, a_hi;
+    DBuf<u64> v_lo, v_hi, a_lo, a_hi, ctr;
     DBuf<u32> v_val;
+    TRY(ctr.alloc(c, 8));
     TRY(v_lo.alloc(c, cap_valid));
     TRY(v_val.alloc(c, cap_valid));
     if (W == 2) TRY(v_hi.alloc(c, cap_valid));
@@ -1140,7 +1144,7 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     TRY(ctr.zero());
     {
         P2Args a;
-        a.rec = rec.p; a.mult = (W == 1 && c->dedup) ? mult.p : nullptr; a.bucket_off = bucket_off.p; a.n_buckets = NB;
+        a.rec = rec; a.mult = (W == 1 && c->dedup) ? mult.p : nullptr; a.bucket_off = bucket_off; a.n_buckets = NB;
         a.min_obs = min_obs; a.stranded = stranded; a.report_all = report_all;
         a.out_lo = v_lo.p; a.out_hi = v_hi.p; a.out_val = v_val.p; a.cap_valid = cap_valid;
         a.all_lo = a_lo.p; a.all_hi = a_hi.p; a.cap_all = cap_all;
@@ -1161,7 +1165,6 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     S.n_valid = V;
     S.n_distinct = U;
     S.n_bucket_splits = h[3];
-    rec.release();
     CU(c, cudaEventRecord(c->ev[2], st));
 
     // ---- P3: ascending order (src/filter.rs:205-219) ----
@@ -1211,6 +1214,37 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         t->n_all = U;
     }
     CU(c, cudaEventRecord(c->ev[3], st));
+    return DBG_OK;
+}
+
+template <int W>
+static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, int report_all, Table** out) {
+    cudaStream_t st = c->stream;
+    dbg_stats& S = c->stats;
+    TRY(arena_begin(c));
+    CU(c, cudaEventRecord(c->ev[0], st));
+    u64 N = 0;
+    u32 max_len = 0;
+    TRY(count_input(c, k, s, &N, &max_len));
+    Table* t = &(new dbg_kmer_table())->t;
+    t->ctx = c;
+    t->k = k;
+    t->n_input = N;
+    S.n_seqs = s->n_seqs;
+    S.n_input_kmers = N;
+    *out = t;
+    if (N == 0) {
+        S.n_records = S.n_buckets = S.n_distinct = S.n_valid = 0;
+        return DBG_OK;
+    }
+    int p, bbits;
+    plan_filter(c, k, N, &p, &bbits);
+    S.msp_p = p; S.bucket_bits = bbits; S.n_buckets = 1u << bbits;
+    PartOut po;
+    TRY(partition_stage<W>(c, k, s, stranded, N, max_len, p, bbits, false, po));
+    S.n_records = po.n_rec;
+    CU(c, cudaEventRecord(c->ev[1], st));
+    TRY(count_sort_stage<W>(c, k, po.rec.p, po.n_rec, po.bucket_off.p, 1u << bbits, N, min_obs, stranded, report_all, t));
     TRY(sync(c));
     cudaEventElapsedTime(&S.ms_partition, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&S.ms_count, c->ev[1], c->ev[2]);
@@ -1231,6 +1265,149 @@ int filter_kmers_dev(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, 
                      : filter_impl<2>(c, k, s, min_obs, stranded, report_all, out);
     if (rc != DBG_OK && *out) { free_table(*out); *out = nullptr; }
     return rc;
+}
+
+// ================================================================================================
+// Multi-GPU building blocks: the counting stage shards by MSP bucket.  Every rank
+// partitions its own reads with the SAME plan (p, bucket bits from the total k-mer count), ships each
+// bucket range to its owning rank (one all-to-all of 16/32-byte super-k-mer records, done by the caller
+// with NCCL on these device buffers), and counts the buckets it owns.  All occurrences of a canonical
+// k-mer share a bucket, so per-rank tables are disjoint and their union is the unsharded table.
+// ================================================================================================
+int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int bbits, Partition** out) {
+    *out = nullptr;
+    if (k < 4 || k > 64) DBG_SET_ERR(c, DBG_E_BADARG, "k=%d outside [4,64]", k);
+    if (bbits < 0 || bbits > 20 || p < 1 || p > 16 || p > k - 3 + (k < 4 ? 0 : 0) || k - p > 63)
+        DBG_SET_ERR(c, DBG_E_BADARG, "bad MSP plan p=%d bucket_bits=%d for k=%d", p, bbits, k);
+    TRY(arena_begin(c));
+    u64 N = 0;
+    u32 max_len = 0;
+    TRY(count_input(c, k, s, &N, &max_len));
+    Partition* P = &(new dbg_partition())->p;
+    P->ctx = c; P->k = k; P->p = p; P->bbits = bbits; P->n_input = N; P->rec_words = k <= 32 ? 2 : 4;
+    PartOut po;
+    int rc = DBG_OK;
+    if (N) rc = k <= 32 ? partition_stage<1>(c, k, s, stranded, N, max_len, p, bbits, true, po)
+                        : partition_stage<2>(c, k, s, stranded, N, max_len, p, bbits, true, po);
+    else {
+        rc = po.bucket_count.alloc_pool(c, 1u << bbits);
+        if (rc == DBG_OK) rc = po.bucket_count.zero();
+    }
+    if (rc != DBG_OK) { delete reinterpret_cast<dbg_partition*>(P); return rc; }
+    rc = sync(c);
+    if (rc != DBG_OK) { delete reinterpret_cast<dbg_partition*>(P); return rc; }
+    P->n_rec = po.n_rec;
+    P->rec = po.rec.p ? po.rec.take() : nullptr;
+    P->bucket_count = po.bucket_count.take();
+    if (po.bucket_off.p) P->bucket_off = po.bucket_off.take();
+    c->stats.n_records = po.n_rec;
+    c->stats.n_input_kmers = N;
+    *out = P;
+    return DBG_OK;
+}
+
+void free_partition(Partition* P) {
+    if (!P) return;
+    cudaStream_t st = P->ctx->stream;
+    if (P->rec) cudaFreeAsync(P->rec, st);
+    if (P->bucket_count) cudaFreeAsync(P->bucket_count, st);
+    if (P->bucket_off) cudaFreeAsync(P->bucket_off, st);
+    delete reinterpret_cast<dbg_partition*>(P);
+}
+
+// One warp per (source, bucket) group: copy the group's records from the received per-source runs into the
+// bucket-contiguous layout.
+template <int RW>
+__global__ void merge_runs_kernel(const u64* __restrict__ src, u64* __restrict__ dst, const u64* __restrict__ g_src,
+                                  const u64* __restrict__ g_dst, const u32* __restrict__ g_cnt, u64 n_groups) {
+    u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (g >= n_groups) return;
+    u64 so = g_src[g], d0 = g_dst[g];
+    u32 cnt = g_cnt[g];
+    for (u32 i = lane; i < cnt; i += 32) {
+        const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(src + (so + i) * RW);
+        ulonglong2* dp = reinterpret_cast<ulonglong2*>(dst + (d0 + i) * RW);
+        dp[0] = sp[0];
+        if (RW == 4) dp[1] = sp[1];
+    }
+}
+
+template <int RW>
+__global__ void sum_record_kmers_kernel(const u64* __restrict__ rec, u64 n, u64* out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 v = i < n ? (rec[i * RW + RW - 1] >> 8) & 63ull : 0;
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
+// d_records: n_src runs back to back, run s holding the records of this rank's n_local buckets in bucket order;
+// h_counts[s * n_local + b] = records of local bucket b in run s.
+int filter_from_records_dev(Ctx* c, int k, const u64* d_records, u64 n_records, const u32* h_counts, u32 n_src, u32 n_local,
+                            u64 n_input_total, u32 min_obs, int stranded, int report_all, Table** out) {
+    *out = nullptr;
+    if (k < 4 || k > 64 || !n_src || !n_local || !h_counts) DBG_SET_ERR(c, DBG_E_BADARG, "bad arguments");
+    const int RW = k <= 32 ? 2 : 4;
+    cudaStream_t st = c->stream;
+    dbg_stats& S = c->stats;
+    TRY(arena_begin(c));
+    CU(c, cudaEventRecord(c->ev[1], st));
+    // host: bucket offsets of the merged layout and per-group source/destination offsets
+    const u64 n_groups = (u64)n_src * n_local;
+    std::vector<u64> h_off(n_local + 1, 0), g_src(n_groups), g_dst(n_groups);
+    for (u32 b = 0; b < n_local; b++) {
+        u64 t = 0;
+        for (u32 sidx = 0; sidx < n_src; sidx++) t += h_counts[(u64)sidx * n_local + b];
+        h_off[b + 1] = h_off[b] + t;
+    }
+    if (h_off[n_local] != n_records) DBG_SET_ERR(c, DBG_E_BADARG, "counts sum to %llu, n_records is %llu", (unsigned long long)h_off[n_local], (unsigned long long)n_records);
+    {
+        u64 run = 0;
+        std::vector<u64> fill(n_local, 0);
+        for (u32 sidx = 0; sidx < n_src; sidx++)
+            for (u32 b = 0; b < n_local; b++) {
+                u64 g = (u64)sidx * n_local + b;
+                g_src[g] = run;
+                g_dst[g] = h_off[b] + fill[b];
+                fill[b] += h_counts[g];
+                run += h_counts[g];
+            }
+    }
+    Table* t = &(new dbg_kmer_table())->t;
+    t->ctx = c; t->k = k; t->n_input = n_input_total;
+    *out = t;
+    S.n_records = n_records;
+    if (n_records == 0) return DBG_OK;
+    DBuf<u64> d_off, d_gsrc, d_gdst, merged;
+    DBuf<u32> d_gcnt;
+    TRY(d_off.alloc(c, n_local + 1)); TRY(d_gsrc.alloc(c, n_groups)); TRY(d_gdst.alloc(c, n_groups)); TRY(d_gcnt.alloc(c, n_groups));
+    TRY(merged.alloc(c, n_records * RW));
+    CU(c, cudaMemcpyAsync(d_off.p, h_off.data(), (n_local + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(d_gsrc.p, g_src.data(), n_groups * 8, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(d_gdst.p, g_dst.data(), n_groups * 8, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(d_gcnt.p, h_counts, n_groups * 4, cudaMemcpyHostToDevice, st));
+    if (RW == 2) merge_runs_kernel<2><<<grid_for(n_groups * 32, 256), 256, 0, st>>>(d_records, merged.p, d_gsrc.p, d_gdst.p, d_gcnt.p, n_groups);
+    else merge_runs_kernel<4><<<grid_for(n_groups * 32, 256), 256, 0, st>>>(d_records, merged.p, d_gsrc.p, d_gdst.p, d_gcnt.p, n_groups);
+    TRY(check_launch(c, "merge_runs"));
+    // k-mer occurrences actually present on this rank (capacity bounds of the counting stage)
+    DBuf<u64> d_sum;
+    TRY(d_sum.alloc(c, 1));
+    TRY(d_sum.zero());
+    if (RW == 2) sum_record_kmers_kernel<2><<<grid_for(n_records, 256), 256, 0, st>>>(merged.p, n_records, d_sum.p);
+    else sum_record_kmers_kernel<4><<<grid_for(n_records, 256), 256, 0, st>>>(merged.p, n_records, d_sum.p);
+    TRY(check_launch(c, "sum_record_kmers"));
+    u64 N_local_bound = 0;
+    TRY(read_u64(c, d_sum.p, &N_local_bound));  // also: host vectors may go out of scope after this sync
+    S.n_input_kmers = N_local_bound;
+    int rc = k <= 32 ? count_sort_stage<1>(c, k, merged.p, n_records, d_off.p, n_local, N_local_bound, min_obs, stranded, report_all, t)
+                     : count_sort_stage<2>(c, k, merged.p, n_records, d_off.p, n_local, N_local_bound, min_obs, stranded, report_all, t);
+    if (rc != DBG_OK) { free_table(t); *out = nullptr; return rc; }
+    TRY(sync(c));
+    cudaEventElapsedTime(&S.ms_count, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&S.ms_sort, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&S.ms_k_count, c->ev[10], c->ev[11]);
+    S.gpu_launches = c->launches;
+    return DBG_OK;
 }
 
 }  // namespace dbg

@@ -1,0 +1,190 @@
+"""Multi-GPU form of the path: one process per GPU, torch.distributed for the plumbing.
+
+filter_kmers shards by MSP bucket — the reference's own sharded flow (src/test.rs:433-456: msp_sequence
+-> per-shard filter_kmers): every rank cuts ITS reads into super-k-mer records with the same plan, one
+all-to-all ships each bucket range to the rank that owns it, and each rank counts its buckets.  All
+occurrences of a canonical k-mer share a bucket, so the per-rank tables are disjoint and their union is
+exactly the unsharded table.
+
+compress_kmers does not shard with a single exchange (unitigs cross buckets): round 1 gathers the valid
+k-mers (V ~ 0.03 N) to every rank and runs the single-GPU compression there ("replicas only for S3-S6",
+SURVEY §8e) — every rank ends with the same, complete BaseGraph.
+
+The pure planning helpers (owner_bounds, split_by_owner, exchange_counts) use only torch CPU/any-backend
+collectives and are covered by world_size-2 gloo tests on CPU."""
+import ctypes as C
+import math
+
+import numpy as np
+
+from .api import BaseGraph, KmerTable
+
+
+def owner_bounds(n_buckets, world):
+    """Rank r owns the contiguous bucket range [bounds[r], bounds[r+1])."""
+    return [(r * n_buckets) // world for r in range(world + 1)]
+
+
+def split_by_owner(counts, world):
+    """Per-destination slices of this rank's bucket histogram (list of uint32 arrays)."""
+    b = owner_bounds(len(counts), world)
+    return [np.ascontiguousarray(counts[b[r]:b[r + 1]]) for r in range(world)]
+
+
+def min_bucket_bits(world):
+    return max(0, math.ceil(math.log2(world))) if world > 1 else 0
+
+
+def exchange_counts(per_dst, group=None, device="cpu"):
+    """All-to-all of the per-bucket record counts: per_dst[r] goes to rank r; returns the list indexed by
+    source rank of counts for THIS rank's buckets."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    n_mine = len(per_dst[rank])
+    send = [torch.from_numpy(x.astype(np.int64)).to(device) for x in per_dst]
+    recv = [torch.empty(n_mine, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_to_all(recv, send, group=group) if device != "cpu" else _all_to_all_via_gather(recv, send, group)
+    return [r.cpu().numpy().astype(np.uint32) for r in recv]
+
+
+def _all_to_all_via_gather(recv, send, group):
+    """gloo has no all_to_all: emulate with one gather-style exchange per destination (CPU tests only)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    for dst in range(world):
+        bufs = [torch.empty_like(send[dst]) for _ in range(world)] if rank == dst else None
+        dist.gather(send[dst], bufs, dst=dst, group=group)
+        if rank == dst:
+            for s in range(world):
+                recv[s].copy_(bufs[s])
+
+
+class _DevView:
+    """Zero-copy torch view of a device buffer owned by the library (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def _as_tensor(ptr, nbytes, device):
+    import torch
+    if nbytes == 0:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.as_tensor(_DevView(ptr, nbytes), device=device)
+
+
+def filter_kmers_sharded(seqs, summarizer, stranded, k=31, group=None, report_all_kmers=False, timings=None):
+    """filter::filter_kmers over ALL ranks' sequences; returns this rank's shard of the table (its buckets)."""
+    import torch
+    import torch.distributed as dist
+    ctx, L = seqs.ctx, seqs.ctx._L
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", ctx.device)
+    n_local = L.dbg_seqset_count_kmers(ctx._h, k, seqs._h)
+    tot = torch.tensor([n_local], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot, group=group)
+    n_total = int(tot.item())
+    p, bits = C.c_int(), C.c_int()
+    ctx.check(L.dbg_plan_filter(ctx._h, k, n_total, C.byref(p), C.byref(bits)))
+    bbits = max(bits.value, min_bucket_bits(world))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timings is not None else None
+    if ev:
+        ev[0].record()
+    part = C.c_void_p()
+    ctx.check(L.dbg_partition_reads(ctx._h, k, seqs._h, int(bool(stranded)), p.value, bbits, C.byref(part)))
+    try:
+        nb = 1 << bbits
+        counts = np.zeros(nb, np.uint32)
+        ctx.check(L.dbg_partition_bucket_counts(part, C.c_void_p(counts.ctypes.data)))
+        per_dst = split_by_owner(counts, world)
+        recv_counts = exchange_counts(per_dst, group, device=dev)
+        rec_bytes = L.dbg_partition_record_bytes(part)
+        send_rec = [int(x.sum(dtype=np.uint64)) for x in per_dst]
+        recv_rec = [int(x.sum(dtype=np.uint64)) for x in recv_counts]
+        send = _as_tensor(L.dbg_partition_records_dev(part), L.dbg_partition_n_records(part) * rec_bytes, dev)
+        recv = torch.empty(sum(recv_rec) * rec_bytes, dtype=torch.uint8, device=dev)
+        if ev:
+            ev[1].record()
+        # the single data-path collective: super-k-mer records by owning rank, over NCCL / NVLink
+        dist.all_to_all_single(recv, send, [r * rec_bytes for r in recv_rec], [s * rec_bytes for s in send_rec], group=group)
+        if ev:
+            ev[2].record()
+        torch.cuda.synchronize(dev)
+    finally:
+        L.dbg_partition_free(part)
+    h_counts = np.ascontiguousarray(np.stack(recv_counts).astype(np.uint32))
+    th = C.c_void_p()
+    ctx.check(L.dbg_filter_from_records(ctx._h, k, C.c_void_p(recv.data_ptr()), sum(recv_rec),
+                                        C.c_void_p(h_counts.ctypes.data), world, h_counts.shape[1], n_total,
+                                        summarizer.min_kmer_obs, int(bool(stranded)), int(bool(report_all_kmers)),
+                                        C.byref(th)))
+    if ev:
+        ev[3].record()
+        torch.cuda.synchronize(dev)
+        timings.update(ms_partition=ev[0].elapsed_time(ev[1]), ms_exchange=ev[1].elapsed_time(ev[2]),
+                       ms_count_sort=ev[2].elapsed_time(ev[3]), exchange_bytes_sent=sum(send_rec) * rec_bytes,
+                       n_input_total=n_total, bucket_bits=bbits)
+    return KmerTable(ctx, th)
+
+
+def gather_table(table, group=None):
+    """Union of every rank's shard on every rank, ascending (sorted again on the device)."""
+    import torch
+    import torch.distributed as dist
+    ctx, L = table.ctx, table.ctx._L
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", ctx.device)
+    k, n = table.k, len(table)
+    two = k > 32
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    mine = torch.tensor([n], dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sizes, mine, group=group)
+    sizes = [int(x) for x in sizes.tolist()]
+    mx, total = max(sizes), sum(sizes)
+    lo, hi, ex, cn = (C.c_void_p() for _ in range(4))
+    ctx.check(L.dbg_table_device_ptrs(table._h, C.byref(lo), C.byref(hi), C.byref(ex), C.byref(cn)))
+
+    def gather(ptr, itemsize):
+        pad = torch.zeros(mx * itemsize, dtype=torch.uint8, device=dev)
+        if n:
+            pad[: n * itemsize] = _as_tensor(ptr.value, n * itemsize, dev)
+        out = torch.empty(world * mx * itemsize, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, pad, group=group)
+        return torch.cat([out[r * mx * itemsize: r * mx * itemsize + sizes[r] * itemsize] for r in range(world)])
+
+    ctx.synchronize()
+    g_lo = gather(lo, 8)
+    g_hi = gather(hi, 8) if two else None
+    g_ex = gather(ex, 1)
+    g_cn = gather(cn, 2)
+    torch.cuda.synchronize(dev)
+    th = C.c_void_p()
+    ctx.check(L.dbg_table_from_device(ctx._h, k, total, C.c_void_p(g_lo.data_ptr()),
+                                      C.c_void_p(g_hi.data_ptr()) if two else None, C.c_void_p(g_ex.data_ptr()),
+                                      C.c_void_p(g_cn.data_ptr()), C.byref(th)))
+    return KmerTable(ctx, th)
+
+
+def reads_to_graph_sharded(seqs, summarizer, spec, stranded=False, k=31, group=None, timings=None):
+    """filter_kmers (bucket-sharded, one all-to-all) -> gather -> compress_kmers_with_hash (replicated)."""
+    import torch
+    from .api import compress_kmers_with_hash
+    shard = filter_kmers_sharded(seqs, summarizer, stranded, k=k, group=group, timings=timings)
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t2 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    full = gather_table(shard, group)
+    t1.record()
+    shard.free()
+    g = compress_kmers_with_hash(stranded, spec, full)
+    t2.record()
+    if timings is not None:
+        torch.cuda.synchronize()
+        timings.update(ms_gather=t0.elapsed_time(t1), ms_compress=t1.elapsed_time(t2), n_valid_total=len(full))
+    full.free()
+    return g

@@ -1,0 +1,66 @@
+"""world_size-2 gloo tests (CPU) of the host-side logic of the multi-GPU path: bucket ownership, the
+per-bucket count exchange, and the offsets dbg_filter_from_records derives from it.  The records themselves
+move on GPUs (tests/test_gpu_parity.py::test_sharded_two_gpus and tools/sharded_check.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nb, out):
+    import torch.distributed as dist
+
+    from rust_debruijn_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    counts = rng.integers(0, 50, size=nb).astype(np.uint32)      # this rank's per-bucket record counts
+    per_dst = sharded.split_by_owner(counts, world)
+    recv = sharded.exchange_counts(per_dst, device="cpu")
+    out[rank] = (counts, [r.copy() for r in recv])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nb", [(2, 16), (2, 1), (3, 8)])
+def test_count_exchange_gloo(world, nb):
+    import torch.multiprocessing as mp
+
+    from rust_debruijn_b200 import sharded
+    if nb < world:
+        nb = world
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, nb, out), nprocs=world, join=True)
+    bounds = sharded.owner_bounds(nb, world)
+    assert bounds[0] == 0 and bounds[-1] == nb and all(bounds[i] <= bounds[i + 1] for i in range(world))
+    for dst in range(world):
+        _, recv = out[dst]
+        for src in range(world):
+            sent = out[src][0][bounds[dst]:bounds[dst + 1]]
+            assert np.array_equal(recv[src], sent), (src, dst)
+    # every bucket has exactly one owner and nothing is lost
+    total_sent = sum(int(out[r][0].sum()) for r in range(world))
+    total_recv = sum(int(sum(x.sum() for x in out[r][1])) for r in range(world))
+    assert total_sent == total_recv
+
+
+def test_owner_bounds_properties():
+    from rust_debruijn_b200 import sharded
+    for world in (1, 2, 3, 4, 8):
+        assert sharded.min_bucket_bits(world) == int(np.ceil(np.log2(world))) if world > 1 else True
+        for bits in range(sharded.min_bucket_bits(world), 12):
+            b = sharded.owner_bounds(1 << bits, world)
+            sizes = np.diff(b)
+            assert sizes.min() >= 1 and sizes.max() - sizes.min() <= 1
