@@ -192,40 +192,59 @@ def main():
     ss = D.SeqSet.synth(ctx, R, 1 + rank, ERR_THR_NOISY)
     filt, spec = D.CountFilter(MIN_OBS), D.SimpleCompress(D.SAT_ADD)
 
+    from rust_debruijn_b200 import sharded
+    last_tm = {}
+
     def step():
-        g = D.reads_to_graph(ss, filt, spec, stranded=False, k=K)
+        if world > 1:
+            # one job over all ranks: MSP-bucket-sharded filter_kmers (one NCCL all-to-all of super-k-mer records),
+            # valid k-mers gathered, compress replicated on every rank (SURVEY §8e fallback for S3-S6)
+            last_tm.clear()
+            g = sharded.reads_to_graph_sharded(ss, filt, spec, stranded=False, k=K, timings=last_tm)
+        else:
+            g = D.reads_to_graph(ss, filt, spec, stranded=False, k=K)
         n = len(g)
         g.free()
         return n
 
     for _ in range(args.warmup):
         step()
-    st0 = ctx.stats()
-    barrier()
-    sampler = ClockSampler(local)
-    if not args.no_clocks:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
-    walls = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        step()
-        walls.append(round((time.perf_counter() - t0) * 1e3, 2))
-    e1.record(ext)
-    barrier()
-    clocks = sampler.stop() if not args.no_clocks else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler off"]}
-    print(f"[bench] rank {rank} per-step wall ms: {walls}", file=sys.stderr)
-    ms_total = e0.elapsed_time(e1)
-    st1 = ctx.stats()
-    n_kmers = st1["n_input_kmers"]
+
+    def timed_run():
+        st0 = ctx.stats()
+        barrier()
+        sampler = ClockSampler(local)
+        if not args.no_clocks:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        walls = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            step()
+            walls.append(round((time.perf_counter() - t0) * 1e3, 2))
+        e1.record(ext)
+        barrier()
+        clocks = sampler.stop() if not args.no_clocks else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler off"]}
+        print(f"[bench] rank {rank} per-step wall ms: {walls}", file=sys.stderr)
+        return e0.elapsed_time(e1), st0, ctx.stats(), clocks
+
+    ms_total, st0, st1, clocks = timed_run()
+    remeasured = None
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks.get("reasons", []))
+    if world == 1 and (bad or ms_total / args.steps > 1.6 * (st1["ms_filter_total"] + st1["ms_compress_total"])):
+        # a throttled run, or one whose wall time is far above the sum of its own device stage timers (host
+        # interference on a shared box), is re-measured ONCE (B200_PROFILING.md timing hygiene); both are kept
+        remeasured = {"first_ms_per_step": ms_total / args.steps, "reason": sorted(bad) or ["wall >> device stage time"]}
+        ms_total, st0, st1, clocks = timed_run()
+    n_kmers = R * (150 - K + 1)
 
     # ---- e2e: host pinned buffers in, BaseGraph arrays out, through the C-ABI host entry point ----
     hw, hs, hl = ss.copy_out()
     pw = torch.empty(len(hw), dtype=torch.int64, pin_memory=True)
     pw.numpy()[:] = hw.view(np.int64)
     words_pinned = pw.numpy().view(np.uint64)
-    M0, nb0 = st1["n_nodes"], st1["n_bases"]
+    M0, nb0 = st1["n_nodes"], st1["n_bases"]  # world > 1: the gathered, complete graph (same on every rank)
     cap_nodes, cap_words = int(M0 * 1.05) + 16, int(nb0 * 1.05) // 32 + 16
     out_bufs = {
         "words": torch.empty(cap_words, dtype=torch.int64, pin_memory=True),
@@ -239,8 +258,14 @@ def main():
 
     def e2e_step():
         gh = C.c_void_p()
-        ctx.check(L.dbg_reads_to_graph_host_uniform(ctx._h, K, C.c_void_p(words_pinned.ctypes.data), len(words_pinned),
-                                                    len(hs), 150, None, MIN_OBS, 0, D.SAT_ADD, None, C.byref(gh)))
+        if world > 1:
+            sse = D.SeqSet.upload_uniform(ctx, words_pinned, len(hs), 150)
+            ge = sharded.reads_to_graph_sharded(sse, filt, spec, stranded=False, k=K)
+            sse.free()
+            gh, ge._h = ge._h, None
+        else:
+            ctx.check(L.dbg_reads_to_graph_host_uniform(ctx._h, K, C.c_void_p(words_pinned.ctypes.data), len(words_pinned),
+                                                        len(hs), 150, None, MIN_OBS, 0, D.SAT_ADD, None, C.byref(gh)))
         m, nw = L.dbg_graph_len(gh), L.dbg_graph_n_words(gh)
         assert m <= cap_nodes and nw <= cap_words
         ctx.check(L.dbg_graph_copy_out(gh, C.c_void_p(out_bufs["words"].data_ptr()), C.c_void_p(out_bufs["start"].data_ptr()),
@@ -274,7 +299,7 @@ def main():
         value = total_kmers / (ms_step * 1e-3)
         e2e_value = total_kmers / (ms_e2e / args.steps * 1e-3)
         # roofline of the dominant kernel (SURVEY.md §8(d) algorithmic bytes: S1 = 150R/4 + 9N, S2 = 9N + 11V)
-        N, V = st1["n_input_kmers"], st1["n_valid"]
+        N, V = n_kmers, st1["n_valid"] if world == 1 else last_tm.get("n_valid_total", 0) // world
         cand = {"msp_partition_kernel": (st1["ms_k_partition"], 150 * R / 4 + 9 * N),
                 "count_kernel": (st1["ms_k_count"], 9 * N + 11 * V)}
         dom = max(cand, key=lambda k_: cand[k_][0])
@@ -291,8 +316,10 @@ def main():
                        "k": K, "reads_per_gpu": R, "input_kmers_per_gpu": N, "valid_kmers": V, "nodes": st1["n_nodes"],
                        "node_bases": st1["n_bases"], "msp_p": st1["msp_p"], "bucket_bits": st1["bucket_bits"],
                        "l2": "inputs and every intermediate exceed the 126 MB L2; no flush needed",
-                       "parallelism": "replicas" if world > 1 else "single"},
-            "clocks": clocks,
+                       "parallelism": ("MSP-bucket-sharded filter_kmers (one NCCL all-to-all of super-k-mer records) + "
+                                       "gathered table, compress replicated per rank") if world > 1 else "single",
+                       "sharded_stage_ms": {k_: (round(v, 3) if isinstance(v, float) else v) for k_, v in last_tm.items()}},
+            "clocks": clocks, "remeasured": remeasured,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(st1["gpu_launches"] - st0["gpu_launches"]),

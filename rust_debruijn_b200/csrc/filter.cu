@@ -1296,6 +1296,7 @@ int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int
     if (rc != DBG_OK) { delete reinterpret_cast<dbg_partition*>(P); return rc; }
     rc = sync(c);
     if (rc != DBG_OK) { delete reinterpret_cast<dbg_partition*>(P); return rc; }
+    if (N) cudaEventElapsedTime(&c->stats.ms_k_partition, c->ev[8], c->ev[9]);
     P->n_rec = po.n_rec;
     P->rec = po.rec.p ? po.rec.take() : nullptr;
     P->bucket_count = po.bucket_count.take();
