@@ -312,7 +312,8 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": {"workload": f"configs[1]: K=31, {R} x 150bp synth-v1 noisy reads per GPU (e=0.5%, 50x), "
-                                   "CountFilter(2), SimpleCompress(sat_add), stranded=false, all MSP buckets on one GPU",
+                                   "CountFilter(2), SimpleCompress(sat_add), stranded=false, " +
+                                   ("all MSP buckets on one GPU" if world == 1 else f"one job of {world * R} reads, MSP buckets sharded over {world} GPUs"),
                        "k": K, "reads_per_gpu": R, "input_kmers_per_gpu": N, "valid_kmers": V, "nodes": st1["n_nodes"],
                        "node_bases": st1["n_bases"], "msp_p": st1["msp_p"], "bucket_bits": st1["bucket_bits"],
                        "l2": "inputs and every intermediate exceed the 126 MB L2; no flush needed",

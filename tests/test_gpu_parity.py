@@ -202,6 +202,23 @@ def test_record_dedup_off(D, ctx, orc):
     c2.close()
 
 
+def test_sharded_two_gpus():
+    """MSP-bucket-sharded filter_kmers over 2 ranks (one NCCL all-to-all) + gathered compress: BaseGraph
+    bit-identical to the oracle run on the union of both ranks' reads.  Needs >= 2 GPUs (skipped otherwise)."""
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "sharded_check.py"),
+                        "--reads", "20000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("BIT-EXACT") == 3 and "MISMATCH" not in r.stdout
+
+
 def test_compress_kmers_slice_variant(D, ctx, orc):
     """compression::compress_kmers (src/compression.rs:598-615): unordered (k-mer, (exts, data)) slice."""
     ss = orc.synth_reads(1500, 1, orc.ERR_THR_NOISY)
