@@ -342,6 +342,17 @@ def compress_kmers(stranded, spec, kmer_exts, k=31, ctx=None):
         t.free()
 
 
+def msp_kmer_buckets(seqs, k, p, stranded=False):
+    """msp::msp_sequence (src/msp.rs:279-324, identity permutation, rc = !stranded): MspIntervalP::bucket() of the
+    interval every k-mer falls in, sequence-major, one u32 per k-mer start."""
+    ctx = seqs.ctx
+    _, _, length = seqs.copy_out()
+    n = int(np.maximum(length.astype(np.int64) - k + 1, 0).sum())
+    out = np.zeros(n, np.uint32)
+    ctx.check(ctx._L.dbg_msp_kmer_buckets(ctx._h, k, p, seqs._h, int(bool(stranded)), _ptr(out), n))
+    return out
+
+
 def reads_to_graph(seqs, summarizer, spec, stranded=False, k=31, keep_table=False):
     """Fused filter_kmers -> compress_kmers_with_hash with the table kept on the device."""
     ctx = seqs.ctx

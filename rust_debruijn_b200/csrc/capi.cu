@@ -605,8 +605,10 @@ int dbg_reads_to_graph_host_uniform(dbg_ctx* ctx, int k, const uint64_t* words, 
 int dbg_msp_kmer_buckets(dbg_ctx* ctx, int k, int p, const dbg_seqset* seqs, int stranded, uint32_t* out_bucket,
                          uint64_t n_out) {
     if (!ctx) return DBG_E_BADARG;
-    (void)k; (void)p; (void)seqs; (void)stranded; (void)out_bucket; (void)n_out;
-    DBG_SET_ERR(CTX(ctx), DBG_E_INTERNAL, "dbg_msp_kmer_buckets: not built yet");
+    NULLCHK(ctx, seqs);
+    if (n_out && !out_bucket) DBG_SET_ERR(CTX(ctx), DBG_E_BADARG, "null output");
+    cudaSetDevice(ctx->c.device);
+    return msp_kmer_buckets_dev(CTX(ctx), k, p, &seqs->s, stranded != 0, out_bucket, n_out);
 }
 
 }  // extern "C"

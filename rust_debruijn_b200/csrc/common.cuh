@@ -236,6 +236,7 @@ int compress_dev(Ctx* c, const Table* t, int stranded, int reduce_op, Graph** ou
 void plan_filter(const Ctx* c, int k, u64 N, int* p_out, int* bbits_out);
 int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int bbits, Partition** out);
 void free_partition(Partition* P);
+int msp_kmer_buckets_dev(Ctx* c, int k, int p, const SeqSet* s, int stranded, u32* h_out, u64 n_out);
 int filter_from_records_dev(Ctx* c, int k, const u64* d_records, u64 n_records, const u32* h_counts, u32 n_src, u32 n_local,
                             u64 n_input_total, u32 min_obs, int stranded, int report_all, Table** out);
 int synth_reads_dev(Ctx* c, u64 R, u64 seed, u32 err_thr, SeqSet** out);

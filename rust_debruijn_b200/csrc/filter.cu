@@ -1411,4 +1411,68 @@ int filter_from_records_dev(Ctx* c, int k, const u64* d_records, u64 n_records, 
     return DBG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// msp::msp_sequence bucket of every k-mer under the reference's DEFAULT (identity) permutation:
+// bucket(k-mer) = min_rc(argmin p-mer).to_u64() (src/msp.rs:115-117, 305-311).  With rc = !stranded and an
+// injective score this is a pure function of the k-mer: the smallest (canonical) p-mer value in its window.
+// ------------------------------------------------------------------------------------------------
+__global__ void msp_bucket_kernel(const u64* __restrict__ words, u64 n_words, const u64* __restrict__ start,
+                                  const u32* __restrict__ length, u32 uniform_len, u64 n_seqs, const u64* __restrict__ koff,
+                                  u64 n_out, int k, int p, int stranded, u32* __restrict__ out) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_out) return;
+    u64 lo = 0, hi = n_seqs;  // last sequence with koff[i] <= t
+    while (lo < hi) { u64 m = (lo + hi) >> 1; if (koff[m] <= t) lo = m + 1; else hi = m; }
+    u64 si = lo - 1;
+    u64 st = uniform_len ? si * (u64)uniform_len : start[si];
+    u64 j = t - koff[si];
+    u32 best = 0xffffffffu, bestv = 0;
+    for (int q = 0; q <= k - p; q++) {
+        u64 b = st + j + q;
+        u64 wi = b >> 5;
+        int sh = (int)(b & 31) * 2;
+        u64 h = wi < n_words ? words[wi] : 0, l = (wi + 1) < n_words ? words[wi + 1] : 0;
+        u64 v = sh ? (h << sh) | (l >> (64 - sh)) : h;
+        u32 x = (u32)(v >> (64 - 2 * p));
+        u32 r = (~rev2_32(x)) >> (32 - 2 * p);
+        u32 canon = x < r ? x : r;
+        u32 score = stranded ? x : canon;  // rc = !stranded (msp.rs:305-311)
+        if (score < best) { best = score; bestv = canon; }   // bucket() canonicalises regardless (msp.rs:115-117)
+    }
+    out[t] = bestv;
+}
+
+__global__ void kmer_count_kernel(const u32* __restrict__ length, u32 uniform_len, u64 n, int k, u32* cnt) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 L = uniform_len ? uniform_len : length[i];
+    cnt[i] = L >= (u32)k ? L - k + 1 : 0;
+}
+
+int msp_kmer_buckets_dev(Ctx* c, int k, int p, const SeqSet* s, int stranded, u32* h_out, u64 n_out) {
+    if (p < 1 || p > 16 || p > k || k > 64 || k < 2) DBG_SET_ERR(c, DBG_E_BADARG, "need 1 <= p <= min(k,16), 2 <= k <= 64");
+    TRY(arena_begin(c));
+    cudaStream_t st = c->stream;
+    if (!s->n_seqs) {
+        if (n_out) DBG_SET_ERR(c, DBG_E_BADARG, "n_out does not match the number of k-mers (0)");
+        return DBG_OK;
+    }
+    DBuf<u32> cnt, d_out;
+    DBuf<u64> koff, tot;
+    TRY(cnt.alloc(c, s->n_seqs)); TRY(koff.alloc(c, s->n_seqs)); TRY(tot.alloc(c, 1));
+    kmer_count_kernel<<<grid_for(s->n_seqs, 256), 256, 0, st>>>(s->length, s->uniform_len, s->n_seqs, k, cnt.p);
+    TRY(check_launch(c, "kmer_count"));
+    TRY(exclusive_scan_u32_to_u64(c, cnt.p, koff.p, s->n_seqs, tot.p));
+    u64 total = 0;
+    TRY(read_u64(c, tot.p, &total));
+    if (total != n_out) DBG_SET_ERR(c, DBG_E_BADARG, "n_out=%llu but the sequences hold %llu k-mers", (unsigned long long)n_out, (unsigned long long)total);
+    if (!total) return DBG_OK;
+    TRY(d_out.alloc(c, total));
+    msp_bucket_kernel<<<grid_for(total, 256), 256, 0, st>>>(s->words, s->n_words, s->start, s->length, s->uniform_len, s->n_seqs,
+                                                            koff.p, total, k, p, stranded, d_out.p);
+    TRY(check_launch(c, "msp_bucket"));
+    CU(c, cudaMemcpyAsync(h_out, d_out.p, total * 4, cudaMemcpyDeviceToHost, st));
+    return sync(c);
+}
+
 }  // namespace dbg

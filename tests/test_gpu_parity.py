@@ -202,6 +202,27 @@ def test_record_dedup_off(D, ctx, orc):
     c2.close()
 
 
+@pytest.mark.parametrize("k,p", [(31, 6), (31, 8), (35, 5), (63, 12), (16, 5)])
+def test_msp_kmer_buckets_match_scanner(D, ctx, orc, k, p):
+    """dbg_msp_kmer_buckets vs the oracle's Scanner::scan (src/msp.rs:207-276): every k-mer of every interval
+    carries the interval's bucket = min_rc(minimizer), identity permutation, rc=true and rc=false."""
+    rng = np.random.default_rng(k * 10 + p)
+    seqs = [random_dna(rng, int(rng.integers(k, 5 * k))) for _ in range(12)] + [np.zeros(3 * k, np.uint8), random_dna(rng, k - 1)]
+    ss = D.SeqSet.upload(ctx, *orc.seqset_from_lists(seqs))
+    for stranded in (False, True):
+        got = D.msp_kmer_buckets(ss, k, p, stranded=stranded)
+        exp = []
+        for sq in seqs:
+            if len(sq) < k:
+                continue
+            iv = orc.msp_scan(k, p, sq, rc=not stranded)
+            per = np.zeros(len(sq) - k + 1, np.uint32)
+            for st, ln, b in zip(iv["start"], iv["len"], iv["bucket"]):
+                per[int(st):int(st) + int(ln) - k + 1] = int(b)
+            exp.append(per)
+        assert np.array_equal(got, np.concatenate(exp))
+
+
 def test_sharded_two_gpus():
     """MSP-bucket-sharded filter_kmers over 2 ranks (one NCCL all-to-all) + gathered compress: BaseGraph
     bit-identical to the oracle run on the union of both ranks' reads.  Needs >= 2 GPUs (skipped otherwise)."""
