@@ -7,7 +7,7 @@
 // greedy walk run with seed order = ascending k-mer (the order filter_kmers produces before
 // BoomHashMap2::new permutes it):
 //
-//   S3 table_build   open-addressed k-mer -> index table in HBM (stands in for BoomHashMap2).
+//   S3 lookup        prefix LUT + binary search over the (already sorted) k-mer array (stands in for BoomHashMap2).
 //   S4 links         per (k-mer, side): the stateless form of try_extend_kmer (:382-444): unique
 //                    extension, neighbour present, neighbour != self, neighbour's extension back is
 //                    unique, no palindromes (unstranded, even K).  Links are symmetric, so components
@@ -35,36 +35,43 @@ __device__ __forceinline__ Kmer<W> load_key(const u64* __restrict__ lo, const u6
     return k;
 }
 
-// ---- S3 -------------------------------------------------------------------------------------------
+// ---- S3: k-mer -> index lookup.  The table arrives sorted (filter.rs:205-219), so instead of building a hash
+// table (the reference's BoomHashMap2) the lookup is a prefix LUT (first index of every top-LB-bit prefix,
+// built with a histogram + exclusive scan) followed by a binary search over the ~8 keys sharing the prefix. ----
 template <int W>
-__global__ void table_build_kernel(const u64* __restrict__ lo, const u64* __restrict__ hi, u64 n, Kmer<W>* tkeys,
-                                   u32* tidx, u64 mask) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Kmer<W> key = load_key<W>(lo, hi, i);
-    u64 slot = Ops<W>::mix(key) & mask;
-    for (;;) {
-        u32 old = atomicCAS(&tidx[slot], NIL, (u32)i);
-        if (old == NIL) { tkeys[slot] = key; return; }
-        slot = (slot + 1) & mask;
-    }
+__device__ __forceinline__ u32 key_prefix(Kmer<W> k, int shift) {  // top bits of the 2K-bit key: key >> shift
+    if constexpr (W == 1) { return (u32)(k.lo >> shift); }
+    else { return shift >= 64 ? (u32)(k.hi >> (shift - 64)) : (u32)((k.hi << (64 - shift)) | (k.lo >> shift)); }
 }
 
 template <int W>
-__device__ __forceinline__ u32 table_find(const Kmer<W>* __restrict__ tkeys, const u32* __restrict__ tidx, u64 mask, Kmer<W> key) {
-    u64 slot = Ops<W>::mix(key) & mask;
-    for (;;) {
-        u32 idx = tidx[slot];
-        if (idx == NIL) return NIL;
-        if (tkeys[slot] == key) return idx;
-        slot = (slot + 1) & mask;
+__global__ void lut_hist_kernel(const u64* __restrict__ lo, const u64* __restrict__ hi, u64 n, int shift, u32* __restrict__ cnt) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 pfx = 0xffffffffu;
+    if (i < n) pfx = key_prefix<W>(load_key<W>(lo, hi, i), shift);
+    // sorted input: lanes of a warp mostly share a prefix -> one atomic per distinct prefix in the warp
+    u32 peers = __match_any_sync(0xffffffffu, pfx);
+    if (i < n && (peers & ((1u << (threadIdx.x & 31)) - 1)) == 0) atomicAdd(&cnt[pfx], (u32)__popc(peers));
+}
+
+template <int W>
+__device__ __forceinline__ u32 table_find(const u64* __restrict__ lo, const u64* __restrict__ hi, const u64* __restrict__ lut,
+                                          int shift, Kmer<W> key) {
+    u32 pfx = key_prefix<W>(key, shift);
+    u64 a = lut[pfx], b = lut[pfx + 1];
+    while (a < b) {
+        u64 m = (a + b) >> 1;
+        Kmer<W> km = load_key<W>(lo, hi, m);
+        if (km == key) return (u32)m;
+        if (km < key) a = m + 1; else b = m;
     }
+    return NIL;
 }
 
 // ---- S4 -------------------------------------------------------------------------------------------
 template <int W>
 __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __restrict__ hi, const u8* __restrict__ exts,
-                             u64 n, const Kmer<W>* __restrict__ tkeys, const u32* __restrict__ tidx, u64 mask,
+                             u64 n, const u64* __restrict__ lut, int lut_shift,
                              int stranded, u32* __restrict__ nxt, u32* __restrict__ err) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -83,7 +90,7 @@ __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __res
                 Kmer<W> r = Ops<W>::rc(kp, nk);
                 if (!(nk < r)) { nk = r; flip = true; }
             }
-            u32 j = table_find<W>(tkeys, tidx, mask, nk);                  // :410
+            u32 j = table_find<W>(lo, hi, lut, lut_shift, nk);             // :410
             if (j != NIL && j != (u32)i) {                                 // not in table / (self => already used) :411-415
                 bool npal = !stranded && is_palindrome<W>(kp, nk);         // :403
                 int inc = (d ^ 1) ^ (flip ? 1 : 0);                        // :419
@@ -358,15 +365,19 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     if (V >= (1ull << 31)) DBG_SET_ERR(c, DBG_E_BADARG, "k-mer table too large for 32-bit port states (%llu)", (unsigned long long)V);
     CU(c, cudaEventRecord(c->ev[0], st));
     // ---- S3 ----
-    u64 cap = 16;
-    while (cap < 2 * V) cap <<= 1;
-    DBuf<Kmer<W>> tkeys;
-    DBuf<u32> tidx;
-    TRY(tkeys.alloc(c, cap));
-    TRY(tidx.alloc(c, cap));
-    TRY(tidx.fill_ff());
-    table_build_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(t->lo, t->hi, V, tkeys.p, tidx.p, cap - 1);
-    TRY(check_launch(c, "table_build"));
+    int lb = 8;
+    while ((1ull << (lb + 4)) <= V && lb < 24) lb++;   // ~8-16 keys per prefix
+    if (lb > 2 * t->k) lb = 2 * t->k;
+    const int lut_shift = 2 * t->k - lb;
+    const u64 n_pfx = 1ull << lb;
+    DBuf<u32> lut_cnt;
+    DBuf<u64> lut;
+    TRY(lut_cnt.alloc(c, n_pfx));
+    TRY(lut.alloc(c, n_pfx + 1));
+    TRY(lut_cnt.zero());
+    lut_hist_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(t->lo, t->hi, V, lut_shift, lut_cnt.p);
+    TRY(check_launch(c, "lut_hist"));
+    TRY(exclusive_scan_u32_to_u64(c, lut_cnt.p, lut.p, n_pfx, lut.p + n_pfx));
     CU(c, cudaEventRecord(c->ev[1], st));
     // ---- S4 ----
     const u64 NS = 2 * V;
@@ -375,7 +386,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     TRY(nxt.alloc(c, NS));
     TRY(ctr.alloc(c, 4));
     TRY(ctr.zero());
-    links_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, V, tkeys.p, tidx.p, cap - 1, stranded, nxt.p,
+    links_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, V, lut.p, lut_shift, stranded, nxt.p,
                                                       (u32*)(ctr.p + 3));
     TRY(check_launch(c, "links"));
     CU(c, cudaEventRecord(c->ev[2], st));
@@ -444,8 +455,6 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
             TRY(check_launch(c, "assign"));
         }
     }
-    tkeys.release();
-    tidx.release();
     CU(c, cudaEventRecord(c->ev[3], st));
     // ---- S6 ----
     derive_seed_kernel<<<grid_for(V, 256), 256, 0, st>>>(seed.p, nlen.p, V, t->k, is_seed.p, node_len.p);

@@ -719,9 +719,12 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                     __syncthreads();
                 }
                 const u32 T = s_pref[P2_RC];
-                for (u32 k0 = threadIdx.x * P2_SEG; k0 < T; k0 += P2_THREADS * P2_SEG) {
+                // segment length: as few rounds as possible with every thread busy (>= P2_SEG to amortise the search)
+                const u32 rounds = (T + P2_THREADS * 16 - 1) / (P2_THREADS * 16);
+                const u32 seg = max((u32)P2_SEG, (T + rounds * P2_THREADS - 1) / (rounds * P2_THREADS));
+                for (u32 k0 = threadIdx.x * seg; k0 < T; k0 += P2_THREADS * seg) {
                     if (*reinterpret_cast<volatile u32*>(&s_overflow)) break;
-                    const u32 k1 = min(T, k0 + (u32)P2_SEG);
+                    const u32 k1 = min(T, k0 + seg);
                     // record holding k-mer k0: largest i with pref[i] <= k0
                     u32 lo = 0, hi = nrc - 1;
                     while (lo < hi) { u32 m = (lo + hi + 1) >> 1; if (s_pref[m] <= k0) lo = m; else hi = m - 1; }
