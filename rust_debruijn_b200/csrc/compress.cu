@@ -118,14 +118,14 @@ __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __res
 // traversed; the walker that started at the smaller-index end then walks again and writes
 // (seed, position, length, orientation) for every k-mer of the unitig.  Paths longer than lmax and cycles
 // are left untouched (nlen stays 0) for the pointer-doubling fallback.
-__global__ void walk_kernel(const u32* __restrict__ nxt, u64 n, u32 lmax, u32* __restrict__ seed, u32* __restrict__ pos,
-                            u32* __restrict__ nlen, u8* __restrict__ flags, u64* __restrict__ written) {
+// vinfo[v] = (seed, position in unitig, unitig length in k-mers [0 = not ranked yet], flags): one 16-byte store
+__global__ void walk_kernel(const u32* __restrict__ nxt, u64 n, u32 lmax, uint4* __restrict__ vinfo, u64* __restrict__ written) {
     u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 wrote = 0;
     if (v < n) {
         u32 a0 = nxt[2 * v], a1 = nxt[2 * v + 1];
         if (a0 == NIL && a1 == NIL) {
-            seed[v] = (u32)v; pos[v] = 0; nlen[v] = 1; flags[v] = 1;
+            vinfo[v] = make_uint4((u32)v, 0u, 1u, 1u);
             wrote = 1;
         } else if (a0 == NIL || a1 == NIL) {
             const u32 d = a0 == NIL ? 1u : 0u;  // the linked side: walk inwards through it
@@ -143,7 +143,7 @@ __global__ void walk_kernel(const u32* __restrict__ nxt, u64 n, u32 lmax, u32* _
                 for (u32 i = 0; i < cnt; i++) {
                     u32 w = cur >> 1, dw = cur & 1u;
                     u32 lp = right ? dw ^ 1u : dw;
-                    seed[w] = minv; pos[w] = right ? i : cnt - 1 - i; nlen[w] = cnt; flags[w] = (u8)((lp == 0) | (lp << 1));
+                    vinfo[w] = make_uint4(minv, right ? i : cnt - 1 - i, cnt, (lp == 0) | (lp << 1));
                     cur = nxt[cur];
                 }
                 wrote = cnt;
@@ -161,13 +161,14 @@ __global__ void pd_init_kernel(const u32* __restrict__ nxt, uint4* __restrict__ 
     if (s < n_states) rec[s] = make_uint4(nxt[s], 1u, (u32)s, 0u);
 }
 
-__global__ void derive_seed_kernel(const u32* __restrict__ seed, const u32* __restrict__ nlen, u64 n, int K,
-                                   u32* __restrict__ is_seed, u64* __restrict__ node_len) {
+__global__ void derive_seed_kernel(const uint4* __restrict__ vinfo, u64 n, int K, u32* __restrict__ is_seed,
+                                   u64* __restrict__ node_len) {
     u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
-    bool issd = seed[v] == (u32)v;
+    uint4 vi = vinfo[v];
+    bool issd = vi.x == (u32)v;
     is_seed[v] = issd;
-    node_len[v] = issd ? (u64)nlen[v] + K - 1 : 0;
+    node_len[v] = issd ? (u64)vi.z + K - 1 : 0;
 }
 
 __device__ __forceinline__ uint4 pd_combine(uint4 a, uint4 t) {
@@ -229,8 +230,7 @@ __global__ void cyc_round_kernel(const u32* __restrict__ list, u64 n, const uint
 // flags: bit0 fwd (k-mer appears in stored orientation), bit1 left_port (side of the k-mer facing the
 // node's left end: 0 = L, 1 = R).
 __global__ void assign_kernel(const uint4* __restrict__ rec, const u32* __restrict__ nxt, const u8* __restrict__ is_cyc,
-                              u64 n, u32* __restrict__ seed, u32* __restrict__ pos, u32* __restrict__ nlen,
-                              u8* __restrict__ flags) {
+                              u64 n, uint4* __restrict__ vinfo) {
     u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     uint4 rl = rec[2 * v], rr = rec[2 * v + 1];
@@ -259,13 +259,13 @@ __global__ void assign_kernel(const uint4* __restrict__ rec, const u32* __restri
         lp = (u32)(p ^ 1);
         fw = lp == 0;
     }
-    seed[v] = sd; pos[v] = ps; nlen[v] = nn; flags[v] = (u8)(fw | (lp << 1));
+    vinfo[v] = make_uint4(sd, ps, nn, fw | (lp << 1));
 }
 
 // ---- S6 ---------------------------------------------------------------------------------------------------
 struct EmitArgs {
     const u64* lo; const u64* hi; const u8* exts; const u16* counts; u64 n;
-    const u32* seed; const u32* pos; const u32* nlen; const u8* flags;
+    const uint4* vinfo;
     const u64* node_id; const u64* node_start;
     u64* words; u64* out_start; u32* out_length; u32* out_exts_w; u64* acc;
     int reduce_op;
@@ -279,7 +279,8 @@ __global__ void emit_kernel(KP kp, EmitArgs a) {
     u64 cnt = 0;
     if (act) {
         const int K = kp.k;
-        u32 sd = a.seed[v], ps = a.pos[v], nn = a.nlen[v], fl = a.flags[v];
+        const uint4 vi = a.vinfo[v];
+        u32 sd = vi.x, ps = vi.y, nn = vi.z, fl = vi.w;
         bool fw = fl & 1;
         int lp = (fl >> 1) & 1;
         nid = a.node_id[sd];
@@ -391,13 +392,13 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     TRY(check_launch(c, "links"));
     CU(c, cudaEventRecord(c->ev[2], st));
     // ---- S5a: walks for short unitigs ----
-    DBuf<u32> seed, pos, nlen, is_seed;
-    DBuf<u8> flags;
+    DBuf<uint4> vinfo;
+    DBuf<u32> is_seed;
     DBuf<u64> node_len, node_id, tot;
-    TRY(seed.alloc(c, V)); TRY(pos.alloc(c, V)); TRY(nlen.alloc(c, V)); TRY(is_seed.alloc(c, V));
-    TRY(flags.alloc(c, V)); TRY(node_len.alloc(c, V)); TRY(node_id.alloc(c, V)); TRY(tot.alloc(c, 2));
-    TRY(nlen.zero());
-    walk_kernel<<<grid_for(V, 256), 256, 0, st>>>(nxt.p, V, 1024u, seed.p, pos.p, nlen.p, flags.p, ctr.p + 2);
+    TRY(vinfo.alloc(c, V)); TRY(is_seed.alloc(c, V));
+    TRY(node_len.alloc(c, V)); TRY(node_id.alloc(c, V)); TRY(tot.alloc(c, 2));
+    TRY(vinfo.zero());
+    walk_kernel<<<grid_for(V, 256), 256, 0, st>>>(nxt.p, V, 1024u, vinfo.p, ctr.p + 2);
     TRY(check_launch(c, "walk"));
     {
         u64 h[4];
@@ -451,13 +452,13 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
                 S.n_cycle_kmers = ncs / 2;
                 S.rank_rounds += cr;
             }
-            assign_kernel<<<grid_for(V, 256), 256, 0, st>>>(src, nxt.p, is_cyc.p, V, seed.p, pos.p, nlen.p, flags.p);
+            assign_kernel<<<grid_for(V, 256), 256, 0, st>>>(src, nxt.p, is_cyc.p, V, vinfo.p);
             TRY(check_launch(c, "assign"));
         }
     }
     CU(c, cudaEventRecord(c->ev[3], st));
     // ---- S6 ----
-    derive_seed_kernel<<<grid_for(V, 256), 256, 0, st>>>(seed.p, nlen.p, V, t->k, is_seed.p, node_len.p);
+    derive_seed_kernel<<<grid_for(V, 256), 256, 0, st>>>(vinfo.p, V, t->k, is_seed.p, node_len.p);
     TRY(check_launch(c, "derive_seed"));
     TRY(exclusive_scan_u32_to_u64(c, is_seed.p, node_id.p, V, tot.p));
     TRY(exclusive_scan_u64(c, node_len.p, node_len.p, V, tot.p + 1));
@@ -475,7 +476,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     TRY(acc.alloc(c, M)); TRY(acc.zero()); TRY(oexts.alloc_pool(c, M)); TRY(odata.alloc_pool(c, M));
     EmitArgs ea;
     ea.lo = t->lo; ea.hi = t->hi; ea.exts = t->exts; ea.counts = t->counts; ea.n = V;
-    ea.seed = seed.p; ea.pos = pos.p; ea.nlen = nlen.p; ea.flags = flags.p;
+    ea.vinfo = vinfo.p;
     ea.node_id = node_id.p; ea.node_start = node_len.p;
     ea.words = words.p; ea.out_start = ostart.p; ea.out_length = olen.p; ea.out_exts_w = oextw.p; ea.acc = acc.p;
     ea.reduce_op = reduce_op;
