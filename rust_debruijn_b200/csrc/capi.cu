@@ -11,6 +11,7 @@ namespace dbg {
 
 void free_seqset(SeqSet* s) {
     if (!s) return;
+    for (int i = 0; i < 8; i++) if (s->pend_ev[i]) cudaEventDestroy(s->pend_ev[i]);
     if (s->owned) {
         cudaStream_t st = s->ctx->stream;
         if (s->words) cudaFreeAsync(s->words, st);
@@ -81,6 +82,7 @@ int synth_reads_dev(Ctx* c, u64 R, u64 seed, u32 err_thr, SeqSet** out) {
     if (R == 0) DBG_SET_ERR(c, DBG_E_BADARG, "n_reads == 0");
     dbg_seqset* h = new (std::nothrow) dbg_seqset();
     SeqSet* s = &h->s;
+    memset(s->pend_ev, 0, sizeof(s->pend_ev));
     s->ctx = c;
     s->n_seqs = R;
     s->n_words = (150 * R + 31) / 32;
@@ -129,6 +131,7 @@ int dbg_ctx_create(int device, dbg_ctx** out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return DBG_E_CUDA; }
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DBG_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->stream); delete h; return DBG_E_CUDA; }
     cudaMemPoolProps pp;
     memset(&pp, 0, sizeof(pp));
     pp.allocType = cudaMemAllocationTypePinned;
@@ -152,6 +155,7 @@ void dbg_ctx_destroy(dbg_ctx* ctx) {
     cudaFreeHost(c->h_scratch);
     if (c->arena) cudaFree(c->arena);
     cudaMemPoolDestroy(c->pool);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete ctx;
 }
@@ -212,6 +216,7 @@ int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, con
     dbg_seqset* h = new (std::nothrow) dbg_seqset();
     if (!h) DBG_SET_ERR(c, DBG_E_OOM, "host allocation failed");
     SeqSet* s = &h->s;
+    memset(s->pend_ev, 0, sizeof(s->pend_ev));
     s->ctx = c; s->n_seqs = n_seqs; s->n_words = n_words; s->max_len = max_len;
     s->uniform_len = uniform ? length[0] : 0;
     s->contiguous = contiguous;
@@ -247,8 +252,8 @@ int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, con
     return DBG_OK;
 }
 
-int dbg_seqset_upload_uniform(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, uint64_t n_seqs, uint32_t read_len,
-                              const uint8_t* seq_exts, dbg_seqset** out) {
+static int upload_uniform_impl(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, uint64_t n_seqs, uint32_t read_len,
+                               const uint8_t* seq_exts, bool pipelined, dbg_seqset** out) {
     if (!ctx || !out) return DBG_E_BADARG;
     Ctx* c = CTX(ctx);
     *out = nullptr;
@@ -258,19 +263,42 @@ int dbg_seqset_upload_uniform(dbg_ctx* ctx, const uint64_t* words, uint64_t n_wo
     dbg_seqset* h = new (std::nothrow) dbg_seqset();
     if (!h) DBG_SET_ERR(c, DBG_E_OOM, "host allocation failed");
     SeqSet* s = &h->s;
+    memset(s->pend_ev, 0, sizeof(s->pend_ev));
     s->ctx = c; s->n_seqs = n_seqs; s->n_words = n_words; s->max_len = read_len; s->uniform_len = read_len;
     s->contiguous = true; s->base0 = 0; s->total_end = n_seqs * (u64)read_len;
     DBuf<u64> dw;
     DBuf<u8> de;
     int rc = dw.alloc_pool(c, n_words + 2);
     if (rc == DBG_OK && cudaMemsetAsync(dw.p + n_words, 0, 16, c->stream) != cudaSuccess) rc = DBG_E_CUDA;
-    if (rc == DBG_OK && cudaMemcpyAsync(dw.p, words, n_words * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = DBG_E_CUDA;
     if (rc == DBG_OK && seq_exts) {
         rc = de.alloc_pool(c, n_seqs);
         if (rc == DBG_OK && cudaMemcpyAsync(de.p, seq_exts, n_seqs, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = DBG_E_CUDA;
     }
+    if (rc == DBG_OK) {
+        const int nch = (pipelined && n_words >= (1u << 22)) ? 8 : 1;   // >= 32 MB: worth overlapping
+        if (nch == 1) {
+            if (cudaMemcpyAsync(dw.p, words, n_words * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = DBG_E_CUDA;
+        } else {
+            // the buffer was allocated on c->stream: order the copy stream after it, then chunked copies + events
+            cudaEvent_t e0;
+            cudaEventCreateWithFlags(&e0, cudaEventDisableTiming);
+            cudaEventRecord(e0, c->stream);
+            cudaStreamWaitEvent(c->copy_stream, e0, 0);
+            cudaEventDestroy(e0);
+            for (int i = 0; i < nch && rc == DBG_OK; i++) {
+                u64 w0 = n_words * i / nch, w1 = n_words * (i + 1) / nch;
+                if (cudaMemcpyAsync(dw.p + w0, words + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess) rc = DBG_E_CUDA;
+                if (rc == DBG_OK && cudaEventCreateWithFlags(&s->pend_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = DBG_E_CUDA;
+                if (rc == DBG_OK && cudaEventRecord(s->pend_ev[i], c->copy_stream) != cudaSuccess) rc = DBG_E_CUDA;
+                s->pend_words_end[i] = w1;
+                s->n_pending = i + 1;
+            }
+        }
+    }
     if (rc != DBG_OK) {
         if (rc == DBG_E_CUDA) c->err = std::string("seqset upload: ") + cudaGetErrorString(cudaGetLastError());
+        cudaStreamSynchronize(c->copy_stream);
+        for (int i = 0; i < 8; i++) if (s->pend_ev[i]) cudaEventDestroy(s->pend_ev[i]);
         delete h;
         return rc;
     }
@@ -278,6 +306,11 @@ int dbg_seqset_upload_uniform(dbg_ctx* ctx, const uint64_t* words, uint64_t n_wo
     if (seq_exts) s->seq_exts = de.take();
     *out = h;
     return DBG_OK;
+}
+
+int dbg_seqset_upload_uniform(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, uint64_t n_seqs, uint32_t read_len,
+                              const uint8_t* seq_exts, dbg_seqset** out) {
+    return upload_uniform_impl(ctx, words, n_words, n_seqs, read_len, seq_exts, false, out);
 }
 
 int dbg_seqset_wrap_device(dbg_ctx* ctx, const uint64_t* d_words, uint64_t n_words, const uint64_t* d_start,
@@ -290,6 +323,7 @@ int dbg_seqset_wrap_device(dbg_ctx* ctx, const uint64_t* d_words, uint64_t n_wor
     dbg_seqset* h = new (std::nothrow) dbg_seqset();
     if (!h) DBG_SET_ERR(c, DBG_E_OOM, "host allocation failed");
     SeqSet* s = &h->s;
+    memset(s->pend_ev, 0, sizeof(s->pend_ev));
     s->ctx = c; s->owned = false;
     s->words = (u64*)d_words; s->n_words = n_words;
     s->start = (u64*)d_start; s->length = (u32*)d_length; s->seq_exts = (u8*)d_seq_exts;
@@ -312,9 +346,10 @@ uint64_t dbg_seqset_n_words(const dbg_seqset* s) { return s ? s->s.n_words : 0; 
 
 int dbg_seqset_copy_out(const dbg_seqset* h, uint64_t* words, uint64_t* start, uint32_t* length) {
     if (!h) return DBG_E_BADARG;
-    const SeqSet* s = &h->s;
+    SeqSet* s = const_cast<SeqSet*>(&h->s);
     Ctx* c = s->ctx;
     cudaSetDevice(c->device);
+    TRY(seqset_ready(c, s));
     if (words && s->n_words) CU(c, cudaMemcpyAsync(words, s->words, s->n_words * 8, cudaMemcpyDeviceToHost, c->stream));
     if (s->uniform_len && (!s->start || !s->length)) {
         for (u64 i = 0; i < s->n_seqs; i++) {
@@ -595,9 +630,12 @@ int dbg_reads_to_graph_host_uniform(dbg_ctx* ctx, int k, const uint64_t* words, 
     if (!ctx || !graph_out) return DBG_E_BADARG;
     *graph_out = nullptr;
     dbg_seqset* s = nullptr;
-    int rc = dbg_seqset_upload_uniform(ctx, words, n_words, n_seqs, read_len, seq_exts, &s);
+    // pipelined: the packed reads go up in chunks on the copy stream while the partition kernel already works on
+    // the chunks that have arrived (the host buffer stays borrowed until this call returns)
+    int rc = upload_uniform_impl(ctx, words, n_words, n_seqs, read_len, seq_exts, true, &s);
     if (rc != DBG_OK) return rc;
     rc = dbg_reads_to_graph(ctx, k, s, min_kmer_obs, stranded, reduce_op, table_out, graph_out);
+    cudaStreamSynchronize(ctx->c.copy_stream);
     dbg_seqset_free(s);
     return rc;
 }

@@ -16,6 +16,7 @@ struct Ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host->device uploads that overlap the partition kernel
     cudaMemPool_t pool = nullptr;
     std::string err;
     dbg_stats stats;
@@ -174,6 +175,10 @@ struct SeqSet {
     bool contiguous = false;  // start[i+1] == start[i] + length[i] (PackedDnaStringSet::add layout)
     u64 base0 = 0, total_end = 0;  // global base range [start[0], start[n-1] + length[n-1]) when contiguous
     bool owned = true;
+    // pipelined upload (fused host entry points): chunk i of `words` is on the device once pend_ev[i] fired
+    int n_pending = 0;
+    cudaEvent_t pend_ev[8];
+    u64 pend_words_end[8];
 };
 
 struct Table {
@@ -210,6 +215,13 @@ struct Partition {
     u32* bucket_count = nullptr; // 2^bbits
     u64* bucket_off = nullptr;   // 2^bbits + 1
 };
+
+// Make every pending upload chunk of a sequence set visible to the ctx stream.
+inline int seqset_ready(Ctx* c, SeqSet* s) {
+    for (int i = 0; i < s->n_pending; i++) CU(c, cudaStreamWaitEvent(c->stream, s->pend_ev[i], 0));
+    s->n_pending = 0;
+    return DBG_OK;
+}
 
 }  // namespace dbg
 // the opaque C handles are thin wrappers (first member) so stage code can allocate them directly

@@ -197,7 +197,8 @@ static const int T1_QCAP = TP;                       // CTA queue of closed runs
 struct TileArgs {
     u64 base0;      // global position of the first base (start[0])
     u64 total_end;  // global position one past the last base
-    u64 n_tiles;
+    u64 tile0;      // first tile of this launch
+    u64 n_tiles;    // one past the last tile of this launch
 };
 
 __device__ __forceinline__ u32 s32_bits(const u32* s32, u32 b) {  // 32 bits starting at staged base b
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = kp.k, p = a.p, wlen = K - p + 1;
 
-    for (u64 tile = blockIdx.x; tile < ta.n_tiles; tile += gridDim.x) {
+    for (u64 tile = ta.tile0 + blockIdx.x; tile < ta.n_tiles; tile += gridDim.x) {
         const u64 g0 = ta.base0 + tile * (u64)TP;                 // global position of tile-relative x = 0
         const u64 sb = (g0 > ta.base0 ? g0 - 1 : g0) & ~31ull;    // staged origin (32-base aligned), covers the left flank
         const u32 ofs = (u32)(g0 - sb);                           // staged index of x = 0
@@ -1078,8 +1079,10 @@ static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, 
     TRY(bucket_fill.alloc(c, NB));
     TRY(ctr.alloc(c, 8));
     TileArgs ta;
-    ta.base0 = s->base0; ta.total_end = s->total_end;
+    ta.base0 = s->base0; ta.total_end = s->total_end; ta.tile0 = 0;
     ta.n_tiles = use_tiles ? (s->total_end - s->base0 + TP - 1) / TP : 0;
+    SeqSet* sm = const_cast<SeqSet*>(s);
+    if (!use_tiles) TRY(seqset_ready(c, sm));
     u32 grid1 = use_tiles ? (u32)std::min<u64>(ta.n_tiles, (u64)c->sm_count * 6)
                           : (u32)std::min<u64>((n_items + P1_WARPS - 1) / P1_WARPS, (u64)c->sm_count * 6);
     u64 n_warps = (u64)grid1 * P1_WARPS;
@@ -1101,9 +1104,30 @@ static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, 
         a.rec = stage_rec.p; a.rec_bucket = stage_bucket.p; a.capacity = capacity;
         a.cursor = ctr.p; a.bucket_count = po.bucket_count.p; a.overflow = (u32*)(ctr.p + 1);
         CU(c, cudaEventRecord(c->ev[8], st));
-        if (use_tiles) msp_tile_kernel<W><<<grid1, T1_THREADS, 0, st>>>(kp, a, ta);
-        else msp_partition_kernel<W><<<grid1, P1_THREADS, 0, st>>>(kp, a);
-        TRY(check_launch(c, "msp_partition"));
+        if (use_tiles && sm->n_pending > 0) {
+            // pipelined upload: one launch per arrived chunk, covering the tiles whose bases (plus halo) are on the device
+            u64 done = 0;
+            const int np = sm->n_pending;
+            for (int ci = 0; ci < np; ci++) {
+                CU(c, cudaStreamWaitEvent(st, sm->pend_ev[ci], 0));
+                u64 bases_ok = sm->pend_words_end[ci] * 32;
+                u64 upto = ci == np - 1 ? ta.n_tiles : (bases_ok > (u64)(TP + 192) ? (bases_ok - 192 - s->base0) / TP : 0);
+                if (upto > ta.n_tiles) upto = ta.n_tiles;
+                if (upto > done) {
+                    TileArgs tc = ta;
+                    tc.tile0 = done; tc.n_tiles = upto;
+                    u32 g = (u32)std::min<u64>(upto - done, (u64)c->sm_count * 6);
+                    msp_tile_kernel<W><<<g, T1_THREADS, 0, st>>>(kp, a, tc);
+                    TRY(check_launch(c, "msp_partition"));
+                    done = upto;
+                }
+            }
+            sm->n_pending = 0;
+        } else {
+            if (use_tiles) msp_tile_kernel<W><<<grid1, T1_THREADS, 0, st>>>(kp, a, ta);
+            else msp_partition_kernel<W><<<grid1, P1_THREADS, 0, st>>>(kp, a);
+            TRY(check_launch(c, "msp_partition"));
+        }
         CU(c, cudaEventRecord(c->ev[9], st));
         u64 h[2];
         TRY(read_u64(c, ctr.p, h, 2));
