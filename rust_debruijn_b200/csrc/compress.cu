@@ -154,11 +154,55 @@ __global__ void walk_kernel(const u32* __restrict__ nxt, u64 n, u32 lmax, uint4*
     if ((threadIdx.x & 31) == 0 && wrote) atomicAdd(written, (u64)wrote);
 }
 
-// rec = (ptr, len, minst, mindist): window of `len` consecutive states starting at s; minst = the
-// state at which the smallest-index k-mer of the window is traversed; mindist = steps from s to it.
-__global__ void pd_init_kernel(const u32* __restrict__ nxt, uint4* __restrict__ rec, u64 n_states) {
-    u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n_states) rec[s] = make_uint4(nxt[s], 1u, (u32)s, 0u);
+// ---- S5b: long unitigs and cycles by list ranking on a CONTRACTED graph ------------------------------------
+// Among the k-mers the walks left unranked, every path end and ~1/density of the others become SPLITTERS.
+// Each (splitter, side) walks to the next splitter (segment_walk_kernel), which contracts the chains to a
+// graph of splitters whose edges carry (length, smallest index inside, distance to it).  Pointer doubling then
+// runs on the 2 x #splitters reduced port states only; the splitters get (seed, position, orientation) from it
+// and hand them to the k-mers inside their segments with one more walk.  Work is O(V), depth ~density + log.
+// rec = (ptr, len, minst, mindist): window of `len` consecutive k-mers starting at reduced state s; minst = the
+// GLOBAL port state in which the smallest-index k-mer of the window is traversed; mindist = k-mers from s to it.
+__global__ void mark_splitters_kernel(const u32* __restrict__ nxt, const uint4* __restrict__ vinfo, u64 n, u32 density_mask,
+                                      u32* __restrict__ is_spl) {
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    u32 f = 0;
+    if (vinfo[v].z == 0) {  // not ranked by the walks
+        bool end = nxt[2 * v] == NIL || nxt[2 * v + 1] == NIL;
+        f = end || (((u32)v * 0x9E3779B1u >> 8) & density_mask) == 0;
+    }
+    is_spl[v] = f;
+}
+__global__ void fill_splitters_kernel(const u32* __restrict__ is_spl, const u64* __restrict__ sid, u64 n, u32* __restrict__ spl_vertex) {
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n && is_spl[v]) spl_vertex[sid[v]] = (u32)v;
+}
+// thread per reduced state (splitter, side): contract the chain up to the next splitter
+__global__ void segment_walk_kernel(const u32* __restrict__ nxt, const u32* __restrict__ is_spl, const u64* __restrict__ sid,
+                                    const u32* __restrict__ spl_vertex, u64 n_red, u32 cap, uint4* __restrict__ rec0,
+                                    u32* __restrict__ err) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_red) return;
+    u32 v = spl_vertex[r >> 1], d = (u32)r & 1u;
+    u32 st = 2u * v + d;
+    u32 cur = nxt[st];
+    u32 len = 1, minst = st, mind = 0, steps = 0;
+    u32 ptr = NIL;
+    while (cur != NIL) {
+        u32 w = cur >> 1;
+        if (is_spl[w]) { ptr = 2u * (u32)sid[w] + (cur & 1u); break; }
+        if (w < (minst >> 1)) { minst = cur; mind = len; }
+        len++;
+        cur = nxt[cur];
+        if (++steps > cap) { atomicExch(err, 3u); break; }
+    }
+    rec0[r] = make_uint4(ptr, len, minst, mind);
+}
+
+__global__ void count_ranked_kernel(const uint4* __restrict__ vinfo, u64 n, u64* ranked, u64* unused) {
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 m = __ballot_sync(0xffffffffu, v < n && vinfo[v].z != 0);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(ranked, (u64)__popc(m));
 }
 
 __global__ void derive_seed_kernel(const uint4* __restrict__ vinfo, u64 n, int K, u32* __restrict__ is_seed,
@@ -198,8 +242,8 @@ __global__ void pd_round_kernel(const uint4* __restrict__ src, uint4* __restrict
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(active, (u64)__popc(m));
 }
 
-// cycles: collect still-active states, restart them from nxt, run a fixed number of rounds
-__global__ void cyc_collect_kernel(const uint4* __restrict__ cur, u64 n_states, const u32* __restrict__ nxt,
+// cycles: collect still-active reduced states, restart them from their contracted segments, fixed rounds
+__global__ void cyc_collect_kernel(const uint4* __restrict__ cur, u64 n_states, const uint4* __restrict__ rec0,
                                    u32* __restrict__ list, u64* cursor, uint4* __restrict__ a, uint4* __restrict__ b,
                                    u8* __restrict__ is_cyc) {
     u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,7 +252,7 @@ __global__ void cyc_collect_kernel(const uint4* __restrict__ cur, u64 n_states, 
     if (p < NIL2) {
         u64 pos = atomicAdd(cursor, 1ull);
         list[pos] = (u32)s;
-        uint4 r = make_uint4(nxt[s], 1u, (u32)s, 0u);
+        uint4 r = rec0[s];
         a[s] = r;
         b[s] = r;
         is_cyc[s >> 1] = 1;
@@ -228,18 +272,20 @@ __global__ void cyc_round_kernel(const u32* __restrict__ list, u64 n, const uint
 
 // ---- S5 result -> per k-mer (seed, position, orientation) ------------------------------------------------
 // flags: bit0 fwd (k-mer appears in stored orientation), bit1 left_port (side of the k-mer facing the
-// node's left end: 0 = L, 1 = R).
-__global__ void assign_kernel(const uint4* __restrict__ rec, const u32* __restrict__ nxt, const u8* __restrict__ is_cyc,
-                              u64 n, uint4* __restrict__ vinfo) {
-    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n) return;
-    uint4 rl = rec[2 * v], rr = rec[2 * v + 1];
+// node's left end: 0 = L, 1 = R).  Thread per splitter.
+__global__ void assign_splitters_kernel(const uint4* __restrict__ rec, const uint4* __restrict__ rec0,
+                                        const u8* __restrict__ is_cyc, const u32* __restrict__ spl_vertex, u64 n_spl,
+                                        uint4* __restrict__ vinfo, u64* __restrict__ n_cycle_kmers) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_spl) return;
+    const u32 v = spl_vertex[i];
+    uint4 rl = rec[2 * i], rr = rec[2 * i + 1];
     u32 sd, ps, nn, fw, lp;
-    if (!is_cyc[v]) {
+    if (!is_cyc[i]) {
         u32 ml = rl.z >> 1, mr = rr.z >> 1;
         nn = rl.y + rr.y - 1;
-        if (ml == (u32)v && mr == (u32)v) {  // v is the seed: stored orientation, extended left then right
-            sd = (u32)v; fw = 1; lp = 0; ps = rl.y - 1;
+        if (ml == v && mr == v) {  // v is the seed: stored orientation, extended left then right
+            sd = v; fw = 1; lp = 0; ps = rl.y - 1;
         } else {
             int d = ml < mr ? 0 : 1;
             u32 arr = d == 0 ? rl.z : rr.z;     // state in which the chain from v traverses the seed
@@ -250,16 +296,41 @@ __global__ void assign_kernel(const uint4* __restrict__ rec, const u32* __restri
         }
     } else {
         // cycle: node = [step n-1 .. step 1, seed] of the chain leaving the seed through L (compression.rs:497-511)
+        atomicAdd(n_cycle_kmers, (u64)rec0[2 * i].y);  // every cycle k-mer lies in exactly one L-going segment
         sd = rl.z >> 1;
-        u32 first = nxt[2u * sd];                 // state after (seed, L)
-        nn = 1 + rec[first].w;
-        int p = (rl.z & 1u) ? 0 : 1;              // direction from v whose chain enters the seed through L (leaves through R)
+        if (sd == v) {
+            uint4 e = rec0[2 * i];               // first contracted segment leaving the seed through L
+            nn = e.y + rec[e.x].w;               // ... plus the way from its far splitter back to the seed
+        } else {
+            nn = rl.w + rr.w;                    // the two ways round from v to the seed
+        }
+        int p = (rl.z & 1u) ? 0 : 1;             // direction from v whose chain enters the seed through L (leaves through R)
         u32 t = p == 0 ? rl.w : rr.w;
         ps = nn - 1 - t;
         lp = (u32)(p ^ 1);
         fw = lp == 0;
     }
     vinfo[v] = make_uint4(sd, ps, nn, fw | (lp << 1));
+}
+// thread per splitter: walk rightwards (node coordinates) to the next splitter and rank the k-mers in between
+__global__ void segment_assign_kernel(const u32* __restrict__ nxt, const u32* __restrict__ is_spl,
+                                      const u32* __restrict__ spl_vertex, u64 n_spl, u32 cap, uint4* __restrict__ vinfo) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_spl) return;
+    const u32 v = spl_vertex[i];
+    const uint4 me = vinfo[v];
+    const u32 d = ((me.w >> 1) & 1u) ^ 1u;  // the side facing right
+    u32 cur = nxt[2u * v + d];
+    u32 ps = me.y, steps = 0;
+    while (cur != NIL) {
+        u32 w = cur >> 1;
+        if (is_spl[w]) break;
+        ps = ps + 1 == me.z ? 0 : ps + 1;        // wraps on cycles (the seed is the LAST k-mer of its node)
+        u32 lp = (cur & 1u) ^ 1u;                // leaving through (cur & 1) = right-facing side
+        vinfo[w] = make_uint4(me.x, ps, me.z, (lp == 0) | (lp << 1));
+        cur = nxt[cur];
+        if (++steps > cap) break;
+    }
 }
 
 // ---- S6 ---------------------------------------------------------------------------------------------------
@@ -406,19 +477,37 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
         if (h[3] == 1) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extension points at a k-mer with no extension back (src/compression.rs:428-434)");
         if (h[3] == 2) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extensions are not reciprocal");
         S.rank_rounds = 0;
-        if (h[2] != V) {
-            // ---- S5b: pointer doubling for what the walks left (long unitigs, cycles) ----
-            DBuf<uint4> recA, recB;
-            TRY(recA.alloc(c, NS));
-            TRY(recB.alloc(c, NS));
-            pd_init_kernel<<<grid_for(NS, 256), 256, 0, st>>>(nxt.p, recA.p, NS);
-            TRY(check_launch(c, "pd_init"));
+        u64 ranked = h[2];
+        // ---- S5b: list ranking on the contracted graph for what the walks left (long unitigs, cycles).
+        // First with ~1/64 of the k-mers as splitters; anything still unranked (a cycle that drew no splitter)
+        // is redone with every k-mer a splitter, which is plain pointer doubling on the leftovers. ----
+        for (int pass = 0; pass < 2 && ranked != V; pass++) {
+            const u32 density_mask = pass == 0 ? 63u : 0u;
+            const u32 cap = 1u << 20;
+            DBuf<u32> is_spl, spl_vertex;
+            DBuf<u64> sid, nsp;
+            TRY(is_spl.alloc(c, V)); TRY(sid.alloc(c, V)); TRY(nsp.alloc(c, 1));
+            mark_splitters_kernel<<<grid_for(V, 256), 256, 0, st>>>(nxt.p, vinfo.p, V, density_mask, is_spl.p);
+            TRY(check_launch(c, "mark_splitters"));
+            TRY(exclusive_scan_u32_to_u64(c, is_spl.p, sid.p, V, nsp.p));
+            u64 NSPL = 0;
+            TRY(read_u64(c, nsp.p, &NSPL));
+            if (!NSPL) continue;  // e.g. only short cycles that drew no splitter: next pass makes every k-mer one
+            const u64 NR = 2 * NSPL;
+            TRY(spl_vertex.alloc(c, NSPL));
+            fill_splitters_kernel<<<grid_for(V, 256), 256, 0, st>>>(is_spl.p, sid.p, V, spl_vertex.p);
+            TRY(check_launch(c, "fill_splitters"));
+            DBuf<uint4> rec0, recA, recB;
+            TRY(rec0.alloc(c, NR)); TRY(recA.alloc(c, NR)); TRY(recB.alloc(c, NR));
+            segment_walk_kernel<<<grid_for(NR, 256), 256, 0, st>>>(nxt.p, is_spl.p, sid.p, spl_vertex.p, NR, cap, rec0.p, (u32*)(ctr.p + 3));
+            TRY(check_launch(c, "segment_walk"));
+            CU(c, cudaMemcpyAsync(recA.p, rec0.p, NR * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
             uint4 *src = recA.p, *dst = recB.p;
             u64 prev_active = ~0ull, active = 0;
             int rounds = 0;
             for (; rounds < 40; rounds++) {
                 CU(c, cudaMemsetAsync(ctr.p, 0, 8, st));
-                pd_round_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, dst, NS, ctr.p);
+                pd_round_kernel<<<grid_for(NR, 256), 256, 0, st>>>(src, dst, NR, ctr.p);
                 TRY(check_launch(c, "pd_round"));
                 std::swap(src, dst);
                 TRY(read_u64(c, ctr.p, &active));
@@ -427,17 +516,17 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
             }
             // one more pass so that states finished in the last round exist in both buffers
             CU(c, cudaMemsetAsync(ctr.p, 0, 8, st));
-            pd_round_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, dst, NS, ctr.p);
+            pd_round_kernel<<<grid_for(NR, 256), 256, 0, st>>>(src, dst, NR, ctr.p);
             TRY(check_launch(c, "pd_round"));
-            S.rank_rounds = rounds + 1;
+            S.rank_rounds += rounds + 1;
             DBuf<u8> is_cyc;
-            TRY(is_cyc.alloc(c, V));
+            TRY(is_cyc.alloc(c, NSPL));
             TRY(is_cyc.zero());
             if (active) {
                 DBuf<u32> list;
                 TRY(list.alloc(c, active));
                 CU(c, cudaMemsetAsync(ctr.p + 1, 0, 8, st));
-                cyc_collect_kernel<<<grid_for(NS, 256), 256, 0, st>>>(src, NS, nxt.p, list.p, ctr.p + 1, src, dst, is_cyc.p);
+                cyc_collect_kernel<<<grid_for(NR, 256), 256, 0, st>>>(src, NR, rec0.p, list.p, ctr.p + 1, src, dst, is_cyc.p);
                 TRY(check_launch(c, "cyc_collect"));
                 u64 ncs = 0;
                 TRY(read_u64(c, ctr.p + 1, &ncs));
@@ -449,12 +538,24 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
                     TRY(check_launch(c, "cyc_round"));
                     std::swap(src, dst);
                 }
-                S.n_cycle_kmers = ncs / 2;
                 S.rank_rounds += cr;
             }
-            assign_kernel<<<grid_for(V, 256), 256, 0, st>>>(src, nxt.p, is_cyc.p, V, vinfo.p);
-            TRY(check_launch(c, "assign"));
+            CU(c, cudaMemsetAsync(ctr.p + 1, 0, 8, st));
+            assign_splitters_kernel<<<grid_for(NSPL, 256), 256, 0, st>>>(src, rec0.p, is_cyc.p, spl_vertex.p, NSPL, vinfo.p, ctr.p + 1);
+            TRY(check_launch(c, "assign_splitters"));
+            segment_assign_kernel<<<grid_for(NSPL, 256), 256, 0, st>>>(nxt.p, is_spl.p, spl_vertex.p, NSPL, cap, vinfo.p);
+            TRY(check_launch(c, "segment_assign"));
+            // how many k-mers are ranked now?
+            CU(c, cudaMemsetAsync(ctr.p + 2, 0, 8, st));
+            count_ranked_kernel<<<grid_for(V, 256), 256, 0, st>>>(vinfo.p, V, ctr.p + 2, nullptr);
+            TRY(check_launch(c, "count_ranked"));
+            u64 hh[4];
+            TRY(read_u64(c, ctr.p, hh, 4));
+            ranked = hh[2];
+            S.n_cycle_kmers += hh[1];
+            if (hh[3] == 3) DBG_SET_ERR(c, DBG_E_INTERNAL, "segment walk exceeded its step cap");
         }
+        if (ranked != V) DBG_SET_ERR(c, DBG_E_INTERNAL, "ranking left %llu k-mers unassigned", (unsigned long long)(V - ranked));
     }
     CU(c, cudaEventRecord(c->ev[3], st));
     // ---- S6 ----

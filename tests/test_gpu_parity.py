@@ -180,6 +180,23 @@ def test_long_sequences_chunked(D, ctx, orc):
     run_both(D, ctx, orc, 63, orc.seqset_from_lists(seqs), 1)
 
 
+def test_long_unitigs_and_long_cycles(D, ctx, orc):
+    """Components longer than the end-walk limit (1024 k-mers) go through the contracted-graph list ranking:
+    long paths, a long cycle (circular sequence), a cycle shorter than the splitter spacing, mixed with short ones."""
+    rng = np.random.default_rng(5)
+    k = 31
+    circ = random_dna(rng, 5000)
+    circular = np.concatenate([circ, circ[:k + 5]])           # wraps past the junction: a true 5000-k-mer cycle
+    small = random_dna(rng, 40)
+    small_circ = np.concatenate([small, small[:k + 5]])       # 40-cycle: may draw no splitter
+    seqs = [random_dna(rng, 9000), circular, small_circ, random_dna(rng, 200), random_dna(rng, 3000)]
+    t, g = run_both(D, ctx, orc, k, orc.seqset_from_lists(seqs), 1)
+    assert ctx.stats()["n_cycle_kmers"] >= 5040
+    for stranded in (False, True):
+        run_both(D, ctx, orc, 21, orc.seqset_from_lists([s[:4000] for s in seqs]), 1, stranded=stranded)
+    run_both(D, ctx, orc, 63, orc.seqset_from_lists(seqs), 1)
+
+
 def test_bucket_split_path(D, ctx, orc):
     """Force shared-memory table overflows (one huge bucket) so the hash-class splitting runs."""
     c2 = D.Context(0)
