@@ -216,6 +216,8 @@ def main():
         sampler = ClockSampler(local)
         if not args.no_clocks:
             sampler.start()
+            step()  # untimed: absorbs the start-up of the nvidia-smi sampler (NVML init stalls launches briefly)
+            barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
         walls = []

@@ -172,6 +172,9 @@ int dbg_filter_from_records(dbg_ctx* ctx, int k, const void* d_records, uint64_t
 int dbg_table_device_ptrs(const dbg_kmer_table* t, void** kmers_lo, void** kmers_hi, void** exts, void** counts);
 int dbg_table_from_device(dbg_ctx* ctx, int k, uint64_t n, const void* d_kmers_lo, const void* d_kmers_hi,
                           const void* d_exts, const void* d_counts, dbg_kmer_table** out);
+/* Same, for arrays that are ALREADY ascending and distinct (verified on the device, DBG_E_BADARG otherwise): no sort. */
+int dbg_table_from_device_sorted(dbg_ctx* ctx, int k, uint64_t n, const void* d_kmers_lo, const void* d_kmers_hi,
+                                 const void* d_exts, const void* d_counts, dbg_kmer_table** out);
 
 /* ---- msp::msp_sequence bucket assignment — src/msp.rs:279-324, 115-117 -----------------------------
  * For every k-mer start position j of every sequence: the MSP bucket of that k-mer under the

@@ -97,6 +97,7 @@ SIGNATURES = {
                                           C.c_int, C.c_int, vpp]),
     "dbg_table_device_ptrs": (C.c_int, [vp, vpp, vpp, vpp, vpp]),
     "dbg_table_from_device": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, vp, vpp]),
+    "dbg_table_from_device_sorted": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, vp, vpp]),
     "dbg_msp_kmer_buckets": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_uint64]),
 }
 

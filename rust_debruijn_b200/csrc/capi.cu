@@ -491,6 +491,48 @@ int dbg_table_from_device(dbg_ctx* ctx, int k, uint64_t n, const void* d_kmers_l
                           const void* d_exts, const void* d_counts, dbg_kmer_table** out) {
     return table_from_arrays(ctx, k, n, d_kmers_lo, d_kmers_hi, d_exts, d_counts, cudaMemcpyDeviceToDevice, out);
 }
+int dbg_table_from_device_sorted(dbg_ctx* ctx, int k, uint64_t n, const void* d_lo, const void* d_hi, const void* d_exts,
+                                 const void* d_counts, dbg_kmer_table** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    Ctx* c = CTX(ctx);
+    *out = nullptr;
+    cudaSetDevice(c->device);
+    if (k < 2 || k > 64) DBG_SET_ERR(c, DBG_E_BADARG, "k=%d outside [2,64]", k);
+    if (n && (!d_lo || !d_exts || !d_counts || (k > 32 && !d_hi))) DBG_SET_ERR(c, DBG_E_BADARG, "null array");
+    const bool two = k > 32;
+    dbg_kmer_table* h = new (std::nothrow) dbg_kmer_table();
+    if (!h) DBG_SET_ERR(c, DBG_E_OOM, "host allocation failed");
+    Table* t = &h->t;
+    t->ctx = c; t->k = k; t->n = n;
+    if (n == 0) { *out = h; return DBG_OK; }
+    DBuf<u64> lo, hi;
+    DBuf<u8> ex;
+    DBuf<u16> cn;
+    DBuf<u32> bad;
+    int rc = arena_begin(c);
+    if (rc == DBG_OK) rc = lo.alloc_pool(c, n);
+    if (rc == DBG_OK && two) rc = hi.alloc_pool(c, n);
+    if (rc == DBG_OK) rc = ex.alloc_pool(c, n);
+    if (rc == DBG_OK) rc = cn.alloc_pool(c, n);
+    if (rc == DBG_OK) rc = bad.alloc(c, 1);
+    if (rc == DBG_OK) rc = bad.zero();
+    if (rc != DBG_OK) { delete h; return rc; }
+    cudaMemcpyAsync(lo.p, d_lo, n * 8, cudaMemcpyDeviceToDevice, c->stream);
+    if (two) cudaMemcpyAsync(hi.p, d_hi, n * 8, cudaMemcpyDeviceToDevice, c->stream);
+    cudaMemcpyAsync(ex.p, d_exts, n, cudaMemcpyDeviceToDevice, c->stream);
+    cudaMemcpyAsync(cn.p, d_counts, n * 2, cudaMemcpyDeviceToDevice, c->stream);
+    check_sorted_unique_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(lo.p, two ? hi.p : nullptr, n, bad.p);
+    c->launches++;
+    cudaMemcpyAsync(c->h_scratch, bad.p, 4, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { delete h; DBG_SET_ERR(c, DBG_E_CUDA, "table_from_device_sorted: %s", cudaGetErrorString(cudaGetLastError())); }
+    if (*(u32*)c->h_scratch) { delete h; DBG_SET_ERR(c, DBG_E_BADARG, "arrays are not ascending and distinct"); }
+    t->lo = lo.take();
+    if (two) t->hi = hi.take();
+    t->exts = ex.take();
+    t->counts = cn.take();
+    *out = h;
+    return DBG_OK;
+}
 int dbg_table_device_ptrs(const dbg_kmer_table* t, void** kmers_lo, void** kmers_hi, void** exts, void** counts) {
     if (!t) return DBG_E_BADARG;
     if (kmers_lo) *kmers_lo = t->t.lo;

@@ -131,8 +131,28 @@ def filter_kmers_sharded(seqs, summarizer, stranded, k=31, group=None, report_al
     return KmerTable(ctx, th)
 
 
+def key_range_splitters(hist_total, world):
+    """Boundaries (in units of histogram bins) that cut a global histogram into `world` ranges of ~equal mass.
+    Returns world+1 bin indices, first 0, last len(hist)."""
+    csum = np.cumsum(hist_total.astype(np.int64))
+    total = int(csum[-1]) if len(csum) else 0
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(csum, (total * r) // world, side="left")) + 1 if total else 0)
+    cuts.append(len(hist_total))
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    cuts[-1] = len(hist_total)
+    return [min(c, len(hist_total)) for c in cuts]
+
+
 def gather_table(table, group=None):
-    """Union of every rank's shard on every rank, ascending (sorted again on the device)."""
+    """Union of every rank's (disjoint, ascending) shard on every rank, ascending.
+
+    A re-sort of the gathered table would cost every rank P times the single-GPU sort.  Instead the shards are
+    first redistributed by KEY RANGE (splitters from an all-reduced histogram of the top 16 key bits, one
+    all-to-all), each rank sorts only its range (V/P k-mers), and the ranges are all-gathered in rank order —
+    already globally ascending, so the table is adopted without sorting (dbg_table_from_device_sorted)."""
     import torch
     import torch.distributed as dist
     ctx, L = table.ctx, table.ctx._L
@@ -140,32 +160,78 @@ def gather_table(table, group=None):
     dev = torch.device("cuda", ctx.device)
     k, n = table.k, len(table)
     two = k > 32
+    lo_p, hi_p, ex_p, cn_p = (C.c_void_p() for _ in range(4))
+    ctx.check(L.dbg_table_device_ptrs(table._h, C.byref(lo_p), C.byref(hi_p), C.byref(ex_p), C.byref(cn_p)))
+    ctx.synchronize()
+    e64 = torch.empty(0, dtype=torch.int64, device=dev)
+    lo = _as_tensor(lo_p.value, n * 8, dev).view(torch.int64) if n else e64
+    hi = (_as_tensor(hi_p.value, n * 8, dev).view(torch.int64) if n else e64) if two else None
+    ex = _as_tensor(ex_p.value, n, dev)
+    cn = _as_tensor(cn_p.value, n * 2, dev)
+    # ---- splitters: top 16 bits of the 2k-bit key ----
+    nbits = 2 * k - 64 if two else 2 * k          # key bits in the most significant word
+    top = hi if two else lo
+    if nbits >= 16:
+        pfx = (top >> (nbits - 16)) & 0xFFFF
+    elif two:                                     # K = 33..39: borrow the missing prefix bits from the low word
+        miss = 16 - nbits
+        pfx = ((top << miss) | ((lo >> (64 - miss)) & ((1 << miss) - 1))) & 0xFFFF
+    else:                                         # K < 8
+        pfx = (top << (16 - nbits)) & 0xFFFF
+    hist = torch.bincount(pfx, minlength=65536)[:65536]
+    dist.all_reduce(hist, group=group)
+    cuts = key_range_splitters(hist.cpu().numpy(), world)
+    # this rank's shard is ascending: destination r gets the contiguous slice with prefix in [cuts[r], cuts[r+1])
+    bounds = torch.searchsorted(pfx, torch.tensor(cuts, dtype=torch.int64, device=dev), right=False)
+    bounds[-1] = n
+    send_n = [int(x) for x in (bounds[1:] - bounds[:-1]).tolist()]
+    sn = torch.tensor(send_n, dtype=torch.int64, device=dev)
+    rn = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(rn, sn, group=group)
+    recv_n = [int(x) for x in rn.tolist()]
+    m = sum(recv_n)
+
+    def a2a(t, itemsize):
+        out = torch.empty(m * itemsize, dtype=torch.uint8, device=dev)
+        dist.all_to_all_single(out, t.view(torch.uint8), [x * itemsize for x in recv_n], [x * itemsize for x in send_n],
+                               group=group)
+        return out
+
+    r_lo, r_ex, r_cn = a2a(lo, 8), a2a(ex, 1), a2a(cn, 2)
+    r_hi = a2a(hi, 8) if two else None
+    torch.cuda.synchronize(dev)
+    # ---- sort this key range (P ascending runs -> one): V/P k-mers ----
+    th = C.c_void_p()
+    ctx.check(L.dbg_table_from_device(ctx._h, k, m, C.c_void_p(r_lo.data_ptr()),
+                                      C.c_void_p(r_hi.data_ptr()) if two else None, C.c_void_p(r_ex.data_ptr()),
+                                      C.c_void_p(r_cn.data_ptr()), C.byref(th)))
+    piece = KmerTable(ctx, th)
+    ctx.check(L.dbg_table_device_ptrs(piece._h, C.byref(lo_p), C.byref(hi_p), C.byref(ex_p), C.byref(cn_p)))
+    # ---- all-gather the ordered ranges (padded to the largest) ----
     sizes = torch.zeros(world, dtype=torch.int64, device=dev)
-    mine = torch.tensor([n], dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(sizes, mine, group=group)
+    dist.all_gather_into_tensor(sizes, torch.tensor([m], dtype=torch.int64, device=dev), group=group)
     sizes = [int(x) for x in sizes.tolist()]
-    mx, total = max(sizes), sum(sizes)
-    lo, hi, ex, cn = (C.c_void_p() for _ in range(4))
-    ctx.check(L.dbg_table_device_ptrs(table._h, C.byref(lo), C.byref(hi), C.byref(ex), C.byref(cn)))
+    mx, total = max(max(sizes), 1), sum(sizes)
 
     def gather(ptr, itemsize):
         pad = torch.zeros(mx * itemsize, dtype=torch.uint8, device=dev)
-        if n:
-            pad[: n * itemsize] = _as_tensor(ptr.value, n * itemsize, dev)
+        if m:
+            pad[: m * itemsize] = _as_tensor(ptr.value, m * itemsize, dev)
         out = torch.empty(world * mx * itemsize, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(out, pad, group=group)
-        return torch.cat([out[r * mx * itemsize: r * mx * itemsize + sizes[r] * itemsize] for r in range(world)])
+        sb = mx * itemsize
+        return torch.cat([out[r * sb: r * sb + sizes[r] * itemsize] for r in range(world)])
 
-    ctx.synchronize()
-    g_lo = gather(lo, 8)
-    g_hi = gather(hi, 8) if two else None
-    g_ex = gather(ex, 1)
-    g_cn = gather(cn, 2)
+    g_lo = gather(lo_p, 8)
+    g_hi = gather(hi_p, 8) if two else None
+    g_ex = gather(ex_p, 1)
+    g_cn = gather(cn_p, 2)
     torch.cuda.synchronize(dev)
+    piece.free()
     th = C.c_void_p()
-    ctx.check(L.dbg_table_from_device(ctx._h, k, total, C.c_void_p(g_lo.data_ptr()),
-                                      C.c_void_p(g_hi.data_ptr()) if two else None, C.c_void_p(g_ex.data_ptr()),
-                                      C.c_void_p(g_cn.data_ptr()), C.byref(th)))
+    ctx.check(L.dbg_table_from_device_sorted(ctx._h, k, total, C.c_void_p(g_lo.data_ptr()),
+                                             C.c_void_p(g_hi.data_ptr()) if two else None, C.c_void_p(g_ex.data_ptr()),
+                                             C.c_void_p(g_cn.data_ptr()), C.byref(th)))
     return KmerTable(ctx, th)
 
 

@@ -64,3 +64,16 @@ def test_owner_bounds_properties():
             b = sharded.owner_bounds(1 << bits, world)
             sizes = np.diff(b)
             assert sizes.min() >= 1 and sizes.max() - sizes.min() <= 1
+
+
+def test_key_range_splitters():
+    from rust_debruijn_b200 import sharded
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        for hist in (rng.integers(0, 100, size=65536), np.zeros(65536, np.int64), np.eye(1, 65536, 7, dtype=np.int64)[0] * 1000):
+            cuts = sharded.key_range_splitters(hist, world)
+            assert len(cuts) == world + 1 and cuts[0] == 0 and cuts[-1] == 65536
+            assert all(cuts[i] <= cuts[i + 1] for i in range(world))
+            if hist.sum() and world > 1 and hist.max() < hist.sum() / world:
+                mass = [hist[cuts[i]:cuts[i + 1]].sum() for i in range(world)]
+                assert max(mass) <= hist.sum() / world + hist.max() + 1
