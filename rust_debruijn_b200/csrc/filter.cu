@@ -505,8 +505,8 @@ static const int P2_RC = 2048;   // records per chunk (prefix sums in smem)
 static const int P2_SEG = 8;     // consecutive k-mers per thread
 
 template <int W> struct P2Cfg;
-template <> struct P2Cfg<1> { static const int CAP = 8192; };  // 8 B key + 4 B val = 96 KB
-template <> struct P2Cfg<2> { static const int CAP = 4096; };  // 16 B key + 4 B val = 80 KB
+template <> struct P2Cfg<1> { static const int CAP = 8192; static const int THREADS = 512; static const int CTAS = 2; };   // 8 B key + 4 B val = 96 KB, 2 CTA/SM
+template <> struct P2Cfg<2> { static const int CAP = 8192; static const int THREADS = 1024; static const int CTAS = 1; };  // 16 B key + 4 B val = 160 KB, 1 CTA/SM
 
 struct P2Args {
     u64* rec; u32* mult;  // records (deduplicated in place per bucket when mult != nullptr) and their multiplicities
@@ -565,8 +565,9 @@ __device__ __forceinline__ int SmemTable<2>::find_or_insert(Kmer<2> key, u32 h, 
 }
 
 template <int W>
-__global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
+__global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kernel(KP kp, P2Args a) {
     constexpr int CAP = P2Cfg<W>::CAP;
+    constexpr int P2T = P2Cfg<W>::THREADS;
     constexpr int RW = RecLayout<W>::WORDS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Kmer<W>* keys = reinterpret_cast<Kmer<W>*>(smem_raw);
@@ -608,13 +609,13 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                 u64 dbase = 0;
                 for (u64 c0 = r0; c0 < r1; c0 += RCAP / 2) {
                     const u32 nrc = (u32)min((u64)(RCAP / 2), r1 - c0);
-                    for (int i = threadIdx.x; i < RCAP; i += P2_THREADS) {
+                    for (int i = threadIdx.x; i < RCAP; i += P2T) {
                         reinterpret_cast<u64*>(rkeys)[2 * i] = ~0ull;
                         reinterpret_cast<u64*>(rkeys)[2 * i + 1] = ~0ull;
                         rcnt[i] = 0;
                     }
                     __syncthreads();
-                    for (u32 i = threadIdx.x; i < nrc; i += P2_THREADS) {
+                    for (u32 i = threadIdx.x; i < nrc; i += P2T) {
                         ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(a.rec + (c0 + i) * 2));
                         Kmer<2> key{v.x, v.y};
                         u32 slot = Ops<2>::hash32(key) >> 8 & (RCAP - 1);
@@ -629,10 +630,10 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                         atomicAdd(&rcnt[slot], 1u);
                     }
                     __syncthreads();
-                    // compact: RCAP / P2_THREADS consecutive slots per thread
+                    // compact: RCAP / P2T consecutive slots per thread
                     u32 mine = 0;
 #pragma unroll
-                    for (int j = 0; j < RCAP / P2_THREADS; j++) mine += rcnt[threadIdx.x * (RCAP / P2_THREADS) + j] != 0;
+                    for (int j = 0; j < RCAP / P2T; j++) mine += rcnt[threadIdx.x * (RCAP / P2T) + j] != 0;
                     {
                         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
                         u32 inc = mine;
@@ -641,7 +642,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                         if (lane == 31) s_wsum[warp] = inc;
                         __syncthreads();
                         if (warp == 0) {
-                            u32 w = lane < P2_THREADS / 32 ? s_wsum[lane] : 0, winc = w;
+                            u32 w = lane < P2T / 32 ? s_wsum[lane] : 0, winc = w;
 #pragma unroll
                             for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
                             s_wsum[lane] = winc - w;
@@ -650,8 +651,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                         __syncthreads();
                         u64 o = r0 + dbase + s_wsum[warp] + inc - mine;
 #pragma unroll
-                        for (int j = 0; j < RCAP / P2_THREADS; j++) {
-                            int sl = threadIdx.x * (RCAP / P2_THREADS) + j;
+                        for (int j = 0; j < RCAP / P2T; j++) {
+                            int sl = threadIdx.x * (RCAP / P2T) + j;
                             u32 cnt = rcnt[sl];
                             if (cnt) {
                                 *reinterpret_cast<ulonglong2*>(a.rec + o * 2) = make_ulonglong2(rkeys[sl].lo, rkeys[sl].hi);
@@ -675,7 +676,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
             const u32 cbits = top & 63u, cres = top >> 6;
             const u32 cmask = cbits ? ((1u << cbits) - 1) : 0;
             __syncthreads();
-            for (int i = threadIdx.x; i < CAP; i += P2_THREADS) {
+            for (int i = threadIdx.x; i < CAP; i += P2T) {
                 if (W == 1) reinterpret_cast<u64*>(keys)[i] = ~0ull;
                 else { reinterpret_cast<u64*>(keys)[2 * i] = ~0ull; reinterpret_cast<u64*>(keys)[2 * i + 1] = ~0ull; }
                 vals[i] = 0;
@@ -689,11 +690,11 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
             for (u64 c0 = r0; c0 < r1; c0 += P2_RC) {
                 const u32 nrc = (u32)min((u64)P2_RC, r1 - c0);
                 {   // prefix sums of k-mers per record
-                    u32 cnt[P2_RC / P2_THREADS];
+                    u32 cnt[P2_RC / P2T];
                     u32 sum = 0;
 #pragma unroll
-                    for (int j = 0; j < P2_RC / P2_THREADS; j++) {
-                        u32 idx = threadIdx.x * (P2_RC / P2_THREADS) + j;
+                    for (int j = 0; j < P2_RC / P2T; j++) {
+                        u32 idx = threadIdx.x * (P2_RC / P2T) + j;
                         cnt[j] = idx < nrc ? ((u32)__ldcg(a.rec + (c0 + idx) * RW + (RW - 1)) >> 8) & 63u : 0;
                         sum += cnt[j];
                     }
@@ -704,7 +705,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                     if (lane == 31) s_wsum[warp] = inc;
                     __syncthreads();
                     if (warp == 0) {
-                        u32 w = lane < P2_THREADS / 32 ? s_wsum[lane] : 0, winc = w;
+                        u32 w = lane < P2T / 32 ? s_wsum[lane] : 0, winc = w;
 #pragma unroll
                         for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
                         s_wsum[lane] = winc - w;
@@ -713,17 +714,17 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                     __syncthreads();
                     u32 ex = s_wsum[warp] + inc - sum;
 #pragma unroll
-                    for (int j = 0; j < P2_RC / P2_THREADS; j++) {
-                        s_pref[threadIdx.x * (P2_RC / P2_THREADS) + j] = ex;
+                    for (int j = 0; j < P2_RC / P2T; j++) {
+                        s_pref[threadIdx.x * (P2_RC / P2T) + j] = ex;
                         ex += cnt[j];
                     }
                     __syncthreads();
                 }
                 const u32 T = s_pref[P2_RC];
                 // segment length: as few rounds as possible with every thread busy (>= P2_SEG to amortise the search)
-                const u32 rounds = (T + P2_THREADS * 16 - 1) / (P2_THREADS * 16);
-                const u32 seg = max((u32)P2_SEG, (T + rounds * P2_THREADS - 1) / (rounds * P2_THREADS));
-                for (u32 k0 = threadIdx.x * seg; k0 < T; k0 += P2_THREADS * seg) {
+                const u32 rounds = (T + P2T * 16 - 1) / (P2T * 16);
+                const u32 seg = max((u32)P2_SEG, (T + rounds * P2T - 1) / (rounds * P2T));
+                for (u32 k0 = threadIdx.x * seg; k0 < T; k0 += P2T * seg) {
                     if (*reinterpret_cast<volatile u32*>(&s_overflow)) break;
                     const u32 k1 = min(T, k0 + seg);
                     // record holding k-mer k0: largest i with pref[i] <= k0
@@ -865,7 +866,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
             }
             // ---- emit: count, block scan, reserve, write ----
             u32 nv = 0, na = 0;
-            for (int i = threadIdx.x; i < CAP; i += P2_THREADS) {
+            for (int i = threadIdx.x; i < CAP; i += P2T) {
                 bool occ = W == 1 ? reinterpret_cast<u64*>(keys)[i] != ~0ull
                                   : !(reinterpret_cast<u64*>(keys)[2 * i] == ~0ull && reinterpret_cast<u64*>(keys)[2 * i + 1] == ~0ull);
                 if (occ) {
@@ -894,7 +895,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
                 if (lane == 31) s_scan[warp] = inc;
                 __syncthreads();
                 if (warp == 0) {
-                    u64 w = lane < P2_THREADS / 32 ? s_scan[lane] : 0;
+                    u64 w = lane < P2T / 32 ? s_scan[lane] : 0;
                     u64 winc = w;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -917,7 +918,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) count_kernel(KP kp, P2Args a) {
             __syncthreads();
             if (a.counters[4] == 0) {
                 u64 pv = s_base_valid + (u32)ex, pa = s_base_all + (u32)(ex >> 32);
-                for (int i = threadIdx.x; i < CAP; i += P2_THREADS) {
+                for (int i = threadIdx.x; i < CAP; i += P2T) {
                     u64 klo = W == 1 ? reinterpret_cast<u64*>(keys)[i] : reinterpret_cast<u64*>(keys)[2 * i];
                     u64 khi = W == 1 ? 0 : reinterpret_cast<u64*>(keys)[2 * i + 1];
                     bool occ = W == 1 ? klo != ~0ull : !(klo == ~0ull && khi == ~0ull);
@@ -1002,7 +1003,7 @@ void plan_filter(const Ctx* c, int k, u64 N, int* p_out, int* bbits_out) {
     if (!target) {
         // k-mer occurrences per bucket such that the bucket's DISTINCT k-mers fit the shared-memory table
         // (8192 slots for one-word keys, 4096 for two-word keys; longer k-mers are also more often distinct)
-        const u64 tmax = W == 1 ? 16384 : 2048;
+        const u64 tmax = W == 1 ? 16384 : 4096;
         target = N / ((u64)c->sm_count * 8);
         if (target < tmax / 8) target = tmax / 8;
         if (target > tmax) target = tmax;
@@ -1178,9 +1179,9 @@ static int count_sort_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucke
         a.counters = ctr.p;
         size_t smem = (sizeof(Kmer<W>) + 4) * P2Cfg<W>::CAP;
         CU(c, cudaFuncSetAttribute(count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        u32 grid2 = (u32)std::min<u64>(NB, (u64)c->sm_count * 2);
+        u32 grid2 = (u32)std::min<u64>(NB, (u64)c->sm_count * P2Cfg<W>::CTAS);
         CU(c, cudaEventRecord(c->ev[10], st));
-        count_kernel<W><<<grid2, P2_THREADS, smem, st>>>(kp, a);
+        count_kernel<W><<<grid2, P2Cfg<W>::THREADS, smem, st>>>(kp, a);
         TRY(check_launch(c, "count_kernel"));
         CU(c, cudaEventRecord(c->ev[11], st));
     }

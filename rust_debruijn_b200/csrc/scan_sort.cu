@@ -135,14 +135,14 @@ static const int OS_TILE = OS_THREADS * OS_ITEMS;  // 4096 keys per CTA
 static const int OS_SEG = 32 * OS_ITEMS;           // contiguous keys per warp
 static const u64 OS_FLAG_AGG = 1ull << 62, OS_FLAG_PREFIX = 2ull << 62, OS_VAL_MASK = (1ull << 62) - 1;
 
-__global__ void __launch_bounds__(512) rs_hist_kernel(const u64* __restrict__ lo, const u64* __restrict__ hi, u64 n, int passes,
+__global__ void __launch_bounds__(512) rs_hist_kernel(const u64* __restrict__ lo, const u64* __restrict__ hi, u64 n, int d0, int passes,
                                                       u64* __restrict__ ghist) {
     __shared__ u32 h[16 * 256];
     for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) h[i] = 0;
     __syncthreads();
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         u64 l = lo[i], hh = passes > 8 ? hi[i] : 0;
-        for (int d = 0; d < passes; d++) {
+        for (int d = d0; d < passes; d++) {
             u32 dg = d < 8 ? (u32)(l >> (8 * d)) & 0xffu : (u32)(hh >> (8 * (d - 8))) & 0xffu;
             atomicAdd(&h[d * 256 + dg], 1u);
         }
@@ -262,39 +262,101 @@ __global__ void __launch_bounds__(OS_THREADS) rs_onesweep(const u64* __restrict_
     }
 }
 
+// After sorting on the top digits only: keys that share the sorted prefix form (rare, short) runs that are still in
+// their original relative order.  The thread at a run start insertion-sorts the run on the full key.  Runs longer
+// than RS_FIX_MAX raise a flag (the caller then sorts on every digit instead).
+static const int RS_FIX_MAX = 48;
+template <int W>
+__global__ void rs_fixup_kernel(u64* __restrict__ lo, u64* __restrict__ hi, u32* __restrict__ val, u64 n, int shift, u32* flag) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto same = [&](u64 x, u64 y) -> bool {   // do keys x and y share the sorted prefix (key >> shift)?
+        if (W == 1) return (lo[x] >> shift) == (lo[y] >> shift);
+        if (shift >= 64) return (hi[x] >> (shift - 64)) == (hi[y] >> (shift - 64));
+        return hi[x] == hi[y] && (lo[x] >> shift) == (lo[y] >> shift);
+    };
+    if (i > 0 && same(i - 1, i)) return;           // not a run start
+    if (i + 1 >= n || !same(i, i + 1)) return;     // run of one
+    u64 j = i + 1;
+    while (j < n && same(i, j) && j - i <= (u64)RS_FIX_MAX) j++;
+    if (j - i > (u64)RS_FIX_MAX) { atomicExch(flag, 1u); return; }
+    for (u64 a = i + 1; a < j; a++) {
+        u64 kl = lo[a], kh = W == 2 ? hi[a] : 0;
+        u32 kv = val[a];
+        u64 b = a;
+        while (b > i) {
+            u64 pl = lo[b - 1], ph = W == 2 ? hi[b - 1] : 0;
+            bool greater = W == 2 ? (ph > kh || (ph == kh && pl > kl)) : pl > kl;
+            if (!greater) break;
+            lo[b] = pl;
+            if (W == 2) hi[b] = ph;
+            val[b] = val[b - 1];
+            b--;
+        }
+        lo[b] = kl;
+        if (W == 2) hi[b] = kh;
+        val[b] = kv;
+    }
+}
+
 int radix_sort_pairs(Ctx* c, int W, int key_bits, u64 n, u64* lo_a, u64* hi_a, u32* val_a, u64* lo_b, u64* hi_b,
                      u32* val_b, u64** res_lo, u64** res_hi, u32** res_val) {
     *res_lo = lo_a; *res_hi = hi_a; *res_val = val_a;
     if (n <= 1) return DBG_OK;
-    int passes = (key_bits + 7) / 8;
+    const int passes = (key_bits + 7) / 8;
+    // digits to sort on: enough top bits that equal prefixes are rare (>= log2(n) + 4 effective bits)
+    int need_bits = 4;
+    while ((1ull << (need_bits - 4)) < n && need_bits < 128) need_bits++;
+    int npass = passes;
+    for (int q = 1; q <= passes; q++) {
+        int eff = 8 * q - (8 * passes - key_bits);
+        if (eff >= need_bits) { npass = q; break; }
+    }
     u32 ntiles = (u32)((n + OS_TILE - 1) / OS_TILE);
     DBuf<u64> ghist, status;
     DBuf<u32> tctr;
     TRY(ghist.alloc(c, 16 * 256));
-    TRY(ghist.zero());
     TRY(status.alloc(c, (u64)ntiles * 256));
-    TRY(tctr.alloc(c, 16));
-    TRY(tctr.zero());
-    u32 hgrid = (u32)std::min<u64>((n + 511) / 512, (u64)c->sm_count * 4);
-    rs_hist_kernel<<<hgrid, 512, 0, c->stream>>>(lo_a, hi_a, n, passes, ghist.p);
-    TRY(check_launch(c, "rs_hist"));
-    rs_hist_scan_kernel<<<passes, 32, 0, c->stream>>>(ghist.p, passes);
-    TRY(check_launch(c, "rs_hist_scan"));
+    TRY(tctr.alloc(c, 32));
     size_t smem = (size_t)OS_TILE * (W == 2 ? 20 : 12);
     if (W == 1) CU(c, cudaFuncSetAttribute(rs_onesweep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else CU(c, cudaFuncSetAttribute(rs_onesweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     u64 *slo = lo_a, *shi = hi_a, *dlo = lo_b, *dhi = hi_b;
     u32 *sv = val_a, *dv = val_b;
-    for (int d = 0; d < passes; d++) {
-        TRY(status.zero());
-        if (W == 1)
-            rs_onesweep<1><<<ntiles, OS_THREADS, smem, c->stream>>>(slo, shi, sv, dlo, dhi, dv, n, d, ghist.p + d * 256, status.p, tctr.p + d);
-        else
-            rs_onesweep<2><<<ntiles, OS_THREADS, smem, c->stream>>>(slo, shi, sv, dlo, dhi, dv, n, d, ghist.p + d * 256, status.p, tctr.p + d);
-        TRY(check_launch(c, "rs_onesweep"));
-        std::swap(slo, dlo);
-        std::swap(shi, dhi);
-        std::swap(sv, dv);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const int d0 = passes - npass;
+        TRY(ghist.zero());
+        TRY(tctr.zero());
+        u32 hgrid = (u32)std::min<u64>((n + 511) / 512, (u64)c->sm_count * 4);
+        rs_hist_kernel<<<hgrid, 512, 0, c->stream>>>(slo, shi, n, d0, passes, ghist.p);
+        TRY(check_launch(c, "rs_hist"));
+        rs_hist_scan_kernel<<<passes, 32, 0, c->stream>>>(ghist.p, passes);
+        TRY(check_launch(c, "rs_hist_scan"));
+        for (int d = d0; d < passes; d++) {
+            TRY(status.zero());
+            if (W == 1)
+                rs_onesweep<1><<<ntiles, OS_THREADS, smem, c->stream>>>(slo, shi, sv, dlo, dhi, dv, n, d, ghist.p + d * 256, status.p, tctr.p + d);
+            else
+                rs_onesweep<2><<<ntiles, OS_THREADS, smem, c->stream>>>(slo, shi, sv, dlo, dhi, dv, n, d, ghist.p + d * 256, status.p, tctr.p + d);
+            TRY(check_launch(c, "rs_onesweep"));
+            std::swap(slo, dlo);
+            std::swap(shi, dhi);
+            std::swap(sv, dv);
+        }
+        if (d0 == 0) break;  // sorted on every digit
+        // fix the runs that share the sorted prefix
+        CU(c, cudaMemsetAsync(tctr.p + 31, 0, 4, c->stream));
+        const int shift = 8 * d0;  // prefix = key >> shift
+        if (W == 1) rs_fixup_kernel<1><<<grid_for(n, 256), 256, 0, c->stream>>>(slo, shi, sv, n, shift, tctr.p + 31);
+        else rs_fixup_kernel<2><<<grid_for(n, 256), 256, 0, c->stream>>>(slo, shi, sv, n, shift, tctr.p + 31);
+        TRY(check_launch(c, "rs_fixup"));
+        u32 flag = 0;
+        CU(c, cudaMemcpyAsync(c->h_scratch, tctr.p + 31, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        flag = *(u32*)c->h_scratch;
+        if (!flag) break;
+        npass = passes;  // long equal-prefix runs (low-complexity data): sort on every digit (LSD passes are stable, so
+                         // re-sorting the partially sorted data on all digits is still correct)
     }
     *res_lo = slo; *res_hi = shi; *res_val = sv;
     return DBG_OK;

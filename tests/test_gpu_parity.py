@@ -208,6 +208,18 @@ def test_bucket_split_path(D, ctx, orc):
     c2.close()
 
 
+def test_sort_prefix_runs_and_fallback(D, ctx, orc):
+    """The table sort works on the top digits plus a run fix-up; many k-mers sharing a long prefix (low-complexity
+    reads that differ only near their 3' end) force the all-digit fallback.  Same bits either way."""
+    rng = np.random.default_rng(8)
+    base = np.zeros(140, np.uint8)
+    seqs = []
+    for i in range(400):   # A...A + random 10-base tail: thousands of k-mers with an identical 20+ base prefix
+        seqs.append(np.concatenate([base[: 100 + i % 30], random_dna(rng, 12)]))
+    for k in (31, 45):
+        run_both(D, ctx, orc, k, orc.seqset_from_lists(seqs), 1, report_all=True)
+
+
 def test_record_dedup_off(D, ctx, orc):
     """The per-bucket super-k-mer deduplication is an optimisation only: same bits with it switched off."""
     c2 = D.Context(0)
