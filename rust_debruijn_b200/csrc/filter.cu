@@ -38,7 +38,7 @@ __device__ __forceinline__ u32 pmer_score(u32 x, int p, bool stranded) {
         u32 r = (~rev2_32(x)) >> (32 - 2 * p);
         x = x < r ? x : r;  // canonical p-mer (score = min(perm[p], perm[rc p]), msp.rs:305-311, perm bijective)
     }
-    x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA6Bu; x ^= x >> 13;
     return x;
 }
 
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
     __shared__ u32 s_vm[T1_BM];   // bit b: a valid k-mer starts at staged index b
     u32* const s_queue = s_sc;    // closed runs of this tile (start | n << 16); reuses the score array after phase B
     __shared__ u32 s_qn;
-    __shared__ u64 s_slot0;
+    __shared__ u64 s_slot0, s_i0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = kp.k, p = a.p, wlen = K - p + 1;
 
@@ -314,12 +314,14 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
             s_s32[2 * t + 1] = (u32)v;
         }
         for (u32 t = tid; t < (u32)T1_BM; t += T1_THREADS) s_bm[t] = 0;
-        if (tid == 0) s_qn = 0;
+        if (tid == 0) {
+            s_qn = 0;
+            if (a.uniform_len) s_i0 = (sb - ta.base0 + a.uniform_len - 1) / a.uniform_len;  // one 64-bit division per tile
+        }
         __syncthreads();
         if (a.uniform_len) {
             const u32 L = a.uniform_len;
-            const u64 rel = sb - ta.base0;
-            u64 i0 = (rel + L - 1) / L;
+            u64 i0 = s_i0;
             for (u64 i = i0 + tid; i <= a.n_seqs; i += T1_THREADS) {
                 u64 g = ta.base0 + i * L;
                 if (g >= sb + nbits) break;
@@ -510,6 +512,8 @@ template <> struct P2Cfg<2> { static const int CAP = 8192; static const int THRE
 
 struct P2Args {
     u64* rec; u32* mult;  // records (deduplicated in place per bucket when mult != nullptr) and their multiplicities
+    int mult_ready;       // records are already deduplicated (retry): bucket b holds dedup_cnt[b] records
+    u32* dedup_cnt;       // per bucket: records left after deduplication
     const u64* bucket_off; u32 n_buckets;
     u32 min_obs; int stranded; int report_all;
     u64* out_lo; u64* out_hi; u32* out_val; u64 cap_valid;
@@ -597,7 +601,9 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
         u64 r1 = a.bucket_off[b + 1];
         if (r0 == r1) continue;
         if constexpr (W == 1) {
-            if (a.mult) {
+            if (a.mult && a.mult_ready) {
+                r1 = r0 + a.dedup_cnt[b];
+            } else if (a.mult) {
                 // ---- P2a: deduplicate this bucket's records.  At sequencing coverage c most super-k-mers of a
                 // genomic site occur ~c/2 times byte-identically; each distinct record is expanded once below and
                 // its k-mers are counted with the record's multiplicity.  The 16-byte records are hashed into a
@@ -664,7 +670,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                     }
                     __syncthreads();
                 }
-                if (threadIdx.x == 0) atomicAdd(&a.counters[5], dbase);
+                if (threadIdx.x == 0) { atomicAdd(&a.counters[5], dbase); a.dedup_cnt[b] = (u32)dbase; }
                 r1 = r0 + dbase;
                 __threadfence_block();
                 __syncthreads();
@@ -1155,24 +1161,29 @@ static int count_sort_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucke
     KP kp = make_kp(k);
     cudaStream_t st = c->stream;
     dbg_stats& S = c->stats;
-    u64 cap_valid = min_obs > 1 ? N / min_obs + 1 : N;
+    // Valid k-mers are a small fraction of the occurrences on real coverage (V/N ~ 0.03 at 50x): size the output by
+    // an estimate and fall back to the exact bound (every valid k-mer needs >= min_obs occurrences) if it overflows.
+    const u64 bound_valid = min_obs > 1 ? N / min_obs + 1 : N;
+    u64 cap_valid = std::min<u64>(bound_valid, c->valid_est_div ? N / c->valid_est_div + 16 : N / 8 + (1u << 20));
     u64 cap_all = report_all ? N : 0;
     DBuf<u64> v_lo, v_hi, a_lo, a_hi, ctr;
     DBuf<u32> v_val;
     TRY(ctr.alloc(c, 8));
-    TRY(v_lo.alloc(c, cap_valid));
-    TRY(v_val.alloc(c, cap_valid));
-    if (W == 2) TRY(v_hi.alloc(c, cap_valid));
     if (report_all) {
         TRY(a_lo.alloc(c, cap_all));
         if (W == 2) TRY(a_hi.alloc(c, cap_all));
     }
-    DBuf<u32> mult;
-    if (W == 1 && c->dedup) TRY(mult.alloc(c, n_rec));
-    TRY(ctr.zero());
-    {
+    DBuf<u32> mult, dedup_cnt;
+    if (W == 1 && c->dedup) { TRY(mult.alloc(c, n_rec)); TRY(dedup_cnt.alloc(c, NB)); }
+    u64 h[6];
+    for (int attempt = 0;; attempt++) {
+        TRY(v_lo.alloc(c, cap_valid));
+        TRY(v_val.alloc(c, cap_valid));
+        if (W == 2) TRY(v_hi.alloc(c, cap_valid));
+        TRY(ctr.zero());
         P2Args a;
-        a.rec = rec; a.mult = (W == 1 && c->dedup) ? mult.p : nullptr; a.bucket_off = bucket_off; a.n_buckets = NB;
+        // a second attempt sees records that the first one already deduplicated in place: multiplicities stay valid
+        a.rec = rec; a.mult = (W == 1 && c->dedup) ? mult.p : nullptr; a.mult_ready = attempt > 0; a.dedup_cnt = dedup_cnt.p; a.bucket_off = bucket_off; a.n_buckets = NB;
         a.min_obs = min_obs; a.stranded = stranded; a.report_all = report_all;
         a.out_lo = v_lo.p; a.out_hi = v_hi.p; a.out_val = v_val.p; a.cap_valid = cap_valid;
         a.all_lo = a_lo.p; a.all_hi = a_hi.p; a.cap_all = cap_all;
@@ -1184,9 +1195,11 @@ static int count_sort_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucke
         count_kernel<W><<<grid2, P2Cfg<W>::THREADS, smem, st>>>(kp, a);
         TRY(check_launch(c, "count_kernel"));
         CU(c, cudaEventRecord(c->ev[11], st));
+        TRY(read_u64(c, ctr.p, h, 6));
+        if (h[4] == 2 && attempt == 0 && cap_valid < bound_valid) { cap_valid = bound_valid; continue; }
+        break;
     }
-    u64 h[6];
-    TRY(read_u64(c, ctr.p, h, 6));
+    if (!(W == 1 && c->dedup)) h[5] = 0;
     S.n_records_distinct = h[5];
     if (h[4]) DBG_SET_ERR(c, DBG_E_INTERNAL, "count_kernel failed (code %llu)", (unsigned long long)h[4]);
     u64 V = h[1], U = h[2];

@@ -220,6 +220,17 @@ def test_sort_prefix_runs_and_fallback(D, ctx, orc):
         run_both(D, ctx, orc, k, orc.seqset_from_lists(seqs), 1, report_all=True)
 
 
+def test_valid_buffer_retry(D, ctx, orc):
+    """The valid-k-mer buffer is sized by an estimate; force it far too small so the exact-bound retry runs
+    (second attempt re-uses the already deduplicated records)."""
+    c2 = D.Context(0)
+    c2.set_param("valid_est_div", 1000)
+    ss = orc.synth_reads(3000, 1, 0)          # clean: every distinct k-mer is valid
+    run_both(D, c2, orc, 31, ss, 1, report_all=True)
+    run_both(D, c2, orc, 63, ss, 1)
+    c2.close()
+
+
 def test_record_dedup_off(D, ctx, orc):
     """The per-bucket super-k-mer deduplication is an optimisation only: same bits with it switched off."""
     c2 = D.Context(0)
