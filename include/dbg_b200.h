@@ -64,6 +64,7 @@ typedef struct {
     float ms_k_partition, ms_k_count; /* the two dominant kernels alone (events right around the launch) */
     float ms_filter_total, ms_compress_total;
     uint64_t n_records_distinct; /* super-k-mer records left after per-bucket deduplication (0 = dedup off) */
+    uint64_t n_passes;           /* passes over the reads chosen by the memory planner (filter.rs:151-168) */
 } dbg_stats;
 
 /* ---- context ------------------------------------------------------------------------------------ */
@@ -72,7 +73,7 @@ void dbg_ctx_destroy(dbg_ctx* ctx);
 const char* dbg_last_error(const dbg_ctx* ctx);
 int dbg_stats_get(const dbg_ctx* ctx, dbg_stats* out);
 /* tunables: "msp_p" (minimizer length, 0 = auto), "bucket_occ" (target k-mer occurrences per MSP
- * bucket, 0 = auto). */
+ * bucket, 0 = auto), "dedup" (0/1), "mem_budget_bytes" (scratch budget of the pass planner, 0 = auto). */
 int dbg_ctx_set_param(dbg_ctx* ctx, const char* name, int64_t value);
 int dbg_ctx_synchronize(dbg_ctx* ctx);
 /* The cudaStream_t every call of this ctx is ordered on (for event timing / interop with other runtimes). */

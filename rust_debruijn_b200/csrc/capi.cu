@@ -180,6 +180,8 @@ int dbg_ctx_set_param(dbg_ctx* ctx, const char* name, int64_t value) {
         c->target_bucket_occ = (int)value;
     } else if (!strcmp(name, "dedup")) {
         c->dedup = value != 0;
+    } else if (!strcmp(name, "mem_budget_bytes")) {
+        c->mem_budget_bytes = value > 0 ? (u64)value : 0;
     } else if (!strcmp(name, "valid_est_div")) {
         c->valid_est_div = value > 0 ? (u64)value : 0;
     } else {

@@ -25,6 +25,7 @@ struct Ctx {
     int target_bucket_occ = 0; // 0 = auto (k-mer occurrences per MSP bucket)
     int dedup = 1;             // deduplicate super-k-mer records per bucket before counting (K <= 32)
     u64 valid_est_div = 0;     // testing: size the valid-k-mer buffer as N / div (0 = default estimate N/8 + 2^20)
+    u64 mem_budget_bytes = 0;  // scratch budget for the pass planner (0 = 60% of free device memory, capped by memory_size)
     u64 launches = 0;          // kernels launched by this ctx (gpu_launches in bench.py)
     // pinned scratch for small D2H reads
     u64* h_scratch = nullptr;

@@ -48,6 +48,7 @@ struct P1Args {
     u64 n_seqs; u32 uniform_len;
     const u32* item_seq; const u32* item_j0; u64 n_items;  // item_seq == nullptr => item i = sequence i, j0 = 0
     int p; int stranded; u32 bucket_mask; int maxk;
+    u32 bk_lo, bk_span;  // this pass keeps records of buckets [bk_lo, bk_lo + bk_span) (multi-pass planner)
     u64* rec; u32* rec_bucket; u64 capacity;                 // staging
     u64* cursor; u32* bucket_count; u32* overflow;
 };
@@ -156,14 +157,16 @@ __global__ void __launch_bounds__(P1_THREADS) msp_partition_kernel(KP kp, P1Args
                         }
                         r[RW - 1] |= hdr;
                         u32 b = bk[prev];
-                        if constexpr (RW == 2) {
-                            *reinterpret_cast<ulonglong2*>(a.rec + slot * 2) = make_ulonglong2(r[0], r[1]);
-                        } else {
-                            *reinterpret_cast<ulonglong2*>(a.rec + slot * 4) = make_ulonglong2(r[0], r[1]);
-                            *reinterpret_cast<ulonglong2*>(a.rec + slot * 4 + 2) = make_ulonglong2(r[2], r[RW - 1]);
+                        if (b - a.bk_lo < a.bk_span) {  // other buckets belong to another pass: the slot stays INVALID
+                            if constexpr (RW == 2) {
+                                *reinterpret_cast<ulonglong2*>(a.rec + slot * 2) = make_ulonglong2(r[0], r[1]);
+                            } else {
+                                *reinterpret_cast<ulonglong2*>(a.rec + slot * 4) = make_ulonglong2(r[0], r[1]);
+                                *reinterpret_cast<ulonglong2*>(a.rec + slot * 4 + 2) = make_ulonglong2(r[2], r[RW - 1]);
+                            }
+                            a.rec_bucket[slot] = b;
+                            atomicAdd(&a.bucket_count[b], 1u);
                         }
-                        a.rec_bucket[slot] = b;
-                        atomicAdd(&a.bucket_count[b], 1u);
                     }
                 }
                 chunk_used += cnt;
@@ -437,7 +440,8 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
                     u32 lower = sm & ((1u << bit) - 1);
                     int prev = lower ? (int)x0 + 31 - __clz(lower) : pr;
                     int n = (int)x0 + bit - prev;
-                    nrec += n <= a.maxk ? 1u : (u32)((n + a.maxk - 1) / a.maxk);
+                    if (s_bk[bkpad((u32)prev)] - a.bk_lo < a.bk_span)   // runs of other buckets belong to another pass
+                        nrec += n <= a.maxk ? 1u : (u32)((n + a.maxk - 1) / a.maxk);
                 }
             }
             u32 inc = nrec;
@@ -456,6 +460,7 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
                     u32 lower = smask & ((1u << bit) - 1);
                     int prev = lower ? (int)x0 + 31 - __clz(lower) : carry;
                     int xe = (int)x0 + bit;
+                    if (s_bk[bkpad((u32)prev)] - a.bk_lo >= a.bk_span) continue;
                     for (int ps = prev; ps < xe; ps += a.maxk) {
                         if (qpos < (u32)T1_QCAP) s_queue[qpos] = (u32)ps | ((u32)min(a.maxk, xe - ps) << 16);
                         qpos++;
@@ -1052,8 +1057,8 @@ struct PartOut {
 
 // ---- P1 + P1b: sequences -> bucket-contiguous super-k-mer records ----
 template <int W>
-static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, u32 max_len, int p, int bbits, bool pool_out,
-                           PartOut& po) {
+static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, u32 max_len, int p, int bbits, u32 bk_lo,
+                           u32 bk_span, bool pool_out, PartOut& po) {
     constexpr int RW = RecLayout<W>::WORDS;
     KP kp = make_kp(k);
     cudaStream_t st = c->stream;
@@ -1093,7 +1098,8 @@ static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, 
     u32 grid1 = use_tiles ? (u32)std::min<u64>(ta.n_tiles, (u64)c->sm_count * 6)
                           : (u32)std::min<u64>((n_items + P1_WARPS - 1) / P1_WARPS, (u64)c->sm_count * 6);
     u64 n_warps = (u64)grid1 * P1_WARPS;
-    u64 capacity = N / 4 + n_warps * WCHUNK + 1024;
+    // records expected in this pass: ~1/10 of its k-mer occurrences; N/4 leaves room, the retry below covers the rest
+    u64 capacity = (u64)((double)N * bk_span / NB) / 4 + n_warps * WCHUNK + 1024;
     DBuf<u64> stage_rec;
     DBuf<u32> stage_bucket;
     u64 n_slots = 0;
@@ -1107,7 +1113,7 @@ static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, 
         a.words = s->words; a.n_words = s->n_words; a.start = s->start; a.length = s->length; a.seq_exts = s->seq_exts;
         a.n_seqs = s->n_seqs; a.uniform_len = s->uniform_len;
         a.item_seq = chunked ? item_seq.p : nullptr; a.item_j0 = chunked ? item_j0.p : nullptr; a.n_items = n_items;
-        a.p = p; a.stranded = stranded; a.bucket_mask = NB - 1; a.maxk = maxk;
+        a.p = p; a.stranded = stranded; a.bucket_mask = NB - 1; a.maxk = maxk; a.bk_lo = bk_lo; a.bk_span = bk_span;
         a.rec = stage_rec.p; a.rec_bucket = stage_bucket.p; a.capacity = capacity;
         a.cursor = ctr.p; a.bucket_count = po.bucket_count.p; a.overflow = (u32*)(ctr.p + 1);
         CU(c, cudaEventRecord(c->ev[8], st));
@@ -1154,61 +1160,85 @@ static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, 
     return DBG_OK;
 }
 
-// ---- P2 + P3: bucket-contiguous records -> ascending (k-mer, exts, count) table ----
+// Valid / distinct k-mers emitted by the counting stage (unordered), kept across the passes of one filter call.
+struct CountOut {
+    DBuf<u64> v_lo, v_hi, a_lo, a_hi, ctr;
+    DBuf<u32> v_val;
+    u64 cap_valid = 0, cap_all = 0;
+    u64 n_valid = 0, n_all = 0, n_splits = 0, n_rec_distinct = 0;
+};
+
 template <int W>
-static int count_sort_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucket_off, u32 NB, u64 N, u32 min_obs, int stranded,
-                            int report_all, Table* t) {
-    KP kp = make_kp(k);
-    cudaStream_t st = c->stream;
-    dbg_stats& S = c->stats;
+static int count_alloc(Ctx* c, u64 N, u32 min_obs, int report_all, bool exact_bound, CountOut& co) {
     // Valid k-mers are a small fraction of the occurrences on real coverage (V/N ~ 0.03 at 50x): size the output by
     // an estimate and fall back to the exact bound (every valid k-mer needs >= min_obs occurrences) if it overflows.
     const u64 bound_valid = min_obs > 1 ? N / min_obs + 1 : N;
-    u64 cap_valid = std::min<u64>(bound_valid, c->valid_est_div ? N / c->valid_est_div + 16 : N / 8 + (1u << 20));
-    u64 cap_all = report_all ? N : 0;
-    DBuf<u64> v_lo, v_hi, a_lo, a_hi, ctr;
-    DBuf<u32> v_val;
-    TRY(ctr.alloc(c, 8));
+    co.cap_valid = exact_bound ? bound_valid
+                               : std::min<u64>(bound_valid, c->valid_est_div ? N / c->valid_est_div + 16 : N / 8 + (1u << 20));
+    co.cap_all = report_all ? N : 0;
+    TRY(co.ctr.alloc(c, 8));
+    TRY(co.ctr.zero());
+    TRY(co.v_lo.alloc(c, co.cap_valid));
+    TRY(co.v_val.alloc(c, co.cap_valid));
+    if (W == 2) TRY(co.v_hi.alloc(c, co.cap_valid));
     if (report_all) {
-        TRY(a_lo.alloc(c, cap_all));
-        if (W == 2) TRY(a_hi.alloc(c, cap_all));
+        TRY(co.a_lo.alloc(c, co.cap_all));
+        if (W == 2) TRY(co.a_hi.alloc(c, co.cap_all));
     }
+    return DBG_OK;
+}
+
+// ---- P2: bucket-contiguous records -> (unordered) valid k-mers appended to co.  Returns DBG_OK and sets
+// *overflow when the valid / all buffers were too small (the caller retries with the exact bound). ----
+template <int W>
+static int count_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucket_off, u32 NB, u32 min_obs, int stranded,
+                       int report_all, CountOut& co, bool* overflow) {
+    KP kp = make_kp(k);
+    cudaStream_t st = c->stream;
+    *overflow = false;
     DBuf<u32> mult, dedup_cnt;
     if (W == 1 && c->dedup) { TRY(mult.alloc(c, n_rec)); TRY(dedup_cnt.alloc(c, NB)); }
+    // per-pass counters: bucket queue [0], splits [3], error [4], distinct records [5]; [1], [2] = output cursors persist
+    CU(c, cudaMemsetAsync(co.ctr.p, 0, 8, st));
+    CU(c, cudaMemsetAsync(co.ctr.p + 3, 0, 24, st));
+    P2Args a;
+    a.rec = rec; a.mult = (W == 1 && c->dedup) ? mult.p : nullptr; a.mult_ready = 0; a.dedup_cnt = dedup_cnt.p;
+    a.bucket_off = bucket_off; a.n_buckets = NB;
+    a.min_obs = min_obs; a.stranded = stranded; a.report_all = report_all;
+    a.out_lo = co.v_lo.p; a.out_hi = co.v_hi.p; a.out_val = co.v_val.p; a.cap_valid = co.cap_valid;
+    a.all_lo = co.a_lo.p; a.all_hi = co.a_hi.p; a.cap_all = co.cap_all;
+    a.counters = co.ctr.p;
+    size_t smem = (sizeof(Kmer<W>) + 4) * P2Cfg<W>::CAP;
+    CU(c, cudaFuncSetAttribute(count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    u32 grid2 = (u32)std::min<u64>(NB, (u64)c->sm_count * P2Cfg<W>::CTAS);
+    CU(c, cudaEventRecord(c->ev[10], st));
+    count_kernel<W><<<grid2, P2Cfg<W>::THREADS, smem, st>>>(kp, a);
+    TRY(check_launch(c, "count_kernel"));
+    CU(c, cudaEventRecord(c->ev[11], st));
     u64 h[6];
-    for (int attempt = 0;; attempt++) {
-        TRY(v_lo.alloc(c, cap_valid));
-        TRY(v_val.alloc(c, cap_valid));
-        if (W == 2) TRY(v_hi.alloc(c, cap_valid));
-        TRY(ctr.zero());
-        P2Args a;
-        // a second attempt sees records that the first one already deduplicated in place: multiplicities stay valid
-        a.rec = rec; a.mult = (W == 1 && c->dedup) ? mult.p : nullptr; a.mult_ready = attempt > 0; a.dedup_cnt = dedup_cnt.p; a.bucket_off = bucket_off; a.n_buckets = NB;
-        a.min_obs = min_obs; a.stranded = stranded; a.report_all = report_all;
-        a.out_lo = v_lo.p; a.out_hi = v_hi.p; a.out_val = v_val.p; a.cap_valid = cap_valid;
-        a.all_lo = a_lo.p; a.all_hi = a_hi.p; a.cap_all = cap_all;
-        a.counters = ctr.p;
-        size_t smem = (sizeof(Kmer<W>) + 4) * P2Cfg<W>::CAP;
-        CU(c, cudaFuncSetAttribute(count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        u32 grid2 = (u32)std::min<u64>(NB, (u64)c->sm_count * P2Cfg<W>::CTAS);
-        CU(c, cudaEventRecord(c->ev[10], st));
-        count_kernel<W><<<grid2, P2Cfg<W>::THREADS, smem, st>>>(kp, a);
-        TRY(check_launch(c, "count_kernel"));
-        CU(c, cudaEventRecord(c->ev[11], st));
-        TRY(read_u64(c, ctr.p, h, 6));
-        if (h[4] == 2 && attempt == 0 && cap_valid < bound_valid) { cap_valid = bound_valid; continue; }
-        break;
-    }
-    if (!(W == 1 && c->dedup)) h[5] = 0;
-    S.n_records_distinct = h[5];
+    TRY(read_u64(c, co.ctr.p, h, 6));
+    if (h[4] == 2) { *overflow = true; return DBG_OK; }
     if (h[4]) DBG_SET_ERR(c, DBG_E_INTERNAL, "count_kernel failed (code %llu)", (unsigned long long)h[4]);
-    u64 V = h[1], U = h[2];
+    co.n_valid = h[1];
+    co.n_all = h[2];
+    co.n_splits += h[3];
+    if (W == 1 && c->dedup) co.n_rec_distinct += h[5];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[10], c->ev[11]);
+    c->stats.ms_k_count += ms;
+    return DBG_OK;
+}
+
+// ---- P3: ascending order (src/filter.rs:205-219) ----
+template <int W>
+static int sort_stage(Ctx* c, int k, int report_all, CountOut& co, Table* t) {
+    cudaStream_t st = c->stream;
+    dbg_stats& S = c->stats;
+    const u64 V = co.n_valid, U = co.n_all;
     S.n_valid = V;
     S.n_distinct = U;
-    S.n_bucket_splits = h[3];
-    CU(c, cudaEventRecord(c->ev[2], st));
-
-    // ---- P3: ascending order (src/filter.rs:205-219) ----
+    S.n_bucket_splits = co.n_splits;
+    S.n_records_distinct = co.n_rec_distinct;
     t->n = V;
     if (V) {
         DBuf<u64> b_lo, b_hi;
@@ -1218,7 +1248,7 @@ static int count_sort_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucke
         if (W == 2) TRY(b_hi.alloc_pool(c, V));
         u64 *rlo, *rhi;
         u32* rval;
-        TRY(radix_sort_pairs(c, W, 2 * k, V, v_lo.p, v_hi.p, v_val.p, b_lo.p, b_hi.p, b_val.p, &rlo, &rhi, &rval));
+        TRY(radix_sort_pairs(c, W, 2 * k, V, co.v_lo.p, co.v_hi.p, co.v_val.p, b_lo.p, b_hi.p, b_val.p, &rlo, &rhi, &rval));
         // keep right-sized arrays: take the V-sized buffer when the result landed there, else copy out of the bound-sized one
         DBuf<u8> d_exts;
         DBuf<u16> d_counts;
@@ -1245,7 +1275,7 @@ static int count_sort_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucke
         TRY(dummy_b.alloc(c, U));
         u64 *rlo, *rhi;
         u32* rval;
-        TRY(radix_sort_pairs(c, W, 2 * k, U, a_lo.p, a_hi.p, dummy_a.p, b_lo.p, b_hi.p, dummy_b.p, &rlo, &rhi, &rval));
+        TRY(radix_sort_pairs(c, W, 2 * k, U, co.a_lo.p, co.a_hi.p, dummy_a.p, b_lo.p, b_hi.p, dummy_b.p, &rlo, &rhi, &rval));
         if (rlo != b_lo.p) {
             CU(c, cudaMemcpyAsync(b_lo.p, rlo, U * 8, cudaMemcpyDeviceToDevice, st));
             if (W == 2) CU(c, cudaMemcpyAsync(b_hi.p, rhi, U * 8, cudaMemcpyDeviceToDevice, st));
@@ -1258,8 +1288,26 @@ static int count_sort_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucke
     return DBG_OK;
 }
 
+// Scratch bytes one pass needs per input k-mer occurrence handled in it (staging 5 + records 2 + dedup 0.5 + slack),
+// plus the job-wide valid-k-mer buffers (~1.5 B per occurrence).  Used by the pass planner only.
+static int plan_passes(Ctx* c, u64 N, u64 mem_gb, u32 NB) {
+    u64 budget = c->mem_budget_bytes;
+    if (!budget) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        budget = (u64)((double)(fr + c->arena_size) * 0.6);        // what the arena may grow to
+        if (mem_gb) budget = std::min<u64>(budget, mem_gb * 1000000000ull);  // the reference's memory_size (filter.rs:151-158)
+    }
+    u64 fixed = (u64)(1.5 * (double)N), per = (u64)(8.0 * (double)N);
+    if (budget <= fixed + (64u << 20)) return (int)std::min<u64>(NB, 64);
+    u64 passes = (per + (budget - fixed) - 1) / (budget - fixed);
+    if (passes < 1) passes = 1;
+    if (passes > NB) passes = NB;
+    return (int)passes;
+}
+
 template <int W>
-static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, int report_all, Table** out) {
+static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, int report_all, u64 mem_gb, Table** out) {
     cudaStream_t st = c->stream;
     dbg_stats& S = c->stats;
     TRY(arena_begin(c));
@@ -1280,30 +1328,64 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     }
     int p, bbits;
     plan_filter(c, k, N, &p, &bbits);
-    S.msp_p = p; S.bucket_bits = bbits; S.n_buckets = 1u << bbits;
-    PartOut po;
-    TRY(partition_stage<W>(c, k, s, stranded, N, max_len, p, bbits, false, po));
-    S.n_records = po.n_rec;
-    CU(c, cudaEventRecord(c->ev[1], st));
-    TRY(count_sort_stage<W>(c, k, po.rec.p, po.n_rec, po.bucket_off.p, 1u << bbits, N, min_obs, stranded, report_all, t));
+    const u32 NB = 1u << bbits;
+    S.msp_p = p; S.bucket_bits = bbits; S.n_buckets = NB;
+    // Pass planner: when one pass over all buckets would not fit the scratch budget, the buckets are split into ranges
+    // and the reads are re-scanned once per range — the reference's own scheme (filter.rs:151-203: "slices" of the 256
+    // prefix buckets sized by memory_size), with the same property: the number of passes never changes the result.
+    const int n_pass = plan_passes(c, N, mem_gb, NB);
+    S.n_passes = n_pass;
+    float ms_part = 0, ms_cnt = 0;
+    for (int attempt = 0;; attempt++) {
+        c->arena_off = 0;
+        S.ms_k_count = 0; S.ms_k_partition = 0; S.n_records = 0;
+        ms_part = ms_cnt = 0;
+        CountOut co;
+        TRY(count_alloc<W>(c, N, min_obs, report_all, attempt > 0, co));
+        const u64 mark = c->arena_off;
+        bool overflow = false;
+        for (int pass = 0; pass < n_pass && !overflow; pass++) {
+            const u32 lo = (u32)((u64)NB * pass / n_pass), hi = (u32)((u64)NB * (pass + 1) / n_pass);
+            {
+                PartOut po;
+                CU(c, cudaEventRecord(c->ev[4], st));
+                TRY(partition_stage<W>(c, k, s, stranded, N, max_len, p, bbits, lo, hi - lo, false, po));
+                S.n_records += po.n_rec;
+                CU(c, cudaEventRecord(c->ev[5], st));
+                TRY(count_stage<W>(c, k, po.rec.p, po.n_rec, po.bucket_off.p, NB, min_obs, stranded, report_all, co, &overflow));
+                CU(c, cudaEventRecord(c->ev[6], st));
+                TRY(sync(c));
+                float a1 = 0, a2 = 0, a3 = 0;
+                cudaEventElapsedTime(&a1, c->ev[4], c->ev[5]);
+                cudaEventElapsedTime(&a2, c->ev[5], c->ev[6]);
+                cudaEventElapsedTime(&a3, c->ev[8], c->ev[9]);
+                ms_part += a1; ms_cnt += a2; S.ms_k_partition += a3;
+            }
+            c->arena_off = mark;  // every per-pass buffer is gone
+        }
+        if (!overflow) {
+            CU(c, cudaEventRecord(c->ev[2], st));
+            TRY(sort_stage<W>(c, k, report_all, co, t));
+            break;
+        }
+        if (attempt == 1) DBG_SET_ERR(c, DBG_E_INTERNAL, "valid k-mer buffer overflow with the exact bound");
+    }
     TRY(sync(c));
-    cudaEventElapsedTime(&S.ms_partition, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&S.ms_count, c->ev[1], c->ev[2]);
+    S.ms_partition = ms_part;
+    S.ms_count = ms_cnt;
     cudaEventElapsedTime(&S.ms_sort, c->ev[2], c->ev[3]);
-    cudaEventElapsedTime(&S.ms_k_partition, c->ev[8], c->ev[9]);
-    cudaEventElapsedTime(&S.ms_k_count, c->ev[10], c->ev[11]);
     cudaEventElapsedTime(&S.ms_filter_total, c->ev[0], c->ev[3]);
     S.gpu_launches = c->launches;
     return DBG_OK;
 }
 
-int filter_kmers_dev(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, int report_all, u64 /*mem_gb*/,
+int filter_kmers_dev(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, int report_all, u64 mem_gb,
                      Table** out) {
     *out = nullptr;
     if (k < 4 || k > 64) DBG_SET_ERR(c, DBG_E_BADARG, "k=%d outside [4,64] (filter::bucket needs k >= 4, src/filter.rs:18-23)", k);
     if (!s) DBG_SET_ERR(c, DBG_E_BADARG, "null seqset");
-    int rc = k <= 32 ? filter_impl<1>(c, k, s, min_obs, stranded, report_all, out)
-                     : filter_impl<2>(c, k, s, min_obs, stranded, report_all, out);
+    int rc = k <= 32 ? filter_impl<1>(c, k, s, min_obs, stranded, report_all, mem_gb, out)
+                     : filter_impl<2>(c, k, s, min_obs, stranded, report_all, mem_gb, out);
     if (rc != DBG_OK && *out) { free_table(*out); *out = nullptr; }
     return rc;
 }
@@ -1328,8 +1410,8 @@ int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int
     P->ctx = c; P->k = k; P->p = p; P->bbits = bbits; P->n_input = N; P->rec_words = k <= 32 ? 2 : 4;
     PartOut po;
     int rc = DBG_OK;
-    if (N) rc = k <= 32 ? partition_stage<1>(c, k, s, stranded, N, max_len, p, bbits, true, po)
-                        : partition_stage<2>(c, k, s, stranded, N, max_len, p, bbits, true, po);
+    if (N) rc = k <= 32 ? partition_stage<1>(c, k, s, stranded, N, max_len, p, bbits, 0, 1u << bbits, true, po)
+                        : partition_stage<2>(c, k, s, stranded, N, max_len, p, bbits, 0, 1u << bbits, true, po);
     else {
         rc = po.bucket_count.alloc_pool(c, 1u << bbits);
         if (rc == DBG_OK) rc = po.bucket_count.zero();
@@ -1441,8 +1523,29 @@ int filter_from_records_dev(Ctx* c, int k, const u64* d_records, u64 n_records, 
     u64 N_local_bound = 0;
     TRY(read_u64(c, d_sum.p, &N_local_bound));  // also: host vectors may go out of scope after this sync
     S.n_input_kmers = N_local_bound;
-    int rc = k <= 32 ? count_sort_stage<1>(c, k, merged.p, n_records, d_off.p, n_local, N_local_bound, min_obs, stranded, report_all, t)
-                     : count_sort_stage<2>(c, k, merged.p, n_records, d_off.p, n_local, N_local_bound, min_obs, stranded, report_all, t);
+    int rc = DBG_OK;
+    S.ms_k_count = 0;
+    for (int attempt = 0; attempt < 2 && rc == DBG_OK; attempt++) {
+        const u64 mark = c->arena_off;
+        CountOut co;
+        bool overflow = false;
+        if (k <= 32) {
+            rc = count_alloc<1>(c, N_local_bound, min_obs, report_all, attempt > 0, co);
+            if (rc == DBG_OK) rc = count_stage<1>(c, k, merged.p, n_records, d_off.p, n_local, min_obs, stranded, report_all, co, &overflow);
+            if (rc == DBG_OK && !overflow) { cudaEventRecord(c->ev[2], st); rc = sort_stage<1>(c, k, report_all, co, t); }
+        } else {
+            rc = count_alloc<2>(c, N_local_bound, min_obs, report_all, attempt > 0, co);
+            if (rc == DBG_OK) rc = count_stage<2>(c, k, merged.p, n_records, d_off.p, n_local, min_obs, stranded, report_all, co, &overflow);
+            if (rc == DBG_OK && !overflow) { cudaEventRecord(c->ev[2], st); rc = sort_stage<2>(c, k, report_all, co, t); }
+        }
+        if (!overflow) break;
+        if (attempt == 1) { c->err = "valid k-mer buffer overflow with the exact bound"; rc = DBG_E_INTERNAL; }
+        c->arena_off = mark;
+        // the records were deduplicated in place by the first attempt: not reusable as input -> merge again
+        if (RW == 2) merge_runs_kernel<2><<<grid_for(n_groups * 32, 256), 256, 0, st>>>(d_records, merged.p, d_gsrc.p, d_gdst.p, d_gcnt.p, n_groups);
+        else merge_runs_kernel<4><<<grid_for(n_groups * 32, 256), 256, 0, st>>>(d_records, merged.p, d_gsrc.p, d_gdst.p, d_gcnt.p, n_groups);
+        c->launches++;
+    }
     if (rc != DBG_OK) { free_table(t); *out = nullptr; return rc; }
     TRY(sync(c));
     cudaEventElapsedTime(&S.ms_count, c->ev[1], c->ev[2]);

@@ -220,6 +220,22 @@ def test_sort_prefix_runs_and_fallback(D, ctx, orc):
         run_both(D, ctx, orc, k, orc.seqset_from_lists(seqs), 1, report_all=True)
 
 
+def test_multi_pass_planner(D, ctx, orc):
+    """memory_size semantics of filter_kmers (src/filter.rs:151-168): a small scratch budget splits the MSP buckets
+    into ranges and re-scans the reads once per range; the number of passes never changes the result."""
+    c2 = D.Context(0)
+    c2.set_param("mem_budget_bytes", 1)
+    ss = orc.synth_reads(3000, 1, orc.ERR_THR_NOISY)
+    run_both(D, c2, orc, 31, ss, 2, report_all=True)
+    assert c2.stats()["n_passes"] > 1
+    run_both(D, c2, orc, 63, ss, 2)
+    rng = np.random.default_rng(3)
+    big = random_dna(rng, 6000)   # non-contiguous layout: the general partition kernel also honours the bucket range
+    run_both(D, c2, orc, 31, (orc.pack_bases(big), np.array([3000, 100], np.uint64), np.array([2500, 1700], np.uint32)), 1)
+    c2.close()
+    assert ctx.stats()["n_passes"] in (0, 1)
+
+
 def test_valid_buffer_retry(D, ctx, orc):
     """The valid-k-mer buffer is sized by an estimate; force it far too small so the exact-bound retry runs
     (second attempt re-uses the already deduplicated records)."""
