@@ -179,7 +179,7 @@ int dbg_ctx_set_param(dbg_ctx* ctx, const char* name, int64_t value) {
         if (value < 0) DBG_SET_ERR(c, DBG_E_BADARG, "bucket_occ must be >= 0");
         c->target_bucket_occ = (int)value;
     } else if (!strcmp(name, "dedup")) {
-        c->dedup = value != 0;
+        c->dedup = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
     } else if (!strcmp(name, "mem_budget_bytes")) {
         c->mem_budget_bytes = value > 0 ? (u64)value : 0;
     } else if (!strcmp(name, "valid_est_div")) {

@@ -680,6 +680,117 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                 __threadfence_block();
                 __syncthreads();
             }
+        } else {
+            if (a.mult) {
+                // ---- P2a for 32-byte records: the table is keyed by a 128-bit hash of the record (one ATOMS.CAS.128);
+                // the slot owner stores the full record, everybody else verifies it before adding to the multiplicity.
+                // A mismatch (128-bit hash collision) only disables deduplication for that chunk. ----
+                constexpr int RCAP = 2048;
+                static_assert(W == 1 || RCAP / 2 == P2Cfg<2>::THREADS, "one record per thread");
+                Kmer<2>* hkeys = reinterpret_cast<Kmer<2>*>(smem_raw);
+                u64* srec = reinterpret_cast<u64*>(smem_raw + sizeof(Kmer<2>) * RCAP);
+                u32* rcnt = reinterpret_cast<u32*>(smem_raw + (sizeof(Kmer<2>) + 32) * RCAP);
+                u64 dbase = 0;
+                for (u64 c0 = r0; c0 < r1; c0 += RCAP / 2) {
+                    const u32 nrc = (u32)min((u64)(RCAP / 2), r1 - c0);
+                    for (int i = threadIdx.x; i < RCAP; i += P2T) {
+                        reinterpret_cast<u64*>(hkeys)[2 * i] = ~0ull;
+                        reinterpret_cast<u64*>(hkeys)[2 * i + 1] = ~0ull;
+                        rcnt[i] = 0;
+                    }
+                    if (threadIdx.x == 0) s_sp_cnt = 0;   // borrowed as the "verification failed" flag of this chunk
+                    __syncthreads();
+                    u64 w[4] = {0, 0, 0, 0};
+                    int my_slot = -1;
+                    const bool have = threadIdx.x < nrc;   // RCAP / 2 == P2T: one record per thread
+                    if (have) {
+                        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.rec + (c0 + threadIdx.x) * 4);
+                        ulonglong2 v0 = __ldcg(src), v1 = __ldcg(src + 1);
+                        w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; w[3] = v1.y;
+                        Kmer<2> hk;
+                        {
+                            u64 x = w[0] ^ (w[1] * 0x9E3779B97F4A7C15ull) ^ (w[2] * 0xC2B2AE3D27D4EB4Full) ^ (w[3] * 0x165667B19E3779F9ull);
+                            x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
+                            u64 y = w[3] ^ (w[2] * 0x9E3779B97F4A7C15ull) ^ (w[1] * 0xC2B2AE3D27D4EB4Full) ^ (w[0] * 0x27D4EB2F165667C5ull);
+                            y ^= y >> 29; y *= 0xBF58476D1CE4E5B9ull; y ^= y >> 32;
+                            hk.lo = x; hk.hi = y & ~1ull;   // never the all-ones EMPTY marker
+                        }
+                        u32 slot = (u32)(hk.lo >> 20) & (RCAP - 1);
+                        const Kmer<2> empty{~0ull, ~0ull};
+                        for (;;) {
+                            volatile u64* kp2 = reinterpret_cast<volatile u64*>(hkeys + slot);
+                            if (kp2[0] == hk.lo && kp2[1] == hk.hi) break;
+                            Kmer<2> old = cas128_shared(hkeys + slot, empty, hk);
+                            if (old.lo == ~0ull && old.hi == ~0ull) {   // slot owner: publish the record itself
+                                srec[4 * slot] = w[0]; srec[4 * slot + 1] = w[1]; srec[4 * slot + 2] = w[2]; srec[4 * slot + 3] = w[3];
+                                break;
+                            }
+                            if (old.lo == hk.lo && old.hi == hk.hi) break;
+                            slot = (slot + 1) & (RCAP - 1);
+                        }
+                        my_slot = (int)slot;
+                    }
+                    __syncthreads();
+                    if (have) {
+                        bool same = srec[4 * my_slot] == w[0] && srec[4 * my_slot + 1] == w[1] && srec[4 * my_slot + 2] == w[2] &&
+                                    srec[4 * my_slot + 3] == w[3];
+                        if (same) atomicAdd(&rcnt[my_slot], 1u);
+                        else s_sp_cnt = 1;
+                    }
+                    __syncthreads();
+                    const bool failed = s_sp_cnt != 0;
+                    u32 mine = 0;
+                    if (failed) mine = have ? 1u : 0u;   // keep every record of the chunk as is (multiplicity 1)
+                    else {
+#pragma unroll
+                        for (int j = 0; j < RCAP / P2T; j++) mine += rcnt[threadIdx.x * (RCAP / P2T) + j] != 0;
+                    }
+                    {
+                        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                        u32 inc = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                        if (lane == 31) s_wsum[warp] = inc;
+                        __syncthreads();
+                        if (warp == 0) {
+                            u32 ww = lane < P2T / 32 ? s_wsum[lane] : 0, winc = ww;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+                            s_wsum[lane] = winc - ww;
+                            if (lane == 31) s_pref[P2_RC] = winc;
+                        }
+                        __syncthreads();   // every record of the chunk is in registers / smem by now: in-place writes are safe
+                        u64 o = r0 + dbase + s_wsum[warp] + inc - mine;
+                        if (failed) {
+                            if (have) {
+                                ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.rec + o * 4);
+                                dst[0] = make_ulonglong2(w[0], w[1]);
+                                dst[1] = make_ulonglong2(w[2], w[3]);
+                                a.mult[o] = 1;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < RCAP / P2T; j++) {
+                                int sl = threadIdx.x * (RCAP / P2T) + j;
+                                u32 cnt = rcnt[sl];
+                                if (cnt) {
+                                    ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.rec + o * 4);
+                                    dst[0] = make_ulonglong2(srec[4 * sl], srec[4 * sl + 1]);
+                                    dst[1] = make_ulonglong2(srec[4 * sl + 2], srec[4 * sl + 3]);
+                                    a.mult[o] = cnt;
+                                    o++;
+                                }
+                            }
+                        }
+                        dbase += s_pref[P2_RC];
+                    }
+                    __syncthreads();
+                }
+                if (threadIdx.x == 0) { atomicAdd(&a.counters[5], dbase); a.dedup_cnt[b] = (u32)dbase; s_sp_cnt = 0; }
+                r1 = r0 + dbase;
+                __threadfence_block();
+                __syncthreads();
+            }
         }
         while (s_nstack > 0) {
             __syncthreads();
@@ -1197,12 +1308,13 @@ static int count_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucket_off
     cudaStream_t st = c->stream;
     *overflow = false;
     DBuf<u32> mult, dedup_cnt;
-    if (W == 1 && c->dedup) { TRY(mult.alloc(c, n_rec)); TRY(dedup_cnt.alloc(c, NB)); }
+    const bool dedup = c->dedup >= (W == 1 ? 1 : 2);   // 32-byte records dedupe only ~1.4x (K=63): opt-in (dedup=2)
+    if (dedup) { TRY(mult.alloc(c, n_rec)); TRY(dedup_cnt.alloc(c, NB)); }
     // per-pass counters: bucket queue [0], splits [3], error [4], distinct records [5]; [1], [2] = output cursors persist
     CU(c, cudaMemsetAsync(co.ctr.p, 0, 8, st));
     CU(c, cudaMemsetAsync(co.ctr.p + 3, 0, 24, st));
     P2Args a;
-    a.rec = rec; a.mult = (W == 1 && c->dedup) ? mult.p : nullptr; a.mult_ready = 0; a.dedup_cnt = dedup_cnt.p;
+    a.rec = rec; a.mult = dedup ? mult.p : nullptr; a.mult_ready = 0; a.dedup_cnt = dedup_cnt.p;
     a.bucket_off = bucket_off; a.n_buckets = NB;
     a.min_obs = min_obs; a.stranded = stranded; a.report_all = report_all;
     a.out_lo = co.v_lo.p; a.out_hi = co.v_hi.p; a.out_val = co.v_val.p; a.cap_valid = co.cap_valid;
@@ -1222,7 +1334,7 @@ static int count_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucket_off
     co.n_valid = h[1];
     co.n_all = h[2];
     co.n_splits += h[3];
-    if (W == 1 && c->dedup) co.n_rec_distinct += h[5];
+    if (dedup) co.n_rec_distinct += h[5];
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[10], c->ev[11]);
     c->stats.ms_k_count += ms;

@@ -255,6 +255,9 @@ def test_record_dedup_off(D, ctx, orc):
     run_both(D, c2, orc, 31, ss, 2, report_all=True)
     seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")
     run_both(D, c2, orc, 31, orc.seqset_from_lists([seq] * 70000), 1)
+    c2.set_param("dedup", 2)   # also deduplicate the 32-byte records of two-word keys (off by default: ~neutral)
+    run_both(D, c2, orc, 63, ss, 2, report_all=True)
+    run_both(D, c2, orc, 40, orc.seqset_from_lists([np.tile(seq, 3)] * 300), 1)
     c2.close()
 
 
