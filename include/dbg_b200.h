@@ -177,6 +177,25 @@ int dbg_table_from_device(dbg_ctx* ctx, int k, uint64_t n, const void* d_kmers_l
 int dbg_table_from_device_sorted(dbg_ctx* ctx, int k, uint64_t n, const void* d_kmers_lo, const void* d_kmers_hi,
                                  const void* d_exts, const void* d_counts, dbg_kmer_table** out);
 
+/* ---- sharded compression (multi-GPU): the sorted table is replicated on every rank, the work is split by k-mer
+ * index range.  Sequence per rank (collectives by the caller, see rust_debruijn_b200/sharded.py):
+ *   dbg_cs_links  -> all-gather nxt -> dbg_cs_paths -> all-gather (seed,length) -> dbg_cs_layout -> dbg_cs_emit
+ *   -> all-reduce(sum) of words / exts / data -> dbg_graph_from_device.
+ * All pointers are DEVICE pointers owned by the caller.  Only unitigs reachable by end walks (<= lmax k-mers) are
+ * handled: if the covered k-mers over all ranks do not add up to the table size (long unitigs, cycles) the caller
+ * falls back to dbg_compress_kmers_with_hash on the replicated table. */
+int dbg_cs_links(dbg_ctx* ctx, const dbg_kmer_table* full_table, int stranded, uint64_t v0, uint64_t v1, void* d_nxt_local);
+int dbg_cs_paths(dbg_ctx* ctx, const void* d_nxt_full, uint64_t v0, uint64_t v1, uint32_t lmax, void* d_paths /* 16 B each */,
+                 uint64_t capacity, uint64_t* n_paths, uint64_t* n_kmers_covered);
+int dbg_cs_layout(dbg_ctx* ctx, int k, uint64_t n_nodes, const void* d_seed_len_pairs /* 8 B each */, void* d_seed_sorted /* u64 */,
+                  void* d_start /* u64 */, void* d_length /* u32 */, uint64_t* n_bases);
+int dbg_cs_emit(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_nxt_full, const void* d_paths, uint64_t n_paths,
+                const void* d_seed_sorted, const void* d_start, uint64_t n_nodes, int reduce_op, void* d_words,
+                void* d_exts_words /* u32, 4 nodes each */, void* d_data /* u16 */);
+int dbg_graph_from_device(dbg_ctx* ctx, int k, int stranded, uint64_t n_nodes, uint64_t n_bases, const void* d_words,
+                          const void* d_start, const void* d_length, const void* d_exts_words, const void* d_data,
+                          dbg_graph** out);
+
 /* ---- msp::msp_sequence bucket assignment — src/msp.rs:279-324, 115-117 -----------------------------
  * For every k-mer start position j of every sequence: the MSP bucket of that k-mer under the
  * reference's default (identity) permutation with rc = !stranded, i.e. the value

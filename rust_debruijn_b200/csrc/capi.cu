@@ -601,6 +601,55 @@ int dbg_filter_from_records(dbg_ctx* ctx, int k, const void* d_records, uint64_t
     return rc;
 }
 
+// ---- sharded compression ------------------------------------------------------------------------------------
+int dbg_cs_links(dbg_ctx* ctx, const dbg_kmer_table* full_table, int stranded, uint64_t v0, uint64_t v1, void* d_nxt_local) {
+    if (!ctx) return DBG_E_BADARG;
+    NULLCHK(ctx, full_table);
+    cudaSetDevice(ctx->c.device);
+    return cs_links_dev(CTX(ctx), &full_table->t, stranded != 0, v0, v1, (u32*)d_nxt_local);
+}
+int dbg_cs_paths(dbg_ctx* ctx, const void* d_nxt_full, uint64_t v0, uint64_t v1, uint32_t lmax, void* d_paths,
+                 uint64_t capacity, uint64_t* n_paths, uint64_t* n_kmers_covered) {
+    if (!ctx || !n_paths || !n_kmers_covered) return DBG_E_BADARG;
+    cudaSetDevice(ctx->c.device);
+    u64 np = 0, nc = 0;
+    int rc = cs_paths_dev(CTX(ctx), (const u32*)d_nxt_full, v0, v1, lmax, (uint4*)d_paths, capacity, &np, &nc);
+    *n_paths = np; *n_kmers_covered = nc;
+    return rc;
+}
+int dbg_cs_layout(dbg_ctx* ctx, int k, uint64_t n_nodes, const void* d_pairs, void* d_seed_sorted, void* d_start,
+                  void* d_length, uint64_t* n_bases) {
+    if (!ctx || !n_bases) return DBG_E_BADARG;
+    cudaSetDevice(ctx->c.device);
+    u64 nb = 0;
+    int rc = cs_layout_dev(CTX(ctx), k, n_nodes, (const uint2*)d_pairs, (u64*)d_seed_sorted, (u64*)d_start, (u32*)d_length, &nb);
+    if (rc == DBG_OK) rc = sync(CTX(ctx));
+    *n_bases = nb;
+    return rc;
+}
+int dbg_cs_emit(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_nxt_full, const void* d_paths, uint64_t n_paths,
+                const void* d_seed_sorted, const void* d_start, uint64_t n_nodes, int reduce_op, void* d_words,
+                void* d_exts_words, void* d_data) {
+    if (!ctx) return DBG_E_BADARG;
+    NULLCHK(ctx, full_table);
+    if (reduce_op < 0 || reduce_op > 3) DBG_SET_ERR(CTX(ctx), DBG_E_BADARG, "unknown reduce_op %d", reduce_op);
+    cudaSetDevice(ctx->c.device);
+    return cs_emit_dev(CTX(ctx), &full_table->t, (const u32*)d_nxt_full, (const uint4*)d_paths, n_paths, (const u64*)d_seed_sorted,
+                       (const u64*)d_start, n_nodes, reduce_op, (u64*)d_words, (u32*)d_exts_words, (u16*)d_data);
+}
+int dbg_graph_from_device(dbg_ctx* ctx, int k, int stranded, uint64_t n_nodes, uint64_t n_bases, const void* d_words,
+                          const void* d_start, const void* d_length, const void* d_exts_words, const void* d_data,
+                          dbg_graph** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    *out = nullptr;
+    cudaSetDevice(ctx->c.device);
+    Graph* g = nullptr;
+    int rc = graph_from_device_dev(CTX(ctx), k, stranded != 0, n_nodes, n_bases, (const u64*)d_words, (const u64*)d_start,
+                                   (const u32*)d_length, (const u32*)d_exts_words, (const u16*)d_data, &g);
+    *out = reinterpret_cast<dbg_graph*>(g);
+    return rc;
+}
+
 void dbg_table_free(dbg_kmer_table* t) { if (t) { cudaSetDevice(t->t.ctx->device); free_table(&t->t); } }
 
 // ---- compress ------------------------------------------------------------------------------------------

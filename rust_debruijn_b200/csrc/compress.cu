@@ -71,10 +71,13 @@ __device__ __forceinline__ u32 table_find(const u64* __restrict__ lo, const u64*
 // ---- S4 -------------------------------------------------------------------------------------------
 template <int W>
 __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __restrict__ hi, const u8* __restrict__ exts,
-                             u64 n, const u64* __restrict__ lut, int lut_shift,
+                             u64 v0, u64 n, const u64* __restrict__ lut, int lut_shift,
                              int stranded, u32* __restrict__ nxt, u32* __restrict__ err) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    // thread t handles k-mer i = v0 + t of the (full) table and writes nxt[2t + side]: v0 = 0, n = V on one GPU;
+    // a rank of the sharded compression handles only its own index range
+    u64 t_ = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_ >= n) return;
+    const u64 i = v0 + t_;
     Kmer<W> key = load_key<W>(lo, hi, i);
     u32 e = exts[i];
     bool pal = !stranded && is_palindrome<W>(kp, key);
@@ -107,8 +110,7 @@ __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __res
                 }
             }
         }
-        u32 s = 2u * (u32)i + d;
-        nxt[s] = succ;
+        nxt[2 * t_ + d] = succ;
     }
 }
 
@@ -458,7 +460,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     TRY(nxt.alloc(c, NS));
     TRY(ctr.alloc(c, 4));
     TRY(ctr.zero());
-    links_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, V, lut.p, lut_shift, stranded, nxt.p,
+    links_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, 0, V, lut.p, lut_shift, stranded, nxt.p,
                                                       (u32*)(ctr.p + 3));
     TRY(check_launch(c, "links"));
     CU(c, cudaEventRecord(c->ev[2], st));
@@ -596,6 +598,270 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     cudaEventElapsedTime(&S.ms_emit, c->ev[3], c->ev[4]);
     cudaEventElapsedTime(&S.ms_compress_total, c->ev[0], c->ev[4]);
     S.gpu_launches = c->launches;
+    return DBG_OK;
+}
+
+// ================================================================================================
+// Sharded compression (multi-GPU): the sorted table is replicated, the WORK is split.
+//   cs_links   links of the rank's own k-mer range [v0, v1)               (caller all-gathers nxt)
+//   cs_paths   unitigs whose winning end lies in [v0, v1): one record each (caller all-gathers seeds)
+//   cs_layout  node order = ascending seed: sort (seed, length), scan     (replicated, M entries only)
+//   cs_emit    the rank re-walks ITS unitigs and writes bases / Exts / data into zeroed full-size arrays
+//              (caller all-reduces: every word has exactly one writer, so sum == OR)
+// Only components reachable by end walks (<= lmax k-mers) are handled; cs_paths reports how many k-mers
+// that covered and the caller falls back to the replicated single-GPU compression otherwise.
+// ================================================================================================
+__device__ __forceinline__ u32 end_rank_hash(u32 v) { u32 h = v * 0x9E3779B1u; h ^= h >> 15; h *= 0x85EBCA6Bu; h ^= h >> 13; return h; }
+
+// path record: x = seed, y = length in k-mers, z = port state at the left end heading right, w = unused
+__global__ void cs_paths_kernel(const u32* __restrict__ nxt, u64 v0, u64 n_local, u32 lmax, uint4* __restrict__ paths,
+                                u64 cap, u64* __restrict__ counters /* [0] n_paths, [1] k-mers covered */) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 covered = 0;
+    if (t < n_local) {
+        const u32 v = (u32)(v0 + t);
+        u32 a0 = nxt[2 * (u64)v], a1 = nxt[2 * (u64)v + 1];
+        bool emit = false;
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (a0 == NIL && a1 == NIL) {
+            emit = true;
+            rec = make_uint4(v, 1u, 2u * v + 1u, 0u);  // single k-mer, stored orientation: heading right = leaving through R
+        } else if (a0 == NIL || a1 == NIL) {
+            const u32 d = a0 == NIL ? 1u : 0u;
+            u32 cur = 2u * v + d, cnt = 1, minv = v, minst = cur;
+            u32 tt = d ? a1 : a0;
+            while (tt != NIL && cnt <= lmax) {
+                cur = tt;
+                cnt++;
+                if ((tt >> 1) < minv) { minv = tt >> 1; minst = tt; }
+                tt = nxt[cur];
+            }
+            const u32 u = cur >> 1;  // far end
+            // exactly one of the two end walkers wins: the end with the smaller (hash, index) — balanced over ranks
+            const u32 hv = end_rank_hash(v), hu = end_rank_hash(u);
+            if (tt == NIL && (hv < hu || (hv == hu && v < u))) {
+                emit = true;
+                const bool right = minst & 1u;               // this walk runs left -> right in node coordinates
+                // left end heading right: this end if the walk runs rightwards, else the far end turned around
+                u32 left_state = right ? 2u * v + d : (cur ^ 1u);
+                rec = make_uint4(minv, cnt, left_state, 0u);
+            }
+        }
+        if (emit) {
+            u64 pos = atomicAdd(&counters[0], 1ull);
+            if (pos < cap) paths[pos] = rec;
+            covered = rec.y;
+        }
+    }
+    for (int o = 16; o; o >>= 1) covered += __shfl_xor_sync(0xffffffffu, covered, o);
+    if ((threadIdx.x & 31) == 0 && covered) atomicAdd(&counters[1], (u64)covered);
+}
+
+__global__ void cs_pack_seeds_kernel(const uint4* __restrict__ paths, u64 n, u64* __restrict__ seed64, u32* __restrict__ nlen) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { seed64[i] = paths[i].x; nlen[i] = paths[i].y; }
+}
+__global__ void cs_unpack_pairs_kernel(const uint2* __restrict__ pairs, u64 m, u64* __restrict__ key, u32* __restrict__ val) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) { uint2 p = pairs[i]; key[i] = p.x; val[i] = p.y; }
+}
+__global__ void cs_node_len_kernel(const u32* __restrict__ nlen, u64 m, int K, u64* __restrict__ node_len, u32* __restrict__ out_length) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) { u64 l = (u64)nlen[i] + K - 1; node_len[i] = l; out_length[i] = (u32)l; }
+}
+
+struct CsEmitArgs {
+    const u64* lo; const u64* hi; const u8* exts; const u16* counts;
+    const u32* nxt; const uint4* paths; u64 n_paths;
+    const u64* seed_sorted; const u64* node_start; u64 n_nodes;
+    u64* words; u32* out_exts_w; u16* out_data; int reduce_op;
+};
+
+template <int W>
+__global__ void cs_emit_kernel(KP kp, CsEmitArgs a) {
+    u64 pi = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= a.n_paths) return;
+    const uint4 pr = a.paths[pi];
+    // node id = rank of the seed among all seeds (ascending): binary search in the replicated sorted list
+    u64 lo_ = 0, hi_ = a.n_nodes;
+    while (lo_ < hi_) { u64 m = (lo_ + hi_) >> 1; if (a.seed_sorted[m] < (u64)pr.x) lo_ = m + 1; else hi_ = m; }
+    const u64 nid = lo_;
+    const u64 st = a.node_start[nid];
+    const int K = kp.k;
+    u32 cur = pr.z;          // at the left end, leaving through its right-facing side
+    u64 acc = 0;
+    u32 eb = 0;
+    for (u32 i = 0; i < pr.y; i++) {
+        const u32 w = cur >> 1, dw = cur & 1u;
+        const bool fw = dw == 1u;                     // leaving through R while heading right = stored orientation
+        Kmer<W> key = load_key<W>(a.lo, a.hi, w);
+        if (!fw) key = Ops<W>::rc(kp, key);
+        if (i == 0) {
+            int off = (int)(st & 31) * 2;
+            u64 wd = st >> 5;
+            if constexpr (W == 1) {
+                u64 X = key.lo << (64 - 2 * K);
+                atomicOr(&a.words[wd], X >> off);
+                if (off && off + 2 * K > 64) atomicOr(&a.words[wd + 1], X << (64 - off));
+            } else {
+                int sh = 128 - 2 * K;
+                u64 H = sh ? (key.hi << sh) | (key.lo >> (64 - sh)) : key.hi;
+                u64 L = key.lo << sh;
+                atomicOr(&a.words[wd], H >> off);
+                u64 m2 = off ? (H << (64 - off)) | (L >> off) : L;
+                if (m2) atomicOr(&a.words[wd + 1], m2);
+                if (off) { u64 t2 = L << (64 - off); if (t2) atomicOr(&a.words[wd + 2], t2); }
+            }
+            u32 nib = exts_side(a.exts[w], (int)(dw ^ 1u));   // left-facing side of the first k-mer
+            if (!fw) nib = exts_complement(nib) & 0xfu;
+            eb |= nib;
+        } else {
+            u64 g = st + i + K - 1;
+            u64 b = Ops<W>::last_base(kp, key);
+            if (b) atomicOr(&a.words[g >> 5], b << (62 - 2 * (g & 31)));
+        }
+        if (i == pr.y - 1) {
+            u32 nib = exts_side(a.exts[w], (int)dw);          // right-facing side of the last k-mer
+            if (!fw) nib = exts_complement(nib) & 0xfu;
+            eb |= nib << 4;
+        }
+        u64 cnt = a.counts[w];
+        if (a.reduce_op == DBG_REDUCE_MAX) acc = cnt > acc ? cnt : acc; else acc += cnt;
+        cur = a.nxt[cur];
+    }
+    if (eb) atomicOr(&a.out_exts_w[nid >> 2], eb << (8 * (nid & 3)));
+    u16 d;
+    switch (a.reduce_op) {
+        case DBG_REDUCE_SAT_ADD: d = (u16)(acc > 65535 ? 65535 : acc); break;
+        case DBG_REDUCE_WRAP_ADD: d = (u16)(acc & 0xffff); break;
+        case DBG_REDUCE_ADD_MOD_65535: d = pr.y == 1 ? (u16)acc : (u16)(acc % 65535); break;
+        default: d = (u16)acc; break;
+    }
+    a.out_data[nid] = d;   // single writer per node
+}
+
+template <int W>
+static int cs_links_impl(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u32* d_nxt_out) {
+    cudaStream_t st = c->stream;
+    KP kp = make_kp(t->k);
+    const u64 V = t->n;
+    TRY(arena_begin(c));
+    int lb = 8;
+    while ((1ull << (lb + 4)) <= V && lb < 24) lb++;
+    if (lb > 2 * t->k) lb = 2 * t->k;
+    const int lut_shift = 2 * t->k - lb;
+    const u64 n_pfx = 1ull << lb;
+    DBuf<u32> lut_cnt;
+    DBuf<u64> lut, ctr;
+    TRY(lut_cnt.alloc(c, n_pfx)); TRY(lut.alloc(c, n_pfx + 1)); TRY(ctr.alloc(c, 4));
+    TRY(lut_cnt.zero()); TRY(ctr.zero());
+    lut_hist_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(t->lo, t->hi, V, lut_shift, lut_cnt.p);
+    TRY(check_launch(c, "lut_hist"));
+    TRY(exclusive_scan_u32_to_u64(c, lut_cnt.p, lut.p, n_pfx, lut.p + n_pfx));
+    if (v1 > v0) {
+        links_kernel<W><<<grid_for(v1 - v0, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, v0, v1 - v0, lut.p, lut_shift, stranded,
+                                                                d_nxt_out, (u32*)(ctr.p + 3));
+        TRY(check_launch(c, "links"));
+    }
+    u64 h[4];
+    TRY(read_u64(c, ctr.p, h, 4));
+    if (h[3] == 1) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extension points at a k-mer with no extension back (src/compression.rs:428-434)");
+    if (h[3] == 2) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extensions are not reciprocal");
+    return DBG_OK;
+}
+
+int cs_links_dev(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u32* d_nxt_out) {
+    if (!t || v1 < v0 || v1 > t->n) DBG_SET_ERR(c, DBG_E_BADARG, "bad k-mer range");
+    if (t->n >= (1ull << 31)) DBG_SET_ERR(c, DBG_E_BADARG, "k-mer table too large for 32-bit port states");
+    return t->k <= 32 ? cs_links_impl<1>(c, t, stranded, v0, v1, d_nxt_out) : cs_links_impl<2>(c, t, stranded, v0, v1, d_nxt_out);
+}
+
+int cs_paths_dev(Ctx* c, const u32* d_nxt_full, u64 v0, u64 v1, u32 lmax, uint4* d_paths, u64 cap, u64* n_paths, u64* n_covered) {
+    TRY(arena_begin(c));
+    DBuf<u64> ctr;
+    TRY(ctr.alloc(c, 2));
+    TRY(ctr.zero());
+    if (v1 > v0) {
+        cs_paths_kernel<<<grid_for(v1 - v0, 256), 256, 0, c->stream>>>(d_nxt_full, v0, v1 - v0, lmax, d_paths, cap, ctr.p);
+        TRY(check_launch(c, "cs_paths"));
+    }
+    u64 h[2];
+    TRY(read_u64(c, ctr.p, h, 2));
+    if (h[0] > cap) DBG_SET_ERR(c, DBG_E_BADARG, "path buffer too small (%llu > %llu)", (unsigned long long)h[0], (unsigned long long)cap);
+    *n_paths = h[0];
+    *n_covered = h[1];
+    return DBG_OK;
+}
+
+// d_pairs: m (seed, length) pairs as uint2 in any order.  Outputs (device, caller-allocated): seed_sorted[m] (u64),
+// start[m] (u64), length[m] (u32); *n_bases = total bases.
+int cs_layout_dev(Ctx* c, int k, u64 m, const uint2* d_pairs, u64* d_seed_sorted, u64* d_start, u32* d_length, u64* n_bases) {
+    *n_bases = 0;
+    if (m == 0) return DBG_OK;
+    TRY(arena_begin(c));
+    cudaStream_t st = c->stream;
+    DBuf<u64> ka, kb, tot, nl64;
+    DBuf<u32> va, vb;
+    TRY(ka.alloc(c, m)); TRY(kb.alloc(c, m)); TRY(va.alloc(c, m)); TRY(vb.alloc(c, m)); TRY(tot.alloc(c, 1)); TRY(nl64.alloc(c, m));
+    cs_unpack_pairs_kernel<<<grid_for(m, 256), 256, 0, st>>>(d_pairs, m, ka.p, va.p);   // (seed, length) -> sort key / payload
+    TRY(check_launch(c, "cs_unpack_pairs"));
+    u64 *rk, *rh;
+    u32* rv;
+    TRY(radix_sort_pairs(c, 1, 32, m, ka.p, nullptr, va.p, kb.p, nullptr, vb.p, &rk, &rh, &rv));
+    CU(c, cudaMemcpyAsync(d_seed_sorted, rk, m * 8, cudaMemcpyDeviceToDevice, st));
+    cs_node_len_kernel<<<grid_for(m, 256), 256, 0, st>>>(rv, m, k, nl64.p, d_length);
+    TRY(check_launch(c, "cs_node_len"));
+    TRY(exclusive_scan_u64(c, nl64.p, d_start, m, tot.p));
+    TRY(read_u64(c, tot.p, n_bases));
+    return DBG_OK;
+}
+
+int cs_emit_dev(Ctx* c, const Table* t, const u32* d_nxt_full, const uint4* d_paths, u64 n_paths, const u64* d_seed_sorted,
+                const u64* d_start, u64 n_nodes, int reduce_op, u64* d_words, u32* d_exts_w, u16* d_data) {
+    if (n_paths == 0) return DBG_OK;
+    KP kp = make_kp(t->k);
+    CsEmitArgs a;
+    a.lo = t->lo; a.hi = t->hi; a.exts = t->exts; a.counts = t->counts;
+    a.nxt = d_nxt_full; a.paths = d_paths; a.n_paths = n_paths;
+    a.seed_sorted = d_seed_sorted; a.node_start = d_start; a.n_nodes = n_nodes;
+    a.words = d_words; a.out_exts_w = d_exts_w; a.out_data = d_data; a.reduce_op = reduce_op;
+    if (t->k <= 32) cs_emit_kernel<1><<<grid_for(n_paths, 128), 128, 0, c->stream>>>(kp, a);
+    else cs_emit_kernel<2><<<grid_for(n_paths, 128), 128, 0, c->stream>>>(kp, a);
+    TRY(check_launch(c, "cs_emit"));
+    return sync(c);
+}
+
+// Adopt caller-owned device arrays (copied) as a BaseGraph handle.  d_exts_w = node Exts packed 4 per u32.
+int graph_from_device_dev(Ctx* c, int k, int stranded, u64 n_nodes, u64 n_bases, const u64* d_words, const u64* d_start,
+                          const u32* d_length, const u32* d_exts_w, const u16* d_data, Graph** out) {
+    *out = nullptr;
+    cudaStream_t st = c->stream;
+    Graph* g = &(new dbg_graph())->g;
+    g->ctx = c; g->k = k; g->stranded = stranded; g->n_nodes = n_nodes; g->n_bases = n_bases; g->n_words = (n_bases + 31) / 32;
+    *out = g;
+    if (n_nodes == 0) return DBG_OK;
+    DBuf<u64> words, ostart;
+    DBuf<u32> olen;
+    DBuf<u8> oexts;
+    DBuf<u16> odata;
+    int rc = words.alloc_pool(c, g->n_words + 3);
+    if (rc == DBG_OK) rc = ostart.alloc_pool(c, n_nodes);
+    if (rc == DBG_OK) rc = olen.alloc_pool(c, n_nodes);
+    if (rc == DBG_OK) rc = oexts.alloc_pool(c, n_nodes);
+    if (rc == DBG_OK) rc = odata.alloc_pool(c, n_nodes);
+    if (rc != DBG_OK) { free_graph(g); *out = nullptr; return rc; }
+    cudaMemcpyAsync(words.p, d_words, g->n_words * 8, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(ostart.p, d_start, n_nodes * 8, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(olen.p, d_length, n_nodes * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(odata.p, d_data, n_nodes * 2, cudaMemcpyDeviceToDevice, st);
+    bytes_from_words_kernel<<<grid_for(n_nodes, 256), 256, 0, st>>>(d_exts_w, oexts.p, n_nodes);
+    c->launches++;
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        free_graph(g); *out = nullptr;
+        DBG_SET_ERR(c, DBG_E_CUDA, "graph_from_device: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    g->words = words.take(); g->start = ostart.take(); g->length = olen.take(); g->exts = oexts.take(); g->data = odata.take();
+    c->stats.n_nodes = n_nodes; c->stats.n_bases = n_bases;
     return DBG_OK;
 }
 

@@ -232,7 +232,112 @@ def gather_table(table, group=None):
     ctx.check(L.dbg_table_from_device_sorted(ctx._h, k, total, C.c_void_p(g_lo.data_ptr()),
                                              C.c_void_p(g_hi.data_ptr()) if two else None, C.c_void_p(g_ex.data_ptr()),
                                              C.c_void_p(g_cn.data_ptr()), C.byref(th)))
-    return KmerTable(ctx, th)
+    full = KmerTable(ctx, th)
+    full.piece_sizes = sizes   # rank r's key range = global indices [sum(sizes[:r]), sum(sizes[:r+1]))
+    return full
+
+
+def _all_gather_uneven(t, sizes, itemsize, group, dev):
+    """All-gather 1-D uint8 views of different lengths (sizes in items); returns the concatenation in rank order."""
+    import torch
+    import torch.distributed as dist
+    world = len(sizes)
+    mx = max(max(sizes), 1) * itemsize
+    pad = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    n = t.numel()
+    if n:
+        pad[:n] = t
+    out = torch.empty(world * mx, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    if all(x == sizes[0] for x in sizes):
+        return out if mx == sizes[0] * itemsize else torch.cat([out[r * mx: r * mx + sizes[r] * itemsize] for r in range(world)])
+    return torch.cat([out[r * mx: r * mx + sizes[r] * itemsize] for r in range(world)])
+
+
+def compress_sharded(full, stranded, spec, group=None, lmax=1024, timings=None):
+    """compression::compress_kmers_with_hash over a table replicated on every rank, with the WORK split by k-mer index
+    range: links for the own range (+ all-gather), unitig discovery for the path ends in the own range, node layout
+    from the all-gathered (seed, length) pairs, emission of the own unitigs into zeroed full-size arrays, one
+    all-reduce (every word has a single writer, so sum == OR).  Every rank returns the complete BaseGraph.
+    Unitigs longer than `lmax` k-mers and cycles are not handled here: the function then returns None and the
+    caller runs the replicated single-GPU compression instead."""
+    import torch
+    import torch.distributed as dist
+    ctx, L = full.ctx, full.ctx._L
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", ctx.device)
+    k, V = full.k, len(full)
+    sizes = getattr(full, "piece_sizes", None)
+    if sizes is None or sum(sizes) != V:
+        sizes = [(V * (r + 1)) // world - (V * r) // world for r in range(world)]
+    v0 = sum(sizes[:rank])
+    v1 = v0 + sizes[rank]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if timings is not None else None
+
+    def mark(i):
+        if ev:
+            ctx.synchronize()
+            ev[i].record()
+
+    mark(0)
+    # ---- links of the own range, all-gather ----
+    nxt_local = torch.empty(2 * (v1 - v0), dtype=torch.int32, device=dev)
+    ctx.check(L.dbg_cs_links(ctx._h, full._h, int(bool(stranded)), v0, v1, C.c_void_p(nxt_local.data_ptr())))
+    nxt = _all_gather_uneven(nxt_local.view(torch.uint8), [2 * x for x in sizes], 4, group, dev)
+    torch.cuda.synchronize(dev)
+    mark(1)
+    # ---- unitigs whose winning end is in the own range ----
+    paths = torch.empty(max(v1 - v0, 1) * 16, dtype=torch.uint8, device=dev)
+    n_paths, n_cov = C.c_uint64(), C.c_uint64()
+    ctx.check(L.dbg_cs_paths(ctx._h, C.c_void_p(nxt.data_ptr()), v0, v1, lmax, C.c_void_p(paths.data_ptr()), max(v1 - v0, 1),
+                             C.byref(n_paths), C.byref(n_cov)))
+    np_local = n_paths.value
+    tot = torch.tensor([np_local, n_cov.value], dtype=torch.int64, device=dev)
+    allc = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc, tot, group=group)
+    allc = allc.view(world, 2).tolist()
+    if sum(int(x[1]) for x in allc) != V:
+        return None   # long unitigs or cycles present: replicated fallback
+    counts = [int(x[0]) for x in allc]
+    M = sum(counts)
+    mark(2)
+    # ---- node layout: all-gather (seed, length), sort + scan (replicated; M entries only) ----
+    pairs_local = paths.view(torch.int32).view(-1, 4)[:np_local, :2].contiguous()
+    pairs = _all_gather_uneven(pairs_local.view(torch.uint8).view(-1), counts, 8, group, dev)
+    seed_sorted = torch.empty(max(M, 1), dtype=torch.int64, device=dev)
+    start = torch.empty(max(M, 1), dtype=torch.int64, device=dev)
+    length = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+    nb = C.c_uint64()
+    torch.cuda.synchronize(dev)
+    ctx.check(L.dbg_cs_layout(ctx._h, k, M, C.c_void_p(pairs.data_ptr()), C.c_void_p(seed_sorted.data_ptr()),
+                              C.c_void_p(start.data_ptr()), C.c_void_p(length.data_ptr()), C.byref(nb)))
+    n_bases = nb.value
+    n_words = (n_bases + 31) // 32
+    mark(3)
+    # ---- emission of the own unitigs, all-reduce ----
+    words = torch.zeros(n_words + 3, dtype=torch.int64, device=dev)
+    extsw = torch.zeros(M // 4 + 1, dtype=torch.int32, device=dev)
+    data = torch.zeros(max(M, 1), dtype=torch.int16, device=dev)
+    torch.cuda.synchronize(dev)
+    ctx.check(L.dbg_cs_emit(ctx._h, full._h, C.c_void_p(nxt.data_ptr()), C.c_void_p(paths.data_ptr()), np_local,
+                            C.c_void_p(seed_sorted.data_ptr()), C.c_void_p(start.data_ptr()), M, spec.func,
+                            C.c_void_p(words.data_ptr()), C.c_void_p(extsw.data_ptr()), C.c_void_p(data.data_ptr())))
+    mark(4)
+    dist.all_reduce(words, group=group)
+    dist.all_reduce(extsw, group=group)
+    dist.all_reduce(data, group=group)
+    torch.cuda.synchronize(dev)
+    gh = C.c_void_p()
+    ctx.check(L.dbg_graph_from_device(ctx._h, k, int(bool(stranded)), M, n_bases, C.c_void_p(words.data_ptr()),
+                                      C.c_void_p(start.data_ptr()), C.c_void_p(length.data_ptr()),
+                                      C.c_void_p(extsw.data_ptr()), C.c_void_p(data.data_ptr()), C.byref(gh)))
+    mark(5)
+    if ev:
+        torch.cuda.synchronize(dev)
+        timings.update(ms_cs_links=ev[0].elapsed_time(ev[1]), ms_cs_paths=ev[1].elapsed_time(ev[2]),
+                       ms_cs_layout=ev[2].elapsed_time(ev[3]), ms_cs_emit=ev[3].elapsed_time(ev[4]),
+                       ms_cs_allreduce=ev[4].elapsed_time(ev[5]), compress="sharded")
+    return BaseGraph(ctx, gh)
 
 
 def reads_to_graph_sharded(seqs, summarizer, spec, stranded=False, k=31, group=None, timings=None):
@@ -247,7 +352,11 @@ def reads_to_graph_sharded(seqs, summarizer, spec, stranded=False, k=31, group=N
     full = gather_table(shard, group)
     t1.record()
     shard.free()
-    g = compress_kmers_with_hash(stranded, spec, full)
+    g = compress_sharded(full, stranded, spec, group=group, timings=timings)
+    if g is None:   # long unitigs / cycles: replicated single-GPU compression on every rank
+        g = compress_kmers_with_hash(stranded, spec, full)
+        if timings is not None:
+            timings["compress"] = "replicated"
     t2.record()
     if timings is not None:
         torch.cuda.synchronize()
