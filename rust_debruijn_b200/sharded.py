@@ -325,7 +325,7 @@ def compress_sharded(full, stranded, spec, group=None, lmax=1024, timings=None):
     mark(4)
     dist.all_reduce(words, group=group)
     dist.all_reduce(extsw, group=group)
-    dist.all_reduce(data, group=group)
+    dist.all_reduce(data.view(torch.uint8), group=group)   # single writer per node: byte-wise sum has no carries
     torch.cuda.synchronize(dev)
     gh = C.c_void_p()
     ctx.check(L.dbg_graph_from_device(ctx._h, k, int(bool(stranded)), M, n_bases, C.c_void_p(words.data_ptr()),
