@@ -73,7 +73,8 @@ void dbg_ctx_destroy(dbg_ctx* ctx);
 const char* dbg_last_error(const dbg_ctx* ctx);
 int dbg_stats_get(const dbg_ctx* ctx, dbg_stats* out);
 /* tunables: "msp_p" (minimizer length, 0 = auto), "bucket_occ" (target k-mer occurrences per MSP
- * bucket, 0 = auto), "dedup" (0 = off, 1 = 16-byte records [default], 2 = also 32-byte records), "mem_budget_bytes" (scratch budget of the pass planner, 0 = auto). */
+ * bucket, 0 = auto), "dedup" (0 = off, 1 = 16-byte records [default], 2 = also 32-byte records), "mem_budget_bytes" (scratch budget of the pass planner, 0 = auto), "fast_compress" (1 = default; 0 = always use the general per-k-mer rank + emit
+ * path of compress_kmers, which otherwise only runs when long unitigs or cycles are present). */
 int dbg_ctx_set_param(dbg_ctx* ctx, const char* name, int64_t value);
 int dbg_ctx_synchronize(dbg_ctx* ctx);
 /* The cudaStream_t every call of this ctx is ordered on (for event timing / interop with other runtimes). */

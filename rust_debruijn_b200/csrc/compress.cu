@@ -72,15 +72,19 @@ __device__ __forceinline__ u32 table_find(const u64* __restrict__ lo, const u64*
 template <int W>
 __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __restrict__ hi, const u8* __restrict__ exts,
                              u64 v0, u64 n, const u64* __restrict__ lut, int lut_shift,
-                             int stranded, u32* __restrict__ nxt, u32* __restrict__ err) {
+                             int stranded, u32* __restrict__ nxt, u32* __restrict__ err, uint4* __restrict__ rec16,
+                             const u16* __restrict__ counts) {
     // thread t handles k-mer i = v0 + t of the (full) table and writes nxt[2t + side]: v0 = 0, n = V on one GPU;
-    // a rank of the sharded compression handles only its own index range
+    // a rank of the sharded compression handles only its own index range.  With rec16 != nullptr the two links go
+    // into ONE 16-byte record per k-mer together with everything a unitig walk needs from that k-mer (count, Exts,
+    // first and last base), so that every later walk step is a single 16-byte load.
     u64 t_ = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t_ >= n) return;
     const u64 i = v0 + t_;
     Kmer<W> key = load_key<W>(lo, hi, i);
     u32 e = exts[i];
     bool pal = !stranded && is_palindrome<W>(kp, key);
+    u32 both[2];
 #pragma unroll
     for (int d = 0; d < 2; d++) {
         u32 succ = NIL;
@@ -110,9 +114,19 @@ __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __res
                 }
             }
         }
-        nxt[2 * t_ + d] = succ;
+        both[d] = succ;
+    }
+    if (rec16) {
+        u32 meta = (u32)counts[i] | (e << 16) | (Ops<W>::first_base(kp, key) << 24) | (Ops<W>::last_base(kp, key) << 26);
+        rec16[t_] = make_uint4(both[0], both[1], meta, 0u);
+    } else {
+        nxt[2 * t_] = both[0];
+        nxt[2 * t_ + 1] = both[1];
     }
 }
+
+// successor of port state s.  sh = 1: compact array nxt[2v + side]; sh = 2: inside the 16-byte records (u32 view)
+__device__ __forceinline__ u32 nxt_at(const u32* __restrict__ nxt, int sh, u32 s) { return nxt[((u64)(s >> 1) << sh) | (s & 1u)]; }
 
 // ---- S5a: short unitigs by walking from their ends ------------------------------------------------------
 // Every k-mer with exactly one free side is a path end.  Its thread walks to the other end (<= lmax steps),
@@ -121,11 +135,11 @@ __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __res
 // (seed, position, length, orientation) for every k-mer of the unitig.  Paths longer than lmax and cycles
 // are left untouched (nlen stays 0) for the pointer-doubling fallback.
 // vinfo[v] = (seed, position in unitig, unitig length in k-mers [0 = not ranked yet], flags): one 16-byte store
-__global__ void walk_kernel(const u32* __restrict__ nxt, u64 n, u32 lmax, uint4* __restrict__ vinfo, u64* __restrict__ written) {
+__global__ void walk_kernel(const u32* __restrict__ nxt, int sh, u64 n, u32 lmax, uint4* __restrict__ vinfo, u64* __restrict__ written) {
     u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 wrote = 0;
     if (v < n) {
-        u32 a0 = nxt[2 * v], a1 = nxt[2 * v + 1];
+        u32 a0 = nxt_at(nxt, sh, 2u * (u32)v), a1 = nxt_at(nxt, sh, 2u * (u32)v + 1u);
         if (a0 == NIL && a1 == NIL) {
             vinfo[v] = make_uint4((u32)v, 0u, 1u, 1u);
             wrote = 1;
@@ -137,7 +151,7 @@ __global__ void walk_kernel(const u32* __restrict__ nxt, u64 n, u32 lmax, uint4*
                 cur = t;
                 cnt++;
                 if ((t >> 1) < minv) { minv = t >> 1; minst = t; }
-                t = nxt[cur];
+                t = nxt_at(nxt, sh, cur);
             }
             if (t == NIL && (u32)v < (cur >> 1)) {  // complete, and this is the walker from the smaller-index end
                 const bool right = minst & 1u;     // the walk leaves the seed through R: it runs left -> right
@@ -146,7 +160,7 @@ __global__ void walk_kernel(const u32* __restrict__ nxt, u64 n, u32 lmax, uint4*
                     u32 w = cur >> 1, dw = cur & 1u;
                     u32 lp = right ? dw ^ 1u : dw;
                     vinfo[w] = make_uint4(minv, right ? i : cnt - 1 - i, cnt, (lp == 0) | (lp << 1));
-                    cur = nxt[cur];
+                    cur = nxt_at(nxt, sh, cur);
                 }
                 wrote = cnt;
             }
@@ -164,13 +178,13 @@ __global__ void walk_kernel(const u32* __restrict__ nxt, u64 n, u32 lmax, uint4*
 // and hand them to the k-mers inside their segments with one more walk.  Work is O(V), depth ~density + log.
 // rec = (ptr, len, minst, mindist): window of `len` consecutive k-mers starting at reduced state s; minst = the
 // GLOBAL port state in which the smallest-index k-mer of the window is traversed; mindist = k-mers from s to it.
-__global__ void mark_splitters_kernel(const u32* __restrict__ nxt, const uint4* __restrict__ vinfo, u64 n, u32 density_mask,
+__global__ void mark_splitters_kernel(const u32* __restrict__ nxt, int sh, const uint4* __restrict__ vinfo, u64 n, u32 density_mask,
                                       u32* __restrict__ is_spl) {
     u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     u32 f = 0;
     if (vinfo[v].z == 0) {  // not ranked by the walks
-        bool end = nxt[2 * v] == NIL || nxt[2 * v + 1] == NIL;
+        bool end = nxt_at(nxt, sh, 2u * (u32)v) == NIL || nxt_at(nxt, sh, 2u * (u32)v + 1u) == NIL;
         f = end || (((u32)v * 0x9E3779B1u >> 8) & density_mask) == 0;
     }
     is_spl[v] = f;
@@ -180,14 +194,14 @@ __global__ void fill_splitters_kernel(const u32* __restrict__ is_spl, const u64*
     if (v < n && is_spl[v]) spl_vertex[sid[v]] = (u32)v;
 }
 // thread per reduced state (splitter, side): contract the chain up to the next splitter
-__global__ void segment_walk_kernel(const u32* __restrict__ nxt, const u32* __restrict__ is_spl, const u64* __restrict__ sid,
+__global__ void segment_walk_kernel(const u32* __restrict__ nxt, int sh, const u32* __restrict__ is_spl, const u64* __restrict__ sid,
                                     const u32* __restrict__ spl_vertex, u64 n_red, u32 cap, uint4* __restrict__ rec0,
                                     u32* __restrict__ err) {
     u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_red) return;
     u32 v = spl_vertex[r >> 1], d = (u32)r & 1u;
     u32 st = 2u * v + d;
-    u32 cur = nxt[st];
+    u32 cur = nxt_at(nxt, sh, st);
     u32 len = 1, minst = st, mind = 0, steps = 0;
     u32 ptr = NIL;
     while (cur != NIL) {
@@ -195,7 +209,7 @@ __global__ void segment_walk_kernel(const u32* __restrict__ nxt, const u32* __re
         if (is_spl[w]) { ptr = 2u * (u32)sid[w] + (cur & 1u); break; }
         if (w < (minst >> 1)) { minst = cur; mind = len; }
         len++;
-        cur = nxt[cur];
+        cur = nxt_at(nxt, sh, cur);
         if (++steps > cap) { atomicExch(err, 3u); break; }
     }
     rec0[r] = make_uint4(ptr, len, minst, mind);
@@ -315,14 +329,14 @@ __global__ void assign_splitters_kernel(const uint4* __restrict__ rec, const uin
     vinfo[v] = make_uint4(sd, ps, nn, fw | (lp << 1));
 }
 // thread per splitter: walk rightwards (node coordinates) to the next splitter and rank the k-mers in between
-__global__ void segment_assign_kernel(const u32* __restrict__ nxt, const u32* __restrict__ is_spl,
+__global__ void segment_assign_kernel(const u32* __restrict__ nxt, int sh, const u32* __restrict__ is_spl,
                                       const u32* __restrict__ spl_vertex, u64 n_spl, u32 cap, uint4* __restrict__ vinfo) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_spl) return;
     const u32 v = spl_vertex[i];
     const uint4 me = vinfo[v];
     const u32 d = ((me.w >> 1) & 1u) ^ 1u;  // the side facing right
-    u32 cur = nxt[2u * v + d];
+    u32 cur = nxt_at(nxt, sh, 2u * v + d);
     u32 ps = me.y, steps = 0;
     while (cur != NIL) {
         u32 w = cur >> 1;
@@ -330,7 +344,7 @@ __global__ void segment_assign_kernel(const u32* __restrict__ nxt, const u32* __
         ps = ps + 1 == me.z ? 0 : ps + 1;        // wraps on cycles (the seed is the LAST k-mer of its node)
         u32 lp = (cur & 1u) ^ 1u;                // leaving through (cur & 1) = right-facing side
         vinfo[w] = make_uint4(me.x, ps, me.z, (lp == 0) | (lp << 1));
-        cur = nxt[cur];
+        cur = nxt_at(nxt, sh, cur);
         if (++steps > cap) break;
     }
 }
@@ -424,6 +438,173 @@ __global__ void bytes_from_words_kernel(const u32* __restrict__ w, u8* __restric
     if (i < n) out[i] = (u8)(w[i >> 2] >> (8 * (i & 3)));
 }
 
+
+// ================================================================================================
+// Fast path: every component is a path of <= lmax k-mers (sequencing data with errors: all of them).
+//   discover   thread per k-mer; a path END walks the chain of 16-byte records to the other end, tracking
+//              the smallest index (= the seed, compression.rs:574-575) and the port state in which the seed
+//              is traversed.  Exactly one of the two end walkers traverses the seed "leaving through R":
+//              that walk runs left -> right in node coordinates, so its start IS the node's left end; it
+//              appends one path record (seed, length, left-end state).  Nothing is written per k-mer.
+//   sort       path records by seed (node order = ascending seed, compression.rs:574-580); M << V records.
+//   emit_walk  thread per NODE in output order: re-walks its chain from the left end, assembles the 2-bit
+//              bases in registers and writes the node's words / Exts / data / start / length — coalesced
+//              per-node stores instead of per-k-mer atomics into random words.
+// One random 16-byte load per k-mer per walk replaces the ~8 random sectors per k-mer of the per-k-mer
+// rank + emit formulation (which stays as the general path for long unitigs and cycles).
+// ================================================================================================
+__global__ void __launch_bounds__(256) discover_kernel(const uint4* __restrict__ rec, u64 n, u32 lmax, int key_shift, u64* __restrict__ pkey,
+                                u32* __restrict__ pval, u64* __restrict__ counters /* [0] paths, [1] k-mers covered */) {
+    const u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool emit = false;
+    u32 seed = 0, len = 0, left_state = 0;
+    if (v < n) {
+        const uint4 r0 = rec[v];
+        if (r0.x == NIL && r0.y == NIL) {
+            emit = true; seed = (u32)v; len = 1; left_state = 2u * (u32)v + 1u;   // stored orientation: heading right = leaving through R
+        } else if (r0.x == NIL || r0.y == NIL) {
+            const u32 d = r0.x == NIL ? 1u : 0u;   // the linked side: walk inwards through it
+            u32 cur = 2u * (u32)v + d, cnt = 1, minv = (u32)v, minst = cur;
+            u32 t = d ? r0.y : r0.x;
+            while (t != NIL && cnt <= lmax) {
+                cur = t;
+                cnt++;
+                if ((t >> 1) < minv) { minv = t >> 1; minst = t; }
+                const uint4 r = rec[t >> 1];
+                t = (t & 1u) ? r.y : r.x;
+            }
+            if (t == NIL && (minst & 1u)) { emit = true; seed = minv; len = cnt; left_state = 2u * (u32)v + d; }
+        }
+    }
+    // one reservation per CTA (same-address L2 atomics serialise: per-warp reservations would cost more than the walks)
+    __shared__ u32 s_wcnt[8], s_wcov[8];
+    __shared__ u64 s_base;
+    const int warp = threadIdx.x >> 5;
+    const u32 m = __ballot_sync(0xffffffffu, emit);
+    u32 cov = emit ? len : 0;
+    for (int o = 16; o; o >>= 1) cov += __shfl_xor_sync(0xffffffffu, cov, o);
+    if (lane == 0) { s_wcnt[warp] = __popc(m); s_wcov[warp] = cov; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 tc = 0, tv = 0;
+        for (int w = 0; w < 8; w++) { u32 x = s_wcnt[w]; s_wcnt[w] = tc; tc += x; tv += s_wcov[w]; }
+        s_base = tc ? atomicAdd(&counters[0], (u64)tc) : 0;
+        if (tv) atomicAdd(&counters[1], (u64)tv);
+    }
+    __syncthreads();
+    if (emit) {
+        const u64 pos = s_base + s_wcnt[warp] + __popc(m & ((1u << lane) - 1));
+        pkey[pos] = ((u64)seed << key_shift) | len;   // seed in the top bits: the sort looks at those only
+        pval[pos] = left_state;
+    }
+}
+
+__global__ void path_len_kernel(const u64* __restrict__ pkey, u64 m, int key_shift, int K, u64* __restrict__ node_len,
+                                u32* __restrict__ out_length) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    u64 l = (pkey[i] & ((1ull << key_shift) - 1)) + K - 1;
+    node_len[i] = l;
+    out_length[i] = (u32)l;
+}
+
+// Bit-contiguous writer for one node (PackedDnaStringSet::add, dna_string.rs:811-821): words strictly inside the
+// node are plain stores, the first / last word may be shared with the neighbouring nodes -> atomicOr.
+struct NodeWriter {
+    u64* words; u64 first_w, last_w, wi; u64 cur;
+    __device__ __forceinline__ void flush() {
+        if (wi == first_w || wi == last_w) { if (cur) atomicOr(&words[wi], cur); }
+        else words[wi] = cur;
+        cur = 0; wi++;
+    }
+    // append n (1..32) bases given left-aligned in x (bits below the n bases must be zero) at base position pos
+    __device__ __forceinline__ void push(u64 x, int n, u64 pos) {
+        const int off = (int)(pos & 31);
+        cur |= x >> (2 * off);
+        if (off + n >= 32) {
+            flush();
+            if (off) cur = x << (64 - 2 * off);
+        }
+    }
+};
+
+struct EmitWalkArgs {
+    const u64* lo; const u64* hi; const uint4* rec;
+    const u64* pkey; const u32* pval; const u64* node_start; u64 n_nodes; int key_shift;
+    u64* words; u8* out_exts; u16* out_data; int reduce_op;
+};
+
+template <int W>
+__global__ void emit_walk_kernel(KP kp, EmitWalkArgs a) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_nodes) return;
+    const int K = kp.k;
+    const u32 len = (u32)(a.pkey[i] & ((1ull << a.key_shift) - 1));
+    u32 cur = a.pval[i];             // at the left end, leaving through its right-facing side
+    const u64 st = a.node_start[i];
+    const u64 L = (u64)len + K - 1;
+    NodeWriter nw;
+    nw.words = a.words; nw.first_w = st >> 5; nw.last_w = (st + L - 1) >> 5; nw.wi = nw.first_w; nw.cur = 0;
+    u64 pos = st;
+    u64 acc = 0;
+    u32 eb = 0;
+    {   // first k-mer: all K bases (compression.rs:489-495)
+        const u32 w = cur >> 1, dw = cur & 1u;
+        const bool fw = dw == 1u;    // leaving through R while heading right = stored orientation
+        Kmer<W> key = load_key<W>(a.lo, a.hi, w);
+        if (!fw) key = Ops<W>::rc(kp, key);
+        if constexpr (W == 1) {
+            nw.push(key.lo << (64 - 2 * K), K, pos);
+        } else {
+            const int sh = 128 - 2 * K;   // 0..62
+            const u64 H = sh ? (key.hi << sh) | (key.lo >> (64 - sh)) : key.hi;
+            nw.push(H, 32, pos);
+            nw.push(key.lo << sh, K - 32, pos + 32);
+        }
+        pos += K;
+        const uint4 r = a.rec[w];
+        const u32 e = (r.z >> 16) & 0xffu;
+        u32 nib = exts_side(e, (int)(dw ^ 1u));          // left-facing side of the first k-mer (:513-517)
+        if (!fw) nib = exts_complement(nib) & 0xfu;
+        eb = nib;
+        if (len == 1) {
+            u32 rn = exts_side(e, (int)dw);
+            if (!fw) rn = exts_complement(rn) & 0xfu;
+            eb |= rn << 4;
+        }
+        acc = r.z & 0xffffu;
+        cur = dw ? r.y : r.x;
+    }
+    for (u32 j = 1; j < len; j++) {
+        const u32 w = cur >> 1, dw = cur & 1u;
+        const bool fw = dw == 1u;
+        const uint4 r = a.rec[w];
+        const u32 fb = (r.z >> 24) & 3u, lb = (r.z >> 26) & 3u;
+        const u64 b = fw ? lb : 3u - fb;                 // last base of the k-mer as it appears in the node
+        nw.push(b << 62, 1, pos);
+        pos++;
+        const u64 cnt = r.z & 0xffffu;
+        if (a.reduce_op == DBG_REDUCE_MAX) acc = cnt > acc ? cnt : acc; else acc += cnt;
+        if (j == len - 1) {
+            u32 rn = exts_side((r.z >> 16) & 0xffu, (int)dw);   // right-facing side of the last k-mer (:534-540)
+            if (!fw) rn = exts_complement(rn) & 0xfu;
+            eb |= rn << 4;
+        }
+        cur = dw ? r.y : r.x;
+    }
+    if (pos & 31) nw.flush();   // partial last word
+    a.out_exts[i] = (u8)eb;
+    u16 d;
+    switch (a.reduce_op) {
+        case DBG_REDUCE_SAT_ADD: d = (u16)(acc > 65535 ? 65535 : acc); break;
+        case DBG_REDUCE_WRAP_ADD: d = (u16)(acc & 0xffff); break;
+        case DBG_REDUCE_ADD_MOD_65535: d = len == 1 ? (u16)acc : (u16)(acc % 65535); break;   // one k-mer: reduce() never called (:495)
+        default: d = (u16)acc; break;
+    }
+    a.out_data[i] = d;
+}
+
 template <int W>
 static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Graph** out) {
     cudaStream_t st = c->stream;
@@ -453,17 +634,70 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     TRY(check_launch(c, "lut_hist"));
     TRY(exclusive_scan_u32_to_u64(c, lut_cnt.p, lut.p, n_pfx, lut.p + n_pfx));
     CU(c, cudaEventRecord(c->ev[1], st));
-    // ---- S4 ----
-    const u64 NS = 2 * V;
-    DBuf<u32> nxt;
+    // ---- S4: links + per-k-mer walk record (16 bytes: both links, count, Exts, first / last base) ----
+    DBuf<uint4> rec16;
     DBuf<u64> ctr;
-    TRY(nxt.alloc(c, NS));
+    TRY(rec16.alloc(c, V));
     TRY(ctr.alloc(c, 4));
     TRY(ctr.zero());
-    links_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, 0, V, lut.p, lut_shift, stranded, nxt.p,
-                                                      (u32*)(ctr.p + 3));
+    links_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, 0, V, lut.p, lut_shift, stranded, nullptr,
+                                                      (u32*)(ctr.p + 3), rec16.p, t->counts);
     TRY(check_launch(c, "links"));
     CU(c, cudaEventRecord(c->ev[2], st));
+    const u32* nxt_p = reinterpret_cast<const u32*>(rec16.p);   // general path: links read in place (stride 4 words)
+    const int nsh = 2;
+    // ---- fast path: all components are short paths -> path records, sorted by seed, one walker per node ----
+    {
+        int bits_v = 1;
+        while ((1ull << bits_v) < V) bits_v++;
+        const int key_shift = 64 - bits_v;
+        const u32 lmax = 1024u;
+        DBuf<u64> pk_a, pk_b;
+        DBuf<u32> pv_a, pv_b;
+        TRY(pk_a.alloc(c, V)); TRY(pv_a.alloc(c, V));
+        discover_kernel<<<grid_for(V, 256), 256, 0, st>>>(rec16.p, V, lmax, key_shift, pk_a.p, pv_a.p, ctr.p);
+        TRY(check_launch(c, "discover"));
+        u64 h[4];
+        TRY(read_u64(c, ctr.p, h, 4));
+        if (h[3] == 1) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extension points at a k-mer with no extension back (src/compression.rs:428-434)");
+        if (h[3] == 2) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extensions are not reciprocal");
+        if (h[1] == V && !c->no_fast_compress) {
+            const u64 M = h[0], Lb = V + M * (u64)(t->k - 1);   // every k-mer adds one base, every node K-1 more
+            TRY(pk_b.alloc(c, M)); TRY(pv_b.alloc(c, M));
+            u64 *rk, *rh;
+            u32* rv;
+            TRY(radix_sort_pairs(c, 1, 64, M, pk_a.p, nullptr, pv_a.p, pk_b.p, nullptr, pv_b.p, &rk, &rh, &rv));
+            g->n_nodes = M; g->n_bases = Lb; g->n_words = (Lb + 31) / 32;
+            S.n_nodes = M; S.n_bases = Lb;
+            DBuf<u64> words, ostart, node_len;
+            DBuf<u32> olen;
+            DBuf<u8> oexts;
+            DBuf<u16> odata;
+            TRY(words.alloc_pool(c, g->n_words + 3)); TRY(words.zero());
+            TRY(ostart.alloc_pool(c, M)); TRY(olen.alloc_pool(c, M)); TRY(oexts.alloc_pool(c, M)); TRY(odata.alloc_pool(c, M));
+            TRY(node_len.alloc(c, M));
+            path_len_kernel<<<grid_for(M, 256), 256, 0, st>>>(rk, M, key_shift, t->k, node_len.p, olen.p);
+            TRY(check_launch(c, "path_len"));
+            TRY(exclusive_scan_u64(c, node_len.p, ostart.p, M, nullptr));
+            CU(c, cudaEventRecord(c->ev[3], st));
+            EmitWalkArgs ea;
+            ea.lo = t->lo; ea.hi = t->hi; ea.rec = rec16.p; ea.pkey = rk; ea.pval = rv; ea.node_start = ostart.p; ea.n_nodes = M;
+            ea.key_shift = key_shift; ea.words = words.p; ea.out_exts = oexts.p; ea.out_data = odata.p; ea.reduce_op = reduce_op;
+            emit_walk_kernel<W><<<grid_for(M, 128), 128, 0, st>>>(kp, ea);
+            TRY(check_launch(c, "emit_walk"));
+            CU(c, cudaEventRecord(c->ev[4], st));
+            TRY(sync(c));
+            g->words = words.take(); g->start = ostart.take(); g->length = olen.take(); g->exts = oexts.take(); g->data = odata.take();
+            cudaEventElapsedTime(&S.ms_table, c->ev[0], c->ev[1]);
+            cudaEventElapsedTime(&S.ms_links, c->ev[1], c->ev[2]);
+            cudaEventElapsedTime(&S.ms_rank, c->ev[2], c->ev[3]);
+            cudaEventElapsedTime(&S.ms_emit, c->ev[3], c->ev[4]);
+            cudaEventElapsedTime(&S.ms_compress_total, c->ev[0], c->ev[4]);
+            S.gpu_launches = c->launches;
+            return DBG_OK;
+        }
+        CU(c, cudaMemsetAsync(ctr.p, 0, 24, st));   // general path below reuses counters [0..2]
+    }
     // ---- S5a: walks for short unitigs ----
     DBuf<uint4> vinfo;
     DBuf<u32> is_seed;
@@ -471,7 +705,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     TRY(vinfo.alloc(c, V)); TRY(is_seed.alloc(c, V));
     TRY(node_len.alloc(c, V)); TRY(node_id.alloc(c, V)); TRY(tot.alloc(c, 2));
     TRY(vinfo.zero());
-    walk_kernel<<<grid_for(V, 256), 256, 0, st>>>(nxt.p, V, 1024u, vinfo.p, ctr.p + 2);
+    walk_kernel<<<grid_for(V, 256), 256, 0, st>>>(nxt_p, nsh, V, 1024u, vinfo.p, ctr.p + 2);
     TRY(check_launch(c, "walk"));
     {
         u64 h[4];
@@ -489,7 +723,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
             DBuf<u32> is_spl, spl_vertex;
             DBuf<u64> sid, nsp;
             TRY(is_spl.alloc(c, V)); TRY(sid.alloc(c, V)); TRY(nsp.alloc(c, 1));
-            mark_splitters_kernel<<<grid_for(V, 256), 256, 0, st>>>(nxt.p, vinfo.p, V, density_mask, is_spl.p);
+            mark_splitters_kernel<<<grid_for(V, 256), 256, 0, st>>>(nxt_p, nsh, vinfo.p, V, density_mask, is_spl.p);
             TRY(check_launch(c, "mark_splitters"));
             TRY(exclusive_scan_u32_to_u64(c, is_spl.p, sid.p, V, nsp.p));
             u64 NSPL = 0;
@@ -501,7 +735,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
             TRY(check_launch(c, "fill_splitters"));
             DBuf<uint4> rec0, recA, recB;
             TRY(rec0.alloc(c, NR)); TRY(recA.alloc(c, NR)); TRY(recB.alloc(c, NR));
-            segment_walk_kernel<<<grid_for(NR, 256), 256, 0, st>>>(nxt.p, is_spl.p, sid.p, spl_vertex.p, NR, cap, rec0.p, (u32*)(ctr.p + 3));
+            segment_walk_kernel<<<grid_for(NR, 256), 256, 0, st>>>(nxt_p, nsh, is_spl.p, sid.p, spl_vertex.p, NR, cap, rec0.p, (u32*)(ctr.p + 3));
             TRY(check_launch(c, "segment_walk"));
             CU(c, cudaMemcpyAsync(recA.p, rec0.p, NR * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
             uint4 *src = recA.p, *dst = recB.p;
@@ -545,7 +779,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
             CU(c, cudaMemsetAsync(ctr.p + 1, 0, 8, st));
             assign_splitters_kernel<<<grid_for(NSPL, 256), 256, 0, st>>>(src, rec0.p, is_cyc.p, spl_vertex.p, NSPL, vinfo.p, ctr.p + 1);
             TRY(check_launch(c, "assign_splitters"));
-            segment_assign_kernel<<<grid_for(NSPL, 256), 256, 0, st>>>(nxt.p, is_spl.p, spl_vertex.p, NSPL, cap, vinfo.p);
+            segment_assign_kernel<<<grid_for(NSPL, 256), 256, 0, st>>>(nxt_p, nsh, is_spl.p, spl_vertex.p, NSPL, cap, vinfo.p);
             TRY(check_launch(c, "segment_assign"));
             // how many k-mers are ranked now?
             CU(c, cudaMemsetAsync(ctr.p + 2, 0, 8, st));
@@ -760,7 +994,7 @@ static int cs_links_impl(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u
     TRY(exclusive_scan_u32_to_u64(c, lut_cnt.p, lut.p, n_pfx, lut.p + n_pfx));
     if (v1 > v0) {
         links_kernel<W><<<grid_for(v1 - v0, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, v0, v1 - v0, lut.p, lut_shift, stranded,
-                                                                d_nxt_out, (u32*)(ctr.p + 3));
+                                                                d_nxt_out, (u32*)(ctr.p + 3), nullptr, nullptr);
         TRY(check_launch(c, "links"));
     }
     u64 h[4];

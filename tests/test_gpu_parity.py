@@ -247,6 +247,30 @@ def test_valid_buffer_retry(D, ctx, orc):
     c2.close()
 
 
+def test_general_compress_path_forced(D, ctx, orc):
+    """compress_kmers has a fast path (all components are short paths: one walker per node) and a general path
+    (per-k-mer rank + emit; long unitigs, cycles).  Same bits when the general path is forced on data the fast
+    path would take, for every reduce op and both key widths."""
+    c2 = D.Context(0)
+    c2.set_param("fast_compress", 0)
+    ss = orc.synth_reads(3000, 1, orc.ERR_THR_NOISY)
+    for op in (0, 1, 2, 3):
+        run_both(D, c2, orc, 31, ss, 2, reduce_op=op)
+    run_both(D, c2, orc, 63, ss, 2)
+    run_both(D, c2, orc, 32, ss, 2, stranded=True)
+    c2.close()
+
+
+def test_fast_compress_node_word_boundaries(D, ctx, orc):
+    """The per-node writer of the fast path: nodes of every length 1..70 k-mers (K = 31, 33, 64) packed back to
+    back, so first / last words are shared between neighbours at every bit offset."""
+    rng = np.random.default_rng(77)
+    for k in (31, 33, 64, 5):
+        seqs = [random_dna(rng, k + n) for n in range(0, 70)]
+        run_both(D, ctx, orc, k, orc.seqset_from_lists(seqs), 1)
+        run_both(D, ctx, orc, k, orc.seqset_from_lists(seqs), 1, stranded=True, reduce_op=3)
+
+
 def test_record_dedup_off(D, ctx, orc):
     """The per-bucket super-k-mer deduplication is an optimisation only: same bits with it switched off."""
     c2 = D.Context(0)
