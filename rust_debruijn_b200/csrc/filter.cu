@@ -508,12 +508,18 @@ __global__ void scatter_records_kernel(const u64* __restrict__ rec, const u32* _
 static const int P2_THREADS = 512;
 static const int MAX_PROBE = 96;
 static const int SPLIT_STACK = 64;
-static const int P2_RC = 2048;   // records per chunk (prefix sums in smem)
-static const int P2_SEG = 8;     // consecutive k-mers per thread
 
 template <int W> struct P2Cfg;
-template <> struct P2Cfg<1> { static const int CAP = 8192; static const int THREADS = 512; static const int CTAS = 2; };   // 8 B key + 4 B val = 96 KB, 2 CTA/SM
-template <> struct P2Cfg<2> { static const int CAP = 8192; static const int THREADS = 1024; static const int CTAS = 1; };  // 16 B key + 4 B val = 160 KB, 1 CTA/SM
+#ifndef P2_CAP1
+#define P2_CAP1 8192
+#define P2_THR1 512
+#define P2_CTA1 2
+#define P2_RC1 1024
+#endif
+// K <= 32: 8 B key + 4 B val = 96 KB tables, 2 CTAs/SM of 512 threads (4 x 256 threads with 48 KB tables measured 5% slower:
+// more bucket splits).  RC = records per chunk.
+template <> struct P2Cfg<1> { static const int CAP = P2_CAP1; static const int THREADS = P2_THR1; static const int CTAS = P2_CTA1; static const int RC = P2_RC1; };
+template <> struct P2Cfg<2> { static const int CAP = 8192; static const int THREADS = 1024; static const int CTAS = 1; static const int RC = 1024; };  // 16 B key + 4 B val = 160 KB, 1 CTA/SM
 
 struct P2Args {
     u64* rec; u32* mult;  // records (deduplicated in place per bucket when mult != nullptr) and their multiplicities
@@ -521,6 +527,7 @@ struct P2Args {
     u32* dedup_cnt;       // per bucket: records left after deduplication
     const u64* bucket_off; u32 n_buckets;
     u32 min_obs; int stranded; int report_all;
+    int task_len;         // k-mers per task of the expansion loop (8, or 16 when records hold more than 32 k-mers)
     u64* out_lo; u64* out_hi; u32* out_val; u64 cap_valid;
     u64* all_lo; u64* all_hi; u64 cap_all;
     u64* counters;  // [0] queue, [1] n_valid, [2] n_all(distinct), [3] splits, [4] error
@@ -577,12 +584,15 @@ template <int W>
 __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kernel(KP kp, P2Args a) {
     constexpr int CAP = P2Cfg<W>::CAP;
     constexpr int P2T = P2Cfg<W>::THREADS;
+    constexpr int P2_RC = P2Cfg<W>::RC;
     constexpr int RW = RecLayout<W>::WORDS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Kmer<W>* keys = reinterpret_cast<Kmer<W>*>(smem_raw);
     u32* vals = reinterpret_cast<u32*>(smem_raw + sizeof(Kmer<W>) * CAP);
     __shared__ u64 s_scan[33];
-    __shared__ u32 s_pref[P2_RC + 1];
+    __shared__ u16 s_task[P2_RC * 4];     // (record in chunk) | (task in record << 10), sorted by task length
+    __shared__ u32 s_cls[17];             // per task length: counter / cursor; [0] = number of tasks
+    __shared__ u32 s_ptot, s_next, s_wr_ok;
     __shared__ u32 s_wsum[32];
     __shared__ u32 s_bucket, s_overflow, s_sp_cnt, s_sp_exts, s_nstack;
     __shared__ u64 s_base_valid, s_base_all;
@@ -591,6 +601,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
     const int K = kp.k;
     const int nxt_word = K >> 5;               // word of the shift register holding base K
     const int nxt_shift = 62 - 2 * (K & 31);   // its bit position there
+    const int tl = a.task_len;
 
     for (;;) {
         __syncthreads();
@@ -605,6 +616,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
         const u64 r0 = a.bucket_off[b];
         u64 r1 = a.bucket_off[b + 1];
         if (r0 == r1) continue;
+        const bool small_bucket = (r1 - r0) * 63ull < (1ull << 24);   // no count can overflow the 24-bit field
         if constexpr (W == 1) {
             if (a.mult && a.mult_ready) {
                 r1 = r0 + a.dedup_cnt[b];
@@ -614,7 +626,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                 // its k-mers are counted with the record's multiplicity.  The 16-byte records are hashed into a
                 // table that borrows the (not yet used) k-mer table memory; distinct records are written back
                 // over the front of the bucket's own range (never ahead of what has been read). ----
-                constexpr int RCAP = 4096;
+                constexpr int RCAP = CAP / 2;   // 20 B per entry inside the 12 B x CAP table memory
                 Kmer<2>* rkeys = reinterpret_cast<Kmer<2>*>(smem_raw);
                 u32* rcnt = reinterpret_cast<u32*>(smem_raw + sizeof(Kmer<2>) * RCAP);
                 u64 dbase = 0;
@@ -657,7 +669,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
 #pragma unroll
                             for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
                             s_wsum[lane] = winc - w;
-                            if (lane == 31) s_pref[P2_RC] = winc;
+                            if (lane == 31) s_ptot = winc;
                         }
                         __syncthreads();
                         u64 o = r0 + dbase + s_wsum[warp] + inc - mine;
@@ -671,7 +683,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                                 o++;
                             }
                         }
-                        dbase += s_pref[P2_RC];
+                        dbase += s_ptot;
                     }
                     __syncthreads();
                 }
@@ -757,7 +769,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
 #pragma unroll
                             for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
                             s_wsum[lane] = winc - ww;
-                            if (lane == 31) s_pref[P2_RC] = winc;
+                            if (lane == 31) s_ptot = winc;
                         }
                         __syncthreads();   // every record of the chunk is in registers / smem by now: in-place writes are safe
                         u64 o = r0 + dbase + s_wsum[warp] + inc - mine;
@@ -782,7 +794,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                                 }
                             }
                         }
-                        dbase += s_pref[P2_RC];
+                        dbase += s_ptot;
                     }
                     __syncthreads();
                 }
@@ -805,75 +817,79 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
             }
             if (threadIdx.x == 0) { s_overflow = 0; s_sp_cnt = 0; s_sp_exts = 0; s_nstack--; }
             __syncthreads();
-            // ---- expand records, insert.  The bucket is processed in chunks of RC records; inside a chunk the
-            // k-mers are numbered consecutively (prefix sum of the per-record counts in smem) and every thread
-            // rolls a segment of SEG consecutive k-mers, crossing record boundaries as needed, so all lanes of a
-            // warp do the same amount of work whatever the record lengths are. ----
+            // ---- expand records, insert.  The bucket is processed in chunks of RC records.  Every record is cut into
+            // TASKS of <= tl consecutive k-mers and the chunk's tasks are counting-sorted by length (descending) in
+            // shared memory, so the 32 lanes of a warp roll tasks of (almost always) the same length: one uniform
+            // loop with no record switching inside it, whatever the record lengths are. ----
             for (u64 c0 = r0; c0 < r1; c0 += P2_RC) {
                 const u32 nrc = (u32)min((u64)P2_RC, r1 - c0);
-                {   // prefix sums of k-mers per record
-                    u32 cnt[P2_RC / P2T];
-                    u32 sum = 0;
+                const int lane = threadIdx.x & 31;
+                if (threadIdx.x <= 16) s_cls[threadIdx.x] = 0;
+                __syncthreads();
+                u32 myn[P2_RC / P2T];
 #pragma unroll
-                    for (int j = 0; j < P2_RC / P2T; j++) {
-                        u32 idx = threadIdx.x * (P2_RC / P2T) + j;
-                        cnt[j] = idx < nrc ? ((u32)__ldcg(a.rec + (c0 + idx) * RW + (RW - 1)) >> 8) & 63u : 0;
-                        sum += cnt[j];
-                    }
-                    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-                    u32 inc = sum;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                    if (lane == 31) s_wsum[warp] = inc;
-                    __syncthreads();
-                    if (warp == 0) {
-                        u32 w = lane < P2T / 32 ? s_wsum[lane] : 0, winc = w;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
-                        s_wsum[lane] = winc - w;
-                        if (lane == 31) s_pref[P2_RC] = winc;
-                    }
-                    __syncthreads();
-                    u32 ex = s_wsum[warp] + inc - sum;
-#pragma unroll
-                    for (int j = 0; j < P2_RC / P2T; j++) {
-                        s_pref[threadIdx.x * (P2_RC / P2T) + j] = ex;
-                        ex += cnt[j];
-                    }
-                    __syncthreads();
+                for (int j = 0; j < P2_RC / P2T; j++) {   // class sizes
+                    const u32 idx = j * P2T + threadIdx.x;
+                    const u32 n = idx < nrc ? ((u32)__ldcg(a.rec + (c0 + idx) * RW + (RW - 1)) >> 8) & 63u : 0;
+                    myn[j] = n;
+                    const u32 full = n / tl, rem = n - full * tl;
+                    const u32 fsum = __reduce_add_sync(0xffffffffu, full);
+                    if (lane == 0 && fsum) atomicAdd(&s_cls[tl], fsum);
+                    if (rem) atomicAdd(&s_cls[rem], 1u);
                 }
-                const u32 T = s_pref[P2_RC];
-                // segment length: as few rounds as possible with every thread busy (>= P2_SEG to amortise the search)
-                const u32 rounds = (T + P2T * 16 - 1) / (P2T * 16);
-                const u32 seg = max((u32)P2_SEG, (T + rounds * P2T - 1) / (rounds * P2T));
-                for (u32 k0 = threadIdx.x * seg; k0 < T; k0 += P2T * seg) {
-                    if (*reinterpret_cast<volatile u32*>(&s_overflow)) break;
-                    const u32 k1 = min(T, k0 + seg);
-                    // record holding k-mer k0: largest i with pref[i] <= k0
-                    u32 lo = 0, hi = nrc - 1;
-                    while (lo < hi) { u32 m = (lo + hi + 1) >> 1; if (s_pref[m] <= k0) lo = m; else hi = m - 1; }
-                    u32 ri = lo;
-                    int t = (int)(k0 - s_pref[ri]);
-                    // current record (shifted so that k-mer t is at the front) and the prefetched next one
-                    u64 s[RW], nx[RW];
+                __syncthreads();
+                if (threadIdx.x == 0) {   // class starts, longest tasks first
+                    u32 acc = 0;
+                    for (int l = tl; l >= 1; l--) { u32 c = s_cls[l]; s_cls[l] = acc; acc += c; }
+                    s_cls[0] = acc;
+                    s_next = 0;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < P2_RC / P2T; j++) {   // scatter (record, first k-mer) into the class ranges
+                    const u32 idx = j * P2T + threadIdx.x;
+                    const u32 n = myn[j];
+                    for (u32 jt = 0; jt < 4; jt++) {
+                        const u32 t0 = jt * tl;
+                        const bool has = t0 < n;
+                        if (!__any_sync(0xffffffffu, has)) break;
+                        const u32 len = has ? min((u32)tl, n - t0) : 0;
+                        const bool isfull = len == (u32)tl;
+                        const u32 fm = __ballot_sync(0xffffffffu, isfull);
+                        u32 base = 0;
+                        if (fm && lane == __ffs(fm) - 1) base = atomicAdd(&s_cls[tl], (u32)__popc(fm));
+                        if (fm) base = __shfl_sync(0xffffffffu, base, __ffs(fm) - 1);
+                        u32 pos = base + __popc(fm & ((1u << lane) - 1));
+                        if (has && !isfull) pos = atomicAdd(&s_cls[len], 1u);
+                        if (has) s_task[pos] = (u16)(idx | (jt << 10));
+                    }
+                }
+                __syncthreads();
+                const u32 NT = s_cls[0];
+                // every lane takes its next task from a shared cursor, longest tasks first (LPT): lanes of a warp hold
+                // tasks of (almost) equal length, and no warp waits at the barrier below for longer than one short task.
+                // Per-lane claims on purpose: no warp-level primitive inside this loop, so lanes may drift freely.
+                for (;;) {
+                    const u32 q = atomicAdd(&s_next, 1u);
+                    if (q >= NT || *reinterpret_cast<volatile u32*>(&s_overflow)) break;
+                    {
+                    const u32 task = s_task[q];
+                    const u32 ri = task & 1023u;
+                    int t = (int)((task >> 10) * tl);
+                    u64 s[RW];
                     {
                         const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.rec + (c0 + ri) * RW);
                         ulonglong2 v0 = __ldcg(src);   // L2 path: records may have been rewritten by this CTA (dedup)
                         s[0] = v0.x; s[1] = v0.y;
                         if constexpr (RW == 4) { ulonglong2 v1 = __ldcg(src + 1); s[2] = v1.x; s[RW - 1] = v1.y; }
-                        const u64 rnx = min(c0 + ri + 1, r1 - 1);
-                        const ulonglong2* srn = reinterpret_cast<const ulonglong2*>(a.rec + rnx * RW);
-                        ulonglong2 n0 = __ldcg(srn);
-                        nx[0] = n0.x; nx[1] = n0.y;
-                        if constexpr (RW == 4) { ulonglong2 n1 = __ldcg(srn + 1); nx[2] = n1.x; nx[RW - 1] = n1.y; }
                     }
-                    u32 mcur = a.mult ? __ldcg(a.mult + c0 + ri) : 1u;
-                    u32 mnx = a.mult ? __ldcg(a.mult + min(c0 + ri + 1, r1 - 1)) : 1u;
-                    u32 hdr = (u32)s[RW - 1] & 0x3fffu;
-                    int n = (int)(hdr >> 8);
-                    u32 rn = (hdr >> 4) & 0xfu, ln = hdr & 0xfu;
+                    const u32 mcur = a.mult ? __ldcg(a.mult + c0 + ri) : 1u;
+                    const u32 hdr = (u32)s[RW - 1] & 0x3fffu;
+                    const int n = (int)(hdr >> 8);
+                    const int tend = min(n, t + tl);
+                    const u32 rn = (hdr >> 4) & 0xfu, ln = hdr & 0xfu;
                     u32 prev_first = 0;
-                    if (t > 0) {  // start inside the record: drop t bases from the front (static register indices only)
+                    if (t > 0) {  // task starts inside the record: drop t bases from the front (static register indices only)
                         const int pb = t - 1, pw = pb >> 5;
                         u64 wsel = s[0];
                         if (pw == 1) wsel = s[1];
@@ -888,7 +904,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                         }
                         if (bs) {
 #pragma unroll
-                            for (int q = 0; q < RW - 1; q++) s[q] = (s[q] << bs) | (s[q + 1] >> (64 - bs));
+                            for (int q2 = 0; q2 < RW - 1; q2++) s[q2] = (s[q2] << bs) | (s[q2 + 1] >> (64 - bs));
                             s[RW - 1] <<= bs;
                         }
                     }
@@ -901,18 +917,16 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                         fwd.lo = sh ? ((s[1] >> sh) | (s[0] << (64 - sh))) : s[1];
                     }
                     Kmer<W> rcv = Ops<W>::rc(kp, fwd);
-                    // one uniform loop: every lane handles one k-mer per iteration; switching to the next record is a
-                    // short predicated block (registers only, the following record is prefetched)
-                    for (u32 k = k0; k < k1; k++) {
+                    for (; t < tend; t++) {
                         u32 nb;  // base t+K (only meaningful when t < n-1)
                         if constexpr (W == 1) nb = (u32)((nxt_word ? s[1] : s[0]) >> nxt_shift) & 3u;
                         else nb = (u32)((nxt_word == 2 ? s[2] : s[1]) >> nxt_shift) & 3u;
-                        u32 left = t == 0 ? ln : (1u << prev_first);
-                        u32 right = t == n - 1 ? rn : (1u << nb);
+                        const u32 left = t == 0 ? ln : (1u << prev_first);
+                        const u32 right = t == n - 1 ? rn : (1u << nb);
                         u32 e = left | (right << 4);
                         Kmer<W> key = fwd;
                         if (!a.stranded && !(fwd < rcv)) { key = rcv; e = exts_rc(e); }  // lib.rs:224-231, filter.rs:190-196
-                        u32 h = Ops<W>::hash32(key);
+                        const u32 h = Ops<W>::hash32(key);
                         if ((h & cmask) == cres) {
                             bool special;
                             if constexpr (W == 1) special = key.lo == ~0ull;
@@ -921,53 +935,34 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                                 atomicAdd(&s_sp_cnt, mcur);
                                 atomicOr(&s_sp_exts, e);
                             } else {
-                                int slot = tab.find_or_insert(key, h, CAP);
+                                const int slot = tab.find_or_insert(key, h, CAP);
                                 if (slot < 0) { s_overflow = 1; break; }
                                 u32 v = *reinterpret_cast<volatile u32*>(vals + slot);
                                 if (e & ~v) atomicOr(vals + slot, e);
-                                // saturating count (filter.rs:57): stop adding once 65535 is reached; steps of <= 255
-                                // keep the transient overshoot far below the 24-bit field
-                                for (u32 rem = mcur;;) {
-                                    u32 stp = min(rem, 255u);
-                                    if ((v >> 8) < 65535u) atomicAdd(vals + slot, stp << 8);
-                                    rem -= stp;
-                                    if (!rem) break;
-                                    v = *reinterpret_cast<volatile u32*>(vals + slot);
+                                if (small_bucket) {
+                                    // the bucket's total occurrences fit the 24-bit field: plain add, clamped at emission
+                                    atomicAdd(vals + slot, mcur << 8);
+                                } else {
+                                    // saturating count (filter.rs:57): stop adding once 65535 is reached; steps of <= 255
+                                    // keep the transient overshoot far below the 24-bit field
+                                    for (u32 rem = mcur;;) {
+                                        u32 stp = min(rem, 255u);
+                                        if ((v >> 8) < 65535u) atomicAdd(vals + slot, stp << 8);
+                                        rem -= stp;
+                                        if (!rem) break;
+                                        v = *reinterpret_cast<volatile u32*>(vals + slot);
+                                    }
                                 }
                             }
                         }
-                        t++;
-                        if (t < n) {  // roll to the next k-mer of this record
-                            prev_first = (u32)(s[0] >> 62);
-                            fwd = Ops<W>::ext_right(kp, fwd, nb);
-                            rcv = Ops<W>::roll_rc(kp, rcv, nb);
+                        // roll to the next k-mer of this record
+                        prev_first = (u32)(s[0] >> 62);
+                        fwd = Ops<W>::ext_right(kp, fwd, nb);
+                        rcv = Ops<W>::roll_rc(kp, rcv, nb);
 #pragma unroll
-                            for (int q = 0; q < RW - 1; q++) s[q] = (s[q] << 2) | (s[q + 1] >> 62);
-                            s[RW - 1] <<= 2;
-                        } else {      // next record
-                            ri++;
-                            t = 0;
-                            mcur = mnx;
-                            mnx = a.mult ? __ldcg(a.mult + min(c0 + ri + 1, r1 - 1)) : 1u;
-#pragma unroll
-                            for (int q = 0; q < RW; q++) s[q] = nx[q];
-                            hdr = (u32)s[RW - 1] & 0x3fffu;
-                            n = (int)(hdr >> 8);
-                            rn = (hdr >> 4) & 0xfu; ln = hdr & 0xfu;
-                            if constexpr (W == 1) {
-                                fwd.lo = s[0] >> (64 - 2 * K);
-                            } else {
-                                const int sh = 128 - 2 * K;
-                                fwd.hi = sh ? (s[0] >> sh) : s[0];
-                                fwd.lo = sh ? ((s[1] >> sh) | (s[0] << (64 - sh))) : s[1];
-                            }
-                            rcv = Ops<W>::rc(kp, fwd);
-                            const u64 rnx = min(c0 + ri + 1, r1 - 1);
-                            const ulonglong2* srn = reinterpret_cast<const ulonglong2*>(a.rec + rnx * RW);
-                            ulonglong2 n0 = __ldcg(srn);
-                            nx[0] = n0.x; nx[1] = n0.y;
-                            if constexpr (RW == 4) { ulonglong2 n1 = __ldcg(srn + 1); nx[2] = n1.x; nx[RW - 1] = n1.y; }
-                        }
+                        for (int q2 = 0; q2 < RW - 1; q2++) s[q2] = (s[q2] << 2) | (s[q2 + 1] >> 62);
+                        s[RW - 1] <<= 2;
+                    }
                     }
                 }
                 __syncthreads();
@@ -1035,10 +1030,12 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                 u32 tv = (u32)tot, ta = (u32)(tot >> 32);
                 s_base_valid = tv ? atomicAdd(&a.counters[1], (u64)tv) : 0;
                 s_base_all = atomicAdd(&a.counters[2], (u64)ta);
-                if (s_base_valid + tv > a.cap_valid || (a.report_all && s_base_all + ta > a.cap_all)) a.counters[4] = 2;
+                const bool over = s_base_valid + tv > a.cap_valid || (a.report_all && s_base_all + ta > a.cap_all);
+                if (over) a.counters[4] = 2;
+                s_wr_ok = over ? 0u : 1u;
             }
             __syncthreads();
-            if (a.counters[4] == 0) {
+            if (s_wr_ok) {
                 u64 pv = s_base_valid + (u32)ex, pa = s_base_all + (u32)(ex >> 32);
                 for (int i = threadIdx.x; i < CAP; i += P2T) {
                     u64 klo = W == 1 ? reinterpret_cast<u64*>(keys)[i] : reinterpret_cast<u64*>(keys)[2 * i];
@@ -1125,7 +1122,7 @@ void plan_filter(const Ctx* c, int k, u64 N, int* p_out, int* bbits_out) {
     if (!target) {
         // k-mer occurrences per bucket such that the bucket's DISTINCT k-mers fit the shared-memory table
         // (8192 slots for one-word keys, 4096 for two-word keys; longer k-mers are also more often distinct)
-        const u64 tmax = W == 1 ? 16384 : 4096;
+        const u64 tmax = W == 1 ? 2 * (u64)P2Cfg<1>::CAP : 4096;
         target = N / ((u64)c->sm_count * 8);
         if (target < tmax / 8) target = tmax / 8;
         if (target > tmax) target = tmax;
@@ -1317,6 +1314,7 @@ static int count_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucket_off
     a.rec = rec; a.mult = dedup ? mult.p : nullptr; a.mult_ready = 0; a.dedup_cnt = dedup_cnt.p;
     a.bucket_off = bucket_off; a.n_buckets = NB;
     a.min_obs = min_obs; a.stranded = stranded; a.report_all = report_all;
+    a.task_len = rec_max_kmers(RecLayout<W>::WORDS, k) <= 32 ? 8 : 16;
     a.out_lo = co.v_lo.p; a.out_hi = co.v_hi.p; a.out_val = co.v_val.p; a.cap_valid = co.cap_valid;
     a.all_lo = co.a_lo.p; a.all_hi = co.a_hi.p; a.cap_all = co.cap_all;
     a.counters = co.ctr.p;
