@@ -170,6 +170,9 @@ void dbg_partition_free(dbg_partition* p);
 int dbg_filter_from_records(dbg_ctx* ctx, int k, const void* d_records, uint64_t n_records, const uint32_t* h_counts,
                             uint32_t n_src, uint32_t n_local_buckets, uint64_t n_input_kmers_total,
                             uint32_t min_kmer_obs, int stranded, int report_all_kmers, dbg_kmer_table** out);
+/* A table of n entries with UNINITIALISED device arrays: the caller fills them (ascending, distinct k-mers) through
+ * dbg_table_device_ptrs, e.g. as the receive buffers of a collective. */
+int dbg_table_alloc(dbg_ctx* ctx, int k, uint64_t n, dbg_kmer_table** out);
 /* Device pointers of a table's arrays (hi is NULL for k <= 32), and a table built from device arrays (any order). */
 int dbg_table_device_ptrs(const dbg_kmer_table* t, void** kmers_lo, void** kmers_hi, void** exts, void** counts);
 int dbg_table_from_device(dbg_ctx* ctx, int k, uint64_t n, const void* d_kmers_lo, const void* d_kmers_hi,
@@ -179,22 +182,25 @@ int dbg_table_from_device_sorted(dbg_ctx* ctx, int k, uint64_t n, const void* d_
                                  const void* d_exts, const void* d_counts, dbg_kmer_table** out);
 
 /* ---- sharded compression (multi-GPU): the sorted table is replicated on every rank, the work is split by k-mer
- * index range.  Sequence per rank (collectives by the caller, see rust_debruijn_b200/sharded.py):
- *   dbg_cs_links  -> all-gather nxt -> dbg_cs_paths -> all-gather (seed,length) -> dbg_cs_layout -> dbg_cs_emit
- *   -> all-reduce(sum) of words / exts / data -> dbg_graph_from_device.
+ * index range / node range; same kernels as the single-GPU fast path of dbg_compress_kmers_with_hash
+ * (src/compression.rs:450-583).  Sequence per rank (collectives by the caller, see rust_debruijn_b200/sharded.py):
+ *   dbg_cs_links [v0,v1) -> all-gather link pairs -> dbg_cs_pack -> dbg_cs_discover [v0,v1) -> all-gather path records
+ *   -> dbg_cs_layout -> dbg_cs_emit nodes [i0,i1) -> all-reduce(sum) of words / exts / data -> dbg_graph_from_device.
  * All pointers are DEVICE pointers owned by the caller.  Only unitigs reachable by end walks (<= lmax k-mers) are
  * handled: if the covered k-mers over all ranks do not add up to the table size (long unitigs, cycles) the caller
  * falls back to dbg_compress_kmers_with_hash on the replicated table. */
-int dbg_cs_links(dbg_ctx* ctx, const dbg_kmer_table* full_table, int stranded, uint64_t v0, uint64_t v1, void* d_nxt_local);
-int dbg_cs_paths(dbg_ctx* ctx, const void* d_nxt_full, uint64_t v0, uint64_t v1, uint32_t lmax, void* d_paths /* 16 B each */,
-                 uint64_t capacity, uint64_t* n_paths, uint64_t* n_kmers_covered);
-int dbg_cs_layout(dbg_ctx* ctx, int k, uint64_t n_nodes, const void* d_seed_len_pairs /* 8 B each */, void* d_seed_sorted /* u64 */,
-                  void* d_start /* u64 */, void* d_length /* u32 */, uint64_t* n_bases);
-int dbg_cs_emit(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_nxt_full, const void* d_paths, uint64_t n_paths,
-                const void* d_seed_sorted, const void* d_start, uint64_t n_nodes, int reduce_op, void* d_words,
-                void* d_exts_words /* u32, 4 nodes each */, void* d_data /* u16 */);
+int dbg_cs_links(dbg_ctx* ctx, const dbg_kmer_table* full_table, int stranded, uint64_t v0, uint64_t v1, void* d_nxt_local /* 8 B per k-mer */);
+int dbg_cs_pack(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_nxt_full, void* d_rec16 /* 16 B per k-mer */);
+int dbg_cs_discover(dbg_ctx* ctx, const void* d_rec16, uint64_t n_total, uint64_t v0, uint64_t v1, uint32_t lmax,
+                    void* d_pkey /* u64 */, void* d_pval /* u32 */, uint64_t capacity, uint64_t* n_paths, uint64_t* n_kmers_covered);
+/* sorts the n_nodes path records by seed; *which = 0 / 1: the (a) or (b) pair holds the sorted records afterwards */
+int dbg_cs_layout(dbg_ctx* ctx, int k, uint64_t n_total, uint64_t n_nodes, void* d_pkey_a, void* d_pval_a, void* d_pkey_b,
+                  void* d_pval_b, int* which, void* d_start /* u64 */, void* d_length /* u32 */, uint64_t* n_bases);
+int dbg_cs_emit(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_rec16, const void* d_pkey_sorted,
+                const void* d_pval_sorted, const void* d_start, uint64_t i0, uint64_t i1, int reduce_op, void* d_words,
+                void* d_exts /* u8 */, void* d_data /* u16 */);
 int dbg_graph_from_device(dbg_ctx* ctx, int k, int stranded, uint64_t n_nodes, uint64_t n_bases, const void* d_words,
-                          const void* d_start, const void* d_length, const void* d_exts_words, const void* d_data,
+                          const void* d_start, const void* d_length, const void* d_exts, const void* d_data,
                           dbg_graph** out);
 
 /* ---- msp::msp_sequence bucket assignment — src/msp.rs:279-324, 115-117 -----------------------------

@@ -95,14 +95,17 @@ SIGNATURES = {
     "dbg_partition_free": (None, [vp]),
     "dbg_filter_from_records": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                           C.c_int, C.c_int, vpp]),
+    "dbg_table_alloc": (C.c_int, [vp, C.c_int, C.c_uint64, vpp]),
     "dbg_table_device_ptrs": (C.c_int, [vp, vpp, vpp, vpp, vpp]),
     "dbg_table_from_device": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, vp, vpp]),
     "dbg_table_from_device_sorted": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, vp, vpp]),
     "dbg_cs_links": (C.c_int, [vp, vp, C.c_int, C.c_uint64, C.c_uint64, vp]),
-    "dbg_cs_paths": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, C.c_uint64, C.POINTER(C.c_uint64),
-                               C.POINTER(C.c_uint64)]),
-    "dbg_cs_layout": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, vp, C.POINTER(C.c_uint64)]),
-    "dbg_cs_emit": (C.c_int, [vp, vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64, C.c_int, vp, vp, vp]),
+    "dbg_cs_pack": (C.c_int, [vp, vp, vp, vp]),
+    "dbg_cs_discover": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, C.c_uint64,
+                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "dbg_cs_layout": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_uint64, vp, vp, vp, vp, C.POINTER(C.c_int), vp, vp,
+                                C.POINTER(C.c_uint64)]),
+    "dbg_cs_emit": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp]),
     "dbg_graph_from_device": (C.c_int, [vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vpp]),
     "dbg_msp_kmer_buckets": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_uint64]),
 }

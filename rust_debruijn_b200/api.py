@@ -138,7 +138,8 @@ class SeqSet:
 
     def free(self):
         if self._h:
-            self.ctx._L.dbg_seqset_free(self._h)
+            if self.ctx._h:
+                self.ctx._L.dbg_seqset_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -203,7 +204,8 @@ class KmerTable:
 
     def free(self):
         if self._h:
-            self.ctx._L.dbg_table_free(self._h)
+            if self.ctx._h:   # a destroyed context already released the device (its pool went with it)
+                self.ctx._L.dbg_table_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -273,7 +275,8 @@ class BaseGraph:
 
     def free(self):
         if self._h:
-            self.ctx._L.dbg_graph_free(self._h)
+            if self.ctx._h:
+                self.ctx._L.dbg_graph_free(self._h)
             self._h = None
 
     def __del__(self):

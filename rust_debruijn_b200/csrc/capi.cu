@@ -539,6 +539,31 @@ int dbg_table_from_device_sorted(dbg_ctx* ctx, int k, uint64_t n, const void* d_
     *out = h;
     return DBG_OK;
 }
+int dbg_table_alloc(dbg_ctx* ctx, int k, uint64_t n, dbg_kmer_table** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    Ctx* c = CTX(ctx);
+    *out = nullptr;
+    cudaSetDevice(c->device);
+    if (k < 2 || k > 64) DBG_SET_ERR(c, DBG_E_BADARG, "k=%d outside [2,64]", k);
+    dbg_kmer_table* h = new (std::nothrow) dbg_kmer_table();
+    if (!h) DBG_SET_ERR(c, DBG_E_OOM, "host allocation failed");
+    Table* t = &h->t;
+    t->ctx = c; t->k = k; t->n = n;
+    DBuf<u64> lo, hi;
+    DBuf<u8> ex;
+    DBuf<u16> cn;
+    int rc = lo.alloc_pool(c, n);
+    if (rc == DBG_OK && k > 32) rc = hi.alloc_pool(c, n);
+    if (rc == DBG_OK) rc = ex.alloc_pool(c, n);
+    if (rc == DBG_OK) rc = cn.alloc_pool(c, n);
+    if (rc != DBG_OK) { delete h; return rc; }
+    t->lo = lo.take();
+    if (k > 32) t->hi = hi.take();
+    t->exts = ex.take();
+    t->counts = cn.take();
+    *out = h;
+    return DBG_OK;
+}
 int dbg_table_device_ptrs(const dbg_kmer_table* t, void** kmers_lo, void** kmers_hi, void** exts, void** counts) {
     if (!t) return DBG_E_BADARG;
     if (kmers_lo) *kmers_lo = t->t.lo;
@@ -610,44 +635,50 @@ int dbg_cs_links(dbg_ctx* ctx, const dbg_kmer_table* full_table, int stranded, u
     cudaSetDevice(ctx->c.device);
     return cs_links_dev(CTX(ctx), &full_table->t, stranded != 0, v0, v1, (u32*)d_nxt_local);
 }
-int dbg_cs_paths(dbg_ctx* ctx, const void* d_nxt_full, uint64_t v0, uint64_t v1, uint32_t lmax, void* d_paths,
-                 uint64_t capacity, uint64_t* n_paths, uint64_t* n_kmers_covered) {
+int dbg_cs_pack(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_nxt_full, void* d_rec16) {
+    if (!ctx) return DBG_E_BADARG;
+    NULLCHK(ctx, full_table);
+    cudaSetDevice(ctx->c.device);
+    return cs_pack_dev(CTX(ctx), &full_table->t, (const u32*)d_nxt_full, (uint4*)d_rec16);
+}
+int dbg_cs_discover(dbg_ctx* ctx, const void* d_rec16, uint64_t n_total, uint64_t v0, uint64_t v1, uint32_t lmax, void* d_pkey,
+                    void* d_pval, uint64_t capacity, uint64_t* n_paths, uint64_t* n_kmers_covered) {
     if (!ctx || !n_paths || !n_kmers_covered) return DBG_E_BADARG;
     cudaSetDevice(ctx->c.device);
     u64 np = 0, nc = 0;
-    int rc = cs_paths_dev(CTX(ctx), (const u32*)d_nxt_full, v0, v1, lmax, (uint4*)d_paths, capacity, &np, &nc);
+    int rc = cs_discover_dev(CTX(ctx), (const uint4*)d_rec16, n_total, v0, v1, lmax, (u64*)d_pkey, (u32*)d_pval, capacity, &np, &nc);
     *n_paths = np; *n_kmers_covered = nc;
     return rc;
 }
-int dbg_cs_layout(dbg_ctx* ctx, int k, uint64_t n_nodes, const void* d_pairs, void* d_seed_sorted, void* d_start,
-                  void* d_length, uint64_t* n_bases) {
-    if (!ctx || !n_bases) return DBG_E_BADARG;
+int dbg_cs_layout(dbg_ctx* ctx, int k, uint64_t n_total, uint64_t n_nodes, void* d_pkey_a, void* d_pval_a, void* d_pkey_b,
+                  void* d_pval_b, int* which, void* d_start, void* d_length, uint64_t* n_bases) {
+    if (!ctx || !n_bases || !which) return DBG_E_BADARG;
     cudaSetDevice(ctx->c.device);
     u64 nb = 0;
-    int rc = cs_layout_dev(CTX(ctx), k, n_nodes, (const uint2*)d_pairs, (u64*)d_seed_sorted, (u64*)d_start, (u32*)d_length, &nb);
-    if (rc == DBG_OK) rc = sync(CTX(ctx));
+    int rc = cs_layout_dev(CTX(ctx), k, n_total, n_nodes, (u64*)d_pkey_a, (u32*)d_pval_a, (u64*)d_pkey_b, (u32*)d_pval_b, which,
+                           (u64*)d_start, (u32*)d_length, &nb);
     *n_bases = nb;
     return rc;
 }
-int dbg_cs_emit(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_nxt_full, const void* d_paths, uint64_t n_paths,
-                const void* d_seed_sorted, const void* d_start, uint64_t n_nodes, int reduce_op, void* d_words,
-                void* d_exts_words, void* d_data) {
+int dbg_cs_emit(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_rec16, const void* d_pkey_sorted,
+                const void* d_pval_sorted, const void* d_start, uint64_t i0, uint64_t i1, int reduce_op, void* d_words, void* d_exts,
+                void* d_data) {
     if (!ctx) return DBG_E_BADARG;
     NULLCHK(ctx, full_table);
     if (reduce_op < 0 || reduce_op > 3) DBG_SET_ERR(CTX(ctx), DBG_E_BADARG, "unknown reduce_op %d", reduce_op);
     cudaSetDevice(ctx->c.device);
-    return cs_emit_dev(CTX(ctx), &full_table->t, (const u32*)d_nxt_full, (const uint4*)d_paths, n_paths, (const u64*)d_seed_sorted,
-                       (const u64*)d_start, n_nodes, reduce_op, (u64*)d_words, (u32*)d_exts_words, (u16*)d_data);
+    return cs_emit_dev(CTX(ctx), &full_table->t, (const uint4*)d_rec16, (const u64*)d_pkey_sorted, (const u32*)d_pval_sorted,
+                       (const u64*)d_start, i0, i1, reduce_op, (u64*)d_words, (u8*)d_exts, (u16*)d_data);
 }
 int dbg_graph_from_device(dbg_ctx* ctx, int k, int stranded, uint64_t n_nodes, uint64_t n_bases, const void* d_words,
-                          const void* d_start, const void* d_length, const void* d_exts_words, const void* d_data,
+                          const void* d_start, const void* d_length, const void* d_exts, const void* d_data,
                           dbg_graph** out) {
     if (!ctx || !out) return DBG_E_BADARG;
     *out = nullptr;
     cudaSetDevice(ctx->c.device);
     Graph* g = nullptr;
     int rc = graph_from_device_dev(CTX(ctx), k, stranded != 0, n_nodes, n_bases, (const u64*)d_words, (const u64*)d_start,
-                                   (const u32*)d_length, (const u32*)d_exts_words, (const u16*)d_data, &g);
+                                   (const u32*)d_length, (const u8*)d_exts, (const u16*)d_data, &g);
     *out = reinterpret_cast<dbg_graph*>(g);
     return rc;
 }

@@ -252,12 +252,15 @@ void plan_filter(const Ctx* c, int k, u64 N, int* p_out, int* bbits_out);
 int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int bbits, Partition** out);
 void free_partition(Partition* P);
 int cs_links_dev(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u32* d_nxt_out);
-int cs_paths_dev(Ctx* c, const u32* d_nxt_full, u64 v0, u64 v1, u32 lmax, uint4* d_paths, u64 cap, u64* n_paths, u64* n_covered);
-int cs_layout_dev(Ctx* c, int k, u64 m, const uint2* d_pairs, u64* d_seed_sorted, u64* d_start, u32* d_length, u64* n_bases);
-int cs_emit_dev(Ctx* c, const Table* t, const u32* d_nxt_full, const uint4* d_paths, u64 n_paths, const u64* d_seed_sorted,
-                const u64* d_start, u64 n_nodes, int reduce_op, u64* d_words, u32* d_exts_w, u16* d_data);
+int cs_pack_dev(Ctx* c, const Table* t, const u32* d_nxt_full, uint4* d_rec16);
+int cs_discover_dev(Ctx* c, const uint4* d_rec16, u64 V, u64 v0, u64 v1, u32 lmax, u64* d_pkey, u32* d_pval, u64 cap, u64* n_paths,
+                    u64* n_covered);
+int cs_layout_dev(Ctx* c, int k, u64 V, u64 m, u64* pkey_a, u32* pval_a, u64* pkey_b, u32* pval_b, int* which, u64* d_start,
+                  u32* d_length, u64* n_bases);
+int cs_emit_dev(Ctx* c, const Table* t, const uint4* d_rec16, const u64* d_pkey, const u32* d_pval, const u64* d_start, u64 i0, u64 i1,
+                int reduce_op, u64* d_words, u8* d_exts, u16* d_data);
 int graph_from_device_dev(Ctx* c, int k, int stranded, u64 n_nodes, u64 n_bases, const u64* d_words, const u64* d_start,
-                          const u32* d_length, const u32* d_exts_w, const u16* d_data, Graph** out);
+                          const u32* d_length, const u8* d_exts, const u16* d_data, Graph** out);
 int msp_kmer_buckets_dev(Ctx* c, int k, int p, const SeqSet* s, int stranded, u32* h_out, u64 n_out);
 int filter_from_records_dev(Ctx* c, int k, const u64* d_records, u64 n_records, const u32* h_counts, u32 n_src, u32 n_local,
                             u64 n_input_total, u32 min_obs, int stranded, int report_all, Table** out);

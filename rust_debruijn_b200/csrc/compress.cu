@@ -453,13 +453,16 @@ __global__ void bytes_from_words_kernel(const u32* __restrict__ w, u8* __restric
 // One random 16-byte load per k-mer per walk replaces the ~8 random sectors per k-mer of the per-k-mer
 // rank + emit formulation (which stays as the general path for long unitigs and cycles).
 // ================================================================================================
-__global__ void __launch_bounds__(256) discover_kernel(const uint4* __restrict__ rec, u64 n, u32 lmax, int key_shift, u64* __restrict__ pkey,
-                                u32* __restrict__ pval, u64* __restrict__ counters /* [0] paths, [1] k-mers covered */) {
-    const u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) discover_kernel(const uint4* __restrict__ rec, u64 v0, u64 n, u32 lmax, int key_shift,
+                                                        u64* __restrict__ pkey, u32* __restrict__ pval, u64 cap,
+                                                        u64* __restrict__ counters /* [0] paths, [1] k-mers covered */) {
+    // thread t handles k-mer v0 + t (v0 = 0, n = V on one GPU; a rank of the sharded compression handles its index range)
+    const u64 t_ = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 v = v0 + t_;
     const int lane = threadIdx.x & 31;
     bool emit = false;
     u32 seed = 0, len = 0, left_state = 0;
-    if (v < n) {
+    if (t_ < n) {
         const uint4 r0 = rec[v];
         if (r0.x == NIL && r0.y == NIL) {
             emit = true; seed = (u32)v; len = 1; left_state = 2u * (u32)v + 1u;   // stored orientation: heading right = leaving through R
@@ -495,8 +498,10 @@ __global__ void __launch_bounds__(256) discover_kernel(const uint4* __restrict__
     __syncthreads();
     if (emit) {
         const u64 pos = s_base + s_wcnt[warp] + __popc(m & ((1u << lane) - 1));
-        pkey[pos] = ((u64)seed << key_shift) | len;   // seed in the top bits: the sort looks at those only
-        pval[pos] = left_state;
+        if (pos < cap) {
+            pkey[pos] = ((u64)seed << key_shift) | len;   // seed in the top bits: the sort looks at those only
+            pval[pos] = left_state;
+        }
     }
 }
 
@@ -531,14 +536,15 @@ struct NodeWriter {
 
 struct EmitWalkArgs {
     const u64* lo; const u64* hi; const uint4* rec;
-    const u64* pkey; const u32* pval; const u64* node_start; u64 n_nodes; int key_shift;
+    const u64* pkey; const u32* pval; const u64* node_start; u64 i0, n_nodes; int key_shift;   // nodes [i0, i0 + n_nodes)
     u64* words; u8* out_exts; u16* out_data; int reduce_op;
 };
 
 template <int W>
 __global__ void emit_walk_kernel(KP kp, EmitWalkArgs a) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_nodes) return;
+    const u64 t_ = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_ >= a.n_nodes) return;
+    const u64 i = a.i0 + t_;
     const int K = kp.k;
     const u32 len = (u32)(a.pkey[i] & ((1ull << a.key_shift) - 1));
     u32 cur = a.pval[i];             // at the left end, leaving through its right-facing side
@@ -655,7 +661,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
         DBuf<u64> pk_a, pk_b;
         DBuf<u32> pv_a, pv_b;
         TRY(pk_a.alloc(c, V)); TRY(pv_a.alloc(c, V));
-        discover_kernel<<<grid_for(V, 256), 256, 0, st>>>(rec16.p, V, lmax, key_shift, pk_a.p, pv_a.p, ctr.p);
+        discover_kernel<<<grid_for(V, 256), 256, 0, st>>>(rec16.p, 0, V, lmax, key_shift, pk_a.p, pv_a.p, V, ctr.p);
         TRY(check_launch(c, "discover"));
         u64 h[4];
         TRY(read_u64(c, ctr.p, h, 4));
@@ -681,7 +687,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
             TRY(exclusive_scan_u64(c, node_len.p, ostart.p, M, nullptr));
             CU(c, cudaEventRecord(c->ev[3], st));
             EmitWalkArgs ea;
-            ea.lo = t->lo; ea.hi = t->hi; ea.rec = rec16.p; ea.pkey = rk; ea.pval = rv; ea.node_start = ostart.p; ea.n_nodes = M;
+            ea.lo = t->lo; ea.hi = t->hi; ea.rec = rec16.p; ea.pkey = rk; ea.pval = rv; ea.node_start = ostart.p; ea.i0 = 0; ea.n_nodes = M;
             ea.key_shift = key_shift; ea.words = words.p; ea.out_exts = oexts.p; ea.out_data = odata.p; ea.reduce_op = reduce_op;
             emit_walk_kernel<W><<<grid_for(M, 128), 128, 0, st>>>(kp, ea);
             TRY(check_launch(c, "emit_walk"));
@@ -836,142 +842,26 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
 }
 
 // ================================================================================================
-// Sharded compression (multi-GPU): the sorted table is replicated, the WORK is split.
-//   cs_links   links of the rank's own k-mer range [v0, v1)               (caller all-gathers nxt)
-//   cs_paths   unitigs whose winning end lies in [v0, v1): one record each (caller all-gathers seeds)
-//   cs_layout  node order = ascending seed: sort (seed, length), scan     (replicated, M entries only)
-//   cs_emit    the rank re-walks ITS unitigs and writes bases / Exts / data into zeroed full-size arrays
-//              (caller all-reduces: every word has exactly one writer, so sum == OR)
-// Only components reachable by end walks (<= lmax k-mers) are handled; cs_paths reports how many k-mers
-// that covered and the caller falls back to the replicated single-GPU compression otherwise.
+// Sharded compression (multi-GPU): the sorted table is replicated, the WORK is split by k-mer
+// index range / node range, with the same kernels as the single-GPU fast path.
+//   cs_links     links of the rank's own k-mer range [v0, v1)                (caller all-gathers the link pairs)
+//   cs_pack      16-byte walk records of the whole table from the gathered links      (replicated, streaming)
+//   cs_discover  path records of the unitigs whose LEFT end lies in [v0, v1)         (caller all-gathers them)
+//   cs_layout    node order = ascending seed: sort, lengths, offsets                  (replicated, M entries only)
+//   cs_emit      the rank walks the nodes [i0, i1) and writes bases / Exts / data into zeroed full-size arrays
+//                (caller all-reduces: every word has exactly one writer per bit, so sum == OR)
+// Only components reachable by end walks (<= lmax k-mers) are handled; cs_discover reports how many k-mers that
+// covered and the caller falls back to the replicated single-GPU compression otherwise.
 // ================================================================================================
-__device__ __forceinline__ u32 end_rank_hash(u32 v) { u32 h = v * 0x9E3779B1u; h ^= h >> 15; h *= 0x85EBCA6Bu; h ^= h >> 13; return h; }
-
-// path record: x = seed, y = length in k-mers, z = port state at the left end heading right, w = unused
-__global__ void cs_paths_kernel(const u32* __restrict__ nxt, u64 v0, u64 n_local, u32 lmax, uint4* __restrict__ paths,
-                                u64 cap, u64* __restrict__ counters /* [0] n_paths, [1] k-mers covered */) {
-    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 covered = 0;
-    if (t < n_local) {
-        const u32 v = (u32)(v0 + t);
-        u32 a0 = nxt[2 * (u64)v], a1 = nxt[2 * (u64)v + 1];
-        bool emit = false;
-        uint4 rec = make_uint4(0, 0, 0, 0);
-        if (a0 == NIL && a1 == NIL) {
-            emit = true;
-            rec = make_uint4(v, 1u, 2u * v + 1u, 0u);  // single k-mer, stored orientation: heading right = leaving through R
-        } else if (a0 == NIL || a1 == NIL) {
-            const u32 d = a0 == NIL ? 1u : 0u;
-            u32 cur = 2u * v + d, cnt = 1, minv = v, minst = cur;
-            u32 tt = d ? a1 : a0;
-            while (tt != NIL && cnt <= lmax) {
-                cur = tt;
-                cnt++;
-                if ((tt >> 1) < minv) { minv = tt >> 1; minst = tt; }
-                tt = nxt[cur];
-            }
-            const u32 u = cur >> 1;  // far end
-            // exactly one of the two end walkers wins: the end with the smaller (hash, index) — balanced over ranks
-            const u32 hv = end_rank_hash(v), hu = end_rank_hash(u);
-            if (tt == NIL && (hv < hu || (hv == hu && v < u))) {
-                emit = true;
-                const bool right = minst & 1u;               // this walk runs left -> right in node coordinates
-                // left end heading right: this end if the walk runs rightwards, else the far end turned around
-                u32 left_state = right ? 2u * v + d : (cur ^ 1u);
-                rec = make_uint4(minv, cnt, left_state, 0u);
-            }
-        }
-        if (emit) {
-            u64 pos = atomicAdd(&counters[0], 1ull);
-            if (pos < cap) paths[pos] = rec;
-            covered = rec.y;
-        }
-    }
-    for (int o = 16; o; o >>= 1) covered += __shfl_xor_sync(0xffffffffu, covered, o);
-    if ((threadIdx.x & 31) == 0 && covered) atomicAdd(&counters[1], (u64)covered);
-}
-
-__global__ void cs_pack_seeds_kernel(const uint4* __restrict__ paths, u64 n, u64* __restrict__ seed64, u32* __restrict__ nlen) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { seed64[i] = paths[i].x; nlen[i] = paths[i].y; }
-}
-__global__ void cs_unpack_pairs_kernel(const uint2* __restrict__ pairs, u64 m, u64* __restrict__ key, u32* __restrict__ val) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) { uint2 p = pairs[i]; key[i] = p.x; val[i] = p.y; }
-}
-__global__ void cs_node_len_kernel(const u32* __restrict__ nlen, u64 m, int K, u64* __restrict__ node_len, u32* __restrict__ out_length) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) { u64 l = (u64)nlen[i] + K - 1; node_len[i] = l; out_length[i] = (u32)l; }
-}
-
-struct CsEmitArgs {
-    const u64* lo; const u64* hi; const u8* exts; const u16* counts;
-    const u32* nxt; const uint4* paths; u64 n_paths;
-    const u64* seed_sorted; const u64* node_start; u64 n_nodes;
-    u64* words; u32* out_exts_w; u16* out_data; int reduce_op;
-};
-
 template <int W>
-__global__ void cs_emit_kernel(KP kp, CsEmitArgs a) {
-    u64 pi = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pi >= a.n_paths) return;
-    const uint4 pr = a.paths[pi];
-    // node id = rank of the seed among all seeds (ascending): binary search in the replicated sorted list
-    u64 lo_ = 0, hi_ = a.n_nodes;
-    while (lo_ < hi_) { u64 m = (lo_ + hi_) >> 1; if (a.seed_sorted[m] < (u64)pr.x) lo_ = m + 1; else hi_ = m; }
-    const u64 nid = lo_;
-    const u64 st = a.node_start[nid];
-    const int K = kp.k;
-    u32 cur = pr.z;          // at the left end, leaving through its right-facing side
-    u64 acc = 0;
-    u32 eb = 0;
-    for (u32 i = 0; i < pr.y; i++) {
-        const u32 w = cur >> 1, dw = cur & 1u;
-        const bool fw = dw == 1u;                     // leaving through R while heading right = stored orientation
-        Kmer<W> key = load_key<W>(a.lo, a.hi, w);
-        if (!fw) key = Ops<W>::rc(kp, key);
-        if (i == 0) {
-            int off = (int)(st & 31) * 2;
-            u64 wd = st >> 5;
-            if constexpr (W == 1) {
-                u64 X = key.lo << (64 - 2 * K);
-                atomicOr(&a.words[wd], X >> off);
-                if (off && off + 2 * K > 64) atomicOr(&a.words[wd + 1], X << (64 - off));
-            } else {
-                int sh = 128 - 2 * K;
-                u64 H = sh ? (key.hi << sh) | (key.lo >> (64 - sh)) : key.hi;
-                u64 L = key.lo << sh;
-                atomicOr(&a.words[wd], H >> off);
-                u64 m2 = off ? (H << (64 - off)) | (L >> off) : L;
-                if (m2) atomicOr(&a.words[wd + 1], m2);
-                if (off) { u64 t2 = L << (64 - off); if (t2) atomicOr(&a.words[wd + 2], t2); }
-            }
-            u32 nib = exts_side(a.exts[w], (int)(dw ^ 1u));   // left-facing side of the first k-mer
-            if (!fw) nib = exts_complement(nib) & 0xfu;
-            eb |= nib;
-        } else {
-            u64 g = st + i + K - 1;
-            u64 b = Ops<W>::last_base(kp, key);
-            if (b) atomicOr(&a.words[g >> 5], b << (62 - 2 * (g & 31)));
-        }
-        if (i == pr.y - 1) {
-            u32 nib = exts_side(a.exts[w], (int)dw);          // right-facing side of the last k-mer
-            if (!fw) nib = exts_complement(nib) & 0xfu;
-            eb |= nib << 4;
-        }
-        u64 cnt = a.counts[w];
-        if (a.reduce_op == DBG_REDUCE_MAX) acc = cnt > acc ? cnt : acc; else acc += cnt;
-        cur = a.nxt[cur];
-    }
-    if (eb) atomicOr(&a.out_exts_w[nid >> 2], eb << (8 * (nid & 3)));
-    u16 d;
-    switch (a.reduce_op) {
-        case DBG_REDUCE_SAT_ADD: d = (u16)(acc > 65535 ? 65535 : acc); break;
-        case DBG_REDUCE_WRAP_ADD: d = (u16)(acc & 0xffff); break;
-        case DBG_REDUCE_ADD_MOD_65535: d = pr.y == 1 ? (u16)acc : (u16)(acc % 65535); break;
-        default: d = (u16)acc; break;
-    }
-    a.out_data[nid] = d;   // single writer per node
+__global__ void cs_pack_kernel(KP kp, const u64* __restrict__ lo, const u64* __restrict__ hi, const u8* __restrict__ exts,
+                               const u16* __restrict__ counts, const uint2* __restrict__ nxt, u64 n, uint4* __restrict__ rec16) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Kmer<W> key = load_key<W>(lo, hi, i);
+    uint2 l = nxt[i];
+    u32 meta = (u32)counts[i] | ((u32)exts[i] << 16) | (Ops<W>::first_base(kp, key) << 24) | (Ops<W>::last_base(kp, key) << 26);
+    rec16[i] = make_uint4(l.x, l.y, meta, 0u);
 }
 
 template <int W>
@@ -1010,14 +900,31 @@ int cs_links_dev(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u32* d_nx
     return t->k <= 32 ? cs_links_impl<1>(c, t, stranded, v0, v1, d_nxt_out) : cs_links_impl<2>(c, t, stranded, v0, v1, d_nxt_out);
 }
 
-int cs_paths_dev(Ctx* c, const u32* d_nxt_full, u64 v0, u64 v1, u32 lmax, uint4* d_paths, u64 cap, u64* n_paths, u64* n_covered) {
+static int cs_key_shift(u64 V) {
+    int bits_v = 1;
+    while ((1ull << bits_v) < V) bits_v++;
+    return 64 - bits_v;
+}
+
+int cs_pack_dev(Ctx* c, const Table* t, const u32* d_nxt_full, uint4* d_rec16) {
+    if (!t) DBG_SET_ERR(c, DBG_E_BADARG, "null table");
+    if (!t->n) return DBG_OK;
+    KP kp = make_kp(t->k);
+    if (t->k <= 32) cs_pack_kernel<1><<<grid_for(t->n, 256), 256, 0, c->stream>>>(kp, t->lo, t->hi, t->exts, t->counts, (const uint2*)d_nxt_full, t->n, d_rec16);
+    else cs_pack_kernel<2><<<grid_for(t->n, 256), 256, 0, c->stream>>>(kp, t->lo, t->hi, t->exts, t->counts, (const uint2*)d_nxt_full, t->n, d_rec16);
+    return check_launch(c, "cs_pack");
+}
+
+int cs_discover_dev(Ctx* c, const uint4* d_rec16, u64 V, u64 v0, u64 v1, u32 lmax, u64* d_pkey, u32* d_pval, u64 cap,
+                    u64* n_paths, u64* n_covered) {
+    if (v1 < v0 || v1 > V) DBG_SET_ERR(c, DBG_E_BADARG, "bad k-mer range");
     TRY(arena_begin(c));
     DBuf<u64> ctr;
     TRY(ctr.alloc(c, 2));
     TRY(ctr.zero());
     if (v1 > v0) {
-        cs_paths_kernel<<<grid_for(v1 - v0, 256), 256, 0, c->stream>>>(d_nxt_full, v0, v1 - v0, lmax, d_paths, cap, ctr.p);
-        TRY(check_launch(c, "cs_paths"));
+        discover_kernel<<<grid_for(v1 - v0, 256), 256, 0, c->stream>>>(d_rec16, v0, v1 - v0, lmax, cs_key_shift(V), d_pkey, d_pval, cap, ctr.p);
+        TRY(check_launch(c, "discover"));
     }
     u64 h[2];
     TRY(read_u64(c, ctr.p, h, 2));
@@ -1027,47 +934,45 @@ int cs_paths_dev(Ctx* c, const u32* d_nxt_full, u64 v0, u64 v1, u32 lmax, uint4*
     return DBG_OK;
 }
 
-// d_pairs: m (seed, length) pairs as uint2 in any order.  Outputs (device, caller-allocated): seed_sorted[m] (u64),
-// start[m] (u64), length[m] (u32); *n_bases = total bases.
-int cs_layout_dev(Ctx* c, int k, u64 m, const uint2* d_pairs, u64* d_seed_sorted, u64* d_start, u32* d_length, u64* n_bases) {
+// In: m path records (pkey_a, pval_a) in any order; scratch (pkey_b, pval_b) of the same size.  Out: *which = 0 / 1 says
+// which pair holds the records sorted by seed; d_start[m] (u64 base offsets), d_length[m] (u32), *n_bases.
+int cs_layout_dev(Ctx* c, int k, u64 V, u64 m, u64* pkey_a, u32* pval_a, u64* pkey_b, u32* pval_b, int* which, u64* d_start,
+                  u32* d_length, u64* n_bases) {
     *n_bases = 0;
+    *which = 0;
     if (m == 0) return DBG_OK;
     TRY(arena_begin(c));
     cudaStream_t st = c->stream;
-    DBuf<u64> ka, kb, tot, nl64;
-    DBuf<u32> va, vb;
-    TRY(ka.alloc(c, m)); TRY(kb.alloc(c, m)); TRY(va.alloc(c, m)); TRY(vb.alloc(c, m)); TRY(tot.alloc(c, 1)); TRY(nl64.alloc(c, m));
-    cs_unpack_pairs_kernel<<<grid_for(m, 256), 256, 0, st>>>(d_pairs, m, ka.p, va.p);   // (seed, length) -> sort key / payload
-    TRY(check_launch(c, "cs_unpack_pairs"));
     u64 *rk, *rh;
     u32* rv;
-    TRY(radix_sort_pairs(c, 1, 32, m, ka.p, nullptr, va.p, kb.p, nullptr, vb.p, &rk, &rh, &rv));
-    CU(c, cudaMemcpyAsync(d_seed_sorted, rk, m * 8, cudaMemcpyDeviceToDevice, st));
-    cs_node_len_kernel<<<grid_for(m, 256), 256, 0, st>>>(rv, m, k, nl64.p, d_length);
-    TRY(check_launch(c, "cs_node_len"));
+    TRY(radix_sort_pairs(c, 1, 64, m, pkey_a, nullptr, pval_a, pkey_b, nullptr, pval_b, &rk, &rh, &rv));
+    *which = rk == pkey_a ? 0 : 1;
+    DBuf<u64> nl64, tot;
+    TRY(nl64.alloc(c, m)); TRY(tot.alloc(c, 1));
+    path_len_kernel<<<grid_for(m, 256), 256, 0, st>>>(rk, m, cs_key_shift(V), k, nl64.p, d_length);
+    TRY(check_launch(c, "path_len"));
     TRY(exclusive_scan_u64(c, nl64.p, d_start, m, tot.p));
     TRY(read_u64(c, tot.p, n_bases));
     return DBG_OK;
 }
 
-int cs_emit_dev(Ctx* c, const Table* t, const u32* d_nxt_full, const uint4* d_paths, u64 n_paths, const u64* d_seed_sorted,
-                const u64* d_start, u64 n_nodes, int reduce_op, u64* d_words, u32* d_exts_w, u16* d_data) {
-    if (n_paths == 0) return DBG_OK;
+int cs_emit_dev(Ctx* c, const Table* t, const uint4* d_rec16, const u64* d_pkey, const u32* d_pval, const u64* d_start, u64 i0,
+                u64 i1, int reduce_op, u64* d_words, u8* d_exts, u16* d_data) {
+    if (i1 <= i0) return DBG_OK;
     KP kp = make_kp(t->k);
-    CsEmitArgs a;
-    a.lo = t->lo; a.hi = t->hi; a.exts = t->exts; a.counts = t->counts;
-    a.nxt = d_nxt_full; a.paths = d_paths; a.n_paths = n_paths;
-    a.seed_sorted = d_seed_sorted; a.node_start = d_start; a.n_nodes = n_nodes;
-    a.words = d_words; a.out_exts_w = d_exts_w; a.out_data = d_data; a.reduce_op = reduce_op;
-    if (t->k <= 32) cs_emit_kernel<1><<<grid_for(n_paths, 128), 128, 0, c->stream>>>(kp, a);
-    else cs_emit_kernel<2><<<grid_for(n_paths, 128), 128, 0, c->stream>>>(kp, a);
-    TRY(check_launch(c, "cs_emit"));
+    EmitWalkArgs ea;
+    ea.lo = t->lo; ea.hi = t->hi; ea.rec = d_rec16; ea.pkey = d_pkey; ea.pval = d_pval; ea.node_start = d_start;
+    ea.i0 = i0; ea.n_nodes = i1 - i0; ea.key_shift = cs_key_shift(t->n);
+    ea.words = d_words; ea.out_exts = d_exts; ea.out_data = d_data; ea.reduce_op = reduce_op;
+    if (t->k <= 32) emit_walk_kernel<1><<<grid_for(i1 - i0, 128), 128, 0, c->stream>>>(kp, ea);
+    else emit_walk_kernel<2><<<grid_for(i1 - i0, 128), 128, 0, c->stream>>>(kp, ea);
+    TRY(check_launch(c, "emit_walk"));
     return sync(c);
 }
 
-// Adopt caller-owned device arrays (copied) as a BaseGraph handle.  d_exts_w = node Exts packed 4 per u32.
+// Adopt caller-owned device arrays (copied) as a BaseGraph handle.
 int graph_from_device_dev(Ctx* c, int k, int stranded, u64 n_nodes, u64 n_bases, const u64* d_words, const u64* d_start,
-                          const u32* d_length, const u32* d_exts_w, const u16* d_data, Graph** out) {
+                          const u32* d_length, const u8* d_exts, const u16* d_data, Graph** out) {
     *out = nullptr;
     cudaStream_t st = c->stream;
     Graph* g = &(new dbg_graph())->g;
@@ -1088,8 +993,7 @@ int graph_from_device_dev(Ctx* c, int k, int stranded, u64 n_nodes, u64 n_bases,
     cudaMemcpyAsync(ostart.p, d_start, n_nodes * 8, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(olen.p, d_length, n_nodes * 4, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(odata.p, d_data, n_nodes * 2, cudaMemcpyDeviceToDevice, st);
-    bytes_from_words_kernel<<<grid_for(n_nodes, 256), 256, 0, st>>>(d_exts_w, oexts.p, n_nodes);
-    c->launches++;
+    cudaMemcpyAsync(oexts.p, d_exts, n_nodes, cudaMemcpyDeviceToDevice, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) {
         free_graph(g); *out = nullptr;
         DBG_SET_ERR(c, DBG_E_CUDA, "graph_from_device: %s", cudaGetErrorString(cudaGetLastError()));
