@@ -138,7 +138,7 @@ def run_reference(args, rank, world):
     v = statistics.mean(vals)
     last["value"] = v
     last["sample"] += " per step; filter stage parallel over sequence ranges and the 256 prefix buckets, compress is serial by construction"
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": statistics.mean(ms), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -146,10 +146,27 @@ def run_reference(args, rank, world):
                    "k": K, "min_kmer_obs": MIN_OBS, "stranded": False},
         "cpu_baseline": last,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+def emit_json(obj):
+    """The ONE JSON line goes to the real stdout; everything else any library prints on fd 1 during the run
+    (e.g. NCCL's version banner) was diverted to stderr by divert_stdout()."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def divert_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
+    divert_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -339,7 +356,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args.cpu_sample_reads, 1)
-        print(json.dumps(out))
+        emit_json(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -173,6 +173,9 @@ int dbg_filter_from_records(dbg_ctx* ctx, int k, const void* d_records, uint64_t
 /* A table of n entries with UNINITIALISED device arrays: the caller fills them (ascending, distinct k-mers) through
  * dbg_table_device_ptrs, e.g. as the receive buffers of a collective. */
 int dbg_table_alloc(dbg_ctx* ctx, int k, uint64_t n, dbg_kmer_table** out);
+/* Histogram of the top `bits` (<= min(24, 2k)) bits of the table's keys into d_hist (device, 2^bits u32, zeroed by the
+ * call; stream-ordered, not synchronised): splitters for redistributing sorted shards by key range. */
+int dbg_table_prefix_hist(dbg_ctx* ctx, const dbg_kmer_table* t, int bits, void* d_hist);
 /* Device pointers of a table's arrays (hi is NULL for k <= 32), and a table built from device arrays (any order). */
 int dbg_table_device_ptrs(const dbg_kmer_table* t, void** kmers_lo, void** kmers_hi, void** exts, void** counts);
 int dbg_table_from_device(dbg_ctx* ctx, int k, uint64_t n, const void* d_kmers_lo, const void* d_kmers_hi,

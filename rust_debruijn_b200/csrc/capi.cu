@@ -564,6 +564,12 @@ int dbg_table_alloc(dbg_ctx* ctx, int k, uint64_t n, dbg_kmer_table** out) {
     *out = h;
     return DBG_OK;
 }
+int dbg_table_prefix_hist(dbg_ctx* ctx, const dbg_kmer_table* t, int bits, void* d_hist) {
+    if (!ctx || !d_hist) return DBG_E_BADARG;
+    NULLCHK(ctx, t);
+    cudaSetDevice(ctx->c.device);
+    return table_prefix_hist_dev(CTX(ctx), &t->t, bits, (u32*)d_hist);
+}
 int dbg_table_device_ptrs(const dbg_kmer_table* t, void** kmers_lo, void** kmers_hi, void** exts, void** counts) {
     if (!t) return DBG_E_BADARG;
     if (kmers_lo) *kmers_lo = t->t.lo;

@@ -900,6 +900,17 @@ int cs_links_dev(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u32* d_nx
     return t->k <= 32 ? cs_links_impl<1>(c, t, stranded, v0, v1, d_nxt_out) : cs_links_impl<2>(c, t, stranded, v0, v1, d_nxt_out);
 }
 
+// histogram of the top `bits` bits of the (ascending) keys: 2^bits u32 counters, zeroed here
+int table_prefix_hist_dev(Ctx* c, const Table* t, int bits, u32* d_hist) {
+    if (!t || bits < 1 || bits > 24 || bits > 2 * t->k) DBG_SET_ERR(c, DBG_E_BADARG, "bad prefix width %d", bits);
+    CU(c, cudaMemsetAsync(d_hist, 0, sizeof(u32) << bits, c->stream));
+    if (!t->n) return DBG_OK;
+    const int shift = 2 * t->k - bits;
+    if (t->k <= 32) lut_hist_kernel<1><<<grid_for(t->n, 256), 256, 0, c->stream>>>(t->lo, t->hi, t->n, shift, d_hist);
+    else lut_hist_kernel<2><<<grid_for(t->n, 256), 256, 0, c->stream>>>(t->lo, t->hi, t->n, shift, d_hist);
+    return check_launch(c, "lut_hist");
+}
+
 static int cs_key_shift(u64 V) {
     int bits_v = 1;
     while ((1ull << bits_v) < V) bits_v++;

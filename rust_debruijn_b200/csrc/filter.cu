@@ -1077,18 +1077,28 @@ __global__ void unpack_vals_kernel(const u32* __restrict__ val, u8* __restrict__
     counts[i] = (u16)(v >> 8);
 }
 
-__global__ void count_input_kmers_kernel(const u32* __restrict__ length, u64 n, int k, u64* out, u32* max_len) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) count_input_kmers_kernel(const u32* __restrict__ length, u64 n, int k, u64* out, u32* max_len) {
+    __shared__ u64 s_v[8];
+    __shared__ u32 s_l[8];
     u64 v = 0;
     u32 L = 0;
-    if (i < n) { L = length[i]; v = L >= (u32)k ? L - k + 1 : 0; }
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u32 l = length[i];
+        L = max(L, l);
+        v += l >= (u32)k ? l - k + 1 : 0;
+    }
     for (int o = 16; o; o >>= 1) {
         v += __shfl_down_sync(0xffffffffu, v, o);
         L = max(L, __shfl_down_sync(0xffffffffu, L, o));
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (v) atomicAdd(out, v);
-        atomicMax(max_len, L);
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = v; s_l[threadIdx.x >> 5] = L; }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // one atomic per CTA (same-address atomics serialise)
+        u64 tv = 0;
+        u32 tl = 0;
+        for (int w = 0; w < 8; w++) { tv += s_v[w]; tl = max(tl, s_l[w]); }
+        if (tv) atomicAdd(out, tv);
+        atomicMax(max_len, tl);
     }
 }
 
@@ -1143,7 +1153,7 @@ static int count_input(Ctx* c, int k, const SeqSet* s, u64* N_out, u32* max_len_
         DBuf<u64> tmp;
         TRY(tmp.alloc(c, 2));
         TRY(tmp.zero());
-        count_input_kmers_kernel<<<grid_for(s->n_seqs, 256), 256, 0, c->stream>>>(s->length, s->n_seqs, k, tmp.p, (u32*)(tmp.p + 1));
+        count_input_kmers_kernel<<<(u32)std::min<u64>(grid_for(s->n_seqs, 256), (u64)c->sm_count * 8), 256, 0, c->stream>>>(s->length, s->n_seqs, k, tmp.p, (u32*)(tmp.p + 1));
         TRY(check_launch(c, "count_input_kmers"));
         u64 h[2];
         TRY(read_u64(c, tmp.p, h, 2));
@@ -1568,11 +1578,20 @@ __global__ void merge_runs_kernel(const u64* __restrict__ src, u64* __restrict__
 }
 
 template <int RW>
-__global__ void sum_record_kmers_kernel(const u64* __restrict__ rec, u64 n, u64* out) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u64 v = i < n ? (rec[i * RW + RW - 1] >> 8) & 63ull : 0;
+__global__ void __launch_bounds__(256) sum_record_kmers_kernel(const u64* __restrict__ rec, u64 n, u64* out) {
+    // grid-stride + one atomic per CTA: same-address L2 atomics serialise, a per-warp atomic would dominate the kernel
+    __shared__ u64 s_w[8];
+    u64 v = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        v += (rec[i * RW + RW - 1] >> 8) & 63ull;
     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 t = 0;
+        for (int w = 0; w < 8; w++) t += s_w[w];
+        if (t) atomicAdd(out, t);
+    }
 }
 
 // d_records: n_src runs back to back, run s holding the records of this rank's n_local buckets in bucket order;
@@ -1627,8 +1646,9 @@ int filter_from_records_dev(Ctx* c, int k, const u64* d_records, u64 n_records, 
     DBuf<u64> d_sum;
     TRY(d_sum.alloc(c, 1));
     TRY(d_sum.zero());
-    if (RW == 2) sum_record_kmers_kernel<2><<<grid_for(n_records, 256), 256, 0, st>>>(merged.p, n_records, d_sum.p);
-    else sum_record_kmers_kernel<4><<<grid_for(n_records, 256), 256, 0, st>>>(merged.p, n_records, d_sum.p);
+    const u32 sgrid = (u32)std::min<u64>(grid_for(n_records, 256), (u64)c->sm_count * 8);
+    if (RW == 2) sum_record_kmers_kernel<2><<<sgrid, 256, 0, st>>>(merged.p, n_records, d_sum.p);
+    else sum_record_kmers_kernel<4><<<sgrid, 256, 0, st>>>(merged.p, n_records, d_sum.p);
     TRY(check_launch(c, "sum_record_kmers"));
     u64 N_local_bound = 0;
     TRY(read_u64(c, d_sum.p, &N_local_bound));  // also: host vectors may go out of scope after this sync

@@ -174,7 +174,7 @@ def _table_views(table, dev):
     return lo, hi, _as_tensor(ex_p.value, n, dev), _as_tensor(cn_p.value, n * 2, dev)
 
 
-def gather_table(table, group=None):
+def gather_table(table, group=None, timings=None):
     """Union of every rank's (disjoint, ascending) shard on every rank, ascending.
 
     A re-sort of the gathered table would cost every rank P times the single-GPU sort.  Instead the shards are
@@ -188,24 +188,29 @@ def gather_table(table, group=None):
     dev = torch.device("cuda", ctx.device)
     k, n = table.k, len(table)
     two = k > 32
-    with torch.cuda.stream(_lib_stream(ctx)):
+    st = _lib_stream(ctx)
+    marks = []
+
+    def mark(name):
+        if timings is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(st)
+            marks.append((name, e))
+
+    with torch.cuda.stream(st):
+        mark("begin")
         lo, hi, ex, cn = _table_views(table, dev)
-        # ---- splitters: top 16 bits of the 2k-bit key ----
-        nbits = 2 * k - 64 if two else 2 * k          # key bits in the most significant word
-        top = hi if two else lo
-        if nbits >= 16:
-            pfx = (top >> (nbits - 16)) & 0xFFFF
-        elif two:                                     # K = 33..39: borrow the missing prefix bits from the low word
-            miss = 16 - nbits
-            pfx = ((top << miss) | ((lo >> (64 - miss)) & ((1 << miss) - 1))) & 0xFFFF
-        else:                                         # K < 8
-            pfx = (top << (16 - nbits)) & 0xFFFF
-        hist = torch.bincount(pfx, minlength=65536)[:65536]
+        # ---- splitters: histogram of the top bits of the 2k-bit key (device kernel), all-reduced ----
+        hbits = min(16, 2 * k)
+        hist_local = torch.empty(1 << hbits, dtype=torch.int32, device=dev)
+        ctx.check(L.dbg_table_prefix_hist(ctx._h, table._h, hbits, C.c_void_p(hist_local.data_ptr())))
+        hist = hist_local.to(torch.int64)
+        mark("hist")
         dist.all_reduce(hist, group=group)
         cuts = key_range_splitters(hist.cpu().numpy(), world)
         # this rank's shard is ascending: destination r gets the contiguous slice with prefix in [cuts[r], cuts[r+1])
-        bounds = torch.searchsorted(pfx, torch.tensor(cuts, dtype=torch.int64, device=dev), right=False)
-        bounds[-1] = n
+        csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(hist_local, 0, dtype=torch.int64)])
+        bounds = csum[torch.tensor(cuts, dtype=torch.int64, device=dev)]
         sn = bounds[1:] - bounds[:-1]
         rn = torch.empty(world, dtype=torch.int64, device=dev)
         dist.all_to_all_single(rn, sn, group=group)
@@ -221,6 +226,7 @@ def gather_table(table, group=None):
 
         r_lo, r_ex, r_cn = a2a(lo, 8), a2a(ex, 1), a2a(cn, 2)
         r_hi = a2a(hi, 8) if two else None
+        mark("a2a")
         # ---- sort this key range (P ascending runs -> one): V/P k-mers ----
         th = C.c_void_p()
         ctx.check(L.dbg_table_from_device(ctx._h, k, m, C.c_void_p(r_lo.data_ptr()),
@@ -228,6 +234,7 @@ def gather_table(table, group=None):
                                           C.c_void_p(r_cn.data_ptr()), C.byref(th)))
         piece = KmerTable(ctx, th)
         del r_lo, r_ex, r_cn, r_hi
+        mark("sort")
         # ---- every rank's ordered range straight into the replicated table ----
         sizes = torch.empty(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(sizes, torch.tensor([m], dtype=torch.int64, device=dev), group=group)
@@ -248,8 +255,12 @@ def gather_table(table, group=None):
                     sl.copy_(s_arr)
                 dist.broadcast(sl, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
             off += sizes[r]
+        mark("bcast")
         ctx.synchronize()
         piece.free()
+    if timings is not None:
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            timings["ms_g_" + n1] = e0.elapsed_time(e1)
     full.piece_sizes = sizes   # rank r's key range = global indices [sum(sizes[:r]), sum(sizes[:r+1]))
     return full
 
@@ -370,7 +381,7 @@ def reads_to_graph_sharded(seqs, summarizer, spec, stranded=False, k=31, group=N
     shard = filter_kmers_sharded(seqs, summarizer, stranded, k=k, group=group, timings=timings)
     t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     t0.record(st)
-    full = gather_table(shard, group)
+    full = gather_table(shard, group, timings=timings)
     t1.record(st)
     shard.free()
     g = compress_sharded(full, stranded, spec, group=group, timings=timings)
