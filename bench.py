@@ -214,10 +214,13 @@ def main():
 
     def step():
         if world > 1:
-            # one job over all ranks: MSP-bucket-sharded filter_kmers (one NCCL all-to-all of super-k-mer records),
-            # valid k-mers gathered, compress replicated on every rank (SURVEY §8e fallback for S3-S6)
+            # one job over all ranks: MSP-bucket-sharded filter_kmers (one NCCL all-to-all of super-k-mer records), valid
+            # k-mers redistributed by key range + replicated, compress work split over the ranks, every rank keeps its
+            # run of nodes of the complete BaseGraph (concatenation in rank order = the single-GPU graph, bit for bit)
             last_tm.clear()
-            g = sharded.reads_to_graph_sharded(ss, filt, spec, stranded=False, k=K, timings=last_tm)
+            g = sharded.reads_to_graph_sharded(ss, filt, spec, stranded=False, k=K, timings=last_tm, replicate=False)
+            last_tm["nodes_total"], last_tm["bases_total"] = g.n_nodes_total, g.n_bases_total
+            last_tm["nodes_this_rank"], last_tm["output"] = len(g), ("complete graph on every rank" if g.replicated else "node-sharded")
         else:
             g = D.reads_to_graph(ss, filt, spec, stranded=False, k=K)
         n = len(g)
@@ -263,8 +266,8 @@ def main():
     pw = torch.empty(len(hw), dtype=torch.int64, pin_memory=True)
     pw.numpy()[:] = hw.view(np.int64)
     words_pinned = pw.numpy().view(np.uint64)
-    M0, nb0 = st1["n_nodes"], st1["n_bases"]  # world > 1: the gathered, complete graph (same on every rank)
-    cap_nodes, cap_words = int(M0 * 1.05) + 16, int(nb0 * 1.05) // 32 + 16
+    M0, nb0 = st1["n_nodes"], st1["n_bases"]  # world > 1: this rank's run of nodes
+    cap_nodes, cap_words = int(M0 * 1.2) + 1024, int(nb0 * 1.2) // 32 + 1024
     out_bufs = {
         "words": torch.empty(cap_words, dtype=torch.int64, pin_memory=True),
         "start": torch.empty(cap_nodes, dtype=torch.int64, pin_memory=True),
@@ -279,7 +282,7 @@ def main():
         gh = C.c_void_p()
         if world > 1:
             sse = D.SeqSet.upload_uniform(ctx, words_pinned, len(hs), 150)
-            ge = sharded.reads_to_graph_sharded(sse, filt, spec, stranded=False, k=K)
+            ge = sharded.reads_to_graph_sharded(sse, filt, spec, stranded=False, k=K, replicate=False)
             sse.free()
             gh, ge._h = ge._h, None
         else:
@@ -307,12 +310,13 @@ def main():
 
     # ---- reduce over ranks: max time, sum of units ----
     times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
-    units = torch.tensor([float(n_kmers)], dtype=torch.float64, device=f"cuda:{local}")
+    units = torch.tensor([float(n_kmers), float(h2d), float(d2h)], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(units, op=dist.ReduceOp.SUM)
     ms_total, ms_e2e = float(times[0]), float(times[1])
     total_kmers = float(units[0])
+    h2d, d2h = int(units[1]), int(units[2])   # whole job: every rank uploads its reads and reads back its nodes
     if rank == 0:
         ms_step = ms_total / args.steps
         value = total_kmers / (ms_step * 1e-3)
@@ -333,11 +337,13 @@ def main():
             "config": {"workload": f"configs[1]: K=31, {R} x 150bp synth-v1 noisy reads per GPU (e=0.5%, 50x), "
                                    "CountFilter(2), SimpleCompress(sat_add), stranded=false, " +
                                    ("all MSP buckets on one GPU" if world == 1 else f"one job of {world * R} reads, MSP buckets sharded over {world} GPUs"),
-                       "k": K, "reads_per_gpu": R, "input_kmers_per_gpu": N, "valid_kmers": V, "nodes": st1["n_nodes"],
-                       "node_bases": st1["n_bases"], "msp_p": st1["msp_p"], "bucket_bits": st1["bucket_bits"],
+                       "k": K, "reads_per_gpu": R, "input_kmers_per_gpu": N, "valid_kmers": V,
+                       "nodes": st1["n_nodes"] if world == 1 else last_tm.get("nodes_total"),
+                       "node_bases": st1["n_bases"] if world == 1 else last_tm.get("bases_total"), "msp_p": st1["msp_p"], "bucket_bits": st1["bucket_bits"],
                        "l2": "inputs and every intermediate exceed the 126 MB L2; no flush needed",
-                       "parallelism": ("MSP-bucket-sharded filter_kmers (one NCCL all-to-all of super-k-mer records) + "
-                                       "gathered table, compress replicated per rank") if world > 1 else "single",
+                       "parallelism": ("MSP-bucket-sharded filter_kmers (one NCCL all-to-all of super-k-mer records) + table "
+                                       "redistributed by key range and replicated + compress work split by k-mer / seed "
+                                       "range; every rank keeps its run of nodes") if world > 1 else "single",
                        "sharded_stage_ms": {k_: (round(v, 3) if isinstance(v, float) else v) for k_, v in last_tm.items()}},
             "clocks": clocks, "remeasured": remeasured,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -187,8 +187,9 @@ int dbg_table_from_device_sorted(dbg_ctx* ctx, int k, uint64_t n, const void* d_
 /* ---- sharded compression (multi-GPU): the sorted table is replicated on every rank, the work is split by k-mer
  * index range / node range; same kernels as the single-GPU fast path of dbg_compress_kmers_with_hash
  * (src/compression.rs:450-583).  Sequence per rank (collectives by the caller, see rust_debruijn_b200/sharded.py):
- *   dbg_cs_links [v0,v1) -> all-gather link pairs -> dbg_cs_pack -> dbg_cs_discover [v0,v1) -> all-gather path records
- *   -> dbg_cs_layout -> dbg_cs_emit nodes [i0,i1) -> all-reduce(sum) of words / exts / data -> dbg_graph_from_device.
+ *   dbg_cs_links [v0,v1) -> all-gather link pairs -> dbg_cs_pack -> dbg_cs_discover [v0,v1) -> dbg_cs_sort_paths ->
+ *   all-to-all of the path records by seed range -> dbg_cs_layout (own seed range) -> dbg_cs_emit (own nodes) ->
+ *   all-reduce(sum) of words / exts / data / start / length -> dbg_graph_from_device.
  * All pointers are DEVICE pointers owned by the caller.  Only unitigs reachable by end walks (<= lmax k-mers) are
  * handled: if the covered k-mers over all ranks do not add up to the table size (long unitigs, cycles) the caller
  * falls back to dbg_compress_kmers_with_hash on the replicated table. */
@@ -199,9 +200,14 @@ int dbg_cs_discover(dbg_ctx* ctx, const void* d_rec16, uint64_t n_total, uint64_
 /* sorts the n_nodes path records by seed; *which = 0 / 1: the (a) or (b) pair holds the sorted records afterwards */
 int dbg_cs_layout(dbg_ctx* ctx, int k, uint64_t n_total, uint64_t n_nodes, void* d_pkey_a, void* d_pval_a, void* d_pkey_b,
                   void* d_pval_b, int* which, void* d_start /* u64 */, void* d_length /* u32 */, uint64_t* n_bases);
+/* sort path records by seed (the pre-sort before they are shipped to the rank that owns their seed range) */
+int dbg_cs_sort_paths(dbg_ctx* ctx, uint64_t n_paths, void* d_pkey_a, void* d_pval_a, void* d_pkey_b, void* d_pval_b, int* which);
+/* the n_paths records (sorted by seed, local base offsets in d_start_local) become nodes node0.. of the graph, bases from
+ * base0 + d_start_local[i]; writes go to the global positions of zeroed full-size arrays (stream-ordered, not synchronised) */
 int dbg_cs_emit(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_rec16, const void* d_pkey_sorted,
-                const void* d_pval_sorted, const void* d_start, uint64_t i0, uint64_t i1, int reduce_op, void* d_words,
-                void* d_exts /* u8 */, void* d_data /* u16 */);
+                const void* d_pval_sorted, const void* d_start_local, uint64_t n_paths, uint64_t node0, uint64_t base0,
+                int reduce_op, void* d_words, void* d_exts /* u8 */, void* d_data /* u16 */, void* d_out_start /* u64 */,
+                void* d_out_length /* u32 */);
 int dbg_graph_from_device(dbg_ctx* ctx, int k, int stranded, uint64_t n_nodes, uint64_t n_bases, const void* d_words,
                           const void* d_start, const void* d_length, const void* d_exts, const void* d_data,
                           dbg_graph** out);

@@ -106,7 +106,8 @@ SIGNATURES = {
                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dbg_cs_layout": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_uint64, vp, vp, vp, vp, C.POINTER(C.c_int), vp, vp,
                                 C.POINTER(C.c_uint64)]),
-    "dbg_cs_emit": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp]),
+    "dbg_cs_sort_paths": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, C.POINTER(C.c_int)]),
+    "dbg_cs_emit": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp, vp, vp]),
     "dbg_graph_from_device": (C.c_int, [vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vpp]),
     "dbg_msp_kmer_buckets": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_uint64]),
 }

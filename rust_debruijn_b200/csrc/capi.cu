@@ -666,15 +666,21 @@ int dbg_cs_layout(dbg_ctx* ctx, int k, uint64_t n_total, uint64_t n_nodes, void*
     *n_bases = nb;
     return rc;
 }
+int dbg_cs_sort_paths(dbg_ctx* ctx, uint64_t n_paths, void* d_pkey_a, void* d_pval_a, void* d_pkey_b, void* d_pval_b, int* which) {
+    if (!ctx || !which) return DBG_E_BADARG;
+    cudaSetDevice(ctx->c.device);
+    return cs_sort_paths_dev(CTX(ctx), n_paths, (u64*)d_pkey_a, (u32*)d_pval_a, (u64*)d_pkey_b, (u32*)d_pval_b, which);
+}
 int dbg_cs_emit(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_rec16, const void* d_pkey_sorted,
-                const void* d_pval_sorted, const void* d_start, uint64_t i0, uint64_t i1, int reduce_op, void* d_words, void* d_exts,
-                void* d_data) {
+                const void* d_pval_sorted, const void* d_start_local, uint64_t n_paths, uint64_t node0, uint64_t base0,
+                int reduce_op, void* d_words, void* d_exts, void* d_data, void* d_out_start, void* d_out_length) {
     if (!ctx) return DBG_E_BADARG;
     NULLCHK(ctx, full_table);
     if (reduce_op < 0 || reduce_op > 3) DBG_SET_ERR(CTX(ctx), DBG_E_BADARG, "unknown reduce_op %d", reduce_op);
     cudaSetDevice(ctx->c.device);
     return cs_emit_dev(CTX(ctx), &full_table->t, (const uint4*)d_rec16, (const u64*)d_pkey_sorted, (const u32*)d_pval_sorted,
-                       (const u64*)d_start, i0, i1, reduce_op, (u64*)d_words, (u8*)d_exts, (u16*)d_data);
+                       (const u64*)d_start_local, n_paths, node0, base0, reduce_op, (u64*)d_words, (u8*)d_exts, (u16*)d_data,
+                       (u64*)d_out_start, (u32*)d_out_length);
 }
 int dbg_graph_from_device(dbg_ctx* ctx, int k, int stranded, uint64_t n_nodes, uint64_t n_bases, const void* d_words,
                           const void* d_start, const void* d_length, const void* d_exts, const void* d_data,

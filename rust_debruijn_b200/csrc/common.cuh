@@ -258,8 +258,9 @@ int cs_discover_dev(Ctx* c, const uint4* d_rec16, u64 V, u64 v0, u64 v1, u32 lma
                     u64* n_covered);
 int cs_layout_dev(Ctx* c, int k, u64 V, u64 m, u64* pkey_a, u32* pval_a, u64* pkey_b, u32* pval_b, int* which, u64* d_start,
                   u32* d_length, u64* n_bases);
-int cs_emit_dev(Ctx* c, const Table* t, const uint4* d_rec16, const u64* d_pkey, const u32* d_pval, const u64* d_start, u64 i0, u64 i1,
-                int reduce_op, u64* d_words, u8* d_exts, u16* d_data);
+int cs_sort_paths_dev(Ctx* c, u64 m, u64* pkey_a, u32* pval_a, u64* pkey_b, u32* pval_b, int* which);
+int cs_emit_dev(Ctx* c, const Table* t, const uint4* d_rec16, const u64* d_pkey, const u32* d_pval, const u64* d_start, u64 m,
+                u64 node0, u64 base0, int reduce_op, u64* d_words, u8* d_exts, u16* d_data, u64* d_out_start, u32* d_out_length);
 int graph_from_device_dev(Ctx* c, int k, int stranded, u64 n_nodes, u64 n_bases, const u64* d_words, const u64* d_start,
                           const u32* d_length, const u8* d_exts, const u16* d_data, Graph** out);
 int msp_kmer_buckets_dev(Ctx* c, int k, int p, const SeqSet* s, int stranded, u32* h_out, u64 n_out);

@@ -536,8 +536,10 @@ struct NodeWriter {
 
 struct EmitWalkArgs {
     const u64* lo; const u64* hi; const uint4* rec;
-    const u64* pkey; const u32* pval; const u64* node_start; u64 i0, n_nodes; int key_shift;   // nodes [i0, i0 + n_nodes)
+    const u64* pkey; const u32* pval; const u64* node_start; u64 i0, n_nodes; int key_shift;   // path records [i0, i0 + n_nodes)
+    u64 out0, base0;   // node id = record index + out0; base offset = node_start[record] + base0 (sharded emission)
     u64* words; u8* out_exts; u16* out_data; int reduce_op;
+    u64* out_start; u32* out_length;   // optional: global start / length of the emitted nodes (sharded emission)
 };
 
 template <int W>
@@ -548,7 +550,7 @@ __global__ void emit_walk_kernel(KP kp, EmitWalkArgs a) {
     const int K = kp.k;
     const u32 len = (u32)(a.pkey[i] & ((1ull << a.key_shift) - 1));
     u32 cur = a.pval[i];             // at the left end, leaving through its right-facing side
-    const u64 st = a.node_start[i];
+    const u64 st = a.node_start[i] + a.base0;
     const u64 L = (u64)len + K - 1;
     NodeWriter nw;
     nw.words = a.words; nw.first_w = st >> 5; nw.last_w = (st + L - 1) >> 5; nw.wi = nw.first_w; nw.cur = 0;
@@ -600,7 +602,8 @@ __global__ void emit_walk_kernel(KP kp, EmitWalkArgs a) {
         cur = dw ? r.y : r.x;
     }
     if (pos & 31) nw.flush();   // partial last word
-    a.out_exts[i] = (u8)eb;
+    a.out_exts[i + a.out0] = (u8)eb;
+    if (a.out_start) { a.out_start[i + a.out0] = st; a.out_length[i + a.out0] = (u32)L; }
     u16 d;
     switch (a.reduce_op) {
         case DBG_REDUCE_SAT_ADD: d = (u16)(acc > 65535 ? 65535 : acc); break;
@@ -608,7 +611,7 @@ __global__ void emit_walk_kernel(KP kp, EmitWalkArgs a) {
         case DBG_REDUCE_ADD_MOD_65535: d = len == 1 ? (u16)acc : (u16)(acc % 65535); break;   // one k-mer: reduce() never called (:495)
         default: d = (u16)acc; break;
     }
-    a.out_data[i] = d;
+    a.out_data[i + a.out0] = d;
 }
 
 template <int W>
@@ -687,7 +690,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
             TRY(exclusive_scan_u64(c, node_len.p, ostart.p, M, nullptr));
             CU(c, cudaEventRecord(c->ev[3], st));
             EmitWalkArgs ea;
-            ea.lo = t->lo; ea.hi = t->hi; ea.rec = rec16.p; ea.pkey = rk; ea.pval = rv; ea.node_start = ostart.p; ea.i0 = 0; ea.n_nodes = M;
+            ea.lo = t->lo; ea.hi = t->hi; ea.rec = rec16.p; ea.pkey = rk; ea.pval = rv; ea.node_start = ostart.p; ea.i0 = 0; ea.n_nodes = M; ea.out0 = 0; ea.base0 = 0; ea.out_start = nullptr; ea.out_length = nullptr;
             ea.key_shift = key_shift; ea.words = words.p; ea.out_exts = oexts.p; ea.out_data = odata.p; ea.reduce_op = reduce_op;
             emit_walk_kernel<W><<<grid_for(M, 128), 128, 0, st>>>(kp, ea);
             TRY(check_launch(c, "emit_walk"));
@@ -967,18 +970,33 @@ int cs_layout_dev(Ctx* c, int k, u64 V, u64 m, u64* pkey_a, u32* pval_a, u64* pk
     return DBG_OK;
 }
 
-int cs_emit_dev(Ctx* c, const Table* t, const uint4* d_rec16, const u64* d_pkey, const u32* d_pval, const u64* d_start, u64 i0,
-                u64 i1, int reduce_op, u64* d_words, u8* d_exts, u16* d_data) {
-    if (i1 <= i0) return DBG_OK;
+// sort path records by seed only (pre-sort before they are shipped to the rank owning the seed range)
+int cs_sort_paths_dev(Ctx* c, u64 m, u64* pkey_a, u32* pval_a, u64* pkey_b, u32* pval_b, int* which) {
+    *which = 0;
+    if (m <= 1) return DBG_OK;
+    TRY(arena_begin(c));
+    u64 *rk, *rh;
+    u32* rv;
+    TRY(radix_sort_pairs(c, 1, 64, m, pkey_a, nullptr, pval_a, pkey_b, nullptr, pval_b, &rk, &rh, &rv));
+    *which = rk == pkey_a ? 0 : 1;
+    return DBG_OK;
+}
+
+// The m path records (sorted by seed, local offsets in d_start) become nodes node0 .. node0 + m of the graph, their
+// bases starting at base0 + d_start[i]: words / exts / data / start / length are written at the GLOBAL positions of
+// full-size arrays (zeroed by the caller, all-reduced afterwards).
+int cs_emit_dev(Ctx* c, const Table* t, const uint4* d_rec16, const u64* d_pkey, const u32* d_pval, const u64* d_start, u64 m,
+                u64 node0, u64 base0, int reduce_op, u64* d_words, u8* d_exts, u16* d_data, u64* d_out_start, u32* d_out_length) {
+    if (m == 0) return DBG_OK;
     KP kp = make_kp(t->k);
     EmitWalkArgs ea;
     ea.lo = t->lo; ea.hi = t->hi; ea.rec = d_rec16; ea.pkey = d_pkey; ea.pval = d_pval; ea.node_start = d_start;
-    ea.i0 = i0; ea.n_nodes = i1 - i0; ea.key_shift = cs_key_shift(t->n);
+    ea.i0 = 0; ea.n_nodes = m; ea.key_shift = cs_key_shift(t->n); ea.out0 = node0; ea.base0 = base0;
     ea.words = d_words; ea.out_exts = d_exts; ea.out_data = d_data; ea.reduce_op = reduce_op;
-    if (t->k <= 32) emit_walk_kernel<1><<<grid_for(i1 - i0, 128), 128, 0, c->stream>>>(kp, ea);
-    else emit_walk_kernel<2><<<grid_for(i1 - i0, 128), 128, 0, c->stream>>>(kp, ea);
-    TRY(check_launch(c, "emit_walk"));
-    return sync(c);
+    ea.out_start = d_out_start; ea.out_length = d_out_length;
+    if (t->k <= 32) emit_walk_kernel<1><<<grid_for(m, 128), 128, 0, c->stream>>>(kp, ea);
+    else emit_walk_kernel<2><<<grid_for(m, 128), 128, 0, c->stream>>>(kp, ea);
+    return check_launch(c, "emit_walk");
 }
 
 // Adopt caller-owned device arrays (copied) as a BaseGraph handle.

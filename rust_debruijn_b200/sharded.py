@@ -282,13 +282,16 @@ def _all_gather_uneven(t, sizes, itemsize, group, dev):
     return torch.cat([out[r * mx: r * mx + sizes[r] * itemsize] for r in range(world)])
 
 
-def compress_sharded(full, stranded, spec, group=None, lmax=1024, timings=None):
+def compress_sharded(full, stranded, spec, group=None, lmax=1024, timings=None, replicate=True):
     """compression::compress_kmers_with_hash over a table replicated on every rank, with the WORK split: links for
     the own k-mer index range (+ all-gather), 16-byte walk records, path discovery for the unitigs whose left end
     lies in the own range (+ all-gather of the path records), node layout (replicated, M entries), emission of the
     own slice of NODES into zeroed full-size arrays, one all-reduce (every bit has a single writer, so sum == OR).
-    Every rank returns the complete BaseGraph.  Unitigs longer than `lmax` k-mers and cycles are not handled here:
-    the function then returns None and the caller runs the replicated single-GPU compression instead."""
+    replicate=True: every rank returns the complete BaseGraph.  replicate=False: every rank returns ITS run of nodes
+    (attributes node0 / base0 = its position in the complete graph, n_nodes_total / n_bases_total); the runs
+    concatenated in rank order are the complete BaseGraph, bit for bit — no full-size arrays, no all-reduce.
+    Unitigs longer than `lmax` k-mers and cycles are not handled here: the function then returns None and the
+    caller runs the replicated single-GPU compression instead."""
     import torch
     import torch.distributed as dist
     ctx, L = full.ctx, full.ctx._L
@@ -328,52 +331,107 @@ def compress_sharded(full, stranded, spec, group=None, lmax=1024, timings=None):
         allc = allc.view(world, 2).tolist()
         if sum(int(x[1]) for x in allc) != V:
             return None   # long unitigs or cycles present: replicated fallback
-        counts = [int(x[0]) for x in allc]
-        M = sum(counts)
         mark(2)
-        # ---- node layout: all-gather the path records, sort by seed + scan (replicated; M entries only) ----
-        pk_all = _all_gather_uneven(pkey[:np_local].view(torch.uint8), counts, 8, group, dev)
-        pv_all = _all_gather_uneven(pval[:np_local].view(torch.uint8), counts, 4, group, dev)
-        pk_b = torch.empty(max(M, 1) * 8, dtype=torch.uint8, device=dev)
-        pv_b = torch.empty(max(M, 1) * 4, dtype=torch.uint8, device=dev)
-        start = torch.empty(max(M, 1), dtype=torch.int64, device=dev)
-        length = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
-        nb, which = C.c_uint64(), C.c_int()
-        ctx.check(L.dbg_cs_layout(ctx._h, k, V, M, C.c_void_p(pk_all.data_ptr()), C.c_void_p(pv_all.data_ptr()),
-                                  C.c_void_p(pk_b.data_ptr()), C.c_void_p(pv_b.data_ptr()), C.byref(which),
-                                  C.c_void_p(start.data_ptr()), C.c_void_p(length.data_ptr()), C.byref(nb)))
-        pk_s, pv_s = (pk_all, pv_all) if which.value == 0 else (pk_b, pv_b)
-        n_bases = nb.value
+        # ---- path records go to the rank that owns their SEED's index range: that rank ends up with a contiguous run
+        # of nodes in the final (ascending seed) order.  Pre-sort by seed so destinations are contiguous slices. ----
+        key_shift = 64 - max((V - 1).bit_length(), 1)
+        pk_b = torch.empty(max(np_local, 1), dtype=torch.int64, device=dev)
+        pv_b = torch.empty(max(np_local, 1), dtype=torch.int32, device=dev)
+        which = C.c_int()
+        ctx.check(L.dbg_cs_sort_paths(ctx._h, np_local, C.c_void_p(pkey.data_ptr()), C.c_void_p(pval.data_ptr()),
+                                      C.c_void_p(pk_b.data_ptr()), C.c_void_p(pv_b.data_ptr()), C.byref(which)))
+        pk_s, pv_s = ((pkey, pval) if which.value == 0 else (pk_b, pv_b))
+        pk_s, pv_s = pk_s[:np_local], pv_s[:np_local]
+        seeds = (pk_s >> key_shift) & ((1 << (64 - key_shift)) - 1)          # arithmetic shift: mask the sign fill
+        # seed-range splitters balanced by NODE count (a seed is the minimum index of its unitig, so seeds crowd the low
+        # indices): cumulative counts of the sorted local seeds at 4096 bin edges, all-reduced, cut at the quantiles
+        nbin = 4096
+        edges = torch.arange(nbin + 1, dtype=torch.int64, device=dev) * ((V + nbin - 1) // nbin)
+        cl = torch.searchsorted(seeds, edges, right=False)
+        cl[-1] = np_local
+        cg = cl.clone()
+        dist.all_reduce(cg, group=group)
+        targets = (cg[-1] * torch.arange(1, world, dtype=torch.int64, device=dev)) // world
+        cut = torch.searchsorted(cg, targets, right=False).clamp_(max=nbin)
+        cut = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), cut, torch.full((1,), nbin, dtype=torch.int64, device=dev)])
+        bnd = cl[cut]
+        sn = bnd[1:] - bnd[:-1]
+        rn = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(rn, sn, group=group)
+        both = torch.stack([sn, rn]).tolist()
+        send_n, recv_n = [int(x) for x in both[0]], [int(x) for x in both[1]]
+        m_own = sum(recv_n)
+        rk = torch.empty(max(m_own, 1), dtype=torch.int64, device=dev)
+        rv = torch.empty(max(m_own, 1), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(rk[:m_own], pk_s, recv_n, send_n, group=group)
+        dist.all_to_all_single(rv[:m_own], pv_s, recv_n, send_n, group=group)
+        # ---- own seed range: sort (P ascending runs -> one), lengths, local offsets ----
+        rk_b, rv_b = torch.empty_like(rk), torch.empty_like(rv)
+        start_l = torch.empty(max(m_own, 1), dtype=torch.int64, device=dev)
+        len_l = torch.empty(max(m_own, 1), dtype=torch.int32, device=dev)
+        nb = C.c_uint64()
+        ctx.check(L.dbg_cs_layout(ctx._h, k, V, m_own, C.c_void_p(rk.data_ptr()), C.c_void_p(rv.data_ptr()),
+                                  C.c_void_p(rk_b.data_ptr()), C.c_void_p(rv_b.data_ptr()), C.byref(which),
+                                  C.c_void_p(start_l.data_ptr()), C.c_void_p(len_l.data_ptr()), C.byref(nb)))
+        ok_s, ov_s = (rk, rv) if which.value == 0 else (rk_b, rv_b)
+        tot = torch.tensor([m_own, nb.value], dtype=torch.int64, device=dev)
+        allc = torch.empty(2 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, tot, group=group)
+        allc = allc.view(world, 2).tolist()
+        M = sum(int(x[0]) for x in allc)
+        n_bases = sum(int(x[1]) for x in allc)
+        node0 = sum(int(x[0]) for x in allc[:rank])
+        base0 = sum(int(x[1]) for x in allc[:rank])
         n_words = (n_bases + 31) // 32
         mark(3)
-        # ---- emission of the own slice of nodes, all-reduce ----
-        words = torch.zeros(n_words + 3, dtype=torch.int64, device=dev)
-        exts = torch.zeros(max(M, 1), dtype=torch.uint8, device=dev)
-        data = torch.zeros(max(M, 1), dtype=torch.int16, device=dev)
-        i0, i1 = (M * rank) // world, (M * (rank + 1)) // world
-        ctx.check(L.dbg_cs_emit(ctx._h, full._h, C.c_void_p(rec16.data_ptr()), C.c_void_p(pk_s.data_ptr()),
-                                C.c_void_p(pv_s.data_ptr()), C.c_void_p(start.data_ptr()), i0, i1, spec.func,
-                                C.c_void_p(words.data_ptr()), C.c_void_p(exts.data_ptr()), C.c_void_p(data.data_ptr())))
-        mark(4)
-        dist.all_reduce(words, group=group)
-        dist.all_reduce(exts, group=group)                      # single writer per node: sums have no carries
-        dist.all_reduce(data.view(torch.uint8), group=group)
         gh = C.c_void_p()
-        ctx.check(L.dbg_graph_from_device(ctx._h, k, int(bool(stranded)), M, n_bases, C.c_void_p(words.data_ptr()),
-                                          C.c_void_p(start.data_ptr()), C.c_void_p(length.data_ptr()),
-                                          C.c_void_p(exts.data_ptr()), C.c_void_p(data.data_ptr()), C.byref(gh)))
+        if replicate:
+            # ---- emission of the own nodes at their global positions, all-reduce ----
+            words = torch.zeros(n_words + 3, dtype=torch.int64, device=dev)
+            exts = torch.zeros(max(M, 1), dtype=torch.uint8, device=dev)
+            data = torch.zeros(max(M, 1), dtype=torch.int16, device=dev)
+            start = torch.zeros(max(M, 1), dtype=torch.int64, device=dev)
+            length = torch.zeros(max(M, 1), dtype=torch.int32, device=dev)
+            ctx.check(L.dbg_cs_emit(ctx._h, full._h, C.c_void_p(rec16.data_ptr()), C.c_void_p(ok_s.data_ptr()),
+                                    C.c_void_p(ov_s.data_ptr()), C.c_void_p(start_l.data_ptr()), m_own, node0, base0, spec.func,
+                                    C.c_void_p(words.data_ptr()), C.c_void_p(exts.data_ptr()), C.c_void_p(data.data_ptr()),
+                                    C.c_void_p(start.data_ptr()), C.c_void_p(length.data_ptr())))
+            mark(4)
+            for t_ in (words, start, length, exts, data.view(torch.uint8)):   # single writer per element: sum == the value
+                dist.all_reduce(t_, group=group)
+            ctx.check(L.dbg_graph_from_device(ctx._h, k, int(bool(stranded)), M, n_bases, C.c_void_p(words.data_ptr()),
+                                              C.c_void_p(start.data_ptr()), C.c_void_p(length.data_ptr()),
+                                              C.c_void_p(exts.data_ptr()), C.c_void_p(data.data_ptr()), C.byref(gh)))
+        else:
+            # ---- emission of the own run of nodes into arrays of its own size (start rebased to the run) ----
+            nb_own = nb.value
+            words = torch.zeros((nb_own + 31) // 32 + 3, dtype=torch.int64, device=dev)
+            exts = torch.empty(max(m_own, 1), dtype=torch.uint8, device=dev)
+            data = torch.empty(max(m_own, 1), dtype=torch.int16, device=dev)
+            ctx.check(L.dbg_cs_emit(ctx._h, full._h, C.c_void_p(rec16.data_ptr()), C.c_void_p(ok_s.data_ptr()),
+                                    C.c_void_p(ov_s.data_ptr()), C.c_void_p(start_l.data_ptr()), m_own, 0, 0, spec.func,
+                                    C.c_void_p(words.data_ptr()), C.c_void_p(exts.data_ptr()), C.c_void_p(data.data_ptr()),
+                                    None, None))
+            mark(4)
+            ctx.check(L.dbg_graph_from_device(ctx._h, k, int(bool(stranded)), m_own, nb_own, C.c_void_p(words.data_ptr()),
+                                              C.c_void_p(start_l.data_ptr()), C.c_void_p(len_l.data_ptr()),
+                                              C.c_void_p(exts.data_ptr()), C.c_void_p(data.data_ptr()), C.byref(gh)))
         mark(5)
     if ev:
         ctx.synchronize()
         timings.update(ms_cs_links=ev[0].elapsed_time(ev[1]), ms_cs_discover=ev[1].elapsed_time(ev[2]),
                        ms_cs_layout=ev[2].elapsed_time(ev[3]), ms_cs_emit=ev[3].elapsed_time(ev[4]),
                        ms_cs_allreduce=ev[4].elapsed_time(ev[5]), compress="sharded")
-    return BaseGraph(ctx, gh)
+    g = BaseGraph(ctx, gh)
+    g.node0, g.base0 = (0, 0) if replicate else (node0, base0)
+    g.n_nodes_total, g.n_bases_total, g.replicated = M, n_bases, bool(replicate)
+    return g
 
 
-def reads_to_graph_sharded(seqs, summarizer, spec, stranded=False, k=31, group=None, timings=None):
+def reads_to_graph_sharded(seqs, summarizer, spec, stranded=False, k=31, group=None, timings=None, replicate=True):
     """filter_kmers (bucket-sharded, one all-to-all) -> table gathered by key range -> compress_kmers_with_hash with the
-    work split over the ranks (replicated single-GPU compression when long unitigs / cycles are present)."""
+    work split over the ranks (replicated single-GPU compression when long unitigs / cycles are present).
+    replicate=False leaves every rank with its own run of nodes (see compress_sharded)."""
     import torch
     from .api import compress_kmers_with_hash
     ctx = seqs.ctx
@@ -384,9 +442,10 @@ def reads_to_graph_sharded(seqs, summarizer, spec, stranded=False, k=31, group=N
     full = gather_table(shard, group, timings=timings)
     t1.record(st)
     shard.free()
-    g = compress_sharded(full, stranded, spec, group=group, timings=timings)
-    if g is None:   # long unitigs / cycles: replicated single-GPU compression on every rank
+    g = compress_sharded(full, stranded, spec, group=group, timings=timings, replicate=replicate)
+    if g is None:   # long unitigs / cycles: replicated single-GPU compression on every rank (complete graph everywhere)
         g = compress_kmers_with_hash(stranded, spec, full)
+        g.node0, g.base0, g.n_nodes_total, g.n_bases_total, g.replicated = 0, 0, len(g), None, True
         if timings is not None:
             timings["compress"] = "replicated"
     t2.record(st)

@@ -38,10 +38,26 @@ for k, noisy, mo in ((a.k, True, 2), (a.k, False, 1), (63, True, 2)):
     ot = O.filter_kmers(k, words, start, length, min_obs=mo)
     og = O.compress_kmers(k, ot["lo"], ot["hi"], ot["exts"], ot["counts"])
     same = all(np.array_equal(gh[f], og[f]) for f in ("words", "start", "length", "exts", "data"))
-    ok &= same
+    # node-sharded output: every rank keeps its run of nodes; the runs concatenated in rank order must be the same graph
+    g2 = sharded.reads_to_graph_sharded(ss, D.CountFilter(mo), D.SimpleCompress(D.SAT_ADD), stranded=False, k=k, replicate=False)
+    h2 = g2.to_host()
+    part = dict(replicated=g2.replicated, node0=g2.node0, base0=g2.base0, n_bases=h2["n_bases"], start=h2["start"], length=h2["length"],
+                exts=h2["exts"], data=h2["data"], bases=O.unpack_bases(h2["words"], 0, h2["n_bases"]))
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(part, parts, dst=0)
+    same2 = True
+    if rank == 0:
+        if parts[0]["replicated"]:
+            parts = parts[:1]
+        cat = {f: np.concatenate([p_[f] for p_ in parts]) for f in ("length", "exts", "data", "bases")}
+        cat["start"] = np.concatenate([p_["start"] + np.uint64(p_["base0"]) for p_ in parts])
+        same2 = (all(np.array_equal(cat[f], og[f]) for f in ("start", "length", "exts", "data")) and
+                 np.array_equal(O.pack_bases(cat["bases"]), og["words"]) and
+                 [p_["node0"] for p_ in parts] == list(np.cumsum([0] + [len(p_["length"]) for p_ in parts[:-1]])))
+    ok &= same and same2
     if rank == 0:
         print(f"[sharded_check] world={world} k={k} noisy={noisy}: nodes={gh['n_nodes']} oracle={og['n_nodes']} "
-              f"{'BIT-EXACT' if same else 'MISMATCH'}  {tm}", flush=True)
+              f"{'BIT-EXACT' if same else 'MISMATCH'} node-sharded {'BIT-EXACT' if same2 else 'MISMATCH'}  {tm}", flush=True)
 flag = torch.tensor([0 if ok else 1], device=f"cuda:{local}")
 dist.all_reduce(flag)
 if a.bench_reads:
