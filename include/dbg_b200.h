@@ -65,6 +65,7 @@ typedef struct {
     float ms_filter_total, ms_compress_total;
     uint64_t n_records_distinct; /* super-k-mer records left after per-bucket deduplication (0 = dedup off) */
     uint64_t n_passes;           /* passes over the reads chosen by the memory planner (filter.rs:151-168) */
+    uint64_t direct_partition;   /* 1 = the last filter call wrote records straight into per-bucket regions (no staging / scatter) */
 } dbg_stats;
 
 /* ---- context ------------------------------------------------------------------------------------ */
@@ -73,7 +74,9 @@ void dbg_ctx_destroy(dbg_ctx* ctx);
 const char* dbg_last_error(const dbg_ctx* ctx);
 int dbg_stats_get(const dbg_ctx* ctx, dbg_stats* out);
 /* tunables: "msp_p" (minimizer length, 0 = auto), "bucket_occ" (target k-mer occurrences per MSP
- * bucket, 0 = auto), "dedup" (0 = off, 1 = 16-byte records [default], 2 = also 32-byte records), "mem_budget_bytes" (scratch budget of the pass planner, 0 = auto), "fast_compress" (1 = default; 0 = always use the general per-k-mer rank + emit
+ * bucket, 0 = auto), "dedup" (0 = off, 1 = 16-byte records [default], 2 = also 32-byte records), "mem_budget_bytes" (scratch budget of the pass planner, 0 = auto), "direct_partition" (1 = default: large contiguous inputs are
+ * partitioned straight into per-bucket regions sized by a sampling pass; 0 = always stage + scatter), "direct_min_tiles"
+ * (smallest input, in 4096-base tiles, that takes the direct partition; default 2048), "fast_compress" (1 = default; 0 = always use the general per-k-mer rank + emit
  * path of compress_kmers, which otherwise only runs when long unitigs or cycles are present). */
 int dbg_ctx_set_param(dbg_ctx* ctx, const char* name, int64_t value);
 int dbg_ctx_synchronize(dbg_ctx* ctx);

@@ -28,7 +28,7 @@ class Stats(C.Structure):
                                           "ms_emit")] +
                 [("msp_p", C.c_uint32), ("bucket_bits", C.c_uint32)] +
                 [(n, C.c_float) for n in ("ms_k_partition", "ms_k_count", "ms_filter_total", "ms_compress_total")] +
-                [("n_records_distinct", C.c_uint64), ("n_passes", C.c_uint64)])
+                [("n_records_distinct", C.c_uint64), ("n_passes", C.c_uint64), ("direct_partition", C.c_uint64)])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

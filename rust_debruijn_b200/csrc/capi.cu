@@ -184,6 +184,10 @@ int dbg_ctx_set_param(dbg_ctx* ctx, const char* name, int64_t value) {
         c->mem_budget_bytes = value > 0 ? (u64)value : 0;
     } else if (!strcmp(name, "valid_est_div")) {
         c->valid_est_div = value > 0 ? (u64)value : 0;
+    } else if (!strcmp(name, "direct_partition")) {
+        c->direct_partition = value ? 1 : 0;
+    } else if (!strcmp(name, "direct_min_tiles")) {
+        c->direct_min_tiles = value > 0 ? (u64)value : 0;
     } else if (!strcmp(name, "fast_compress")) {
         c->no_fast_compress = value ? 0 : 1;
     } else {

@@ -51,6 +51,10 @@ struct P1Args {
     u32 bk_lo, bk_span;  // this pass keeps records of buckets [bk_lo, bk_lo + bk_span) (multi-pass planner)
     u64* rec; u32* rec_bucket; u64 capacity;                 // staging
     u64* cursor; u32* bucket_count; u32* overflow;
+    // tile kernel only.  mode 0: records -> staging + bucket ids (scattered afterwards); mode 1: bucket histogram of the
+    // visited tiles only (sampling pass); mode 2: records straight into per-bucket regions [bucket_start[b], +bucket_cap[b])
+    int mode;
+    const u64* bucket_start; const u32* bucket_cap; u32* bucket_fill;
 };
 
 template <int W>
@@ -202,6 +206,7 @@ struct TileArgs {
     u64 total_end;  // global position one past the last base
     u64 tile0;      // first tile of this launch
     u64 n_tiles;    // one past the last tile of this launch
+    u32 tstride;    // visit every tstride-th tile (1 = all; > 1 = sampling pass)
 };
 
 __device__ __forceinline__ u32 s32_bits(const u32* s32, u32 b) {  // 32 bits starting at staged base b
@@ -233,7 +238,7 @@ __device__ __forceinline__ u64 seq_index_of(const u64* __restrict__ start, u64 n
 
 template <int W>
 __device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs& ta, int K, const u32* s_s32, const u32* s_bm,
-                                                 const u32* s_bk, u64 sb, u32 ofs, int ps, int nn, u64 slot) {
+                                                 u32 bkt, u64 sb, u32 ofs, int ps, int nn, u64 slot) {
     constexpr int RW = RecLayout<W>::WORDS;
     u32 eb = ofs + (u32)ps;            // staged index of the run's first base
     u32 nbase = (u32)nn + K - 1;
@@ -277,15 +282,16 @@ __device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs
         if (t > lastw) r[t] = 0;
     }
     r[RW - 1] |= hdr;
-    u32 bkt = s_bk[ps + (ps >> 4)];  // padded layout (bkpad)
     if constexpr (RW == 2) {
         *reinterpret_cast<ulonglong2*>(a.rec + slot * 2) = make_ulonglong2(r[0], r[1]);
     } else {
         *reinterpret_cast<ulonglong2*>(a.rec + slot * 4) = make_ulonglong2(r[0], r[1]);
         *reinterpret_cast<ulonglong2*>(a.rec + slot * 4 + 2) = make_ulonglong2(r[2], r[RW - 1]);
     }
-    a.rec_bucket[slot] = bkt;
-    atomicAdd(&a.bucket_count[bkt], 1u);
+    if (a.mode == 0) {
+        a.rec_bucket[slot] = bkt;
+        atomicAdd(&a.bucket_count[bkt], 1u);
+    }
 }
 
 __device__ __forceinline__ u32 bkpad(u32 x) { return x + (x >> 4); }  // padded index: lane stride 17 words, conflict-free
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = kp.k, p = a.p, wlen = K - p + 1;
 
-    for (u64 tile = ta.tile0 + blockIdx.x; tile < ta.n_tiles; tile += gridDim.x) {
+    for (u64 tile = ta.tile0 + (u64)blockIdx.x * ta.tstride; tile < ta.n_tiles; tile += (u64)gridDim.x * ta.tstride) {
         const u64 g0 = ta.base0 + tile * (u64)TP;                 // global position of tile-relative x = 0
         const u64 sb = (g0 > ta.base0 ? g0 - 1 : g0) & ~31ull;    // staged origin (32-base aligned), covers the left flank
         const u32 ofs = (u32)(g0 - sb);                           // staged index of x = 0
@@ -469,21 +475,67 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
             }
         }
         __syncthreads();
-        // ---- phase D: one exact reservation per tile, then one thread per record ----
+        // ---- phase D: one thread per record.  mode 0: one exact staging reservation per tile; mode 2: the record's slot
+        // comes from its bucket's own cursor (no staging, no scatter pass); mode 1: histogram only ----
         const u32 nq = s_qn;
         if (tid == 0) {
-            u64 s0 = nq ? atomicAdd(a.cursor, (u64)nq) : 0;
+            u64 s0 = (nq && a.mode == 0) ? atomicAdd(a.cursor, (u64)nq) : 0;
             s_slot0 = s0;
-            if (s0 + nq > a.capacity || nq > (u32)T1_QCAP) *a.overflow = 1;
+            if ((a.mode == 0 && s0 + nq > a.capacity) || nq > (u32)T1_QCAP) *a.overflow = 1;
         }
         __syncthreads();
         const u64 slot0 = s_slot0;
         for (u32 q = tid; q < nq && q < (u32)T1_QCAP; q += T1_THREADS) {
-            u32 ent = s_queue[q];
-            if (slot0 + q < a.capacity)
-                tile_emit_record<W>(a, ta, K, s_s32, s_bm, s_bk, sb, ofs, (int)(ent & 0xffffu), (int)(ent >> 16), slot0 + q);
+            const u32 ent = s_queue[q];
+            const int ps = (int)(ent & 0xffffu), nn = (int)(ent >> 16);
+            const u32 bkt = s_bk[bkpad((u32)ps)];
+            if (a.mode == 1) { atomicAdd(&a.bucket_count[bkt], 1u); continue; }
+            u64 slot = slot0 + q;
+            if (a.mode == 2) {
+                const u32 r = atomicAdd(&a.bucket_fill[bkt], 1u);
+                slot = a.bucket_start[bkt] + r;
+                // region (or the whole buffer) too small: drop the record, the host falls back to staging
+                if (r >= a.bucket_cap[bkt] || slot >= a.capacity) { *a.overflow = 1; continue; }
+            } else if (slot >= a.capacity) {
+                continue;
+            }
+            tile_emit_record<W>(a, ta, K, s_s32, s_bm, bkt, sb, ofs, ps, nn, slot);
         }
     }
+}
+
+// direct partition, between the sampling pass and the main pass: region capacity of every bucket from its sampled
+// count (estimate + 6 sigma of the thinning noise + slack)
+__global__ void bucket_caps_kernel(const u32* __restrict__ sample, u32 nb, float scale, u32* __restrict__ cap) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    float est = (float)sample[b] * scale;
+    cap[b] = (u32)(est + 6.0f * sqrtf(est * scale) + 64.0f);
+}
+// after the main pass: records actually stored per bucket (cursor clipped to the capacity) and their total
+__global__ void __launch_bounds__(256) bucket_fill_final_kernel(const u32* __restrict__ fill, const u32* __restrict__ cap,
+                                                                const u64* __restrict__ start, u64 bound, u32 nb,
+                                                                u32* __restrict__ cnt, u64* __restrict__ total) {
+    __shared__ u64 s_w[8];
+    u64 v = 0;
+    for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+        u32 c = min(fill[b], cap[b]);
+        const u64 s0 = start[b];
+        if (s0 + c > bound) c = s0 < bound ? (u32)(bound - s0) : 0u;   // (overflow case: results are discarded, stay in bounds)
+        cnt[b] = c;
+        v += c;
+    }
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 t = 0;
+        for (int w = 0; w < 8; w++) t += s_w[w];
+        if (t) atomicAdd(total, t);
+    }
+}
+__global__ void check_total_kernel(const u64* total, u64 bound, u32* overflow) {
+    if (*total > bound) *overflow = 1;
 }
 
 // records (staging order) -> per-bucket contiguous ranges
@@ -525,7 +577,7 @@ struct P2Args {
     u64* rec; u32* mult;  // records (deduplicated in place per bucket when mult != nullptr) and their multiplicities
     int mult_ready;       // records are already deduplicated (retry): bucket b holds dedup_cnt[b] records
     u32* dedup_cnt;       // per bucket: records left after deduplication
-    const u64* bucket_off; u32 n_buckets;
+    const u64* bucket_start; const u32* bucket_cnt; u32 n_buckets;   // bucket b = records [start[b], start[b] + cnt[b])
     u32 min_obs; int stranded; int report_all;
     int task_len;         // k-mers per task of the expansion loop (8, or 16 when records hold more than 32 k-mers)
     u64* out_lo; u64* out_hi; u32* out_val; u64 cap_valid;
@@ -613,8 +665,8 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
         __syncthreads();
         const u32 b = s_bucket;
         if (b >= a.n_buckets) break;
-        const u64 r0 = a.bucket_off[b];
-        u64 r1 = a.bucket_off[b + 1];
+        const u64 r0 = a.bucket_start[b];
+        u64 r1 = r0 + a.bucket_cnt[b];
         if (r0 == r1) continue;
         const bool small_bucket = (r1 - r0) * 63ull < (1ull << 24);   // no count can overflow the 24-bit field
         if constexpr (W == 1) {
@@ -1209,7 +1261,7 @@ static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, 
     TRY(bucket_fill.alloc(c, NB));
     TRY(ctr.alloc(c, 8));
     TileArgs ta;
-    ta.base0 = s->base0; ta.total_end = s->total_end; ta.tile0 = 0;
+    ta.base0 = s->base0; ta.total_end = s->total_end; ta.tile0 = 0; ta.tstride = 1;
     ta.n_tiles = use_tiles ? (s->total_end - s->base0 + TP - 1) / TP : 0;
     SeqSet* sm = const_cast<SeqSet*>(s);
     if (!use_tiles) TRY(seqset_ready(c, sm));
@@ -1234,6 +1286,7 @@ static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, 
         a.p = p; a.stranded = stranded; a.bucket_mask = NB - 1; a.maxk = maxk; a.bk_lo = bk_lo; a.bk_span = bk_span;
         a.rec = stage_rec.p; a.rec_bucket = stage_bucket.p; a.capacity = capacity;
         a.cursor = ctr.p; a.bucket_count = po.bucket_count.p; a.overflow = (u32*)(ctr.p + 1);
+        a.mode = 0; a.bucket_start = nullptr; a.bucket_cap = nullptr; a.bucket_fill = nullptr;
         CU(c, cudaEventRecord(c->ev[8], st));
         if (use_tiles && sm->n_pending > 0) {
             // pipelined upload: one launch per arrived chunk, covering the tiles whose bases (plus halo) are on the device
@@ -1278,6 +1331,97 @@ static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, 
     return DBG_OK;
 }
 
+// ---- P1 direct: sequences -> per-bucket regions without staging or scatter (contiguous layouts, one pass) ----
+// A sampling pass over ~1/16 of the tiles (bucket histogram only) sizes every bucket's region (estimate + 6 sigma of the
+// thinning noise + slack); the main pass then takes each record's slot from its bucket's own cursor and writes it in
+// place.  Nothing is read back here: the caller checks ctr[1] (a region, or the total, was too small -> staging path) and
+// ctr[2] (records stored) together with the counting stage's counters.
+struct DirectOut {
+    DBuf<u64> rec, bucket_start, ctr;   // ctr: [0] sum of capacities, [1] overflow flag, [2] records stored
+    DBuf<u32> cap, fill, cnt;
+    u64 rec_bound = 0;
+};
+
+template <int W>
+static int partition_direct(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, int p, int bbits, DirectOut& d) {
+    constexpr int RW = RecLayout<W>::WORDS;
+    KP kp = make_kp(k);
+    cudaStream_t st = c->stream;
+    const u32 NB = 1u << bbits;
+    SeqSet* sm = const_cast<SeqSet*>(s);
+    TileArgs ta;
+    ta.base0 = s->base0; ta.total_end = s->total_end; ta.tile0 = 0; ta.tstride = 1;
+    ta.n_tiles = (s->total_end - s->base0 + TP - 1) / TP;
+    // expected records: one per (K-p+2)/2 k-mers (window of K-p+1 p-mers); 3.5x covers read ends, length caps and the
+    // regions' slack — a larger need raises the overflow flag and the caller falls back to staging
+    d.rec_bound = (u64)(3.5 * 2.0 * (double)N / (double)(k - p + 2)) + (u64)NB * 64 + 4096;
+    TRY(d.rec.alloc(c, d.rec_bound * RW));
+    TRY(d.bucket_start.alloc(c, (u64)NB + 1));
+    TRY(d.cap.alloc(c, NB)); TRY(d.fill.alloc(c, NB)); TRY(d.cnt.alloc(c, NB)); TRY(d.ctr.alloc(c, 4));
+    TRY(d.cnt.zero()); TRY(d.fill.zero()); TRY(d.ctr.zero());
+    P1Args a;
+    a.words = s->words; a.n_words = s->n_words; a.start = s->start; a.length = s->length; a.seq_exts = s->seq_exts;
+    a.n_seqs = s->n_seqs; a.uniform_len = s->uniform_len;
+    a.item_seq = nullptr; a.item_j0 = nullptr; a.n_items = 0;
+    a.p = p; a.stranded = stranded; a.bucket_mask = NB - 1; a.maxk = rec_max_kmers(RW, k); a.bk_lo = 0; a.bk_span = NB;
+    a.rec = d.rec.p; a.rec_bucket = nullptr; a.capacity = d.rec_bound;
+    a.cursor = nullptr; a.bucket_count = d.cnt.p; a.overflow = (u32*)(d.ctr.p + 1);
+    a.bucket_start = d.bucket_start.p; a.bucket_cap = d.cap.p; a.bucket_fill = d.fill.p;
+    CU(c, cudaEventRecord(c->ev[8], st));
+    // ---- sampling pass (with a pipelined upload: over the first chunk, as soon as it has arrived) ----
+    const int np = sm->n_pending;
+    auto tiles_upto = [&](int ci) -> u64 {
+        if (ci == np - 1) return ta.n_tiles;
+        u64 bases_ok = sm->pend_words_end[ci] * 32;
+        u64 upto = bases_ok > (u64)(TP + 192) ? (bases_ok - 192 - s->base0) / TP : 0;
+        return std::min<u64>(upto, ta.n_tiles);
+    };
+    u64 t_s = ta.n_tiles;
+    if (np > 0) {
+        CU(c, cudaStreamWaitEvent(st, sm->pend_ev[0], 0));
+        t_s = tiles_upto(0);
+    }
+    const u32 stride = (u32)std::max<u64>(1, t_s * 16 / ta.n_tiles);
+    const u64 n_sampled = (t_s + stride - 1) / stride;
+    const float scale = (float)((double)ta.n_tiles / (double)std::max<u64>(n_sampled, 1));
+    {
+        TileArgs tc = ta;
+        tc.n_tiles = t_s; tc.tstride = stride;
+        a.mode = 1;
+        msp_tile_kernel<W><<<(u32)std::min<u64>(std::max<u64>(n_sampled, 1), (u64)c->sm_count * 6), T1_THREADS, 0, st>>>(kp, a, tc);
+        TRY(check_launch(c, "msp_partition_sample"));
+    }
+    bucket_caps_kernel<<<grid_for(NB, 256), 256, 0, st>>>(d.cnt.p, NB, scale, d.cap.p);
+    TRY(check_launch(c, "bucket_caps"));
+    TRY(exclusive_scan_u32_to_u64(c, d.cap.p, d.bucket_start.p, NB, d.ctr.p));
+    check_total_kernel<<<1, 1, 0, st>>>(d.ctr.p, d.rec_bound, (u32*)(d.ctr.p + 1));
+    TRY(check_launch(c, "check_total"));
+    // ---- main pass: records straight into their bucket's region ----
+    a.mode = 2;
+    if (np > 0) {
+        u64 done = 0;
+        for (int ci = 0; ci < np; ci++) {
+            CU(c, cudaStreamWaitEvent(st, sm->pend_ev[ci], 0));
+            const u64 upto = tiles_upto(ci);
+            if (upto > done) {
+                TileArgs tc = ta;
+                tc.tile0 = done; tc.n_tiles = upto;
+                msp_tile_kernel<W><<<(u32)std::min<u64>(upto - done, (u64)c->sm_count * 6), T1_THREADS, 0, st>>>(kp, a, tc);
+                TRY(check_launch(c, "msp_partition"));
+                done = upto;
+            }
+        }
+        sm->n_pending = 0;
+    } else {
+        msp_tile_kernel<W><<<(u32)std::min<u64>(ta.n_tiles, (u64)c->sm_count * 6), T1_THREADS, 0, st>>>(kp, a, ta);
+        TRY(check_launch(c, "msp_partition"));
+    }
+    CU(c, cudaEventRecord(c->ev[9], st));
+    bucket_fill_final_kernel<<<(u32)std::min<u64>(grid_for(NB, 256), (u64)c->sm_count * 4), 256, 0, st>>>(d.fill.p, d.cap.p, d.bucket_start.p, d.rec_bound, NB, d.cnt.p, d.ctr.p + 2);
+    TRY(check_launch(c, "bucket_fill_final"));
+    return DBG_OK;
+}
+
 // Valid / distinct k-mers emitted by the counting stage (unordered), kept across the passes of one filter call.
 struct CountOut {
     DBuf<u64> v_lo, v_hi, a_lo, a_hi, ctr;
@@ -1309,8 +1453,8 @@ static int count_alloc(Ctx* c, u64 N, u32 min_obs, int report_all, bool exact_bo
 // ---- P2: bucket-contiguous records -> (unordered) valid k-mers appended to co.  Returns DBG_OK and sets
 // *overflow when the valid / all buffers were too small (the caller retries with the exact bound). ----
 template <int W>
-static int count_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucket_off, u32 NB, u32 min_obs, int stranded,
-                       int report_all, CountOut& co, bool* overflow) {
+static int count_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucket_start, const u32* bucket_cnt, u32 NB, u32 min_obs,
+                       int stranded, int report_all, CountOut& co, bool* overflow) {
     KP kp = make_kp(k);
     cudaStream_t st = c->stream;
     *overflow = false;
@@ -1322,7 +1466,7 @@ static int count_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucket_off
     CU(c, cudaMemsetAsync(co.ctr.p + 3, 0, 24, st));
     P2Args a;
     a.rec = rec; a.mult = dedup ? mult.p : nullptr; a.mult_ready = 0; a.dedup_cnt = dedup_cnt.p;
-    a.bucket_off = bucket_off; a.n_buckets = NB;
+    a.bucket_start = bucket_start; a.bucket_cnt = bucket_cnt; a.n_buckets = NB;
     a.min_obs = min_obs; a.stranded = stranded; a.report_all = report_all;
     a.task_len = rec_max_kmers(RecLayout<W>::WORDS, k) <= 32 ? 8 : 16;
     a.out_lo = co.v_lo.p; a.out_hi = co.v_hi.p; a.out_val = co.v_val.p; a.cap_valid = co.cap_valid;
@@ -1456,6 +1600,12 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     const int n_pass = plan_passes(c, N, mem_gb, NB);
     S.n_passes = n_pass;
     float ms_part = 0, ms_cnt = 0;
+    // direct partition (no staging, no scatter pass): contiguous layouts, one pass, enough tiles for the sampling pass
+    const u64 n_tiles_all = (s->contiguous && s->total_end > s->base0) ? (s->total_end - s->base0 + TP - 1) / TP : 0;
+    // (a pipelined upload keeps the staging path: its sampling pass could only look at the first chunk, which is not a
+    // uniform sample of position-sorted input, and a mispredicted region costs a second partition + count)
+    bool use_direct = c->direct_partition && n_pass == 1 && n_tiles_all >= c->direct_min_tiles && s->n_pending == 0;
+    S.direct_partition = 0;
     for (int attempt = 0;; attempt++) {
         c->arena_off = 0;
         S.ms_k_count = 0; S.ms_k_partition = 0; S.n_records = 0;
@@ -1463,18 +1613,32 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
         CountOut co;
         TRY(count_alloc<W>(c, N, min_obs, report_all, attempt > 0, co));
         const u64 mark = c->arena_off;
-        bool overflow = false;
+        bool overflow = false, direct_failed = false;
         for (int pass = 0; pass < n_pass && !overflow; pass++) {
             const u32 lo = (u32)((u64)NB * pass / n_pass), hi = (u32)((u64)NB * (pass + 1) / n_pass);
-            {
+            if (use_direct) {
+                DirectOut d;
+                CU(c, cudaEventRecord(c->ev[4], st));
+                TRY(partition_direct<W>(c, k, s, stranded, N, p, bbits, d));
+                CU(c, cudaEventRecord(c->ev[5], st));
+                TRY(count_stage<W>(c, k, d.rec.p, d.rec_bound, d.bucket_start.p, d.cnt.p, NB, min_obs, stranded, report_all, co, &overflow));
+                CU(c, cudaEventRecord(c->ev[6], st));
+                u64 h[3];
+                TRY(read_u64(c, d.ctr.p, h, 3));
+                if ((u32)h[1]) { direct_failed = true; break; }   // a region (or the total) was too small: redo through staging
+                S.n_records += h[2];
+                S.direct_partition = 1;
+            } else {
                 PartOut po;
                 CU(c, cudaEventRecord(c->ev[4], st));
                 TRY(partition_stage<W>(c, k, s, stranded, N, max_len, p, bbits, lo, hi - lo, false, po));
                 S.n_records += po.n_rec;
                 CU(c, cudaEventRecord(c->ev[5], st));
-                TRY(count_stage<W>(c, k, po.rec.p, po.n_rec, po.bucket_off.p, NB, min_obs, stranded, report_all, co, &overflow));
+                TRY(count_stage<W>(c, k, po.rec.p, po.n_rec, po.bucket_off.p, po.bucket_count.p, NB, min_obs, stranded, report_all, co, &overflow));
                 CU(c, cudaEventRecord(c->ev[6], st));
                 TRY(sync(c));
+            }
+            {
                 float a1 = 0, a2 = 0, a3 = 0;
                 cudaEventElapsedTime(&a1, c->ev[4], c->ev[5]);
                 cudaEventElapsedTime(&a2, c->ev[5], c->ev[6]);
@@ -1483,6 +1647,7 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
             }
             c->arena_off = mark;  // every per-pass buffer is gone
         }
+        if (direct_failed) { use_direct = false; attempt--; continue; }
         if (!overflow) {
             CU(c, cudaEventRecord(c->ev[2], st));
             TRY(sort_stage<W>(c, k, report_all, co, t));
@@ -1632,7 +1797,11 @@ int filter_from_records_dev(Ctx* c, int k, const u64* d_records, u64 n_records, 
     S.n_records = n_records;
     if (n_records == 0) return DBG_OK;
     DBuf<u64> d_off, d_gsrc, d_gdst, merged;
-    DBuf<u32> d_gcnt;
+    DBuf<u32> d_gcnt, d_bcnt;
+    std::vector<u32> h_bcnt(n_local);
+    for (u32 b = 0; b < n_local; b++) h_bcnt[b] = (u32)(h_off[b + 1] - h_off[b]);
+    TRY(d_bcnt.alloc(c, n_local));
+    CU(c, cudaMemcpyAsync(d_bcnt.p, h_bcnt.data(), (u64)n_local * 4, cudaMemcpyHostToDevice, st));
     TRY(d_off.alloc(c, n_local + 1)); TRY(d_gsrc.alloc(c, n_groups)); TRY(d_gdst.alloc(c, n_groups)); TRY(d_gcnt.alloc(c, n_groups));
     TRY(merged.alloc(c, n_records * RW));
     CU(c, cudaMemcpyAsync(d_off.p, h_off.data(), (n_local + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1661,11 +1830,11 @@ int filter_from_records_dev(Ctx* c, int k, const u64* d_records, u64 n_records, 
         bool overflow = false;
         if (k <= 32) {
             rc = count_alloc<1>(c, N_local_bound, min_obs, report_all, attempt > 0, co);
-            if (rc == DBG_OK) rc = count_stage<1>(c, k, merged.p, n_records, d_off.p, n_local, min_obs, stranded, report_all, co, &overflow);
+            if (rc == DBG_OK) rc = count_stage<1>(c, k, merged.p, n_records, d_off.p, d_bcnt.p, n_local, min_obs, stranded, report_all, co, &overflow);
             if (rc == DBG_OK && !overflow) { cudaEventRecord(c->ev[2], st); rc = sort_stage<1>(c, k, report_all, co, t); }
         } else {
             rc = count_alloc<2>(c, N_local_bound, min_obs, report_all, attempt > 0, co);
-            if (rc == DBG_OK) rc = count_stage<2>(c, k, merged.p, n_records, d_off.p, n_local, min_obs, stranded, report_all, co, &overflow);
+            if (rc == DBG_OK) rc = count_stage<2>(c, k, merged.p, n_records, d_off.p, d_bcnt.p, n_local, min_obs, stranded, report_all, co, &overflow);
             if (rc == DBG_OK && !overflow) { cudaEventRecord(c->ev[2], st); rc = sort_stage<2>(c, k, report_all, co, t); }
         }
         if (!overflow) break;

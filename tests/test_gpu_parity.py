@@ -247,6 +247,27 @@ def test_valid_buffer_retry(D, ctx, orc):
     c2.close()
 
 
+def test_direct_partition_and_staging_agree(D, ctx, orc):
+    """The partition stage writes records straight into per-bucket regions sized by a sampling pass (large contiguous
+    inputs) or stages + scatters them (everything else, and the fallback when a region overflows).  Same bits: direct
+    forced on small inputs (few tiles: poor estimates, overflow -> fallback exercised too), direct off, both key widths."""
+    ss = orc.synth_reads(6000, 1, orc.ERR_THR_NOISY)
+    c2 = D.Context(0)
+    c2.set_param("direct_min_tiles", 1)
+    t, _ = run_both(D, c2, orc, 31, ss, 2, report_all=True)
+    st = c2.stats()
+    run_both(D, c2, orc, 63, ss, 2)
+    run_both(D, c2, orc, 31, orc.synth_reads(300, 1, 0), 1)          # 11 tiles: the sample sees almost nothing
+    seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGAGGATCCA")
+    run_both(D, c2, orc, 31, orc.seqset_from_lists([seq] * 3000 + [random_dna(np.random.default_rng(5), 4000)]), 1)   # one heavy bucket
+    c2.set_param("direct_partition", 0)
+    t2, _ = run_both(D, c2, orc, 31, ss, 2, report_all=True)
+    assert c2.stats()["direct_partition"] == 0
+    assert_tables_equal(t, t2)
+    c2.close()
+    assert st["n_records"] > 0
+
+
 def test_general_compress_path_forced(D, ctx, orc):
     """compress_kmers has a fast path (all components are short paths: one walker per node) and a general path
     (per-k-mer rank + emit; long unitigs, cycles).  Same bits when the general path is forced on data the fast
