@@ -41,16 +41,36 @@ def env_int(name, default):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  Sampled in-process through
+    NVML (two light calls every 20 ms): an `nvidia-smi -lms` child polling power / reasons was measured to stall this
+    process's kernel launches by tens of milliseconds per poll on the shared box.  nvidia-smi is only the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv, self.h, self.stop_flag = index, [], None, None, None, False
+        self.sm, self.reasons, self.mx = [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it lists integers
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
 
     def start(self):
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -60,11 +80,34 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.h))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -83,7 +126,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def hbm_peak():
@@ -249,16 +292,23 @@ def main():
         barrier()
         clocks = sampler.stop() if not args.no_clocks else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler off"]}
         print(f"[bench] rank {rank} per-step wall ms: {walls}", file=sys.stderr)
-        return e0.elapsed_time(e1), st0, ctx.stats(), clocks
+        return e0.elapsed_time(e1), st0, ctx.stats(), clocks, walls
 
-    ms_total, st0, st1, clocks = timed_run()
+    def disturbed(walls):
+        """Host interference on the shared box shows as isolated steps far above the median (the kernels themselves
+        repeat to within 1%): such a run is re-measured ONCE (B200_PROFILING.md timing hygiene); both numbers are kept."""
+        flag = torch.tensor([1.0 if max(walls) > 1.25 * statistics.median(walls) else 0.0], device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)   # every rank must take the same decision
+        return bool(flag.item())
+
+    ms_total, st0, st1, clocks, walls = timed_run()
     remeasured = None
     bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks.get("reasons", []))
-    if world == 1 and (bad or ms_total / args.steps > 1.6 * (st1["ms_filter_total"] + st1["ms_compress_total"])):
-        # a throttled run, or one whose wall time is far above the sum of its own device stage timers (host
-        # interference on a shared box), is re-measured ONCE (B200_PROFILING.md timing hygiene); both are kept
-        remeasured = {"first_ms_per_step": ms_total / args.steps, "reason": sorted(bad) or ["wall >> device stage time"]}
-        ms_total, st0, st1, clocks = timed_run()
+    if (world == 1 and bad) or disturbed(walls):
+        remeasured = {"first_ms_per_step": ms_total / args.steps, "reason": sorted(bad) or ["isolated slow steps: host interference"],
+                      "first_walls_ms": walls}
+        ms_total, st0, st1, clocks, walls = timed_run()
     n_kmers = R * (150 - K + 1)
 
     # ---- e2e: host pinned buffers in, BaseGraph arrays out, through the C-ABI host entry point ----
@@ -296,15 +346,28 @@ def main():
         L.dbg_graph_free(gh)
         return m, nw
 
-    e2e_step()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(ext)
-    for _ in range(args.steps):
-        m_nodes, n_gw = e2e_step()
-    f1.record(ext)
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
+    for _ in range(args.warmup):   # same W untimed steps as the device-resident arm (the scratch arena re-sizes itself once
+        e2e_step()                 # for this entry point's allocation pattern: not part of the steady state)
+
+    def timed_e2e():
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(ext)
+        ws, res = [], None
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            res = e2e_step()
+            ws.append(round((time.perf_counter() - t0) * 1e3, 2))
+        f1.record(ext)
+        barrier()
+        print(f"[bench] rank {rank} e2e per-step wall ms: {ws}", file=sys.stderr)
+        return f0.elapsed_time(f1), ws, res
+
+    ms_e2e, e2e_walls, (m_nodes, n_gw) = timed_e2e()
+    e2e_remeasured = None
+    if disturbed(e2e_walls):
+        e2e_remeasured = {"first_ms_per_step": ms_e2e / args.steps, "first_walls_ms": e2e_walls}
+        ms_e2e, e2e_walls, (m_nodes, n_gw) = timed_e2e()
     h2d = int(len(words_pinned) * 8)
     d2h = int(n_gw * 8 + m_nodes * (8 + 4 + 1 + 2))
 
@@ -347,7 +410,7 @@ def main():
                        "sharded_stage_ms": {k_: (round(v, 3) if isinstance(v, float) else v) for k_, v in last_tm.items()}},
             "clocks": clocks, "remeasured": remeasured,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "remeasured": e2e_remeasured},
             "gpu_launches": int(st1["gpu_launches"] - st0["gpu_launches"]),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "peak_kind": peak_kind, "traffic": tr.get(dom),

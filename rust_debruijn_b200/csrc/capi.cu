@@ -481,7 +481,7 @@ static int table_from_arrays(dbg_ctx* ctx, int k, uint64_t n, const void* kmers_
     T2(check_launch(c, "check_sorted_unique"));
     u32 hbad = 0;
     CU2(cudaMemcpyAsync(c->h_scratch, bad.p, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU2(cudaStreamSynchronize(c->stream));
+    CU2(spin_sync(c->stream));
     hbad = *(u32*)c->h_scratch;
     if (hbad) { c->err = "duplicate k-mers in table"; return fail(DBG_E_BADARG); }
     t->lo = (rlo == alo.p) ? alo.take() : blo.take();
@@ -534,7 +534,7 @@ int dbg_table_from_device_sorted(dbg_ctx* ctx, int k, uint64_t n, const void* d_
     check_sorted_unique_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(lo.p, two ? hi.p : nullptr, n, bad.p);
     c->launches++;
     cudaMemcpyAsync(c->h_scratch, bad.p, 4, cudaMemcpyDeviceToHost, c->stream);
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { delete h; DBG_SET_ERR(c, DBG_E_CUDA, "table_from_device_sorted: %s", cudaGetErrorString(cudaGetLastError())); }
+    if (spin_sync(c->stream) != cudaSuccess) { delete h; DBG_SET_ERR(c, DBG_E_CUDA, "table_from_device_sorted: %s", cudaGetErrorString(cudaGetLastError())); }
     if (*(u32*)c->h_scratch) { delete h; DBG_SET_ERR(c, DBG_E_BADARG, "arrays are not ascending and distinct"); }
     t->lo = lo.take();
     if (two) t->hi = hi.take();
@@ -779,7 +779,7 @@ int dbg_reads_to_graph_host_uniform(dbg_ctx* ctx, int k, const uint64_t* words, 
     int rc = upload_uniform_impl(ctx, words, n_words, n_seqs, read_len, seq_exts, true, &s);
     if (rc != DBG_OK) return rc;
     rc = dbg_reads_to_graph(ctx, k, s, min_kmer_obs, stranded, reduce_op, table_out, graph_out);
-    cudaStreamSynchronize(ctx->c.copy_stream);
+    spin_sync(ctx->c.copy_stream);
     dbg_seqset_free(s);
     return rc;
 }

@@ -147,14 +147,22 @@ inline int arena_begin(Ctx* c) {
     return DBG_OK;
 }
 
+// Host waits spin on cudaStreamQuery instead of blocking in cudaStreamSynchronize: the path has ~10 short waits per call
+// (sizes read back between stages), and on a shared host a thread that went to sleep in the driver can take tens of
+// milliseconds to be scheduled again — far longer than the kernels it waits for.
+inline cudaError_t spin_sync(cudaStream_t st) {
+    cudaError_t e;
+    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {}
+    return e;
+}
 inline int sync(Ctx* c) {
-    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, spin_sync(c->stream));
     return DBG_OK;
 }
 // Read a few u64 from the device (blocking).
 inline int read_u64(Ctx* c, const void* dptr, u64* out, int count = 1) {
     CU(c, cudaMemcpyAsync(c->h_scratch, dptr, 8 * count, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, spin_sync(c->stream));
     for (int i = 0; i < count; i++) out[i] = c->h_scratch[i];
     return DBG_OK;
 }

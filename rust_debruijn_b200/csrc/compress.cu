@@ -1023,7 +1023,7 @@ int graph_from_device_dev(Ctx* c, int k, int stranded, u64 n_nodes, u64 n_bases,
     cudaMemcpyAsync(olen.p, d_length, n_nodes * 4, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(odata.p, d_data, n_nodes * 2, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(oexts.p, d_exts, n_nodes, cudaMemcpyDeviceToDevice, st);
-    if (cudaStreamSynchronize(st) != cudaSuccess) {
+    if (spin_sync(st) != cudaSuccess) {
         free_graph(g); *out = nullptr;
         DBG_SET_ERR(c, DBG_E_CUDA, "graph_from_device: %s", cudaGetErrorString(cudaGetLastError()));
     }

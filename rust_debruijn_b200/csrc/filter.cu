@@ -309,18 +309,38 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = kp.k, p = a.p, wlen = K - p + 1;
 
-    for (u64 tile = ta.tile0 + (u64)blockIdx.x * ta.tstride; tile < ta.n_tiles; tile += (u64)gridDim.x * ta.tstride) {
+    // the (at most T1_S32 / 2 = 134) packed words of a tile are one load per thread: the NEXT tile's word is fetched into
+    // a register while the current tile is processed, so no tile starts by waiting on HBM
+    constexpr u32 NWST = T1_S32 / 2;
+    static_assert(NWST <= T1_THREADS, "one staged word per thread");
+    auto tile_origin = [&](u64 tile) -> u64 {
+        const u64 g = ta.base0 + tile * (u64)TP;
+        return (g > ta.base0 ? g - 1 : g) & ~31ull;
+    };
+    const u64 tile_step = (u64)gridDim.x * ta.tstride;
+    u64 pre = 0;
+    {
+        const u64 tile_first = ta.tile0 + (u64)blockIdx.x * ta.tstride;
+        if (tile_first < ta.n_tiles && tid < (int)NWST) {
+            const u64 wi = (tile_origin(tile_first) >> 5) + tid;
+            pre = wi < a.n_words ? a.words[wi] : 0;
+        }
+    }
+    for (u64 tile = ta.tile0 + (u64)blockIdx.x * ta.tstride; tile < ta.n_tiles; tile += tile_step) {
         const u64 g0 = ta.base0 + tile * (u64)TP;                 // global position of tile-relative x = 0
         const u64 sb = (g0 > ta.base0 ? g0 - 1 : g0) & ~31ull;    // staged origin (32-base aligned), covers the left flank
         const u32 ofs = (u32)(g0 - sb);                           // staged index of x = 0
         const u32 nbits = ofs + TP + K + 2;                       // staged indices that may be touched
         __syncthreads();
         // ---- stage bases (u32, base order) and the sequence-boundary bitmap ----
-        for (u32 t = tid; t < (nbits + 31) / 32 + 2; t += T1_THREADS) {
-            u64 wi = (sb >> 5) + t;
-            u64 v = wi < a.n_words ? a.words[wi] : 0;
-            s_s32[2 * t] = (u32)(v >> 32);
-            s_s32[2 * t + 1] = (u32)v;
+        if (tid < (int)NWST) {
+            s_s32[2 * tid] = (u32)(pre >> 32);
+            s_s32[2 * tid + 1] = (u32)pre;
+            const u64 nt = tile + tile_step;
+            if (nt < ta.n_tiles) {
+                const u64 wi = (tile_origin(nt) >> 5) + tid;
+                pre = wi < a.n_words ? a.words[wi] : 0;
+            }
         }
         for (u32 t = tid; t < (u32)T1_BM; t += T1_THREADS) s_bm[t] = 0;
         if (tid == 0) {

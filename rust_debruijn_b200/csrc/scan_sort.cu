@@ -352,7 +352,7 @@ int radix_sort_pairs(Ctx* c, int W, int key_bits, u64 n, u64* lo_a, u64* hi_a, u
         TRY(check_launch(c, "rs_fixup"));
         u32 flag = 0;
         CU(c, cudaMemcpyAsync(c->h_scratch, tctr.p + 31, 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
+        CU(c, spin_sync(c->stream));
         flag = *(u32*)c->h_scratch;
         if (!flag) break;
         npass = passes;  // long equal-prefix runs (low-complexity data): sort on every digit (LSD passes are stable, so

@@ -39,13 +39,14 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "lts__t_sector_hit_rate.pct"]
 out.append("## ncu --set full --clock-control none --import-source on (one launch per kernel)\n")
-seen = {}
 traffic = {}
+best = collections.OrderedDict()   # one launch per kernel name: the longest (e.g. the main pass, not the sampling pass)
 for r in rr[2:]:
     name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "")
-    if name in seen:
-        continue
-    seen[name] = 1
+    dur = float(r[idx["gpu__time_duration.sum"]].replace(",", ""))
+    if name not in best or dur > best[name][0]:
+        best[name] = (dur, r)
+for name, (_, r) in best.items():
     out.append(f"### {name}\n\n| metric | value | unit |\n|---|---|---|")
     for w in want:
         if w in idx:
