@@ -331,7 +331,7 @@ def main():
     def e2e_step():
         gh = C.c_void_p()
         if world > 1:
-            sse = D.SeqSet.upload_uniform(ctx, words_pinned, len(hs), 150)
+            sse = D.SeqSet.upload_uniform(ctx, words_pinned, len(hs), 150, pipelined=True)
             ge = sharded.reads_to_graph_sharded(sse, filt, spec, stranded=False, k=K, replicate=False)
             sse.free()
             gh, ge._h = ge._h, None

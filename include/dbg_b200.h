@@ -92,6 +92,11 @@ int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, con
  * sequencer layout; no start/length arrays to transfer or validate. */
 int dbg_seqset_upload_uniform(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, uint64_t n_seqs, uint32_t read_len,
                               const uint8_t* seq_exts, dbg_seqset** out);
+/* Same, asynchronous: returns at once, the packed words go up in chunks on a copy stream and the partition stage of
+ * the next dbg_filter_kmers / dbg_partition_reads / dbg_reads_to_graph call starts on the chunks that have arrived.
+ * `words` (pinned host memory for real overlap) must stay valid and unchanged until that call has returned. */
+int dbg_seqset_upload_uniform_async(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, uint64_t n_seqs, uint32_t read_len,
+                                    const uint8_t* seq_exts, dbg_seqset** out);
 /* Wrap caller-owned DEVICE buffers (e.g. torch tensors) without copying. */
 int dbg_seqset_wrap_device(dbg_ctx* ctx, const uint64_t* d_words, uint64_t n_words, const uint64_t* d_start,
                            const uint32_t* d_length, const uint8_t* d_seq_exts, uint64_t n_seqs, uint32_t max_len,

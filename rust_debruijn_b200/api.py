@@ -112,14 +112,18 @@ class SeqSet:
         return SeqSet(ctx, h)
 
     @staticmethod
-    def upload_uniform(ctx, words, n_seqs, read_len, seq_exts=None):
+    def upload_uniform(ctx, words, n_seqs, read_len, seq_exts=None, pipelined=False):
+        """pipelined=True: asynchronous chunked upload overlapping the partition stage of the next call; `words` (pinned
+        for real overlap) must stay untouched until that call has returned (the SeqSet keeps a reference)."""
         words = np.ascontiguousarray(words, np.uint64)
         if seq_exts is not None:
             seq_exts = np.ascontiguousarray(seq_exts, np.uint8)
         h = C.c_void_p()
-        ctx.check(ctx._L.dbg_seqset_upload_uniform(ctx._h, _ptr(words), len(words), n_seqs, read_len, _ptr(seq_exts),
-                                                   C.byref(h)))
-        return SeqSet(ctx, h)
+        fn = ctx._L.dbg_seqset_upload_uniform_async if pipelined else ctx._L.dbg_seqset_upload_uniform
+        ctx.check(fn(ctx._h, _ptr(words), len(words), n_seqs, read_len, _ptr(seq_exts), C.byref(h)))
+        ss = SeqSet(ctx, h)
+        ss._keep = (words, seq_exts) if pipelined else None   # the asynchronous copies read these buffers
+        return ss
 
     @staticmethod
     def synth(ctx, n_reads, seed=1, err_thr=0):

@@ -11,6 +11,7 @@ namespace dbg {
 
 void free_seqset(SeqSet* s) {
     if (!s) return;
+    if (s->n_pending > 0) spin_sync(s->ctx->copy_stream);   // an asynchronous upload nobody consumed: let it land first
     for (int i = 0; i < 8; i++) if (s->pend_ev[i]) cudaEventDestroy(s->pend_ev[i]);
     if (s->owned) {
         cudaStream_t st = s->ctx->stream;
@@ -321,6 +322,11 @@ static int upload_uniform_impl(dbg_ctx* ctx, const uint64_t* words, uint64_t n_w
 int dbg_seqset_upload_uniform(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, uint64_t n_seqs, uint32_t read_len,
                               const uint8_t* seq_exts, dbg_seqset** out) {
     return upload_uniform_impl(ctx, words, n_words, n_seqs, read_len, seq_exts, false, out);
+}
+
+int dbg_seqset_upload_uniform_async(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, uint64_t n_seqs, uint32_t read_len,
+                                    const uint8_t* seq_exts, dbg_seqset** out) {
+    return upload_uniform_impl(ctx, words, n_words, n_seqs, read_len, seq_exts, true, out);
 }
 
 int dbg_seqset_wrap_device(dbg_ctx* ctx, const uint64_t* d_words, uint64_t n_words, const uint64_t* d_start,

@@ -529,8 +529,10 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
 __global__ void bucket_caps_kernel(const u32* __restrict__ sample, u32 nb, float scale, u32* __restrict__ cap) {
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
+    // thinning 1 : scale leaves Poisson-like noise of variance ~ scale * count; "+ scale" keeps the bound honest when the
+    // sample saw (almost) nothing of a small bucket
     float est = (float)sample[b] * scale;
-    cap[b] = (u32)(est + 6.0f * sqrtf(est * scale) + 64.0f);
+    cap[b] = (u32)(est + 6.0f * sqrtf(scale * (est + scale)) + 64.0f);
 }
 // after the main pass: records actually stored per bucket (cursor clipped to the capacity) and their total
 __global__ void __launch_bounds__(256) bucket_fill_final_kernel(const u32* __restrict__ fill, const u32* __restrict__ cap,
@@ -1624,7 +1626,8 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     const u64 n_tiles_all = (s->contiguous && s->total_end > s->base0) ? (s->total_end - s->base0 + TP - 1) / TP : 0;
     // (a pipelined upload keeps the staging path: its sampling pass could only look at the first chunk, which is not a
     // uniform sample of position-sorted input, and a mispredicted region costs a second partition + count)
-    bool use_direct = c->direct_partition && n_pass == 1 && n_tiles_all >= c->direct_min_tiles && s->n_pending == 0;
+    // Two-word keys keep staging as well: their buckets hold ~340 records, too few for a 1/16 sample to size tightly.
+    bool use_direct = c->direct_partition && W == 1 && n_pass == 1 && n_tiles_all >= c->direct_min_tiles && s->n_pending == 0;
     S.direct_partition = 0;
     for (int attempt = 0;; attempt++) {
         c->arena_off = 0;

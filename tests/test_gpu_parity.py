@@ -163,6 +163,24 @@ def test_uniform_upload_entry_point(D, ctx, orc):
         D.SeqSet.upload_uniform(ctx, w, 2501, 150)
 
 
+def test_pipelined_upload_matches_oracle(D, ctx, orc):
+    """Asynchronous chunked upload (>= 32 MB of packed reads: 8 chunks on the copy stream, the partition kernel starts on
+    the chunks that have arrived): table bit-identical to the oracle, through both entry points that use it."""
+    import ctypes as C
+    R = 900_000                                       # 4.2 M words: the smallest size that is actually chunked
+    w, s, l = orc.synth_reads(R, 3, orc.ERR_THR_NOISY)
+    ot = orc.filter_kmers(31, w, s, l, min_obs=2)
+    ss = D.SeqSet.upload_uniform(ctx, w, R, 150, pipelined=True)
+    table, _ = D.filter_kmers(ss, D.CountFilter(2), False, False, 4, k=31)
+    assert_tables_equal(table.to_host(), ot)
+    og = orc.compress_kmers(31, ot["lo"], ot["hi"], ot["exts"], ot["counts"])
+    gh = C.c_void_p()
+    L = ctx._L
+    ctx.check(L.dbg_reads_to_graph_host_uniform(ctx._h, 31, C.c_void_p(w.ctypes.data), len(w), R, 150, None, 2, 0, D.SAT_ADD,
+                                                None, C.byref(gh)))
+    assert_graphs_equal(D.BaseGraph(ctx, gh).to_host(), og)
+
+
 def test_count_saturation(D, ctx, orc):
     """filter.rs:57 counts saturate at 65535; compression.rs:495 single-k-mer node keeps raw data."""
     seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")
