@@ -92,6 +92,12 @@ int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, con
  * sequencer layout; no start/length arrays to transfer or validate. */
 int dbg_seqset_upload_uniform(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, uint64_t n_seqs, uint32_t read_len,
                               const uint8_t* seq_exts, dbg_seqset** out);
+/* Ingest — DnaString::from_acgt_bytes (src/dna_string.rs:224-250; AVX2 twin src/bitops_avx2.rs:8-132) for a batch of ASCII
+ * sequences, appended like PackedDnaStringSet::add (src/dna_string.rs:811-821): sequence i = ascii[start[i] .. +length[i])
+ * (host buffer, byte offsets); A/a C/c G/g T/t -> 0..3, anything else -> A; *n_invalid (optional) counts those.  The 2-bit
+ * packing runs on the device; the result is a contiguous sequence set ready for dbg_filter_kmers. */
+int dbg_seqset_from_ascii(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, const uint64_t* start, const uint32_t* length,
+                          const uint8_t* seq_exts, uint64_t n_seqs, uint64_t* n_invalid, dbg_seqset** out);
 /* Same, asynchronous: returns at once, the packed words go up in chunks on a copy stream and the partition stage of
  * the next dbg_filter_kmers / dbg_partition_reads / dbg_reads_to_graph call starts on the chunks that have arrived.
  * `words` (pinned host memory for real overlap) must stay valid and unchanged until that call has returned. */

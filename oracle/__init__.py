@@ -80,6 +80,30 @@ def pack_bases(bases):
     return words
 
 
+def acgt_to_bits(ascii_bytes):
+    """lib.rs:65-73 base_to_bits over a byte array: A/a=0 C/c=1 G/g=2 T/t=3, anything else 0.  Returns (bits, valid)."""
+    lut = np.zeros(256, np.uint8)
+    ok = np.zeros(256, bool)
+    for ch, v in ((b"A", 0), (b"C", 1), (b"G", 2), (b"T", 3)):
+        for c in (ch[0], ch.lower()[0]):
+            lut[c], ok[c] = v, True
+    a = np.frombuffer(bytes(ascii_bytes), np.uint8) if not isinstance(ascii_bytes, np.ndarray) else ascii_bytes
+    return lut[a], ok[a]
+
+
+def from_acgt_bytes(ascii_seqs):
+    """DnaString::from_acgt_bytes (dna_string.rs:224-250; AVX2 twin bitops_avx2.rs:48-132: same mapping, invalid -> A)
+    for every sequence, appended with PackedDnaStringSet::add (dna_string.rs:811-821).
+    Returns (words, start, length, n_invalid)."""
+    bits, n_bad = [], 0
+    for sq in ascii_seqs:
+        b, ok = acgt_to_bits(sq)
+        bits.append(b)
+        n_bad += int((~ok).sum())
+    w, st, ln = seqset_from_lists(bits)
+    return w, st, ln, n_bad
+
+
 def seqset_from_lists(seqs):
     """list of uint8 base arrays -> (words, start, length) in PackedDnaStringSet layout."""
     length = np.array([len(s) for s in seqs], dtype=np.uint32)

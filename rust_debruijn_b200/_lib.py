@@ -57,6 +57,7 @@ SIGNATURES = {
     "dbg_seqset_upload": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vpp]),
     "dbg_seqset_upload_uniform": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vpp]),
     "dbg_seqset_upload_uniform_async": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vpp]),
+    "dbg_seqset_from_ascii": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vpp]),
     "dbg_seqset_wrap_device": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.c_uint32, vpp]),
     "dbg_seqset_synth": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint32, vpp]),
     "dbg_seqset_len": (C.c_uint64, [vp]),

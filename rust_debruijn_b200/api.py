@@ -112,6 +112,25 @@ class SeqSet:
         return SeqSet(ctx, h)
 
     @staticmethod
+    def from_ascii(ctx, ascii_seqs, seq_exts=None):
+        """DnaString::from_acgt_bytes (src/dna_string.rs:224-250) for a list of ASCII sequences (bytes), packed on the
+        device like PackedDnaStringSet::add.  Non-ACGT characters become A; their number is left in .n_invalid."""
+        buf = b"".join(bytes(x) for x in ascii_seqs)
+        length = np.array([len(x) for x in ascii_seqs], np.uint32)
+        start = np.zeros(len(ascii_seqs), np.uint64)
+        if len(ascii_seqs) > 1:
+            start[1:] = np.cumsum(length[:-1], dtype=np.uint64)
+        arr = np.frombuffer(buf, np.uint8) if buf else np.zeros(0, np.uint8)
+        if seq_exts is not None:
+            seq_exts = np.ascontiguousarray(seq_exts, np.uint8)
+        h, bad = C.c_void_p(), C.c_uint64()
+        ctx.check(ctx._L.dbg_seqset_from_ascii(ctx._h, _ptr(arr) if len(arr) else None, len(arr), _ptr(start), _ptr(length),
+                                               _ptr(seq_exts), len(ascii_seqs), C.byref(bad), C.byref(h)))
+        ss = SeqSet(ctx, h)
+        ss.n_invalid = bad.value
+        return ss
+
+    @staticmethod
     def upload_uniform(ctx, words, n_seqs, read_len, seq_exts=None, pipelined=False):
         """pipelined=True: asynchronous chunked upload overlapping the partition stage of the next call; `words` (pinned
         for real overlap) must stay untouched until that call has returned (the SeqSet keeps a reference)."""

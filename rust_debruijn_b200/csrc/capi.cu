@@ -329,6 +329,114 @@ int dbg_seqset_upload_uniform_async(dbg_ctx* ctx, const uint64_t* words, uint64_
     return upload_uniform_impl(ctx, words, n_words, n_seqs, read_len, seq_exts, true, out);
 }
 
+// ---- ingest: DnaString::from_acgt_bytes (src/dna_string.rs:224-250, AVX2 twin src/bitops_avx2.rs:8-132) + PackedDnaStringSet::add
+// (src/dna_string.rs:811-821) for a whole batch of ASCII sequences.  Thread = one output word (32 bases of the
+// concatenation): finds the sequence holding its first base (binary search over the output offsets), then walks
+// the ASCII bytes, crossing sequence boundaries as needed.  A/a=0 C/c=1 G/g=2 T/t=3, anything else -> A (counted).
+__global__ void ascii_pack_kernel(const u8* __restrict__ ascii, const u64* __restrict__ in_start, const u64* __restrict__ out_start,
+                                  const u32* __restrict__ length, u64 n_seqs, u64 n_bases, u64* __restrict__ words,
+                                  u64* __restrict__ n_invalid) {
+    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 bad = 0;
+    if (w * 32 < n_bases) {
+        const u64 b0 = w * 32;
+        u64 lo = 0, hi = n_seqs;   // last sequence with out_start <= b0 (skips empty sequences sharing an offset)
+        while (lo < hi) { u64 m = (lo + hi) >> 1; if (out_start[m] <= b0) lo = m + 1; else hi = m; }
+        u64 si = lo - 1;
+        u64 off = b0 - out_start[si];
+        u64 out = 0;
+        const int nb = (int)min((u64)32, n_bases - b0);
+        for (int t = 0; t < nb; t++) {
+            while (off >= length[si]) { si++; off = 0; }
+            const u32 c = ascii[in_start[si] + off];
+            const u32 up = c & 0xDFu;   // fold case
+            const bool ok = up == 'A' || up == 'C' || up == 'G' || up == 'T';
+            u32 v = (c >> 1) & 3u;      // A 0, C 1, T 2, G 3
+            v ^= v >> 1;                // swap 2 <-> 3
+            if (!ok) { v = 0; bad++; }
+            out |= (u64)v << (62 - 2 * t);
+            off++;
+        }
+        words[w] = out;
+    }
+    for (int o = 16; o; o >>= 1) bad += __shfl_down_sync(0xffffffffu, bad, o);
+    __shared__ u32 s_bad[8];
+    if ((threadIdx.x & 31) == 0) s_bad[threadIdx.x >> 5] = bad;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += s_bad[i];
+        if (t) atomicAdd(n_invalid, (u64)t);   // one atomic per CTA
+    }
+}
+
+int dbg_seqset_from_ascii(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, const uint64_t* start, const uint32_t* length,
+                          const uint8_t* seq_exts, uint64_t n_seqs, uint64_t* n_invalid, dbg_seqset** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    Ctx* c = CTX(ctx);
+    *out = nullptr;
+    cudaSetDevice(c->device);
+    if (n_seqs && (!start || !length || !ascii)) DBG_SET_ERR(c, DBG_E_BADARG, "null argument");
+    std::vector<u64> ostart(n_seqs + 1, 0);
+    u32 max_len = 0;
+    bool uniform = n_seqs > 0;
+    for (u64 i = 0; i < n_seqs; i++) {
+        if ((u64)start[i] + length[i] > n_bytes) DBG_SET_ERR(c, DBG_E_BADARG, "sequence %llu runs past the ASCII buffer", (unsigned long long)i);
+        ostart[i + 1] = ostart[i] + length[i];
+        if (length[i] > max_len) max_len = length[i];
+        if (length[i] != length[0]) uniform = false;
+    }
+    const u64 n_bases = ostart[n_seqs], n_words = (n_bases + 31) / 32;
+    dbg_seqset* h = new (std::nothrow) dbg_seqset();
+    if (!h) DBG_SET_ERR(c, DBG_E_OOM, "host allocation failed");
+    SeqSet* s = &h->s;
+    memset(s->pend_ev, 0, sizeof(s->pend_ev));
+    s->ctx = c; s->n_seqs = n_seqs; s->n_words = n_words; s->max_len = max_len;
+    s->uniform_len = (uniform && n_seqs) ? length[0] : 0;
+    s->contiguous = n_seqs > 0; s->base0 = 0; s->total_end = n_bases;
+    DBuf<u64> dw, ds, din, dbad;
+    DBuf<u32> dl;
+    DBuf<u8> de, dasc;
+    int rc = arena_begin(c);
+    do {
+        if (rc != DBG_OK) break;
+        if ((rc = dw.alloc_pool(c, n_words + 2)) != DBG_OK) break;
+        if ((rc = dw.zero()) != DBG_OK) break;
+        if ((rc = ds.alloc_pool(c, n_seqs + 1)) != DBG_OK) break;
+        if ((rc = dl.alloc_pool(c, n_seqs)) != DBG_OK) break;
+        if ((rc = din.alloc(c, n_seqs)) != DBG_OK) break;
+        if ((rc = dasc.alloc(c, n_bytes)) != DBG_OK) break;
+        if ((rc = dbad.alloc(c, 1)) != DBG_OK) break;
+        if ((rc = dbad.zero()) != DBG_OK) break;
+        if (seq_exts) {
+            if ((rc = de.alloc_pool(c, n_seqs)) != DBG_OK) break;
+            if (n_seqs && cudaMemcpyAsync(de.p, seq_exts, n_seqs, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = DBG_E_CUDA; break; }
+        }
+        if (n_seqs) {
+            if (cudaMemcpyAsync(ds.p, ostart.data(), (n_seqs + 1) * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                cudaMemcpyAsync(dl.p, length, n_seqs * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                cudaMemcpyAsync(din.p, start, n_seqs * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                (n_bytes && cudaMemcpyAsync(dasc.p, ascii, n_bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)) { rc = DBG_E_CUDA; break; }
+        }
+        if (n_words) {
+            ascii_pack_kernel<<<grid_for(n_words, 256), 256, 0, c->stream>>>(dasc.p, din.p, ds.p, dl.p, n_seqs, n_bases, dw.p, dbad.p);
+            if ((rc = check_launch(c, "ascii_pack")) != DBG_OK) break;
+        }
+        u64 bad = 0;
+        if ((rc = read_u64(c, dbad.p, &bad)) != DBG_OK) break;   // also: ostart may go out of scope after this sync
+        if (n_invalid) *n_invalid = bad;
+    } while (0);
+    if (rc != DBG_OK) {
+        if (rc == DBG_E_CUDA) c->err = std::string("seqset_from_ascii: ") + cudaGetErrorString(cudaGetLastError());
+        delete h;
+        return rc;
+    }
+    s->words = dw.take(); s->start = ds.take(); s->length = dl.take();
+    if (seq_exts) s->seq_exts = de.take();
+    *out = h;
+    return DBG_OK;
+}
+
 int dbg_seqset_wrap_device(dbg_ctx* ctx, const uint64_t* d_words, uint64_t n_words, const uint64_t* d_start,
                            const uint32_t* d_length, const uint8_t* d_seq_exts, uint64_t n_seqs, uint32_t max_len,
                            dbg_seqset** out) {

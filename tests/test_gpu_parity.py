@@ -181,6 +181,29 @@ def test_pipelined_upload_matches_oracle(D, ctx, orc):
     assert_graphs_equal(D.BaseGraph(ctx, gh).to_host(), og)
 
 
+def test_from_ascii_ingest(D, ctx, orc):
+    """dbg_seqset_from_ascii = DnaString::from_acgt_bytes + PackedDnaStringSet::add on the device: packed words, offsets,
+    lengths and the invalid-character count identical to the oracle; the packed set then feeds filter_kmers."""
+    rng = np.random.default_rng(41)
+    alphabet = np.frombuffer(b"ACGTacgtNn-*X", np.uint8)
+    pr = np.array([.22, .22, .22, .22, .02, .02, .02, .02, .01, .01, .005, .005, .01])
+    seqs = [bytes(rng.choice(alphabet, size=n, p=pr / pr.sum())) for n in (0, 1, 31, 32, 33, 64, 150, 151, 0, 1000, 95, 4097, 7)]
+    ow, ost, oln, obad = orc.from_acgt_bytes(seqs)
+    ss = D.SeqSet.from_ascii(ctx, seqs)
+    w, st, ln = ss.copy_out()
+    assert ss.n_invalid == obad and obad > 0
+    assert np.array_equal(w, ow) and np.array_equal(st, ost) and np.array_equal(ln, oln)
+    table, _ = D.filter_kmers(ss, D.CountFilter(1), False, False, 4, k=31)
+    assert_tables_equal(table.to_host(), orc.filter_kmers(31, ow, ost, oln, min_obs=1))
+    # uniform reads (the fast tile layout), all valid
+    reads = [bytes(rng.choice(alphabet[:4], size=150)) for _ in range(500)]
+    ss2 = D.SeqSet.from_ascii(ctx, reads)
+    ow2, ost2, oln2, _ = orc.from_acgt_bytes(reads)
+    assert ss2.n_invalid == 0 and np.array_equal(ss2.copy_out()[0], ow2)
+    empty = D.SeqSet.from_ascii(ctx, [])
+    assert len(empty.copy_out()[1]) == 0
+
+
 def test_count_saturation(D, ctx, orc):
     """filter.rs:57 counts saturate at 65535; compression.rs:495 single-k-mer node keeps raw data."""
     seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")

@@ -309,3 +309,25 @@ def test_msp_sharded_filter_equals_unsharded(orc):
             assert int(x) not in got
             got[int(x)] = (int(e), int(c))
     assert got == {int(x): (int(e), int(c)) for x, e, c in zip(ref["lo"], ref["exts"], ref["counts"])}
+
+
+def test_from_acgt_bytes_matches_reference_kats(orc):
+    """DnaString::from_acgt_bytes (dna_string.rs:224-250): same words as from_dna_string on the reference's own test
+    strings (test_from_dna_string, dna_string.rs:954-975), case-insensitive, non-ACGT -> A (lib.rs:65-73;
+    bitops_avx2.rs test_invalid_bases :196-215 checks exactly this validity rule)."""
+    dna = ("TGCATTAGAAAACTCCTTGCCTGTCAGCCCGACAGGTAGAAACTCATTAATCCACACATTGA"
+           "CTCTATTTCAGGTAAATATGACGTCAACTCCTGCATGTTGAAGGCAGTGAGTGGCTGAAACAGCATCAAGGCGTGAAGGC")   # dna_string.rs:1062
+    w, st, ln, bad = orc.from_acgt_bytes([dna.encode()])
+    assert bad == 0 and list(ln) == [142] and np.array_equal(w, orc.pack_bases(enc(dna)))
+    w2, _, _, bad2 = orc.from_acgt_bytes([dna.lower().encode()])
+    assert bad2 == 0 and np.array_equal(w2, w)
+    w3, _, _, bad3 = orc.from_acgt_bytes([b"ACGTNNacgtXy-\x00\xff"])
+    assert bad3 == 7 and np.array_equal(w3, orc.pack_bases(enc("ACGTAAACGTAAAAA")))
+    # doctest string of dna_string.rs:19: k-mer 0 of slice(10, 40) is CACGTATGACAGATAG
+    s = "ACAGCAGCAGCACGTATGACAGATAGTGACAGCAGTTTGTGACCGCAAGAGCAGTAATATGATG"
+    w4, _, _, _ = orc.from_acgt_bytes([s.encode()])
+    assert np.array_equal(orc.unpack_bases(w4, 10, 16), enc("CACGTATGACAGATAG"))
+    # several sequences are appended bit-contiguously (PackedDnaStringSet::add, dna_string.rs:811-821)
+    w5, st5, ln5, _ = orc.from_acgt_bytes([b"ACG", b"", b"TTTTT", b"g"])
+    assert list(st5) == [0, 3, 3, 8] and list(ln5) == [3, 0, 5, 1]
+    assert np.array_equal(w5, orc.pack_bases(enc("ACGTTTTTG")))
