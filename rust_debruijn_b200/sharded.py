@@ -265,6 +265,26 @@ def gather_table(table, group=None, timings=None):
     return full
 
 
+def balanced_seed_bounds(seeds_sorted, V, world, group=None, nbin=4096):
+    """Slice boundaries (world + 1 indices into this rank's ASCENDING seeds) that send every path record to the rank
+    owning its seed's range, with ranges cut at the node-count quantiles over ALL ranks: a seed is the minimum index of
+    its unitig, so seeds crowd the low indices and equal index ranges would be badly unbalanced.  Cumulative counts of
+    the local seeds at nbin + 1 bin edges are all-reduced; every rank derives the same cuts from the global counts."""
+    import torch
+    import torch.distributed as dist
+    dev = seeds_sorted.device
+    n = seeds_sorted.numel()
+    edges = torch.arange(nbin + 1, dtype=torch.int64, device=dev) * ((V + nbin - 1) // nbin)
+    cl = torch.searchsorted(seeds_sorted, edges, right=False)
+    cl[-1] = n
+    cg = cl.clone()
+    dist.all_reduce(cg, group=group)
+    targets = (cg[-1] * torch.arange(1, world, dtype=torch.int64, device=dev)) // world
+    cut = torch.searchsorted(cg, targets, right=False).clamp_(max=nbin)
+    cut = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), cut, torch.full((1,), nbin, dtype=torch.int64, device=dev)])
+    return cl[cut]
+
+
 def _all_gather_uneven(t, sizes, itemsize, group, dev):
     """All-gather 1-D uint8 views of different lengths (sizes in items); returns the concatenation in rank order."""
     import torch
@@ -343,18 +363,7 @@ def compress_sharded(full, stranded, spec, group=None, lmax=1024, timings=None, 
         pk_s, pv_s = ((pkey, pval) if which.value == 0 else (pk_b, pv_b))
         pk_s, pv_s = pk_s[:np_local], pv_s[:np_local]
         seeds = (pk_s >> key_shift) & ((1 << (64 - key_shift)) - 1)          # arithmetic shift: mask the sign fill
-        # seed-range splitters balanced by NODE count (a seed is the minimum index of its unitig, so seeds crowd the low
-        # indices): cumulative counts of the sorted local seeds at 4096 bin edges, all-reduced, cut at the quantiles
-        nbin = 4096
-        edges = torch.arange(nbin + 1, dtype=torch.int64, device=dev) * ((V + nbin - 1) // nbin)
-        cl = torch.searchsorted(seeds, edges, right=False)
-        cl[-1] = np_local
-        cg = cl.clone()
-        dist.all_reduce(cg, group=group)
-        targets = (cg[-1] * torch.arange(1, world, dtype=torch.int64, device=dev)) // world
-        cut = torch.searchsorted(cg, targets, right=False).clamp_(max=nbin)
-        cut = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), cut, torch.full((1,), nbin, dtype=torch.int64, device=dev)])
-        bnd = cl[cut]
+        bnd = balanced_seed_bounds(seeds, V, world, group)
         sn = bnd[1:] - bnd[:-1]
         rn = torch.empty(world, dtype=torch.int64, device=dev)
         dist.all_to_all_single(rn, sn, group=group)

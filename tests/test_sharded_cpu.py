@@ -77,3 +77,50 @@ def test_key_range_splitters():
             if hist.sum() and world > 1 and hist.max() < hist.sum() / world:
                 mass = [hist[cuts[i]:cuts[i + 1]].sum() for i in range(world)]
                 assert max(mass) <= hist.sum() / world + hist.max() + 1
+
+
+def _seed_worker(rank, world, port, V, n, out):
+    import torch
+    import torch.distributed as dist
+
+    from rust_debruijn_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7 + rank)
+    # seeds crowd the low indices (minimum of a few uniform draws), different amounts per rank
+    seeds = np.sort(np.minimum.reduce(rng.integers(0, V, size=(4, n + 100 * rank)), axis=0)).astype(np.int64)
+    bnd = sharded.balanced_seed_bounds(torch.from_numpy(seeds), V, world)
+    out[rank] = (seeds, bnd.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_balanced_seed_bounds_gloo(world):
+    """Seed-range splitters of the sharded compression: contiguous slices, the same seed thresholds on every rank,
+    destinations balanced by node count although the seeds are far from uniform."""
+    import torch.multiprocessing as mp
+    V, n = 1_000_000, 20_000
+    port = _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_seed_worker, args=(world, port, V, n, out), nprocs=world, join=True)
+    per_dst = np.zeros(world, np.int64)
+    hi_prev = [-1] * world   # largest seed sent to each destination so far / smallest sent to the next
+    for r in range(world):
+        seeds, bnd = out[r]
+        assert bnd[0] == 0 and bnd[-1] == len(seeds) and np.all(np.diff(bnd) >= 0)
+        for d in range(world):
+            sl = seeds[bnd[d]:bnd[d + 1]]
+            per_dst[d] += len(sl)
+            if len(sl):
+                hi_prev[d] = max(hi_prev[d], int(sl.max()))
+    # ranges are disjoint and ordered across ranks: everything sent to d is below everything sent to d + 1
+    for r in range(world):
+        seeds, bnd = out[r]
+        for d in range(1, world):
+            sl = seeds[bnd[d]:bnd[d + 1]]
+            if len(sl):
+                assert int(sl.min()) > max(hi_prev[:d])
+    total = per_dst.sum()
+    assert per_dst.max() - per_dst.min() <= 0.1 * total / world + 4096   # quantile cuts at 4096-bin granularity
