@@ -1197,11 +1197,6 @@ __global__ void item_fill_kernel(const u32* __restrict__ cnt, const u64* __restr
 // TOTAL number of input k-mers.
 void plan_filter(const Ctx* c, int k, u64 N, int* p_out, int* bbits_out) {
     const int W = k <= 32 ? 1 : 2;
-    int p = c->msp_p > 0 ? c->msp_p : 12;
-    if (p > k - 3) p = k - 3;  // window of K-p+1 >= 4 p-mers (register-tiled window minimum)
-    if (p > 16) p = 16;
-    if (p < 1) p = 1;
-    if (k - p > 63) p = k - 63;
     u64 target = c->target_bucket_occ > 0 ? (u64)c->target_bucket_occ : 0;
     if (!target) {
         // k-mer occurrences per bucket such that the bucket's DISTINCT k-mers fit the shared-memory table
@@ -1213,6 +1208,15 @@ void plan_filter(const Ctx* c, int k, u64 N, int* p_out, int* bbits_out) {
     }
     int bbits = 0;
     while (bbits < 20 && (N >> (bbits + 1)) >= target) bbits++;
+    // Minimizer length: 12 up to 2^16 buckets, one more base per further bucket bit.  A bucket is the union of the
+    // minimizers whose hash ends in its bits; with p fixed, finer bucketing leaves only a handful of (very unevenly
+    // used) minimizers per bucket and the bucket sizes spread out: 7 141 table-overflow splits at 2^19 buckets with
+    // p = 12 against 94 at 2^16.  4^p / 2 canonical p-mers >= 128 per bucket keeps the spread of the 2^16 case.
+    int p = c->msp_p > 0 ? c->msp_p : 12 + (bbits > 16 ? bbits - 16 : 0);
+    if (p > k - 3) p = k - 3;  // window of K-p+1 >= 4 p-mers (register-tiled window minimum)
+    if (p > 16) p = 16;
+    if (p < 1) p = 1;
+    if (k - p > 63) p = k - 63;
     *p_out = p;
     *bbits_out = bbits;
 }
