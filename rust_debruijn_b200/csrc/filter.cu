@@ -666,7 +666,8 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
     __shared__ u64 s_scan[33];
     __shared__ u16 s_task[P2_RC * 4];     // (record in chunk) | (task in record << 10), sorted by task length
     __shared__ u32 s_cls[17];             // per task length: counter / cursor; [0] = number of tasks
-    __shared__ u32 s_ptot, s_next, s_wr_ok;
+    __shared__ u32 s_ptot, s_next, s_wr_ok, s_cnt;
+    __shared__ u64 s_r0;
     __shared__ u32 s_wsum[32];
     __shared__ u32 s_bucket, s_overflow, s_sp_cnt, s_sp_exts, s_nstack;
     __shared__ u64 s_base_valid, s_base_all;
@@ -677,18 +678,28 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
     const int nxt_shift = 62 - 2 * (K & 31);   // its bit position there
     const int tl = a.task_len;
 
+    // thread 0 keeps one bucket in flight: the queue atomic and the bucket's (start, count) loads are issued while the
+    // previous bucket is still being processed, so the CTA never idles on an L2 round trip between buckets
+    u32 nb_id = 0, nb_cnt = 0;
+    u64 nb_r0 = 0;
+    if (threadIdx.x == 0) {
+        nb_id = (u32)atomicAdd(&a.counters[0], 1ull);
+        if (nb_id < a.n_buckets) { nb_r0 = a.bucket_start[nb_id]; nb_cnt = a.bucket_cnt[nb_id]; }
+    }
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            s_bucket = (u32)atomicAdd(&a.counters[0], 1ull);
+            s_bucket = nb_id; s_r0 = nb_r0; s_cnt = nb_cnt;
             s_nstack = 1;
             s_stack[0] = 0;
+            if (nb_id < a.n_buckets) nb_id = (u32)atomicAdd(&a.counters[0], 1ull);   // result needed one bucket later
         }
         __syncthreads();
         const u32 b = s_bucket;
         if (b >= a.n_buckets) break;
-        const u64 r0 = a.bucket_start[b];
-        u64 r1 = r0 + a.bucket_cnt[b];
+        const u64 r0 = s_r0;
+        u64 r1 = r0 + s_cnt;
+        if (threadIdx.x == 0 && nb_id < a.n_buckets) { nb_r0 = a.bucket_start[nb_id]; nb_cnt = a.bucket_cnt[nb_id]; }
         if (r0 == r1) continue;
         const bool small_bucket = (r1 - r0) * 63ull < (1ull << 24);   // no count can overflow the 24-bit field
         if constexpr (W == 1) {
@@ -1057,14 +1068,19 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
             }
             // ---- emit: count, block scan, reserve, write ----
             u32 nv = 0, na = 0;
-            for (int i = threadIdx.x; i < CAP; i += P2T) {
+            u32 occm = 0, valm = 0;   // bit j: slot threadIdx.x + j * P2T is occupied / valid (CAP / P2T <= 32 slots per thread)
+            static_assert(CAP / P2T <= 32, "slot masks are 32 bits");
+#pragma unroll
+            for (int j = 0; j < CAP / P2T; j++) {
+                const int i = threadIdx.x + j * P2T;
                 bool occ = W == 1 ? reinterpret_cast<u64*>(keys)[i] != ~0ull
                                   : !(reinterpret_cast<u64*>(keys)[2 * i] == ~0ull && reinterpret_cast<u64*>(keys)[2 * i + 1] == ~0ull);
                 if (occ) {
                     na++;
+                    occm |= 1u << j;
                     u32 c = vals[i] >> 8;
                     c = c > 65535u ? 65535u : c;
-                    if (c >= a.min_obs) nv++;
+                    if (c >= a.min_obs) { nv++; valm |= 1u << j; }
                 }
             }
             if (threadIdx.x == 0 && s_sp_cnt) {
@@ -1111,23 +1127,25 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
             __syncthreads();
             if (s_wr_ok) {
                 u64 pv = s_base_valid + (u32)ex, pa = s_base_all + (u32)(ex >> 32);
-                for (int i = threadIdx.x; i < CAP; i += P2T) {
+                // only the slots the first pass marked: valid ones (a few per cent of the table on reads with errors), or
+                // every occupied one when all_kmers is requested — in slot order, like the counts above
+                for (u32 m = a.report_all ? occm : valm; m; m &= m - 1) {
+                    const int j = __ffs(m) - 1;
+                    const int i = threadIdx.x + j * P2T;
                     u64 klo = W == 1 ? reinterpret_cast<u64*>(keys)[i] : reinterpret_cast<u64*>(keys)[2 * i];
                     u64 khi = W == 1 ? 0 : reinterpret_cast<u64*>(keys)[2 * i + 1];
-                    bool occ = W == 1 ? klo != ~0ull : !(klo == ~0ull && khi == ~0ull);
-                    if (!occ) continue;
-                    u32 v = vals[i];
-                    u32 c = v >> 8;
-                    c = c > 65535u ? 65535u : c;
-                    if (a.report_all) { a.all_lo[pa] = klo; if (W == 2) a.all_hi[pa] = khi; }
-                    pa++;
-                    if (c >= a.min_obs) {
+                    if (a.report_all) { a.all_lo[pa] = klo; if (W == 2) a.all_hi[pa] = khi; pa++; }
+                    if ((valm >> j) & 1u) {
+                        u32 v = vals[i];
+                        u32 c = v >> 8;
+                        c = c > 65535u ? 65535u : c;
                         a.out_lo[pv] = klo;
                         if (W == 2) a.out_hi[pv] = khi;
                         a.out_val[pv] = (v & 0xffu) | (c << 8);
                         pv++;
                     }
                 }
+                if (!a.report_all) pa += na;
                 if (threadIdx.x == 0 && s_sp_cnt) {
                     u32 c = s_sp_cnt > 65535u ? 65535u : s_sp_cnt;
                     if (a.report_all) { a.all_lo[pa] = ~0ull; if (W == 2) a.all_hi[pa] = ~0ull; }

@@ -34,6 +34,18 @@ check(6, O.seqset_from_lists([rng.integers(0, 2, 60, dtype=np.uint8) for _ in ra
 big = rng.integers(0, 4, 3000, dtype=np.uint8)
 words = O.pack_bases(big)
 check(31, (words, np.array([2000, 100], np.uint64), np.array([900, 700], np.uint32)), 1)   # general (non-contiguous) kernel
+c3 = D.Context(0)
+c3.set_param("direct_min_tiles", 1)
+check(31, O.synth_reads(4000, 1, O.ERR_THR_NOISY), 2, c=c3)                                 # direct partition (sampling + regions)
+check(31, O.synth_reads(200, 1, 0), 1, c=c3)                                                # ... with a useless sample: overflow fallback
+c3.set_param("fast_compress", 0)
+check(31, O.synth_reads(1500, 1, O.ERR_THR_NOISY), 2, c=c3)                                 # general compression path forced
+ascii_reads = [bytes(rng.choice(np.frombuffer(b"ACGTacgtN", np.uint8), size=n)) for n in (0, 31, 150, 33, 4097, 1)]
+ssa = D.SeqSet.from_ascii(ctx, ascii_reads)
+ow, ost, oln, obad = O.from_acgt_bytes(ascii_reads)
+same = np.array_equal(ssa.copy_out()[0], ow) and ssa.n_invalid == obad
+ok &= same
+print("from_ascii", "OK" if same else "MISMATCH", flush=True)
 c2 = D.Context(0)
 c2.set_param("bucket_occ", 1 << 30)
 check(31, O.synth_reads(1200, 1, O.ERR_THR_NOISY), 2, c=c2)                                 # bucket splits
