@@ -560,20 +560,40 @@ __global__ void check_total_kernel(const u64* total, u64 bound, u32* overflow) {
     if (*total > bound) *overflow = 1;
 }
 
-// records (staging order) -> per-bucket contiguous ranges
+// records (staging order) -> per-bucket contiguous ranges.  Four independent slots per thread: the chain bucket id ->
+// bucket offset / cursor atomic -> 16-byte copy is pure latency, so four chains are kept in flight per thread.
 template <int RW>
-__global__ void scatter_records_kernel(const u64* __restrict__ rec, const u32* __restrict__ rec_bucket, u64 n_slots,
-                                       const u64* __restrict__ bucket_off, u32* __restrict__ bucket_fill,
-                                       u64* __restrict__ out) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
-    u32 b = rec_bucket[i];
-    if (b == INVALID_BUCKET) return;
-    u64 pos = bucket_off[b] + atomicAdd(&bucket_fill[b], 1u);
-    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(rec + i * RW);
-    ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + pos * RW);
-    dst[0] = src[0];
-    if (RW == 4) dst[1] = src[1];
+__global__ void __launch_bounds__(256) scatter_records_kernel(const u64* __restrict__ rec, const u32* __restrict__ rec_bucket,
+                                                              u64 n_slots, const u64* __restrict__ bucket_off,
+                                                              u32* __restrict__ bucket_fill, u64* __restrict__ out) {
+    constexpr int U = 4;
+    const u64 base = (u64)blockIdx.x * (256 * U) + threadIdx.x;
+    u32 b[U];
+    u64 pos[U];
+    ulonglong2 r0[U], r1[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const u64 i = base + (u64)u * 256;
+        b[u] = i < n_slots ? rec_bucket[i] : INVALID_BUCKET;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const u64 i = base + (u64)u * 256;
+        pos[u] = 0;
+        if (b[u] != INVALID_BUCKET) {
+            pos[u] = bucket_off[b[u]] + atomicAdd(&bucket_fill[b[u]], 1u);
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(rec + i * RW);
+            r0[u] = src[0];
+            if (RW == 4) r1[u] = src[1];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (b[u] == INVALID_BUCKET) continue;
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + pos[u] * RW);
+        dst[0] = r0[u];
+        if (RW == 4) dst[1] = r1[u];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1369,7 +1389,7 @@ static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, 
     if (pool_out) TRY(po.rec.alloc_pool(c, po.n_rec * RW)); else TRY(po.rec.alloc(c, po.n_rec * RW));
     TRY(bucket_fill.zero());
     if (n_slots > capacity) n_slots = capacity;
-    scatter_records_kernel<RW><<<grid_for(n_slots, 256), 256, 0, st>>>(stage_rec.p, stage_bucket.p, n_slots, po.bucket_off.p,
+    scatter_records_kernel<RW><<<grid_for(n_slots, 1024), 256, 0, st>>>(stage_rec.p, stage_bucket.p, n_slots, po.bucket_off.p,
                                                                         bucket_fill.p, po.rec.p);
     TRY(check_launch(c, "scatter_records"));
     return DBG_OK;
@@ -1411,7 +1431,6 @@ static int partition_direct(Ctx* c, int k, const SeqSet* s, int stranded, u64 N,
     a.rec = d.rec.p; a.rec_bucket = nullptr; a.capacity = d.rec_bound;
     a.cursor = nullptr; a.bucket_count = d.cnt.p; a.overflow = (u32*)(d.ctr.p + 1);
     a.bucket_start = d.bucket_start.p; a.bucket_cap = d.cap.p; a.bucket_fill = d.fill.p;
-    CU(c, cudaEventRecord(c->ev[8], st));
     // ---- sampling pass (with a pipelined upload: over the first chunk, as soon as it has arrived) ----
     const int np = sm->n_pending;
     auto tiles_upto = [&](int ci) -> u64 {
@@ -1440,8 +1459,9 @@ static int partition_direct(Ctx* c, int k, const SeqSet* s, int stranded, u64 N,
     TRY(exclusive_scan_u32_to_u64(c, d.cap.p, d.bucket_start.p, NB, d.ctr.p));
     check_total_kernel<<<1, 1, 0, st>>>(d.ctr.p, d.rec_bound, (u32*)(d.ctr.p + 1));
     TRY(check_launch(c, "check_total"));
-    // ---- main pass: records straight into their bucket's region ----
+    // ---- main pass: records straight into their bucket's region (ev[8..9] time this launch alone) ----
     a.mode = 2;
+    CU(c, cudaEventRecord(c->ev[8], st));
     if (np > 0) {
         u64 done = 0;
         for (int ci = 0; ci < np; ci++) {

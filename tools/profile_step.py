@@ -13,10 +13,13 @@ ap.add_argument("--k", type=int, default=31)
 ap.add_argument("--clean", action="store_true")
 ap.add_argument("--p", type=int, default=0)
 ap.add_argument("--bucket-occ", type=int, default=0)
+ap.add_argument("--no-direct", action="store_true")
 a = ap.parse_args()
 ctx = D.Context(0)
 if a.p:
     ctx.set_param("msp_p", a.p)
+if a.no_direct:
+    ctx.set_param("direct_partition", 0)
 if a.bucket_occ:
     ctx.set_param("bucket_occ", a.bucket_occ)
 ss = D.SeqSet.synth(ctx, a.reads, 1, 0 if a.clean else 83886)
