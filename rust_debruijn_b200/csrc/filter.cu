@@ -238,7 +238,9 @@ __device__ __forceinline__ u64 seq_index_of(const u64* __restrict__ start, u64 n
 
 template <int W>
 __device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs& ta, int K, const u32* s_s32, const u32* s_bm,
-                                                 u32 bkt, u64 sb, u32 ofs, int ps, int nn, u64 slot) {
+                                                 u32 bkt, u64 sb, u32 ofs, int ps, int nn, u64 slot, bool ok) {
+    // `slot` / `ok` may depend on an atomic that is still in flight (direct partition): nothing below touches them
+    // until the final store, so the record is assembled while the atomic travels
     constexpr int RW = RecLayout<W>::WORDS;
     u32 eb = ofs + (u32)ps;            // staged index of the run's first base
     u32 nbase = (u32)nn + K - 1;
@@ -282,6 +284,10 @@ __device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs
         if (t > lastw) r[t] = 0;
     }
     r[RW - 1] |= hdr;
+    if (!ok) {
+        if (a.mode == 2) *a.overflow = 1;   // region (or the whole buffer) too small: record dropped, the host falls back to staging
+        return;
+    }
     if constexpr (RW == 2) {
         *reinterpret_cast<ulonglong2*>(a.rec + slot * 2) = make_ulonglong2(r[0], r[1]);
     } else {
@@ -511,15 +517,13 @@ __global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, T
             const u32 bkt = s_bk[bkpad((u32)ps)];
             if (a.mode == 1) { atomicAdd(&a.bucket_count[bkt], 1u); continue; }
             u64 slot = slot0 + q;
+            bool ok = slot < a.capacity;
             if (a.mode == 2) {
-                const u32 r = atomicAdd(&a.bucket_fill[bkt], 1u);
+                const u32 r = atomicAdd(&a.bucket_fill[bkt], 1u);   // no branch on r here: see tile_emit_record
                 slot = a.bucket_start[bkt] + r;
-                // region (or the whole buffer) too small: drop the record, the host falls back to staging
-                if (r >= a.bucket_cap[bkt] || slot >= a.capacity) { *a.overflow = 1; continue; }
-            } else if (slot >= a.capacity) {
-                continue;
+                ok = r < a.bucket_cap[bkt] && slot < a.capacity;
             }
-            tile_emit_record<W>(a, ta, K, s_s32, s_bm, bkt, sb, ofs, ps, nn, slot);
+            tile_emit_record<W>(a, ta, K, s_s32, s_bm, bkt, sb, ofs, ps, nn, slot, ok);
         }
     }
 }
