@@ -187,6 +187,10 @@ int dbg_filter_from_records(dbg_ctx* ctx, int k, const void* d_records, uint64_t
 /* A table of n entries with UNINITIALISED device arrays: the caller fills them (ascending, distinct k-mers) through
  * dbg_table_device_ptrs, e.g. as the receive buffers of a collective. */
 int dbg_table_alloc(dbg_ctx* ctx, int k, uint64_t n, dbg_kmer_table** out);
+/* filter::remove_censored_exts (src/filter.rs:280-306; sharded = 0) and remove_censored_exts_sharded (:238-276; sharded = 1):
+ * rewrites the table's Exts in place, dropping every extension that points at a k-mer which is not in the table (plain), or
+ * which is not in the table but is in the table's all_kmers (sharded; needs report_all_kmers at filter time). */
+int dbg_remove_censored_exts(dbg_ctx* ctx, dbg_kmer_table* table, int stranded, int sharded);
 /* Histogram of the top `bits` (<= min(24, 2k)) bits of the table's keys into d_hist (device, 2^bits u32, zeroed by the
  * call; stream-ordered, not synchronised): splitters for redistributing sorted shards by key range. */
 int dbg_table_prefix_hist(dbg_ctx* ctx, const dbg_kmer_table* t, int bits, void* d_hist);

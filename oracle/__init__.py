@@ -59,6 +59,7 @@ def lib():
         L.orc_synth_genome_bases.restype = C.c_uint64
         L.orc_synth_genome_bases.argtypes = [C.c_uint64]
         L.orc_synth_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, u64p]
+        L.orc_remove_censored_exts.argtypes = [C.c_int, C.c_uint64, u64p, u64p, u8p, C.c_int, C.c_uint64, u64p, u64p, C.c_int]
         _lib = L
     return _lib
 
@@ -145,6 +146,19 @@ def filter_kmers(k, words, start, length, seq_exts=None, min_obs=1, stranded=Fal
                      _p(out["counts"], C.c_uint16), _p(out["all_lo"], C.c_uint64), _p(out["all_hi"], C.c_uint64))
     L.orc_table_free(h)
     return out
+
+
+def remove_censored_exts(k, t, stranded=False, sharded=False):
+    """filter::remove_censored_exts (src/filter.rs:280-306) or, with sharded=True, remove_censored_exts_sharded
+    (:238-276, needs the table's all_kmers).  Returns the new exts array (the table dict is not modified)."""
+    lo = np.ascontiguousarray(t["lo"], np.uint64)
+    hi = np.ascontiguousarray(t["hi"], np.uint64)
+    exts = np.array(t["exts"], np.uint8, copy=True)
+    alo = np.ascontiguousarray(t["all_lo"], np.uint64) if sharded else np.zeros(0, np.uint64)
+    ahi = np.ascontiguousarray(t["all_hi"], np.uint64) if sharded else np.zeros(0, np.uint64)
+    lib().orc_remove_censored_exts(k, len(lo), _p(lo, C.c_uint64), _p(hi, C.c_uint64), _p(exts, C.c_uint8), int(stranded),
+                                   len(alo), _p(alo, C.c_uint64), _p(ahi, C.c_uint64), int(sharded))
+    return exts
 
 
 def compress_kmers(k, lo, hi, exts, counts, stranded=False, reduce_op=SAT_ADD, seed_order=None):

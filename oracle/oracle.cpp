@@ -538,6 +538,27 @@ struct OrcTable {
     int passes;
 };
 
+// filter::remove_censored_exts / remove_censored_exts_sharded — src/filter.rs:238-306.  exts is updated in place.
+// all_n == 0 and sharded == 0: plain variant (keep an extension iff the extended k-mer is valid).  sharded: drop an
+// extension only when the extended k-mer is NOT valid but IS in all_kmers (it was seen in this shard and censored).
+template <typename T>
+static void remove_censored(int k, const T* keys, uint64_t n, uint8_t* exts, int stranded, const T* all, uint64_t all_n, int sharded) {
+    KOps<T> K(k);
+    for (uint64_t idx = 0; idx < n; idx++) {
+        uint8_t ne = 0;
+        for (int dir = 0; dir < 2; dir++)
+            for (int i = 0; i < 4; i++) {
+                if (!((exts[idx] >> (4 * dir + i)) & 1)) continue;                 // Exts::has_ext, lib.rs:609-618
+                T e = dir ? K.ext_right(keys[idx], (uint8_t)i) : K.ext_left(keys[idx], (uint8_t)i);
+                if (!stranded) { T r = K.rc(e); if (r < e) e = r; }                // min_rc
+                bool valid = std::binary_search(keys, keys + n, e);
+                bool keep = sharded ? (valid || !std::binary_search(all, all + all_n, e)) : valid;
+                if (keep) ne |= (uint8_t)(1u << (4 * dir + i));
+            }
+        exts[idx] = ne;
+    }
+}
+
 extern "C" {
 
 uint64_t orc_kmer_rc(int k, uint64_t x) { return KOps<uint64_t>(k).rc(x); }
@@ -597,6 +618,18 @@ void orc_table_copy(void* h, uint64_t* lo, uint64_t* hi, uint8_t* exts, uint16_t
     if (all_hi && !t->all_hi.empty()) memcpy(all_hi, t->all_hi.data(), t->all_hi.size() * 8);
 }
 void orc_table_free(void* h) { delete (OrcTable*)h; }
+
+void orc_remove_censored_exts(int k, uint64_t n, const uint64_t* lo, const uint64_t* hi, uint8_t* exts, int stranded,
+                              uint64_t all_n, const uint64_t* all_lo, const uint64_t* all_hi, int sharded) {
+    if (k <= 32) {
+        remove_censored<uint64_t>(k, lo, n, exts, stranded, all_lo, all_n, sharded);
+    } else {
+        std::vector<u128> keys(n), all(all_n);
+        for (uint64_t i = 0; i < n; i++) keys[i] = ((u128)hi[i] << 64) | lo[i];
+        for (uint64_t i = 0; i < all_n; i++) all[i] = ((u128)all_hi[i] << 64) | all_lo[i];
+        remove_censored<u128>(k, keys.data(), n, exts, stranded, all.data(), all_n, sharded);
+    }
+}
 
 // compress_kmers: kmers given as lo[] (+hi[] when k > 32), in SEED ORDER = array order unless seed_order given.
 void* orc_compress_kmers(int k, uint64_t n, const uint64_t* lo, const uint64_t* hi, const uint8_t* exts,

@@ -98,6 +98,7 @@ SIGNATURES = {
     "dbg_filter_from_records": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                           C.c_int, C.c_int, vpp]),
     "dbg_table_alloc": (C.c_int, [vp, C.c_int, C.c_uint64, vpp]),
+    "dbg_remove_censored_exts": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "dbg_table_prefix_hist": (C.c_int, [vp, vp, C.c_int, vp]),
     "dbg_table_device_ptrs": (C.c_int, [vp, vpp, vpp, vpp, vpp]),
     "dbg_table_from_device": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, vp, vpp]),

@@ -309,6 +309,16 @@ class BaseGraph:
             pass
 
 
+def remove_censored_exts(stranded, table):
+    """filter::remove_censored_exts (src/filter.rs:280-306): in place on the device table."""
+    table.ctx.check(table.ctx._L.dbg_remove_censored_exts(table.ctx._h, table._h, int(bool(stranded)), 0))
+
+
+def remove_censored_exts_sharded(stranded, table):
+    """filter::remove_censored_exts_sharded (src/filter.rs:238-276); all_kmers = the table's own (report_all_kmers)."""
+    table.ctx.check(table.ctx._L.dbg_remove_censored_exts(table.ctx._h, table._h, int(bool(stranded)), 1))
+
+
 def filter_kmers(seqs, summarizer, stranded, report_all_kmers, memory_size, k=31, ctx=None):
     """filter::filter_kmers (src/filter.rs:139-148).
 

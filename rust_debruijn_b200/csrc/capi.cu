@@ -682,6 +682,12 @@ int dbg_table_alloc(dbg_ctx* ctx, int k, uint64_t n, dbg_kmer_table** out) {
     *out = h;
     return DBG_OK;
 }
+int dbg_remove_censored_exts(dbg_ctx* ctx, dbg_kmer_table* table, int stranded, int sharded) {
+    if (!ctx) return DBG_E_BADARG;
+    NULLCHK(ctx, table);
+    cudaSetDevice(ctx->c.device);
+    return remove_censored_exts_dev(CTX(ctx), &table->t, stranded != 0, sharded != 0);
+}
 int dbg_table_prefix_hist(dbg_ctx* ctx, const dbg_kmer_table* t, int bits, void* d_hist) {
     if (!ctx || !d_hist) return DBG_E_BADARG;
     NULLCHK(ctx, t);

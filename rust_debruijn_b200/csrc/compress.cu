@@ -903,6 +903,81 @@ int cs_links_dev(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u32* d_nx
     return t->k <= 32 ? cs_links_impl<1>(c, t, stranded, v0, v1, d_nxt_out) : cs_links_impl<2>(c, t, stranded, v0, v1, d_nxt_out);
 }
 
+// ================================================================================================
+// filter::remove_censored_exts / remove_censored_exts_sharded (src/filter.rs:238-306), SURVEY §8f N2: drop the
+// extension bits of every valid k-mer that point at a k-mer which is not valid (plain variant), or which is not
+// valid but was seen in this shard, i.e. is in all_kmers (sharded variant: extensions into other shards are
+// kept).  One thread per k-mer, up to 8 (16) lookups through the same prefix LUT + binary search that stands in
+// for the reference's binary_search_by_key.  Only keys are read, every thread rewrites its own Exts byte.
+// ================================================================================================
+template <int W>
+static int build_prefix_lut(Ctx* c, int k, const u64* lo, const u64* hi, u64 n, DBuf<u32>& cnt, DBuf<u64>& lut, int* shift_out) {
+    int lb = 8;
+    while ((1ull << (lb + 4)) <= n && lb < 24) lb++;
+    if (lb > 2 * k) lb = 2 * k;
+    const int shift = 2 * k - lb;
+    const u64 n_pfx = 1ull << lb;
+    TRY(cnt.alloc(c, n_pfx));
+    TRY(lut.alloc(c, n_pfx + 1));
+    TRY(cnt.zero());
+    if (n) {
+        lut_hist_kernel<W><<<grid_for(n, 256), 256, 0, c->stream>>>(lo, hi, n, shift, cnt.p);
+        TRY(check_launch(c, "lut_hist"));
+    }
+    TRY(exclusive_scan_u32_to_u64(c, cnt.p, lut.p, n_pfx, lut.p + n_pfx));
+    *shift_out = shift;
+    return DBG_OK;
+}
+
+template <int W>
+__global__ void censor_exts_kernel(KP kp, const u64* __restrict__ lo, const u64* __restrict__ hi, u8* __restrict__ exts, u64 n,
+                                   const u64* __restrict__ lut, int lut_shift, int stranded, const u64* __restrict__ all_lo,
+                                   const u64* __restrict__ all_hi, const u64* __restrict__ all_lut, int all_shift, int sharded) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Kmer<W> key = load_key<W>(lo, hi, i);
+    const u32 e = exts[i];
+    u32 ne = 0;
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const u32 bit = 1u << (4 * d + b);
+            if (!(e & bit)) continue;                                                    // Exts::has_ext
+            Kmer<W> nk = d == 0 ? Ops<W>::ext_left(kp, key, b) : Ops<W>::ext_right(kp, key, b);   // kmer.extend(i, dir)
+            if (!stranded) { Kmer<W> r = Ops<W>::rc(kp, nk); if (r < nk) nk = r; }        // min_rc
+            bool keep = table_find<W>(lo, hi, lut, lut_shift, nk) != NIL;                 // valid: not censored
+            if (!keep && sharded) keep = table_find<W>(all_lo, all_hi, all_lut, all_shift, nk) == NIL;   // not seen here: other shard
+            if (keep) ne |= bit;
+        }
+    }
+    exts[i] = (u8)ne;
+}
+
+template <int W>
+static int censor_impl(Ctx* c, Table* t, int stranded, int sharded) {
+    if (t->n == 0) return DBG_OK;
+    if (t->n >= (1ull << 32) - 1 || t->n_all >= (1ull << 32) - 1) DBG_SET_ERR(c, DBG_E_BADARG, "table too large for 32-bit lookups");
+    TRY(arena_begin(c));
+    KP kp = make_kp(t->k);
+    DBuf<u32> cnt, acnt;
+    DBuf<u64> lut, alut;
+    int shift = 0, ashift = 0;
+    TRY(build_prefix_lut<W>(c, t->k, t->lo, t->hi, t->n, cnt, lut, &shift));
+    if (sharded) TRY(build_prefix_lut<W>(c, t->k, t->all_lo, t->all_hi, t->n_all, acnt, alut, &ashift));
+    censor_exts_kernel<W><<<grid_for(t->n, 256), 256, 0, c->stream>>>(kp, t->lo, t->hi, t->exts, t->n, lut.p, shift, stranded,
+                                                                      t->all_lo, t->all_hi, alut.p, ashift, sharded);
+    TRY(check_launch(c, "censor_exts"));
+    return sync(c);
+}
+
+int remove_censored_exts_dev(Ctx* c, Table* t, int stranded, int sharded) {
+    if (!t) DBG_SET_ERR(c, DBG_E_BADARG, "null table");
+    if (sharded && t->n_all == 0 && t->n != 0)
+        DBG_SET_ERR(c, DBG_E_BADARG, "remove_censored_exts_sharded needs all_kmers: run filter_kmers with report_all_kmers");
+    return t->k <= 32 ? censor_impl<1>(c, t, stranded, sharded) : censor_impl<2>(c, t, stranded, sharded);
+}
+
 // histogram of the top `bits` bits of the (ascending) keys: 2^bits u32 counters, zeroed here
 int table_prefix_hist_dev(Ctx* c, const Table* t, int bits, u32* d_hist) {
     if (!t || bits < 1 || bits > 24 || bits > 2 * t->k) DBG_SET_ERR(c, DBG_E_BADARG, "bad prefix width %d", bits);

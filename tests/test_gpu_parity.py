@@ -204,6 +204,30 @@ def test_from_ascii_ingest(D, ctx, orc):
     assert len(empty.copy_out()[1]) == 0
 
 
+def test_remove_censored_exts(D, ctx, orc):
+    """dbg_remove_censored_exts vs the oracle's filter::remove_censored_exts / _sharded (filter.rs:238-306), then the pruned
+    table through compress_kmers: Exts bytes and BaseGraph identical, both key widths, sequence-level Exts make the two
+    variants differ."""
+    rng = np.random.default_rng(9)
+    w, st, ln = orc.synth_reads(2500, 1, orc.ERR_THR_NOISY)
+    for k, stranded in ((31, False), (32, True), (63, False), (33, True)):
+        sx = rng.integers(0, 256, size=len(st)).astype(np.uint8)
+        ot = orc.filter_kmers(k, w, st, ln, seq_exts=sx, min_obs=2, stranded=stranded, report_all=True)
+        for sharded in (False, True):
+            table, _ = D.filter_kmers((w, st, ln, sx), D.CountFilter(2), stranded, True, 4, k=k, ctx=ctx)
+            (D.remove_censored_exts_sharded if sharded else D.remove_censored_exts)(stranded, table)
+            oe = orc.remove_censored_exts(k, ot, stranded=stranded, sharded=sharded)
+            t = table.to_host()
+            assert np.array_equal(t["exts"], oe) and np.array_equal(t["lo"], ot["lo"]) and np.array_equal(t["counts"], ot["counts"])
+            g = D.compress_kmers_with_hash(stranded, D.SimpleCompress(D.SAT_ADD), table).to_host()
+            og = orc.compress_kmers(k, ot["lo"], ot["hi"], oe, ot["counts"], stranded=stranded)
+            assert og["error"] == 0
+            assert_graphs_equal(g, og)
+    t0, _ = D.filter_kmers((w, st, ln), D.CountFilter(2), False, False, 4, k=31, ctx=ctx)
+    with pytest.raises(D.DbgError):
+        D.remove_censored_exts_sharded(False, t0)     # no all_kmers in this table
+
+
 def test_count_saturation(D, ctx, orc):
     """filter.rs:57 counts saturate at 65535; compression.rs:495 single-k-mer node keeps raw data."""
     seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")

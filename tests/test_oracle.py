@@ -331,3 +331,24 @@ def test_from_acgt_bytes_matches_reference_kats(orc):
     w5, st5, ln5, _ = orc.from_acgt_bytes([b"ACG", b"", b"TTTTT", b"g"])
     assert list(st5) == [0, 3, 3, 8] and list(ln5) == [3, 0, 5, 1]
     assert np.array_equal(w5, orc.pack_bases(enc("ACGTTTTTG")))
+
+
+def test_remove_censored_exts_properties(orc):
+    """filter::remove_censored_exts[_sharded] (filter.rs:238-306; the reference has no test of its own for them): every kept
+    extension points at a valid k-mer, nothing is added, the operation is idempotent; the sharded variant keeps exactly the
+    extensions whose target was never seen in the shard (here: the ones injected through sequence-level Exts)."""
+    rng = np.random.default_rng(9)
+    w, st, ln = orc.synth_reads(1500, 1, orc.ERR_THR_NOISY)
+    for k, stranded in ((31, False), (32, True), (63, False)):
+        sx = rng.integers(0, 256, size=len(st)).astype(np.uint8)
+        t = orc.filter_kmers(k, w, st, ln, seq_exts=sx, min_obs=2, stranded=stranded, report_all=True)
+        e1 = orc.remove_censored_exts(k, t, stranded=stranded)
+        e2 = orc.remove_censored_exts(k, t, stranded=stranded, sharded=True)
+        assert np.all(e1 & ~t["exts"] == 0) and np.all(e2 & ~t["exts"] == 0) and np.all(e1 & ~e2 == 0)
+        assert (e1 != t["exts"]).any() and (e2 != e1).any()
+        t1 = dict(t, exts=e1)
+        assert np.array_equal(orc.remove_censored_exts(k, t1, stranded=stranded), e1)
+        # with pruned Exts nothing points outside the table any more: compression merges the paths the dangling bits split
+        g0 = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], stranded=stranded)
+        g1 = orc.compress_kmers(k, t["lo"], t["hi"], e1, t["counts"], stranded=stranded)
+        assert g1["error"] == 0 and g1["n_nodes"] < g0["n_nodes"] and g1["n_bases"] - g1["n_nodes"] * (k - 1) == len(t["lo"])
