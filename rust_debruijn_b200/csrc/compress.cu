@@ -11,15 +11,18 @@
 //   S4 links         per (k-mer, side): the stateless form of try_extend_kmer (:382-444): unique
 //                    extension, neighbour present, neighbour != self, neighbour's extension back is
 //                    unique, no palindromes (unstranded, even K).  Links are symmetric, so components
-//                    are simple paths or simple cycles of k-mers.
-//   S5 rank          pointer doubling over port states s = 2i+d ("at k-mer i, leaving through side d")
-//                    carrying (window length, min k-mer index in window, distance to it, arrival port).
-//                    Seed of a component = its smallest index = the k-mer the greedy loop would reach
-//                    first (:574-575).  Cycles (never-ending chains) get a fixed-round second phase.
-//   S6 emit          node id / base offsets by exclusive scans over seeds; every k-mer ORs its base(s)
-//                    into the bit-contiguous PackedDnaStringSet words (src/dna_string.rs:811-821,
-//                    383-399); end k-mers supply the node Exts (:513-517,534-540); counts are reduced
-//                    per node (SimpleCompress::reduce, :58-60).
+//                    are simple paths or simple cycles of k-mers.  Both links, the count, the Exts and the first /
+//                    last base go into ONE 16-byte walk record per k-mer.
+//   fast path        (every component is a path of <= 1024 k-mers)  discover: path ends walk to the other end, the
+//                    walker that started at the node's left end appends one path record (seed = smallest index =
+//                    the k-mer the greedy loop would reach first, :574-575); path records sorted by seed = node
+//                    order; emit_walk: one thread per node re-walks its chain and writes whole words.
+//   general path     (long unitigs, cycles)  S5 rank: end walks, then list ranking on a contracted graph of
+//                    splitters (pointer doubling over port states s = 2i+d carrying window length, min index,
+//                    distance, arrival port), cycles in a fixed-round second phase; S6 emit: node id / base offsets
+//                    by exclusive scans over seeds, every k-mer ORs its base(s) into the bit-contiguous
+//                    PackedDnaStringSet words (src/dna_string.rs:811-821, 383-399), end k-mers supply the node Exts
+//                    (:513-517,534-540), counts are reduced per node (SimpleCompress::reduce, :58-60).
 #include "common.cuh"
 
 namespace dbg {

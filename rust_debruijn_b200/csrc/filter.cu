@@ -4,15 +4,18 @@
 // prefix buckets and merge-sorts each bucket (src/filter.rs:186-219).  Here the N occurrences are
 // never written to HBM:
 //
-//   P1  msp_partition   warp per sequence chunk: 2-bit p-mer scores, sliding-window minimum
-//                       (minimum-substring partitioning, src/msp.rs:207-276 with a hash permutation
-//                       and rc = !stranded), maximal runs of k-mers with equal bucket -> one
-//                       16/32-byte SUPER-K-MER record (bases + boundary Exts nibbles,
-//                       Exts::from_slice_bounds src/lib.rs:645-660).  ~1.5 B per k-mer instead of 9-16.
-//   P1b scatter         records -> contiguous per-bucket ranges (histogram + exclusive scan).
-//   P2  count           one CTA per bucket (persistent, atomic work queue): records are expanded
-//                       with ROLLING fwd / reverse-complement k-mers (KmerExtsIter src/lib.rs:812-841,
-//                       min_rc_flip :224-231, Exts::rc :746), and inserted into an open-addressed
+//   P1  msp_partition   2-bit p-mer scores, sliding-window minimum (minimum-substring partitioning, src/msp.rs:207-276
+//                       with a hash permutation and rc = !stranded), maximal runs of k-mers with equal bucket -> one
+//                       16/32-byte SUPER-K-MER record (bases + boundary Exts nibbles, Exts::from_slice_bounds
+//                       src/lib.rs:645-660).  ~1.7 B per k-mer instead of 9-16.  Contiguous layouts: tile-per-CTA kernel
+//                       (msp_tile_kernel); anything else: warp per sequence chunk (msp_partition_kernel).
+//                       Direct mode (large device-resident inputs): a sampling pass over 1/16 of the tiles sizes one
+//                       region per bucket, the main pass writes every record into its bucket's region.
+//   P1b scatter         staging mode only (small inputs, multi-pass, pipelined uploads, the multi-GPU partition):
+//                       records -> contiguous per-bucket ranges (histogram + exclusive scan + scatter).
+//   P2  count           one CTA per bucket (persistent, atomic work queue): records are deduplicated, cut into
+//                       length-sorted tasks and expanded with ROLLING fwd / reverse-complement k-mers (KmerExtsIter
+//                       src/lib.rs:812-841, min_rc_flip :224-231, Exts::rc :746), inserted into an open-addressed
 //                       table in SHARED memory: key CAS, Exts OR, count add — CountFilter::summarize
 //                       (src/filter.rs:52-63).  A table overflow splits the bucket by hash class
 //                       (always terminates: the class hash is a bijection of the key).
