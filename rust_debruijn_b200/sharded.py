@@ -179,8 +179,8 @@ def gather_table(table, group=None, timings=None):
 
     A re-sort of the gathered table would cost every rank P times the single-GPU sort.  Instead the shards are
     first redistributed by KEY RANGE (splitters from an all-reduced histogram of the top 16 key bits, one
-    all-to-all per array), each rank sorts only its range (V/P k-mers), and the ordered ranges are broadcast
-    straight into the arrays of the replicated table (dbg_table_alloc) — no padding, no re-sort, no extra copy."""
+    all-to-all per array), each rank sorts only its range (V/P k-mers), and the ordered ranges are all-gathered
+    (one collective per array) and copied into the arrays of the replicated table (dbg_table_alloc) — no re-sort."""
     import torch
     import torch.distributed as dist
     ctx, L = table.ctx, table.ctx._L
@@ -245,16 +245,30 @@ def gather_table(table, group=None, timings=None):
         full = KmerTable(ctx, th)
         dst = _table_views(full, dev)
         src = _table_views(piece, dev)
-        off = 0
-        for r in range(world):
-            for d_arr, s_arr, isz in zip(dst, src, (1, 1, 1, 2)):
-                if d_arr is None or sizes[r] == 0:
-                    continue
-                sl = d_arr[off * isz:(off + sizes[r]) * isz]
-                if r == rank:
-                    sl.copy_(s_arr)
-                dist.broadcast(sl, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
-            off += sizes[r]
+        # one all-gather per array (pieces padded to the largest: they differ by < 1 bin of the splitter histogram), then
+        # P slice copies into the table — concurrent transfers over NVSwitch instead of P sequential broadcasts
+        mx = max(max(sizes), 1)
+        offs = [sum(sizes[:r]) for r in range(world)]
+        for d_arr, s_arr, isz in zip(dst, src, (1, 1, 1, 2)):
+            if d_arr is None:
+                continue
+            if world <= 2:   # two ranks: a broadcast each way moves the same bytes without the padded staging copies
+                for r in range(world):
+                    if sizes[r]:
+                        sl = d_arr[offs[r] * isz:(offs[r] + sizes[r]) * isz]
+                        if r == rank:
+                            sl.copy_(s_arr)
+                        dist.broadcast(sl, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+                continue
+            es = d_arr.element_size() * isz          # bytes per k-mer in this array (views of exts / counts are uint8)
+            pad = torch.empty(mx * es, dtype=torch.uint8, device=dev)
+            pad[:m * es] = s_arr.view(torch.uint8)[:m * es]
+            out = torch.empty(world * mx * es, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(out, pad, group=group)
+            d8 = d_arr.view(torch.uint8)
+            for r in range(world):
+                if sizes[r]:
+                    d8[offs[r] * es:(offs[r] + sizes[r]) * es] = out[r * mx * es:(r * mx + sizes[r]) * es]
         mark("bcast")
         ctx.synchronize()
         piece.free()
