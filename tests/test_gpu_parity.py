@@ -393,8 +393,9 @@ def test_msp_kmer_buckets_match_scanner(D, ctx, orc, k, p):
 
 
 def test_sharded_two_gpus():
-    """MSP-bucket-sharded filter_kmers over 2 ranks (one NCCL all-to-all) + gathered compress: BaseGraph
-    bit-identical to the oracle run on the union of both ranks' reads.  Needs >= 2 GPUs (skipped otherwise)."""
+    """MSP-bucket-sharded filter_kmers over 2 ranks (one NCCL all-to-all) + key-range gathered table + compression with the
+    work split over the ranks: BaseGraph bit-identical to the oracle run on the union of both ranks' reads, as the
+    complete graph on every rank and as per-rank runs of nodes.  Needs >= 2 GPUs (skipped otherwise)."""
     import subprocess
     import sys
 
@@ -406,7 +407,8 @@ def test_sharded_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "sharded_check.py"),
                         "--reads", "20000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("BIT-EXACT") == 3 and "MISMATCH" not in r.stdout
+    # three configurations, each checked in both output modes (complete graph on every rank / node-sharded)
+    assert r.stdout.count("node-sharded BIT-EXACT") == 3 and r.stdout.count("BIT-EXACT") == 6 and "MISMATCH" not in r.stdout
 
 
 def test_compress_kmers_slice_variant(D, ctx, orc):
