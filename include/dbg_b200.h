@@ -148,6 +148,12 @@ uint64_t dbg_graph_n_words(const dbg_graph* g);  /* ceil(n_bases / 32)          
 int dbg_graph_stranded(const dbg_graph* g);
 int dbg_graph_copy_out(const dbg_graph* g, uint64_t* words, uint64_t* start, uint32_t* length, uint8_t* exts,
                        uint16_t* data);
+/* BaseGraph::finish + DebruijnGraph::find_edges for EVERY (node, side) — src/graph.rs:116-142 (left_order / right_order),
+ * :223-291 (find_edges, find_link).  Host outputs of 8 * n_nodes entries, slot (node * 2 + side) * 4 + base (side 0 = Left,
+ * 1 = Right; base = A, C, G, T): target = node the extension leads to (0xffffffff: the node has no such extension, or the
+ * link is not in this graph — "this edge doesn't exist within this shard", graph.rs:236), flags bit 0 = side of the target
+ * through which it is entered (0 Left, 1 Right), bit 1 = reverse-complement switch. */
+int dbg_graph_edges(dbg_ctx* ctx, const dbg_graph* graph, uint32_t* target, uint8_t* flags);
 void dbg_graph_free(dbg_graph* g);
 
 /* ---- fused path: reads -> BaseGraph with the k-mer table kept device-resident ----------------------

@@ -59,6 +59,8 @@ def lib():
         L.orc_synth_genome_bases.restype = C.c_uint64
         L.orc_synth_genome_bases.argtypes = [C.c_uint64]
         L.orc_synth_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, u64p]
+        L.orc_graph_edges.restype = C.c_int64
+        L.orc_graph_edges.argtypes = [C.c_int, C.c_int, C.c_uint64, u64p, u64p, u32p, u8p, u32p, u8p]
         L.orc_remove_censored_exts.argtypes = [C.c_int, C.c_uint64, u64p, u64p, u8p, C.c_int, C.c_uint64, u64p, u64p, C.c_int]
         _lib = L
     return _lib
@@ -146,6 +148,23 @@ def filter_kmers(k, words, start, length, seq_exts=None, min_obs=1, stranded=Fal
                      _p(out["counts"], C.c_uint16), _p(out["all_lo"], C.c_uint64), _p(out["all_hi"], C.c_uint64))
     L.orc_table_free(h)
     return out
+
+
+def graph_edges(k, g, stranded=False):
+    """BaseGraph::finish + DebruijnGraph::find_edges for every (node, side) (src/graph.rs:116-142, 223-291) and
+    is_compressed (:296-334, join_test = true).  Returns (target[M,2,4] uint32 with 0xffffffff = none,
+    flags[M,2,4] uint8: bit0 incoming side, bit1 rc, collapsible pair or None)."""
+    m = int(g["n_nodes"])
+    words = np.ascontiguousarray(np.concatenate([g["words"], np.zeros(1, np.uint64)]), np.uint64)
+    start = np.ascontiguousarray(g["start"], np.uint64)
+    length = np.ascontiguousarray(g["length"], np.uint32)
+    exts = np.ascontiguousarray(g["exts"], np.uint8)
+    target = np.zeros(m * 8, np.uint32)
+    flags = np.zeros(m * 8, np.uint8)
+    r = lib().orc_graph_edges(k, int(stranded), m, _p(words, C.c_uint64), _p(start, C.c_uint64), _p(length, C.c_uint32),
+                              _p(exts, C.c_uint8), _p(target, C.c_uint32), _p(flags, C.c_uint8))
+    pair = None if r < 0 else (int(r >> 32), int(r & 0xffffffff))
+    return target.reshape(m, 2, 4), flags.reshape(m, 2, 4), pair
 
 
 def remove_censored_exts(k, t, stranded=False, sharded=False):

@@ -559,6 +559,96 @@ static void remove_censored(int k, const T* keys, uint64_t n, uint8_t* exts, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// BaseGraph::finish + DebruijnGraph::find_edges / find_link / is_compressed — src/graph.rs:116-142, 223-334
+// (SURVEY §8f N1).  left_order / right_order (BoomHashMap: first / last k-mer of every node -> node id) are
+// restated as sorted vectors with exact key lookup.  edges: slot (node * 2 + dir) * 4 + base; target = 0xffffffff
+// when the node has no such extension or the link is missing; flags bit 0 = incoming side (0 Left, 1 Right),
+// bit 1 = rc flip.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct NodeIndex {
+    int k;
+    int stranded;
+    KOps<T> K;
+    std::vector<std::pair<T, uint32_t>> left, right;   // (first k-mer, node), (last k-mer, node), sorted by k-mer
+    std::vector<T> first, last;
+    NodeIndex(int k_, int stranded_, uint64_t m, const uint64_t* words, const uint64_t* start, const uint32_t* length)
+        : k(k_), stranded(stranded_), K(k_) {
+        first.resize(m); last.resize(m);
+        for (uint64_t i = 0; i < m; i++) {
+            T a = 0, b = 0;
+            for (int j = 0; j < k; j++) {                                   // Vmer::get_kmer: first_kmer / last_kmer, lib.rs:369-376
+                a = (a << 2) | (T)dna_get(words, start[i] + j);
+                b = (b << 2) | (T)dna_get(words, start[i] + length[i] - k + j);
+            }
+            first[i] = a; last[i] = b;
+            left.push_back({a, (uint32_t)i});
+            right.push_back({b, (uint32_t)i});
+        }
+        std::sort(left.begin(), left.end());
+        std::sort(right.begin(), right.end());
+    }
+    bool search(T kmer, int side, uint32_t& idx) const {                    // search_kmer, graph.rs:245-250
+        const auto& v = side ? right : left;
+        auto it = std::lower_bound(v.begin(), v.end(), std::make_pair(kmer, (uint32_t)0));
+        if (it == v.end() || it->first != kmer) return false;
+        idx = it->second;
+        return true;
+    }
+    bool find_link(T kmer, int dir, uint32_t& idx, int& inc, bool& flip) const {   // graph.rs:252-291
+        T rc = K.rc(kmer);
+        if (dir == 0) {
+            if (search(kmer, 1, idx)) { inc = 1; flip = false; return true; }
+            if (!stranded && search(rc, 0, idx)) { inc = 0; flip = true; return true; }
+        } else {
+            if (search(kmer, 0, idx)) { inc = 0; flip = false; return true; }
+            if (!stranded && search(rc, 1, idx)) { inc = 1; flip = true; return true; }
+        }
+        return false;
+    }
+    void edges(const uint8_t* exts, uint64_t m, uint32_t* target, uint8_t* flags) const {   // find_edges, graph.rs:223-242
+        for (uint64_t n = 0; n < m; n++)
+            for (int dir = 0; dir < 2; dir++) {
+                T kmer = dir ? last[n] : first[n];                          // term_kmer
+                for (int i = 0; i < 4; i++) {
+                    uint64_t slot = (n * 2 + dir) * 4 + i;
+                    target[slot] = 0xffffffffu; flags[slot] = 0;
+                    if (!((exts[n] >> (4 * dir + i)) & 1)) continue;
+                    T e = dir ? K.ext_right(kmer, (uint8_t)i) : K.ext_left(kmer, (uint8_t)i);
+                    uint32_t idx; int inc; bool flip;
+                    if (find_link(e, dir, idx, inc, flip)) { target[slot] = idx; flags[slot] = (uint8_t)(inc | (flip ? 2 : 0)); }
+                }
+            }
+    }
+};
+
+template <typename T>
+static int64_t graph_is_compressed(int k, int stranded, uint64_t m, const uint64_t* words, const uint64_t* start, const uint32_t* length,
+                                   const uint8_t* exts, uint32_t* target, uint8_t* flags) {
+    NodeIndex<T> ix(k, stranded, m, words, start, length);
+    ix.edges(exts, m, target, flags);
+    auto single = [&](uint64_t n, int dir, uint32_t& nxt, int& ret) {
+        int cnt = 0;
+        for (int i = 0; i < 4; i++) {
+            uint64_t s = (n * 2 + dir) * 4 + i;
+            if (target[s] != 0xffffffffu) { cnt++; nxt = target[s]; ret = flags[s] & 1; }
+        }
+        return cnt == 1;
+    };
+    for (uint64_t i = 0; i < m; i++)                                           // is_compressed, graph.rs:296-334 (join_test = true)
+        for (int dir = 0; dir < 2; dir++) {
+            uint32_t nxt = 0, back = 0; int ret = 0, r2 = 0;
+            if (!single(i, dir, nxt, ret)) continue;
+            if (!single(nxt, ret, back, r2)) continue;
+            if (length[i] == (uint32_t)k && ix.K.is_pal(ix.first[i])) continue;
+            if (length[nxt] == (uint32_t)k && ix.K.is_pal(ix.first[nxt])) continue;
+            if (i == nxt) continue;
+            return (int64_t)((i << 32) | nxt);
+        }
+    return -1;
+}
+
 extern "C" {
 
 uint64_t orc_kmer_rc(int k, uint64_t x) { return KOps<uint64_t>(k).rc(x); }
@@ -619,6 +709,12 @@ void orc_table_copy(void* h, uint64_t* lo, uint64_t* hi, uint8_t* exts, uint16_t
 }
 void orc_table_free(void* h) { delete (OrcTable*)h; }
 
+// returns -1 when the graph is compressed, else (i << 32) | next of the first collapsible pair; fills the edge arrays
+int64_t orc_graph_edges(int k, int stranded, uint64_t m, const uint64_t* words, const uint64_t* start, const uint32_t* length,
+                        const uint8_t* exts, uint32_t* target, uint8_t* flags) {
+    return k <= 32 ? graph_is_compressed<uint64_t>(k, stranded, m, words, start, length, exts, target, flags)
+                   : graph_is_compressed<u128>(k, stranded, m, words, start, length, exts, target, flags);
+}
 void orc_remove_censored_exts(int k, uint64_t n, const uint64_t* lo, const uint64_t* hi, uint8_t* exts, int stranded,
                               uint64_t all_n, const uint64_t* all_lo, const uint64_t* all_hi, int sharded) {
     if (k <= 32) {

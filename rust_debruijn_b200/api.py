@@ -283,6 +283,14 @@ class BaseGraph:
             self._host = g
         return self._host
 
+    def edges(self):
+        """DebruijnGraph::find_edges for every (node, side) after BaseGraph::finish (src/graph.rs:116-142, 223-291):
+        (target[M, 2, 4] uint32, 0xffffffff = none; flags[M, 2, 4] uint8: bit 0 incoming side, bit 1 rc)."""
+        m = len(self)
+        target, flags = np.zeros(8 * m, np.uint32), np.zeros(8 * m, np.uint8)
+        self.ctx.check(self.ctx._L.dbg_graph_edges(self.ctx._h, self._h, _ptr(target), _ptr(flags)))
+        return target.reshape(m, 2, 4), flags.reshape(m, 2, 4)
+
     @property
     def sequences(self):
         g = self.to_host()

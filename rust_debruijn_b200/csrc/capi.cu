@@ -855,6 +855,13 @@ int dbg_graph_copy_out(const dbg_graph* h, uint64_t* words, uint64_t* start, uin
     return sync(c);
 }
 
+int dbg_graph_edges(dbg_ctx* ctx, const dbg_graph* graph, uint32_t* target, uint8_t* flags) {
+    if (!ctx) return DBG_E_BADARG;
+    NULLCHK(ctx, graph);
+    cudaSetDevice(ctx->c.device);
+    return graph_edges_dev(CTX(ctx), &graph->g, target, flags);
+}
+
 void dbg_graph_free(dbg_graph* g) { if (g) { cudaSetDevice(g->g.ctx->device); free_graph(&g->g); } }
 
 // ---- fused ------------------------------------------------------------------------------------------------

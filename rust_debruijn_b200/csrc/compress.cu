@@ -981,6 +981,121 @@ int remove_censored_exts_dev(Ctx* c, Table* t, int stranded, int sharded) {
     return t->k <= 32 ? censor_impl<1>(c, t, stranded, sharded) : censor_impl<2>(c, t, stranded, sharded);
 }
 
+// ================================================================================================
+// BaseGraph::finish + DebruijnGraph::find_edges / find_link for every (node, side) — src/graph.rs:116-142, 223-291
+// (SURVEY §8f N1).  left_order / right_order (BoomHashMap: first / last k-mer of a node -> node id) become two
+// sorted (k-mer, node) arrays searched through a prefix LUT; one thread per (node, side) tries its <= 4 extensions.
+// Output slot (node * 2 + side) * 4 + base: target node (0xffffffff = no such extension / link not in this graph),
+// flags bit 0 = incoming side (0 Left, 1 Right), bit 1 = rc flip.
+// ================================================================================================
+template <int W>
+__device__ __forceinline__ Kmer<W> kmer_at(const KP& kp, const u64* __restrict__ words, u64 b) {   // Vmer::get_kmer
+    const int K = kp.k;
+    Kmer<W> r;
+    if constexpr (W == 1) {
+        r.lo = bases64(words, b) >> (64 - 2 * K);
+    } else {
+        const u64 H = bases64(words, b), L = bases64(words, b + 32);
+        const int sh = 128 - 2 * K;   // 0..62
+        r.hi = sh ? H >> sh : H;
+        r.lo = sh ? (L >> sh) | (H << (64 - sh)) : L;
+    }
+    return r;
+}
+
+template <int W>
+__global__ void node_term_kmers_kernel(KP kp, const u64* __restrict__ words, const u64* __restrict__ start, const u32* __restrict__ length,
+                                       u64 m, u64* __restrict__ f_lo, u64* __restrict__ f_hi, u64* __restrict__ l_lo, u64* __restrict__ l_hi,
+                                       u32* __restrict__ id_a, u32* __restrict__ id_b) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const Kmer<W> f = kmer_at<W>(kp, words, start[i]);                         // first_kmer, lib.rs:369-371
+    const Kmer<W> l = kmer_at<W>(kp, words, start[i] + length[i] - kp.k);      // last_kmer, lib.rs:374-376
+    f_lo[i] = f.lo; l_lo[i] = l.lo;
+    if constexpr (W == 2) { f_hi[i] = f.hi; l_hi[i] = l.hi; }
+    id_a[i] = (u32)i; id_b[i] = (u32)i;
+}
+
+template <int W>
+struct EndMap { const u64* lo; const u64* hi; const u32* node; const u64* lut; int shift; };
+
+template <int W>
+__device__ __forceinline__ u32 endmap_find(const EndMap<W>& mp, Kmer<W> key) {
+    const u32 j = table_find<W>(mp.lo, mp.hi, mp.lut, mp.shift, key);
+    return j == NIL ? NIL : mp.node[j];
+}
+
+template <int W>
+__global__ void graph_edges_kernel(KP kp, const u64* __restrict__ words, const u64* __restrict__ start, const u32* __restrict__ length,
+                                   const u8* __restrict__ exts, u64 m, int stranded, EndMap<W> left, EndMap<W> right,
+                                   u32* __restrict__ target, u8* __restrict__ flags) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * m) return;
+    const u64 n = t >> 1;
+    const int dir = (int)(t & 1);
+    const Kmer<W> kmer = kmer_at<W>(kp, words, dir ? start[n] + length[n] - kp.k : start[n]);   // term_kmer
+    const u32 e = exts[n];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u32 tg = NIL, fl = 0;
+        if ((e >> (4 * dir + i)) & 1u) {                                            // find_edges, graph.rs:229-239
+            const Kmer<W> x = dir ? Ops<W>::ext_right(kp, kmer, i) : Ops<W>::ext_left(kp, kmer, i);
+            // find_link, graph.rs:252-291: same strand through the opposite side, else (unstranded) the rc through the same side
+            tg = endmap_find<W>(dir ? left : right, x);
+            fl = dir ? 0u : 1u;
+            if (tg == NIL && !stranded) {
+                tg = endmap_find<W>(dir ? right : left, Ops<W>::rc(kp, x));
+                fl = (dir ? 1u : 0u) | 2u;
+            }
+            if (tg == NIL) fl = 0;
+        }
+        target[t * 4 + i] = tg;
+        flags[t * 4 + i] = (u8)fl;
+    }
+}
+
+template <int W>
+static int graph_edges_impl(Ctx* c, const Graph* g, u32* h_target, u8* h_flags) {
+    const u64 m = g->n_nodes;
+    if (m == 0) return DBG_OK;
+    if (m >= (1ull << 31)) DBG_SET_ERR(c, DBG_E_BADARG, "too many nodes for 32-bit ids");
+    TRY(arena_begin(c));
+    cudaStream_t st = c->stream;
+    KP kp = make_kp(g->k);
+    DBuf<u64> fa_lo, fa_hi, fb_lo, fb_hi, la_lo, la_hi, lb_lo, lb_hi;
+    DBuf<u32> ia, ib, ja, jb, d_target;
+    DBuf<u8> d_flags;
+    TRY(fa_lo.alloc(c, m)); TRY(fb_lo.alloc(c, m)); TRY(la_lo.alloc(c, m)); TRY(lb_lo.alloc(c, m));
+    if (W == 2) { TRY(fa_hi.alloc(c, m)); TRY(fb_hi.alloc(c, m)); TRY(la_hi.alloc(c, m)); TRY(lb_hi.alloc(c, m)); }
+    TRY(ia.alloc(c, m)); TRY(ib.alloc(c, m)); TRY(ja.alloc(c, m)); TRY(jb.alloc(c, m));
+    TRY(d_target.alloc(c, 8 * m)); TRY(d_flags.alloc(c, 8 * m));
+    node_term_kmers_kernel<W><<<grid_for(m, 256), 256, 0, st>>>(kp, g->words, g->start, g->length, m, fa_lo.p, fa_hi.p, la_lo.p, la_hi.p, ia.p, ja.p);
+    TRY(check_launch(c, "node_term_kmers"));
+    u64 *flo, *fhi, *llo, *lhi;
+    u32 *fid, *lid;
+    TRY(radix_sort_pairs(c, W, 2 * g->k, m, fa_lo.p, fa_hi.p, ia.p, fb_lo.p, fb_hi.p, ib.p, &flo, &fhi, &fid));   // left_order
+    TRY(radix_sort_pairs(c, W, 2 * g->k, m, la_lo.p, la_hi.p, ja.p, lb_lo.p, lb_hi.p, jb.p, &llo, &lhi, &lid));   // right_order
+    DBuf<u32> cnt_l, cnt_r;
+    DBuf<u64> lut_l, lut_r;
+    EndMap<W> L, R;
+    L.lo = flo; L.hi = fhi; L.node = fid;
+    R.lo = llo; R.hi = lhi; R.node = lid;
+    TRY(build_prefix_lut<W>(c, g->k, flo, fhi, m, cnt_l, lut_l, &L.shift));
+    TRY(build_prefix_lut<W>(c, g->k, llo, lhi, m, cnt_r, lut_r, &R.shift));
+    L.lut = lut_l.p; R.lut = lut_r.p;
+    graph_edges_kernel<W><<<grid_for(2 * m, 256), 256, 0, st>>>(kp, g->words, g->start, g->length, g->exts, m, g->stranded, L, R,
+                                                                d_target.p, d_flags.p);
+    TRY(check_launch(c, "graph_edges"));
+    CU(c, cudaMemcpyAsync(h_target, d_target.p, 8 * m * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(h_flags, d_flags.p, 8 * m, cudaMemcpyDeviceToHost, st));
+    return sync(c);
+}
+
+int graph_edges_dev(Ctx* c, const Graph* g, u32* h_target, u8* h_flags) {
+    if (!g || !h_target || !h_flags) DBG_SET_ERR(c, DBG_E_BADARG, "null argument");
+    return g->k <= 32 ? graph_edges_impl<1>(c, g, h_target, h_flags) : graph_edges_impl<2>(c, g, h_target, h_flags);
+}
+
 // histogram of the top `bits` bits of the (ascending) keys: 2^bits u32 counters, zeroed here
 int table_prefix_hist_dev(Ctx* c, const Table* t, int bits, u32* d_hist) {
     if (!t || bits < 1 || bits > 24 || bits > 2 * t->k) DBG_SET_ERR(c, DBG_E_BADARG, "bad prefix width %d", bits);

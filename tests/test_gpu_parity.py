@@ -228,6 +228,29 @@ def test_remove_censored_exts(D, ctx, orc):
         D.remove_censored_exts_sharded(False, t0)     # no all_kmers in this table
 
 
+def test_graph_edges(D, ctx, orc):
+    """dbg_graph_edges (BaseGraph::finish + find_edges for every node and side, graph.rs:116-142, 223-291) vs the oracle:
+    identical target / flag arrays; K = 31 / 32 / 63 / 64, stranded and not, cycles and hairpins at small K."""
+    rng = np.random.default_rng(15)
+    w, st, ln = orc.synth_reads(2500, 1, orc.ERR_THR_NOISY)
+    cases = [(31, False, (w, st, ln), 2), (63, False, (w, st, ln), 2), (32, True, (w, st, ln), 2), (31, False, orc.synth_reads(1500, 1, 0), 1)]
+    for k in (5, 6, 7, 64):
+        contigs = small_k_contigs(rng, alphabet=2 if k < 8 else 4, lo=max(k, 8), hi=max(4 * k, 60))
+        contigs = [c for c in contigs if len(c) >= k]
+        cases.append((k, bool(k & 1), orc.seqset_from_lists(contigs), 1))
+    for k, stranded, ss, mo in cases:
+        table, _ = D.filter_kmers(ss, D.CountFilter(mo), stranded, False, 4, k=k, ctx=ctx)
+        if k == 31 and mo == 2:
+            D.remove_censored_exts(stranded, table)
+        graph = D.compress_kmers_with_hash(stranded, D.SimpleCompress(D.SAT_ADD), table)
+        g = graph.to_host()
+        target, flags = graph.edges()
+        ot, of, _ = orc.graph_edges(k, g, stranded=stranded)
+        assert np.array_equal(target, ot) and np.array_equal(flags, of), (k, stranded)
+    empty, _ = D.filter_kmers((np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint32)), D.CountFilter(1), False, False, 4, k=31, ctx=ctx)
+    assert D.compress_kmers_with_hash(False, D.SimpleCompress(), empty).edges()[0].shape == (0, 2, 4)
+
+
 def test_count_saturation(D, ctx, orc):
     """filter.rs:57 counts saturate at 65535; compression.rs:495 single-k-mer node keeps raw data."""
     seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")

@@ -352,3 +352,38 @@ def test_remove_censored_exts_properties(orc):
         g0 = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], stranded=stranded)
         g1 = orc.compress_kmers(k, t["lo"], t["hi"], e1, t["counts"], stranded=stranded)
         assert g1["error"] == 0 and g1["n_nodes"] < g0["n_nodes"] and g1["n_bases"] - g1["n_nodes"] * (k - 1) == len(t["lo"])
+
+
+def test_graph_edges_and_is_compressed(orc):
+    """BaseGraph::finish + find_edges / find_link (graph.rs:116-142, 223-291) restated, pinned by the property the reference's
+    own tests assert after compress_kmers: `is_compressed(&spec) == None` (test.rs:249-254, 268-274) — on tables where every
+    k-mer is valid (the reference's case: each contig twice / CountFilter(1)) and on censored tables after
+    remove_censored_exts.  Edges are reciprocal (odd K): the target's edge list on the incoming side leads back."""
+    from helpers import random_contigs
+    rng = np.random.default_rng(5)
+    cases = []
+    for k, stranded in ((31, False), (32, False), (6, False), (5, True), (33, True)):
+        contigs = [c for c in random_contigs(rng) if len(c) >= k]
+        ss = orc.seqset_from_lists(contigs + contigs)
+        t = orc.filter_kmers(k, *ss, min_obs=2, stranded=stranded)
+        cases.append((k, stranded, t, t["exts"]))
+    w, st, ln = orc.synth_reads(1500, 1, orc.ERR_THR_NOISY)
+    t = orc.filter_kmers(31, w, st, ln, min_obs=2)
+    cases.append((31, False, t, orc.remove_censored_exts(31, t)))
+    for k, stranded, t, exts in cases:
+        g = orc.compress_kmers(k, t["lo"], t["hi"], exts, t["counts"], stranded=stranded)
+        assert g["error"] == 0
+        target, flags, pair = orc.graph_edges(k, g, stranded=stranded)
+        assert pair is None, (k, stranded, pair)
+        m = g["n_nodes"]
+        if k % 2 == 0:
+            continue   # even K: palindromic k-mers (flipped-branch quirk, lib.rs:224-231) make find_link's answers one-sided
+        for n in range(0, m, max(1, m // 300)):
+            for d in range(2):
+                for i in range(4):
+                    if target[n, d, i] != 0xffffffff:
+                        nxt, inc = int(target[n, d, i]), int(flags[n, d, i] & 1)
+                        assert n in [int(x) for x in target[nxt, inc]], "edge without a way back"
+    # the uncensored noisy table is NOT compressed in is_compressed's sense: dangling Exts keep paths apart (SURVEY §4 caveat)
+    g = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], t["counts"])
+    assert orc.graph_edges(31, g)[2] is not None
