@@ -154,6 +154,10 @@ int dbg_graph_copy_out(const dbg_graph* g, uint64_t* words, uint64_t* start, uin
  * link is not in this graph — "this edge doesn't exist within this shard", graph.rs:236), flags bit 0 = side of the target
  * through which it is entered (0 Left, 1 Right), bit 1 = reverse-complement switch. */
 int dbg_graph_edges(dbg_ctx* ctx, const dbg_graph* graph, uint32_t* target, uint8_t* flags);
+/* DebruijnGraph::fix_exts / get_valid_exts — src/graph.rs:337-377: rewrites the graph's node Exts in place, keeping an
+ * extension only if find_link resolves it (and, with valid_nodes != NULL — host, one byte per node, the reference's BitSet —
+ * only if the target node is marked).  "Remove non-existent extensions that may be created due to filtered kmers". */
+int dbg_graph_fix_exts(dbg_ctx* ctx, dbg_graph* graph, const uint8_t* valid_nodes);
 void dbg_graph_free(dbg_graph* g);
 
 /* ---- fused path: reads -> BaseGraph with the k-mer table kept device-resident ----------------------

@@ -167,6 +167,18 @@ def graph_edges(k, g, stranded=False):
     return target.reshape(m, 2, 4), flags.reshape(m, 2, 4), pair
 
 
+def graph_fix_exts(k, g, stranded=False, valid_nodes=None):
+    """DebruijnGraph::fix_exts / get_valid_exts (src/graph.rs:337-377): an extension survives iff find_link resolves it
+    (and the target is in valid_nodes when given).  Returns the new node Exts array."""
+    target, _, _ = graph_edges(k, g, stranded=stranded)
+    ok = target != 0xffffffff
+    if valid_nodes is not None:
+        vn = np.asarray(valid_nodes).astype(bool)
+        ok &= vn[np.where(ok, target, 0)]
+    bits = (1 << np.arange(8, dtype=np.uint32)).reshape(2, 4)      # Exts bit 4 * dir + base (lib.rs:609-618)
+    return (ok * bits).sum(axis=(1, 2)).astype(np.uint8)
+
+
 def remove_censored_exts(k, t, stranded=False, sharded=False):
     """filter::remove_censored_exts (src/filter.rs:280-306) or, with sharded=True, remove_censored_exts_sharded
     (:238-276, needs the table's all_kmers).  Returns the new exts array (the table dict is not modified)."""

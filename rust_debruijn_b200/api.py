@@ -291,6 +291,15 @@ class BaseGraph:
         self.ctx.check(self.ctx._L.dbg_graph_edges(self.ctx._h, self._h, _ptr(target), _ptr(flags)))
         return target.reshape(m, 2, 4), flags.reshape(m, 2, 4)
 
+    def fix_exts(self, valid_nodes=None):
+        """DebruijnGraph::fix_exts (src/graph.rs:337-343), in place on the device; valid_nodes: optional bool/uint8 array."""
+        if valid_nodes is not None:
+            valid_nodes = np.ascontiguousarray(np.asarray(valid_nodes).astype(np.uint8))
+            if len(valid_nodes) != len(self):
+                raise ValueError("valid_nodes needs one entry per node")
+        self.ctx.check(self.ctx._L.dbg_graph_fix_exts(self.ctx._h, self._h, _ptr(valid_nodes)))
+        self._host = None
+
     @property
     def sequences(self):
         g = self.to_host()

@@ -862,6 +862,13 @@ int dbg_graph_edges(dbg_ctx* ctx, const dbg_graph* graph, uint32_t* target, uint
     return graph_edges_dev(CTX(ctx), &graph->g, target, flags);
 }
 
+int dbg_graph_fix_exts(dbg_ctx* ctx, dbg_graph* graph, const uint8_t* valid_nodes) {
+    if (!ctx) return DBG_E_BADARG;
+    NULLCHK(ctx, graph);
+    cudaSetDevice(ctx->c.device);
+    return graph_fix_exts_dev(CTX(ctx), &graph->g, valid_nodes);
+}
+
 void dbg_graph_free(dbg_graph* g) { if (g) { cudaSetDevice(g->g.ctx->device); free_graph(&g->g); } }
 
 // ---- fused ------------------------------------------------------------------------------------------------

@@ -1054,8 +1054,23 @@ __global__ void graph_edges_kernel(KP kp, const u64* __restrict__ words, const u
     }
 }
 
+// valid_nodes (optional, host, one byte per node): fix_exts' BitSet — links into nodes marked 0 do not count
+__global__ void fix_exts_kernel(const u32* __restrict__ target, const u8* __restrict__ valid_nodes, u64 m, u8* __restrict__ exts) {
+    const u64 n = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= m) return;
+    u32 e = 0;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {   // slot (n * 2 + dir) * 4 + i  <->  Exts bit 4 * dir + i
+        const u32 tg = target[n * 8 + s];
+        if (tg != NIL && (!valid_nodes || valid_nodes[tg])) e |= 1u << s;
+    }
+    exts[n] = (u8)e;
+}
+
+// h_target / h_flags != nullptr: copy the adjacency out (dbg_graph_edges); fix != 0: rewrite the graph's Exts from it
+// (DebruijnGraph::fix_exts / get_valid_exts, graph.rs:337-377)
 template <int W>
-static int graph_edges_impl(Ctx* c, const Graph* g, u32* h_target, u8* h_flags) {
+static int graph_edges_impl(Ctx* c, Graph* g, u32* h_target, u8* h_flags, int fix, const u8* h_valid_nodes) {
     const u64 m = g->n_nodes;
     if (m == 0) return DBG_OK;
     if (m >= (1ull << 31)) DBG_SET_ERR(c, DBG_E_BADARG, "too many nodes for 32-bit ids");
@@ -1086,14 +1101,31 @@ static int graph_edges_impl(Ctx* c, const Graph* g, u32* h_target, u8* h_flags) 
     graph_edges_kernel<W><<<grid_for(2 * m, 256), 256, 0, st>>>(kp, g->words, g->start, g->length, g->exts, m, g->stranded, L, R,
                                                                 d_target.p, d_flags.p);
     TRY(check_launch(c, "graph_edges"));
-    CU(c, cudaMemcpyAsync(h_target, d_target.p, 8 * m * sizeof(u32), cudaMemcpyDeviceToHost, st));
-    CU(c, cudaMemcpyAsync(h_flags, d_flags.p, 8 * m, cudaMemcpyDeviceToHost, st));
+    if (h_target) {
+        CU(c, cudaMemcpyAsync(h_target, d_target.p, 8 * m * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CU(c, cudaMemcpyAsync(h_flags, d_flags.p, 8 * m, cudaMemcpyDeviceToHost, st));
+    }
+    if (fix) {
+        DBuf<u8> d_valid;
+        if (h_valid_nodes) {
+            TRY(d_valid.alloc(c, m));
+            CU(c, cudaMemcpyAsync(d_valid.p, h_valid_nodes, m, cudaMemcpyHostToDevice, st));
+        }
+        fix_exts_kernel<<<grid_for(m, 256), 256, 0, st>>>(d_target.p, h_valid_nodes ? d_valid.p : nullptr, m, g->exts);
+        TRY(check_launch(c, "fix_exts"));
+        return sync(c);
+    }
     return sync(c);
 }
 
 int graph_edges_dev(Ctx* c, const Graph* g, u32* h_target, u8* h_flags) {
     if (!g || !h_target || !h_flags) DBG_SET_ERR(c, DBG_E_BADARG, "null argument");
-    return g->k <= 32 ? graph_edges_impl<1>(c, g, h_target, h_flags) : graph_edges_impl<2>(c, g, h_target, h_flags);
+    Graph* gm = const_cast<Graph*>(g);   // not modified when fix == 0
+    return g->k <= 32 ? graph_edges_impl<1>(c, gm, h_target, h_flags, 0, nullptr) : graph_edges_impl<2>(c, gm, h_target, h_flags, 0, nullptr);
+}
+int graph_fix_exts_dev(Ctx* c, Graph* g, const u8* h_valid_nodes) {
+    if (!g) DBG_SET_ERR(c, DBG_E_BADARG, "null graph");
+    return g->k <= 32 ? graph_edges_impl<1>(c, g, nullptr, nullptr, 1, h_valid_nodes) : graph_edges_impl<2>(c, g, nullptr, nullptr, 1, h_valid_nodes);
 }
 
 // histogram of the top `bits` bits of the (ascending) keys: 2^bits u32 counters, zeroed here

@@ -251,6 +251,22 @@ def test_graph_edges(D, ctx, orc):
     assert D.compress_kmers_with_hash(False, D.SimpleCompress(), empty).edges()[0].shape == (0, 2, 4)
 
 
+def test_graph_fix_exts(D, ctx, orc):
+    """dbg_graph_fix_exts (DebruijnGraph::fix_exts, graph.rs:337-377) vs the oracle, with and without valid_nodes, K = 31 / 63."""
+    w, st, ln = orc.synth_reads(2500, 1, orc.ERR_THR_NOISY)
+    for k in (31, 63):
+        table, _ = D.filter_kmers((w, st, ln), D.CountFilter(2), False, False, 4, k=k, ctx=ctx)
+        for use_mask in (False, True):
+            graph = D.compress_kmers_with_hash(False, D.SimpleCompress(D.SAT_ADD), table)
+            g = graph.to_host()
+            vn = (np.arange(g["n_nodes"]) % 3 != 0) if use_mask else None
+            oe = orc.graph_fix_exts(k, g, valid_nodes=vn)
+            graph.fix_exts(vn)
+            g2 = graph.to_host()
+            assert np.array_equal(g2["exts"], oe) and (oe != g["exts"]).any()
+            assert np.array_equal(g2["words"], g["words"]) and np.array_equal(g2["data"], g["data"])
+
+
 def test_count_saturation(D, ctx, orc):
     """filter.rs:57 counts saturate at 65535; compression.rs:495 single-k-mer node keeps raw data."""
     seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")

@@ -387,3 +387,21 @@ def test_graph_edges_and_is_compressed(orc):
     # the uncensored noisy table is NOT compressed in is_compressed's sense: dangling Exts keep paths apart (SURVEY §4 caveat)
     g = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], t["counts"])
     assert orc.graph_edges(31, g)[2] is not None
+
+
+def test_graph_fix_exts_properties(orc):
+    """DebruijnGraph::fix_exts (graph.rs:337-377): afterwards every node extension resolves to a node (no dangling bits),
+    nothing is added, idempotent; with valid_nodes, extensions into unmarked nodes go too."""
+    w, st, ln = orc.synth_reads(1500, 1, orc.ERR_THR_NOISY)
+    t = orc.filter_kmers(31, w, st, ln, min_obs=2)
+    g = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], t["counts"])
+    ne = orc.graph_fix_exts(31, g)
+    assert np.all(ne & ~g["exts"] == 0) and (ne != g["exts"]).any()
+    g2 = dict(g, exts=ne)
+    target, _, _ = orc.graph_edges(31, g2)
+    popc = np.array([bin(int(x)).count("1") for x in ne])
+    assert np.array_equal((target != 0xffffffff).sum(axis=(1, 2)), popc)
+    assert np.array_equal(orc.graph_fix_exts(31, g2), ne)
+    vn = np.arange(g["n_nodes"]) % 3 != 0
+    nv = orc.graph_fix_exts(31, g, valid_nodes=vn)
+    assert np.all(nv & ~ne == 0) and (nv != ne).any()
