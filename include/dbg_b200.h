@@ -44,7 +44,9 @@ typedef enum {
     DBG_REDUCE_SAT_ADD = 0,       /* |a,b| a.saturating_add(*b)              src/test.rs:383,459 */
     DBG_REDUCE_WRAP_ADD = 1,      /* |a,b| a + b (release: wrapping)          src/test.rs:265,546 */
     DBG_REDUCE_ADD_MOD_65535 = 2, /* |a,b| ((a as u32 + *b as u32) % 65535)   src/test.rs:247     */
-    DBG_REDUCE_MAX = 3            /* |a,b| max(a,*b)                          src/test.rs:469     */
+    DBG_REDUCE_MAX = 3,           /* |a,b| max(a,*b)                          src/test.rs:469     */
+    DBG_REDUCE_SCMAP = 4          /* ScmapCompress (src/compression.rs:66-98): join_test = data equality, reduce keeps the value;
+                                     dbg_compress_kmers_with_hash only (the sharded dbg_cs_* stages take 0..3) */
 } dbg_reduce_op;
 
 typedef struct dbg_ctx dbg_ctx;

@@ -70,7 +70,7 @@ def _p(a, t):
     return None if a is None else a.ctypes.data_as(C.POINTER(t))
 
 
-SAT_ADD, WRAP_ADD, ADD_MOD_65535, MAX = 0, 1, 2, 3
+SAT_ADD, WRAP_ADD, ADD_MOD_65535, MAX, SCMAP = 0, 1, 2, 3, 4   # SCMAP: ScmapCompress (compression.rs:66-98)
 ERR_THR_NOISY = 83886
 
 

@@ -262,12 +262,13 @@ static FilterOut<T> filter_kmers(int k, const uint64_t* words, const uint64_t* s
 // ---------------------------------------------------------------------------------------------
 // compress_kmers (CompressFromHash + SimpleCompress) — src/compression.rs:355-594
 // ---------------------------------------------------------------------------------------------
-enum ReduceOp { RED_SAT_ADD = 0, RED_WRAP_ADD = 1, RED_ADD_MOD_65535 = 2, RED_MAX = 3 };
+enum ReduceOp { RED_SAT_ADD = 0, RED_WRAP_ADD = 1, RED_ADD_MOD_65535 = 2, RED_MAX = 3, RED_SCMAP = 4 };  // 4: ScmapCompress, compression.rs:66-98
 static inline uint16_t reduce_data(int op, uint16_t a, uint16_t b) {
     switch (op) {
         case RED_SAT_ADD: { uint32_t s = (uint32_t)a + b; return (uint16_t)(s > 65535 ? 65535 : s); }  // test.rs:383
         case RED_WRAP_ADD: return (uint16_t)(a + b);                                                   // test.rs:265 (release wraps)
         case RED_ADD_MOD_65535: return (uint16_t)(((uint32_t)a + (uint32_t)b) % 65535);                // test.rs:247
+        case RED_SCMAP: return a;                                                                      // compression.rs:85-90 (a == b)
         default: return a > b ? a : b;                                                                 // test.rs:469
     }
 }
@@ -359,7 +360,8 @@ struct Compressor {
             error = 1;
             term = exts_single_dir(e, dir);
             return false;
-        } else if (incoming_count == 1 && !pal) {  // join_test == true for SimpleCompress (:62-64)
+        } else if ((op != RED_SCMAP || data[id] == data[nid]) && incoming_count == 1 && !pal) {
+            // can_join (:425): join_test is true for SimpleCompress (:62-64), data equality for ScmapCompress (:92-97)
             next = nk;
             next_dir = nd;
             return true;

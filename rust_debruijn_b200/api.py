@@ -18,6 +18,7 @@ from . import _lib
 from ._lib import DbgError
 
 SAT_ADD, WRAP_ADD, ADD_MOD_65535, MAX = 0, 1, 2, 3
+_SCMAP = 4
 
 
 def _ptr(a):
@@ -187,6 +188,11 @@ class SimpleCompress:
         if func not in (SAT_ADD, WRAP_ADD, ADD_MOD_65535, MAX):
             raise ValueError("SimpleCompress: func must be one of SAT_ADD, WRAP_ADD, ADD_MOD_65535, MAX")
         self.func = func
+
+
+class ScmapCompress:
+    """src/compression.rs:66-98: join_test = equality of the two k-mers' data, reduce keeps the (common) value."""
+    func = _SCMAP
 
 
 class KmerTable:
@@ -366,8 +372,8 @@ def filter_kmers(seqs, summarizer, stranded, report_all_kmers, memory_size, k=31
 
 def compress_kmers_with_hash(stranded, spec, index):
     """compression::compress_kmers_with_hash (src/compression.rs:588-594)."""
-    if not isinstance(spec, SimpleCompress):
-        raise TypeError("only SimpleCompress is on the accelerated path (SURVEY.md §8)")
+    if not isinstance(spec, (SimpleCompress, ScmapCompress)):
+        raise TypeError("only SimpleCompress / ScmapCompress are on the accelerated path (SURVEY.md §8)")
     ctx = index.ctx
     h = C.c_void_p()
     ctx.check(ctx._L.dbg_compress_kmers_with_hash(ctx._h, index._h, int(bool(stranded)), spec.func, C.byref(h)))

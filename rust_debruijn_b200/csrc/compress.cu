@@ -76,7 +76,7 @@ template <int W>
 __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __restrict__ hi, const u8* __restrict__ exts,
                              u64 v0, u64 n, const u64* __restrict__ lut, int lut_shift,
                              int stranded, u32* __restrict__ nxt, u32* __restrict__ err, uint4* __restrict__ rec16,
-                             const u16* __restrict__ counts) {
+                             const u16* __restrict__ counts, int scmap) {
     // thread t handles k-mer i = v0 + t of the (full) table and writes nxt[2t + side]: v0 = 0, n = V on one GPU;
     // a rank of the sharded compression handles only its own index range.  With rec16 != nullptr the two links go
     // into ONE 16-byte record per k-mer together with everything a unitig walk needs from that k-mer (count, Exts,
@@ -108,7 +108,9 @@ __global__ void links_kernel(KP kp, const u64* __restrict__ lo, const u64* __res
                 u32 nnib = exts_side(ne, inc);
                 int cnt = popc4(nnib);                                     // :422
                 if (cnt == 0 && !npal) atomicExch(err, 1u);                // :428-434 panic!("unreachable")
-                if (cnt == 1 && !npal) {                                   // :435
+                // CompressionSpec::join_test (:425): always true for SimpleCompress, data equality for ScmapCompress (:92-97)
+                const bool can_join = !scmap || counts[i] == counts[j];
+                if (can_join && cnt == 1 && !npal) {                       // :435
                     // reciprocity (always true for tables built by filter_kmers)
                     Kmer<W> back = inc == 0 ? Ops<W>::ext_left(kp, nk, unique_base(nnib)) : Ops<W>::ext_right(kp, nk, unique_base(nnib));
                     if (!stranded) { Kmer<W> r = Ops<W>::rc(kp, back); if (!(back < r)) back = r; }
@@ -410,13 +412,13 @@ __global__ void emit_kernel(KP kp, EmitArgs a) {
     // per-node data reduction; whole-warp-same-node fast path keeps giant unitigs off a single hot address
     u32 peers = __match_any_sync(0xffffffffu, nid);
     if (peers == 0xffffffffu) {
-        if (a.reduce_op == DBG_REDUCE_MAX) { for (int o = 16; o; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o)); }
+        if (a.reduce_op >= DBG_REDUCE_MAX) { for (int o = 16; o; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o)); }
         else { for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
         if ((threadIdx.x & 31) == 0 && act) {
-            if (a.reduce_op == DBG_REDUCE_MAX) atomicMax(&a.acc[nid], cnt); else atomicAdd(&a.acc[nid], cnt);
+            if (a.reduce_op >= DBG_REDUCE_MAX) atomicMax(&a.acc[nid], cnt); else atomicAdd(&a.acc[nid], cnt);
         }
     } else if (act) {
-        if (a.reduce_op == DBG_REDUCE_MAX) atomicMax(&a.acc[nid], cnt); else atomicAdd(&a.acc[nid], cnt);
+        if (a.reduce_op >= DBG_REDUCE_MAX) atomicMax(&a.acc[nid], cnt); else atomicAdd(&a.acc[nid], cnt);
     }
 }
 
@@ -596,7 +598,7 @@ __global__ void emit_walk_kernel(KP kp, EmitWalkArgs a) {
         nw.push(b << 62, 1, pos);
         pos++;
         const u64 cnt = r.z & 0xffffu;
-        if (a.reduce_op == DBG_REDUCE_MAX) acc = cnt > acc ? cnt : acc; else acc += cnt;
+        if (a.reduce_op >= DBG_REDUCE_MAX) acc = cnt > acc ? cnt : acc; else acc += cnt;   // SCMAP: all equal, max == the value
         if (j == len - 1) {
             u32 rn = exts_side((r.z >> 16) & 0xffu, (int)dw);   // right-facing side of the last k-mer (:534-540)
             if (!fw) rn = exts_complement(rn) & 0xfu;
@@ -653,7 +655,7 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
     TRY(ctr.alloc(c, 4));
     TRY(ctr.zero());
     links_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, 0, V, lut.p, lut_shift, stranded, nullptr,
-                                                      (u32*)(ctr.p + 3), rec16.p, t->counts);
+                                                      (u32*)(ctr.p + 3), rec16.p, t->counts, reduce_op == DBG_REDUCE_SCMAP);
     TRY(check_launch(c, "links"));
     CU(c, cudaEventRecord(c->ev[2], st));
     const u32* nxt_p = reinterpret_cast<const u32*>(rec16.p);   // general path: links read in place (stride 4 words)
@@ -890,7 +892,7 @@ static int cs_links_impl(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u
     TRY(exclusive_scan_u32_to_u64(c, lut_cnt.p, lut.p, n_pfx, lut.p + n_pfx));
     if (v1 > v0) {
         links_kernel<W><<<grid_for(v1 - v0, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, v0, v1 - v0, lut.p, lut_shift, stranded,
-                                                                d_nxt_out, (u32*)(ctr.p + 3), nullptr, nullptr);
+                                                                d_nxt_out, (u32*)(ctr.p + 3), nullptr, t->counts, 0);
         TRY(check_launch(c, "links"));
     }
     u64 h[4];
@@ -1260,7 +1262,7 @@ int graph_from_device_dev(Ctx* c, int k, int stranded, u64 n_nodes, u64 n_bases,
 int compress_dev(Ctx* c, const Table* t, int stranded, int reduce_op, Graph** out) {
     *out = nullptr;
     if (!t) DBG_SET_ERR(c, DBG_E_BADARG, "null table");
-    if (reduce_op < 0 || reduce_op > 3) DBG_SET_ERR(c, DBG_E_BADARG, "unknown reduce_op %d", reduce_op);
+    if (reduce_op < 0 || reduce_op > DBG_REDUCE_SCMAP) DBG_SET_ERR(c, DBG_E_BADARG, "unknown reduce_op %d", reduce_op);
     int rc = t->k <= 32 ? compress_impl<1>(c, t, stranded, reduce_op, out) : compress_impl<2>(c, t, stranded, reduce_op, out);
     if (rc != DBG_OK && *out) { free_graph(*out); *out = nullptr; }
     return rc;

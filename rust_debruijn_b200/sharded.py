@@ -332,6 +332,8 @@ def compress_sharded(full, stranded, spec, group=None, lmax=1024, timings=None, 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cuda", ctx.device)
     k, V = full.k, len(full)
+    if spec.func > 3:
+        return None   # ScmapCompress: the sharded link stage has no join_test; the caller compresses replicated
     per = max((V + world - 1) // world, 1)          # equal index ranges: the link all-gather needs no padding logic
     v0, v1 = min(rank * per, V), min((rank + 1) * per, V)
     st = _lib_stream(ctx)

@@ -267,6 +267,23 @@ def test_graph_fix_exts(D, ctx, orc):
             assert np.array_equal(g2["words"], g["words"]) and np.array_equal(g2["data"], g["data"])
 
 
+def test_scmap_compress(D, ctx, orc):
+    """ScmapCompress (compression.rs:66-98, join_test = data equality) through compress_kmers: BaseGraph identical to the
+    oracle, fast path (noisy reads) and general path (clean reads: long unitigs broken only where the data changes)."""
+    for noisy, mo in ((True, 2), (False, 1)):
+        w, st, ln = orc.synth_reads(2000, 1, orc.ERR_THR_NOISY if noisy else 0)
+        ot = orc.filter_kmers(31, w, st, ln, min_obs=mo)
+        counts = (ot["counts"] % 3).astype(np.uint16)
+        g = D.compress_kmers(False, D.ScmapCompress(), (ot["lo"], None, ot["exts"], counts), k=31, ctx=ctx).to_host()
+        og = orc.compress_kmers(31, ot["lo"], ot["hi"], ot["exts"], counts, reduce_op=orc.SCMAP)
+        assert og["error"] == 0
+        assert_graphs_equal(g, og)
+    ot63 = orc.filter_kmers(63, w, st, ln, min_obs=1)
+    c63 = (ot63["counts"] % 2).astype(np.uint16)
+    g = D.compress_kmers(False, D.ScmapCompress(), (ot63["lo"], ot63["hi"], ot63["exts"], c63), k=63, ctx=ctx).to_host()
+    assert_graphs_equal(g, orc.compress_kmers(63, ot63["lo"], ot63["hi"], ot63["exts"], c63, reduce_op=orc.SCMAP))
+
+
 def test_count_saturation(D, ctx, orc):
     """filter.rs:57 counts saturate at 65535; compression.rs:495 single-k-mer node keeps raw data."""
     seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")

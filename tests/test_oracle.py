@@ -405,3 +405,31 @@ def test_graph_fix_exts_properties(orc):
     vn = np.arange(g["n_nodes"]) % 3 != 0
     nv = orc.graph_fix_exts(31, g, valid_nodes=vn)
     assert np.all(nv & ~ne == 0) and (nv != ne).any()
+
+
+def test_scmap_compress_properties(orc):
+    """ScmapCompress (compression.rs:66-98): join_test = data equality.  Every node's k-mers carry one data value (its own
+    data), two k-mers of a node never differ, and with all data equal the result is SimpleCompress's."""
+    w, st, ln = orc.synth_reads(1500, 1, orc.ERR_THR_NOISY)
+    t = orc.filter_kmers(31, w, st, ln, min_obs=2)
+    counts = (t["counts"] % 3).astype(np.uint16)           # few distinct values: long equal-data runs and many breaks
+    g = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], counts, reduce_op=orc.SCMAP)
+    g0 = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], counts, reduce_op=orc.MAX)
+    assert g["error"] == 0 and g["n_nodes"] > g0["n_nodes"] and g["n_bases"] - g["n_nodes"] * 30 == len(t["lo"])
+    # data of every k-mer of a node equals the node's data: look each node k-mer up in the table
+    idx = {int(k_): i for i, k_ in enumerate(t["lo"])}
+    mask = (1 << 62) - 1
+    for n in range(0, g["n_nodes"], 7):
+        b = orc.unpack_bases(g["words"], int(g["start"][n]), int(g["length"][n]))
+        x = 0
+        for j, base in enumerate(b):
+            x = ((x << 2) | int(base)) & mask
+            if j >= 30:
+                r = 0
+                for q in range(31):
+                    r |= (3 - ((x >> (2 * q)) & 3)) << (2 * (30 - q))
+                assert counts[idx[min(x, r)]] == g["data"][n]
+    same = np.full(len(counts), 5, np.uint16)
+    ga = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], same, reduce_op=orc.SCMAP)
+    gb = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], same, reduce_op=orc.MAX)
+    assert all(np.array_equal(ga[f], gb[f]) for f in ("words", "start", "length", "exts", "data"))
