@@ -148,6 +148,7 @@ uint64_t dbg_graph_len(const dbg_graph* g);      /* BaseGraph::len, src/graph.rs
 uint64_t dbg_graph_n_bases(const dbg_graph* g);  /* sequences.sequence.len()           */
 uint64_t dbg_graph_n_words(const dbg_graph* g);  /* ceil(n_bases / 32)                  */
 int dbg_graph_stranded(const dbg_graph* g);
+int dbg_graph_k(const dbg_graph* g);
 int dbg_graph_copy_out(const dbg_graph* g, uint64_t* words, uint64_t* start, uint32_t* length, uint8_t* exts,
                        uint16_t* data);
 /* BaseGraph::finish + DebruijnGraph::find_edges for EVERY (node, side) — src/graph.rs:116-142 (left_order / right_order),

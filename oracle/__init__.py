@@ -167,6 +167,26 @@ def graph_edges(k, g, stranded=False):
     return target.reshape(m, 2, 4), flags.reshape(m, 2, 4), pair
 
 
+def write_gfa(k, g, stranded=False):
+    """DebruijnGraph::write_gfa / node_to_gfa (src/graph.rs:538-614) as text: "H\\tVN:Z:debruijn-rs", then per node its S line,
+    the L lines of l_edges with target >= node_id ("-" out of the node), the L lines of r_edges with target > node_id ("+");
+    the target's orientation is "+" when it is entered through its Left side (Dir::Left => "+"), overlap (K-1)M."""
+    target, flags, _ = graph_edges(k, g, stranded=stranded)
+    out = ["H\tVN:Z:debruijn-rs\n"]
+    for n in range(int(g["n_nodes"])):
+        seq = "".join("ACGT"[int(b)] for b in unpack_bases(g["words"], int(g["start"][n]), int(g["length"][n])))
+        out.append("S\t%d\t%s\n" % (n, seq))
+        for i in range(4):
+            t = int(target[n, 0, i])
+            if t != 0xffffffff and t >= n:
+                out.append("L\t%d\t-\t%d\t%s\t%dM\n" % (n, t, "-" if flags[n, 0, i] & 1 else "+", k - 1))
+        for i in range(4):
+            t = int(target[n, 1, i])
+            if t != 0xffffffff and t > n:
+                out.append("L\t%d\t+\t%d\t%s\t%dM\n" % (n, t, "-" if flags[n, 1, i] & 1 else "+", k - 1))
+    return "".join(out)
+
+
 def graph_fix_exts(k, g, stranded=False, valid_nodes=None):
     """DebruijnGraph::fix_exts / get_valid_exts (src/graph.rs:337-377): an extension survives iff find_link resolves it
     (and the target is in valid_nodes when given).  Returns the new node Exts array."""

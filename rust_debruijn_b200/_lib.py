@@ -79,6 +79,7 @@ SIGNATURES = {
     "dbg_graph_n_bases": (C.c_uint64, [vp]),
     "dbg_graph_n_words": (C.c_uint64, [vp]),
     "dbg_graph_stranded": (C.c_int, [vp]),
+    "dbg_graph_k": (C.c_int, [vp]),
     "dbg_graph_copy_out": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "dbg_graph_edges": (C.c_int, [vp, vp, vp, vp]),
     "dbg_graph_fix_exts": (C.c_int, [vp, vp, vp]),

@@ -260,6 +260,22 @@ class PackedDnaStringSet:
         return ((w >> (np.uint64(62) - np.uint64(2) * (idx & np.uint64(31)))) & np.uint64(3)).astype(np.uint8)
 
 
+def format_gfa(k, g, target, flags):
+    """Text of DebruijnGraph::write_gfa (src/graph.rs:538-614) from host node arrays and find_edges results."""
+    words, start, length = g["words"], g["start"], g["length"]
+    lines = ["H\tVN:Z:debruijn-rs"]
+    for n in range(int(g["n_nodes"])):
+        idx = np.arange(int(start[n]), int(start[n]) + int(length[n]), dtype=np.uint64)
+        b = (words[(idx >> np.uint64(5)).astype(np.int64)] >> (np.uint64(62) - np.uint64(2) * (idx & np.uint64(31)))) & np.uint64(3)
+        lines.append(f"S\t{n}\t" + "".join("ACGT"[int(x)] for x in b))
+        for d, sign, keep in ((0, "-", lambda t: t >= n), (1, "+", lambda t: t > n)):   # l_edges then r_edges
+            for i in range(4):
+                t = int(target[n, d, i])
+                if t != 0xffffffff and keep(t):
+                    lines.append(f"L\t{n}\t{sign}\t{t}\t{'-' if flags[n, d, i] & 1 else '+'}\t{k - 1}M")
+    return "\n".join(lines) + "\n"
+
+
 class BaseGraph:
     """src/graph.rs:44-114.  Device-resident (dbg_graph) until to_host() is called."""
 
@@ -305,6 +321,19 @@ class BaseGraph:
                 raise ValueError("valid_nodes needs one entry per node")
         self.ctx.check(self.ctx._L.dbg_graph_fix_exts(self.ctx._h, self._h, _ptr(valid_nodes)))
         self._host = None
+
+    def write_gfa(self, out):
+        """DebruijnGraph::write_gfa (src/graph.rs:538-614): header, one S line per node, L lines for the left edges with
+        target >= node and the right edges with target > node (edge direction '+' = enters the target through its left
+        side), overlap (K-1)M.  `out`: path or text file object.  Edges come from dbg_graph_edges on the device."""
+        g = self.to_host()
+        target, flags = self.edges()
+        text = format_gfa(self.ctx._L.dbg_graph_k(self._h), g, target, flags)
+        if hasattr(out, "write"):
+            out.write(text)
+        else:
+            with open(out, "w") as f:
+                f.write(text)
 
     @property
     def sequences(self):

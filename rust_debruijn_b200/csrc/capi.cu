@@ -838,6 +838,7 @@ uint64_t dbg_graph_len(const dbg_graph* g) { return g ? g->g.n_nodes : 0; }
 uint64_t dbg_graph_n_bases(const dbg_graph* g) { return g ? g->g.n_bases : 0; }
 uint64_t dbg_graph_n_words(const dbg_graph* g) { return g ? g->g.n_words : 0; }
 int dbg_graph_stranded(const dbg_graph* g) { return g ? g->g.stranded : 0; }
+int dbg_graph_k(const dbg_graph* g) { return g ? g->g.k : 0; }
 
 int dbg_graph_copy_out(const dbg_graph* h, uint64_t* words, uint64_t* start, uint32_t* length, uint8_t* exts,
                        uint16_t* data) {

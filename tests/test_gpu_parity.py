@@ -284,6 +284,20 @@ def test_scmap_compress(D, ctx, orc):
     assert_graphs_equal(g, orc.compress_kmers(63, ot63["lo"], ot63["hi"], ot63["exts"], c63, reduce_op=orc.SCMAP))
 
 
+def test_write_gfa(D, ctx, orc):
+    """BaseGraph.write_gfa (DebruijnGraph::write_gfa, graph.rs:538-614; edges from dbg_graph_edges) = the oracle's text."""
+    import io
+    w, st, ln = orc.synth_reads(1200, 1, orc.ERR_THR_NOISY)
+    for k, stranded in ((31, False), (32, True)):
+        table, _ = D.filter_kmers((w, st, ln), D.CountFilter(2), stranded, False, 4, k=k, ctx=ctx)
+        D.remove_censored_exts(stranded, table)
+        graph = D.compress_kmers_with_hash(stranded, D.SimpleCompress(D.SAT_ADD), table)
+        buf = io.StringIO()
+        graph.write_gfa(buf)
+        assert buf.getvalue() == orc.write_gfa(k, graph.to_host(), stranded=stranded)
+        assert buf.getvalue().count("\nL\t") > 0
+
+
 def test_count_saturation(D, ctx, orc):
     """filter.rs:57 counts saturate at 65535; compression.rs:495 single-k-mer node keeps raw data."""
     seq = enc("ACGTTGCATGCATCGATCGATCGTAGCTAGA")

@@ -433,3 +433,24 @@ def test_scmap_compress_properties(orc):
     ga = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], same, reduce_op=orc.SCMAP)
     gb = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], same, reduce_op=orc.MAX)
     assert all(np.array_equal(ga[f], gb[f]) for f in ("words", "start", "length", "exts", "data"))
+
+
+def test_write_gfa_format(orc):
+    """DebruijnGraph::write_gfa (graph.rs:538-614): header, one S line per node in node order, every link reported once
+    (left edges with target >= node, right edges with target > node), overlap K-1."""
+    seq = "ACGTTGCATGCATCGATCGATCGTAGCTAGAGGATCCATTAGC"
+    a, b = seq + "A" + "GGTCAAT" * 5, seq + "C" + "TTGACAT" * 5      # a fork after the shared prefix
+    ss = orc.seqset_from_lists([enc(a), enc(a), enc(b), enc(b)])
+    t = orc.filter_kmers(31, *ss, min_obs=2)
+    g = orc.compress_kmers(31, t["lo"], t["hi"], t["exts"], t["counts"])
+    text = orc.write_gfa(31, g)
+    lines = text.splitlines()
+    assert lines[0] == "H\tVN:Z:debruijn-rs"
+    s_lines = [l for l in lines if l.startswith("S\t")]
+    l_lines = [l for l in lines if l.startswith("L\t")]
+    assert len(s_lines) == g["n_nodes"] == 3 and [int(l.split("\t")[1]) for l in s_lines] == [0, 1, 2]
+    assert len(l_lines) == 2 and all(l.endswith("\t30M") for l in l_lines)
+    for l in l_lines:
+        f = l.split("\t")
+        assert f[2] in "+-" and f[4] in "+-" and int(f[1]) <= int(f[3])
+    assert sum(len(l.split("\t")[2]) for l in s_lines) == g["n_bases"]
