@@ -481,6 +481,17 @@ def test_sharded_two_gpus():
     assert r.stdout.count("node-sharded BIT-EXACT") == 3 and r.stdout.count("BIT-EXACT") == 6 and "MISMATCH" not in r.stdout
 
 
+def test_full_size_properties():
+    """BASELINE.json configs[1] at its FULL size (10M x 150bp, K=31; the oracle would need minutes): size-independent
+    properties through tools/fullsize_check.py — ascending distinct k-mers, node bookkeeping, sampled nodes re-derived from the
+    table (membership + saturating data), direct and staged partition bit-identical."""
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fullsize_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "FULLSIZE OK" in r.stdout and "FAIL" not in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_compress_kmers_slice_variant(D, ctx, orc):
     """compression::compress_kmers (src/compression.rs:598-615): unordered (k-mer, (exts, data)) slice."""
     ss = orc.synth_reads(1500, 1, orc.ERR_THR_NOISY)
