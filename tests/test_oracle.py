@@ -454,3 +454,20 @@ def test_write_gfa_format(orc):
         f = l.split("\t")
         assert f[2] in "+-" and f[4] in "+-" and int(f[1]) <= int(f[3])
     assert sum(len(l.split("\t")[2]) for l in s_lines) == g["n_bases"]
+
+
+def test_widened_rows_golden(orc):
+    """The oracle's outputs for the widened rows (remove_censored_exts, graph edges / is_compressed, fix_exts, GFA text,
+    ScmapCompress, from_acgt_bytes) equal the committed vectors of tests/golden/widened.json (made by
+    tests/golden/make_golden.py from this same oracle: a regression pin, the reference has no expected outputs here)."""
+    import importlib.util
+    import json
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    want = json.load(open(os.path.join(here, "golden", "widened.json")))["rows"]
+    assert mg.rows() == want
+    # one number here IS independently anchored: SURVEY.md §4 (second, independent restatement made during the survey) found
+    # 68 nodes for synth-v1 noisy R=1000, K=31 after remove_censored_exts semantics (896 without pruning, Appendix B)
+    assert want[0]["pruned_nodes"] == 68 and want[0]["n_valid"] == 3584
