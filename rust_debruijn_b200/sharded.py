@@ -8,12 +8,16 @@ exactly the unsharded table.
 
 compress_kmers does not shard with a single exchange (unitigs cross buckets): the valid k-mers (V ~ 0.03 N) are
 redistributed by key range, sorted per range and replicated; the compression WORK is then split by k-mer index
-range / node range with the single-GPU fast-path kernels (link pairs and path records all-gathered, node arrays
-all-reduced), so every rank ends with the same, complete BaseGraph.  Long unitigs / cycles fall back to the
+range / seed range with the single-GPU fast-path kernels (link pairs all-gathered, path records shipped to the
+rank owning their seed range).  Every rank then holds a contiguous run of nodes of the final order: it keeps it
+(replicate=False; the runs concatenated in rank order are the single-GPU BaseGraph bit for bit) or the runs are
+all-reduced into the complete graph on every rank (replicate=True).  Long unitigs / cycles fall back to the
 replicated single-GPU compression.
 
-The pure planning helpers (owner_bounds, split_by_owner, exchange_counts) use only torch CPU/any-backend
-collectives and are covered by world_size-2 gloo tests on CPU."""
+Every torch op and collective runs under the library's own CUDA stream (_lib_stream), so library kernels, NCCL and
+torch are stream-ordered without host synchronisation.  The pure planning helpers (owner_bounds, split_by_owner,
+exchange_counts, key_range_splitters, balanced_seed_bounds) use only torch CPU/any-backend collectives and are
+covered by world_size-2/3 gloo tests on CPU."""
 import ctypes as C
 import math
 
