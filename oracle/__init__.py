@@ -13,10 +13,38 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liboracle.so")
 
 
+def _cpu_id():
+    """Identity of the host CPU (model + ISA flags): the library is built -march=native, so a copy built on another
+    machine (this repo travels to the GPU box as a snapshot) must be rebuilt before it is loaded."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            lines = [ln for ln in f if ln.startswith(("model name", "flags"))][:2]
+        return hashlib.sha1("".join(lines).encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
 def build(force=False):
     src = os.path.join(_HERE, "oracle.cpp")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    stamp = os.path.join(_HERE, ".build_cpu")
+    cpu = _cpu_id()
+    try:
+        with open(stamp) as f:
+            built_for = f.read().strip()
+    except OSError:
+        built_for = None
+    stale = not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src) or built_for != cpu
+    if force or stale:
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-B", "-s"], stdout=subprocess.DEVNULL)
+        except (subprocess.CalledProcessError, OSError):
+            if os.path.exists(_SO) and built_for is None:
+                return _SO   # no compiler here: keep the shipped library (built x86-64-v2 compatible by the fallback below)
+            subprocess.check_call(["make", "-C", _HERE, "-B", "-s", "ARCH=-march=x86-64-v2 -mtune=generic"],
+                                  stdout=subprocess.DEVNULL)
+        with open(stamp, "w") as f:
+            f.write(cpu)
     return _SO
 
 

@@ -178,6 +178,10 @@ class CountFilter:
 
     def __init__(self, min_kmer_obs):
         self.min_kmer_obs = int(min_kmer_obs)
+        if self.min_kmer_obs < 0:
+            raise ValueError("CountFilter: min_kmer_obs must be >= 0")
+        # counts saturate at 65535 (filter.rs:57): any larger threshold censors everything, and the ABI takes a u32
+        self.min_kmer_obs = min(self.min_kmer_obs, 65536)
 
 
 class SimpleCompress:

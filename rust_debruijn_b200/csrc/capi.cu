@@ -218,8 +218,9 @@ int dbg_seqset_upload(dbg_ctx* ctx, const uint64_t* words, uint64_t n_words, con
     u32 max_len = 0;
     bool uniform = n_seqs > 0, contiguous = n_seqs > 0;
     for (u64 i = 0; i < n_seqs; i++) {
+        const u64 limit = n_words * 32;   // overflow-safe: start near 2^64 must not wrap past the check
+        if (start[i] > limit || length[i] > limit - start[i]) DBG_SET_ERR(c, DBG_E_BADARG, "sequence %llu runs past the packed words", (unsigned long long)i);
         u64 e = (u64)start[i] + length[i];
-        if (e > n_words * 32) DBG_SET_ERR(c, DBG_E_BADARG, "sequence %llu runs past the packed words", (unsigned long long)i);
         if (length[i] > max_len) max_len = length[i];
         if (uniform && (length[i] != length[0] || start[i] != i * (u64)length[0])) uniform = false;
         if (contiguous && i + 1 < n_seqs && start[i + 1] != e) contiguous = false;
@@ -381,7 +382,7 @@ int dbg_seqset_from_ascii(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, 
     u32 max_len = 0;
     bool uniform = n_seqs > 0;
     for (u64 i = 0; i < n_seqs; i++) {
-        if ((u64)start[i] + length[i] > n_bytes) DBG_SET_ERR(c, DBG_E_BADARG, "sequence %llu runs past the ASCII buffer", (unsigned long long)i);
+        if (start[i] > n_bytes || length[i] > n_bytes - start[i]) DBG_SET_ERR(c, DBG_E_BADARG, "sequence %llu runs past the ASCII buffer", (unsigned long long)i);
         ostart[i + 1] = ostart[i] + length[i];
         if (length[i] > max_len) max_len = length[i];
         if (length[i] != length[0]) uniform = false;
@@ -547,11 +548,15 @@ __global__ void unpack_vals_kernel2(const u32* val, u8* exts, u16* counts, u64 n
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { u32 v = val[i]; exts[i] = (u8)v; counts[i] = (u16)(v >> 8); }
 }
-__global__ void check_sorted_unique_kernel(const u64* lo, const u64* hi, u64 n, u32* bad) {
+// bad = 1: not ascending / duplicate; bad = 2: bits set above the 2k key bits (VarIntKmer equality is on raw storage,
+// src/kmer.rs:438-442: such keys would sort and compare differently from the k-mers they spell)
+__global__ void check_sorted_unique_kernel(const u64* lo, const u64* hi, u64 n, u32* bad, u64 mask_lo, u64 mask_hi) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if ((lo[i] & ~mask_lo) || (hi && (hi[i] & ~mask_hi))) { *bad = 2; return; }
     if (i + 1 >= n) return;
     bool ok = hi ? (hi[i] < hi[i + 1] || (hi[i] == hi[i + 1] && lo[i] < lo[i + 1])) : lo[i] < lo[i + 1];
-    if (!ok) *bad = 1;
+    if (!ok) atomicMax(bad, 1u);
 }
 
 static int table_from_arrays(dbg_ctx* ctx, int k, uint64_t n, const void* kmers_lo, const void* kmers_hi,
@@ -591,13 +596,13 @@ static int table_from_arrays(dbg_ctx* ctx, int k, uint64_t n, const void* kmers_
     unpack_vals_kernel2<<<grid_for(n, 256), 256, 0, c->stream>>>(rv, de.p, dc.p, n);
     T2(check_launch(c, "unpack_vals"));
     T2(bad.zero());
-    check_sorted_unique_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(rlo, W == 2 ? rhi : nullptr, n, bad.p);
+    check_sorted_unique_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(rlo, W == 2 ? rhi : nullptr, n, bad.p, make_kp(k).mask_lo, make_kp(k).mask_hi);
     T2(check_launch(c, "check_sorted_unique"));
     u32 hbad = 0;
     CU2(cudaMemcpyAsync(c->h_scratch, bad.p, 4, cudaMemcpyDeviceToHost, c->stream));
     CU2(spin_sync(c->stream));
     hbad = *(u32*)c->h_scratch;
-    if (hbad) { c->err = "duplicate k-mers in table"; return fail(DBG_E_BADARG); }
+    if (hbad) { c->err = hbad == 2 ? "k-mer words have bits set above the 2k key bits" : "duplicate k-mers in table"; return fail(DBG_E_BADARG); }
     t->lo = (rlo == alo.p) ? alo.take() : blo.take();
     if (W == 2) t->hi = (rhi == ahi.p) ? ahi.take() : bhi.take();
     t->exts = de.take();
@@ -645,11 +650,11 @@ int dbg_table_from_device_sorted(dbg_ctx* ctx, int k, uint64_t n, const void* d_
     if (two) cudaMemcpyAsync(hi.p, d_hi, n * 8, cudaMemcpyDeviceToDevice, c->stream);
     cudaMemcpyAsync(ex.p, d_exts, n, cudaMemcpyDeviceToDevice, c->stream);
     cudaMemcpyAsync(cn.p, d_counts, n * 2, cudaMemcpyDeviceToDevice, c->stream);
-    check_sorted_unique_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(lo.p, two ? hi.p : nullptr, n, bad.p);
+    check_sorted_unique_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(lo.p, two ? hi.p : nullptr, n, bad.p, make_kp(k).mask_lo, make_kp(k).mask_hi);
     c->launches++;
     cudaMemcpyAsync(c->h_scratch, bad.p, 4, cudaMemcpyDeviceToHost, c->stream);
     if (spin_sync(c->stream) != cudaSuccess) { delete h; DBG_SET_ERR(c, DBG_E_CUDA, "table_from_device_sorted: %s", cudaGetErrorString(cudaGetLastError())); }
-    if (*(u32*)c->h_scratch) { delete h; DBG_SET_ERR(c, DBG_E_BADARG, "arrays are not ascending and distinct"); }
+    if (*(u32*)c->h_scratch) { const bool hb = *(u32*)c->h_scratch == 2; delete h; DBG_SET_ERR(c, DBG_E_BADARG, hb ? "k-mer words have bits set above the 2k key bits" : "arrays are not ascending and distinct"); }
     t->lo = lo.take();
     if (two) t->hi = hi.take();
     t->exts = ex.take();

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sched.h>
 #include <string>
 #include <vector>
 
@@ -147,12 +148,17 @@ inline int arena_begin(Ctx* c) {
     return DBG_OK;
 }
 
-// Host waits spin on cudaStreamQuery instead of blocking in cudaStreamSynchronize: the path has ~10 short waits per call
+// Host waits poll cudaStreamQuery instead of blocking in cudaStreamSynchronize: the path has a few short waits per call
 // (sizes read back between stages), and on a shared host a thread that went to sleep in the driver can take tens of
-// milliseconds to be scheduled again — far longer than the kernels it waits for.
+// milliseconds to be scheduled again — far longer than the kernels it waits for.  The first ~50 us are a pure spin
+// (most waits end there); after that every poll is followed by sched_yield(), so a rank waiting on a long kernel does
+// not starve the other rank processes / producer threads of the node while staying runnable itself.
 inline cudaError_t spin_sync(cudaStream_t st) {
     cudaError_t e;
-    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {}
+    int spins = 0;
+    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {
+        if (++spins > 64) sched_yield();
+    }
     return e;
 }
 inline int sync(Ctx* c) {

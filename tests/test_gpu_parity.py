@@ -339,7 +339,8 @@ def test_bucket_split_path(D, ctx, orc):
     ss = orc.synth_reads(3000, 1, orc.ERR_THR_NOISY)
     for k in (31, 63):
         t, g = run_both(D, c2, orc, k, ss, 2, report_all=True)
-    assert c2.stats()["n_bucket_splits"] > 0 or True
+        # ~20 000 (27 000) distinct k-mers in one bucket against an 8192-slot table: the splitting must have run
+        assert c2.stats()["n_buckets"] == 1 and c2.stats()["n_bucket_splits"] > 0, c2.stats()
     c2.close()
 
 
@@ -481,15 +482,92 @@ def test_sharded_two_gpus():
     assert r.stdout.count("node-sharded BIT-EXACT") == 3 and r.stdout.count("BIT-EXACT") == 6 and "MISMATCH" not in r.stdout
 
 
-def test_full_size_properties():
-    """BASELINE.json configs[1] at its FULL size (10M x 150bp, K=31; the oracle would need minutes): size-independent
-    properties through tools/fullsize_check.py — ascending distinct k-mers, node bookkeeping, sampled nodes re-derived from the
-    table (membership + saturating data), direct and staged partition bit-identical."""
-    import subprocess
-    import sys
-    root = os.path.dirname(HERE)
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fullsize_check.py")], capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and "FULLSIZE OK" in r.stdout and "FAIL" not in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+def _full_size_bit_exact(D, orc, k, also_staged):
+    """BASELINE.json configs[1] / configs[2] at their FULL size (10M x 150bp synth-v1 noisy reads): the whole k-mer table
+    and every BaseGraph array compared with the oracle (multi-threaded filter stage; the greedy walk is serial)."""
+    import os
+    R = 10_000_000
+    ctx = D.Context(0)
+    ss = D.SeqSet.synth(ctx, R, 1, orc.ERR_THR_NOISY)
+    table, graph = D.reads_to_graph(ss, D.CountFilter(2), D.SimpleCompress(D.SAT_ADD), k=k, keep_table=True)
+    st = ctx.stats()
+    t, g = table.to_host(), graph.to_host()
+    table.free(); graph.free()
+    if also_staged:   # the staged partition (what pipelined uploads and small inputs use) must give the same table
+        assert st["direct_partition"] == 1
+        ctx.set_param("direct_partition", 0)
+        t2 = D.filter_kmers(ss, D.CountFilter(2), False, False, 0, k=k)[0]
+        assert ctx.stats()["direct_partition"] == 0
+        h2 = t2.to_host()
+        t2.free()
+        assert_tables_equal(t, h2)
+        del h2
+    ss.free()
+    ctx.close()
+    w, s_, l = orc.synth_reads(R, 1, orc.ERR_THR_NOISY)
+    ot = orc.filter_kmers(k, w, s_, l, min_obs=2, threads=os.cpu_count() or 1)
+    del w, s_, l
+    assert t["n_input"] == ot["n_input"] == R * (150 - k + 1)
+    assert_tables_equal(t, ot)
+    og = orc.compress_kmers(k, ot["lo"], ot["hi"], ot["exts"], ot["counts"])
+    assert og["error"] == 0
+    assert_graphs_equal(g, og)
+    V, M = len(t["lo"]), g["n_nodes"]
+    assert int(g["length"].astype(np.uint64).sum()) == V + M * (k - 1) == g["n_bases"]
+
+
+def test_full_size_config1_bit_exact(D, orc):
+    """configs[1]: K=31, 10^7 reads, N = 1.2 * 10^9 k-mers — table and graph byte-identical to the oracle."""
+    _full_size_bit_exact(D, orc, 31, also_staged=True)
+
+
+def test_full_size_config2_k63_bit_exact(D, orc):
+    """configs[2]: K=63 (two-u64 keys), 10^7 reads, N = 8.8 * 10^8 k-mers — table and graph byte-identical to the oracle."""
+    _full_size_bit_exact(D, orc, 63, also_staged=False)
+
+
+def _canon_form(orc, g):
+    """SURVEY §8c L1: multiset of (min(seq, rc seq), exts passed through Exts::rc when the rc was chosen, data)."""
+    L = orc.lib()
+    out = []
+    for i in range(g["n_nodes"]):
+        b = orc.unpack_bases(g["words"], int(g["start"][i]), int(g["length"][i]))
+        r = (3 - b[::-1]).astype(np.uint8)
+        e = int(g["exts"][i])
+        if bytes(r) < bytes(b):
+            b, e = r, L.orc_exts_rc(e)
+        out.append((bytes(b), e, int(g["data"][i])))
+    return sorted(out)
+
+
+@pytest.mark.parametrize("k", [31, 32, 63])
+def test_canonical_form_invariant_to_seed_order(D, ctx, orc, k):
+    """The reference seeds unitigs in boomphf slot order (src/compression.rs:574-580), which this repo cannot reproduce
+    (third-party hash, un-pinned).  The boomphf-proof statement: the CANONICAL form of the GPU graph equals the canonical
+    form of the greedy walk run under ANY seed order — checked against 5 shuffled orders on acyclic data (only cyclic
+    components depend on the order: their break-point moves)."""
+    rng = np.random.default_rng(900 + k)
+    contigs = [c for c in random_contigs(rng) if len(c) >= k]
+    ss = orc.seqset_from_lists(contigs + contigs)
+    table, _ = D.filter_kmers(ss, D.CountFilter(2), False, False, 4, k=k, ctx=ctx)
+    g = D.compress_kmers_with_hash(False, D.SimpleCompress(D.SAT_ADD), table).to_host()
+    t = table.to_host()
+    mine = _canon_form(orc, g)
+    for it in range(5):
+        perm = rng.permutation(len(t["lo"])).astype(np.uint32)
+        og = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], seed_order=perm)
+        assert og["error"] == 0 and og["n_nodes"] == g["n_nodes"]
+        assert _canon_form(orc, og) == mine, f"canonical graph differs under shuffled seed order {it}"
+    # noisy synthetic reads as well (censored k-mers leave dangling Exts: many short unitigs)
+    ss = orc.synth_reads(3000, 1, orc.ERR_THR_NOISY)
+    table, _ = D.filter_kmers(ss, D.CountFilter(2), False, False, 4, k=k, ctx=ctx)
+    g = D.compress_kmers_with_hash(False, D.SimpleCompress(D.SAT_ADD), table).to_host()
+    t = table.to_host()
+    mine = _canon_form(orc, g)
+    for it in range(5):
+        perm = rng.permutation(len(t["lo"])).astype(np.uint32)
+        og = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], seed_order=perm)
+        assert _canon_form(orc, og) == mine
 
 
 def test_compress_kmers_slice_variant(D, ctx, orc):
