@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <sched.h>
+#include <time.h>
 #include <string>
 #include <vector>
 
@@ -149,15 +150,25 @@ inline int arena_begin(Ctx* c) {
 }
 
 // Host waits poll cudaStreamQuery instead of blocking in cudaStreamSynchronize: the path has a few short waits per call
-// (sizes read back between stages), and on a shared host a thread that went to sleep in the driver can take tens of
-// milliseconds to be scheduled again — far longer than the kernels it waits for.  The first ~50 us are a pure spin
-// (most waits end there); after that every poll is followed by sched_yield(), so a rank waiting on a long kernel does
-// not starve the other rank processes / producer threads of the node while staying runnable itself.
+// (sizes read back between stages), and on a shared host a thread that went to sleep in the driver — or that gave up
+// its time slice with sched_yield(), measured in round 2: isolated 35-95 ms steps — can take tens of milliseconds to be
+// scheduled again, far longer than the kernels it waits for.  Every wait of the steady-state path ends within a few
+// milliseconds, so the poll is a pure spin for the first 50 ms; only a wait that outlives that (a cold start, a huge
+// input) starts yielding between polls so that it does not pin a core for seconds.
 inline cudaError_t spin_sync(cudaStream_t st) {
     cudaError_t e;
-    int spins = 0;
+    timespec t0, t1;
+    bool timed = false, polite = false;
+    unsigned spins = 0;
     while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {
-        if (++spins > 64) sched_yield();
+        if (polite) { sched_yield(); continue; }
+        if ((++spins & 1023u) == 0) {
+            if (!timed) { clock_gettime(CLOCK_MONOTONIC, &t0); timed = true; }
+            else {
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                polite = (t1.tv_sec - t0.tv_sec) * 1000000000ll + (t1.tv_nsec - t0.tv_nsec) > 50000000ll;
+            }
+        }
     }
     return e;
 }

@@ -185,44 +185,88 @@ __global__ void __launch_bounds__(P1_THREADS) msp_partition_kernel(KP kp, P1Args
 }
 
 // ------------------------------------------------------------------------------------------------
-// P1 fast path: tile-per-CTA partition for CONTIGUOUSLY packed sequences (PackedDnaStringSet::add
-// layout: start[i+1] = start[i] + length[i]; uniform-length reads are the arithmetic special case).
-// A tile is TP consecutive base positions of the concatenation.  Three position-parallel phases in
-// shared memory, no per-sequence control flow:
-//   A  scores     thread = 4 consecutive p-mers: 3 LDS.32 + funnel shifts, canonical + hash, STS.128
-//   B  buckets    thread = 4 consecutive k-mers: register-tiled window minimum (w/4 LDS.128 per 4 outputs)
-//   C  records    lane = position: validity from a sequence-boundary bitmap, run starts by ballot,
-//                 the lane that sees a run END emits the record(s)
+// P1 fast path: partition of CONTIGUOUSLY packed sequences (PackedDnaStringSet::add layout:
+// start[i+1] = start[i] + length[i]; uniform-length reads are the arithmetic special case).
+//
+// Round-2 form: no CTA-wide barrier in the steady state.  BLOCKS of packed words (8 warp tiles, ~1 KB)
+// stream from HBM into a 4-deep shared-memory ring by bulk asynchronous copies (cp.async.bulk = TMA,
+// completion on the slot's "full" mbarrier).  The 8 warps of a CTA CLAIM warp tiles from a ticket
+// counter and process each on their own, synchronising with __syncwarp only; a finished tile arrives on
+// the slot's "empty" mbarrier, and the warp that finishes a block's last tile refills the slot the
+// previous block has left (no producer warp, nobody polls).  Warps of a CTA drift a few blocks apart,
+// warps of different CTAs are independent: the phases below (which used to be separated by
+// __syncthreads and left half the issue slots idle) overlap freely across the 40 resident warps of an SM.
+//
+// A warp tile EXAMINES 512 consecutive k-mer start positions (16 per lane) and OWNS the first
+// tpw = 512 - (w - 1) of them (w = K - p + 1 p-mers per window): the 512 p-mer scores it computes are
+// then exactly the ones its owned windows need, so no halo is ever recomputed.
+//   A  scores     lane = 4 consecutive p-mers x 4 rounds: 3 LDS.32 + funnel shifts, canonical + hash, STS.128
+//   B  buckets    lane = 4 consecutive k-mers x 4 rounds: register-tiled window minimum
+//   C  runs       lane = 16 positions: validity / sequence-start / bucket-change masks, run starts and
+//                 closers by bit tricks + two warp scans; closed runs go to the warp's queue
+//   D  records    lane = one queued run: slot from the bucket's cursor (direct mode) or from the warp's
+//                 staging chunk, 16/32-byte record assembled from the staged bases, one vector store
 // ------------------------------------------------------------------------------------------------
-static const int T1_THREADS = 256;
-static const int T1_WARPS = T1_THREADS / 32;
-static const int TP = 4096;                          // k-mer start positions per tile
-static const int T1_SEG = TP / T1_WARPS;             // positions per warp in phase C
-static const int T1_NB = TP + 64 + 2 + 32;           // staged bases: left flank + tile + K + right flank + alignment slack
-static const int T1_S32 = T1_NB / 16 + 6;            // staged 2-bit data as u32 in base order
-static const int T1_SC = TP + 64 + 8;                // p-mer scores
-static const int T1_BM = T1_NB / 32 + 4;             // boundary bitmap words
-static const int T1_QCAP = TP;                       // CTA queue of closed runs (<= one per k-mer start)
+static const int WT_CW = 8;                          // consumer warps per CTA
+static const int WT_THREADS = WT_CW * 32;
+static const int WT_CTAS = 5;                        // resident CTAs per SM (42.6 KB static shared memory each)
+static const int WT_REG_CTAS = 6;                    // register budget of __launch_bounds__: 40 registers (the 48-register build ran 5% slower)
+static const int WP = 512;                           // positions a warp tile examines
+static const int WSC = WP + 64 + 8;                  // p-mer scores per warp tile (+ what the un-owned windows may touch)
+static const int WBK = WP + WP / 16 + 8;             // bucket of every examined position, padded (bkpad)
+static const int WBM = 24;                           // bitmap words per warp tile (>= (31 + WP + 64 + 2) / 32 + 3)
+static const int NST = 4;                            // ring depth
+static const int SB_BYTES = 1088;                    // bytes staged per block (8 warp tiles + flanks), multiple of 16
+static const int SBW = 288;                          // u32 words per ring slot
+static const int TP = 4096;                          // (size unit of the direct_min_tiles parameter only)
 
 struct TileArgs {
     u64 base0;      // global position of the first base (start[0])
     u64 total_end;  // global position one past the last base
-    u64 tile0;      // first tile of this launch
-    u64 n_tiles;    // one past the last tile of this launch
-    u32 tstride;    // visit every tstride-th tile (1 = all; > 1 = sampling pass)
+    u64 tile0;      // first block of this launch
+    u64 n_tiles;    // one past the last block of this launch
+    u32 tstride;    // visit every tstride-th block (1 = all; > 1 = sampling pass)
 };
+// positions one block covers (host and device agree on this): 8 warp tiles of 512 - (w - 1) owned positions
+__host__ __device__ __forceinline__ u32 tile_owned(int k, int p) { return (u32)(WP - (k - p)); }
 
-__device__ __forceinline__ u32 s32_bits(const u32* s32, u32 b) {  // 32 bits starting at staged base b
-    u32 i = b >> 4;
-    return __funnelshift_l(s32[i + 1], s32[i], 2 * (b & 15));
+// ---- mbarrier + bulk-copy primitives (PTX ISA 8.x, sm_90+; SASS: SYNCS.*, UBLKCP) ----
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ u32 s32_base(const u32* s32, u32 b) { return (s32[b >> 4] >> (30 - 2 * (b & 15))) & 3u; }
-__device__ __forceinline__ u64 bm_bits(const u32* bm, u32 b) {  // 64 boundary bits starting at staged index b (LSB = b)
-    u32 i = b >> 5, sh = b & 31;
-    u32 lo = __funnelshift_r(bm[i], bm[i + 1], sh);
-    u32 hi = __funnelshift_r(bm[i + 1], bm[i + 2], sh);
-    return ((u64)hi << 32) | lo;
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(u32 addr, u32 parity) {
+    u32 ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+// consumer side: the data is almost always there already (the ring runs 3 blocks ahead)
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    const u32 addr = smem_u32(bar);
+    while (!mbar_try_wait(addr, parity)) __nanosleep(64);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"((u64)__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// The ring slots hold the packed u64 words exactly as they lie in HBM; read as u32, the word of BASE-ORDER index j
+// (16 bases each, first base in the top bits) sits at u32 index j ^ 1 (little-endian halves of a u64).
+__device__ __forceinline__ u32 st_word(const u32* st, u32 j) { return st[j ^ 1u]; }
+__device__ __forceinline__ u32 st_bits(const u32* st, u32 b) {  // 32 bits starting at staged base b
+    const u32 i = b >> 4;
+    return __funnelshift_l(st_word(st, i + 1), st_word(st, i), 2 * (b & 15));
+}
+__device__ __forceinline__ u32 st_base(const u32* st, u32 b) { return (st_word(st, b >> 4) >> (30 - 2 * (b & 15))) & 3u; }
+__device__ __forceinline__ u32 bm_bit(const u32* bm, u32 b) { return (bm[b >> 5] >> (b & 31)) & 1u; }
 __device__ __forceinline__ u32 bm_bits32(const u32* bm, u32 b) {  // 32 bitmap bits starting at index b (LSB = b)
     u32 i = b >> 5;
     return __funnelshift_r(bm[i], bm[i + 1], b & 31);
@@ -239,17 +283,19 @@ __device__ __forceinline__ u64 seq_index_of(const u64* __restrict__ start, u64 n
     return lo - 1;
 }
 
+// One record: run of nn k-mers starting at tile position ps.  st = ring slot (staged origin sb, global), ofs = staged
+// index of tile position 0, bm = the warp's boundary bitmap whose bit 0 is staged index wo.
 template <int W>
-__device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs& ta, int K, const u32* s_s32, const u32* s_bm,
+__device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs& ta, int K, const u32* st, const u32* bm, u32 wo,
                                                  u32 bkt, u64 sb, u32 ofs, int ps, int nn, u64 slot, bool ok) {
     // `slot` / `ok` may depend on an atomic that is still in flight (direct partition): nothing below touches them
     // until the final store, so the record is assembled while the atomic travels
     constexpr int RW = RecLayout<W>::WORDS;
-    u32 eb = ofs + (u32)ps;            // staged index of the run's first base
-    u32 nbase = (u32)nn + K - 1;
-    u64 gpos = sb + eb;
-    bool at_first = (bm_bits(s_bm, eb) & 1ull) != 0;                                           // run starts a sequence
-    bool at_last = (bm_bits(s_bm, eb + nbase) & 1ull) != 0 || (gpos + nbase >= ta.total_end);  // run ends a sequence
+    const u32 eb = ofs + (u32)ps;            // staged index of the run's first base
+    const u32 nbase = (u32)nn + K - 1;
+    const u64 gpos = sb + eb;
+    const bool at_first = bm_bit(bm, eb - wo) != 0;                                              // run starts a sequence
+    const bool at_last = bm_bit(bm, eb + nbase - wo) != 0 || (gpos + nbase >= ta.total_end);   // run ends a sequence
     u32 ln, rn;
     if (at_first) {  // KmerExtsIter: first k-mer takes the sequence-level left nibble (lib.rs:820-824)
         u32 sx = 0;
@@ -259,7 +305,7 @@ __device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs
         }
         ln = sx & 0xfu;
     } else {
-        ln = 1u << s32_base(s_s32, eb - 1);
+        ln = 1u << st_base(st, eb - 1);
     }
     if (at_last) {   // last k-mer takes the sequence-level right nibble (lib.rs:826-830)
         u32 sx = 0;
@@ -270,17 +316,21 @@ __device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs
         }
         rn = (sx >> 4) & 0xfu;
     } else {
-        rn = 1u << s32_base(s_s32, eb + nbase);
+        rn = 1u << st_base(st, eb + nbase);
     }
-    u64 hdr = ((u64)nn << 8) | (rn << 4) | ln;
+    const u64 hdr = ((u64)nn << 8) | (rn << 4) | ln;
     u64 r[RW];
+    {   // the record's 2 * RW + 1 staged words are loaded once each, then realigned in registers
+        const u32 j0 = eb >> 4, sh = 2 * (eb & 15);
+        u32 wv[2 * RW + 1];
 #pragma unroll
-    for (int t = 0; t < RW; t++) {
-        u32 bt = eb + 32 * t;
-        r[t] = (32u * t < nbase) ? (((u64)s32_bits(s_s32, bt) << 32) | s32_bits(s_s32, bt + 16)) : 0;
+        for (int t = 0; t < 2 * RW + 1; t++) wv[t] = st_word(st, j0 + t);
+#pragma unroll
+        for (int t = 0; t < RW; t++)
+            r[t] = ((u64)__funnelshift_l(wv[2 * t + 1], wv[2 * t], sh) << 32) | __funnelshift_l(wv[2 * t + 2], wv[2 * t + 1], sh);
     }
-    int lastw = (int)((nbase - 1) >> 5);
-    int used = (int)(nbase - 32 * lastw);
+    const int lastw = (int)((nbase - 1) >> 5);
+    const int used = (int)(nbase - 32 * lastw);
 #pragma unroll
     for (int t = 0; t < RW; t++) {
         if (t == lastw && used < 32) r[t] &= ~0ull << (64 - 2 * used);
@@ -288,7 +338,7 @@ __device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs
     }
     r[RW - 1] |= hdr;
     if (!ok) {
-        if (a.mode == 2) *a.overflow = 1;   // region (or the whole buffer) too small: record dropped, the host falls back to staging
+        *a.overflow = 1;   // region / staging buffer too small: record dropped, the host retries (staging) or falls back to staging (direct)
         return;
     }
     if constexpr (RW == 2) {
@@ -306,227 +356,300 @@ __device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs
 __device__ __forceinline__ u32 bkpad(u32 x) { return x + (x >> 4); }  // padded index: lane stride 17 words, conflict-free
 
 template <int W>
-__global__ void __launch_bounds__(T1_THREADS) msp_tile_kernel(KP kp, P1Args a, TileArgs ta) {
-    __shared__ __align__(16) u32 s_s32[T1_S32];
-    __shared__ __align__(16) u32 s_sc[T1_SC];
-    __shared__ u32 s_bk[TP + TP / 16 + 8];   // bucket of every k-mer start, padded (bkpad)
-    __shared__ u32 s_bm[T1_BM];   // bit b: a sequence starts at staged index b (or the data ends there)
-    __shared__ u32 s_vm[T1_BM];   // bit b: a valid k-mer starts at staged index b
-    u32* const s_queue = s_sc;    // closed runs of this tile (start | n << 16); reuses the score array after phase B
-    __shared__ u32 s_qn;
-    __shared__ u64 s_slot0, s_i0;
+__global__ void __launch_bounds__(WT_THREADS, WT_REG_CTAS) msp_tile_kernel(KP kp, P1Args a, TileArgs ta) {
+    __shared__ __align__(128) u32 s_stage[NST][SBW];
+    __shared__ __align__(16) u32 s_sc_all[WT_CW][WSC];
+    __shared__ u32 s_bk_all[WT_CW][WBK];
+    __shared__ u32 s_bm_all[WT_CW][WBM], s_vm_all[WT_CW][WBM];
+    __shared__ __align__(8) u64 s_full[NST];   // per ring slot: "the block's bytes have landed" (1 arrival + transaction bytes)
+    __shared__ __align__(8) u64 s_empty[NST];  // per ring slot: "all 8 warp tiles of the block are finished" (8 arrivals)
+    __shared__ u32 s_ticket;                   // next warp tile of this CTA to be processed
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = kp.k, p = a.p, wlen = K - p + 1;
-
-    // the (at most T1_S32 / 2 = 134) packed words of a tile are one load per thread: the NEXT tile's word is fetched into
-    // a register while the current tile is processed, so no tile starts by waiting on HBM
-    constexpr u32 NWST = T1_S32 / 2;
-    static_assert(NWST <= T1_THREADS, "one staged word per thread");
-    auto tile_origin = [&](u64 tile) -> u64 {
-        const u64 g = ta.base0 + tile * (u64)TP;
-        return (g > ta.base0 ? g - 1 : g) & ~31ull;
-    };
-    const u64 tile_step = (u64)gridDim.x * ta.tstride;
-    u64 pre = 0;
-    {
-        const u64 tile_first = ta.tile0 + (u64)blockIdx.x * ta.tstride;
-        if (tile_first < ta.n_tiles && tid < (int)NWST) {
-            const u64 wi = (tile_origin(tile_first) >> 5) + tid;
-            pre = wi < a.n_words ? a.words[wi] : 0;
-        }
+    const u32 tpw = tile_owned(K, p);          // positions a warp tile owns
+    const u64 bp = (u64)WT_CW * tpw;           // positions per block
+    if (tid == 0) {
+        for (int s = 0; s < NST; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], WT_CW); }
+        s_ticket = 0;
+        mbar_fence_init();
     }
-    for (u64 tile = ta.tile0 + (u64)blockIdx.x * ta.tstride; tile < ta.n_tiles; tile += tile_step) {
-        const u64 g0 = ta.base0 + tile * (u64)TP;                 // global position of tile-relative x = 0
-        const u64 sb = (g0 > ta.base0 ? g0 - 1 : g0) & ~31ull;    // staged origin (32-base aligned), covers the left flank
-        const u32 ofs = (u32)(g0 - sb);                           // staged index of x = 0
-        const u32 nbits = ofs + TP + K + 2;                       // staged indices that may be touched
-        __syncthreads();
-        // ---- stage bases (u32, base order) and the sequence-boundary bitmap ----
-        if (tid < (int)NWST) {
-            s_s32[2 * tid] = (u32)(pre >> 32);
-            s_s32[2 * tid + 1] = (u32)pre;
-            const u64 nt = tile + tile_step;
-            if (nt < ta.n_tiles) {
-                const u64 wi = (tile_origin(nt) >> 5) + tid;
-                pre = wi < a.n_words ? a.words[wi] : 0;
+    __syncthreads();   // the only CTA-wide barrier: the mbarriers exist
+    const u64 blk_step = (u64)gridDim.x * ta.tstride;
+    const u64 blk_first = ta.tile0 + (u64)blockIdx.x * ta.tstride;
+    const bool tma_ok = (reinterpret_cast<unsigned long long>(a.words) & 15ull) == 0;
+
+    // Block i of this CTA -> ring slot i % NST by one bulk asynchronous copy (TMA) that completes on the slot's "full"
+    // mbarrier.  Called by a whole warp: warp 0 for the first NST blocks; afterwards the warp that finishes the LAST warp
+    // tile of block j waits for block j - 1 to be released (its "empty" mbarrier: normally long complete, every tile of
+    // block j - 1 was claimed before any tile of block j) and refills that slot with block j - 1 + NST.  There is no
+    // producer warp and nobody polls: a dedicated producer spinning on try_wait cost 12-16% of the executed instructions
+    // (neither __nanosleep nor the suspend-time hint parked it for longer than ~20 ns).
+    auto issue_load = [&](u32 i) {
+        const u64 blk = blk_first + (u64)i * blk_step;
+        if (blk >= ta.n_tiles) return;
+        const u32 s = i % NST;
+        const u64 g0B = ta.base0 + blk * bp;
+        const u64 sbB = (g0B > ta.base0 ? g0B - 1 : g0B) & ~63ull;   // 64 bases = 16 bytes: bulk-copy alignment
+        const u64 ow = sbB >> 5;                                      // first packed word of the block
+        const u64 avail = ow < a.n_words ? (a.n_words - ow) * 8 : 0;
+        const u32 copy = tma_ok ? (u32)min((u64)SB_BYTES, avail & ~15ull) : 0u;
+        // whatever the bulk copy cannot take (end of the buffer, unaligned caller memory) goes through registers
+        u64* dst = reinterpret_cast<u64*>(s_stage[s]);
+        for (u32 j = copy / 8 + lane; j < (u32)SB_BYTES / 8; j += 32) dst[j] = (ow + j) < a.n_words ? a.words[ow + j] : 0ull;
+        __syncwarp();
+        if (lane == 0) {
+            if (copy) {
+                mbar_arrive_expect_tx(&s_full[s], copy);
+                bulk_g2s(dst, a.words + ow, copy, &s_full[s]);
+            } else {
+                mbar_arrive(&s_full[s]);
             }
         }
-        for (u32 t = tid; t < (u32)T1_BM; t += T1_THREADS) s_bm[t] = 0;
-        if (tid == 0) {
-            s_qn = 0;
-            if (a.uniform_len) s_i0 = (sb - ta.base0 + a.uniform_len - 1) / a.uniform_len;  // one 64-bit division per tile
-        }
-        __syncthreads();
-        if (a.uniform_len) {
-            const u32 L = a.uniform_len;
-            u64 i0 = s_i0;
-            for (u64 i = i0 + tid; i <= a.n_seqs; i += T1_THREADS) {
-                u64 g = ta.base0 + i * L;
-                if (g >= sb + nbits) break;
-                atomicOr(&s_bm[(g - sb) >> 5], 1u << ((g - sb) & 31));
-            }
-        } else {
-            u64 i0 = seq_lower_bound(a.start, a.n_seqs, sb);
-            for (u64 i = i0 + tid; i < a.n_seqs; i += T1_THREADS) {
-                u64 g = a.start[i];
-                if (g >= sb + nbits) break;
-                atomicOr(&s_bm[(g - sb) >> 5], 1u << ((g - sb) & 31));
-            }
-            if (tid == 0 && ta.total_end >= sb && ta.total_end < sb + nbits)
-                atomicOr(&s_bm[(ta.total_end - sb) >> 5], 1u << ((ta.total_end - sb) & 31));
-        }
-        // ---- phase A: p-mer scores, 4 consecutive positions per thread ----
-        for (u32 q0 = 4 * tid; q0 < (u32)(TP + K - p + 1); q0 += 4 * T1_THREADS) {
-            u32 b = ofs + q0, i = b >> 4, sh = 2 * (b & 15);
-            u32 w0 = s_s32[i], w1 = s_s32[i + 1], w2 = s_s32[i + 2];
-            u32 hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
-            uint4 sc;
-            sc.x = pmer_score(hi >> (32 - 2 * p), p, a.stranded != 0);
-            sc.y = pmer_score(__funnelshift_l(lo, hi, 2) >> (32 - 2 * p), p, a.stranded != 0);
-            sc.z = pmer_score(__funnelshift_l(lo, hi, 4) >> (32 - 2 * p), p, a.stranded != 0);
-            sc.w = pmer_score(__funnelshift_l(lo, hi, 6) >> (32 - 2 * p), p, a.stranded != 0);
-            *reinterpret_cast<uint4*>(&s_sc[q0]) = sc;
-        }
-        __syncthreads();
-        // ---- validity bitmap: a k-mer at b is valid iff no boundary in (b, b+K) and b lies before the end of data.
-        // OR over the K-1 following boundary bits by doubling on a 96-bit register window. ----
-        for (u32 j = tid; j < (u32)T1_BM - 3; j += T1_THREADS) {
-            u32 w0 = s_bm[j], w1 = s_bm[j + 1], w2 = s_bm[j + 2];
-            // y = boundary bits shifted down by 1 (bit b of y = boundary at b+1)
-            u32 y0 = __funnelshift_r(w0, w1, 1), y1 = __funnelshift_r(w1, w2, 1), y2 = w2 >> 1;
-            int have = 1;            // y covers offsets 1 .. have
-            const int need = K - 1;  // offsets 1 .. K-1
-            while (have * 2 <= need) {
-                int sft = have;      // < 32
-                u32 z0 = __funnelshift_r(y0, y1, sft), z1 = __funnelshift_r(y1, y2, sft), z2 = y2 >> sft;
-                y0 |= z0; y1 |= z1; y2 |= z2;
-                have *= 2;
-            }
-            if (have < need) {
-                int sft = need - have;  // < have <= 32
-                u32 z0 = __funnelshift_r(y0, y1, sft), z1 = __funnelshift_r(y1, y2, sft);
-                y0 |= z0; y1 |= z1;
-            }
-            u32 inv = need > 0 ? y0 : 0;
-            u64 endi = ta.total_end - sb;  // staged index of the end of data
-            u32 in_range = (u64)32 * j + 32 <= endi ? 0xffffffffu : ((u64)32 * j >= endi ? 0u : ((1u << (endi - 32 * j)) - 1));
-            s_vm[j] = ~inv & in_range;
-        }
-        // ---- phase B: window minimum (w >= 4) for 4 consecutive k-mers per thread ----
-        for (u32 x0 = 4 * tid; x0 < (u32)TP; x0 += 4 * T1_THREADS) {
-            uint4 f = *reinterpret_cast<const uint4*>(&s_sc[x0]);
-            u32 c = f.w;  // running min over indices 3 .. wlen-1
-            int e = 4;
-            for (; e + 3 < wlen; e += 4) {
-                uint4 v = *reinterpret_cast<const uint4*>(&s_sc[x0 + e]);
-                c = min(min(c, v.x), min(v.y, min(v.z, v.w)));
-            }
-            for (; e < wlen; e++) c = min(c, s_sc[x0 + e]);
-            u32 t0 = s_sc[x0 + wlen], t1 = s_sc[x0 + wlen + 1], t2 = s_sc[x0 + wlen + 2];
-            u32 pb = bkpad(x0);  // x0 % 4 == 0: the four padded indices are consecutive
-            s_bk[pb] = min(min(f.x, f.y), min(f.z, c)) & a.bucket_mask;
-            s_bk[pb + 1] = min(min(f.y, f.z), min(c, t0)) & a.bucket_mask;
-            s_bk[pb + 2] = min(min(f.z, c), min(t0, t1)) & a.bucket_mask;
-            s_bk[pb + 3] = min(min(c, t0), min(t1, t2)) & a.bucket_mask;
-        }
-        __syncthreads();
-        // ---- phase C: runs.  Warp `warp` owns tile positions [seg0, seg0 + 512); lane owns 16 consecutive
-        // positions and works on 16/17-bit masks: valid, first-of-sequence, bucket-differs.  A set bit in
-        // `smask` starts a run or (first invalid position after a run) closes one; bit 16 of the last lane is
-        // the virtual closer at the segment end.  Closed runs go to the CTA queue. ----
-        {
-            const u32 seg0 = warp * T1_SEG;
-            const u32 x0 = seg0 + 16 * lane;
-            const u32 b0 = ofs + x0;
-            u32 vm = bm_bits32(s_vm, b0) & 0xffffu;
-            u32 fm = bm_bits32(s_bm, b0) & 0xffffu;
-            u32 dm = 0;
-            {
-                u32 prevb = s_bk[bkpad(x0 ? x0 - 1 : 0)];
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    u32 cur = s_bk[bkpad(x0 + i)];
-                    dm |= (cur != prevb ? 1u : 0u) << i;
-                    prevb = cur;
+    };
+    if (warp == 0)
+        for (u32 i = 0; i < (u32)NST; i++) issue_load(i);
+
+    // ---- consumer warps ----
+    u32* const sc = s_sc_all[warp];
+    u32* const bk = s_bk_all[warp];
+    u32* const bm = s_bm_all[warp];   // bit b: a sequence starts at staged index wo + b (or the data ends there)
+    u32* const vm = s_vm_all[warp];   // bit b: a valid k-mer starts at staged index wo + b
+    u32* const queue = sc;            // closed runs (start | n << 16); reuses the score array after phase B
+    const bool part = a.bk_span <= a.bucket_mask || a.maxk < 17;   // multi-pass planner: only some buckets belong to this pass
+    u64 chunk_base = 0;               // staging mode: the warp's current chunk of record slots
+    u32 chunk_used = 0, chunk_cap = 0;
+    // Warp tiles are CLAIMED, not assigned: one ticket counter per CTA, ticket = 8 * (block of this CTA) + (warp tile of
+    // that block), handed out in order.  A warp that is ahead simply takes more tiles and nobody waits for the slowest
+    // warp of the CTA (with a fixed warp -> tile map the fast warps spun on the ring: 19% of the executed instructions).
+    // A warp holding a ticket of block i keeps that block's ring slot from being released, so the slot's "full" barrier
+    // can be at most one phase ahead of what the warp waits for.
+    for (;;) {
+        u32 ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&s_ticket, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        const u32 i = ticket >> 3, wt = ticket & 7u;                   // block of this CTA, warp tile of the block
+        const u64 blk = blk_first + (u64)i * blk_step;
+        if (blk >= ta.n_tiles) break;
+        const u32 s = i % NST, use = i / NST;
+        const u64 g0B = ta.base0 + blk * bp;
+        const u64 sbB = (g0B > ta.base0 ? g0B - 1 : g0B) & ~63ull;    // global position of staged index 0
+        const u64 g0 = g0B + (u64)wt * tpw;                            // global position of this warp tile's x = 0
+        mbar_wait(&s_full[s], use & 1);
+        if (g0 < ta.total_end) {
+            const u32* st = s_stage[s];
+            const u32 ofs = (u32)(g0 - sbB);                           // staged index of x = 0
+            const u32 wo = (g0 > ta.base0 ? ofs - 1 : ofs) & ~31u;     // staged index of bitmap bit 0 (covers the left flank)
+            const u32 nbits = (ofs - wo) + WP + K + 2;                 // bitmap bits that may be touched
+            const u64 gw = sbB + wo;                                   // global position of bitmap bit 0
+            // ---- sequence-boundary bitmap ----
+            if (lane < WBM) bm[lane] = 0;
+            __syncwarp();
+            if (a.uniform_len) {
+                const u32 L = a.uniform_len;
+                const u64 i0 = gw <= ta.base0 ? 0 : (gw - ta.base0 + L - 1) / L;
+                for (u64 q = i0 + lane; q <= a.n_seqs; q += 32) {
+                    const u64 g = ta.base0 + q * L;
+                    if (g >= gw + nbits) break;
+                    atomicOr(&bm[(g - gw) >> 5], 1u << ((g - gw) & 31));
                 }
-            }
-            u32 up = __shfl_up_sync(0xffffffffu, vm, 1);
-            u32 pv = (vm << 1) | (lane ? (up >> 15) & 1u : 0u);           // bits 0..16: valid(x-1)
-            u32 start = vm & (fm | ~pv | dm | (lane == 0 ? 1u : 0u));
-            u32 closer = ~vm & pv & (lane == 31 ? 0x1ffffu : 0xffffu);    // bit 16 (x = seg end) only for the last lane
-            u32 smask = start | closer;
-            u32 cmask = smask & pv;
-            // carry: position of the last set bit of smask in any lower lane
-            int mylast = smask ? (int)x0 + 31 - __clz(smask) : -1;
-            int carry = mylast;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, carry, o); if (lane >= o) carry = max(carry, t); }
-            carry = __shfl_up_sync(0xffffffffu, carry, 1);
-            if (lane == 0) carry = (int)seg0;
-            // records this lane will push (runs longer than maxk are cut)
-            u32 nrec = 0;
-            {
-                u32 m = cmask;
-                int pr = carry;
-                u32 sm = smask;
-                while (m) {
-                    int bit = __ffs(m) - 1;
-                    m &= m - 1;
-                    u32 lower = sm & ((1u << bit) - 1);
-                    int prev = lower ? (int)x0 + 31 - __clz(lower) : pr;
-                    int n = (int)x0 + bit - prev;
-                    if (s_bk[bkpad((u32)prev)] - a.bk_lo < a.bk_span)   // runs of other buckets belong to another pass
-                        nrec += n <= a.maxk ? 1u : (u32)((n + a.maxk - 1) / a.maxk);
+            } else {
+                const u64 i0 = seq_lower_bound(a.start, a.n_seqs, gw);
+                for (u64 q = i0 + lane; q < a.n_seqs; q += 32) {
+                    const u64 g = a.start[q];
+                    if (g >= gw + nbits) break;
+                    atomicOr(&bm[(g - gw) >> 5], 1u << ((g - gw) & 31));
                 }
+                if (lane == 0 && ta.total_end >= gw && ta.total_end < gw + nbits)
+                    atomicOr(&bm[(ta.total_end - gw) >> 5], 1u << ((ta.total_end - gw) & 31));
             }
-            u32 inc = nrec;
+            // ---- phase A: p-mer scores of the 512 examined positions, 4 consecutive positions per lane and round ----
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            u32 wtotal = __shfl_sync(0xffffffffu, inc, 31);
-            u32 wbase = 0;
-            if (lane == 0 && wtotal) wbase = atomicAdd(&s_qn, wtotal);
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            u32 qpos = wbase + inc - nrec;
+            for (int it = 0; it < WP / 128; it++) {
+                const u32 q0 = 128 * it + 4 * lane;
+                const u32 b = ofs + q0, j = b >> 4, sh = 2 * (b & 15);
+                const u32 w0 = st_word(st, j), w1 = st_word(st, j + 1), w2 = st_word(st, j + 2);
+                const u32 hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+                uint4 v;
+                v.x = pmer_score(hi >> (32 - 2 * p), p, a.stranded != 0);
+                v.y = pmer_score(__funnelshift_l(lo, hi, 2) >> (32 - 2 * p), p, a.stranded != 0);
+                v.z = pmer_score(__funnelshift_l(lo, hi, 4) >> (32 - 2 * p), p, a.stranded != 0);
+                v.w = pmer_score(__funnelshift_l(lo, hi, 6) >> (32 - 2 * p), p, a.stranded != 0);
+                *reinterpret_cast<uint4*>(&sc[q0]) = v;
+            }
+            __syncwarp();
+            // ---- validity bitmap: a k-mer at b is valid iff no boundary in (b, b+K) and b lies before the end of data.
+            // OR over the K-1 following boundary bits by doubling on a 96-bit register window. ----
+            if (lane < WBM - 3) {
+                const u32 j = lane;
+                const u32 w0 = bm[j], w1 = bm[j + 1], w2 = bm[j + 2];
+                u32 y0 = __funnelshift_r(w0, w1, 1), y1 = __funnelshift_r(w1, w2, 1), y2 = w2 >> 1;
+                int have = 1;            // y covers offsets 1 .. have
+                const int need = K - 1;  // offsets 1 .. K-1
+                while (have * 2 <= need) {
+                    const int sft = have;      // < 32
+                    const u32 z0 = __funnelshift_r(y0, y1, sft), z1 = __funnelshift_r(y1, y2, sft), z2 = y2 >> sft;
+                    y0 |= z0; y1 |= z1; y2 |= z2;
+                    have *= 2;
+                }
+                if (have < need) {
+                    const int sft = need - have;  // < have <= 32
+                    const u32 z0 = __funnelshift_r(y0, y1, sft), z1 = __funnelshift_r(y1, y2, sft);
+                    y0 |= z0; y1 |= z1;
+                }
+                const u32 inv = need > 0 ? y0 : 0;
+                const u64 endi = ta.total_end - gw;  // bitmap index of the end of data
+                const u32 in_range = (u64)32 * j + 32 <= endi ? 0xffffffffu : ((u64)32 * j >= endi ? 0u : ((1u << (endi - 32 * j)) - 1));
+                vm[j] = ~inv & in_range;
+            }
+            // ---- phase B: window minimum (w >= 4) for 4 consecutive k-mers per lane and round ----
+#pragma unroll 1
+            for (int it = 0; it < WP / 128; it++) {
+                const u32 x0 = 128 * it + 4 * lane;
+                const uint4 f = *reinterpret_cast<const uint4*>(&sc[x0]);
+                u32 c = f.w;  // running min over indices 3 .. wlen-1
+                int e = 4;
+                for (; e + 3 < wlen; e += 4) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(&sc[x0 + e]);
+                    c = min(min(c, v.x), min(v.y, min(v.z, v.w)));
+                }
+                for (; e < wlen; e++) c = min(c, sc[x0 + e]);
+                const u32 t0 = sc[x0 + wlen], t1 = sc[x0 + wlen + 1], t2 = sc[x0 + wlen + 2];
+                const u32 pb = bkpad(x0);  // x0 % 4 == 0: the four padded indices are consecutive
+                bk[pb] = min(min(f.x, f.y), min(f.z, c)) & a.bucket_mask;
+                bk[pb + 1] = min(min(f.y, f.z), min(c, t0)) & a.bucket_mask;
+                bk[pb + 2] = min(min(f.z, c), min(t0, t1)) & a.bucket_mask;
+                bk[pb + 3] = min(min(c, t0), min(t1, t2)) & a.bucket_mask;
+            }
+            __syncwarp();
+            // ---- phase C: runs.  The lane owns 16 consecutive positions and works on 16/17-bit masks: valid,
+            // first-of-sequence, bucket-differs.  A set bit in `smask` starts a run or (first invalid position after a
+            // run) closes one.  Positions >= tpw belong to the next warp tile: invalid here, which closes the last run. ----
+            u32 wtotal, nrec, qbase;
+            u32 smask, cmask;
+            int carry;
+            const u32 x0 = 16 * lane;
             {
+                const u32 b0 = ofs + x0 - wo;
+                const u32 own = tpw > x0 ? (tpw - x0 >= 16 ? 0xffffu : (1u << (tpw - x0)) - 1) : 0u;
+                const u32 vmk = bm_bits32(vm, b0) & own;
+                const u32 fm = bm_bits32(bm, b0) & 0xffffu;
+                u32 dm = 0;
+                {
+                    u32 prevb = bk[bkpad(x0 ? x0 - 1 : 0)];
+#pragma unroll
+                    for (int t = 0; t < 16; t++) {
+                        const u32 cur = bk[bkpad(x0 + t)];
+                        dm |= (cur != prevb ? 1u : 0u) << t;
+                        prevb = cur;
+                    }
+                }
+                const u32 up = __shfl_up_sync(0xffffffffu, vmk, 1);
+                const u32 pv = (vmk << 1) | (lane ? (up >> 15) & 1u : 0u);           // bits 0..16: valid(x-1)
+                const u32 start = vmk & (fm | ~pv | dm | (lane == 0 ? 1u : 0u));
+                const u32 closer = ~vmk & pv & (lane == 31 ? 0x1ffffu : 0xffffu);    // bit 16 (x = 512) only for the last lane
+                smask = start | closer;
+                cmask = smask & pv;
+                // carry: position of the last set bit of smask in any lower lane (only read when a run is open there)
+                const int mylast = smask ? (int)x0 + 31 - __clz(smask) : -1;
+                const u32 below = __ballot_sync(0xffffffffu, smask != 0) & ((1u << lane) - 1);
+                carry = __shfl_sync(0xffffffffu, mylast, below ? 31 - __clz(below) : 0);
+                if (!below) carry = 0;
+                // records this lane will push (runs longer than maxk are cut)
+                if (!part) {
+                    // one pass over all buckets.  maxk >= 26 > 16 positions per lane: only a run that began in a lower lane
+                    // can be longer than maxk, and only the lane's first set bit can close it
+                    nrec = (u32)__popc(cmask);
+                    if (cmask & (smask & (0u - smask))) {
+                        const int n = (int)x0 + __ffs(smask) - 1 - carry;
+                        if (n > a.maxk) nrec += (u32)((n - 1) / a.maxk);
+                    }
+                } else {
+                    nrec = 0;
+                    u32 m = cmask;
+                    while (m) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        const u32 lower = smask & ((1u << bit) - 1);
+                        const int prev = lower ? (int)x0 + 31 - __clz(lower) : carry;
+                        const int n = (int)x0 + bit - prev;
+                        if (bk[bkpad((u32)prev)] - a.bk_lo < a.bk_span)   // runs of other buckets belong to another pass
+                            nrec += n <= a.maxk ? 1u : (u32)((n + a.maxk - 1) / a.maxk);
+                    }
+                }
+                u32 inc = nrec;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                wtotal = __shfl_sync(0xffffffffu, inc, 31);
+                qbase = inc - nrec;
+            }
+            __syncwarp();   // every lane is done with the scores' last readers (phase B) before the queue overwrites them
+            {
+                u32 qpos = qbase;
                 u32 m = cmask;
                 while (m) {
-                    int bit = __ffs(m) - 1;
+                    const int bit = __ffs(m) - 1;
                     m &= m - 1;
-                    u32 lower = smask & ((1u << bit) - 1);
-                    int prev = lower ? (int)x0 + 31 - __clz(lower) : carry;
-                    int xe = (int)x0 + bit;
-                    if (s_bk[bkpad((u32)prev)] - a.bk_lo >= a.bk_span) continue;
+                    const u32 lower = smask & ((1u << bit) - 1);
+                    const int prev = lower ? (int)x0 + 31 - __clz(lower) : carry;
+                    const int xe = (int)x0 + bit;
+                    if (part && bk[bkpad((u32)prev)] - a.bk_lo >= a.bk_span) continue;
                     for (int ps = prev; ps < xe; ps += a.maxk) {
-                        if (qpos < (u32)T1_QCAP) s_queue[qpos] = (u32)ps | ((u32)min(a.maxk, xe - ps) << 16);
+                        queue[qpos] = (u32)ps | ((u32)min(a.maxk, xe - ps) << 16);   // qpos < wtotal <= WP: one run per position at most
                         qpos++;
                     }
                 }
             }
-        }
-        __syncthreads();
-        // ---- phase D: one thread per record.  mode 0: one exact staging reservation per tile; mode 2: the record's slot
-        // comes from its bucket's own cursor (no staging, no scatter pass); mode 1: histogram only ----
-        const u32 nq = s_qn;
-        if (tid == 0) {
-            u64 s0 = (nq && a.mode == 0) ? atomicAdd(a.cursor, (u64)nq) : 0;
-            s_slot0 = s0;
-            if ((a.mode == 0 && s0 + nq > a.capacity) || nq > (u32)T1_QCAP) *a.overflow = 1;
-        }
-        __syncthreads();
-        const u64 slot0 = s_slot0;
-        for (u32 q = tid; q < nq && q < (u32)T1_QCAP; q += T1_THREADS) {
-            const u32 ent = s_queue[q];
-            const int ps = (int)(ent & 0xffffu), nn = (int)(ent >> 16);
-            const u32 bkt = s_bk[bkpad((u32)ps)];
-            if (a.mode == 1) { atomicAdd(&a.bucket_count[bkt], 1u); continue; }
-            u64 slot = slot0 + q;
-            bool ok = slot < a.capacity;
-            if (a.mode == 2) {
-                const u32 r = atomicAdd(&a.bucket_fill[bkt], 1u);   // no branch on r here: see tile_emit_record
-                slot = a.bucket_start[bkt] + r;
-                ok = r < a.bucket_cap[bkt] && slot < a.capacity;
+            __syncwarp();
+            // ---- phase D: one lane per record.  mode 0: slots from the warp's staging chunk (a new chunk is reserved from
+            // the global cursor when the current one cannot take this tile's records; unused slots stay INVALID and are
+            // skipped by the scatter pass); mode 2: the record's slot comes from its bucket's own cursor (no staging, no
+            // scatter pass); mode 1: histogram only ----
+            u64 slot0 = 0;
+            bool chunk_ok = true;
+            if (a.mode == 0 && wtotal) {
+                if (chunk_used + wtotal > chunk_cap) {
+                    chunk_cap = max((u32)WCHUNK, wtotal);
+                    u64 cb = 0;
+                    if (lane == 0) cb = atomicAdd(a.cursor, (u64)chunk_cap);
+                    chunk_base = __shfl_sync(0xffffffffu, cb, 0);
+                    chunk_used = 0;
+                }
+                slot0 = chunk_base + chunk_used;
+                chunk_used += wtotal;
+                chunk_ok = chunk_base + chunk_cap <= a.capacity;
             }
-            tile_emit_record<W>(a, ta, K, s_s32, s_bm, bkt, sb, ofs, ps, nn, slot, ok);
+            // two records per lane and round: both bucket-cursor atomics are in flight before either record is assembled
+            for (u32 q = lane; q < wtotal; q += 64) {
+                const u32 q1 = q + 32;
+                const bool has1 = q1 < wtotal;
+                const u32 ent0 = queue[q], ent1 = has1 ? queue[q1] : 0u;
+                const int ps0 = (int)(ent0 & 0xffffu), nn0 = (int)(ent0 >> 16);
+                const int ps1 = (int)(ent1 & 0xffffu), nn1 = (int)(ent1 >> 16);
+                const u32 bkt0 = bk[bkpad((u32)ps0)], bkt1 = bk[bkpad((u32)ps1)];
+                if (a.mode == 1) {
+                    atomicAdd(&a.bucket_count[bkt0], 1u);
+                    if (has1) atomicAdd(&a.bucket_count[bkt1], 1u);
+                    continue;
+                }
+                u64 slotA = slot0 + q, slotB = slot0 + q1;
+                bool okA = chunk_ok, okB = chunk_ok;
+                if (a.mode == 2) {
+                    const u32 r0 = atomicAdd(&a.bucket_fill[bkt0], 1u);   // no branch on r0 / r1 here: see tile_emit_record
+                    const u32 r1 = has1 ? atomicAdd(&a.bucket_fill[bkt1], 1u) : 0u;
+                    slotA = a.bucket_start[bkt0] + r0;
+                    okA = r0 < a.bucket_cap[bkt0] && slotA < a.capacity;
+                    slotB = a.bucket_start[bkt1] + r1;
+                    okB = r1 < a.bucket_cap[bkt1] && slotB < a.capacity;
+                }
+                tile_emit_record<W>(a, ta, K, st, bm, wo, bkt0, sbB, ofs, ps0, nn0, slotA, okA);
+                if (has1) tile_emit_record<W>(a, ta, K, st, bm, wo, bkt1, sbB, ofs, ps1, nn1, slotB, okB);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);   // this warp tile no longer reads ring slot s
+        if (wt == (u32)WT_CW - 1 && i >= 1) {      // last tile of block i: refill the slot of block i - 1
+            mbar_wait(&s_empty[(i - 1) % NST], ((i - 1) / NST) & 1);
+            issue_load(i - 1 + NST);
         }
     }
 }
@@ -1333,12 +1456,13 @@ static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, 
     TRY(ctr.alloc(c, 8));
     TileArgs ta;
     ta.base0 = s->base0; ta.total_end = s->total_end; ta.tile0 = 0; ta.tstride = 1;
-    ta.n_tiles = use_tiles ? (s->total_end - s->base0 + TP - 1) / TP : 0;
+    const u64 bp = (u64)WT_CW * tile_owned(k, p);   // positions per block of the tile kernel
+    ta.n_tiles = use_tiles ? (s->total_end - s->base0 + bp - 1) / bp : 0;
     SeqSet* sm = const_cast<SeqSet*>(s);
     if (!use_tiles) TRY(seqset_ready(c, sm));
-    u32 grid1 = use_tiles ? (u32)std::min<u64>(ta.n_tiles, (u64)c->sm_count * 6)
+    u32 grid1 = use_tiles ? (u32)std::min<u64>(ta.n_tiles, (u64)c->sm_count * WT_CTAS)
                           : (u32)std::min<u64>((n_items + P1_WARPS - 1) / P1_WARPS, (u64)c->sm_count * 6);
-    u64 n_warps = (u64)grid1 * P1_WARPS;
+    u64 n_warps = (u64)grid1 * (use_tiles ? WT_CW : P1_WARPS);
     // records expected in this pass: ~1/10 of its k-mer occurrences; N/4 leaves room, the retry below covers the rest
     u64 capacity = (u64)((double)N * bk_span / NB) / 4 + n_warps * WCHUNK + 1024;
     DBuf<u64> stage_rec;
@@ -1366,20 +1490,21 @@ static int partition_stage(Ctx* c, int k, const SeqSet* s, int stranded, u64 N, 
             for (int ci = 0; ci < np; ci++) {
                 CU(c, cudaStreamWaitEvent(st, sm->pend_ev[ci], 0));
                 u64 bases_ok = sm->pend_words_end[ci] * 32;
-                u64 upto = ci == np - 1 ? ta.n_tiles : (bases_ok > (u64)(TP + 192) ? (bases_ok - 192 - s->base0) / TP : 0);
+                // a block touches bases up to its end + K + 2 (flank); 192 covers that for every K <= 64
+                u64 upto = ci == np - 1 ? ta.n_tiles : (bases_ok > s->base0 + bp + 192 ? (bases_ok - 192 - s->base0) / bp : 0);
                 if (upto > ta.n_tiles) upto = ta.n_tiles;
                 if (upto > done) {
                     TileArgs tc = ta;
                     tc.tile0 = done; tc.n_tiles = upto;
-                    u32 g = (u32)std::min<u64>(upto - done, (u64)c->sm_count * 6);
-                    msp_tile_kernel<W><<<g, T1_THREADS, 0, st>>>(kp, a, tc);
+                    u32 g = (u32)std::min<u64>(upto - done, (u64)c->sm_count * WT_CTAS);
+                    msp_tile_kernel<W><<<g, WT_THREADS, 0, st>>>(kp, a, tc);
                     TRY(check_launch(c, "msp_partition"));
                     done = upto;
                 }
             }
             sm->n_pending = 0;
         } else {
-            if (use_tiles) msp_tile_kernel<W><<<grid1, T1_THREADS, 0, st>>>(kp, a, ta);
+            if (use_tiles) msp_tile_kernel<W><<<grid1, WT_THREADS, 0, st>>>(kp, a, ta);
             else msp_partition_kernel<W><<<grid1, P1_THREADS, 0, st>>>(kp, a);
             TRY(check_launch(c, "msp_partition"));
         }
@@ -1422,7 +1547,8 @@ static int partition_direct(Ctx* c, int k, const SeqSet* s, int stranded, u64 N,
     SeqSet* sm = const_cast<SeqSet*>(s);
     TileArgs ta;
     ta.base0 = s->base0; ta.total_end = s->total_end; ta.tile0 = 0; ta.tstride = 1;
-    ta.n_tiles = (s->total_end - s->base0 + TP - 1) / TP;
+    const u64 bp = (u64)WT_CW * tile_owned(k, p);   // positions per block of the tile kernel
+    ta.n_tiles = (s->total_end - s->base0 + bp - 1) / bp;
     // expected records: one per (K-p+2)/2 k-mers (window of K-p+1 p-mers); 3.5x covers read ends, length caps and the
     // regions' slack — a larger need raises the overflow flag and the caller falls back to staging
     d.rec_bound = (u64)(3.5 * 2.0 * (double)N / (double)(k - p + 2)) + (u64)NB * 64 + 4096;
@@ -1443,7 +1569,7 @@ static int partition_direct(Ctx* c, int k, const SeqSet* s, int stranded, u64 N,
     auto tiles_upto = [&](int ci) -> u64 {
         if (ci == np - 1) return ta.n_tiles;
         u64 bases_ok = sm->pend_words_end[ci] * 32;
-        u64 upto = bases_ok > (u64)(TP + 192) ? (bases_ok - 192 - s->base0) / TP : 0;
+        u64 upto = bases_ok > s->base0 + bp + 192 ? (bases_ok - 192 - s->base0) / bp : 0;
         return std::min<u64>(upto, ta.n_tiles);
     };
     u64 t_s = ta.n_tiles;
@@ -1458,7 +1584,7 @@ static int partition_direct(Ctx* c, int k, const SeqSet* s, int stranded, u64 N,
         TileArgs tc = ta;
         tc.n_tiles = t_s; tc.tstride = stride;
         a.mode = 1;
-        msp_tile_kernel<W><<<(u32)std::min<u64>(std::max<u64>(n_sampled, 1), (u64)c->sm_count * 6), T1_THREADS, 0, st>>>(kp, a, tc);
+        msp_tile_kernel<W><<<(u32)std::min<u64>(std::max<u64>(n_sampled, 1), (u64)c->sm_count * WT_CTAS), WT_THREADS, 0, st>>>(kp, a, tc);
         TRY(check_launch(c, "msp_partition_sample"));
     }
     bucket_caps_kernel<<<grid_for(NB, 256), 256, 0, st>>>(d.cnt.p, NB, scale, d.cap.p);
@@ -1477,14 +1603,14 @@ static int partition_direct(Ctx* c, int k, const SeqSet* s, int stranded, u64 N,
             if (upto > done) {
                 TileArgs tc = ta;
                 tc.tile0 = done; tc.n_tiles = upto;
-                msp_tile_kernel<W><<<(u32)std::min<u64>(upto - done, (u64)c->sm_count * 6), T1_THREADS, 0, st>>>(kp, a, tc);
+                msp_tile_kernel<W><<<(u32)std::min<u64>(upto - done, (u64)c->sm_count * WT_CTAS), WT_THREADS, 0, st>>>(kp, a, tc);
                 TRY(check_launch(c, "msp_partition"));
                 done = upto;
             }
         }
         sm->n_pending = 0;
     } else {
-        msp_tile_kernel<W><<<(u32)std::min<u64>(ta.n_tiles, (u64)c->sm_count * 6), T1_THREADS, 0, st>>>(kp, a, ta);
+        msp_tile_kernel<W><<<(u32)std::min<u64>(ta.n_tiles, (u64)c->sm_count * WT_CTAS), WT_THREADS, 0, st>>>(kp, a, ta);
         TRY(check_launch(c, "msp_partition"));
     }
     CU(c, cudaEventRecord(c->ev[9], st));
