@@ -36,15 +36,6 @@ static const int SW_N = 24;          // staged 2-bit words per item: (CHUNK + 64
 static const int WCHUNK = 256;       // record slots a warp reserves per global atomic
 static const u32 INVALID_BUCKET = 0xffffffffu;
 
-__device__ __forceinline__ u32 pmer_score(u32 x, int p, bool stranded) {
-    if (!stranded) {
-        u32 r = (~rev2_32(x)) >> (32 - 2 * p);
-        x = x < r ? x : r;  // canonical p-mer (score = min(perm[p], perm[rc p]), msp.rs:305-311, perm bijective)
-    }
-    x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA6Bu; x ^= x >> 13;
-    return x;
-}
-
 struct P1Args {
     const u64* words; u64 n_words;
     const u64* start; const u32* length; const u8* seq_exts;
@@ -188,14 +179,15 @@ __global__ void __launch_bounds__(P1_THREADS) msp_partition_kernel(KP kp, P1Args
 // P1 fast path: partition of CONTIGUOUSLY packed sequences (PackedDnaStringSet::add layout:
 // start[i+1] = start[i] + length[i]; uniform-length reads are the arithmetic special case).
 //
-// Round-2 form: no CTA-wide barrier in the steady state.  BLOCKS of packed words (8 warp tiles, ~1 KB)
-// stream from HBM into a 4-deep shared-memory ring by bulk asynchronous copies (cp.async.bulk = TMA,
-// completion on the slot's "full" mbarrier).  The 8 warps of a CTA CLAIM warp tiles from a ticket
-// counter and process each on their own, synchronising with __syncwarp only; a finished tile arrives on
-// the slot's "empty" mbarrier, and the warp that finishes a block's last tile refills the slot the
-// previous block has left (no producer warp, nobody polls).  Warps of a CTA drift a few blocks apart,
+// Round-2 form: no CTA-wide barrier in the steady state.  A CTA is 8 consumer warps + 1 producer warp.
+// The producer streams BLOCKS of packed words (8 warp tiles, ~1 KB) from HBM into a 4-deep
+// shared-memory ring with bulk asynchronous copies (cp.async.bulk = TMA, completion on the slot's
+// "full" mbarrier) and waits on the slot's "empty" mbarrier in between.  The consumer warps CLAIM warp
+// tiles from a ticket counter and process each on their own, synchronising with __syncwarp only; a
+// finished tile arrives on the slot's "empty" mbarrier.  Warps of a CTA drift up to 3 blocks apart,
 // warps of different CTAs are independent: the phases below (which used to be separated by
-// __syncthreads and left half the issue slots idle) overlap freely across the 40 resident warps of an SM.
+// __syncthreads and left half the issue slots idle) overlap freely across the 40 resident consumer
+// warps of an SM.
 //
 // A warp tile EXAMINES 512 consecutive k-mer start positions (16 per lane) and OWNS the first
 // tpw = 512 - (w - 1) of them (w = K - p + 1 p-mers per window): the 512 p-mer scores it computes are
@@ -208,9 +200,8 @@ __global__ void __launch_bounds__(P1_THREADS) msp_partition_kernel(KP kp, P1Args
 //                 staging chunk, 16/32-byte record assembled from the staged bases, one vector store
 // ------------------------------------------------------------------------------------------------
 static const int WT_CW = 8;                          // consumer warps per CTA
-static const int WT_THREADS = WT_CW * 32;
+static const int WT_THREADS = (WT_CW + 1) * 32;      // + 1 producer warp
 static const int WT_CTAS = 5;                        // resident CTAs per SM (42.6 KB static shared memory each)
-static const int WT_REG_CTAS = 6;                    // register budget of __launch_bounds__: 40 registers (the 48-register build ran 5% slower)
 static const int WP = 512;                           // positions a warp tile examines
 static const int WSC = WP + 64 + 8;                  // p-mer scores per warp tile (+ what the un-owned windows may touch)
 static const int WBK = WP + WP / 16 + 8;             // bucket of every examined position, padded (bkpad)
@@ -252,6 +243,15 @@ __device__ __forceinline__ bool mbar_try_wait(u32 addr, u32 parity) {
 __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
     const u32 addr = smem_u32(bar);
     while (!mbar_try_wait(addr, parity)) __nanosleep(64);
+}
+// producer side: the wait for a free slot lasts a whole block; the suspend-time hint lets the hardware park the warp
+__device__ __forceinline__ void mbar_wait_suspended(u64* bar, u32 parity) {
+    const u32 addr = smem_u32(bar);
+    u32 ok = 0;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+    } while (!ok);
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -356,7 +356,7 @@ __device__ __forceinline__ void tile_emit_record(const P1Args& a, const TileArgs
 __device__ __forceinline__ u32 bkpad(u32 x) { return x + (x >> 4); }  // padded index: lane stride 17 words, conflict-free
 
 template <int W>
-__global__ void __launch_bounds__(WT_THREADS, WT_REG_CTAS) msp_tile_kernel(KP kp, P1Args a, TileArgs ta) {
+__global__ void __launch_bounds__(WT_THREADS, WT_CTAS) msp_tile_kernel(KP kp, P1Args a, TileArgs ta) {
     __shared__ __align__(128) u32 s_stage[NST][SBW];
     __shared__ __align__(16) u32 s_sc_all[WT_CW][WSC];
     __shared__ u32 s_bk_all[WT_CW][WBK];
@@ -378,36 +378,36 @@ __global__ void __launch_bounds__(WT_THREADS, WT_REG_CTAS) msp_tile_kernel(KP kp
     const u64 blk_first = ta.tile0 + (u64)blockIdx.x * ta.tstride;
     const bool tma_ok = (reinterpret_cast<unsigned long long>(a.words) & 15ull) == 0;
 
-    // Block i of this CTA -> ring slot i % NST by one bulk asynchronous copy (TMA) that completes on the slot's "full"
-    // mbarrier.  Called by a whole warp: warp 0 for the first NST blocks; afterwards the warp that finishes the LAST warp
-    // tile of block j waits for block j - 1 to be released (its "empty" mbarrier: normally long complete, every tile of
-    // block j - 1 was claimed before any tile of block j) and refills that slot with block j - 1 + NST.  There is no
-    // producer warp and nobody polls: a dedicated producer spinning on try_wait cost 12-16% of the executed instructions
-    // (neither __nanosleep nor the suspend-time hint parked it for longer than ~20 ns).
-    auto issue_load = [&](u32 i) {
-        const u64 blk = blk_first + (u64)i * blk_step;
-        if (blk >= ta.n_tiles) return;
-        const u32 s = i % NST;
-        const u64 g0B = ta.base0 + blk * bp;
-        const u64 sbB = (g0B > ta.base0 ? g0B - 1 : g0B) & ~63ull;   // 64 bases = 16 bytes: bulk-copy alignment
-        const u64 ow = sbB >> 5;                                      // first packed word of the block
-        const u64 avail = ow < a.n_words ? (a.n_words - ow) * 8 : 0;
-        const u32 copy = tma_ok ? (u32)min((u64)SB_BYTES, avail & ~15ull) : 0u;
-        // whatever the bulk copy cannot take (end of the buffer, unaligned caller memory) goes through registers
-        u64* dst = reinterpret_cast<u64*>(s_stage[s]);
-        for (u32 j = copy / 8 + lane; j < (u32)SB_BYTES / 8; j += 32) dst[j] = (ow + j) < a.n_words ? a.words[ow + j] : 0ull;
-        __syncwarp();
-        if (lane == 0) {
-            if (copy) {
-                mbar_arrive_expect_tx(&s_full[s], copy);
-                bulk_g2s(dst, a.words + ow, copy, &s_full[s]);
-            } else {
-                mbar_arrive(&s_full[s]);
+    if (warp == WT_CW) {
+        // ---- producer warp: block i of this CTA -> ring slot i % NST by one bulk asynchronous copy (TMA) that completes
+        // on the slot's "full" mbarrier, issued as soon as the slot's previous block was released ("empty" mbarrier).
+        // Measured alternatives without a producer warp (the finisher of a block's last tile refills a slot, elected by
+        // a shared counter or by tile number) ran 5-14% slower: the dedicated warp keeps the ring one block deeper and
+        // its polling only takes issue slots nobody else wanted. ----
+        u32 i = 0;
+        for (u64 blk = blk_first; blk < ta.n_tiles; blk += blk_step, i++) {
+            const u32 s = i % NST;
+            if (i >= (u32)NST) mbar_wait_suspended(&s_empty[s], ((i / NST) - 1) & 1);
+            const u64 g0B = ta.base0 + blk * bp;
+            const u64 sbB = (g0B > ta.base0 ? g0B - 1 : g0B) & ~63ull;   // 64 bases = 16 bytes: bulk-copy alignment
+            const u64 ow = sbB >> 5;                                      // first packed word of the block
+            const u64 avail = ow < a.n_words ? (a.n_words - ow) * 8 : 0;
+            const u32 copy = tma_ok ? (u32)min((u64)SB_BYTES, avail & ~15ull) : 0u;
+            // whatever the bulk copy cannot take (end of the buffer, unaligned caller memory) goes through registers
+            u64* dst = reinterpret_cast<u64*>(s_stage[s]);
+            for (u32 j = copy / 8 + lane; j < (u32)SB_BYTES / 8; j += 32) dst[j] = (ow + j) < a.n_words ? a.words[ow + j] : 0ull;
+            __syncwarp();
+            if (lane == 0) {
+                if (copy) {
+                    mbar_arrive_expect_tx(&s_full[s], copy);
+                    bulk_g2s(dst, a.words + ow, copy, &s_full[s]);
+                } else {
+                    mbar_arrive(&s_full[s]);
+                }
             }
         }
-    };
-    if (warp == 0)
-        for (u32 i = 0; i < (u32)NST; i++) issue_load(i);
+        return;
+    }
 
     // ---- consumer warps ----
     u32* const sc = s_sc_all[warp];
@@ -647,10 +647,6 @@ __global__ void __launch_bounds__(WT_THREADS, WT_REG_CTAS) msp_tile_kernel(KP kp
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[s]);   // this warp tile no longer reads ring slot s
-        if (wt == (u32)WT_CW - 1 && i >= 1) {      // last tile of block i: refill the slot of block i - 1
-            mbar_wait(&s_empty[(i - 1) % NST], ((i - 1) / NST) & 1);
-            issue_load(i - 1 + NST);
-        }
     }
 }
 

@@ -170,6 +170,33 @@ HD u32 exts_side(u32 v, int dir) { return dir ? (v >> 4) & 0xfu : v & 0xfu; }  /
 HD int popc4(u32 nib) { return (int)((0x4332322132212110ull >> (4 * nib)) & 7); }
 HD int unique_base(u32 nib) { return nib == 1 ? 0 : nib == 2 ? 1 : nib == 4 ? 2 : 3; }
 
+// ---- minimum-substring partitioning (src/msp.rs): score of a p-mer (p <= 16, right-aligned in 32 bits) and MSP bucket
+// of a k-mer.  score = a hash permutation of the CANONICAL p-mer when unstranded (min(perm[p], perm[rc p]), msp.rs:305-311
+// with a bijective perm), of the p-mer itself when stranded; bucket(k-mer) = low bits of the smallest score among its
+// K - p + 1 p-mers: a pure, strand-symmetric function of the k-mer, so every occurrence of a canonical k-mer lands in
+// the same bucket whatever read, strand or rank it was seen on. ----
+HD u32 pmer_score(u32 x, int p, bool stranded) {
+    if (!stranded) {
+        u32 r = (~rev2_32(x)) >> (32 - 2 * p);
+        x = x < r ? x : r;
+    }
+    x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA6Bu; x ^= x >> 13;
+    return x;
+}
+template <int W>
+HD u32 kmer_min_score(const KP& kp, Kmer<W> x, int p, bool stranded) {
+    const u32 pmask = p == 16 ? 0xffffffffu : ((1u << (2 * p)) - 1);
+    u32 best = 0xffffffffu;
+    // p-mer t (t = 0 .. K-p) = bases t .. t+p-1 = key >> 2(K-p-t); walk from the last p-mer towards the first by shifting right
+    for (int t = kp.k - p; t >= 0; t--) {
+        const u32 s = pmer_score((u32)x.lo & pmask, p, stranded);
+        best = s < best ? s : best;
+        if constexpr (W == 1) { x.lo >>= 2; }
+        else { x.lo = (x.lo >> 2) | (x.hi << 62); x.hi >>= 2; }
+    }
+    return best;
+}
+
 // ---- DnaString word layout (src/dna_string.rs:383-399): base b of the concatenation sits in word
 // b/32 at bits 62-2(b%32) --------------------------------------------------------------------------
 // 64 bits starting at base offset `b` (bases b..b+31 left-aligned); words[] must be readable at
