@@ -243,6 +243,53 @@ int dbg_graph_from_device(dbg_ctx* ctx, int k, int stranded, uint64_t n_nodes, u
                           const void* d_start, const void* d_length, const void* d_exts, const void* d_data,
                           dbg_graph** out);
 
+/* ---- multi-GPU entry points: the whole path over several GPUs INSIDE the library (NCCL over NVLink, CUDA IPC peer windows) ----
+ * Replaces the per-shard flow of the reference's sharded test (src/test.rs:418-470: msp_sequence -> per-shard filter_kmers ->
+ * per-shard compress -> BaseGraph::combine + compress_graph) with one collective call whose per-rank outputs, concatenated in
+ * rank order, are the single-GPU BaseGraph bit for bit (node order = ascending smallest k-mer).
+ * A communicator is one rank: one process per GPU (dbg_comm_create; every rank passes the same 128-byte id obtained from
+ * dbg_comm_unique_id on one rank and distributed by the caller's own rendezvous), or one process driving several GPUs with one
+ * host thread per rank (dbg_multi_*; the communicators are owned by the handle).  Calls are collective: every rank must make
+ * the same call.  Transport "nccl" = grouped ncclSend/ncclRecv + all-reduce on the ctx stream; "local" (dbg_multi_* only, when
+ * the device list repeats a device, NCCL is missing, or DBG_MULTI_TRANSPORT=local) stages through cudaMemcpy between the ranks'
+ * buffers and exists so that the multi-rank logic can be exercised on ONE GPU. */
+typedef struct dbg_comm dbg_comm;
+typedef struct dbg_multi dbg_multi;
+typedef struct {
+    uint32_t n_ranks, rank;
+    uint64_t n_input_total;  /* k-mer occurrences of the whole job */
+    uint64_t n_valid_total, n_valid_local;   /* valid k-mers: whole job / this rank's shard of the table */
+    uint64_t n_nodes_total, n_bases_total;   /* the complete BaseGraph */
+    uint64_t node0, base0;   /* position of this rank's run of nodes in the complete graph (0 when replicated) */
+    uint64_t n_queries_sent; /* neighbour lookups this rank had to send to other ranks */
+    uint64_t exchange_bytes_sent; /* super-k-mer record bytes this rank sent in the all-to-all */
+    uint32_t replicated;     /* 1 = long unitigs / cycles: the table was gathered and every rank returns the COMPLETE graph */
+    uint32_t check_ok;       /* n_bases_total == n_valid_total + n_nodes_total * (k - 1) and every k-mer was covered */
+    uint32_t msp_p, bucket_bits;
+    float ms_partition, ms_exchange, ms_count_sort, ms_links, ms_discover, ms_layout, ms_emit, ms_total;
+} dbg_multi_info;
+int dbg_comm_unique_id(void* id_out /* 128 bytes */);
+int dbg_comm_create(dbg_ctx* ctx, int n_ranks, int rank, const void* unique_id, dbg_comm** out);
+void dbg_comm_destroy(dbg_comm* comm);
+int dbg_comm_rank(const dbg_comm* comm);
+int dbg_comm_size(const dbg_comm* comm);
+const char* dbg_comm_transport(const dbg_comm* comm);
+/* filter_kmers(CountFilter) + compress_kmers_with_hash(SimpleCompress / ScmapCompress) over ALL ranks' sequences.  graph_out = this
+ * rank's run of nodes (start[] relative to the run; info->node0 / base0 place it), or the complete graph when info->replicated. */
+int dbg_reads_to_graph_multi(dbg_comm* comm, int k, const dbg_seqset* seqs, uint32_t min_kmer_obs, int stranded, int reduce_op,
+                             dbg_multi_info* info, dbg_graph** graph_out);
+/* one process, n ranks: rank i runs on devices[i] with its own ctx (dbg_multi_ctx: create that rank's sequence set on it) */
+int dbg_multi_create(const int* devices, int n, dbg_multi** out);
+void dbg_multi_destroy(dbg_multi* m);
+int dbg_multi_size(const dbg_multi* m);
+dbg_ctx* dbg_multi_ctx(dbg_multi* m, int rank);
+const char* dbg_multi_transport(const dbg_multi* m);
+int dbg_multi_reads_to_graph(dbg_multi* m, int k, const dbg_seqset* const* seqs, uint32_t min_kmer_obs, int stranded, int reduce_op,
+                             dbg_multi_info* infos /* n or NULL */, dbg_graph** graphs_out /* n */);
+/* pure host helpers of the plan (no GPU): bucket ownership (rank r owns [bounds[r], bounds[r+1])) and quantile cuts of a histogram */
+int dbg_plan_owner_bounds(uint64_t n_buckets, int n_ranks, uint64_t* bounds_out /* n_ranks + 1 */);
+int dbg_plan_quantile_cuts(const uint64_t* hist, uint64_t n_bins, int n_ranks, uint64_t* cuts_out /* n_ranks + 1 */);
+
 /* ---- msp::msp_sequence bucket assignment — src/msp.rs:279-324, 115-117 -----------------------------
  * For every k-mer start position j of every sequence: the MSP bucket of that k-mer under the
  * reference's default (identity) permutation with rc = !stranded, i.e. the value

@@ -34,6 +34,18 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class MultiInfo(C.Structure):
+    _fields_ = ([("n_ranks", C.c_uint32), ("rank", C.c_uint32)] +
+                [(n, C.c_uint64) for n in ("n_input_total", "n_valid_total", "n_valid_local", "n_nodes_total", "n_bases_total",
+                                           "node0", "base0", "n_queries_sent", "exchange_bytes_sent")] +
+                [(n, C.c_uint32) for n in ("replicated", "check_ok", "msp_p", "bucket_bits")] +
+                [(n, C.c_float) for n in ("ms_partition", "ms_exchange", "ms_count_sort", "ms_links", "ms_discover", "ms_layout",
+                                          "ms_emit", "ms_total")])
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 def build(verbose=False):
     """Compile every CUDA source for sm_100a into libdbg_b200.so (nvcc cross-compiles without a GPU)."""
     out = None if verbose else subprocess.DEVNULL
@@ -116,6 +128,21 @@ SIGNATURES = {
     "dbg_cs_emit": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp, vp, vp]),
     "dbg_graph_from_device": (C.c_int, [vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vpp]),
     "dbg_msp_kmer_buckets": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_uint64]),
+    "dbg_comm_unique_id": (C.c_int, [vp]),
+    "dbg_comm_create": (C.c_int, [vp, C.c_int, C.c_int, vp, vpp]),
+    "dbg_comm_destroy": (None, [vp]),
+    "dbg_comm_rank": (C.c_int, [vp]),
+    "dbg_comm_size": (C.c_int, [vp]),
+    "dbg_comm_transport": (C.c_char_p, [vp]),
+    "dbg_reads_to_graph_multi": (C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_int, C.c_int, C.POINTER(MultiInfo), vpp]),
+    "dbg_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, vpp]),
+    "dbg_multi_destroy": (None, [vp]),
+    "dbg_multi_size": (C.c_int, [vp]),
+    "dbg_multi_ctx": (C.c_void_p, [vp, C.c_int]),
+    "dbg_multi_transport": (C.c_char_p, [vp]),
+    "dbg_multi_reads_to_graph": (C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_int, C.c_int, vp, vp]),
+    "dbg_plan_owner_bounds": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
+    "dbg_plan_quantile_cuts": (C.c_int, [C.POINTER(C.c_uint64), C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

@@ -1407,6 +1407,11 @@ static int count_input(Ctx* c, int k, const SeqSet* s, u64* N_out, u32* max_len_
     return DBG_OK;
 }
 
+int count_input_kmers_dev(Ctx* c, int k, const SeqSet* s, u64* N_out) {
+    u32 max_len = 0;
+    return count_input(c, k, s, N_out, &max_len);
+}
+
 // Output of the partition stage: super-k-mer records grouped by MSP bucket.
 struct PartOut {
     DBuf<u64> rec;         // n_rec records of RW words, bucket-contiguous
