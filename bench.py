@@ -276,6 +276,9 @@ def main():
                 out_info["nodes_total"], out_info["bases_total"] = g.n_nodes_total, g.n_bases_total
                 out_info["n_valid_total"] = g.n_valid_total
                 out_info["check"] = g.invariants
+                out_info["stage_ms_rank0"] = {k_: round(v, 3) for k_, v in g.info.items() if k_.startswith("ms_")}
+                out_info["queries_sent_rank0"], out_info["exchange_bytes_sent_rank0"] = g.info["n_queries_sent"], g.info["exchange_bytes_sent"]
+                out_info["replicated"], out_info["transport"] = g.replicated, comm.transport
             else:
                 g = D.reads_to_graph(ss, filt, spec, stranded=False, k=k)
             n = len(g)

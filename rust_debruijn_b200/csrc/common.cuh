@@ -305,7 +305,8 @@ int count_input_kmers_dev(Ctx* c, int k, const SeqSet* s, u64* N_out);
 // ---- sharded compression over a bucket-sharded table (shard_compress.cu; orchestrated by multi.cu) ----------------
 #define DBG_MAX_RANKS 8
 struct ShardCfg { int P, me, p, bbits, stranded, scmap; };
-struct RecPeers { const uint4* rec[DBG_MAX_RANKS]; };   // every rank's walk records (2 x uint4 per k-mer), peer-mapped
+// every rank's peer-mapped window: walk records (one uint4 per k-mer) and a copy of the shard's k-mers
+struct RecPeers { const uint4* rec[DBG_MAX_RANKS]; const u64* klo[DBG_MAX_RANKS]; const u64* khi[DBG_MAX_RANKS]; };
 struct SegOff { u64 off[DBG_MAX_RANKS + 1]; };
 // neighbour queries of one rank, grouped by owning rank: segment r = [off[r], off[r + 1]) of msg / src
 struct MsQueries {
@@ -315,7 +316,7 @@ struct MsQueries {
     int lut_shift = 0;
     u64 n_total = 0, n_dst[DBG_MAX_RANKS] = {0}, off[DBG_MAX_RANKS + 1] = {0};
 };
-int ms_links_dev(Ctx* c, const Table* t, ShardCfg cfg, uint4* d_rec, MsQueries* q);
+int ms_links_dev(Ctx* c, const Table* t, ShardCfg cfg, uint4* d_rec, u64* d_klo, u64* d_khi, MsQueries* q);
 u32 ms_query_bytes(int k);
 u32 ms_path_bytes(int k);
 int ms_resolve_dev(Ctx* c, const Table* t, const MsQueries* q, int stranded, const void* d_queries, u64 nq, uint2* d_reply);
@@ -323,7 +324,8 @@ int ms_apply_dev(Ctx* c, const Table* t, ShardCfg cfg, const MsQueries* q, const
 int ms_link_error(Ctx* c, const MsQueries* q, u32* code);
 int ms_discover_dev(Ctx* c, int k, const RecPeers& peers, int me, u64 n, u32 lmax, u64* pk_lo, u64* pk_hi, u32* p_state, u32* p_len,
                     u64 cap, u64* n_paths, u64* n_covered);
-int ms_pack_paths_dev(Ctx* c, int k, const u64* k_lo, const u64* k_hi, const u32* idx, const u32* p_state, const u32* p_len, u64 m, int me, void* out);
+int ms_scatter_paths_dev(Ctx* c, int k, const u64* k_lo, const u64* k_hi, const u32* p_state, const u32* p_len, u64 m, int me, int P, int bits,
+                         const u64* cuts, const u64* seg_off, void* out);
 int ms_unpack_paths_dev(Ctx* c, int k, const void* in, u64 m, u64* k_lo, u64* k_hi, u32* idx);
 int ms_node_len_dev(Ctx* c, int k, const void* msgs, const u32* idx, u64 m, u64* node_len, u32* out_length);
 int ms_emit_dev(Ctx* c, int k, const RecPeers& peers, const void* msgs, const u32* idx, const u64* node_start, u64 m, int reduce_op,

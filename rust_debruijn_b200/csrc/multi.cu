@@ -415,13 +415,28 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     I.n_valid_local = V;
     // ================= compression over the sharded table =================
     TRY(arena_begin(c));
-    TRY(T->ensure_window((V ? V : 1) * 32));
+    // window of this rank: [walk records: V x 16 B][k-mers lo: V x 8 B][k-mers hi: V x 8 B (K > 32)], each part 256-byte aligned
+    const int W = k <= 32 ? 1 : 2;
+    std::vector<u64> Vs(P);
+    TRY(T->all_gather_host(&V, 1, Vs.data()));
+    auto al = [](u64 x) { return (x + 255) & ~255ull; };
+    TRY(T->ensure_window(al((V ? V : 1) * 16) + al((V ? V : 1) * 8) * W));
     RecPeers peers;
-    for (int r = 0; r < DBG_MAX_RANKS; r++) peers.rec[r] = r < P ? reinterpret_cast<const uint4*>(T->peer_ptr[r]) : nullptr;
+    for (int r = 0; r < DBG_MAX_RANKS; r++) {
+        peers.rec[r] = nullptr; peers.klo[r] = nullptr; peers.khi[r] = nullptr;
+        if (r >= P || !T->peer_ptr[r]) continue;
+        char* base = reinterpret_cast<char*>(T->peer_ptr[r]);
+        const u64 vr = Vs[r] ? Vs[r] : 1;
+        peers.rec[r] = reinterpret_cast<const uint4*>(base);
+        peers.klo[r] = reinterpret_cast<const u64*>(base + al(vr * 16));
+        peers.khi[r] = W == 2 ? reinterpret_cast<const u64*>(base + al(vr * 16) + al(vr * 8)) : nullptr;
+    }
     uint4* my_rec = reinterpret_cast<uint4*>(T->win);
+    u64* my_klo = const_cast<u64*>(peers.klo[me]);
+    u64* my_khi = const_cast<u64*>(peers.khi[me]);
     ShardCfg cfg{P, me, p, bbits, stranded, reduce_op == DBG_REDUCE_SCMAP};
     MsQueries q;
-    TRY(ms_links_dev(c, shard, cfg, my_rec, &q));
+    TRY(ms_links_dev(c, shard, cfg, my_rec, my_klo, my_khi, &q));
     I.n_queries_sent = q.n_total;
     // query counts: M[s][d] = queries rank s has for rank d
     std::vector<u64> M((u64)P * P);
@@ -448,10 +463,9 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     // every rank's records are final before anybody walks them
     TRY(T->barrier());
     // ---- discover the unitigs whose left end lies in this shard ----
-    DBuf<u64> pk_lo, pk_hi, pk_lo_b, pk_hi_b;
-    DBuf<u32> p_state, p_len, idx_a, idx_b;
+    DBuf<u64> pk_lo, pk_hi;
+    DBuf<u32> p_state, p_len;
     const u64 cap = V ? V : 1;
-    const int W = k <= 32 ? 1 : 2;
     TRY(pk_lo.alloc_pool(c, cap)); TRY(p_state.alloc_pool(c, cap)); TRY(p_len.alloc_pool(c, cap));
     if (W == 2) TRY(pk_hi.alloc_pool(c, cap));
     u64 n_paths = 0, n_cov = 0;
@@ -478,18 +492,12 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
         *out = g;
         return DBG_OK;
     }
-    // ---- path records -> the rank owning their seed's key range ----
-    TRY(idx_a.alloc_pool(c, cap)); TRY(idx_b.alloc_pool(c, cap)); TRY(pk_lo_b.alloc_pool(c, cap));
-    if (W == 2) TRY(pk_hi_b.alloc_pool(c, cap));
-    if (n_paths) { iota_kernel<<<grid_for(n_paths, 256), 256, 0, st>>>(idx_a.p, n_paths); TRY(check_launch(c, "iota")); }
-    u64 *rk_lo = pk_lo.p, *rk_hi = pk_hi.p;
-    u32* ridx = idx_a.p;
-    TRY(radix_sort_pairs(c, W, 2 * k, n_paths, pk_lo.p, pk_hi.p, idx_a.p, pk_lo_b.p, pk_hi_b.p, idx_b.p, &rk_lo, &rk_hi, &ridx));
+    // ---- path records -> the rank owning their seed's key range (quantile cuts of the all-reduced seed histogram) ----
     const int hb = std::min(16, 2 * k);
     const u64 nbins = 1ull << hb;
     DBuf<u32> d_hist, d_ghist;
     TRY(d_hist.alloc_pool(c, nbins)); TRY(d_ghist.alloc_pool(c, nbins));
-    TRY(ms_key_hist_dev(c, k, rk_lo, rk_hi, n_paths, hb, d_hist.p));
+    TRY(ms_key_hist_dev(c, k, pk_lo.p, pk_hi.p, n_paths, hb, d_hist.p));
     CU(c, cudaMemcpyAsync(d_ghist.p, d_hist.p, nbins * 4, cudaMemcpyDeviceToDevice, st));
     TRY(T->all_reduce_sum(d_ghist.p, nbins, false));
     std::vector<u32> h_hist(nbins), h_ghist(nbins);
@@ -502,7 +510,7 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
         for (u64 i = 0; i < nbins; i++) g64[i] = h_ghist[i];
         quantile_cuts(g64.data(), nbins, P, cuts);
         u64 acc = 0, b = 0;
-        for (int r = 0; r <= P; r++) {   // the local records are ascending: destination r gets the bins [cuts[r], cuts[r + 1])
+        for (int r = 0; r <= P; r++) {   // destination r gets the seeds whose bin lies in [cuts[r], cuts[r + 1])
             while (b < cuts[r]) acc += h_hist[b++];
             pbound[r] = acc;
         }
@@ -510,7 +518,7 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     const u32 pb = ms_path_bytes(k);
     DBuf<unsigned char> pmsg_out, pmsg_in;
     TRY(pmsg_out.alloc_pool(c, (n_paths ? n_paths : 1) * pb));
-    TRY(ms_pack_paths_dev(c, k, rk_lo, rk_hi, ridx, p_state.p, p_len.p, n_paths, me, pmsg_out.p));
+    TRY(ms_scatter_paths_dev(c, k, pk_lo.p, pk_hi.p, p_state.p, p_len.p, n_paths, me, P, hb, cuts, pbound, pmsg_out.p));
     u64 psend[DBG_MAX_RANKS];
     for (int r = 0; r < P; r++) psend[r] = pbound[r + 1] - pbound[r];
     std::vector<u64> PM((u64)P * P);
@@ -519,7 +527,7 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     for (int r = 0; r < P; r++) { so[r] = pbound[r] * pb; sc[r] = psend[r] * pb; ro[r] = m_own * pb; rc[r] = PM[(u64)r * P + me] * pb; m_own += PM[(u64)r * P + me]; }
     TRY(pmsg_in.alloc_pool(c, (m_own ? m_own : 1) * pb));
     TRY(T->all_to_all_v(pmsg_out.p, so, sc, pmsg_in.p, ro, rc));
-    // ---- own seed range: sort (P ascending runs -> one), node lengths, offsets ----
+    // ---- own seed range: sort, node lengths, offsets ----
     DBuf<u64> nk_lo, nk_hi, nk_lo_b, nk_hi_b, node_len, node_start, d_tot;
     DBuf<u32> ni_a, ni_b, olen;
     const u64 mcap = m_own ? m_own : 1;

@@ -11,15 +11,17 @@
 //             one 16/32-byte query; queries are grouped by owner, exchanged (all-to-all), answered from the owner's shard
 //             (index + the Exts nibble on the entered side + data), and the answers patched into the walk records.
 //             Consecutive k-mers of a unitig mostly share their minimizer, so only ~1 link in 8 is remote.
-//   records   32 bytes per k-mer: both links (index on the owning rank, side, owner rank), count, Exts, first / last
-//             base and the k-mer itself.  The record arrays of all ranks are mapped into every rank's address space
-//             (CUDA IPC over NVLink, or plain peer access inside one process).
-//   discover  every path end walks its unitig, hopping across ranks through the peer-mapped records (one 32-byte load
+//   records   16 bytes per k-mer: both links (index on the owning rank, side, owner rank), count, Exts, first / last
+//             base; next to them a copy of the shard's k-mers.  This WINDOW of every rank is mapped into every rank's
+//             address space (CUDA IPC over NVLink, or plain peer access inside one process).
+//   discover  every path end walks its unitig, hopping across ranks through the peer-mapped records (one 16-byte load
 //             per k-mer), tracking the smallest K-MER (= the seed, src/compression.rs:574-575: ascending k-mer order is
-//             the seed order) — the walk that traverses the seed "leaving through R" started at the node's left end and
+//             the seed order).  Inside one shard index order IS k-mer order, so k-mers are only fetched when the walk
+//             changes rank.  The walk that traverses the seed "leaving through R" started at the node's left end and
 //             emits one path record (seed k-mer, length, left end).
-//   layout    path records go to the rank owning their seed's key range (quantile splitters): that rank sorts them and
-//             holds a contiguous run of nodes of the final order.
+//   layout    path records go to the rank owning their seed's key range (quantile cuts of an all-reduced histogram,
+//             one CTA-aggregated scatter by destination): that rank sorts them and holds a contiguous run of nodes of
+//             the final order.
 //   emit      one thread per node re-walks its chain (peer loads again) and writes the node's bases / Exts / data.
 // Only unitigs reachable by end walks (<= lmax k-mers) are handled here; the caller falls back to gathering the table
 // and running the single-GPU compression when long unitigs or cycles are present.
@@ -38,9 +40,9 @@ template <> struct __align__(16) PathMsg<2> { u64 lo, hi; u32 state; u32 len_ran
 template <int W> __device__ __forceinline__ Kmer<W> qkey(const QMsg<W>& m) {
     if constexpr (W == 1) return Kmer<1>{m.lo}; else return Kmer<2>{m.lo, m.hi};
 }
-template <int W> __device__ __forceinline__ Kmer<W> rec_key(const uint4& b) {
-    if constexpr (W == 1) return Kmer<1>{((u64)b.y << 32) | b.x};
-    else return Kmer<2>{((u64)b.y << 32) | b.x, ((u64)b.w << 32) | b.z};
+template <int W> __device__ __forceinline__ Kmer<W> peer_key(const RecPeers& p, u32 rank, u32 idx) {
+    if constexpr (W == 1) return Kmer<1>{p.klo[rank][idx]};
+    else return Kmer<2>{p.klo[rank][idx], p.khi[rank][idx]};
 }
 
 // ---- links of the rank's shard; remote neighbours become queries (flat queue, grouped by owner afterwards) ----
@@ -49,7 +51,8 @@ template <int W>
 __global__ void __launch_bounds__(ML_THREADS) ms_links_kernel(KP kp, const u64* __restrict__ lo, const u64* __restrict__ hi,
                                                               const u8* __restrict__ exts, const u16* __restrict__ counts, u64 n,
                                                               const u64* __restrict__ lut, int lut_shift, ShardCfg cfg,
-                                                              uint4* __restrict__ rec, u64* __restrict__ q_lo, u64* __restrict__ q_hi,
+                                                              uint4* __restrict__ rec, u64* __restrict__ w_klo, u64* __restrict__ w_khi,
+                                                              u64* __restrict__ q_lo, u64* __restrict__ q_hi,
                                                               u32* __restrict__ q_src, u32* __restrict__ q_dst, u64 q_cap,
                                                               u64* __restrict__ ctr /* [0] queries, [1 + r] queries for rank r */,
                                                               u32* __restrict__ err) {
@@ -104,10 +107,9 @@ __global__ void __launch_bounds__(ML_THREADS) ms_links_kernel(KP kp, const u64* 
             both[d] = succ;
         }
         const u32 meta = (u32)counts[i] | (e << 16) | (Ops<W>::first_base(kp, key) << 24) | (Ops<W>::last_base(kp, key) << 26);
-        rec[2 * i] = make_uint4(both[0], both[1], meta, (u32)cfg.me | ((u32)cfg.me << 8));
-        u64 khi = 0;
-        if constexpr (W == 2) khi = key.hi;
-        rec[2 * i + 1] = make_uint4((u32)key.lo, (u32)(key.lo >> 32), (u32)khi, (u32)(khi >> 32));
+        rec[i] = make_uint4(both[0], both[1], meta, (u32)cfg.me | ((u32)cfg.me << 8));
+        w_klo[i] = key.lo;
+        if constexpr (W == 2) w_khi[i] = key.hi;
         if (nq) {
             slot = atomicAdd(&s_n, nq);
             for (u32 t = 0; t < nq; t++) atomicAdd(&s_dst[qd[t] & 0xffu], 1u);
@@ -208,7 +210,7 @@ __global__ void ms_apply_kernel(KP kp, const u64* __restrict__ lo, const u64* __
         Kmer<W> back = inc == 0 ? Ops<W>::ext_left(kp, nk, unique_base(nnib)) : Ops<W>::ext_right(kp, nk, unique_base(nnib));
         if (!cfg.stranded) { const Kmer<W> rr = Ops<W>::rc(kp, back); if (!(back < rr)) back = rr; }
         if (back == key) {
-            u32* w = reinterpret_cast<u32*>(rec + 2 * (u64)i);
+            u32* w = reinterpret_cast<u32*>(rec + (u64)i);
             w[d] = 2u * r.x + (u32)(inc ^ 1);
             reinterpret_cast<u8*>(w + 3)[d] = (u8)owner;
         } else {
@@ -218,6 +220,8 @@ __global__ void ms_apply_kernel(KP kp, const u64* __restrict__ lo, const u64* __
 }
 
 // ---- discover: path ends walk across the peer-mapped records ----
+// Running minimum of the walk = (rank, index): on the same rank the smaller index is the smaller k-mer (shards are
+// ascending); k-mers are fetched and compared only when the walk reaches a k-mer of another rank than the candidate's.
 template <int W>
 __global__ void __launch_bounds__(256) ms_discover_kernel(RecPeers peers, int me, u64 n, u32 lmax, u64* __restrict__ pk_lo,
                                                            u64* __restrict__ pk_hi, u32* __restrict__ p_state, u32* __restrict__ p_len,
@@ -228,28 +232,35 @@ __global__ void __launch_bounds__(256) ms_discover_kernel(RecPeers peers, int me
     Kmer<W> seed = Ops<W>::zero();
     u32 len = 0, left_state = 0;
     if (v < n) {
-        const uint4* mine = peers.rec[me];
-        const uint4 a0 = mine[2 * v], b0 = mine[2 * v + 1];
-        const Kmer<W> key = rec_key<W>(b0);
+        const uint4 a0 = peers.rec[me][v];
         if (a0.x == NIL && a0.y == NIL) {
-            emit = true; seed = key; len = 1; left_state = 2u * (u32)v + 1u;   // stored orientation: heading right = leaving through R
+            emit = true; seed = peer_key<W>(peers, (u32)me, (u32)v); len = 1; left_state = 2u * (u32)v + 1u;   // stored orientation: heading right = leaving through R
         } else if (a0.x == NIL || a0.y == NIL) {
             const u32 d = a0.x == NIL ? 1u : 0u;   // the linked side: walk inwards through it
-            u32 cnt = 1, minside = d;
-            Kmer<W> minkey = key;
+            u32 cnt = 1;
+            u32 c_rank = (u32)me, c_idx = (u32)v, c_side = d;   // candidate seed: where, and through which side the walk leaves it
+            bool c_known = false;
+            Kmer<W> c_key = Ops<W>::zero();
             u32 t = d ? a0.y : a0.x;
             u32 trank = (a0.w >> (8 * d)) & 0xffu;
             while (t != NIL && cnt <= lmax) {
-                const uint4* rp = peers.rec[trank] + 2 * (u64)(t >> 1);
-                const uint4 a = rp[0], b = rp[1];
-                const u32 side = t & 1u;
+                const u32 idx = t >> 1, side = t & 1u;
+                const uint4 a = peers.rec[trank][idx];
                 cnt++;
-                const Kmer<W> k2 = rec_key<W>(b);
-                if (k2 < minkey) { minkey = k2; minside = side; }
+                if (trank == c_rank) {
+                    if (idx < c_idx) { c_idx = idx; c_side = side; c_known = false; }
+                } else {
+                    if (!c_known) { c_key = peer_key<W>(peers, c_rank, c_idx); c_known = true; }
+                    const Kmer<W> k2 = peer_key<W>(peers, trank, idx);
+                    if (k2 < c_key) { c_key = k2; c_rank = trank; c_idx = idx; c_side = side; }
+                }
                 t = side ? a.y : a.x;
                 trank = (a.w >> (8 * side)) & 0xffu;
             }
-            if (t == NIL && minside == 1u) { emit = true; seed = minkey; len = cnt; left_state = 2u * (u32)v + d; }
+            if (t == NIL && c_side == 1u) {
+                emit = true; len = cnt; left_state = 2u * (u32)v + d;
+                seed = c_known ? c_key : peer_key<W>(peers, c_rank, c_idx);
+            }
         }
     }
     __shared__ u32 s_wcnt[8], s_wcov[8];
@@ -278,19 +289,37 @@ __global__ void __launch_bounds__(256) ms_discover_kernel(RecPeers peers, int me
     }
 }
 
-// path records sorted by seed (payload = original index) -> messages for the rank owning the seed's key range
+// path records (any order) -> messages grouped by the rank owning the seed's key range: destination = range of the seed's
+// top-bits bin among the quantile cuts; one reservation per (CTA, destination)
 template <int W>
-__global__ void ms_pack_paths_kernel(const u64* __restrict__ k_lo, const u64* __restrict__ k_hi, const u32* __restrict__ idx,
-                                     const u32* __restrict__ p_state, const u32* __restrict__ p_len, u64 m, int me, PathMsg<W>* __restrict__ out) {
+__global__ void __launch_bounds__(256) ms_scatter_paths_kernel(const u64* __restrict__ k_lo, const u64* __restrict__ k_hi,
+                                                                const u32* __restrict__ p_state, const u32* __restrict__ p_len, u64 m, int me,
+                                                                int P, int bin_shift, SegOff cuts /* bins */, SegOff seg /* message offsets */,
+                                                                u64* __restrict__ seg_fill, PathMsg<W>* __restrict__ out) {
+    __shared__ u32 s_cnt[DBG_MAX_RANKS];
+    __shared__ u64 s_base[DBG_MAX_RANKS];
+    if (threadIdx.x < DBG_MAX_RANKS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const u32 j = idx[i];
-    PathMsg<W> r;
-    r.lo = k_lo[i];
-    if constexpr (W == 2) { r.hi = k_hi[i]; r.pad = 0; }
-    r.state = p_state[j];
-    r.len_rank = p_len[j] | ((u32)me << 16);
-    out[i] = r;
+    u32 dst = 0, loc = 0;
+    Kmer<W> key = Ops<W>::zero();
+    if (i < m) {
+        if constexpr (W == 1) key = Kmer<1>{k_lo[i]}; else key = Kmer<2>{k_lo[i], k_hi[i]};
+        const u32 bin = key_prefix<W>(key, bin_shift);
+        while ((int)dst + 1 < P && (u64)bin >= cuts.off[dst + 1]) dst++;
+        loc = atomicAdd(&s_cnt[dst], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < DBG_MAX_RANKS && s_cnt[threadIdx.x]) s_base[threadIdx.x] = seg.off[threadIdx.x] + atomicAdd(&seg_fill[threadIdx.x], (u64)s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (i < m) {
+        PathMsg<W> r;
+        r.lo = key.lo;
+        if constexpr (W == 2) { r.hi = key.hi; r.pad = 0; }
+        r.state = p_state[i];
+        r.len_rank = p_len[i] | ((u32)me << 16);
+        out[s_base[dst] + loc] = r;
+    }
 }
 template <int W>
 __global__ void ms_unpack_paths_kernel(const PathMsg<W>* __restrict__ in, u64 m, u64* __restrict__ k_lo, u64* __restrict__ k_hi, u32* __restrict__ idx) {
@@ -346,9 +375,8 @@ __global__ void ms_emit_kernel(KP kp, RecPeers peers, const PathMsg<W>* __restri
     {   // first k-mer: all K bases (compression.rs:489-495)
         const u32 dw = cur & 1u;
         const bool fw = dw == 1u;    // leaving through R while heading right = stored orientation
-        const uint4* rp = peers.rec[rank] + 2 * (u64)(cur >> 1);
-        const uint4 r = rp[0], kb = rp[1];
-        Kmer<W> key = rec_key<W>(kb);
+        const uint4 r = peers.rec[rank][cur >> 1];
+        Kmer<W> key = peer_key<W>(peers, rank, cur >> 1);
         if (!fw) key = Ops<W>::rc(kp, key);
         if constexpr (W == 1) {
             nw.push(key.lo << (64 - 2 * K), K, pos);
@@ -375,7 +403,7 @@ __global__ void ms_emit_kernel(KP kp, RecPeers peers, const PathMsg<W>* __restri
     for (u32 j = 1; j < len; j++) {
         const u32 dw = cur & 1u;
         const bool fw = dw == 1u;
-        const uint4 r = peers.rec[rank][2 * (u64)(cur >> 1)];
+        const uint4 r = peers.rec[rank][cur >> 1];
         const u32 fb = (r.z >> 24) & 3u, lb = (r.z >> 26) & 3u;
         const u64 b = fw ? lb : 3u - fb;                 // last base of the k-mer as it appears in the node
         nw.push(b << 62, 1, pos);
@@ -406,7 +434,7 @@ __global__ void ms_emit_kernel(KP kp, RecPeers peers, const PathMsg<W>* __restri
 // stage entry points (called by multi.cu)
 // ================================================================================================
 template <int W>
-static int ms_links_impl(Ctx* c, const Table* t, ShardCfg cfg, uint4* d_rec, MsQueries* q) {
+static int ms_links_impl(Ctx* c, const Table* t, ShardCfg cfg, uint4* d_rec, u64* d_klo, u64* d_khi, MsQueries* q) {
     cudaStream_t st = c->stream;
     KP kp = make_kp(t->k);
     const u64 n = t->n;
@@ -422,7 +450,7 @@ static int ms_links_impl(Ctx* c, const Table* t, ShardCfg cfg, uint4* d_rec, MsQ
     const u64 cap = 2 * n;
     TRY(f_lo.alloc_pool(c, cap)); TRY(f_src.alloc_pool(c, cap)); TRY(f_dst.alloc_pool(c, cap));
     if (W == 2) TRY(f_hi.alloc_pool(c, cap));
-    ms_links_kernel<W><<<grid_for(n, ML_THREADS), ML_THREADS, 0, st>>>(kp, t->lo, t->hi, t->exts, t->counts, n, q->lut.p, q->lut_shift, cfg, d_rec,
+    ms_links_kernel<W><<<grid_for(n, ML_THREADS), ML_THREADS, 0, st>>>(kp, t->lo, t->hi, t->exts, t->counts, n, q->lut.p, q->lut_shift, cfg, d_rec, d_klo, d_khi,
                                                                       f_lo.p, f_hi.p, f_src.p, f_dst.p, cap, q->ctr.p, (u32*)(q->ctr.p + 1 + DBG_MAX_RANKS));
     TRY(check_launch(c, "ms_links"));
     u64 h[2 + DBG_MAX_RANKS];
@@ -447,8 +475,8 @@ static int ms_links_impl(Ctx* c, const Table* t, ShardCfg cfg, uint4* d_rec, MsQ
     }
     return DBG_OK;
 }
-int ms_links_dev(Ctx* c, const Table* t, ShardCfg cfg, uint4* d_rec, MsQueries* q) {
-    return t->k <= 32 ? ms_links_impl<1>(c, t, cfg, d_rec, q) : ms_links_impl<2>(c, t, cfg, d_rec, q);
+int ms_links_dev(Ctx* c, const Table* t, ShardCfg cfg, uint4* d_rec, u64* d_klo, u64* d_khi, MsQueries* q) {
+    return t->k <= 32 ? ms_links_impl<1>(c, t, cfg, d_rec, d_klo, d_khi, q) : ms_links_impl<2>(c, t, cfg, d_rec, d_klo, d_khi, q);
 }
 u32 ms_query_bytes(int k) { return k <= 32 ? (u32)sizeof(QMsg<1>) : (u32)sizeof(QMsg<2>); }
 u32 ms_path_bytes(int k) { return k <= 32 ? (u32)sizeof(PathMsg<1>) : (u32)sizeof(PathMsg<2>); }
@@ -506,11 +534,20 @@ int ms_discover_dev(Ctx* c, int k, const RecPeers& peers, int me, u64 n, u32 lma
     return DBG_OK;
 }
 
-int ms_pack_paths_dev(Ctx* c, int k, const u64* k_lo, const u64* k_hi, const u32* idx, const u32* p_state, const u32* p_len, u64 m, int me, void* out) {
+// cuts: P + 1 bin indices over the top `bits` key bits; seg_off: P + 1 message offsets (prefix sums of the per-destination
+// counts the caller derived from the local histogram and the cuts)
+int ms_scatter_paths_dev(Ctx* c, int k, const u64* k_lo, const u64* k_hi, const u32* p_state, const u32* p_len, u64 m, int me, int P, int bits,
+                         const u64* cuts, const u64* seg_off, void* out) {
     if (!m) return DBG_OK;
-    if (k <= 32) ms_pack_paths_kernel<1><<<grid_for(m, 256), 256, 0, c->stream>>>(k_lo, k_hi, idx, p_state, p_len, m, me, reinterpret_cast<PathMsg<1>*>(out));
-    else ms_pack_paths_kernel<2><<<grid_for(m, 256), 256, 0, c->stream>>>(k_lo, k_hi, idx, p_state, p_len, m, me, reinterpret_cast<PathMsg<2>*>(out));
-    return check_launch(c, "ms_pack_paths");
+    SegOff cu, sg;
+    for (int r = 0; r <= DBG_MAX_RANKS; r++) { cu.off[r] = cuts[r <= P ? r : P]; sg.off[r] = seg_off[r <= P ? r : P]; }
+    DBuf<u64> fill;
+    TRY(fill.alloc_pool(c, DBG_MAX_RANKS));
+    TRY(fill.zero());
+    const int shift = 2 * k - bits;
+    if (k <= 32) ms_scatter_paths_kernel<1><<<grid_for(m, 256), 256, 0, c->stream>>>(k_lo, k_hi, p_state, p_len, m, me, P, shift, cu, sg, fill.p, reinterpret_cast<PathMsg<1>*>(out));
+    else ms_scatter_paths_kernel<2><<<grid_for(m, 256), 256, 0, c->stream>>>(k_lo, k_hi, p_state, p_len, m, me, P, shift, cu, sg, fill.p, reinterpret_cast<PathMsg<2>*>(out));
+    return check_launch(c, "ms_scatter_paths");
 }
 int ms_unpack_paths_dev(Ctx* c, int k, const void* in, u64 m, u64* k_lo, u64* k_hi, u32* idx) {
     if (!m) return DBG_OK;

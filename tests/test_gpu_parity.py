@@ -463,23 +463,45 @@ def test_msp_kmer_buckets_match_scanner(D, ctx, orc, k, p):
         assert np.array_equal(got, np.concatenate(exp))
 
 
-def test_sharded_two_gpus():
-    """MSP-bucket-sharded filter_kmers over 2 ranks (one NCCL all-to-all) + key-range gathered table + compression with the
-    work split over the ranks: BaseGraph bit-identical to the oracle run on the union of both ranks' reads, as the
-    complete graph on every rank and as per-rank runs of nodes.  Needs >= 2 GPUs (skipped otherwise)."""
+def _run_tool(args, timeout=900):
     import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    return subprocess.run([sys.executable] + args, capture_output=True, text=True, timeout=timeout, cwd=root)
+
+
+@pytest.mark.parametrize("ranks", [2, 3])
+def test_multi_rank_path_on_one_gpu(ranks):
+    """The multi-GPU path of the library (dbg_multi_reads_to_graph: MSP-bucket-sharded filter_kmers, bucket-sharded table,
+    remote neighbour queries, cross-rank unitig walks, path records by seed-key range) with several ranks on ONE device over
+    the local transport: the per-rank runs of nodes, concatenated, are the oracle's BaseGraph bit for bit — K=31 noisy / clean
+    (replicated fallback), K=63, stranded + max, many buckets (p >= 13), ScmapCompress.  tools/multi_check.py."""
+    r = _run_tool([os.path.join("tools", "multi_check.py"), "--local", str(ranks), "--reads", "30000"])
+    assert r.returncode == 0 and "MULTI OK" in r.stdout and r.stdout.count("BIT-EXACT") == 6 and "MISMATCH" not in r.stdout, \
+        r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_multi_rank_path_2m_reads_on_one_gpu():
+    """Same at 2 * 10^6 reads in total (N = 2.4 * 10^8 k-mers, 2^13+ buckets, ~7 * 10^6 valid k-mers over 2 ranks)."""
+    r = _run_tool([os.path.join("tools", "multi_check.py"), "--local", "2", "--reads", "2000", "--big-reads", "2000000"])
+    assert r.returncode == 0 and "MULTI OK" in r.stdout and "R=2000000" in r.stdout and "MISMATCH" not in r.stdout, \
+        r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_multi_gpu_nccl():
+    """One process per GPU under torchrun (NCCL all-to-alls + CUDA IPC peer windows inside the library): bit-exact vs the oracle
+    on the union of the ranks' reads, incl. a 2 * 10^6-read configuration.  Needs >= 2 GPUs (skipped otherwise)."""
     import sys
 
     import torch
-    if torch.cuda.device_count() < 2:
+    n = torch.cuda.device_count()
+    if n < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
-    root = os.path.dirname(HERE)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "sharded_check.py"),
-                        "--reads", "20000"], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    # three configurations, each checked in both output modes (complete graph on every rank / node-sharded)
-    assert r.stdout.count("node-sharded BIT-EXACT") == 3 and r.stdout.count("BIT-EXACT") == 6 and "MISMATCH" not in r.stdout
+    n = 2 if n < 4 else 4
+    r = _run_tool(["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+                   "--master-port", "29533", os.path.join("tools", "multi_check.py"), "--reads", "40000", "--big-reads", "2000000"])
+    assert r.returncode == 0 and "MULTI OK" in r.stdout and r.stdout.count("BIT-EXACT") == 7 and "MISMATCH" not in r.stdout, \
+        r.stdout[-3000:] + r.stderr[-3000:]
 
 
 def _full_size_bit_exact(D, orc, k, also_staged):

@@ -1,6 +1,8 @@
-"""world_size-2 gloo tests (CPU) of the host-side logic of the multi-GPU path: bucket ownership, the
-per-bucket count exchange, and the offsets dbg_filter_from_records derives from it.  The records themselves
-move on GPUs (tests/test_gpu_parity.py::test_sharded_two_gpus and tools/sharded_check.py)."""
+"""world_size-2/3 gloo tests (CPU) of the host-side logic of the multi-GPU path: bucket ownership, the per-bucket count
+exchange, and the quantile cuts that route path records to the rank owning their seed's key range.  The planning functions
+are the library's own (dbg_plan_owner_bounds / dbg_plan_quantile_cuts through ctypes: pure host code, no GPU needed).  The
+data itself moves on GPUs: tests/test_gpu_parity.py::test_multi_rank_path_on_one_gpu (several ranks on one device) and
+::test_multi_gpu_nccl (torchrun, NCCL + CUDA IPC), both through tools/multi_check.py."""
 import os
 import socket
 
@@ -32,13 +34,11 @@ def _worker(rank, world, port, nb, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nb", [(2, 16), (2, 1), (3, 8)])
+@pytest.mark.parametrize("world,nb", [(2, 16), (2, 2), (3, 8)])
 def test_count_exchange_gloo(world, nb):
     import torch.multiprocessing as mp
 
     from rust_debruijn_b200 import sharded
-    if nb < world:
-        nb = world
     port = _free_port()
     mgr = mp.Manager()
     out = mgr.dict()
@@ -57,13 +57,17 @@ def test_count_exchange_gloo(world, nb):
 
 
 def test_owner_bounds_properties():
+    """bounds agree with the device-side owner function owner(b) = (b * P) >> bits, every rank owns >= 1 bucket."""
     from rust_debruijn_b200 import sharded
-    for world in (1, 2, 3, 4, 8):
-        assert sharded.min_bucket_bits(world) == int(np.ceil(np.log2(world))) if world > 1 else True
+    for world in (1, 2, 3, 4, 5, 8):
+        assert sharded.min_bucket_bits(world) == (int(np.ceil(np.log2(world))) if world > 1 else 0)
         for bits in range(sharded.min_bucket_bits(world), 12):
             b = sharded.owner_bounds(1 << bits, world)
             sizes = np.diff(b)
-            assert sizes.min() >= 1 and sizes.max() - sizes.min() <= 1
+            assert b[0] == 0 and b[-1] == 1 << bits and sizes.min() >= 1 and sizes.max() - sizes.min() <= 1
+            owner = (np.arange(1 << bits, dtype=np.uint64) * np.uint64(world)) >> np.uint64(bits)
+            for r in range(world):
+                assert np.all(owner[b[r]:b[r + 1]] == r)
 
 
 def test_key_range_splitters():
@@ -79,7 +83,7 @@ def test_key_range_splitters():
                 assert max(mass) <= hist.sum() / world + hist.max() + 1
 
 
-def _seed_worker(rank, world, port, V, n, out):
+def _seed_worker(rank, world, port, bits, n, out):
     import torch
     import torch.distributed as dist
 
@@ -88,39 +92,40 @@ def _seed_worker(rank, world, port, V, n, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.default_rng(7 + rank)
-    # seeds crowd the low indices (minimum of a few uniform draws), different amounts per rank
-    seeds = np.sort(np.minimum.reduce(rng.integers(0, V, size=(4, n + 100 * rank)), axis=0)).astype(np.int64)
-    bnd = sharded.balanced_seed_bounds(torch.from_numpy(seeds), V, world)
-    out[rank] = (seeds, bnd.numpy().copy())
+    # seed k-mers (62-bit keys) crowd the low values (a seed is the minimum of its unitig), different amounts per rank
+    keys = np.sort(np.minimum.reduce(rng.integers(0, 1 << 62, size=(4, n + 100 * rank), dtype=np.int64), axis=0))
+    hist_local = np.bincount((keys >> (62 - bits)).astype(np.int64), minlength=1 << bits).astype(np.int64)
+    hg = torch.from_numpy(hist_local.copy())
+    dist.all_reduce(hg)                                             # the library: ncclAllReduce of the same histogram
+    cuts = sharded.key_range_splitters(hg.numpy(), world)           # identical on every rank
+    bnd = sharded.local_bounds(hist_local, cuts)
+    out[rank] = (keys, bnd, cuts)
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_balanced_seed_bounds_gloo(world):
-    """Seed-range splitters of the sharded compression: contiguous slices, the same seed thresholds on every rank,
-    destinations balanced by node count although the seeds are far from uniform."""
+def test_seed_key_ranges_gloo(world):
+    """Seed-key ranges of the sharded compression: contiguous slices, the same cuts on every rank, destinations balanced by node
+    count although the seeds are far from uniform, ranges ordered (so that per-rank runs concatenate to the global node order)."""
     import torch.multiprocessing as mp
-    V, n = 1_000_000, 20_000
+    bits, n = 16, 20_000
     port = _free_port()
     out = mp.Manager().dict()
-    mp.spawn(_seed_worker, args=(world, port, V, n, out), nprocs=world, join=True)
+    mp.spawn(_seed_worker, args=(world, port, bits, n, out), nprocs=world, join=True)
     per_dst = np.zeros(world, np.int64)
-    hi_prev = [-1] * world   # largest seed sent to each destination so far / smallest sent to the next
+    hi = [-1] * world
+    lo = [1 << 62] * world
     for r in range(world):
-        seeds, bnd = out[r]
-        assert bnd[0] == 0 and bnd[-1] == len(seeds) and np.all(np.diff(bnd) >= 0)
+        keys, bnd, cuts = out[r]
+        assert cuts == out[0][2]
+        assert bnd[0] == 0 and bnd[-1] == len(keys) and all(bnd[i] <= bnd[i + 1] for i in range(world))
         for d in range(world):
-            sl = seeds[bnd[d]:bnd[d + 1]]
+            sl = keys[bnd[d]:bnd[d + 1]]
             per_dst[d] += len(sl)
             if len(sl):
-                hi_prev[d] = max(hi_prev[d], int(sl.max()))
-    # ranges are disjoint and ordered across ranks: everything sent to d is below everything sent to d + 1
-    for r in range(world):
-        seeds, bnd = out[r]
-        for d in range(1, world):
-            sl = seeds[bnd[d]:bnd[d + 1]]
-            if len(sl):
-                assert int(sl.min()) > max(hi_prev[:d])
+                hi[d], lo[d] = max(hi[d], int(sl.max())), min(lo[d], int(sl.min()))
+    for d in range(1, world):
+        assert lo[d] > max(hi[:d])
     total = per_dst.sum()
-    assert per_dst.max() - per_dst.min() <= 0.1 * total / world + 4096   # quantile cuts at 4096-bin granularity
+    assert per_dst.max() - per_dst.min() <= 0.1 * total / world + 4096   # quantile cuts at 2^16-bin granularity

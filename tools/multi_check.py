@@ -43,7 +43,7 @@ CONFIGS = [  # (k, noisy, min_obs, stranded, reduce_op, params)
     (31, False, 1, False, 0, {}),            # one genome-long unitig: the replicated fallback
     (63, True, 2, False, 0, {}),
     (32, True, 2, True, 3, {}),
-    (31, True, 2, False, 0, {"bucket_occ": 64}),   # many buckets: minimizer length follows the bucket count (p >= 13)
+    (31, True, 2, False, 0, {"bucket_occ": 16}),   # many buckets: minimizer length follows the bucket count (p >= 13)
     (31, True, 2, False, 4, {}),             # ScmapCompress: join_test crosses ranks
 ]
 
