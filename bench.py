@@ -260,8 +260,8 @@ def main():
         for i in range(args.steps):
             res = fn()
             ev[i + 1].record(ext)
-            if sampler is not None:
-                sampler.sample()
+            if sampler is not None and (i + 1 == args.steps // 2 or i + 1 == args.steps):
+                sampler.sample()   # two samples per run: NVML reads were seen to stall a step now and then
         barrier()
         per = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
         return ev[0].elapsed_time(ev[-1]), per, res
@@ -285,9 +285,12 @@ def main():
             g.free()
             return n
 
+        sampler = ClockSampler(local)
         for _ in range(args.warmup):
             step()
-        sampler = ClockSampler(local)
+            if not args.no_clocks:
+                sampler.sample()   # NVML's first reads are slow (lazy initialisation) and showed up as a slow 2nd timed step
+        sampler.sm, sampler.reasons = [], set()
         st0 = ctx.stats()
         ms_total, per, _ = timed(step, None if args.no_clocks else sampler)
         remeasured = None
@@ -295,7 +298,7 @@ def main():
         if (world == 1 and bad) or disturbed(per):
             remeasured = {"first_ms_per_step": ms_total / args.steps, "first_step_ms": [round(x, 3) for x in per],
                           "reason": sorted(bad) or ["isolated slow steps: host interference"]}
-            sampler = ClockSampler(local)
+            sampler.sm, sampler.reasons = [], set()
             st0 = ctx.stats()
             ms_total, per, _ = timed(step, None if args.no_clocks else sampler)
         st1 = ctx.stats()

@@ -322,11 +322,23 @@ u32 ms_path_bytes(int k);
 int ms_resolve_dev(Ctx* c, const Table* t, const MsQueries* q, int stranded, const void* d_queries, u64 nq, uint2* d_reply);
 int ms_apply_dev(Ctx* c, const Table* t, ShardCfg cfg, const MsQueries* q, const uint2* d_reply, uint4* d_rec);
 int ms_link_error(Ctx* c, const MsQueries* q, u32* code);
-int ms_discover_dev(Ctx* c, int k, const RecPeers& peers, int me, u64 n, u32 lmax, u64* pk_lo, u64* pk_hi, u32* p_state, u32* p_len,
-                    u64 cap, u64* n_paths, u64* n_covered);
-int ms_scatter_paths_dev(Ctx* c, int k, const u64* k_lo, const u64* k_hi, const u32* p_state, const u32* p_len, u64 m, int me, int P, int bits,
-                         const u64* cuts, const u64* seg_off, void* out);
-int ms_unpack_paths_dev(Ctx* c, int k, const void* in, u64 m, u64* k_lo, u64* k_hi, u32* idx);
+// outputs of one walker round: destinations 0 .. P-1 = per-rank outboxes, P = the rank's own list (emit entries / finished nodes)
+struct WalkOut {
+    void* box[DBG_MAX_RANKS + 1];
+    u64 cap[DBG_MAX_RANKS + 1];
+    u64* cursor;   // [0 .. P] items appended per destination, [P + 1] k-mers covered by the emit entries, [P + 2] overflow flag
+    int P;
+};
+int ms_count_ends_dev(Ctx* c, const uint4* d_rec, u64 n, u64* d_out);
+u32 ms_witem_bytes();
+u32 ms_entry_bytes();
+u32 ms_citem_bytes(int k);
+int ms_walk_start_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, u64 n, u32 lmax, const WalkOut& out);
+int ms_walk_continue_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, const void* inbox, u64 n_in, u32 lmax, const WalkOut& out);
+int ms_collect_start_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, const void* entries, u64 n, int reduce_op, const WalkOut& out);
+int ms_collect_continue_dev(Ctx* c, int k, const uint4* rec, int me, const void* inbox, u64 n, int reduce_op, const WalkOut& out);
+int ms_scatter_nodes_dev(Ctx* c, int k, const void* nmsg, u64 m, int P, int bits, const u64* cuts, const u64* seg_off, void* out);
+int ms_unpack_nodes_dev(Ctx* c, int k, const void* in, u64 m, u64* k_lo, u64* k_hi, u32* idx);
 int ms_node_len_dev(Ctx* c, int k, const void* msgs, const u32* idx, u64 m, u64* node_len, u32* out_length);
 int ms_emit_dev(Ctx* c, int k, const RecPeers& peers, const void* msgs, const u32* idx, const u64* node_start, u64 m, int reduce_op,
                 u64* words, u8* out_exts, u16* out_data);

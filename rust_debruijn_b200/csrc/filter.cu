@@ -820,8 +820,6 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
     __shared__ u32 s_stack[SPLIT_STACK];  // (residue << 6) | bits ; residue < 2^26 (deeper => error)
     SmemTable<W> tab{keys, vals};
     const int K = kp.k;
-    const int nxt_word = K >> 5;               // word of the shift register holding base K
-    const int nxt_shift = 62 - 2 * (K & 31);   // its bit position there
     const int tl = a.task_len;
 
     // thread 0 keeps one bucket in flight: the queue atomic and the bucket's (start, count) loads are issued while the
@@ -1102,7 +1100,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                 // Per-lane claims on purpose: no warp-level primitive inside this loop, so lanes may drift freely.
                 for (;;) {
                     const u32 q = atomicAdd(&s_next, 1u);
-                    if (q >= NT || *reinterpret_cast<volatile u32*>(&s_overflow)) break;
+                    if (q >= NT) break;
                     {
                     const u32 task = s_task[q];
                     const u32 ri = task & 1023u;
@@ -1148,15 +1146,28 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                         fwd.lo = sh ? ((s[1] >> sh) | (s[0] << (64 - sh))) : s[1];
                     }
                     Kmer<W> rcv = Ops<W>::rc(kp, fwd);
+                    // the (at most 16) bases a task can touch, as two 32-bit windows: PF = bases t .. t+15 (the first bases of its
+                    // k-mers), NX = bases t+K .. t+K+15 (the bases shifted in); no shift register of the whole record in the loop
+                    u32 PF = (u32)(s[0] >> 32), NX;
+                    if constexpr (W == 1) {
+                        NX = K < 32 ? (u32)(((s[0] << (2 * K)) | (s[1] >> (64 - 2 * K))) >> 32) : (u32)(s[1] >> 32);
+                    } else {
+                        const int kk = K - 32;   // 1..32
+                        NX = kk < 32 ? (u32)(((s[1] << (2 * kk)) | (s[2] >> (64 - 2 * kk))) >> 32) : (u32)(s[2] >> 32);
+                    }
+                    // Exts::rc of a one-base nibble 1 << b is 1 << (3 - b); the sequence-end nibbles are complemented once
+                    const u32 ln_c = exts_complement(ln) & 0xfu, rn_c = exts_complement(rn) & 0xfu;
                     for (; t < tend; t++) {
-                        u32 nb;  // base t+K (only meaningful when t < n-1)
-                        if constexpr (W == 1) nb = (u32)((nxt_word ? s[1] : s[0]) >> nxt_shift) & 3u;
-                        else nb = (u32)((nxt_word == 2 ? s[2] : s[1]) >> nxt_shift) & 3u;
-                        const u32 left = t == 0 ? ln : (1u << prev_first);
-                        const u32 right = t == n - 1 ? rn : (1u << nb);
-                        u32 e = left | (right << 4);
-                        Kmer<W> key = fwd;
-                        if (!a.stranded && !(fwd < rcv)) { key = rcv; e = exts_rc(e); }  // lib.rs:224-231, filter.rs:190-196
+                        const u32 nb = NX >> 30;   // base t+K (only meaningful when t < n-1)
+                        NX <<= 2;
+                        const u32 cf = PF >> 30;   // first base of this k-mer
+                        PF <<= 2;
+                        const bool first = t == 0, last = t == n - 1;
+                        const bool use_rc = !a.stranded && !(fwd < rcv);   // lib.rs:224-231 (equality -> flipped), filter.rs:190-196
+                        const u32 el = use_rc ? (last ? rn_c : (8u >> nb)) : (first ? ln : (1u << prev_first));
+                        const u32 er = use_rc ? (first ? ln_c : (8u >> prev_first)) : (last ? rn : (1u << nb));
+                        const u32 e = el | (er << 4);
+                        const Kmer<W> key = use_rc ? rcv : fwd;
                         const u32 h = Ops<W>::hash32(key);
                         if ((h & cmask) == cres) {
                             bool special;
@@ -1167,7 +1178,11 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                                 atomicOr(&s_sp_exts, e);
                             } else {
                                 const int slot = tab.find_or_insert(key, h, CAP);
-                                if (slot < 0) { s_overflow = 1; break; }
+                                if (slot < 0) {   // table full: stop everybody's claims (no flag polled in the loop), the bucket is split
+                                    atomicExch(&s_overflow, 1u);
+                                    atomicMax(&s_next, 0x40000000u);
+                                    break;
+                                }
                                 u32 v = *reinterpret_cast<volatile u32*>(vals + slot);
                                 if (e & ~v) atomicOr(vals + slot, e);
                                 if (small_bucket) {
@@ -1187,16 +1202,14 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                             }
                         }
                         // roll to the next k-mer of this record
-                        prev_first = (u32)(s[0] >> 62);
+                        prev_first = cf;
                         fwd = Ops<W>::ext_right(kp, fwd, nb);
                         rcv = Ops<W>::roll_rc(kp, rcv, nb);
-#pragma unroll
-                        for (int q2 = 0; q2 < RW - 1; q2++) s[q2] = (s[q2] << 2) | (s[q2 + 1] >> 62);
-                        s[RW - 1] <<= 2;
                     }
                     }
                 }
                 __syncthreads();
+                if (s_overflow) break;   // (uniform: every thread reads the flag after the barrier)
             }
             __syncthreads();
             if (s_overflow) {

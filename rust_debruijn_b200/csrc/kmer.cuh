@@ -108,8 +108,8 @@ struct Ops<1> {
     static HD u32 first_base(const KP& p, K x) { return (u32)(x.lo >> p.top_shift) & 3u; }
     static HD u32 last_base(const KP&, K x) { return (u32)x.lo & 3u; }
     static HD u32 hash32(K x) {  // cheap 32-bit mix for the shared-memory table (slot = high bits, class = low bits)
-        u32 h = (u32)x.lo * 0x9E3779B1u ^ ((u32)(x.lo >> 32) * 0x85EBCA6Bu + 0x7F4A7C15u);
-        h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+        u32 h = (u32)x.lo * 0x9E3779B1u + (u32)(x.lo >> 32) * 0x85EBCA6Bu;
+        h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
         return h;
     }
     static HD u64 mix(K x) {  // bijective 64-bit finaliser (slot selection in the HBM table)
@@ -141,9 +141,8 @@ struct Ops<2> {
     static HD u32 first_base(const KP& p, K x) { return (u32)(x.hi >> p.top_shift) & 3u; }
     static HD u32 last_base(const KP&, K x) { return (u32)x.lo & 3u; }
     static HD u32 hash32(K x) {
-        u32 h = (u32)x.lo * 0x9E3779B1u ^ ((u32)(x.lo >> 32) * 0x85EBCA6Bu + 0x7F4A7C15u);
-        h ^= (u32)x.hi * 0xC2B2AE35u ^ ((u32)(x.hi >> 32) * 0x27D4EB2Fu);
-        h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+        u32 h = (u32)x.lo * 0x9E3779B1u + (u32)(x.lo >> 32) * 0x85EBCA6Bu + (u32)x.hi * 0xC2B2AE35u + (u32)(x.hi >> 32) * 0x27D4EB2Fu;
+        h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
         return h;
     }
     static HD u64 mix(K x) {

@@ -460,16 +460,65 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     u32 lerr = 0;
     TRY(ms_link_error(c, &q, &lerr));
     tm.mark(st);   // 4
-    // every rank's records are final before anybody walks them
-    TRY(T->barrier());
-    // ---- discover the unitigs whose left end lies in this shard ----
-    DBuf<u64> pk_lo, pk_hi;
-    DBuf<u32> p_state, p_len;
-    const u64 cap = V ? V : 1;
-    TRY(pk_lo.alloc_pool(c, cap)); TRY(p_state.alloc_pool(c, cap)); TRY(p_len.alloc_pool(c, cap));
-    if (W == 2) TRY(pk_hi.alloc_pool(c, cap));
-    u64 n_paths = 0, n_cov = 0;
-    TRY(ms_discover_dev(c, k, peers, me, V, 1024u, pk_lo.p, pk_hi.p, p_state.p, p_len.p, cap, &n_paths, &n_cov));
+    // ---- discover + collect: walkers that never leave their rank; a walk that must continue elsewhere is shipped there ----
+    const uint4* rec = my_rec;
+    const u32 wib = ms_witem_bytes(), enb = ms_entry_bytes(), cib = ms_citem_bytes(k), pb = ms_path_bytes(k);
+    DBuf<u64> d_ends, cur, d_allc;
+    TRY(d_ends.alloc_pool(c, 1)); TRY(cur.alloc_pool(c, DBG_MAX_RANKS + 4)); TRY(d_allc.alloc_pool(c, (u64)P * P));
+    TRY(ms_count_ends_dev(c, rec, V, d_ends.p));
+    u64 n_ends = 0;
+    TRY(read_u64(c, d_ends.p, &n_ends));
+    // capacities: a link side is crossed at most once per direction, so rank d receives at most (my link sides pointing at d)
+    // walkers from me, plus one notice per walker d ever sent me
+    u64 ocap[DBG_MAX_RANKS + 1], ooff[DBG_MAX_RANKS + 1], icap = 0, otot = 0;
+    for (int r = 0; r < P; r++) { ocap[r] = q.n_dst[r] + M[(u64)r * P + me] + 32; ooff[r] = otot; otot += ocap[r]; icap += q.n_dst[r] + M[(u64)r * P + me] + 32; }
+    const u64 ecap = n_ends + 32;
+    DBuf<unsigned char> obox, ibox, entries, nmsg;
+    TRY(obox.alloc_pool(c, otot * (u64)std::max(wib, cib))); TRY(ibox.alloc_pool(c, icap * (u64)std::max(wib, cib)));
+    TRY(entries.alloc_pool(c, ecap * enb)); TRY(nmsg.alloc_pool(c, ecap * pb));
+    u64 n_paths = 0, n_cov = 0, n_done = 0;
+    std::vector<u64> allc((u64)P * P);
+    auto run_rounds = [&](bool collect) -> int {
+        // per-destination outboxes (item size isz), the rank's own list (emit entries / finished nodes) as destination P
+        const u32 isz = collect ? cib : wib;
+        WalkOut wo;
+        for (int r = 0; r < P; r++) { wo.box[r] = obox.p + ooff[r] * isz; wo.cap[r] = ocap[r]; }
+        for (int r = P; r <= DBG_MAX_RANKS; r++) { wo.box[r] = nullptr; wo.cap[r] = 0; }
+        wo.box[P] = collect ? nmsg.p : entries.p; wo.cap[P] = ecap;
+        wo.cursor = cur.p; wo.P = P;
+        CU(c, cudaMemsetAsync(cur.p, 0, 8 * (DBG_MAX_RANKS + 4), st));
+        u64 n_in = 0;
+        for (int round = 0; round < 4096; round++) {
+            if (round == 0) {
+                if (collect) TRY(ms_collect_start_dev(c, k, rec, my_klo, my_khi, me, entries.p, n_paths, reduce_op, wo));
+                else TRY(ms_walk_start_dev(c, k, rec, my_klo, my_khi, me, V, 1024u, wo));
+            } else {
+                if (collect) TRY(ms_collect_continue_dev(c, k, rec, me, ibox.p, n_in, reduce_op, wo));
+                else TRY(ms_walk_continue_dev(c, k, rec, my_klo, my_khi, me, ibox.p, n_in, 1024u, wo));
+            }
+            // everybody learns everybody's outbox counts: the same matrix on every rank decides when the rounds end
+            TRY(T->all_gather(cur.p, d_allc.p, 8ull * P));
+            u64 own[3];
+            CU(c, cudaMemcpyAsync(allc.data(), d_allc.p, 8ull * P * P, cudaMemcpyDeviceToHost, st));
+            TRY(read_u64(c, cur.p + P, own, 3));
+            if (own[2]) DBG_SET_ERR(c, DBG_E_INTERNAL, "walker buffer overflow");
+            u64 inflight = 0;
+            for (u64 i = 0; i < (u64)P * P; i++) inflight += allc[i];
+            if (collect) n_done = own[0]; else { n_paths = own[0]; n_cov = own[1]; }
+            if (!inflight) return DBG_OK;
+            u64 s_o[DBG_MAX_RANKS], s_c[DBG_MAX_RANKS], r_o[DBG_MAX_RANKS], r_c[DBG_MAX_RANKS];
+            n_in = 0;
+            for (int r = 0; r < P; r++) {
+                s_o[r] = ooff[r] * isz; s_c[r] = allc[(u64)me * P + r] * isz;
+                r_o[r] = n_in * isz; r_c[r] = allc[(u64)r * P + me] * isz; n_in += allc[(u64)r * P + me];
+            }
+            if (n_in > icap) DBG_SET_ERR(c, DBG_E_INTERNAL, "walker inbox overflow");
+            TRY(T->all_to_all_v(obox.p, s_o, s_c, ibox.p, r_o, r_c));
+            CU(c, cudaMemsetAsync(cur.p, 0, 8 * P, st));   // the outboxes are empty again; the own list and its counters carry on
+        }
+        DBG_SET_ERR(c, DBG_E_INTERNAL, "walker rounds did not terminate");
+    };
+    TRY(run_rounds(false));
     u64 red[5] = {V, n_cov, n_paths, lerr == 1 ? 1ull : 0ull, lerr == 2 ? 1ull : 0ull};
     TRY(T->all_reduce_host(red, 5));
     I.n_valid_total = red[0];
@@ -492,7 +541,16 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
         *out = g;
         return DBG_OK;
     }
-    // ---- path records -> the rank owning their seed's key range (quantile cuts of the all-reduced seed histogram) ----
+    // ---- walk 2: the nodes themselves (finished where their right end lives) ----
+    TRY(run_rounds(true));
+    obox.release(); ibox.release();
+    n_paths = n_done;   // from here on: the finished nodes held by this rank
+    DBuf<u64> pk_lo, pk_hi;
+    DBuf<u32> pk_idx;
+    TRY(pk_lo.alloc_pool(c, n_paths ? n_paths : 1)); TRY(pk_idx.alloc_pool(c, n_paths ? n_paths : 1));
+    if (W == 2) TRY(pk_hi.alloc_pool(c, n_paths ? n_paths : 1));
+    TRY(ms_unpack_nodes_dev(c, k, nmsg.p, n_paths, pk_lo.p, pk_hi.p, pk_idx.p));
+    // ---- finished nodes -> the rank owning their seed's key range (quantile cuts of the all-reduced seed histogram) ----
     const int hb = std::min(16, 2 * k);
     const u64 nbins = 1ull << hb;
     DBuf<u32> d_hist, d_ghist;
@@ -515,10 +573,10 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
             pbound[r] = acc;
         }
     }
-    const u32 pb = ms_path_bytes(k);
     DBuf<unsigned char> pmsg_out, pmsg_in;
     TRY(pmsg_out.alloc_pool(c, (n_paths ? n_paths : 1) * pb));
-    TRY(ms_scatter_paths_dev(c, k, pk_lo.p, pk_hi.p, p_state.p, p_len.p, n_paths, me, P, hb, cuts, pbound, pmsg_out.p));
+    TRY(ms_scatter_nodes_dev(c, k, nmsg.p, n_paths, P, hb, cuts, pbound, pmsg_out.p));
+    nmsg.release();
     u64 psend[DBG_MAX_RANKS];
     for (int r = 0; r < P; r++) psend[r] = pbound[r + 1] - pbound[r];
     std::vector<u64> PM((u64)P * P);
@@ -534,7 +592,7 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     TRY(nk_lo.alloc_pool(c, mcap)); TRY(nk_lo_b.alloc_pool(c, mcap)); TRY(ni_a.alloc_pool(c, mcap)); TRY(ni_b.alloc_pool(c, mcap));
     if (W == 2) { TRY(nk_hi.alloc_pool(c, mcap)); TRY(nk_hi_b.alloc_pool(c, mcap)); }
     TRY(node_len.alloc_pool(c, mcap)); TRY(node_start.alloc_pool(c, mcap)); TRY(olen.alloc_pool(c, mcap)); TRY(d_tot.alloc_pool(c, 1));
-    TRY(ms_unpack_paths_dev(c, k, pmsg_in.p, m_own, nk_lo.p, nk_hi.p, ni_a.p));
+    TRY(ms_unpack_nodes_dev(c, k, pmsg_in.p, m_own, nk_lo.p, nk_hi.p, ni_a.p));
     u64 *sk_lo = nk_lo.p, *sk_hi = nk_hi.p;
     u32* sidx = ni_a.p;
     TRY(radix_sort_pairs(c, W, 2 * k, m_own, nk_lo.p, nk_hi.p, ni_a.p, nk_lo_b.p, nk_hi_b.p, ni_b.p, &sk_lo, &sk_hi, &sidx));

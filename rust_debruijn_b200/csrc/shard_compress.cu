@@ -22,9 +22,13 @@
 //   layout    path records go to the rank owning their seed's key range (quantile cuts of an all-reduced histogram,
 //             one CTA-aggregated scatter by destination): that rank sorts them and holds a contiguous run of nodes of
 //             the final order.
-//   emit      one thread per node re-walks its chain (peer loads again) and writes the node's bases / Exts / data.
+//   emit      the left-end walker of discover already collected the node (bases, Exts, data) into its message, so the
+//             owner of the key range only copies bits into the bit-contiguous PackedDnaStringSet words; nodes too long for
+//             a message are re-walked there through the peer windows.
 // Only unitigs reachable by end walks (<= lmax k-mers) are handled here; the caller falls back to gathering the table
 // and running the single-GPU compression when long unitigs or cycles are present.
+#include <algorithm>
+
 #include "common.cuh"
 #include "lookup.cuh"
 
@@ -33,10 +37,16 @@ namespace dbg {
 template <int W> struct QMsg;
 template <> struct __align__(16) QMsg<1> { u64 lo; u32 inc; u32 pad; };
 template <> struct __align__(16) QMsg<2> { u64 lo, hi; u32 inc; u32 pad0; u64 pad1; };
-// path record shipped to the rank owning the seed's key range: seed k-mer, left end (port state on rank len_rank >> 16), length
-template <int W> struct PathMsg;
-template <> struct __align__(16) PathMsg<1> { u64 lo; u32 state; u32 len_rank; };
-template <> struct __align__(16) PathMsg<2> { u64 lo, hi; u32 state; u32 len_rank; u64 pad; };
+// A finished node, shipped to the rank owning its seed's key range: seed k-mer, length, Exts, data and the node's BASES
+// (left-aligned 2-bit words), collected by the walker at the node's left end — where most of the unitig is local — so the
+// owner of the key range only copies bits.  Nodes longer than 32 * NBW bases carry their left end instead (flag LONG:
+// b[0] = port state, aux >> 16 = rank) and are re-walked by the owner through the peer windows.
+// meta = length in k-mers | Exts << 16 | flags << 24;  aux = data | rank << 16
+static const u32 NODE_LONG = 1u;
+template <int W> struct NodeMsg;
+template <> struct __align__(16) NodeMsg<1> { u64 lo; u32 meta; u32 aux; u64 b[6]; };          // 64 bytes, <= 192 bases
+template <> struct __align__(16) NodeMsg<2> { u64 lo, hi; u32 meta; u32 aux; u64 b[9]; };      // 96 bytes, <= 288 bases
+template <int W> struct NodeCfg { static const int NBW = W == 1 ? 6 : 9; };
 template <int W> __device__ __forceinline__ Kmer<W> qkey(const QMsg<W>& m) {
     if constexpr (W == 1) return Kmer<1>{m.lo}; else return Kmer<2>{m.lo, m.hi};
 }
@@ -219,92 +229,345 @@ __global__ void ms_apply_kernel(KP kp, const u64* __restrict__ lo, const u64* __
     }
 }
 
-// ---- discover: path ends walk across the peer-mapped records ----
-// Running minimum of the walk = (rank, index): on the same rank the smaller index is the smaller k-mer (shards are
-// ascending); k-mers are fetched and compared only when the walk reaches a k-mer of another rank than the candidate's.
-template <int W>
-__global__ void __launch_bounds__(256) ms_discover_kernel(RecPeers peers, int me, u64 n, u32 lmax, u64* __restrict__ pk_lo,
-                                                           u64* __restrict__ pk_hi, u32* __restrict__ p_state, u32* __restrict__ p_len,
-                                                           u64 cap, u64* __restrict__ counters /* [0] paths, [1] k-mers covered */) {
-    const u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    bool emit = false;
-    Kmer<W> seed = Ops<W>::zero();
-    u32 len = 0, left_state = 0;
-    if (v < n) {
-        const uint4 a0 = peers.rec[me][v];
-        if (a0.x == NIL && a0.y == NIL) {
-            emit = true; seed = peer_key<W>(peers, (u32)me, (u32)v); len = 1; left_state = 2u * (u32)v + 1u;   // stored orientation: heading right = leaving through R
-        } else if (a0.x == NIL || a0.y == NIL) {
-            const u32 d = a0.x == NIL ? 1u : 0u;   // the linked side: walk inwards through it
-            u32 cnt = 1;
-            u32 c_rank = (u32)me, c_idx = (u32)v, c_side = d;   // candidate seed: where, and through which side the walk leaves it
-            bool c_known = false;
-            Kmer<W> c_key = Ops<W>::zero();
-            u32 t = d ? a0.y : a0.x;
-            u32 trank = (a0.w >> (8 * d)) & 0xffu;
-            while (t != NIL && cnt <= lmax) {
-                const u32 idx = t >> 1, side = t & 1u;
-                const uint4 a = peers.rec[trank][idx];
-                cnt++;
-                if (trank == c_rank) {
-                    if (idx < c_idx) { c_idx = idx; c_side = side; c_known = false; }
-                } else {
-                    if (!c_known) { c_key = peer_key<W>(peers, c_rank, c_idx); c_known = true; }
-                    const Kmer<W> k2 = peer_key<W>(peers, trank, idx);
-                    if (k2 < c_key) { c_key = k2; c_rank = trank; c_idx = idx; c_side = side; }
-                }
-                t = side ? a.y : a.x;
-                trank = (a.w >> (8 * side)) & 0xffu;
-            }
-            if (t == NIL && c_side == 1u) {
-                emit = true; len = cnt; left_state = 2u * (u32)v + d;
-                seed = c_known ? c_key : peer_key<W>(peers, c_rank, c_idx);
-            }
-        }
-    }
-    __shared__ u32 s_wcnt[8], s_wcov[8];
-    __shared__ u64 s_base;
-    const int warp = threadIdx.x >> 5;
-    const u32 m = __ballot_sync(0xffffffffu, emit);
-    u32 cov = emit ? len : 0;
-    for (int o = 16; o; o >>= 1) cov += __shfl_xor_sync(0xffffffffu, cov, o);
-    if (lane == 0) { s_wcnt[warp] = __popc(m); s_wcov[warp] = cov; }
+// ---- discover + collect by WALKER HAND-OFF ------------------------------------------------------------------------
+// Fine-grained loads from another GPU's memory are ruinously slow (measured: a discover kernel that followed links
+// through peer-mapped records took 9 ms on 2 GPUs and 412 ms on 8, against 1.7 ms on one), so a walk never leaves its
+// rank: when the next k-mer lives elsewhere the WALKER is shipped there — a 32-byte item in a per-destination outbox,
+// exchanged in bulk once per round (all-to-all) — and continues on the records of the rank that owns them.
+//   walk 1  every path end walks inwards tracking the smallest k-mer (index order = k-mer order inside a shard; k-mers are
+//           compared only at a rank change) and the side through which the walk leaves it.  The walker that reaches the
+//           far end and left the seed "through R" started at the node's LEFT end (compression.rs:574-583, ascending seed
+//           order): the left end's rank gets an emit entry (left end, seed k-mer, length) — directly or by a notice item.
+//   walk 2  every emit entry walks the node once more from its left end and collects it: bases (left-aligned words in
+//           registers), end Exts (compression.rs:513-517,534-540), reduced data (:500-511); at a rank change the partial
+//           node travels on as an 80/112-byte item.  The rank where the walk ends holds the finished NodeMsg.
+// Every walker emits at most ONE thing, so outputs are appended with one reservation per (CTA, destination).
+static const u32 IT_WALK = 0, IT_NOTICE = 1;
+// info = origin rank | side through which the walk leaves the current minimum << 8 | kind << 9
+struct __align__(16) WItem { u64 lo, hi; u32 port, cnt, origin_port, info; };                       // 32 bytes
+template <int W> struct __align__(16) CItem { NodeMsg<W> node; u32 port, done; u64 acc; };          // 80 / 112 bytes
+struct __align__(16) EmitEntry { u64 lo, hi; u32 port, len; u64 pad; };   // 32 bytes: left end (port state on this rank), seed k-mer, length
+
+template <typename T>
+__device__ __forceinline__ void walk_append(const WalkOut& o, int dest, bool have, const T& item, u32 covered) {
+    __shared__ u32 s_cnt[DBG_MAX_RANKS + 1], s_cov;
+    __shared__ u64 s_base[DBG_MAX_RANKS + 1];
+    if (threadIdx.x <= DBG_MAX_RANKS) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_cov = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        u32 tc = 0, tv = 0;
-        for (int w = 0; w < 8; w++) { u32 x = s_wcnt[w]; s_wcnt[w] = tc; tc += x; tv += s_wcov[w]; }
-        s_base = tc ? atomicAdd(&counters[0], (u64)tc) : 0;
-        if (tv) atomicAdd(&counters[1], (u64)tv);
-    }
+    u32 loc = 0;
+    if (have) { loc = atomicAdd(&s_cnt[dest], 1u); if (covered) atomicAdd(&s_cov, covered); }
     __syncthreads();
-    if (emit) {
-        const u64 pos = s_base + s_wcnt[warp] + __popc(m & ((1u << lane) - 1));
-        if (pos < cap) {
-            pk_lo[pos] = seed.lo;
-            if constexpr (W == 2) pk_hi[pos] = seed.hi;
-            p_state[pos] = left_state;
-            p_len[pos] = len;
-        }
+    if (threadIdx.x <= DBG_MAX_RANKS && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&o.cursor[threadIdx.x], (u64)s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0 && s_cov) atomicAdd(&o.cursor[o.P + 1], (u64)s_cov);
+    __syncthreads();
+    if (have) {
+        const u64 pos = s_base[dest] + loc;
+        if (pos < o.cap[dest]) reinterpret_cast<T*>(o.box[dest])[pos] = item;
+        else o.cursor[o.P + 2] = 1;
     }
 }
 
-// path records (any order) -> messages grouped by the rank owning the seed's key range: destination = range of the seed's
-// top-bits bin among the quantile cuts; one reservation per (CTA, destination)
+// local part of walk 1: from port state `t` (at k-mer t >> 1 of THIS rank, about to be counted) onwards while the links
+// stay on this rank.  Returns the state the walk stops at: NIL (path end) or a port on rank `trank`.
+struct LocalMin { u32 idx, side; bool any; };
+__device__ __forceinline__ u32 walk_local(const uint4* __restrict__ rec, int me, u32 t, u32& trank, u32& cnt, u32 lmax, LocalMin& lm) {
+    while (t != NIL && trank == (u32)me && cnt <= lmax) {
+        const u32 idx = t >> 1, side = t & 1u;
+        const uint4 a = rec[idx];
+        cnt++;
+        if (!lm.any || idx < lm.idx) { lm.idx = idx; lm.side = side; lm.any = true; }
+        t = side ? a.y : a.x;
+        trank = (a.w >> (8 * side)) & 0xffu;
+    }
+    return t;
+}
+
 template <int W>
-__global__ void __launch_bounds__(256) ms_scatter_paths_kernel(const u64* __restrict__ k_lo, const u64* __restrict__ k_hi,
-                                                                const u32* __restrict__ p_state, const u32* __restrict__ p_len, u64 m, int me,
-                                                                int P, int bin_shift, SegOff cuts /* bins */, SegOff seg /* message offsets */,
-                                                                u64* __restrict__ seg_fill, PathMsg<W>* __restrict__ out) {
+__device__ __forceinline__ Kmer<W> local_key(const u64* __restrict__ klo, const u64* __restrict__ khi, u32 idx) {
+    if constexpr (W == 1) return Kmer<1>{klo[idx]}; else return Kmer<2>{klo[idx], khi[idx]};
+}
+
+// walk 1, round 0: thread per k-mer of the shard
+template <int W>
+__global__ void __launch_bounds__(256) ms_walk_start_kernel(const uint4* __restrict__ rec, const u64* __restrict__ klo, const u64* __restrict__ khi,
+                                                             int me, u64 n, u32 lmax, WalkOut out) {
+    const u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool have = false, is_entry = false;
+    int dest = 0;
+    u32 covered = 0;
+    WItem it;
+    EmitEntry en;
+    it.lo = it.hi = 0; it.port = it.cnt = it.origin_port = it.info = 0;
+    en.lo = en.hi = 0; en.port = en.len = 0; en.pad = 0;
+    if (v < n) {
+        const uint4 a0 = rec[v];
+        if (a0.x == NIL && a0.y == NIL) {
+            const Kmer<W> key = local_key<W>(klo, khi, (u32)v);
+            have = is_entry = true; dest = out.P; covered = 1;
+            en.lo = key.lo; if constexpr (W == 2) en.hi = key.hi;
+            en.port = 2u * (u32)v + 1u; en.len = 1;   // stored orientation: heading right = leaving through R
+        } else if (a0.x == NIL || a0.y == NIL) {
+            const u32 d = a0.x == NIL ? 1u : 0u;   // the linked side: walk inwards through it
+            u32 cnt = 1;
+            LocalMin lm{(u32)v, d, true};
+            u32 t = d ? a0.y : a0.x;
+            u32 trank = (a0.w >> (8 * d)) & 0xffu;
+            t = walk_local(rec, me, t, trank, cnt, lmax, lm);
+            if (cnt <= lmax) {
+                const Kmer<W> key = local_key<W>(klo, khi, lm.idx);
+                if (t == NIL) {
+                    if (lm.side == 1u) {   // the whole path is local and this end is its left end
+                        have = is_entry = true; dest = out.P; covered = cnt;
+                        en.lo = key.lo; if constexpr (W == 2) en.hi = key.hi;
+                        en.port = 2u * (u32)v + d; en.len = cnt;
+                    }
+                } else {
+                    have = true; dest = (int)trank;
+                    it.lo = key.lo; if constexpr (W == 2) it.hi = key.hi;
+                    it.port = t; it.cnt = cnt; it.origin_port = 2u * (u32)v + d;
+                    it.info = (u32)me | (lm.side << 8) | (IT_WALK << 9);
+                }
+            }
+        }
+    }
+    // (both item types are 32 bytes: one append serves the outboxes and the emit list)
+    if (is_entry) it = *reinterpret_cast<WItem*>(&en);
+    walk_append<WItem>(out, dest, have, it, covered);
+}
+
+// walk 1, later rounds: thread per received item
+template <int W>
+__global__ void __launch_bounds__(256) ms_walk_continue_kernel(const uint4* __restrict__ rec, const u64* __restrict__ klo, const u64* __restrict__ khi,
+                                                                int me, const WItem* __restrict__ inbox, u64 n_in, u32 lmax, WalkOut out) {
+    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool have = false;
+    int dest = 0;
+    u32 covered = 0;
+    WItem it;
+    it.lo = it.hi = 0; it.port = it.cnt = it.origin_port = it.info = 0;
+    if (q < n_in) {
+        it = inbox[q];
+        const u32 kind = (it.info >> 9) & 1u;
+        if (kind == IT_NOTICE) {   // "your port origin_port is the left end of a node": becomes an emit entry here
+            EmitEntry en;
+            en.lo = it.lo; en.hi = it.hi; en.port = it.origin_port; en.len = it.cnt; en.pad = 0;
+            have = true; dest = out.P; covered = it.cnt;
+            it = *reinterpret_cast<WItem*>(&en);
+        } else {
+            u32 cnt = it.cnt, trank = (u32)me;
+            LocalMin lm{0, 0, false};
+            u32 t = walk_local(rec, me, it.port, trank, cnt, lmax, lm);
+            if (cnt <= lmax) {
+                Kmer<W> ckey;
+                if constexpr (W == 1) ckey = Kmer<1>{it.lo}; else ckey = Kmer<2>{it.lo, it.hi};
+                u32 cside = (it.info >> 8) & 1u;
+                const Kmer<W> lk = local_key<W>(klo, khi, lm.idx);   // lm.any: the item's port is a k-mer of this rank
+                if (lk < ckey) { ckey = lk; cside = lm.side; }
+                it.lo = ckey.lo; if constexpr (W == 2) it.hi = ckey.hi;
+                it.cnt = cnt;
+                const u32 origin = it.info & 0xffu;
+                if (t == NIL) {
+                    if (cside == 1u) {   // the walker started at the node's left end
+                        have = true; covered = 0;
+                        if (origin == (u32)me) {
+                            EmitEntry en;
+                            en.lo = it.lo; en.hi = it.hi; en.port = it.origin_port; en.len = cnt; en.pad = 0;
+                            dest = out.P; covered = cnt;
+                            it = *reinterpret_cast<WItem*>(&en);
+                        } else {
+                            dest = (int)origin;
+                            it.info = origin | (1u << 8) | (IT_NOTICE << 9);
+                        }
+                    }
+                } else {
+                    have = true; dest = (int)trank;
+                    it.port = t;
+                    it.info = origin | (cside << 8) | (IT_WALK << 9);
+                }
+            }
+        }
+    }
+    walk_append<WItem>(out, dest, have, it, covered);
+}
+
+// ---- walk 2: collect the node ----
+template <int W>
+struct Collector {
+    static constexpr int NBW = NodeCfg<W>::NBW;
+    u64 bw[NBW];
+    u64 acc;
+    u32 eb;      // Exts of the node: left nibble set at the first k-mer, right nibble at the last
+    u32 done;    // k-mers collected so far
+    // k-mer at port state `cur` (leaving side = cur & 1) of this rank; j = its position in the node
+    __device__ __forceinline__ void first(const KP& kp, const uint4& r, Kmer<W> key, u32 cur, u32 len) {
+        const int K = kp.k;
+        const u32 dw = cur & 1u;
+        const bool fw = dw == 1u;    // leaving through R while heading right = stored orientation
+        if (!fw) key = Ops<W>::rc(kp, key);
+        if constexpr (W == 1) {
+            bw[0] = key.lo << (64 - 2 * K);
+        } else {
+            const int sh = 128 - 2 * K;   // 0..62
+            bw[0] = sh ? (key.hi << sh) | (key.lo >> (64 - sh)) : key.hi;
+            bw[1] = key.lo << sh;
+        }
+        const u32 e = (r.z >> 16) & 0xffu;
+        u32 nib = exts_side(e, (int)(dw ^ 1u));          // left-facing side of the first k-mer (:513-517)
+        if (!fw) nib = exts_complement(nib) & 0xfu;
+        eb = nib;
+        if (len == 1) {
+            u32 rn = exts_side(e, (int)dw);
+            if (!fw) rn = exts_complement(rn) & 0xfu;
+            eb |= rn << 4;
+        }
+        acc = r.z & 0xffffu;
+        done = 1;
+    }
+    __device__ __forceinline__ void next(const KP& kp, const uint4& r, u32 cur, u32 len, int reduce_op) {
+        const u32 dw = cur & 1u;
+        const bool fw = dw == 1u;
+        const u32 fb = (r.z >> 24) & 3u, lb = (r.z >> 26) & 3u;
+        const u64 bb = fw ? lb : 3u - fb;                // last base of the k-mer as it appears in the node
+        const u32 pos = (u32)kp.k + done - 1;
+        const u64 x = bb << (62 - 2 * (pos & 31));
+#pragma unroll
+        for (int w = 0; w < NBW; w++) if (w == (int)(pos >> 5)) bw[w] |= x;
+        const u64 cnt2 = r.z & 0xffffu;
+        if (reduce_op >= DBG_REDUCE_MAX) acc = cnt2 > acc ? cnt2 : acc; else acc += cnt2;   // SCMAP: all equal, max == the value
+        if (done == len - 1) {
+            u32 rn = exts_side((r.z >> 16) & 0xffu, (int)dw);   // right-facing side of the last k-mer (:534-540)
+            if (!fw) rn = exts_complement(rn) & 0xfu;
+            eb |= rn << 4;
+        }
+        done++;
+    }
+    __device__ __forceinline__ u32 data16(u32 len, int reduce_op) const {
+        switch (reduce_op) {
+            case DBG_REDUCE_SAT_ADD: return (u32)(acc > 65535 ? 65535 : acc);
+            case DBG_REDUCE_WRAP_ADD: return (u32)(acc & 0xffff);
+            case DBG_REDUCE_ADD_MOD_65535: return len == 1 ? (u32)acc : (u32)(acc % 65535);   // one k-mer: reduce() never called (:495)
+            default: return (u32)acc;
+        }
+    }
+};
+
+// common tail of the two collect kernels: walk on while the links are local, then finish the node or hand it off
+template <int W>
+__device__ __forceinline__ void collect_run(const KP& kp, const uint4* __restrict__ rec, int me, Collector<W>& col, u32 cur, u32 crank, u32 len,
+                                            int reduce_op, Kmer<W> seed, bool active, WalkOut out) {
+    constexpr int NBW = NodeCfg<W>::NBW;
+    if (active) {
+        while (col.done < len && crank == (u32)me && cur != NIL) {
+            const uint4 r = rec[cur >> 1];
+            col.next(kp, r, cur, len, reduce_op);
+            const u32 dw = cur & 1u;
+            cur = dw ? r.y : r.x;
+            crank = (r.w >> (8 * dw)) & 0xffu;
+        }
+    }
+    CItem<W> ci;
+    ci.node.lo = seed.lo;
+    if constexpr (W == 2) ci.node.hi = seed.hi;
+#pragma unroll
+    for (int w = 0; w < NBW; w++) ci.node.b[w] = col.bw[w];
+    ci.port = cur; ci.done = col.done; ci.acc = col.acc;
+    const bool finished = active && col.done >= len;
+    ci.node.meta = len | (col.eb << 16);
+    ci.node.aux = finished ? (col.data16(len, reduce_op) | ((u32)me << 16)) : 0u;
+    // finished nodes go to the rank's own list as plain NodeMsg, unfinished ones travel on as CItem
+    __shared__ u32 s_cnt[DBG_MAX_RANKS + 1];
+    __shared__ u64 s_base[DBG_MAX_RANKS + 1];
+    if (threadIdx.x <= DBG_MAX_RANKS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int dest = finished ? out.P : (int)crank;
+    u32 loc = 0;
+    if (active) loc = atomicAdd(&s_cnt[dest], 1u);
+    __syncthreads();
+    if (threadIdx.x <= DBG_MAX_RANKS && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&out.cursor[threadIdx.x], (u64)s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (active) {
+        const u64 pos = s_base[dest] + loc;
+        if (pos >= out.cap[dest]) out.cursor[out.P + 2] = 1;
+        else if (finished) reinterpret_cast<NodeMsg<W>*>(out.box[dest])[pos] = ci.node;
+        else reinterpret_cast<CItem<W>*>(out.box[dest])[pos] = ci;
+    }
+}
+
+// walk 2, round 0: thread per emit entry (a node whose left end is a k-mer of this rank)
+template <int W>
+__global__ void __launch_bounds__(256) ms_collect_start_kernel(KP kp, const uint4* __restrict__ rec, const u64* __restrict__ klo, const u64* __restrict__ khi,
+                                                                int me, const EmitEntry* __restrict__ entries, u64 n, int reduce_op, WalkOut out) {
+    constexpr int NBW = NodeCfg<W>::NBW;
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    Collector<W> col;
+#pragma unroll
+    for (int w = 0; w < NBW; w++) col.bw[w] = 0;
+    col.acc = 0; col.eb = 0; col.done = 0;
+    u32 cur = 0, crank = (u32)me, len = 1;
+    Kmer<W> seed = Ops<W>::zero();
+    const bool active = i < n;
+    if (active) {
+        const EmitEntry en = entries[i];
+        if constexpr (W == 1) seed = Kmer<1>{en.lo}; else seed = Kmer<2>{en.lo, en.hi};
+        len = en.len;
+        cur = en.port;
+        if ((u64)len + kp.k - 1 > 32ull * NBW) {
+            // too long for a message: the owner of the key range re-walks it through the peer windows (flag LONG)
+            col.bw[0] = cur; col.done = len; col.eb = NODE_LONG << 8;   // eb << 16 lands the flag in meta bits 24..
+        } else {
+            const uint4 r = rec[cur >> 1];
+            col.first(kp, r, local_key<W>(klo, khi, cur >> 1), cur, len);
+            const u32 dw = cur & 1u;
+            cur = dw ? r.y : r.x;
+            crank = (r.w >> (8 * dw)) & 0xffu;
+        }
+    }
+    collect_run<W>(kp, rec, me, col, cur, crank, len, reduce_op, seed, active, out);
+}
+
+// walk 2, later rounds: thread per received partial node
+template <int W>
+__global__ void __launch_bounds__(256) ms_collect_continue_kernel(KP kp, const uint4* __restrict__ rec, int me, const CItem<W>* __restrict__ inbox, u64 n,
+                                                                   int reduce_op, WalkOut out) {
+    constexpr int NBW = NodeCfg<W>::NBW;
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    Collector<W> col;
+#pragma unroll
+    for (int w = 0; w < NBW; w++) col.bw[w] = 0;
+    col.acc = 0; col.eb = 0; col.done = 0;
+    u32 cur = 0, len = 1;
+    Kmer<W> seed = Ops<W>::zero();
+    const bool active = i < n;
+    if (active) {
+        const CItem<W> ci = inbox[i];
+        if constexpr (W == 1) seed = Kmer<1>{ci.node.lo}; else seed = Kmer<2>{ci.node.lo, ci.node.hi};
+#pragma unroll
+        for (int w = 0; w < NBW; w++) col.bw[w] = ci.node.b[w];
+        col.acc = ci.acc; col.done = ci.done; col.eb = (ci.node.meta >> 16) & 0xffu;
+        len = ci.node.meta & 0xffffu;
+        cur = ci.port;
+    }
+    collect_run<W>(kp, rec, me, col, cur, (u32)me, len, reduce_op, seed, active, out);
+}
+
+// node messages (any order) -> grouped by the rank owning the seed's key range: destination = range of the seed's top-bits
+// bin among the quantile cuts; one reservation per (CTA, destination)
+template <int W>
+__global__ void __launch_bounds__(256) ms_scatter_nodes_kernel(const NodeMsg<W>* __restrict__ in, u64 m, int P, int bin_shift,
+                                                                SegOff cuts /* bins */, SegOff seg /* message offsets */,
+                                                                u64* __restrict__ seg_fill, NodeMsg<W>* __restrict__ out) {
     __shared__ u32 s_cnt[DBG_MAX_RANKS];
     __shared__ u64 s_base[DBG_MAX_RANKS];
     if (threadIdx.x < DBG_MAX_RANKS) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 dst = 0, loc = 0;
-    Kmer<W> key = Ops<W>::zero();
+    NodeMsg<W> r;
     if (i < m) {
-        if constexpr (W == 1) key = Kmer<1>{k_lo[i]}; else key = Kmer<2>{k_lo[i], k_hi[i]};
+        r = in[i];
+        Kmer<W> key;
+        if constexpr (W == 1) key = Kmer<1>{r.lo}; else key = Kmer<2>{r.lo, r.hi};
         const u32 bin = key_prefix<W>(key, bin_shift);
         while ((int)dst + 1 < P && (u64)bin >= cuts.off[dst + 1]) dst++;
         loc = atomicAdd(&s_cnt[dst], 1u);
@@ -312,17 +575,10 @@ __global__ void __launch_bounds__(256) ms_scatter_paths_kernel(const u64* __rest
     __syncthreads();
     if (threadIdx.x < DBG_MAX_RANKS && s_cnt[threadIdx.x]) s_base[threadIdx.x] = seg.off[threadIdx.x] + atomicAdd(&seg_fill[threadIdx.x], (u64)s_cnt[threadIdx.x]);
     __syncthreads();
-    if (i < m) {
-        PathMsg<W> r;
-        r.lo = key.lo;
-        if constexpr (W == 2) { r.hi = key.hi; r.pad = 0; }
-        r.state = p_state[i];
-        r.len_rank = p_len[i] | ((u32)me << 16);
-        out[s_base[dst] + loc] = r;
-    }
+    if (i < m) out[s_base[dst] + loc] = r;
 }
 template <int W>
-__global__ void ms_unpack_paths_kernel(const PathMsg<W>* __restrict__ in, u64 m, u64* __restrict__ k_lo, u64* __restrict__ k_hi, u32* __restrict__ idx) {
+__global__ void ms_unpack_nodes_kernel(const NodeMsg<W>* __restrict__ in, u64 m, u64* __restrict__ k_lo, u64* __restrict__ k_hi, u32* __restrict__ idx) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     k_lo[i] = in[i].lo;
@@ -330,10 +586,10 @@ __global__ void ms_unpack_paths_kernel(const PathMsg<W>* __restrict__ in, u64 m,
     idx[i] = (u32)i;
 }
 template <int W>
-__global__ void ms_node_len_kernel(const PathMsg<W>* __restrict__ in, const u32* __restrict__ idx, u64 m, int K, u64* __restrict__ node_len, u32* __restrict__ out_length) {
+__global__ void ms_node_len_kernel(const NodeMsg<W>* __restrict__ in, const u32* __restrict__ idx, u64 m, int K, u64* __restrict__ node_len, u32* __restrict__ out_length) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    const u64 l = (u64)(in[idx[i]].len_rank & 0xffffu) + K - 1;
+    const u64 l = (u64)(in[idx[i]].meta & 0xffffu) + K - 1;
     node_len[i] = l;
     out_length[i] = (u32)l;
 }
@@ -356,20 +612,37 @@ struct MsNodeWriter {   // same as the single-GPU NodeWriter: interior words are
 };
 
 template <int W>
-__global__ void ms_emit_kernel(KP kp, RecPeers peers, const PathMsg<W>* __restrict__ msgs, const u32* __restrict__ idx, const u64* __restrict__ node_start,
+__global__ void ms_emit_kernel(KP kp, RecPeers peers, const NodeMsg<W>* __restrict__ msgs, const u32* __restrict__ idx, const u64* __restrict__ node_start,
                                u64 m, int reduce_op, u64* __restrict__ words, u8* __restrict__ out_exts, u16* __restrict__ out_data) {
+    constexpr int NBW = NodeCfg<W>::NBW;
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const int K = kp.k;
-    const PathMsg<W> pm = msgs[idx[i]];
-    const u32 len = pm.len_rank & 0xffffu;
-    u32 rank = pm.len_rank >> 16;
-    u32 cur = pm.state;              // at the left end, leaving through its right-facing side
+    const NodeMsg<W> pm = msgs[idx[i]];
+    const u32 len = pm.meta & 0xffffu;
     const u64 st = node_start[i];
     const u64 L = (u64)len + K - 1;
     MsNodeWriter nw;
     nw.words = words; nw.first_w = st >> 5; nw.last_w = (st + L - 1) >> 5; nw.wi = nw.first_w; nw.cur = 0;
     u64 pos = st;
+    if (!((pm.meta >> 24) & NODE_LONG)) {
+        // the node arrived complete: PackedDnaStringSet::add (dna_string.rs:811-821) is a bit copy
+#pragma unroll
+        for (int w = 0; w < NBW; w++) {
+            if ((u64)32 * w < L) {
+                const int nb = (int)(L - 32 * w < 32 ? L - 32 * w : 32);
+                nw.push(pm.b[w], nb, pos);
+                pos += nb;
+            }
+        }
+        if (pos & 31) nw.flush();
+        out_exts[i] = (u8)(pm.meta >> 16);
+        out_data[i] = (u16)pm.aux;
+        return;
+    }
+    // long node: walk it from its left end through the peer windows
+    u32 rank = pm.aux >> 16;
+    u32 cur = (u32)pm.b[0];          // at the left end, leaving through its right-facing side
     u64 acc = 0;
     u32 eb = 0;
     {   // first k-mer: all K bases (compression.rs:489-495)
@@ -479,7 +752,7 @@ int ms_links_dev(Ctx* c, const Table* t, ShardCfg cfg, uint4* d_rec, u64* d_klo,
     return t->k <= 32 ? ms_links_impl<1>(c, t, cfg, d_rec, d_klo, d_khi, q) : ms_links_impl<2>(c, t, cfg, d_rec, d_klo, d_khi, q);
 }
 u32 ms_query_bytes(int k) { return k <= 32 ? (u32)sizeof(QMsg<1>) : (u32)sizeof(QMsg<2>); }
-u32 ms_path_bytes(int k) { return k <= 32 ? (u32)sizeof(PathMsg<1>) : (u32)sizeof(PathMsg<2>); }
+u32 ms_path_bytes(int k) { return k <= 32 ? (u32)sizeof(NodeMsg<1>) : (u32)sizeof(NodeMsg<2>); }
 
 int ms_resolve_dev(Ctx* c, const Table* t, const MsQueries* q, int stranded, const void* d_queries, u64 nq, uint2* d_reply) {
     if (!nq) return DBG_OK;
@@ -516,28 +789,63 @@ int ms_link_error(Ctx* c, const MsQueries* q, u32* code) {
     return DBG_OK;
 }
 
-int ms_discover_dev(Ctx* c, int k, const RecPeers& peers, int me, u64 n, u32 lmax, u64* pk_lo, u64* pk_hi, u32* p_state, u32* p_len,
-                    u64 cap, u64* n_paths, u64* n_covered) {
-    *n_paths = *n_covered = 0;
+__global__ void __launch_bounds__(256) ms_count_ends_kernel(const uint4* __restrict__ rec, u64 n, u64* __restrict__ out) {
+    __shared__ u32 s_w[8];
+    u32 c = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const uint4 a = rec[i];
+        c += (a.x == NIL || a.y == NIL) ? 1u : 0u;
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 t = 0;
+        for (int w = 0; w < 8; w++) t += s_w[w];
+        if (t) atomicAdd(out, t);
+    }
+}
+// number of path ends (k-mers with a free side) in the shard: bounds the emit entries and the finished nodes of this rank
+int ms_count_ends_dev(Ctx* c, const uint4* d_rec, u64 n, u64* d_out) {
+    CU(c, cudaMemsetAsync(d_out, 0, 8, c->stream));
     if (!n) return DBG_OK;
-    DBuf<u64> ctr;
-    TRY(ctr.alloc_pool(c, 2));
-    TRY(ctr.zero());
-    if (k <= 32) ms_discover_kernel<1><<<grid_for(n, 256), 256, 0, c->stream>>>(peers, me, n, lmax, pk_lo, pk_hi, p_state, p_len, cap, ctr.p);
-    else ms_discover_kernel<2><<<grid_for(n, 256), 256, 0, c->stream>>>(peers, me, n, lmax, pk_lo, pk_hi, p_state, p_len, cap, ctr.p);
-    TRY(check_launch(c, "ms_discover"));
-    u64 h[2];
-    TRY(read_u64(c, ctr.p, h, 2));
-    if (h[0] > cap) DBG_SET_ERR(c, DBG_E_INTERNAL, "path buffer too small");
-    *n_paths = h[0];
-    *n_covered = h[1];
-    return DBG_OK;
+    ms_count_ends_kernel<<<(u32)std::min<u64>(grid_for(n, 256), (u64)c->sm_count * 8), 256, 0, c->stream>>>(d_rec, n, d_out);
+    return check_launch(c, "ms_count_ends");
+}
+u32 ms_witem_bytes() { return (u32)sizeof(WItem); }
+u32 ms_entry_bytes() { return (u32)sizeof(EmitEntry); }
+u32 ms_citem_bytes(int k) { return k <= 32 ? (u32)sizeof(CItem<1>) : (u32)sizeof(CItem<2>); }
+
+int ms_walk_start_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, u64 n, u32 lmax, const WalkOut& out) {
+    if (!n) return DBG_OK;
+    if (k <= 32) ms_walk_start_kernel<1><<<grid_for(n, 256), 256, 0, c->stream>>>(rec, klo, khi, me, n, lmax, out);
+    else ms_walk_start_kernel<2><<<grid_for(n, 256), 256, 0, c->stream>>>(rec, klo, khi, me, n, lmax, out);
+    return check_launch(c, "ms_walk_start");
+}
+int ms_walk_continue_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, const void* inbox, u64 n_in, u32 lmax, const WalkOut& out) {
+    if (!n_in) return DBG_OK;
+    if (k <= 32) ms_walk_continue_kernel<1><<<grid_for(n_in, 256), 256, 0, c->stream>>>(rec, klo, khi, me, reinterpret_cast<const WItem*>(inbox), n_in, lmax, out);
+    else ms_walk_continue_kernel<2><<<grid_for(n_in, 256), 256, 0, c->stream>>>(rec, klo, khi, me, reinterpret_cast<const WItem*>(inbox), n_in, lmax, out);
+    return check_launch(c, "ms_walk_continue");
+}
+int ms_collect_start_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, const void* entries, u64 n, int reduce_op, const WalkOut& out) {
+    if (!n) return DBG_OK;
+    KP kp = make_kp(k);
+    if (k <= 32) ms_collect_start_kernel<1><<<grid_for(n, 256), 256, 0, c->stream>>>(kp, rec, klo, khi, me, reinterpret_cast<const EmitEntry*>(entries), n, reduce_op, out);
+    else ms_collect_start_kernel<2><<<grid_for(n, 256), 256, 0, c->stream>>>(kp, rec, klo, khi, me, reinterpret_cast<const EmitEntry*>(entries), n, reduce_op, out);
+    return check_launch(c, "ms_collect_start");
+}
+int ms_collect_continue_dev(Ctx* c, int k, const uint4* rec, int me, const void* inbox, u64 n, int reduce_op, const WalkOut& out) {
+    if (!n) return DBG_OK;
+    KP kp = make_kp(k);
+    if (k <= 32) ms_collect_continue_kernel<1><<<grid_for(n, 256), 256, 0, c->stream>>>(kp, rec, me, reinterpret_cast<const CItem<1>*>(inbox), n, reduce_op, out);
+    else ms_collect_continue_kernel<2><<<grid_for(n, 256), 256, 0, c->stream>>>(kp, rec, me, reinterpret_cast<const CItem<2>*>(inbox), n, reduce_op, out);
+    return check_launch(c, "ms_collect_continue");
 }
 
 // cuts: P + 1 bin indices over the top `bits` key bits; seg_off: P + 1 message offsets (prefix sums of the per-destination
 // counts the caller derived from the local histogram and the cuts)
-int ms_scatter_paths_dev(Ctx* c, int k, const u64* k_lo, const u64* k_hi, const u32* p_state, const u32* p_len, u64 m, int me, int P, int bits,
-                         const u64* cuts, const u64* seg_off, void* out) {
+int ms_scatter_nodes_dev(Ctx* c, int k, const void* nmsg, u64 m, int P, int bits, const u64* cuts, const u64* seg_off, void* out) {
     if (!m) return DBG_OK;
     SegOff cu, sg;
     for (int r = 0; r <= DBG_MAX_RANKS; r++) { cu.off[r] = cuts[r <= P ? r : P]; sg.off[r] = seg_off[r <= P ? r : P]; }
@@ -545,28 +853,28 @@ int ms_scatter_paths_dev(Ctx* c, int k, const u64* k_lo, const u64* k_hi, const 
     TRY(fill.alloc_pool(c, DBG_MAX_RANKS));
     TRY(fill.zero());
     const int shift = 2 * k - bits;
-    if (k <= 32) ms_scatter_paths_kernel<1><<<grid_for(m, 256), 256, 0, c->stream>>>(k_lo, k_hi, p_state, p_len, m, me, P, shift, cu, sg, fill.p, reinterpret_cast<PathMsg<1>*>(out));
-    else ms_scatter_paths_kernel<2><<<grid_for(m, 256), 256, 0, c->stream>>>(k_lo, k_hi, p_state, p_len, m, me, P, shift, cu, sg, fill.p, reinterpret_cast<PathMsg<2>*>(out));
-    return check_launch(c, "ms_scatter_paths");
+    if (k <= 32) ms_scatter_nodes_kernel<1><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const NodeMsg<1>*>(nmsg), m, P, shift, cu, sg, fill.p, reinterpret_cast<NodeMsg<1>*>(out));
+    else ms_scatter_nodes_kernel<2><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const NodeMsg<2>*>(nmsg), m, P, shift, cu, sg, fill.p, reinterpret_cast<NodeMsg<2>*>(out));
+    return check_launch(c, "ms_scatter_nodes");
 }
-int ms_unpack_paths_dev(Ctx* c, int k, const void* in, u64 m, u64* k_lo, u64* k_hi, u32* idx) {
+int ms_unpack_nodes_dev(Ctx* c, int k, const void* in, u64 m, u64* k_lo, u64* k_hi, u32* idx) {
     if (!m) return DBG_OK;
-    if (k <= 32) ms_unpack_paths_kernel<1><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const PathMsg<1>*>(in), m, k_lo, k_hi, idx);
-    else ms_unpack_paths_kernel<2><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const PathMsg<2>*>(in), m, k_lo, k_hi, idx);
-    return check_launch(c, "ms_unpack_paths");
+    if (k <= 32) ms_unpack_nodes_kernel<1><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const NodeMsg<1>*>(in), m, k_lo, k_hi, idx);
+    else ms_unpack_nodes_kernel<2><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const NodeMsg<2>*>(in), m, k_lo, k_hi, idx);
+    return check_launch(c, "ms_unpack_nodes");
 }
 int ms_node_len_dev(Ctx* c, int k, const void* msgs, const u32* idx, u64 m, u64* node_len, u32* out_length) {
     if (!m) return DBG_OK;
-    if (k <= 32) ms_node_len_kernel<1><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const PathMsg<1>*>(msgs), idx, m, k, node_len, out_length);
-    else ms_node_len_kernel<2><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const PathMsg<2>*>(msgs), idx, m, k, node_len, out_length);
+    if (k <= 32) ms_node_len_kernel<1><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const NodeMsg<1>*>(msgs), idx, m, k, node_len, out_length);
+    else ms_node_len_kernel<2><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const NodeMsg<2>*>(msgs), idx, m, k, node_len, out_length);
     return check_launch(c, "ms_node_len");
 }
 int ms_emit_dev(Ctx* c, int k, const RecPeers& peers, const void* msgs, const u32* idx, const u64* node_start, u64 m, int reduce_op,
                 u64* words, u8* out_exts, u16* out_data) {
     if (!m) return DBG_OK;
     KP kp = make_kp(k);
-    if (k <= 32) ms_emit_kernel<1><<<grid_for(m, 128), 128, 0, c->stream>>>(kp, peers, reinterpret_cast<const PathMsg<1>*>(msgs), idx, node_start, m, reduce_op, words, out_exts, out_data);
-    else ms_emit_kernel<2><<<grid_for(m, 128), 128, 0, c->stream>>>(kp, peers, reinterpret_cast<const PathMsg<2>*>(msgs), idx, node_start, m, reduce_op, words, out_exts, out_data);
+    if (k <= 32) ms_emit_kernel<1><<<grid_for(m, 128), 128, 0, c->stream>>>(kp, peers, reinterpret_cast<const NodeMsg<1>*>(msgs), idx, node_start, m, reduce_op, words, out_exts, out_data);
+    else ms_emit_kernel<2><<<grid_for(m, 128), 128, 0, c->stream>>>(kp, peers, reinterpret_cast<const NodeMsg<2>*>(msgs), idx, node_start, m, reduce_op, words, out_exts, out_data);
     return check_launch(c, "ms_emit");
 }
 
