@@ -36,7 +36,9 @@ MIN_OBS = 2
 ERR_THR_NOISY = 83886
 METRIC = "k-mers/sec filter_kmers+compress_kmers K=31 150bp reads"
 UNIT = "k-mers/s"
-CONFIGS = {"c2": dict(k=31, label="configs[1]"), "c3": dict(k=63, label="configs[2]")}
+CONFIGS = {"c2": dict(k=31, label="configs[1]"), "c3": dict(k=63, label="configs[2]"),
+           # configs[3]: 100M reads over 8 GPUs = 12.5M reads per rank (run with --gpus 8 under torchrun)
+           "c4": dict(k=31, label="configs[3]", reads=12_500_000)}
 
 
 def env_int(name, default):
@@ -187,7 +189,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="c2 = configs[1] (K=31), c3 = configs[2] (K=63)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
+                    help="c2 = configs[1] (K=31), c3 = configs[2] (K=63), c4 = configs[3] (K=31, 100M reads over 8 GPUs)")
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU (configs[1], configs[2]: 10M)")
     ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
     ap.add_argument("--ref-reads", type=int, default=1_000_000)
@@ -196,6 +199,8 @@ def main():
     ap.add_argument("--no-clocks", action="store_true", help="debug: do not sample clocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if "reads" in CONFIGS[args.config]:
+        args.reads = CONFIGS[args.config]["reads"]
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
