@@ -161,6 +161,10 @@ int dbg_graph_edges(dbg_ctx* ctx, const dbg_graph* graph, uint32_t* target, uint
  * extension only if find_link resolves it (and, with valid_nodes != NULL — host, one byte per node, the reference's BitSet —
  * only if the target node is marked).  "Remove non-existent extensions that may be created due to filtered kmers". */
 int dbg_graph_fix_exts(dbg_ctx* ctx, dbg_graph* graph, const uint8_t* valid_nodes);
+/* DebruijnGraph::is_compressed — src/graph.rs:296-334, the property the reference's tests assert after compress_kmers
+ * (src/test.rs:248-254, 266-274): *pair_out = -1 when no two nodes could be collapsed, else (node << 32) | next_node for the FIRST
+ * pair in the reference's iteration order.  scmap_join_test != 0: spec.join_test = data equality (ScmapCompress), else always true. */
+int dbg_graph_is_compressed(dbg_ctx* ctx, const dbg_graph* graph, int scmap_join_test, int64_t* pair_out);
 void dbg_graph_free(dbg_graph* g);
 
 /* ---- fused path: reads -> BaseGraph with the k-mer table kept device-resident ----------------------

@@ -326,6 +326,14 @@ class BaseGraph:
         self.ctx.check(self.ctx._L.dbg_graph_fix_exts(self.ctx._h, self._h, _ptr(valid_nodes)))
         self._host = None
 
+    def is_compressed(self, spec=None):
+        """DebruijnGraph::is_compressed (src/graph.rs:296-334) on the device: None if no two nodes could be collapsed, else the
+        first (node, next_node) pair in the reference's iteration order.  spec: SimpleCompress (join_test always true, the
+        default) or ScmapCompress (join_test = data equality)."""
+        pr = C.c_int64(-1)
+        self.ctx.check(self.ctx._L.dbg_graph_is_compressed(self.ctx._h, self._h, int(isinstance(spec, ScmapCompress)), C.byref(pr)))
+        return None if pr.value < 0 else (int(pr.value >> 32), int(pr.value & 0xffffffff))
+
     def write_gfa(self, out):
         """DebruijnGraph::write_gfa (src/graph.rs:538-614): header, one S line per node, L lines for the left edges with
         target >= node and the right edges with target > node (edge direction '+' = enters the target through its left

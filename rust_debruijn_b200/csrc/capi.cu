@@ -875,6 +875,16 @@ int dbg_graph_fix_exts(dbg_ctx* ctx, dbg_graph* graph, const uint8_t* valid_node
     return graph_fix_exts_dev(CTX(ctx), &graph->g, valid_nodes);
 }
 
+int dbg_graph_is_compressed(dbg_ctx* ctx, const dbg_graph* graph, int scmap_join_test, int64_t* pair_out) {
+    if (!ctx || !pair_out) return DBG_E_BADARG;
+    NULLCHK(ctx, graph);
+    cudaSetDevice(ctx->c.device);
+    long long pr = -1;
+    int rc = graph_is_compressed_dev(CTX(ctx), &graph->g, scmap_join_test, &pr);
+    *pair_out = (int64_t)pr;
+    return rc;
+}
+
 void dbg_graph_free(dbg_graph* g) { if (g) { cudaSetDevice(g->g.ctx->device); free_graph(&g->g); } }
 
 // ---- fused ------------------------------------------------------------------------------------------------

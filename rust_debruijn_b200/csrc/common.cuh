@@ -281,6 +281,7 @@ void free_partition(Partition* P);
 int cs_links_dev(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u32* d_nxt_out);
 int graph_edges_dev(Ctx* c, const Graph* g, u32* h_target, u8* h_flags);
 int graph_fix_exts_dev(Ctx* c, Graph* g, const u8* h_valid_nodes);
+int graph_is_compressed_dev(Ctx* c, const Graph* g, int scmap, long long* pair_out);
 int remove_censored_exts_dev(Ctx* c, Table* t, int stranded, int sharded);
 int table_prefix_hist_dev(Ctx* c, const Table* t, int bits, u32* d_hist);
 int cs_pack_dev(Ctx* c, const Table* t, const u32* d_nxt_full, uint4* d_rec16);

@@ -1007,11 +1007,41 @@ __global__ void fix_exts_kernel(const u32* __restrict__ target, const u8* __rest
     exts[n] = (u8)e;
 }
 
-// h_target / h_flags != nullptr: copy the adjacency out (dbg_graph_edges); fix != 0: rewrite the graph's Exts from it
-// (DebruijnGraph::fix_exts / get_valid_exts, graph.rs:337-377)
+// DebruijnGraph::is_compressed (graph.rs:296-334): thread per (node, dir); the FIRST collapsible pair in the reference's
+// iteration order (node ascending, Left before Right) wins through an atomicMin on ((node * 2 + dir) << 32 | next).
 template <int W>
-static int graph_edges_impl(Ctx* c, Graph* g, u32* h_target, u8* h_flags, int fix, const u8* h_valid_nodes) {
+__global__ void is_compressed_kernel(KP kp, const u64* __restrict__ words, const u64* __restrict__ start, const u32* __restrict__ length,
+                                     const u16* __restrict__ data, const u32* __restrict__ target, const u8* __restrict__ flags, u64 m,
+                                     int stranded, int scmap, u64* __restrict__ result) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * m) return;
+    const u64 i = t >> 1;
+    const int dir = (int)(t & 1);
+    auto single = [&](u64 n, int d, u32& nxt, int& ret) {
+        int cnt = 0;
+        for (int b = 0; b < 4; b++) {
+            const u64 s = (n * 2 + d) * 4 + b;
+            if (target[s] != NIL) { cnt++; nxt = target[s]; ret = flags[s] & 1; }
+        }
+        return cnt == 1;
+    };
+    u32 nxt = 0, back = 0;
+    int ret = 0, r2 = 0;
+    if (!single(i, dir, nxt, ret)) return;                       // dir_edges.len() == 1
+    if (!single(nxt, ret, back, r2)) return;                     // ret_edges.len() == 1
+    if (length[i] == (u32)kp.k && is_palindrome<W>(kp, kmer_at<W>(kp, words, start[i]))) return;      // we are a palindrome
+    if (length[nxt] == (u32)kp.k && is_palindrome<W>(kp, kmer_at<W>(kp, words, start[nxt]))) return;  // the neighbour is
+    if (i == nxt) return;                                        // smooth circle biting its own tail
+    if (scmap && data[i] != data[nxt]) return;                   // spec.join_test (ScmapCompress: data equality)
+    atomicMin(result, (t << 32) | nxt);
+}
+
+// h_target / h_flags != nullptr: copy the adjacency out (dbg_graph_edges); fix == 1: rewrite the graph's Exts from it
+// (DebruijnGraph::fix_exts / get_valid_exts, graph.rs:337-377); fix == 2: is_compressed, *pair_out = -1 or (node << 32 | next)
+template <int W>
+static int graph_edges_impl(Ctx* c, Graph* g, u32* h_target, u8* h_flags, int fix, const u8* h_valid_nodes, int scmap = 0, long long* pair_out = nullptr) {
     const u64 m = g->n_nodes;
+    if (pair_out) *pair_out = -1;
     if (m == 0) return DBG_OK;
     if (m >= (1ull << 31)) DBG_SET_ERR(c, DBG_E_BADARG, "too many nodes for 32-bit ids");
     TRY(arena_begin(c));
@@ -1045,6 +1075,18 @@ static int graph_edges_impl(Ctx* c, Graph* g, u32* h_target, u8* h_flags, int fi
         CU(c, cudaMemcpyAsync(h_target, d_target.p, 8 * m * sizeof(u32), cudaMemcpyDeviceToHost, st));
         CU(c, cudaMemcpyAsync(h_flags, d_flags.p, 8 * m, cudaMemcpyDeviceToHost, st));
     }
+    if (fix == 2) {
+        DBuf<u64> res;
+        TRY(res.alloc(c, 1));
+        TRY(res.fill_ff());
+        is_compressed_kernel<W><<<grid_for(2 * m, 256), 256, 0, st>>>(kp, g->words, g->start, g->length, g->data, d_target.p, d_flags.p, m,
+                                                                     g->stranded, scmap, res.p);
+        TRY(check_launch(c, "is_compressed"));
+        u64 h = 0;
+        TRY(read_u64(c, res.p, &h));
+        if (h != ~0ull) *pair_out = (long long)(((h >> 33) << 32) | (h & 0xffffffffull));
+        return DBG_OK;
+    }
     if (fix) {
         DBuf<u8> d_valid;
         if (h_valid_nodes) {
@@ -1062,6 +1104,11 @@ int graph_edges_dev(Ctx* c, const Graph* g, u32* h_target, u8* h_flags) {
     if (!g || !h_target || !h_flags) DBG_SET_ERR(c, DBG_E_BADARG, "null argument");
     Graph* gm = const_cast<Graph*>(g);   // not modified when fix == 0
     return g->k <= 32 ? graph_edges_impl<1>(c, gm, h_target, h_flags, 0, nullptr) : graph_edges_impl<2>(c, gm, h_target, h_flags, 0, nullptr);
+}
+int graph_is_compressed_dev(Ctx* c, const Graph* g, int scmap, long long* pair_out) {
+    if (!g || !pair_out) DBG_SET_ERR(c, DBG_E_BADARG, "null argument");
+    Graph* gm = const_cast<Graph*>(g);   // not modified
+    return g->k <= 32 ? graph_edges_impl<1>(c, gm, nullptr, nullptr, 2, nullptr, scmap, pair_out) : graph_edges_impl<2>(c, gm, nullptr, nullptr, 2, nullptr, scmap, pair_out);
 }
 int graph_fix_exts_dev(Ctx* c, Graph* g, const u8* h_valid_nodes) {
     if (!g) DBG_SET_ERR(c, DBG_E_BADARG, "null graph");

@@ -1894,6 +1894,23 @@ int filter_kmers_dev(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, 
 // with NCCL on these device buffers), and counts the buckets it owns.  All occurrences of a canonical
 // k-mer share a bucket, so per-rank tables are disjoint and their union is the unsharded table.
 // ================================================================================================
+// bucket regions with slack (direct partition) -> bucket-contiguous records: one warp per bucket, coalesced 16-byte copies
+template <int RW>
+__global__ void __launch_bounds__(256) compact_regions_kernel(const u64* __restrict__ src, const u64* __restrict__ reg_start, const u32* __restrict__ cnt,
+                                                               const u64* __restrict__ dst_off, u32 nb, u64* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    for (u64 b = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += ((u64)gridDim.x * blockDim.x) >> 5) {
+        const u64 s0 = reg_start[b], d0 = dst_off[b];
+        const u32 n = cnt[b];
+        for (u32 i = lane; i < n; i += 32) {
+            const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(src + (s0 + i) * RW);
+            ulonglong2* dp = reinterpret_cast<ulonglong2*>(dst + (d0 + i) * RW);
+            dp[0] = sp[0];
+            if (RW == 4) dp[1] = sp[1];
+        }
+    }
+}
+
 int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int bbits, Partition** out) {
     *out = nullptr;
     if (k < 4 || k > 64) DBG_SET_ERR(c, DBG_E_BADARG, "k=%d outside [4,64]", k);
@@ -1907,7 +1924,36 @@ int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int
     P->ctx = c; P->k = k; P->p = p; P->bbits = bbits; P->n_input = N; P->rec_words = k <= 32 ? 2 : 4;
     PartOut po;
     int rc = DBG_OK;
-    if (N) rc = k <= 32 ? partition_stage<1>(c, k, s, stranded, N, max_len, p, bbits, 0, 1u << bbits, true, po)
+    bool done = false;
+    // Large contiguous device-resident inputs: the direct partition (sampling pass + records straight into per-bucket
+    // regions) followed by ONE streaming pass that closes the gaps between the regions — 2 x 16 bytes per record moved
+    // coalesced, against the staging path's scatter of every record through a bucket-cursor atomic.
+    const u64 n_tiles_all = (s->contiguous && s->total_end > s->base0) ? (s->total_end - s->base0 + TP - 1) / TP : 0;
+    if (N && k <= 32 && c->direct_partition && n_tiles_all >= c->direct_min_tiles && s->n_pending == 0) {
+        const u32 NB = 1u << bbits;
+        DirectOut d;
+        rc = partition_direct<1>(c, k, s, stranded, N, p, bbits, d);
+        if (rc == DBG_OK) rc = po.bucket_count.alloc_pool(c, NB);
+        if (rc == DBG_OK) rc = po.bucket_off.alloc_pool(c, (u64)NB + 1);
+        if (rc == DBG_OK) rc = exclusive_scan_u32_to_u64(c, d.cnt.p, po.bucket_off.p, NB, po.bucket_off.p + NB);
+        u64 h[3] = {0, 0, 0};
+        if (rc == DBG_OK) rc = read_u64(c, d.ctr.p, h, 3);   // [1] overflow flag, [2] records stored
+        if (rc == DBG_OK && !(u32)h[1]) {
+            po.n_rec = h[2];
+            rc = po.rec.alloc_pool(c, po.n_rec * 2);
+            if (rc == DBG_OK) {
+                CU(c, cudaMemcpyAsync(po.bucket_count.p, d.cnt.p, (u64)NB * 4, cudaMemcpyDeviceToDevice, c->stream));
+                compact_regions_kernel<2><<<(u32)std::min<u64>(((u64)NB + 7) / 8, (u64)c->sm_count * 32), 256, 0, c->stream>>>(
+                    d.rec.p, d.bucket_start.p, d.cnt.p, po.bucket_off.p, NB, po.rec.p);
+                rc = check_launch(c, "compact_regions");
+            }
+            done = rc == DBG_OK;
+        }
+        if (rc != DBG_OK) { delete reinterpret_cast<dbg_partition*>(P); return rc; }
+        if (!done) { po.bucket_count.release(); po.bucket_off.release(); }   // a region overflowed: staging path below
+    }
+    if (done) {
+    } else if (N) rc = k <= 32 ? partition_stage<1>(c, k, s, stranded, N, max_len, p, bbits, 0, 1u << bbits, true, po)
                         : partition_stage<2>(c, k, s, stranded, N, max_len, p, bbits, 0, 1u << bbits, true, po);
     else {
         rc = po.bucket_count.alloc_pool(c, 1u << bbits);
@@ -1927,6 +1973,7 @@ int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int
     return DBG_OK;
 }
 
+// (defined above partition_reads_dev's first use)
 void free_partition(Partition* P) {
     if (!P) return;
     cudaStream_t st = P->ctx->stream;

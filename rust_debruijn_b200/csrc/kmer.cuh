@@ -182,6 +182,30 @@ HD u32 pmer_score(u32 x, int p, bool stranded) {
     x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA6Bu; x ^= x >> 13;
     return x;
 }
+// Smallest p-mer score of the k-mer WITHOUT its first p-mer (drop_first) and WITHOUT its last p-mer (drop_last): the two
+// neighbours of a k-mer share all but one p-mer with it, so their buckets cost one more score each instead of K - p + 1.
+template <int W>
+HD void kmer_min_scores_shared(const KP& kp, Kmer<W> x, int p, bool stranded, u32& drop_first, u32& drop_last) {
+    const u32 pmask = p == 16 ? 0xffffffffu : ((1u << (2 * p)) - 1);
+    u32 a = 0xffffffffu, b = 0xffffffffu;   // a: p-mers 0 .. w-2, b: p-mers 1 .. w-1
+    const int w1 = kp.k - p;                 // index of the last p-mer
+    for (int t = w1; t >= 0; t--) {          // from the last p-mer towards the first, shifting right
+        const u32 s = pmer_score((u32)x.lo & pmask, p, stranded);
+        if (t != w1) a = s < a ? s : a;
+        if (t != 0) b = s < b ? s : b;
+        if constexpr (W == 1) { x.lo >>= 2; }
+        else { x.lo = (x.lo >> 2) | (x.hi << 62); x.hi >>= 2; }
+    }
+    drop_first = b;
+    drop_last = a;
+}
+template <int W>
+HD u32 kmer_first_pmer(const KP& kp, Kmer<W> x, int p) {   // the p-mer at bases 0 .. p-1
+    const u32 pmask = p == 16 ? 0xffffffffu : ((1u << (2 * p)) - 1);
+    const int sh = 2 * (kp.k - p);
+    if constexpr (W == 1) { return (u32)(x.lo >> sh) & pmask; }
+    else { return (u32)(sh >= 64 ? x.hi >> (sh - 64) : (x.hi << (64 - sh)) | (x.lo >> sh)) & pmask; }
+}
 template <int W>
 HD u32 kmer_min_score(const KP& kp, Kmer<W> x, int p, bool stranded) {
     const u32 pmask = p == 16 ? 0xffffffffu : ((1u << (2 * p)) - 1);

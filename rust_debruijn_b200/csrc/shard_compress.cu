@@ -80,6 +80,11 @@ __global__ void __launch_bounds__(ML_THREADS) ms_links_kernel(KP kp, const u64* 
         const u32 e = exts[i];
         const bool pal = !cfg.stranded && is_palindrome<W>(kp, key);
         u32 both[2];
+        // a neighbour shares all p-mers but one with this k-mer: the shared minima are computed once for both sides
+        u32 m_drop_first = 0, m_drop_last = 0;
+        if (!pal && (popc4(exts_side(e, 0)) == 1 || popc4(exts_side(e, 1)) == 1))
+            kmer_min_scores_shared<W>(kp, key, cfg.p, cfg.stranded != 0, m_drop_first, m_drop_last);
+        const u32 pm_mask = cfg.p == 16 ? 0xffffffffu : ((1u << (2 * cfg.p)) - 1);
 #pragma unroll
         for (int d = 0; d < 2; d++) {
             u32 succ = NIL;
@@ -87,7 +92,12 @@ __global__ void __launch_bounds__(ML_THREADS) ms_links_kernel(KP kp, const u64* 
             if (popc4(nib) == 1 && !pal) {                                     // compression.rs:386
                 const u32 base = unique_base(nib);                             // :390
                 Kmer<W> nk = d == 0 ? Ops<W>::ext_left(kp, key, base) : Ops<W>::ext_right(kp, key, base);  // :392
-                const u32 bkt = kmer_min_score<W>(kp, nk, cfg.p, cfg.stranded != 0) & mask;   // strand-symmetric: before canonicalisation
+                // MSP bucket of the neighbour (strand-symmetric, so taken before canonicalisation): the left neighbour keeps this
+                // k-mer's p-mers 0 .. w-2 and gains a new first p-mer, the right neighbour keeps 1 .. w-1 and gains a new last one
+                const u32 snew = d == 0 ? pmer_score(kmer_first_pmer<W>(kp, nk, cfg.p), cfg.p, cfg.stranded != 0)
+                                        : pmer_score((u32)nk.lo & pm_mask, cfg.p, cfg.stranded != 0);
+                const u32 sold = d == 0 ? m_drop_last : m_drop_first;
+                const u32 bkt = (snew < sold ? snew : sold) & mask;
                 const u32 owner = (u32)(((u64)bkt * (u32)cfg.P) >> cfg.bbits);
                 bool flip = false;
                 if (!cfg.stranded) {                                           // :396-400

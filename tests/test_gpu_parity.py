@@ -592,6 +592,42 @@ def test_canonical_form_invariant_to_seed_order(D, ctx, orc, k):
         assert _canon_form(orc, og) == mine
 
 
+def test_is_compressed_on_device(D, ctx, orc):
+    """DebruijnGraph::is_compressed (src/graph.rs:296-334) as a device kernel: None after compress_kmers on all-valid tables
+    (the property src/test.rs:248-254 asserts), and the same first collapsible pair as the oracle's restatement on graphs that
+    are NOT compressed (censored k-mers leave dangling Exts that end unitigs early; is_compressed ignores missing links)."""
+    rng = np.random.default_rng(21)
+    for k in (31, 32, 63):
+        contigs = [c for c in random_contigs(rng) if len(c) >= k]
+        table, _ = D.filter_kmers(orc.seqset_from_lists(contigs + contigs), D.CountFilter(2), False, False, 4, k=k, ctx=ctx)
+        g = D.compress_kmers_with_hash(False, D.SimpleCompress(D.SAT_ADD), table)
+        assert g.is_compressed() is None
+        assert orc.graph_edges(k, g.to_host())[2] is None
+    for k, R in ((31, 3000), (63, 2000), (31, 20000)):
+        table, _ = D.filter_kmers(orc.synth_reads(R, 1, orc.ERR_THR_NOISY), D.CountFilter(2), False, False, 4, k=k, ctx=ctx)
+        g = D.compress_kmers_with_hash(False, D.SimpleCompress(D.SAT_ADD), table)
+        want = orc.graph_edges(k, g.to_host())[2]
+        assert want is not None and g.is_compressed() == want
+        # ScmapCompress: the data of both nodes must agree (join_test) — checked against a host evaluation of the same rule
+        got = g.is_compressed(D.ScmapCompress())
+        tgt, flg = g.edges()
+        h = g.to_host()
+        exp = None
+        for i in range(h["n_nodes"]):
+            for d in (0, 1):
+                e1 = [(int(tgt[i, d, b]), int(flg[i, d, b]) & 1) for b in range(4) if tgt[i, d, b] != 0xffffffff]
+                if len(e1) != 1:
+                    continue
+                nx, rd = e1[0]
+                e2 = [b for b in range(4) if tgt[nx, rd, b] != 0xffffffff]
+                if len(e2) == 1 and nx != i and h["data"][i] == h["data"][nx]:
+                    exp = (i, nx)
+                    break
+            if exp:
+                break
+        assert got == exp
+
+
 def test_compress_kmers_slice_variant(D, ctx, orc):
     """compression::compress_kmers (src/compression.rs:598-615): unordered (k-mer, (exts, data)) slice."""
     ss = orc.synth_reads(1500, 1, orc.ERR_THR_NOISY)
