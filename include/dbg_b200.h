@@ -46,7 +46,7 @@ typedef enum {
     DBG_REDUCE_ADD_MOD_65535 = 2, /* |a,b| ((a as u32 + *b as u32) % 65535)   src/test.rs:247     */
     DBG_REDUCE_MAX = 3,           /* |a,b| max(a,*b)                          src/test.rs:469     */
     DBG_REDUCE_SCMAP = 4          /* ScmapCompress (src/compression.rs:66-98): join_test = data equality, reduce keeps the value;
-                                     dbg_compress_kmers_with_hash only (the sharded dbg_cs_* stages take 0..3) */
+                                     also honoured by dbg_reads_to_graph_multi: the join_test crosses ranks) */
 } dbg_reduce_op;
 
 typedef struct dbg_ctx dbg_ctx;
@@ -100,6 +100,16 @@ int dbg_seqset_upload_uniform(dbg_ctx* ctx, const uint64_t* words, uint64_t n_wo
  * packing runs on the device; the result is a contiguous sequence set ready for dbg_filter_kmers. */
 int dbg_seqset_from_ascii(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, const uint64_t* start, const uint32_t* length,
                           const uint8_t* seq_exts, uint64_t n_seqs, uint64_t* n_invalid, dbg_seqset** out);
+/* DnaString::from_acgt_bytes_hashn (src/dna_string.rs:254-278): as above, but a non-ACGT character at position pos of a sequence
+ * becomes the repeatable pseudo-random base  DefaultHasher(read_name, pos) % 4  — SipHash-1-3 with a zero key over
+ * [len(name) u64 LE][name][pos u64 LE], the byte stream Rust's Hash impls for [u8] and usize feed the hasher.  names: all read
+ * names back to back (host), name i = names[name_start[i] .. + name_len[i]). */
+int dbg_seqset_from_ascii_hashn(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, const uint64_t* start, const uint32_t* length,
+                                const uint8_t* names, uint64_t n_name_bytes, const uint64_t* name_start, const uint32_t* name_len,
+                                const uint8_t* seq_exts, uint64_t n_seqs, uint64_t* n_invalid, dbg_seqset** out);
+/* SipHash-1-3, zero key, of a byte string (host): the primitive behind the call above, exported so that it can be pinned against
+ * an independent implementation. */
+uint64_t dbg_siphash13(const uint8_t* bytes, uint64_t n);
 /* Same, asynchronous: returns at once, the packed words go up in chunks on a copy stream and the partition stage of
  * the next dbg_filter_kmers / dbg_partition_reads / dbg_reads_to_graph call starts on the chunks that have arrived.
  * `words` (pinned host memory for real overlap) must stay valid and unchanged until that call has returned. */
@@ -127,6 +137,14 @@ int dbg_filter_kmers(dbg_ctx* ctx, int k, const dbg_seqset* seqs, uint32_t min_k
 int dbg_filter_kmers_host(dbg_ctx* ctx, int k, const uint64_t* words, uint64_t n_words, const uint64_t* start,
                           const uint32_t* length, const uint8_t* seq_exts, uint64_t n_seqs, uint32_t min_kmer_obs,
                           int stranded, int report_all_kmers, uint64_t memory_size_gb, dbg_kmer_table** out);
+/* filter::filter_kmers with CountFilterSet<u8>::new(min_kmer_obs) — src/filter.rs:68-101: `labels` (host, one per sequence, < 64) is
+ * the D1 of the reference's (V, Exts, D1) tuples; the summary of a k-mer is the sorted, deduplicated set of the labels it was
+ * observed with, returned as a 64-bit mask per k-mer (dbg_table_colorsets: bit c = label c) — the content of the reference's
+ * Vec<u8> after sort() + dedup().  Valid iff observations >= min_kmer_obs (<= 65535).  Exts as for CountFilter; the table's
+ * counts hold min(observations, 65535). */
+int dbg_filter_kmers_colorset(dbg_ctx* ctx, int k, const dbg_seqset* seqs, const uint8_t* labels, uint32_t min_kmer_obs, int stranded,
+                              uint64_t memory_size_gb, dbg_kmer_table** out);
+int dbg_table_colorsets(const dbg_kmer_table* t, uint64_t* masks /* dbg_table_len entries */);
 uint64_t dbg_table_len(const dbg_kmer_table* t);      /* BoomHashMap2::len */
 uint64_t dbg_table_all_len(const dbg_kmer_table* t);  /* all_kmers.len()   */
 uint64_t dbg_table_n_input(const dbg_kmer_table* t);
@@ -151,6 +169,13 @@ int dbg_graph_stranded(const dbg_graph* g);
 int dbg_graph_k(const dbg_graph* g);
 int dbg_graph_copy_out(const dbg_graph* g, uint64_t* words, uint64_t* start, uint32_t* length, uint8_t* exts,
                        uint16_t* data);
+/* serde image of BaseGraph<K, u16> in bincode 1.x's default encoding (little-endian fixed-width integers, u64 sequence lengths),
+ * field order as derived in the crate (src/graph.rs:43-50; src/dna_string.rs:72-76, 762-767; src/lib.rs:577-580):
+ *   sequences.sequence.storage | sequences.sequence.len | sequences.start | sequences.length | exts | data | stranded
+ * i.e. what `bincode::serialize(&base_graph)` writes and `bincode::deserialize::<BaseGraph<K, u16>>` reads.  Two-phase:
+ * *n_bytes is always set, `out` is written only when cap >= *n_bytes.  K is a type parameter in the crate: deserialize takes k. */
+int dbg_graph_serialize(const dbg_graph* g, uint8_t* out, uint64_t cap, uint64_t* n_bytes);
+int dbg_graph_deserialize(dbg_ctx* ctx, int k, const uint8_t* bytes, uint64_t n_bytes, dbg_graph** out);
 /* BaseGraph::finish + DebruijnGraph::find_edges for EVERY (node, side) — src/graph.rs:116-142 (left_order / right_order),
  * :223-291 (find_edges, find_link).  Host outputs of 8 * n_nodes entries, slot (node * 2 + side) * 4 + base (side 0 = Left,
  * 1 = Right; base = A, C, G, T): target = node the extension leads to (0xffffffff: the node has no such extension, or the
@@ -180,10 +205,10 @@ int dbg_reads_to_graph_host(dbg_ctx* ctx, int k, const uint64_t* words, uint64_t
                             const uint32_t* length, const uint8_t* seq_exts, uint64_t n_seqs, uint32_t min_kmer_obs,
                             int stranded, int reduce_op, dbg_kmer_table** table_out, dbg_graph** graph_out);
 
-/* ---- multi-GPU building blocks: MSP-bucket sharding of the counting stage (the reference's sharded flow,
- * src/test.rs:433-456: msp_sequence -> per-shard filter_kmers).  Every rank partitions its own reads with the
- * same plan, the caller exchanges bucket ranges between ranks (one all-to-all of super-k-mer records over
- * NCCL on the device pointers below), and each rank counts the buckets it owns.  See rust_debruijn_b200/sharded.py. */
+/* ---- building blocks of the bucket-sharded counting stage (the reference's sharded flow, src/test.rs:433-456: msp_sequence
+ * -> per-shard filter_kmers), exported for callers that run their own exchange: every rank partitions its own reads with the
+ * same plan, ships each bucket range to its owner and counts the buckets it owns.  dbg_reads_to_graph_multi (above) does all
+ * of this inside the library. */
 typedef struct dbg_partition dbg_partition;
 /* Minimizer length and log2(#buckets) for a job of n_input_kmers_total k-mer occurrences (same on every rank). */
 int dbg_plan_filter(dbg_ctx* ctx, int k, uint64_t n_input_kmers_total, int* msp_p, int* bucket_bits);
@@ -219,30 +244,7 @@ int dbg_table_from_device(dbg_ctx* ctx, int k, uint64_t n, const void* d_kmers_l
 int dbg_table_from_device_sorted(dbg_ctx* ctx, int k, uint64_t n, const void* d_kmers_lo, const void* d_kmers_hi,
                                  const void* d_exts, const void* d_counts, dbg_kmer_table** out);
 
-/* ---- sharded compression (multi-GPU): the sorted table is replicated on every rank, the work is split by k-mer
- * index range / node range; same kernels as the single-GPU fast path of dbg_compress_kmers_with_hash
- * (src/compression.rs:450-583).  Sequence per rank (collectives by the caller, see rust_debruijn_b200/sharded.py):
- *   dbg_cs_links [v0,v1) -> all-gather link pairs -> dbg_cs_pack -> dbg_cs_discover [v0,v1) -> dbg_cs_sort_paths ->
- *   all-to-all of the path records by seed range -> dbg_cs_layout (own seed range) -> dbg_cs_emit (own nodes) ->
- *   all-reduce(sum) of words / exts / data / start / length -> dbg_graph_from_device.
- * All pointers are DEVICE pointers owned by the caller.  Only unitigs reachable by end walks (<= lmax k-mers) are
- * handled: if the covered k-mers over all ranks do not add up to the table size (long unitigs, cycles) the caller
- * falls back to dbg_compress_kmers_with_hash on the replicated table. */
-int dbg_cs_links(dbg_ctx* ctx, const dbg_kmer_table* full_table, int stranded, uint64_t v0, uint64_t v1, void* d_nxt_local /* 8 B per k-mer */);
-int dbg_cs_pack(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_nxt_full, void* d_rec16 /* 16 B per k-mer */);
-int dbg_cs_discover(dbg_ctx* ctx, const void* d_rec16, uint64_t n_total, uint64_t v0, uint64_t v1, uint32_t lmax,
-                    void* d_pkey /* u64 */, void* d_pval /* u32 */, uint64_t capacity, uint64_t* n_paths, uint64_t* n_kmers_covered);
-/* sorts the n_nodes path records by seed; *which = 0 / 1: the (a) or (b) pair holds the sorted records afterwards */
-int dbg_cs_layout(dbg_ctx* ctx, int k, uint64_t n_total, uint64_t n_nodes, void* d_pkey_a, void* d_pval_a, void* d_pkey_b,
-                  void* d_pval_b, int* which, void* d_start /* u64 */, void* d_length /* u32 */, uint64_t* n_bases);
-/* sort path records by seed (the pre-sort before they are shipped to the rank that owns their seed range) */
-int dbg_cs_sort_paths(dbg_ctx* ctx, uint64_t n_paths, void* d_pkey_a, void* d_pval_a, void* d_pkey_b, void* d_pval_b, int* which);
-/* the n_paths records (sorted by seed, local base offsets in d_start_local) become nodes node0.. of the graph, bases from
- * base0 + d_start_local[i]; writes go to the global positions of zeroed full-size arrays (stream-ordered, not synchronised) */
-int dbg_cs_emit(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_rec16, const void* d_pkey_sorted,
-                const void* d_pval_sorted, const void* d_start_local, uint64_t n_paths, uint64_t node0, uint64_t base0,
-                int reduce_op, void* d_words, void* d_exts /* u8 */, void* d_data /* u16 */, void* d_out_start /* u64 */,
-                void* d_out_length /* u32 */);
+/* A BaseGraph handle from caller-owned device arrays (copied). */
 int dbg_graph_from_device(dbg_ctx* ctx, int k, int stranded, uint64_t n_nodes, uint64_t n_bases, const void* d_words,
                           const void* d_start, const void* d_length, const void* d_exts, const void* d_data,
                           dbg_graph** out);
@@ -301,6 +303,14 @@ int dbg_plan_quantile_cuts(const uint64_t* hist, uint64_t n_bins, int n_ranks, u
  * out_bucket has sum_i max(length[i]-k+1, 0) entries, sequence-major. */
 int dbg_msp_kmer_buckets(dbg_ctx* ctx, int k, int p, const dbg_seqset* seqs, int stranded, uint32_t* out_bucket,
                          uint64_t n_out);
+
+/* msp::msp_sequence — src/msp.rs:279-324 with Scanner::scan (:207-276): the MSP intervals of every sequence, in scan order, as
+ * (sequence index, start, len [the Vmer the reference copies out is bases start .. start+len of that sequence], bucket =
+ * MspIntervalP::bucket() as u32, Exts::from_slice_bounds src/lib.rs:645-660).  permutation: host array of 4^p scores (NULL = the
+ * reference's default identity permutation; tables up to p = 12), rc = the reference's `rc` argument.  Sequences shorter than k
+ * yield nothing.  Two-phase: *n_intervals is always set; the arrays are written only when cap >= *n_intervals. */
+int dbg_msp_sequence(dbg_ctx* ctx, int k, int p, const dbg_seqset* seqs, int rc, const uint32_t* permutation, uint64_t cap,
+                     uint64_t* n_intervals, uint32_t* seq, uint32_t* start, uint32_t* len, uint32_t* bucket, uint8_t* exts);
 
 #ifdef __cplusplus
 }

@@ -135,6 +135,65 @@ def from_acgt_bytes(ascii_seqs):
     return w, st, ln, n_bad
 
 
+def siphash13(data, k0=0, k1=0):
+    """SipHash-1-3 (the function behind Rust's DefaultHasher, zero key) in plain Python integers — test infrastructure."""
+    M = (1 << 64) - 1
+    v0, v1, v2, v3 = k0 ^ 0x736f6d6570736575, k1 ^ 0x646f72616e646f6d, k0 ^ 0x6c7967656e657261, k1 ^ 0x7465646279746573
+
+    def rotl(x, b):
+        return ((x << b) | (x >> (64 - b))) & M
+
+    def rnd(v0, v1, v2, v3):
+        v0 = (v0 + v1) & M; v1 = rotl(v1, 13); v1 ^= v0; v0 = rotl(v0, 32)
+        v2 = (v2 + v3) & M; v3 = rotl(v3, 16); v3 ^= v2
+        v0 = (v0 + v3) & M; v3 = rotl(v3, 21); v3 ^= v0
+        v2 = (v2 + v1) & M; v1 = rotl(v1, 17); v1 ^= v2; v2 = rotl(v2, 32)
+        return v0, v1, v2, v3
+
+    data = bytes(data)
+    n = len(data)
+    for i in range(0, n - n % 8, 8):
+        m = int.from_bytes(data[i:i + 8], "little")
+        v3 ^= m
+        v0, v1, v2, v3 = rnd(v0, v1, v2, v3)
+        v0 ^= m
+    b = int.from_bytes(data[n - n % 8:], "little") | ((n & 0xff) << 56)
+    v3 ^= b
+    v0, v1, v2, v3 = rnd(v0, v1, v2, v3)
+    v0 ^= b
+    v2 ^= 0xff
+    for _ in range(3):
+        v0, v1, v2, v3 = rnd(v0, v1, v2, v3)
+    return v0 ^ v1 ^ v2 ^ v3
+
+
+def from_acgt_bytes_hashn(ascii_seqs, read_names):
+    """DnaString::from_acgt_bytes_hashn (dna_string.rs:254-278) for every (sequence, read name): a non-ACGT position becomes
+    DefaultHasher{read_name.hash(); pos.hash()}.finish() % 4 — SipHash-1-3, zero key, over [len(name) u64 LE][name][pos u64 LE]
+    (Hash for [u8] writes the length prefix and the bytes, usize its 8 native-endian bytes).  Returns (words, start, length, n_invalid)."""
+    bits, n_bad = [], 0
+    for sq, name in zip(ascii_seqs, read_names):
+        b, ok = acgt_to_bits(sq)
+        b = b.copy()
+        pre = len(name).to_bytes(8, "little") + bytes(name)
+        for pos in np.nonzero(~ok)[0]:
+            b[pos] = siphash13(pre + int(pos).to_bytes(8, "little")) % 4
+        bits.append(b)
+        n_bad += int((~ok).sum())
+    w, st, ln = seqset_from_lists(bits)
+    return w, st, ln, n_bad
+
+
+def graph_to_bincode(g):
+    """bincode 1.x image of BaseGraph<K, u16> (serde field order: graph.rs:43-50, dna_string.rs:72-76, 762-767): storage Vec<u64>,
+    len usize, start Vec<usize>, length Vec<u32>, exts Vec<u8>, data Vec<u16>, stranded bool; u64 little-endian lengths."""
+    def vec(a, dt):
+        a = np.ascontiguousarray(a, dt)
+        return int(len(a)).to_bytes(8, "little") + a.tobytes()
+    return (vec(g["words"], "<u8") + int(g["n_bases"]).to_bytes(8, "little") + vec(g["start"], "<u8") + vec(g["length"], "<u4") +
+            vec(g["exts"], "u1") + vec(g["data"], "<u2") + (b"\x01" if g.get("stranded") else b"\x00"))
+
+
 def seqset_from_lists(seqs):
     """list of uint8 base arrays -> (words, start, length) in PackedDnaStringSet layout."""
     length = np.array([len(s) for s in seqs], dtype=np.uint32)

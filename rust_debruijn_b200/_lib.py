@@ -70,6 +70,10 @@ SIGNATURES = {
     "dbg_seqset_upload_uniform": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vpp]),
     "dbg_seqset_upload_uniform_async": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vpp]),
     "dbg_seqset_from_ascii": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vpp]),
+    "dbg_seqset_from_ascii_hashn": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vpp]),
+    "dbg_siphash13": (C.c_uint64, [vp, C.c_uint64]),
+    "dbg_graph_serialize": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "dbg_graph_deserialize": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vpp]),
     "dbg_seqset_wrap_device": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.c_uint32, vpp]),
     "dbg_seqset_synth": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint32, vpp]),
     "dbg_seqset_len": (C.c_uint64, [vp]),
@@ -79,6 +83,8 @@ SIGNATURES = {
     "dbg_filter_kmers": (C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_int, C.c_int, C.c_uint64, vpp]),
     "dbg_filter_kmers_host": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_int,
                                         C.c_int, C.c_uint64, vpp]),
+    "dbg_filter_kmers_colorset": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint32, C.c_int, C.c_uint64, vpp]),
+    "dbg_table_colorsets": (C.c_int, [vp, vp]),
     "dbg_table_len": (C.c_uint64, [vp]),
     "dbg_table_all_len": (C.c_uint64, [vp]),
     "dbg_table_n_input": (C.c_uint64, [vp]),
@@ -119,16 +125,9 @@ SIGNATURES = {
     "dbg_table_device_ptrs": (C.c_int, [vp, vpp, vpp, vpp, vpp]),
     "dbg_table_from_device": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, vp, vpp]),
     "dbg_table_from_device_sorted": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, vp, vpp]),
-    "dbg_cs_links": (C.c_int, [vp, vp, C.c_int, C.c_uint64, C.c_uint64, vp]),
-    "dbg_cs_pack": (C.c_int, [vp, vp, vp, vp]),
-    "dbg_cs_discover": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, C.c_uint64,
-                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
-    "dbg_cs_layout": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_uint64, vp, vp, vp, vp, C.POINTER(C.c_int), vp, vp,
-                                C.POINTER(C.c_uint64)]),
-    "dbg_cs_sort_paths": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, C.POINTER(C.c_int)]),
-    "dbg_cs_emit": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp, vp, vp]),
     "dbg_graph_from_device": (C.c_int, [vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vpp]),
     "dbg_msp_kmer_buckets": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_uint64]),
+    "dbg_msp_sequence": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, vp, vp, vp, vp]),
     "dbg_comm_unique_id": (C.c_int, [vp]),
     "dbg_comm_create": (C.c_int, [vp, C.c_int, C.c_int, vp, vpp]),
     "dbg_comm_destroy": (None, [vp]),

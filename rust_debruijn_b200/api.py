@@ -132,6 +132,32 @@ class SeqSet:
         return ss
 
     @staticmethod
+    def from_ascii_hashn(ctx, ascii_seqs, read_names, seq_exts=None):
+        """DnaString::from_acgt_bytes_hashn (src/dna_string.rs:254-278) for a list of ASCII sequences with their read names:
+        a non-ACGT character becomes the repeatable base DefaultHasher(name, position) % 4.  .n_invalid counts them."""
+        if len(read_names) != len(ascii_seqs):
+            raise ValueError("one read name per sequence")
+        buf = b"".join(bytes(x) for x in ascii_seqs)
+        nbuf = b"".join(bytes(x) for x in read_names)
+        length = np.array([len(x) for x in ascii_seqs], np.uint32)
+        nlen = np.array([len(x) for x in read_names], np.uint32)
+        start = np.zeros(len(ascii_seqs), np.uint64)
+        nstart = np.zeros(len(ascii_seqs), np.uint64)
+        if len(ascii_seqs) > 1:
+            start[1:] = np.cumsum(length[:-1], dtype=np.uint64)
+            nstart[1:] = np.cumsum(nlen[:-1], dtype=np.uint64)
+        arr = np.frombuffer(buf, np.uint8) if buf else np.zeros(1, np.uint8)
+        narr = np.frombuffer(nbuf, np.uint8) if nbuf else np.zeros(1, np.uint8)
+        if seq_exts is not None:
+            seq_exts = np.ascontiguousarray(seq_exts, np.uint8)
+        h, bad = C.c_void_p(), C.c_uint64()
+        ctx.check(ctx._L.dbg_seqset_from_ascii_hashn(ctx._h, _ptr(arr), len(buf), _ptr(start), _ptr(length), _ptr(narr), len(nbuf),
+                                                     _ptr(nstart), _ptr(nlen), _ptr(seq_exts), len(ascii_seqs), C.byref(bad), C.byref(h)))
+        ss = SeqSet(ctx, h)
+        ss.n_invalid = bad.value
+        return ss
+
+    @staticmethod
     def upload_uniform(ctx, words, n_seqs, read_len, seq_exts=None, pipelined=False):
         """pipelined=True: asynchronous chunked upload overlapping the partition stage of the next call; `words` (pinned
         for real overlap) must stay untouched until that call has returned (the SeqSet keeps a reference)."""
@@ -184,6 +210,16 @@ class CountFilter:
         self.min_kmer_obs = min(self.min_kmer_obs, 65536)
 
 
+class CountFilterSet:
+    """src/filter.rs:68-101 with D = u8: keep k-mers observed at least `min_kmer_obs` times; the summary of a k-mer is the sorted,
+    deduplicated set of the labels (one per input sequence, < 64) it was observed with."""
+
+    def __init__(self, min_kmer_obs):
+        self.min_kmer_obs = int(min_kmer_obs)
+        if not 0 <= self.min_kmer_obs <= 65535:
+            raise ValueError("CountFilterSet: min_kmer_obs must be in [0, 65535]")
+
+
 class SimpleCompress:
     """src/compression.rs:40-65.  The closure cannot cross to the GPU: `func` is one of the four
     reductions the reference's tests use (SAT_ADD, WRAP_ADD, ADD_MOD_65535, MAX); join_test is always true."""
@@ -227,6 +263,13 @@ class KmerTable:
                                             _ptr(out["exts"]), _ptr(out["counts"]), _ptr(out["all_lo"]),
                                             _ptr(out["all_hi"]) if two else None))
         return out
+
+    def colorsets(self):
+        """CountFilterSet tables: per k-mer the sorted list of labels (the reference's Vec<u8> summary), from the 64-bit masks."""
+        n = len(self)
+        masks = np.zeros(n, np.uint64)
+        self.ctx.check(self.ctx._L.dbg_table_colorsets(self._h, _ptr(masks)))
+        return [[c for c in range(64) if (int(m) >> c) & 1] for m in masks]
 
     def iter(self):
         """(kmer, exts, count) in table order, like BoomHashMap2::iter (order here: ascending k-mer)."""
@@ -334,6 +377,24 @@ class BaseGraph:
         self.ctx.check(self.ctx._L.dbg_graph_is_compressed(self.ctx._h, self._h, int(isinstance(spec, ScmapCompress)), C.byref(pr)))
         return None if pr.value < 0 else (int(pr.value >> 32), int(pr.value & 0xffffffff))
 
+    def to_bincode(self):
+        """bincode 1.x image of the crate's serde-derived BaseGraph<K, u16> (field order src/graph.rs:43-50): bytes."""
+        L = self.ctx._L
+        n = C.c_uint64()
+        self.ctx.check(L.dbg_graph_serialize(self._h, None, 0, C.byref(n)))
+        buf = np.zeros(n.value, np.uint8)
+        self.ctx.check(L.dbg_graph_serialize(self._h, _ptr(buf), n.value, C.byref(n)))
+        return buf.tobytes()
+
+    @staticmethod
+    def from_bincode(data, k, ctx=None):
+        """Inverse of to_bincode (K is a type parameter in the crate, so it is an argument here)."""
+        ctx = ctx or default_context()
+        buf = np.frombuffer(bytes(data), np.uint8)
+        h = C.c_void_p()
+        ctx.check(ctx._L.dbg_graph_deserialize(ctx._h, k, _ptr(buf), len(buf), C.byref(h)))
+        return BaseGraph(ctx, h)
+
     def write_gfa(self, out):
         """DebruijnGraph::write_gfa (src/graph.rs:538-614): header, one S line per node, L lines for the left edges with
         target >= node and the right edges with target > node (edge direction '+' = enters the target through its left
@@ -383,13 +444,34 @@ def remove_censored_exts_sharded(stranded, table):
     table.ctx.check(table.ctx._L.dbg_remove_censored_exts(table.ctx._h, table._h, int(bool(stranded)), 1))
 
 
-def filter_kmers(seqs, summarizer, stranded, report_all_kmers, memory_size, k=31, ctx=None):
+def filter_kmers(seqs, summarizer, stranded, report_all_kmers, memory_size, k=31, ctx=None, labels=None):
     """filter::filter_kmers (src/filter.rs:139-148).
 
     seqs: a SeqSet, or (words, start, length[, seq_exts]) host arrays in PackedDnaStringSet layout.
-    summarizer: CountFilter.  Returns (KmerTable, all_kmers) — all_kmers is empty unless report_all_kmers."""
+    summarizer: CountFilter, or CountFilterSet with `labels` (one u8 < 64 per sequence: the D1 of the reference's tuples).
+    Returns (KmerTable, all_kmers) — all_kmers is empty unless report_all_kmers."""
+    if isinstance(summarizer, CountFilterSet):
+        if labels is None or report_all_kmers:
+            raise ValueError("CountFilterSet needs labels (and does not report all_kmers)")
+        own = None
+        if isinstance(seqs, SeqSet):
+            ss, ctx = seqs, seqs.ctx
+        else:
+            ctx = ctx or default_context()
+            ss = own = SeqSet.upload(ctx, *seqs)
+        lab = np.ascontiguousarray(labels, np.uint8)
+        if len(lab) != len(ss):
+            raise ValueError("one label per sequence")
+        try:
+            h = C.c_void_p()
+            ctx.check(ctx._L.dbg_filter_kmers_colorset(ctx._h, k, ss._h, _ptr(lab), summarizer.min_kmer_obs, int(bool(stranded)),
+                                                       int(memory_size), C.byref(h)))
+        finally:
+            if own is not None:
+                own.free()
+        return KmerTable(ctx, h), np.zeros(0, np.uint64)
     if not isinstance(summarizer, CountFilter):
-        raise TypeError("only CountFilter is on the accelerated path (SURVEY.md §8)")
+        raise TypeError("only CountFilter / CountFilterSet are on the accelerated path (SURVEY.md §8)")
     own = None
     if isinstance(seqs, SeqSet):
         ss, ctx = seqs, seqs.ctx
@@ -450,6 +532,24 @@ def msp_kmer_buckets(seqs, k, p, stranded=False):
     n = int(np.maximum(length.astype(np.int64) - k + 1, 0).sum())
     out = np.zeros(n, np.uint32)
     ctx.check(ctx._L.dbg_msp_kmer_buckets(ctx._h, k, p, seqs._h, int(bool(stranded)), _ptr(out), n))
+    return out
+
+
+def msp_sequence(seqs, k, p, permutation=None, rc=True):
+    """msp::msp_sequence (src/msp.rs:279-324) for every sequence of a SeqSet: dict of arrays (seq, start, len, bucket, exts), one
+    entry per MSP interval in scan order; the reference's Vmer of an interval is bases start .. start+len of sequence seq."""
+    ctx = seqs.ctx
+    perm = None if permutation is None else np.ascontiguousarray(permutation, np.uint32)
+    if perm is not None and len(perm) != 4 ** p:
+        raise ValueError("permutation needs 4^p entries")
+    n = C.c_uint64()
+    ctx.check(ctx._L.dbg_msp_sequence(ctx._h, k, p, seqs._h, int(bool(rc)), _ptr(perm), 0, C.byref(n), None, None, None, None, None))
+    m = n.value
+    out = dict(seq=np.zeros(m, np.uint32), start=np.zeros(m, np.uint32), len=np.zeros(m, np.uint32), bucket=np.zeros(m, np.uint32),
+               exts=np.zeros(m, np.uint8))
+    if m:
+        ctx.check(ctx._L.dbg_msp_sequence(ctx._h, k, p, seqs._h, int(bool(rc)), _ptr(perm), m, C.byref(n), _ptr(out["seq"]), _ptr(out["start"]),
+                                          _ptr(out["len"]), _ptr(out["bucket"]), _ptr(out["exts"])))
     return out
 
 

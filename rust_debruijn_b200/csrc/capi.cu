@@ -31,6 +31,7 @@ void free_table(Table* t) {
     if (t->counts) cudaFreeAsync(t->counts, st);
     if (t->all_lo) cudaFreeAsync(t->all_lo, st);
     if (t->all_hi) cudaFreeAsync(t->all_hi, st);
+    if (t->colors) cudaFreeAsync(t->colors, st);
     delete reinterpret_cast<dbg_kmer_table*>(t);
 }
 void free_graph(Graph* g) {
@@ -334,9 +335,53 @@ int dbg_seqset_upload_uniform_async(dbg_ctx* ctx, const uint64_t* words, uint64_
 // (src/dna_string.rs:811-821) for a whole batch of ASCII sequences.  Thread = one output word (32 bases of the
 // concatenation): finds the sequence holding its first base (binary search over the output offsets), then walks
 // the ASCII bytes, crossing sequence boundaries as needed.  A/a=0 C/c=1 G/g=2 T/t=3, anything else -> A (counted).
+// SipHash-1-3 with a zero key over the byte stream [len(name) as u64 LE][name][pos as u64 LE]: what Rust's
+// std::collections::hash_map::DefaultHasher yields for `read_name.hash(&mut h); pos.hash(&mut h_clone); h_clone.finish()`
+// (DnaString::from_acgt_bytes_hashn, src/dna_string.rs:254-278: Hash for [u8] writes the length prefix, then the bytes;
+// usize writes its 8 native-endian bytes).
+__host__ __device__ __forceinline__ u64 sip_rotl(u64 x, int b) { return (x << b) | (x >> (64 - b)); }
+struct Sip13 {
+    u64 v0, v1, v2, v3;
+    __host__ __device__ void init() { v0 = 0x736f6d6570736575ull; v1 = 0x646f72616e646f6dull; v2 = 0x6c7967656e657261ull; v3 = 0x7465646279746573ull; }
+    __host__ __device__ void round() {
+        v0 += v1; v1 = sip_rotl(v1, 13); v1 ^= v0; v0 = sip_rotl(v0, 32);
+        v2 += v3; v3 = sip_rotl(v3, 16); v3 ^= v2;
+        v0 += v3; v3 = sip_rotl(v3, 21); v3 ^= v0;
+        v2 += v1; v1 = sip_rotl(v1, 17); v1 ^= v2; v2 = sip_rotl(v2, 32);
+    }
+    __host__ __device__ void word(u64 m) { v3 ^= m; round(); v0 ^= m; }
+    __host__ __device__ u64 finish(u64 b) { v3 ^= b; round(); v0 ^= b; v2 ^= 0xff; round(); round(); round(); return v0 ^ v1 ^ v2 ^ v3; }
+};
+__host__ __device__ inline u64 sip13_name_pos(const u8* name, u32 L, u64 pos) {
+    Sip13 h;
+    h.init();
+    h.word((u64)L);
+    u64 m = 0;
+    const u32 total = L + 8;
+    for (u32 i = 0; i < total; i++) {
+        const u64 byte = i < L ? name[i] : (pos >> (8 * (i - L))) & 0xffull;
+        m |= byte << (8 * (i & 7));
+        if ((i & 7) == 7) { h.word(m); m = 0; }
+    }
+    return h.finish(m | ((u64)((16 + L) & 0xffu) << 56));
+}
+// plain SipHash-1-3 (zero key) of a byte string: the primitive alone, exported so that tests can pin it to an independent
+// implementation (CPython's bytes hash under PYTHONHASHSEED=0 is the same function)
+static u64 sip13_bytes(const u8* p, u64 n) {
+    Sip13 h;
+    h.init();
+    u64 m = 0;
+    for (u64 i = 0; i < n; i++) {
+        m |= (u64)p[i] << (8 * (i & 7));
+        if ((i & 7) == 7) { h.word(m); m = 0; }
+    }
+    return h.finish(m | ((n & 0xff) << 56));
+}
+
 __global__ void ascii_pack_kernel(const u8* __restrict__ ascii, const u64* __restrict__ in_start, const u64* __restrict__ out_start,
                                   const u32* __restrict__ length, u64 n_seqs, u64 n_bases, u64* __restrict__ words,
-                                  u64* __restrict__ n_invalid) {
+                                  u64* __restrict__ n_invalid, const u8* __restrict__ names, const u64* __restrict__ name_start,
+                                  const u32* __restrict__ name_len) {
     const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 bad = 0;
     if (w * 32 < n_bases) {
@@ -354,7 +399,10 @@ __global__ void ascii_pack_kernel(const u8* __restrict__ ascii, const u64* __res
             const bool ok = up == 'A' || up == 'C' || up == 'G' || up == 'T';
             u32 v = (c >> 1) & 3u;      // A 0, C 1, T 2, G 3
             v ^= v >> 1;                // swap 2 <-> 3
-            if (!ok) { v = 0; bad++; }
+            if (!ok) {   // from_acgt_bytes: 'A'; from_acgt_bytes_hashn: repeatable pseudo-random base from (read name, position)
+                v = names ? (u32)(sip13_name_pos(names + name_start[si], name_len[si], off) & 3ull) : 0u;
+                bad++;
+            }
             out |= (u64)v << (62 - 2 * t);
             off++;
         }
@@ -371,13 +419,19 @@ __global__ void ascii_pack_kernel(const u8* __restrict__ ascii, const u64* __res
     }
 }
 
-int dbg_seqset_from_ascii(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, const uint64_t* start, const uint32_t* length,
-                          const uint8_t* seq_exts, uint64_t n_seqs, uint64_t* n_invalid, dbg_seqset** out) {
+static int seqset_from_ascii_impl(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, const uint64_t* start, const uint32_t* length,
+                                  const uint8_t* names, uint64_t n_name_bytes, const uint64_t* name_start, const uint32_t* name_len,
+                                  const uint8_t* seq_exts, uint64_t n_seqs, uint64_t* n_invalid, dbg_seqset** out) {
     if (!ctx || !out) return DBG_E_BADARG;
     Ctx* c = CTX(ctx);
     *out = nullptr;
     cudaSetDevice(c->device);
     if (n_seqs && (!start || !length || !ascii)) DBG_SET_ERR(c, DBG_E_BADARG, "null argument");
+    if (names) {
+        if (!name_start || !name_len) DBG_SET_ERR(c, DBG_E_BADARG, "name_start / name_len are required with names");
+        for (u64 i = 0; i < n_seqs; i++)
+            if (name_start[i] > n_name_bytes || name_len[i] > n_name_bytes - name_start[i]) DBG_SET_ERR(c, DBG_E_BADARG, "name %llu runs past the name buffer", (unsigned long long)i);
+    }
     std::vector<u64> ostart(n_seqs + 1, 0);
     u32 max_len = 0;
     bool uniform = n_seqs > 0;
@@ -395,9 +449,9 @@ int dbg_seqset_from_ascii(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, 
     s->ctx = c; s->n_seqs = n_seqs; s->n_words = n_words; s->max_len = max_len;
     s->uniform_len = (uniform && n_seqs) ? length[0] : 0;
     s->contiguous = n_seqs > 0; s->base0 = 0; s->total_end = n_bases;
-    DBuf<u64> dw, ds, din, dbad;
-    DBuf<u32> dl;
-    DBuf<u8> de, dasc;
+    DBuf<u64> dw, ds, din, dbad, dns;
+    DBuf<u32> dl, dnl;
+    DBuf<u8> de, dasc, dnm;
     int rc = arena_begin(c);
     do {
         if (rc != DBG_OK) break;
@@ -419,8 +473,17 @@ int dbg_seqset_from_ascii(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, 
                 cudaMemcpyAsync(din.p, start, n_seqs * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
                 (n_bytes && cudaMemcpyAsync(dasc.p, ascii, n_bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)) { rc = DBG_E_CUDA; break; }
         }
+        if (names && n_seqs) {
+            if ((rc = dnm.alloc(c, n_name_bytes)) != DBG_OK) break;
+            if ((rc = dns.alloc(c, n_seqs)) != DBG_OK) break;
+            if ((rc = dnl.alloc(c, n_seqs)) != DBG_OK) break;
+            if ((n_name_bytes && cudaMemcpyAsync(dnm.p, names, n_name_bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) ||
+                cudaMemcpyAsync(dns.p, name_start, n_seqs * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                cudaMemcpyAsync(dnl.p, name_len, n_seqs * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = DBG_E_CUDA; break; }
+        }
         if (n_words) {
-            ascii_pack_kernel<<<grid_for(n_words, 256), 256, 0, c->stream>>>(dasc.p, din.p, ds.p, dl.p, n_seqs, n_bases, dw.p, dbad.p);
+            ascii_pack_kernel<<<grid_for(n_words, 256), 256, 0, c->stream>>>(dasc.p, din.p, ds.p, dl.p, n_seqs, n_bases, dw.p, dbad.p,
+                                                                           names ? dnm.p : nullptr, dns.p, dnl.p);
             if ((rc = check_launch(c, "ascii_pack")) != DBG_OK) break;
         }
         u64 bad = 0;
@@ -437,6 +500,18 @@ int dbg_seqset_from_ascii(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, 
     *out = h;
     return DBG_OK;
 }
+
+int dbg_seqset_from_ascii(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, const uint64_t* start, const uint32_t* length,
+                          const uint8_t* seq_exts, uint64_t n_seqs, uint64_t* n_invalid, dbg_seqset** out) {
+    return seqset_from_ascii_impl(ctx, ascii, n_bytes, start, length, nullptr, 0, nullptr, nullptr, seq_exts, n_seqs, n_invalid, out);
+}
+int dbg_seqset_from_ascii_hashn(dbg_ctx* ctx, const uint8_t* ascii, uint64_t n_bytes, const uint64_t* start, const uint32_t* length,
+                                const uint8_t* names, uint64_t n_name_bytes, const uint64_t* name_start, const uint32_t* name_len,
+                                const uint8_t* seq_exts, uint64_t n_seqs, uint64_t* n_invalid, dbg_seqset** out) {
+    if (ctx && !names) DBG_SET_ERR(CTX(ctx), DBG_E_BADARG, "names is null (use dbg_seqset_from_ascii)");
+    return seqset_from_ascii_impl(ctx, ascii, n_bytes, start, length, names, n_name_bytes, name_start, name_len, seq_exts, n_seqs, n_invalid, out);
+}
+uint64_t dbg_siphash13(const uint8_t* bytes, uint64_t n) { return sip13_bytes(bytes, n); }
 
 int dbg_seqset_wrap_device(dbg_ctx* ctx, const uint64_t* d_words, uint64_t n_words, const uint64_t* d_start,
                            const uint32_t* d_length, const uint8_t* d_seq_exts, uint64_t n_seqs, uint32_t max_len,
@@ -764,53 +839,6 @@ int dbg_filter_from_records(dbg_ctx* ctx, int k, const void* d_records, uint64_t
 }
 
 // ---- sharded compression ------------------------------------------------------------------------------------
-int dbg_cs_links(dbg_ctx* ctx, const dbg_kmer_table* full_table, int stranded, uint64_t v0, uint64_t v1, void* d_nxt_local) {
-    if (!ctx) return DBG_E_BADARG;
-    NULLCHK(ctx, full_table);
-    cudaSetDevice(ctx->c.device);
-    return cs_links_dev(CTX(ctx), &full_table->t, stranded != 0, v0, v1, (u32*)d_nxt_local);
-}
-int dbg_cs_pack(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_nxt_full, void* d_rec16) {
-    if (!ctx) return DBG_E_BADARG;
-    NULLCHK(ctx, full_table);
-    cudaSetDevice(ctx->c.device);
-    return cs_pack_dev(CTX(ctx), &full_table->t, (const u32*)d_nxt_full, (uint4*)d_rec16);
-}
-int dbg_cs_discover(dbg_ctx* ctx, const void* d_rec16, uint64_t n_total, uint64_t v0, uint64_t v1, uint32_t lmax, void* d_pkey,
-                    void* d_pval, uint64_t capacity, uint64_t* n_paths, uint64_t* n_kmers_covered) {
-    if (!ctx || !n_paths || !n_kmers_covered) return DBG_E_BADARG;
-    cudaSetDevice(ctx->c.device);
-    u64 np = 0, nc = 0;
-    int rc = cs_discover_dev(CTX(ctx), (const uint4*)d_rec16, n_total, v0, v1, lmax, (u64*)d_pkey, (u32*)d_pval, capacity, &np, &nc);
-    *n_paths = np; *n_kmers_covered = nc;
-    return rc;
-}
-int dbg_cs_layout(dbg_ctx* ctx, int k, uint64_t n_total, uint64_t n_nodes, void* d_pkey_a, void* d_pval_a, void* d_pkey_b,
-                  void* d_pval_b, int* which, void* d_start, void* d_length, uint64_t* n_bases) {
-    if (!ctx || !n_bases || !which) return DBG_E_BADARG;
-    cudaSetDevice(ctx->c.device);
-    u64 nb = 0;
-    int rc = cs_layout_dev(CTX(ctx), k, n_total, n_nodes, (u64*)d_pkey_a, (u32*)d_pval_a, (u64*)d_pkey_b, (u32*)d_pval_b, which,
-                           (u64*)d_start, (u32*)d_length, &nb);
-    *n_bases = nb;
-    return rc;
-}
-int dbg_cs_sort_paths(dbg_ctx* ctx, uint64_t n_paths, void* d_pkey_a, void* d_pval_a, void* d_pkey_b, void* d_pval_b, int* which) {
-    if (!ctx || !which) return DBG_E_BADARG;
-    cudaSetDevice(ctx->c.device);
-    return cs_sort_paths_dev(CTX(ctx), n_paths, (u64*)d_pkey_a, (u32*)d_pval_a, (u64*)d_pkey_b, (u32*)d_pval_b, which);
-}
-int dbg_cs_emit(dbg_ctx* ctx, const dbg_kmer_table* full_table, const void* d_rec16, const void* d_pkey_sorted,
-                const void* d_pval_sorted, const void* d_start_local, uint64_t n_paths, uint64_t node0, uint64_t base0,
-                int reduce_op, void* d_words, void* d_exts, void* d_data, void* d_out_start, void* d_out_length) {
-    if (!ctx) return DBG_E_BADARG;
-    NULLCHK(ctx, full_table);
-    if (reduce_op < 0 || reduce_op > 3) DBG_SET_ERR(CTX(ctx), DBG_E_BADARG, "unknown reduce_op %d", reduce_op);
-    cudaSetDevice(ctx->c.device);
-    return cs_emit_dev(CTX(ctx), &full_table->t, (const uint4*)d_rec16, (const u64*)d_pkey_sorted, (const u32*)d_pval_sorted,
-                       (const u64*)d_start_local, n_paths, node0, base0, reduce_op, (u64*)d_words, (u8*)d_exts, (u16*)d_data,
-                       (u64*)d_out_start, (u32*)d_out_length);
-}
 int dbg_graph_from_device(dbg_ctx* ctx, int k, int stranded, uint64_t n_nodes, uint64_t n_bases, const void* d_words,
                           const void* d_start, const void* d_length, const void* d_exts, const void* d_data,
                           dbg_graph** out) {
@@ -859,6 +887,86 @@ int dbg_graph_copy_out(const dbg_graph* h, uint64_t* words, uint64_t* start, uin
         if (data) CU(c, cudaMemcpyAsync(data, g->data, g->n_nodes * 2, cudaMemcpyDeviceToHost, c->stream));
     }
     return sync(c);
+}
+
+// bincode 1.x (fixed-width little-endian integers, u64 sequence lengths) image of the crate's serde-derived BaseGraph<K, u16>:
+//   sequences.sequence.storage: Vec<u64> | sequences.sequence.len: usize | sequences.start: Vec<usize> | sequences.length: Vec<u32>
+//   | exts: Vec<Exts{val: u8}> | data: Vec<u16> | stranded: bool | phantom: PhantomData<K> (no bytes)
+// (field order: src/graph.rs:43-50, src/dna_string.rs:72-76, 762-767, src/lib.rs:577-580)
+static u64 graph_bincode_size(const Graph* g) {
+    return 8 + g->n_words * 8 + 8 + 8 + g->n_nodes * 8 + 8 + g->n_nodes * 4 + 8 + g->n_nodes + 8 + g->n_nodes * 2 + 1;
+}
+int dbg_graph_serialize(const dbg_graph* h, uint8_t* out, uint64_t cap, uint64_t* n_bytes) {
+    if (!h || !n_bytes) return DBG_E_BADARG;
+    const Graph* g = &h->g;
+    Ctx* c = g->ctx;
+    const u64 need = graph_bincode_size(g);
+    *n_bytes = need;
+    if (!out || cap < need) return DBG_OK;   // size query
+    cudaSetDevice(c->device);
+    u8* q = out;
+    auto put64 = [&](u64 v) { memcpy(q, &v, 8); q += 8; };
+    const u64 m = g->n_nodes;
+    put64(g->n_words);
+    u8* p_words = q; q += g->n_words * 8;
+    put64(g->n_bases);
+    put64(m);
+    u8* p_start = q; q += m * 8;
+    put64(m);
+    u8* p_len = q; q += m * 4;
+    put64(m);
+    u8* p_exts = q; q += m;
+    put64(m);
+    u8* p_data = q; q += m * 2;
+    *q++ = g->stranded ? 1 : 0;
+    if (m) {
+        if (g->n_words) CU(c, cudaMemcpyAsync(p_words, g->words, g->n_words * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(p_start, g->start, m * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(p_len, g->length, m * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(p_exts, g->exts, m, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(p_data, g->data, m * 2, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return sync(c);
+}
+int dbg_graph_deserialize(dbg_ctx* ctx, int k, const uint8_t* bytes, uint64_t n_bytes, dbg_graph** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    Ctx* c = CTX(ctx);
+    *out = nullptr;
+    if (!bytes || k < 2 || k > 64) DBG_SET_ERR(c, DBG_E_BADARG, "null buffer or k outside [2,64]");
+    cudaSetDevice(c->device);
+    const u8* q = bytes;
+    const u8* end = bytes + n_bytes;
+    bool bad = false;
+    auto get64 = [&]() -> u64 { if ((u64)(end - q) < 8) { bad = true; return 0; } u64 v; memcpy(&v, q, 8); q += 8; return v; };
+    auto skip = [&](u64 n, u64 es) -> const u8* { if (bad || n > (u64)(end - q) / es) { bad = true; return q; } const u8* r = q; q += n * es; return r; };
+    const u64 nw = get64();
+    const u8* p_words = skip(nw, 8);
+    const u64 nb = get64();
+    const u64 m1 = get64(); const u8* p_start = skip(m1, 8);
+    const u64 m2 = get64(); const u8* p_len = skip(m2, 4);
+    const u64 m3 = get64(); const u8* p_exts = skip(m3, 1);
+    const u64 m4 = get64(); const u8* p_data = skip(m4, 2);
+    if (bad || end - q < 1) DBG_SET_ERR(c, DBG_E_BADARG, "truncated BaseGraph image");
+    const int stranded = *q++ != 0;
+    if (m1 != m2 || m1 != m3 || m1 != m4 || nw != (nb + 31) / 32) DBG_SET_ERR(c, DBG_E_BADARG, "inconsistent BaseGraph image");
+    // stage through device buffers and adopt them (graph_from_device_dev copies device -> device)
+    DBuf<u64> dw, ds;
+    DBuf<u32> dl;
+    DBuf<u8> de;
+    DBuf<u16> dd;
+    TRY(dw.alloc_pool(c, nw + 1)); TRY(ds.alloc_pool(c, m1 + 1)); TRY(dl.alloc_pool(c, m1 + 1)); TRY(de.alloc_pool(c, m1 + 1)); TRY(dd.alloc_pool(c, m1 + 1));
+    if (nw) CU(c, cudaMemcpyAsync(dw.p, p_words, nw * 8, cudaMemcpyHostToDevice, c->stream));
+    if (m1) {
+        CU(c, cudaMemcpyAsync(ds.p, p_start, m1 * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(dl.p, p_len, m1 * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(de.p, p_exts, m1, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(dd.p, p_data, m1 * 2, cudaMemcpyHostToDevice, c->stream));
+    }
+    TRY(sync(c));   // the source buffer is the caller's
+    Graph* g = nullptr;
+    TRY(graph_from_device_dev(c, k, stranded, m1, nb, dw.p, ds.p, dl.p, de.p, dd.p, &g));
+    *out = reinterpret_cast<dbg_graph*>(g);
+    return DBG_OK;
 }
 
 int dbg_graph_edges(dbg_ctx* ctx, const dbg_graph* graph, uint32_t* target, uint8_t* flags) {
@@ -941,6 +1049,38 @@ int dbg_msp_kmer_buckets(dbg_ctx* ctx, int k, int p, const dbg_seqset* seqs, int
     if (n_out && !out_bucket) DBG_SET_ERR(CTX(ctx), DBG_E_BADARG, "null output");
     cudaSetDevice(ctx->c.device);
     return msp_kmer_buckets_dev(CTX(ctx), k, p, &seqs->s, stranded != 0, out_bucket, n_out);
+}
+
+int dbg_msp_sequence(dbg_ctx* ctx, int k, int p, const dbg_seqset* seqs, int rc, const uint32_t* permutation, uint64_t cap,
+                     uint64_t* n_intervals, uint32_t* seq, uint32_t* start, uint32_t* len, uint32_t* bucket, uint8_t* exts) {
+    if (!ctx || !n_intervals) return DBG_E_BADARG;
+    NULLCHK(ctx, seqs);
+    cudaSetDevice(ctx->c.device);
+    u64 n = 0;
+    int rcode = msp_sequence_dev(CTX(ctx), k, p, &seqs->s, rc != 0, permutation, cap, &n, seq, start, len, bucket, exts);
+    *n_intervals = n;
+    return rcode;
+}
+
+int dbg_filter_kmers_colorset(dbg_ctx* ctx, int k, const dbg_seqset* seqs, const uint8_t* labels, uint32_t min_kmer_obs, int stranded,
+                              uint64_t memory_size_gb, dbg_kmer_table** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    *out = nullptr;
+    NULLCHK(ctx, seqs);
+    cudaSetDevice(ctx->c.device);
+    Table* t = nullptr;
+    int rc = filter_kmers_colorset_dev(CTX(ctx), k, &seqs->s, labels, min_kmer_obs, stranded, memory_size_gb, &t);
+    if (rc == DBG_OK) *out = reinterpret_cast<dbg_kmer_table*>(t);
+    return rc;
+}
+int dbg_table_colorsets(const dbg_kmer_table* h, uint64_t* masks) {
+    if (!h || !masks) return DBG_E_BADARG;
+    const Table* t = &h->t;
+    Ctx* c = t->ctx;
+    if (!t->colors && t->n) DBG_SET_ERR(c, DBG_E_BADARG, "the table was not built by dbg_filter_kmers_colorset");
+    cudaSetDevice(c->device);
+    if (t->n) CU(c, cudaMemcpyAsync(masks, t->colors, t->n * 8, cudaMemcpyDeviceToHost, c->stream));
+    return sync(c);
 }
 
 }  // extern "C"

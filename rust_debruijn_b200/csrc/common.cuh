@@ -222,6 +222,7 @@ struct Table {
     u16* counts = nullptr;
     u64* all_lo = nullptr;
     u64* all_hi = nullptr;
+    u64* colors = nullptr;  // CountFilterSet only: bit c = label c was observed for the k-mer
 };
 
 struct Graph {
@@ -275,25 +276,19 @@ int radix_sort_pairs(Ctx* c, int W, int key_bits, u64 n, u64* lo_a, u64* hi_a, u
 int filter_kmers_dev(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded, int report_all, u64 mem_gb,
                      Table** out);
 int compress_dev(Ctx* c, const Table* t, int stranded, int reduce_op, Graph** out);
+int filter_kmers_colorset_dev(Ctx* c, int k, const SeqSet* s, const u8* h_labels, u32 min_obs, int stranded, u64 mem_gb, Table** out);
 void plan_filter(const Ctx* c, int k, u64 N, int* p_out, int* bbits_out);
 int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int bbits, Partition** out);
 void free_partition(Partition* P);
-int cs_links_dev(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u32* d_nxt_out);
 int graph_edges_dev(Ctx* c, const Graph* g, u32* h_target, u8* h_flags);
 int graph_fix_exts_dev(Ctx* c, Graph* g, const u8* h_valid_nodes);
 int graph_is_compressed_dev(Ctx* c, const Graph* g, int scmap, long long* pair_out);
 int remove_censored_exts_dev(Ctx* c, Table* t, int stranded, int sharded);
 int table_prefix_hist_dev(Ctx* c, const Table* t, int bits, u32* d_hist);
-int cs_pack_dev(Ctx* c, const Table* t, const u32* d_nxt_full, uint4* d_rec16);
-int cs_discover_dev(Ctx* c, const uint4* d_rec16, u64 V, u64 v0, u64 v1, u32 lmax, u64* d_pkey, u32* d_pval, u64 cap, u64* n_paths,
-                    u64* n_covered);
-int cs_layout_dev(Ctx* c, int k, u64 V, u64 m, u64* pkey_a, u32* pval_a, u64* pkey_b, u32* pval_b, int* which, u64* d_start,
-                  u32* d_length, u64* n_bases);
-int cs_sort_paths_dev(Ctx* c, u64 m, u64* pkey_a, u32* pval_a, u64* pkey_b, u32* pval_b, int* which);
-int cs_emit_dev(Ctx* c, const Table* t, const uint4* d_rec16, const u64* d_pkey, const u32* d_pval, const u64* d_start, u64 m,
-                u64 node0, u64 base0, int reduce_op, u64* d_words, u8* d_exts, u16* d_data, u64* d_out_start, u32* d_out_length);
 int graph_from_device_dev(Ctx* c, int k, int stranded, u64 n_nodes, u64 n_bases, const u64* d_words, const u64* d_start,
                           const u32* d_length, const u8* d_exts, const u16* d_data, Graph** out);
+int msp_sequence_dev(Ctx* c, int k, int p, const SeqSet* s, int rc, const u32* h_perm, u64 cap, u64* n_out, u32* h_seq, u32* h_start,
+                     u32* h_len, u32* h_bucket, u8* h_exts);
 int msp_kmer_buckets_dev(Ctx* c, int k, int p, const SeqSet* s, int stranded, u32* h_out, u64 n_out);
 int filter_from_records_dev(Ctx* c, int k, const u64* d_records, u64 n_records, const u32* h_counts, u32 n_src, u32 n_local,
                             u64 n_input_total, u32 min_obs, int stranded, int report_all, Table** out);

@@ -807,65 +807,6 @@ static int compress_impl(Ctx* c, const Table* t, int stranded, int reduce_op, Gr
 }
 
 // ================================================================================================
-// Sharded compression (multi-GPU): the sorted table is replicated, the WORK is split by k-mer
-// index range / node range, with the same kernels as the single-GPU fast path.
-//   cs_links     links of the rank's own k-mer range [v0, v1)                (caller all-gathers the link pairs)
-//   cs_pack      16-byte walk records of the whole table from the gathered links      (replicated, streaming)
-//   cs_discover  path records of the unitigs whose LEFT end lies in [v0, v1)         (caller all-gathers them)
-//   cs_layout    node order = ascending seed: sort, lengths, offsets                  (replicated, M entries only)
-//   cs_emit      the rank walks the nodes [i0, i1) and writes bases / Exts / data into zeroed full-size arrays
-//                (caller all-reduces: every word has exactly one writer per bit, so sum == OR)
-// Only components reachable by end walks (<= lmax k-mers) are handled; cs_discover reports how many k-mers that
-// covered and the caller falls back to the replicated single-GPU compression otherwise.
-// ================================================================================================
-template <int W>
-__global__ void cs_pack_kernel(KP kp, const u64* __restrict__ lo, const u64* __restrict__ hi, const u8* __restrict__ exts,
-                               const u16* __restrict__ counts, const uint2* __restrict__ nxt, u64 n, uint4* __restrict__ rec16) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Kmer<W> key = load_key<W>(lo, hi, i);
-    uint2 l = nxt[i];
-    u32 meta = (u32)counts[i] | ((u32)exts[i] << 16) | (Ops<W>::first_base(kp, key) << 24) | (Ops<W>::last_base(kp, key) << 26);
-    rec16[i] = make_uint4(l.x, l.y, meta, 0u);
-}
-
-template <int W>
-static int cs_links_impl(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u32* d_nxt_out) {
-    cudaStream_t st = c->stream;
-    KP kp = make_kp(t->k);
-    const u64 V = t->n;
-    TRY(arena_begin(c));
-    int lb = 8;
-    while ((1ull << (lb + 4)) <= V && lb < 24) lb++;
-    if (lb > 2 * t->k) lb = 2 * t->k;
-    const int lut_shift = 2 * t->k - lb;
-    const u64 n_pfx = 1ull << lb;
-    DBuf<u32> lut_cnt;
-    DBuf<u64> lut, ctr;
-    TRY(lut_cnt.alloc(c, n_pfx)); TRY(lut.alloc(c, n_pfx + 1)); TRY(ctr.alloc(c, 4));
-    TRY(lut_cnt.zero()); TRY(ctr.zero());
-    lut_hist_kernel<W><<<grid_for(V, 256), 256, 0, st>>>(t->lo, t->hi, V, lut_shift, lut_cnt.p);
-    TRY(check_launch(c, "lut_hist"));
-    TRY(exclusive_scan_u32_to_u64(c, lut_cnt.p, lut.p, n_pfx, lut.p + n_pfx));
-    if (v1 > v0) {
-        links_kernel<W><<<grid_for(v1 - v0, 256), 256, 0, st>>>(kp, t->lo, t->hi, t->exts, v0, v1 - v0, lut.p, lut_shift, stranded,
-                                                                d_nxt_out, (u32*)(ctr.p + 3), nullptr, t->counts, 0);
-        TRY(check_launch(c, "links"));
-    }
-    u64 h[4];
-    TRY(read_u64(c, ctr.p, h, 4));
-    if (h[3] == 1) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extension points at a k-mer with no extension back (src/compression.rs:428-434)");
-    if (h[3] == 2) DBG_SET_ERR(c, DBG_E_INCONSISTENT_EXTS, "k-mer extensions are not reciprocal");
-    return DBG_OK;
-}
-
-int cs_links_dev(Ctx* c, const Table* t, int stranded, u64 v0, u64 v1, u32* d_nxt_out) {
-    if (!t || v1 < v0 || v1 > t->n) DBG_SET_ERR(c, DBG_E_BADARG, "bad k-mer range");
-    if (t->n >= (1ull << 31)) DBG_SET_ERR(c, DBG_E_BADARG, "k-mer table too large for 32-bit port states");
-    return t->k <= 32 ? cs_links_impl<1>(c, t, stranded, v0, v1, d_nxt_out) : cs_links_impl<2>(c, t, stranded, v0, v1, d_nxt_out);
-}
-
-// ================================================================================================
 // filter::remove_censored_exts / remove_censored_exts_sharded (src/filter.rs:238-306), SURVEY §8f N2: drop the
 // extension bits of every valid k-mer that point at a k-mer which is not valid (plain variant), or which is not
 // valid but was seen in this shard, i.e. is in all_kmers (sharded variant: extensions into other shards are
@@ -1124,91 +1065,6 @@ int table_prefix_hist_dev(Ctx* c, const Table* t, int bits, u32* d_hist) {
     if (t->k <= 32) lut_hist_kernel<1><<<grid_for(t->n, 256), 256, 0, c->stream>>>(t->lo, t->hi, t->n, shift, d_hist);
     else lut_hist_kernel<2><<<grid_for(t->n, 256), 256, 0, c->stream>>>(t->lo, t->hi, t->n, shift, d_hist);
     return check_launch(c, "lut_hist");
-}
-
-static int cs_key_shift(u64 V) {
-    int bits_v = 1;
-    while ((1ull << bits_v) < V) bits_v++;
-    return 64 - bits_v;
-}
-
-int cs_pack_dev(Ctx* c, const Table* t, const u32* d_nxt_full, uint4* d_rec16) {
-    if (!t) DBG_SET_ERR(c, DBG_E_BADARG, "null table");
-    if (!t->n) return DBG_OK;
-    KP kp = make_kp(t->k);
-    if (t->k <= 32) cs_pack_kernel<1><<<grid_for(t->n, 256), 256, 0, c->stream>>>(kp, t->lo, t->hi, t->exts, t->counts, (const uint2*)d_nxt_full, t->n, d_rec16);
-    else cs_pack_kernel<2><<<grid_for(t->n, 256), 256, 0, c->stream>>>(kp, t->lo, t->hi, t->exts, t->counts, (const uint2*)d_nxt_full, t->n, d_rec16);
-    return check_launch(c, "cs_pack");
-}
-
-int cs_discover_dev(Ctx* c, const uint4* d_rec16, u64 V, u64 v0, u64 v1, u32 lmax, u64* d_pkey, u32* d_pval, u64 cap,
-                    u64* n_paths, u64* n_covered) {
-    if (v1 < v0 || v1 > V) DBG_SET_ERR(c, DBG_E_BADARG, "bad k-mer range");
-    TRY(arena_begin(c));
-    DBuf<u64> ctr;
-    TRY(ctr.alloc(c, 2));
-    TRY(ctr.zero());
-    if (v1 > v0) {
-        discover_kernel<<<grid_for(v1 - v0, 256), 256, 0, c->stream>>>(d_rec16, v0, v1 - v0, lmax, cs_key_shift(V), d_pkey, d_pval, cap, ctr.p);
-        TRY(check_launch(c, "discover"));
-    }
-    u64 h[2];
-    TRY(read_u64(c, ctr.p, h, 2));
-    if (h[0] > cap) DBG_SET_ERR(c, DBG_E_BADARG, "path buffer too small (%llu > %llu)", (unsigned long long)h[0], (unsigned long long)cap);
-    *n_paths = h[0];
-    *n_covered = h[1];
-    return DBG_OK;
-}
-
-// In: m path records (pkey_a, pval_a) in any order; scratch (pkey_b, pval_b) of the same size.  Out: *which = 0 / 1 says
-// which pair holds the records sorted by seed; d_start[m] (u64 base offsets), d_length[m] (u32), *n_bases.
-int cs_layout_dev(Ctx* c, int k, u64 V, u64 m, u64* pkey_a, u32* pval_a, u64* pkey_b, u32* pval_b, int* which, u64* d_start,
-                  u32* d_length, u64* n_bases) {
-    *n_bases = 0;
-    *which = 0;
-    if (m == 0) return DBG_OK;
-    TRY(arena_begin(c));
-    cudaStream_t st = c->stream;
-    u64 *rk, *rh;
-    u32* rv;
-    TRY(radix_sort_pairs(c, 1, 64, m, pkey_a, nullptr, pval_a, pkey_b, nullptr, pval_b, &rk, &rh, &rv));
-    *which = rk == pkey_a ? 0 : 1;
-    DBuf<u64> nl64, tot;
-    TRY(nl64.alloc(c, m)); TRY(tot.alloc(c, 1));
-    path_len_kernel<<<grid_for(m, 256), 256, 0, st>>>(rk, m, cs_key_shift(V), k, nl64.p, d_length);
-    TRY(check_launch(c, "path_len"));
-    TRY(exclusive_scan_u64(c, nl64.p, d_start, m, tot.p));
-    TRY(read_u64(c, tot.p, n_bases));
-    return DBG_OK;
-}
-
-// sort path records by seed only (pre-sort before they are shipped to the rank owning the seed range)
-int cs_sort_paths_dev(Ctx* c, u64 m, u64* pkey_a, u32* pval_a, u64* pkey_b, u32* pval_b, int* which) {
-    *which = 0;
-    if (m <= 1) return DBG_OK;
-    TRY(arena_begin(c));
-    u64 *rk, *rh;
-    u32* rv;
-    TRY(radix_sort_pairs(c, 1, 64, m, pkey_a, nullptr, pval_a, pkey_b, nullptr, pval_b, &rk, &rh, &rv));
-    *which = rk == pkey_a ? 0 : 1;
-    return DBG_OK;
-}
-
-// The m path records (sorted by seed, local offsets in d_start) become nodes node0 .. node0 + m of the graph, their
-// bases starting at base0 + d_start[i]: words / exts / data / start / length are written at the GLOBAL positions of
-// full-size arrays (zeroed by the caller, all-reduced afterwards).
-int cs_emit_dev(Ctx* c, const Table* t, const uint4* d_rec16, const u64* d_pkey, const u32* d_pval, const u64* d_start, u64 m,
-                u64 node0, u64 base0, int reduce_op, u64* d_words, u8* d_exts, u16* d_data, u64* d_out_start, u32* d_out_length) {
-    if (m == 0) return DBG_OK;
-    KP kp = make_kp(t->k);
-    EmitWalkArgs ea;
-    ea.lo = t->lo; ea.hi = t->hi; ea.rec = d_rec16; ea.pkey = d_pkey; ea.pval = d_pval; ea.node_start = d_start;
-    ea.i0 = 0; ea.n_nodes = m; ea.key_shift = cs_key_shift(t->n); ea.out0 = node0; ea.base0 = base0;
-    ea.words = d_words; ea.out_exts = d_exts; ea.out_data = d_data; ea.reduce_op = reduce_op;
-    ea.out_start = d_out_start; ea.out_length = d_out_length;
-    if (t->k <= 32) emit_walk_kernel<1><<<grid_for(m, 128), 128, 0, c->stream>>>(kp, ea);
-    else emit_walk_kernel<2><<<grid_for(m, 128), 128, 0, c->stream>>>(kp, ea);
-    return check_launch(c, "emit_walk");
 }
 
 // Adopt caller-owned device arrays (copied) as a BaseGraph handle.

@@ -2177,4 +2177,277 @@ int msp_kmer_buckets_dev(Ctx* c, int k, int p, const SeqSet* s, int stranded, u3
     return sync(c);
 }
 
+// ------------------------------------------------------------------------------------------------
+// msp::msp_sequence (src/msp.rs:279-324): the MSP INTERVALS of every sequence exactly as Scanner::scan (:207-276) cuts
+// them — boundaries depend on which occurrence of the minimizer the scan is holding (ties: find_min keeps the largest
+// position, MinPos::cmp :127-140; an entering p-mer replaces the held one only when STRICTLY smaller, :244-246), i.e. on
+// scan history, so one thread replays the scan of one sequence.  Two launches: count, then write at scanned offsets.
+// Reads are short; a genome-long sequence would serialise on its thread (the per-k-mer bucket of dbg_msp_kmer_buckets is
+// the history-free form the partition kernels use).
+// ------------------------------------------------------------------------------------------------
+struct MspSeqArgs {
+    const u64* words; u64 n_words; const u64* start; const u32* length; u32 uniform_len; u64 n_seqs;
+    int k, p, rc; const u32* perm;
+    const u64* off;   // nullptr: count pass (cnt[i] = intervals of sequence i)
+    u32* cnt; u32* o_seq; u32* o_start; u32* o_len; u32* o_bucket; u8* o_exts;
+};
+__device__ __forceinline__ u32 msp_pmer_at(const MspSeqArgs& a, u64 st, u32 pos) {   // p-mer starting at base pos of the sequence
+    const u64 b = st + pos;
+    const u64 wi = b >> 5;
+    const int sh = (int)(b & 31) * 2;
+    const u64 h = wi < a.n_words ? a.words[wi] : 0, l = (wi + 1) < a.n_words ? a.words[wi + 1] : 0;
+    const u64 v = sh ? (h << sh) | (l >> (64 - sh)) : h;
+    return (u32)(v >> (64 - 2 * a.p));
+}
+__device__ __forceinline__ u32 msp_score(const MspSeqArgs& a, u32 x) {   // msp.rs:305-311
+    u32 v = a.perm ? a.perm[x] : x;
+    if (a.rc) {
+        const u32 r = (~rev2_32(x)) >> (32 - 2 * a.p);
+        const u32 vr = a.perm ? a.perm[r] : r;
+        v = v < vr ? v : vr;
+    }
+    return v;
+}
+__global__ void msp_sequence_kernel(MspSeqArgs a) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_seqs) return;
+    const u32 m = a.uniform_len ? a.uniform_len : a.length[i];
+    const u64 st = a.uniform_len ? i * (u64)a.uniform_len : a.start[i];
+    const int k = a.k, p = a.p;
+    if (m < (u32)k) { if (!a.off) a.cnt[i] = 0; return; }   // msp.rs:294-296
+    u64 o = a.off ? a.off[i] : 0;
+    u32 n_iv = 0;
+    // held minimizer
+    u32 mpos = 0, mval = 0, mkmer = 0;
+    auto find_min = [&](u32 lo, u32 hi) {   // msp.rs:218-228: ties -> the LARGEST position
+        mpos = lo; mkmer = msp_pmer_at(a, st, lo); mval = msp_score(a, mkmer);
+        for (u32 q = lo + 1; q <= hi; q++) {
+            const u32 x = msp_pmer_at(a, st, q), v = msp_score(a, x);
+            if (v <= mval) { mval = v; mpos = q; mkmer = x; }
+        }
+    };
+    auto emit = [&](u32 s0, u32 len, u32 kmer) {
+        if (a.off) {
+            const u32 r = (~rev2_32(kmer)) >> (32 - 2 * p);
+            a.o_seq[o] = (u32)i; a.o_start[o] = s0; a.o_len[o] = len;
+            a.o_bucket[o] = kmer < r ? kmer : r;                                          // MspIntervalP::bucket, msp.rs:115-117
+            const u32 le = s0 > 0 ? 1u << base_at(a.words, st + s0 - 1) : 0u;             // Exts::from_slice_bounds, lib.rs:645-660
+            const u32 re = s0 + len < m ? 1u << base_at(a.words, st + s0 + len) : 0u;
+            a.o_exts[o] = (u8)((re << 4) | le);
+            o++;
+        }
+        n_iv++;
+    };
+    find_min(0, (u32)(k - p));
+    u32 cur_start = 0, cur_kmer = mkmer;
+    for (u32 j = 1; j + k <= m; j++) {
+        const u32 epos = j + (u32)(k - p);               // end_pos always corresponds to j + k - p (msp.rs:238-239)
+        bool fresh = false;
+        if (j > mpos) { find_min(j, epos); fresh = true; }                                    // the minimizer left the window (:241-243)
+        else {
+            const u32 x = msp_pmer_at(a, st, epos), v = msp_score(a, x);
+            if (v < mval) { mval = v; mpos = epos; mkmer = x; fresh = true; }                 // strictly smaller p-mer entered (:244-246)
+        }
+        if (fresh) {
+            emit(cur_start, j + (u32)k - 1 - cur_start, cur_kmer);                            // :253-263
+            cur_start = j; cur_kmer = mkmer;
+        }
+    }
+    emit(cur_start, m - cur_start, cur_kmer);                                                 // :266-273
+    if (!a.off) a.cnt[i] = n_iv;
+}
+
+int msp_sequence_dev(Ctx* c, int k, int p, const SeqSet* s, int rc, const u32* h_perm, u64 cap, u64* n_out, u32* h_seq, u32* h_start,
+                     u32* h_len, u32* h_bucket, u8* h_exts) {
+    if (p < 1 || p > 16 || p > k || k < 2) DBG_SET_ERR(c, DBG_E_BADARG, "need 1 <= p <= min(k, 16), k >= 2");
+    if (h_perm && p > 12) DBG_SET_ERR(c, DBG_E_BADARG, "a permutation table is supported up to p = 12 (4^p entries)");
+    *n_out = 0;
+    if (!s->n_seqs) return DBG_OK;
+    TRY(arena_begin(c));
+    cudaStream_t st = c->stream;
+    DBuf<u32> cnt, perm;
+    DBuf<u64> off, tot;
+    TRY(cnt.alloc(c, s->n_seqs)); TRY(off.alloc(c, s->n_seqs)); TRY(tot.alloc(c, 1));
+    if (h_perm) {
+        TRY(perm.alloc(c, 1ull << (2 * p)));
+        CU(c, cudaMemcpyAsync(perm.p, h_perm, sizeof(u32) << (2 * p), cudaMemcpyHostToDevice, st));
+    }
+    MspSeqArgs a;
+    a.words = s->words; a.n_words = s->n_words; a.start = s->start; a.length = s->length; a.uniform_len = s->uniform_len; a.n_seqs = s->n_seqs;
+    a.k = k; a.p = p; a.rc = rc; a.perm = h_perm ? perm.p : nullptr;
+    a.off = nullptr; a.cnt = cnt.p; a.o_seq = a.o_start = a.o_len = a.o_bucket = nullptr; a.o_exts = nullptr;
+    msp_sequence_kernel<<<grid_for(s->n_seqs, 128), 128, 0, st>>>(a);
+    TRY(check_launch(c, "msp_sequence_count"));
+    TRY(exclusive_scan_u32_to_u64(c, cnt.p, off.p, s->n_seqs, tot.p));
+    u64 total = 0;
+    TRY(read_u64(c, tot.p, &total));
+    *n_out = total;
+    if (cap < total || !total) return DBG_OK;   // size query (or nothing to write)
+    if (!h_seq || !h_start || !h_len || !h_bucket || !h_exts) DBG_SET_ERR(c, DBG_E_BADARG, "null output array");
+    DBuf<u32> d_seq, d_start, d_len, d_bucket;
+    DBuf<u8> d_exts;
+    TRY(d_seq.alloc(c, total)); TRY(d_start.alloc(c, total)); TRY(d_len.alloc(c, total)); TRY(d_bucket.alloc(c, total)); TRY(d_exts.alloc(c, total));
+    a.off = off.p; a.o_seq = d_seq.p; a.o_start = d_start.p; a.o_len = d_len.p; a.o_bucket = d_bucket.p; a.o_exts = d_exts.p;
+    msp_sequence_kernel<<<grid_for(s->n_seqs, 128), 128, 0, st>>>(a);
+    TRY(check_launch(c, "msp_sequence"));
+    CU(c, cudaMemcpyAsync(h_seq, d_seq.p, total * 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(h_start, d_start.p, total * 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(h_len, d_len.p, total * 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(h_bucket, d_bucket.p, total * 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(h_exts, d_exts.p, total, cudaMemcpyDeviceToHost, st));
+    return sync(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CountFilterSet<u8> (src/filter.rs:68-101): per k-mer the SORTED, DEDUPLICATED set of the data values (labels / colours, one
+// per input sequence) of its observations; valid iff the number of observations >= min_kmer_obs.  Labels < 64, so the set
+// is a 64-bit mask (bit c = label c seen) — exactly the information of the reference's Vec<u8> after sort() + dedup().
+// Built from the CountFilter path: sequences are grouped by label, every group is counted on its own (CountFilter(1): all its
+// distinct k-mers with Exts and per-label counts), the per-label tables are concatenated, sorted by k-mer and reduced per
+// k-mer (Exts OR, counts summed, label bits OR).  A per-label count saturates at 65535 like every CountFilter count, so
+// thresholds above 65535 are not supported here.
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_subset_kernel(const u64* __restrict__ start, const u32* __restrict__ length, const u8* __restrict__ exts, u32 uniform_len,
+                                     const u32* __restrict__ idx, u64 n, u64* __restrict__ o_start, u32* __restrict__ o_length, u8* __restrict__ o_exts) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 j = idx[i];
+    o_start[i] = uniform_len ? (u64)j * uniform_len : start[j];
+    o_length[i] = uniform_len ? uniform_len : length[j];
+    if (o_exts) o_exts[i] = exts[j];
+}
+__global__ void pack_label_vals_kernel(const u8* __restrict__ exts, const u16* __restrict__ counts, u32 label, u64 n, u32* __restrict__ val) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) val[i] = (u32)exts[i] | ((u32)counts[i] << 8) | (label << 24);
+}
+// thread at the head of every run of equal keys reduces the run (<= 64 entries: one per label)
+template <int W>
+__global__ void colorset_reduce_kernel(const u64* __restrict__ lo, const u64* __restrict__ hi, const u32* __restrict__ val, u64 n, u32 min_obs,
+                                       const u64* __restrict__ pos /* nullptr: flag pass */, u32* __restrict__ flag, u64* __restrict__ o_lo,
+                                       u64* __restrict__ o_hi, u8* __restrict__ o_exts, u16* __restrict__ o_counts, u64* __restrict__ o_colors) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool head = i == 0 || lo[i] != lo[i - 1] || (W == 2 && hi[i] != hi[i - 1]);
+    if (!head) { if (!pos) flag[i] = 0; return; }
+    u32 e = 0;
+    u64 nobs = 0, colors = 0;
+    for (u64 j = i; j < n && lo[j] == lo[i] && (W == 1 || hi[j] == hi[i]); j++) {
+        const u32 v = val[j];
+        e |= v & 0xffu;
+        nobs += (v >> 8) & 0xffffu;
+        colors |= 1ull << (v >> 24);
+    }
+    const bool valid = nobs >= min_obs;
+    if (!pos) { flag[i] = valid ? 1u : 0u; return; }
+    if (!valid) return;
+    const u64 o = pos[i];
+    o_lo[o] = lo[i];
+    if (W == 2) o_hi[o] = hi[i];
+    o_exts[o] = (u8)e;
+    o_counts[o] = (u16)(nobs > 65535 ? 65535 : nobs);
+    o_colors[o] = colors;
+}
+
+template <int W>
+static int colorset_merge(Ctx* c, int k, std::vector<Table*>& parts, const std::vector<u32>& labels, u32 min_obs, Table* t) {
+    cudaStream_t st = c->stream;
+    u64 total = 0;
+    for (Table* p : parts) total += p->n;
+    t->n = 0;
+    if (!total) return DBG_OK;
+    TRY(arena_begin(c));
+    DBuf<u64> a_lo, a_hi, b_lo, b_hi, pos, tot;
+    DBuf<u32> a_v, b_v, flag;
+    TRY(a_lo.alloc(c, total)); TRY(b_lo.alloc(c, total)); TRY(a_v.alloc(c, total)); TRY(b_v.alloc(c, total));
+    if (W == 2) { TRY(a_hi.alloc(c, total)); TRY(b_hi.alloc(c, total)); }
+    u64 off = 0;
+    for (size_t q = 0; q < parts.size(); q++) {
+        Table* p = parts[q];
+        if (!p->n) continue;
+        CU(c, cudaMemcpyAsync(a_lo.p + off, p->lo, p->n * 8, cudaMemcpyDeviceToDevice, st));
+        if (W == 2) CU(c, cudaMemcpyAsync(a_hi.p + off, p->hi, p->n * 8, cudaMemcpyDeviceToDevice, st));
+        pack_label_vals_kernel<<<grid_for(p->n, 256), 256, 0, st>>>(p->exts, p->counts, labels[q], p->n, a_v.p + off);
+        TRY(check_launch(c, "pack_label_vals"));
+        off += p->n;
+    }
+    u64 *rlo, *rhi;
+    u32* rv;
+    TRY(radix_sort_pairs(c, W, 2 * k, total, a_lo.p, a_hi.p, a_v.p, b_lo.p, b_hi.p, b_v.p, &rlo, &rhi, &rv));
+    TRY(flag.alloc(c, total)); TRY(pos.alloc(c, total)); TRY(tot.alloc(c, 1));
+    colorset_reduce_kernel<W><<<grid_for(total, 256), 256, 0, st>>>(rlo, rhi, rv, total, min_obs, nullptr, flag.p, nullptr, nullptr, nullptr, nullptr, nullptr);
+    TRY(check_launch(c, "colorset_flag"));
+    TRY(exclusive_scan_u32_to_u64(c, flag.p, pos.p, total, tot.p));
+    u64 V = 0;
+    TRY(read_u64(c, tot.p, &V));
+    t->n = V;
+    if (!V) return DBG_OK;
+    DBuf<u64> o_lo, o_hi, o_col;
+    DBuf<u8> o_e;
+    DBuf<u16> o_c;
+    TRY(o_lo.alloc_pool(c, V)); TRY(o_col.alloc_pool(c, V)); TRY(o_e.alloc_pool(c, V)); TRY(o_c.alloc_pool(c, V));
+    if (W == 2) TRY(o_hi.alloc_pool(c, V));
+    colorset_reduce_kernel<W><<<grid_for(total, 256), 256, 0, st>>>(rlo, rhi, rv, total, min_obs, pos.p, nullptr, o_lo.p, o_hi.p, o_e.p, o_c.p, o_col.p);
+    TRY(check_launch(c, "colorset_reduce"));
+    TRY(sync(c));
+    t->lo = o_lo.take(); if (W == 2) t->hi = o_hi.take();
+    t->exts = o_e.take(); t->counts = o_c.take(); t->colors = o_col.take();
+    return DBG_OK;
+}
+
+int filter_kmers_colorset_dev(Ctx* c, int k, const SeqSet* s, const u8* h_labels, u32 min_obs, int stranded, u64 mem_gb, Table** out) {
+    *out = nullptr;
+    if (k < 4 || k > 64) DBG_SET_ERR(c, DBG_E_BADARG, "k=%d outside [4,64]", k);
+    if (!s || (s->n_seqs && !h_labels)) DBG_SET_ERR(c, DBG_E_BADARG, "null argument");
+    if (min_obs > 65535) DBG_SET_ERR(c, DBG_E_BADARG, "CountFilterSet thresholds above 65535 are not supported (per-label counts saturate)");
+    if (s->n_seqs >= (1ull << 32)) DBG_SET_ERR(c, DBG_E_BADARG, "too many sequences");
+    std::vector<std::vector<u32>> groups(64);
+    for (u64 i = 0; i < s->n_seqs; i++) {
+        if (h_labels[i] >= 64) DBG_SET_ERR(c, DBG_E_BADARG, "label %u of sequence %llu: labels must be < 64", (unsigned)h_labels[i], (unsigned long long)i);
+        groups[h_labels[i]].push_back((u32)i);
+    }
+    SeqSet* sm = const_cast<SeqSet*>(s);
+    TRY(seqset_ready(c, sm));
+    std::vector<Table*> parts;
+    std::vector<u32> labels;
+    auto cleanup = [&]() { for (Table* p : parts) free_table(p); };
+    u64 n_input = 0;
+    for (u32 lab = 0; lab < 64; lab++) {
+        const std::vector<u32>& g = groups[lab];
+        if (g.empty()) continue;
+        DBuf<u32> d_idx, d_len;
+        DBuf<u64> d_start;
+        DBuf<u8> d_exts;
+        int rc = d_idx.alloc_pool(c, g.size());
+        if (rc == DBG_OK) rc = d_len.alloc_pool(c, g.size());
+        if (rc == DBG_OK) rc = d_start.alloc_pool(c, g.size());
+        if (rc == DBG_OK && s->seq_exts) rc = d_exts.alloc_pool(c, g.size());
+        if (rc != DBG_OK) { cleanup(); return rc; }
+        cudaMemcpyAsync(d_idx.p, g.data(), g.size() * 4, cudaMemcpyHostToDevice, c->stream);
+        gather_subset_kernel<<<grid_for(g.size(), 256), 256, 0, c->stream>>>(s->start, s->length, s->seq_exts, s->uniform_len, d_idx.p, g.size(),
+                                                                             d_start.p, d_len.p, s->seq_exts ? d_exts.p : nullptr);
+        rc = check_launch(c, "gather_subset");
+        if (rc == DBG_OK) rc = sync(c);   // g.data() is host memory
+        if (rc != DBG_OK) { cleanup(); return rc; }
+        SeqSet sub;
+        memset(sub.pend_ev, 0, sizeof(sub.pend_ev));
+        sub.ctx = c; sub.words = s->words; sub.n_words = s->n_words; sub.start = d_start.p; sub.length = d_len.p;
+        sub.seq_exts = s->seq_exts ? d_exts.p : nullptr; sub.n_seqs = g.size(); sub.uniform_len = 0;
+        sub.max_len = s->uniform_len ? s->uniform_len : s->max_len; sub.contiguous = false; sub.owned = false;
+        Table* tp = nullptr;
+        rc = filter_kmers_dev(c, k, &sub, 1, stranded, 0, mem_gb, &tp);   // CountFilter(1): every distinct k-mer of this label
+        if (rc != DBG_OK) { cleanup(); return rc; }
+        n_input += tp->n_input;
+        parts.push_back(tp);
+        labels.push_back(lab);
+    }
+    Table* t = &(new dbg_kmer_table())->t;
+    t->ctx = c; t->k = k; t->n_input = n_input;
+    int rc = k <= 32 ? colorset_merge<1>(c, k, parts, labels, min_obs, t) : colorset_merge<2>(c, k, parts, labels, min_obs, t);
+    cleanup();
+    if (rc != DBG_OK) { free_table(t); return rc; }
+    c->stats.n_valid = t->n; c->stats.n_input_kmers = n_input;
+    *out = t;
+    return DBG_OK;
+}
+
 }  // namespace dbg

@@ -86,3 +86,33 @@ def assert_graphs_equal(a, b):
     assert a["n_nodes"] == b["n_nodes"] and a["n_bases"] == b["n_bases"], (a["n_nodes"], b["n_nodes"], a["n_bases"], b["n_bases"])
     for f in ("words", "start", "length", "exts", "data"):
         assert np.array_equal(a[f], b[f]), f"graph field {f} differs"
+
+
+def brute_filter_colorset(orc, k, seqs, labels, min_obs, stranded=False, seq_exts=None):
+    """filter_kmers with CountFilterSet<u8> (src/filter.rs:68-101, 138-231) by brute force over python ints: returns ascending
+    lists (kmers, exts, label sets) of the valid k-mers.  KmerExtsIter (lib.rs:812-841), min_rc_flip (:224-231), Exts::rc (:746)."""
+    L = orc.lib()
+    acc = {}
+    mask = (1 << (2 * k)) - 1
+    for si, (sq, lab) in enumerate(zip(seqs, labels)):
+        n = len(sq)
+        sx = int(seq_exts[si]) if seq_exts is not None else 0
+        x = 0
+        for i, b in enumerate(sq):
+            x = ((x << 2) | int(b)) & mask
+            if i < k - 1:
+                continue
+            j = i - k + 1
+            left = (sx & 0xf) if j == 0 else 1 << int(sq[j - 1])
+            right = ((sx >> 4) & 0xf) if j == n - k else 1 << int(sq[j + k])
+            e = left | (right << 4)
+            r = rc_int(x, k)
+            key = x
+            if not stranded and not x < r:
+                key, e = r, L.orc_exts_rc(e)
+            a = acc.setdefault(key, [0, 0, set()])
+            a[0] += 1
+            a[1] |= e
+            a[2].add(int(lab))
+    keys = sorted(kk for kk, a in acc.items() if a[0] >= min_obs)
+    return keys, [acc[kk][1] for kk in keys], [sorted(acc[kk][2]) for kk in keys], [min(acc[kk][0], 65535) for kk in keys]

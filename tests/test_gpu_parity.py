@@ -7,8 +7,8 @@ import os
 import numpy as np
 import pytest
 
-from helpers import (assert_graphs_equal, assert_tables_equal, enc, random_contigs, random_dna, simple_random_contigs,
-                     small_k_contigs)
+from helpers import (assert_graphs_equal, assert_tables_equal, brute_filter_colorset, enc, random_contigs, random_dna,
+                     simple_random_contigs, small_k_contigs)
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -461,6 +461,101 @@ def test_msp_kmer_buckets_match_scanner(D, ctx, orc, k, p):
                 per[int(st):int(st) + int(ln) - k + 1] = int(b)
             exp.append(per)
         assert np.array_equal(got, np.concatenate(exp))
+
+
+@pytest.mark.parametrize("k,p", [(31, 6), (31, 8), (35, 5), (63, 12), (16, 5)])
+def test_msp_sequence_intervals_match_scanner(D, ctx, orc, k, p):
+    """dbg_msp_sequence vs the oracle's Scanner::scan + msp_sequence (src/msp.rs:207-324): same intervals (start, len), buckets
+    and boundary Exts in scan order — identity permutation and a random one, rc = true / false, low-complexity sequences with
+    tied minimizers (the history-dependent case), sequences shorter than k."""
+    rng = np.random.default_rng(k * 13 + p)
+    seqs = [random_dna(rng, int(rng.integers(k, 6 * k))) for _ in range(20)] + \
+           [np.zeros(3 * k, np.uint8), np.tile(np.array([0, 1], np.uint8), 2 * k), random_dna(rng, k - 1), random_dna(rng, k),
+            rng.integers(0, 2, size=5 * k).astype(np.uint8)]
+    ss = D.SeqSet.upload(ctx, *orc.seqset_from_lists(seqs))
+    perms = [None] + ([rng.permutation(4 ** p).astype(np.uint32)] if p <= 8 else [])
+    for perm in perms:
+        for rc in (True, False):
+            got = D.msp_sequence(ss, k, p, permutation=perm, rc=rc)
+            exp = {f: [] for f in ("seq", "start", "len", "bucket", "exts")}
+            for si, sq in enumerate(seqs):
+                if len(sq) < k:
+                    continue
+                iv = orc.msp_scan(k, p, sq, perm=None if perm is None else perm.astype(np.uint64), rc=rc)
+                exp["seq"] += [si] * len(iv["start"])
+                for f in ("start", "len", "bucket", "exts"):
+                    exp[f] += [int(x) for x in iv[f]]
+            for f in exp:
+                assert np.array_equal(got[f].astype(np.int64), np.array(exp[f], np.int64)), (f, perm is None, rc)
+    # uniform-length reads through the fixed-length layout
+    w, s_, l = orc.synth_reads(500, 1, orc.ERR_THR_NOISY)
+    got = D.msp_sequence(D.SeqSet.upload(ctx, w, s_, l), 31, 8)
+    n_exp = sum(len(orc.msp_scan(31, 8, orc.unpack_bases(w, 150 * i, 150))["start"]) for i in range(500))
+    assert len(got["start"]) == n_exp and int(got["len"].max()) <= 2 * 31 - 8
+
+
+def test_from_ascii_hashn_on_device(D, ctx, orc):
+    """dbg_seqset_from_ascii_hashn vs the oracle's restatement of DnaString::from_acgt_bytes_hashn (src/dna_string.rs:254-278)."""
+    rng = np.random.default_rng(17)
+    alpha = np.frombuffer(b"ACGTacgtNnRYKMSW-.", np.uint8)
+    seqs = [bytes(rng.choice(alpha, size=n)) for n in (0, 1, 31, 32, 33, 150, 150, 4097, 64)]
+    names = [("read:%d/%d" % (i, i * 7919)).encode() + b"x" * (i % 9) for i in range(len(seqs))]
+    ss = D.SeqSet.from_ascii_hashn(ctx, seqs, names)
+    ow, ost, oln, obad = orc.from_acgt_bytes_hashn(seqs, names)
+    w, s_, l = ss.copy_out()
+    assert np.array_equal(w, ow) and np.array_equal(s_, ost) and np.array_equal(l, oln) and ss.n_invalid == obad
+    # and the graph built from it equals the oracle's on the same packed bases
+    t, g = run_both(D, ctx, orc, 15, (ow, ost, oln), 1)
+    assert g["n_nodes"] > 0
+
+
+def test_bincode_image_round_trip(D, ctx, orc):
+    """dbg_graph_serialize / dbg_graph_deserialize: the bincode image of BaseGraph<K, u16> equals the oracle's (hand-checked layout,
+    tests/test_oracle.py::test_bincode_image_layout) and reads back to the same arrays."""
+    for k, stranded in ((31, False), (63, False), (32, True)):
+        ss = orc.synth_reads(2000, 1, orc.ERR_THR_NOISY)
+        table, _ = D.filter_kmers(ss, D.CountFilter(2), stranded, False, 4, k=k, ctx=ctx)
+        g = D.compress_kmers_with_hash(stranded, D.SimpleCompress(D.SAT_ADD), table)
+        img = g.to_bincode()
+        h = g.to_host()
+        assert img == orc.graph_to_bincode(h)
+        g2 = D.BaseGraph.from_bincode(img, k, ctx=ctx)
+        assert_graphs_equal(g2.to_host(), h)
+        assert g2.stranded == stranded
+    e = np.zeros(0, np.uint64)
+    table, _ = D.filter_kmers((e, e, np.zeros(0, np.uint32)), D.CountFilter(1), False, False, 4, k=31, ctx=ctx)
+    g0 = D.compress_kmers_with_hash(False, D.SimpleCompress(), table)
+    assert len(D.BaseGraph.from_bincode(g0.to_bincode(), 31, ctx=ctx)) == 0
+    with pytest.raises(D.DbgError):
+        D.BaseGraph.from_bincode(img[:-5], 31, ctx=ctx)
+
+
+@pytest.mark.parametrize("k,stranded", [(31, False), (63, False), (12, True), (32, False)])
+def test_count_filter_set(D, ctx, orc, k, stranded):
+    """filter_kmers with CountFilterSet<u8> (src/filter.rs:68-101): valid k-mers, Exts and per-k-mer label sets against a
+    brute-force restatement — shared k-mers across labels, a label with a single sequence, thresholds 1..3, sequence-level Exts."""
+    rng = np.random.default_rng(500 + k + stranded)
+    base = [random_dna(rng, int(rng.integers(k + 5, 6 * k))) for _ in range(6)]
+    seqs, labels = [], []
+    for rep in range(14):   # overlapping fragments of the same contigs under different labels
+        c = base[int(rng.integers(0, len(base)))]
+        a = int(rng.integers(0, max(1, len(c) - k - 2)))
+        seqs.append(c[a:a + int(rng.integers(k, len(c) - a + 1))])
+        labels.append(int(rng.choice([0, 1, 5, 63])))
+    seqs.append(random_dna(rng, k - 1)); labels.append(7)          # shorter than k: contributes nothing
+    seqs.append(base[0]); labels.append(17)                        # a label used once
+    sx = rng.integers(0, 256, size=len(seqs)).astype(np.uint8)
+    w, st, ln = orc.seqset_from_lists(seqs)
+    for mo in (1, 2, 3):
+        table, _ = D.filter_kmers((w, st, ln, sx), D.CountFilterSet(mo), stranded, False, 4, k=k, ctx=ctx, labels=labels)
+        t = table.to_host()
+        keys, exts, sets, nobs = brute_filter_colorset(orc, k, seqs, labels, mo, stranded=stranded, seq_exts=sx)
+        got = [int(lo) | ((int(hi) << 64) if k > 32 else 0) for lo, hi in zip(t["lo"], t["hi"] if k > 32 else t["lo"])]
+        assert got == keys
+        assert [int(x) for x in t["exts"]] == exts and [int(x) for x in t["counts"]] == nobs
+        assert table.colorsets() == sets
+        # the table feeds compress_kmers like any other (ScmapCompress joins k-mers of equal data; here: the counts)
+        assert len(D.compress_kmers_with_hash(stranded, D.SimpleCompress(D.MAX), table)) > 0
 
 
 def _run_tool(args, timeout=900):

@@ -471,3 +471,56 @@ def test_widened_rows_golden(orc):
     # one number here IS independently anchored: SURVEY.md §4 (second, independent restatement made during the survey) found
     # 68 nodes for synth-v1 noisy R=1000, K=31 after remove_censored_exts semantics (896 without pruning, Appendix B)
     assert want[0]["pruned_nodes"] == 68 and want[0]["n_valid"] == 3584
+
+
+def test_siphash13_matches_cpython_and_the_library(orc):
+    """The SipHash-1-3 behind from_acgt_bytes_hashn (Rust's DefaultHasher, zero key) is pinned twice: the oracle's plain-Python
+    version and the library's C version (dbg_siphash13, host code: no GPU needed) both equal CPython's bytes hash under
+    PYTHONHASHSEED=0 (CPython >= 3.11 uses SipHash-1-3 and an all-zero key when randomisation is off)."""
+    import ctypes as C
+    import subprocess
+    import sys
+
+    from rust_debruijn_b200 import _lib
+    rng = np.random.default_rng(4)
+    msgs = [b"", b"a", b"read/1", b"01234567", b"0123456789abcdef!"] + [bytes(rng.integers(0, 256, size=int(n), dtype=np.uint8)) for n in (3, 8, 15, 16, 31, 64, 200)]
+    code = "import sys; print([hash(bytes.fromhex(x)) & 0xffffffffffffffff for x in sys.argv[1:]])"
+    out = subprocess.run([sys.executable, "-c", code] + [m.hex() for m in msgs[1:]], capture_output=True, text=True,
+                         env={"PYTHONHASHSEED": "0", "PATH": "/usr/bin:/bin"}).stdout
+    ref = eval(out)
+    L = _lib.lib()
+    for m, r in zip(msgs[1:], ref):
+        mine = orc.siphash13(m)
+        if r != (-2) & 0xffffffffffffffff:   # CPython maps the value -1 to -2
+            assert mine == r, m
+        buf = np.frombuffer(m, np.uint8)
+        assert L.dbg_siphash13(buf.ctypes.data_as(C.c_void_p), len(m)) == mine
+    assert L.dbg_siphash13(None, 0) == orc.siphash13(b"")
+
+
+def test_from_acgt_bytes_hashn_oracle(orc):
+    """ACGT positions are untouched, non-ACGT ones are repeatable, depend on the read name and the position, and cover 0..3."""
+    seqs = [b"ACGTNNNNacgtRYKM" * 8, b"NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN", b"ACGT"]
+    names = [b"read_1", b"read_2", b"x"]
+    w, s, l, bad = orc.from_acgt_bytes_hashn(seqs, names)
+    w2, _, _, bad2 = orc.from_acgt_bytes_hashn(seqs, names)
+    assert np.array_equal(w, w2) and bad == bad2 == 8 * 8 + 40
+    plain = orc.from_acgt_bytes(seqs)[0]
+    b_h, b_p = orc.unpack_bases(w, 0, int(l.sum())), orc.unpack_bases(plain, 0, int(l.sum()))
+    ok = np.concatenate([orc.acgt_to_bits(x)[1] for x in seqs])
+    assert np.array_equal(b_h[ok], b_p[ok]) and set(b_h[~ok].tolist()) == {0, 1, 2, 3}
+    w3 = orc.from_acgt_bytes_hashn(seqs, [b"read_9", b"read_2", b"x"])[0]
+    assert not np.array_equal(w, w3)
+
+
+def test_bincode_image_layout(orc):
+    """Hand-derived bytes of a two-node BaseGraph in bincode 1.x's default encoding (serde field order of the crate)."""
+    g = dict(words=np.array([0x1b00000000000000], np.uint64), n_bases=7, start=np.array([0, 4], np.uint64), length=np.array([4, 3], np.uint32),
+             exts=np.array([0x12, 0x80], np.uint8), data=np.array([5, 65535], np.uint16), stranded=True)
+    img = orc.graph_to_bincode(g)
+    exp = (b"\x01" + b"\0" * 7 + bytes.fromhex("000000000000001b") + b"\x07" + b"\0" * 7 +
+           b"\x02" + b"\0" * 7 + b"\0" * 8 + b"\x04" + b"\0" * 7 +
+           b"\x02" + b"\0" * 7 + b"\x04\0\0\0\x03\0\0\0" +
+           b"\x02" + b"\0" * 7 + b"\x12\x80" +
+           b"\x02" + b"\0" * 7 + b"\x05\x00\xff\xff" + b"\x01")
+    assert img == exp
