@@ -190,6 +190,17 @@ int dbg_graph_fix_exts(dbg_ctx* ctx, dbg_graph* graph, const uint8_t* valid_node
  * (src/test.rs:248-254, 266-274): *pair_out = -1 when no two nodes could be collapsed, else (node << 32) | next_node for the FIRST
  * pair in the reference's iteration order.  scmap_join_test != 0: spec.join_test = data equality (ScmapCompress), else always true. */
 int dbg_graph_is_compressed(dbg_ctx* ctx, const dbg_graph* graph, int scmap_join_test, int64_t* pair_out);
+/* BaseGraph::combine — src/graph.rs:71-100: the nodes of every graph re-added in order (bases re-packed contiguously, Exts and data
+ * concatenated).  Graphs of one K; mixing stranded and unstranded graphs (a panic there, :90-92) returns DBG_E_BADARG. */
+int dbg_graph_combine(dbg_ctx* ctx, const dbg_graph* const* graphs, uint32_t n_graphs, dbg_graph** out);
+/* compression::compress_graph — src/compression.rs:291-349 (CompressFromGraph :100-287): fix_exts(Some(available)) on a copy of the
+ * Exts, merge every unbranched run of available nodes (censor_nodes: host array of node ids that are not available, may be NULL),
+ * finish + fix_exts(None).  `stranded` is the function's own argument (palindrome rule, flag of the result); links are resolved under
+ * the input graph's flag, as DebruijnGraph::find_link does.  Output nodes in the greedy loop's order: by the smallest node id of the
+ * run, that node forward, a cycle of nodes opened so that it ends on it.  reduce_op as for dbg_compress_kmers_with_hash.  A graph whose node links are not reciprocal (the
+ * greedy result would depend on the walk order) or that trips the reference's "unreachable" panic returns DBG_E_INCONSISTENT_EXTS. */
+int dbg_compress_graph(dbg_ctx* ctx, const dbg_graph* graph, int stranded, int reduce_op, const uint64_t* censor_nodes,
+                       uint64_t n_censor, dbg_graph** out);
 void dbg_graph_free(dbg_graph* g);
 
 /* ---- fused path: reads -> BaseGraph with the k-mer table kept device-resident ----------------------

@@ -77,6 +77,8 @@ def lib():
         L.orc_compress_kmers.restype = C.c_void_p
         L.orc_compress_kmers.argtypes = [C.c_int, C.c_uint64, u64p, u64p, u8p, u16p, C.c_int, C.c_int, u32p]
         L.orc_graph_error.argtypes = [C.c_void_p]
+        L.orc_compress_graph.restype = C.c_void_p
+        L.orc_compress_graph.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, u64p, u32p, u8p, u16p, u8p]
         for f in ("orc_graph_n_nodes", "orc_graph_n_bases"):
             getattr(L, f).restype = C.c_uint64
             getattr(L, f).argtypes = [C.c_void_p]
@@ -318,6 +320,58 @@ def compress_kmers(k, lo, hi, exts, counts, stranded=False, reduce_op=SAT_ADD, s
                      _p(g["exts"], C.c_uint8), _p(g["data"], C.c_uint16))
     L.orc_graph_free(h)
     return g
+
+
+def _graph_out(h, stranded):
+    L = lib()
+    err = L.orc_graph_error(h)
+    m, nb = L.orc_graph_n_nodes(h), L.orc_graph_n_bases(h)
+    g = dict(error=err, n_nodes=m, n_bases=nb, words=np.zeros((nb + 31) // 32, np.uint64), start=np.zeros(m, np.uint64),
+             length=np.zeros(m, np.uint32), exts=np.zeros(m, np.uint8), data=np.zeros(m, np.uint16), stranded=stranded)
+    L.orc_graph_copy(h, _p(g["words"], C.c_uint64), _p(g["start"], C.c_uint64), _p(g["length"], C.c_uint32),
+                     _p(g["exts"], C.c_uint8), _p(g["data"], C.c_uint16))
+    L.orc_graph_free(h)
+    return g
+
+
+def combine_graphs(graphs):
+    """BaseGraph::combine (src/graph.rs:71-100): the nodes of every graph appended in order (PackedDnaStringSet::add re-packs the
+    bases contiguously); mixing stranded and unstranded graphs panics there -> ValueError here."""
+    st = [bool(g["stranded"]) for g in graphs]
+    if any(st) and not all(st):
+        raise ValueError("attempted to combine stranded and unstranded graphs")
+    bases, start, length, pos = [], [], [], 0
+    for g in graphs:
+        for i in range(int(g["n_nodes"])):
+            n = int(g["length"][i])
+            bases.append(unpack_bases(g["words"], int(g["start"][i]), n))
+            start.append(pos)
+            length.append(n)
+            pos += n
+    allb = np.concatenate(bases) if bases else np.zeros(0, np.uint8)
+    return dict(error=0, n_nodes=len(start), n_bases=pos, words=pack_bases(allb), start=np.array(start, np.uint64),
+                length=np.array(length, np.uint32), exts=np.concatenate([np.asarray(g["exts"], np.uint8) for g in graphs]) if graphs else np.zeros(0, np.uint8),
+                data=np.concatenate([np.asarray(g["data"], np.uint16) for g in graphs]) if graphs else np.zeros(0, np.uint16),
+                stranded=all(st) if st else False)
+
+
+def compress_graph(k, g, stranded=False, reduce_op=SAT_ADD, censor_nodes=None):
+    """compression::compress_graph (src/compression.rs:291-349): fix_exts(Some(available)) -> greedy node walk in node order ->
+    finish + fix_exts(None).  censor_nodes: iterable of node ids.  Returns BaseGraph arrays (error: 1 "unreachable", 3 "No kmer")."""
+    L = lib()
+    m = int(g["n_nodes"])
+    words = np.ascontiguousarray(np.concatenate([g["words"], np.zeros(1, np.uint64)]), np.uint64)
+    start = np.ascontiguousarray(g["start"], np.uint64)
+    length = np.ascontiguousarray(g["length"], np.uint32)
+    exts = np.ascontiguousarray(g["exts"], np.uint8)
+    data = np.ascontiguousarray(g["data"], np.uint16)
+    censor = None
+    if censor_nodes is not None:
+        censor = np.zeros(m, np.uint8)
+        censor[np.asarray(list(censor_nodes), np.int64)] = 1
+    h = L.orc_compress_graph(k, int(stranded), reduce_op, m, _p(words, C.c_uint64), _p(start, C.c_uint64), _p(length, C.c_uint32),
+                             _p(exts, C.c_uint8), _p(data, C.c_uint16), _p(censor, C.c_uint8))
+    return _graph_out(h, stranded)
 
 
 def msp_scan(k, p, seq, perm=None, rc=True):

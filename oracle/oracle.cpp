@@ -651,6 +651,130 @@ static int64_t graph_is_compressed(int k, int stranded, uint64_t m, const uint64
     return -1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// compress_graph (CompressFromGraph) — src/compression.rs:100-349 ; BaseGraph::combine src/graph.rs:71-100 ;
+// sequence_of_path src/graph.rs:471-491 ; fix_exts / get_valid_exts src/graph.rs:337-377.  (rest)
+// The greedy node walk exactly as written: available_nodes BitSet, seeds in node order, Left walk then Right walk.
+// error: 1 = panic!("unreachable") :195, 3 = panic!("No kmer") :138, 4 = assert!(consistent) :165.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct GraphCompressor {
+    int k, stranded, op;
+    uint64_t m;
+    const uint64_t* words; const uint64_t* start; const uint32_t* length; const uint16_t* data;
+    std::vector<uint8_t> exts;          // old_graph's Exts after fix_exts(Some(&available_nodes))  :309
+    std::vector<uint8_t> avail;         // available_nodes  :298-307
+    NodeIndex<T> ix;                    // old_graph's left_order / right_order (BaseGraph::finish)
+    int error = 0;
+    struct Step { uint32_t node; int dir; };
+
+    GraphCompressor(int k_, int stranded_, int op_, uint64_t m_, const uint64_t* w, const uint64_t* st, const uint32_t* len,
+                    const uint8_t* e, const uint16_t* d, const uint8_t* censor /* one byte per node, may be null */)
+        : k(k_), stranded(stranded_), op(op_), m(m_), words(w), start(st), length(len), data(d), exts(e, e + m_), avail(m_, 1),
+          ix(k_, stranded_, m_, w, st, len) {
+        if (censor) for (uint64_t i = 0; i < m; i++) if (censor[i]) avail[i] = 0;
+        fix_exts(ix, exts, avail.data());
+    }
+    // DebruijnGraph::fix_exts — graph.rs:337-377: an extension survives iff find_link resolves it into a valid node
+    static void fix_exts(const NodeIndex<T>& ix, std::vector<uint8_t>& ex, const uint8_t* valid) {
+        const uint64_t m = ex.size();
+        std::vector<uint32_t> target(8 * m); std::vector<uint8_t> flags(8 * m);
+        ix.edges(ex.data(), m, target.data(), flags.data());
+        for (uint64_t n = 0; n < m; n++) {
+            uint8_t ne = 0;
+            for (int s = 0; s < 8; s++) {
+                uint32_t tg = target[n * 8 + s];
+                if (tg != 0xffffffffu && (!valid || valid[tg])) ne |= (uint8_t)(1u << s);
+            }
+            ex[n] = ne;
+        }
+    }
+    // try_extend_node — compression.rs:115-205.  true = Unique(next, next_dir_outgoing), false = Terminal(term)
+    bool try_extend_node(uint32_t node, int dir, uint32_t& next, int& next_out, uint8_t& term) {
+        const uint8_t e = exts[node];
+        if (exts_num_dir(e, dir) != 1 || (!stranded && length[node] == (uint32_t)k && ix.K.is_pal(ix.first[node]))) {   // :120-123
+            term = exts_single_dir(e, dir);
+            return false;
+        }
+        const int base = exts_unique(e, dir);                                                  // :126
+        const T end_kmer = dir ? ix.last[node] : ix.first[node];                                // term_kmer :127
+        const T next_kmer = dir ? ix.K.ext_right(end_kmer, (uint8_t)base) : ix.K.ext_left(end_kmer, (uint8_t)base);   // :129
+        uint32_t nid; int inc; bool rc;
+        if (!ix.find_link(next_kmer, dir, nid, inc, rc)) { error = 3; term = 0; return false; } // :130-140
+        const bool consistent = length[nid] == (uint32_t)k || (dir == LEFT && inc == RIGHT && !rc) || (dir == LEFT && inc == LEFT && rc) ||
+                                (dir == RIGHT && inc == LEFT && !rc) || (dir == RIGHT && inc == RIGHT && rc);   // :145-165
+        if (!consistent) { error = 4; term = 0; return false; }
+        if (!avail[nid] || (!stranded && ix.K.is_pal(next_kmer)) || (op == RED_SCMAP && data[node] != data[nid])) {   // :173-182
+            term = exts_single_dir(e, dir);
+            return false;
+        }
+        const int out = inc ^ 1;                                                               // next_side_outgoing :185
+        const int incoming_count = exts_num_dir(exts[nid], inc);                               // :187
+        if (incoming_count == 0) { error = 1; term = 0; return false; }                        // :190-195
+        if (incoming_count == 1) { next = nid; next_out = out; return true; }                  // :196-198
+        term = exts_single_dir(e, dir);                                                        // :199-203
+        return false;
+    }
+    // extend_node — :208-235
+    uint8_t extend_node(uint32_t start_node, int start_dir, std::vector<Step>& path) {
+        int cur_dir = start_dir;
+        uint32_t cur = start_node;
+        path.clear();
+        avail[start_node] = 0;
+        for (;;) {
+            uint32_t nx = 0; int out = 0; uint8_t term = 0;
+            if (try_extend_node(cur, cur_dir, nx, out, term)) {
+                path.push_back({nx, out ^ 1});   // (next_node, next_dir_incoming)
+                avail[nx] = 0;
+                cur = nx;
+                cur_dir = out;
+            } else {
+                return term;
+            }
+            if (error) return 0;
+        }
+    }
+    void push_node(GraphOut& g, uint32_t node, int dir, bool first, uint64_t& len) {            // sequence_of_path graph.rs:471-491
+        const uint32_t L = length[node];
+        for (uint32_t p = first ? 0 : (uint32_t)(k - 1); p < L; p++) {
+            uint8_t b = dir == LEFT ? dna_get(words, start[node] + p) : (uint8_t)(3 - dna_get(words, start[node] + (L - 1 - p)));
+            g.seq.push(b);
+            len++;
+        }
+    }
+    // build_node :240-287 + the loop of compress_graph :322-327
+    void run(GraphOut& g) {
+        std::vector<Step> l_path, r_path;
+        for (uint64_t seed = 0; seed < m; seed++) {
+            if (!avail[seed]) continue;
+            const uint8_t l_ext = extend_node((uint32_t)seed, LEFT, l_path);
+            if (error) { g.error = error; return; }
+            const uint8_t r_ext = extend_node((uint32_t)seed, RIGHT, r_path);
+            if (error) { g.error = error; return; }
+            uint16_t nd = data[seed];
+            std::deque<Step> node_path;
+            node_path.push_back({(uint32_t)seed, LEFT});
+            for (auto& s : l_path) { node_path.push_front({s.node, s.dir ^ 1}); nd = reduce_data(op, nd, data[s.node]); }
+            for (auto& s : r_path) { node_path.push_back({s.node, s.dir}); nd = reduce_data(op, nd, data[s.node]); }
+            uint8_t left_extend = l_ext, right_extend = r_ext;
+            if (!l_path.empty() && l_path.back().dir == LEFT) left_extend = exts_complement(l_ext);     // :266-270
+            if (!r_path.empty() && r_path.back().dir == RIGHT) right_extend = exts_complement(r_ext);   // :272-276
+            g.start.push_back(g.seq.len);
+            uint64_t len = 0;
+            bool first = true;
+            for (auto& s : node_path) { push_node(g, s.node, s.dir, first, len); first = false; }
+            g.length.push_back((uint32_t)len);
+            g.exts.push_back((uint8_t)((right_extend << 4) | (left_extend & 0xf)));
+            g.data.push_back(nd);
+        }
+        // graph.finish(); dbg.fix_exts(None)  :330-331
+        std::vector<uint64_t> w2(g.seq.storage);
+        w2.push_back(0);
+        NodeIndex<T> ix2(k, stranded, g.start.size(), w2.data(), g.start.data(), g.length.data());
+        fix_exts(ix2, g.exts, nullptr);
+    }
+};
+
 extern "C" {
 
 uint64_t orc_kmer_rc(int k, uint64_t x) { return KOps<uint64_t>(k).rc(x); }
@@ -742,6 +866,14 @@ void* orc_compress_kmers(int k, uint64_t n, const uint64_t* lo, const uint64_t* 
         Compressor<u128> c(k, stranded, reduce_op, km.data(), exts, counts, n);
         c.run(seed_order, *g);
     }
+    return g;
+}
+// compress_graph(stranded, spec, old_graph, censor_nodes): censor = one byte per node (non-zero = in censor_nodes) or null.
+void* orc_compress_graph(int k, int stranded, int reduce_op, uint64_t m, const uint64_t* words, const uint64_t* start,
+                         const uint32_t* length, const uint8_t* exts, const uint16_t* data, const uint8_t* censor) {
+    GraphOut* g = new GraphOut();
+    if (k <= 32) { GraphCompressor<uint64_t> c(k, stranded, reduce_op, m, words, start, length, exts, data, censor); c.run(*g); }
+    else { GraphCompressor<u128> c(k, stranded, reduce_op, m, words, start, length, exts, data, censor); c.run(*g); }
     return g;
 }
 int orc_graph_error(void* h) { return ((GraphOut*)h)->error; }

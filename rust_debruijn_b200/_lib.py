@@ -102,6 +102,8 @@ SIGNATURES = {
     "dbg_graph_edges": (C.c_int, [vp, vp, vp, vp]),
     "dbg_graph_fix_exts": (C.c_int, [vp, vp, vp]),
     "dbg_graph_is_compressed": (C.c_int, [vp, vp, C.c_int, C.POINTER(C.c_int64)]),
+    "dbg_graph_combine": (C.c_int, [vp, vp, C.c_uint32, vpp]),
+    "dbg_compress_graph": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_uint64, vpp]),
     "dbg_graph_free": (None, [vp]),
     "dbg_reads_to_graph": (C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_int, C.c_int, vpp, vpp]),
     "dbg_reads_to_graph_host": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_int,

@@ -352,6 +352,23 @@ class BaseGraph:
             self._host = g
         return self._host
 
+    @staticmethod
+    def combine(graphs):
+        """BaseGraph::combine (src/graph.rs:71-100): one graph holding the nodes of `graphs` in order."""
+        graphs = list(graphs)
+        if not graphs:
+            raise ValueError("combine needs at least one graph")
+        ctx = graphs[0].ctx
+        arr = (C.c_void_p * len(graphs))(*[g._h for g in graphs])
+        h = C.c_void_p()
+        ctx.check(ctx._L.dbg_graph_combine(ctx._h, arr, len(graphs), C.byref(h)))
+        return BaseGraph(ctx, h)
+
+    def finish(self):
+        """BaseGraph::finish (src/graph.rs:116-142).  The first/last-k-mer maps are rebuilt on the device by the calls that need them
+        (edges, fix_exts, is_compressed, compress_graph), so the DebruijnGraph is this object."""
+        return self
+
     def edges(self):
         """DebruijnGraph::find_edges for every (node, side) after BaseGraph::finish (src/graph.rs:116-142, 223-291):
         (target[M, 2, 4] uint32, 0xffffffff = none; flags[M, 2, 4] uint8: bit 0 incoming side, bit 1 rc)."""
@@ -394,6 +411,17 @@ class BaseGraph:
         h = C.c_void_p()
         ctx.check(ctx._L.dbg_graph_deserialize(ctx._h, k, _ptr(buf), len(buf), C.byref(h)))
         return BaseGraph(ctx, h)
+
+    @staticmethod
+    def from_host(g, k, ctx=None):
+        """A device BaseGraph from host arrays (dict with words / start / length / exts / data / stranded), through the bincode image."""
+        def vec(x, dt):
+            x = np.ascontiguousarray(x, dt)
+            return np.uint64(len(x)).tobytes() + x.tobytes()
+        nw = (int(g["n_bases"]) + 31) // 32
+        img = (vec(np.asarray(g["words"])[:nw], "<u8") + np.uint64(int(g["n_bases"])).tobytes() + vec(g["start"], "<u8") + vec(g["length"], "<u4") +
+               vec(g["exts"], "u1") + vec(g["data"], "<u2") + bytes([1 if g.get("stranded") else 0]))
+        return BaseGraph.from_bincode(img, k, ctx=ctx)
 
     def write_gfa(self, out):
         """DebruijnGraph::write_gfa (src/graph.rs:538-614): header, one S line per node, L lines for the left edges with
@@ -500,6 +528,19 @@ def compress_kmers_with_hash(stranded, spec, index):
     ctx = index.ctx
     h = C.c_void_p()
     ctx.check(ctx._L.dbg_compress_kmers_with_hash(ctx._h, index._h, int(bool(stranded)), spec.func, C.byref(h)))
+    return BaseGraph(ctx, h)
+
+
+def compress_graph(stranded, spec, old_graph, censor_nodes=None):
+    """compression::compress_graph (src/compression.rs:338-349): merge the unbranched runs of a (partially compressed) graph,
+    optionally leaving out `censor_nodes` (node ids).  Returns the new graph; old_graph is not modified."""
+    if not isinstance(spec, (SimpleCompress, ScmapCompress)):
+        raise TypeError("only SimpleCompress / ScmapCompress are on the accelerated path (SURVEY.md §8)")
+    ctx = old_graph.ctx
+    cn = None if censor_nodes is None else np.ascontiguousarray(np.asarray(list(censor_nodes), dtype=np.uint64))
+    h = C.c_void_p()
+    ctx.check(ctx._L.dbg_compress_graph(ctx._h, old_graph._h, int(bool(stranded)), spec.func, _ptr(cn) if cn is not None and len(cn) else None,
+                                        0 if cn is None else len(cn), C.byref(h)))
     return BaseGraph(ctx, h)
 
 

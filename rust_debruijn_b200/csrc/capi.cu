@@ -983,6 +983,35 @@ int dbg_graph_fix_exts(dbg_ctx* ctx, dbg_graph* graph, const uint8_t* valid_node
     return graph_fix_exts_dev(CTX(ctx), &graph->g, valid_nodes);
 }
 
+int dbg_graph_combine(dbg_ctx* ctx, const dbg_graph* const* graphs, uint32_t n_graphs, dbg_graph** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    *out = nullptr;
+    NULLCHK(ctx, graphs);
+    cudaSetDevice(ctx->c.device);
+    std::vector<const Graph*> gs(n_graphs);
+    for (uint32_t i = 0; i < n_graphs; i++) {
+        if (!graphs[i]) DBG_SET_ERR(CTX(ctx), DBG_E_BADARG, "graphs[%u] is null", i);
+        if (graphs[i]->g.ctx != CTX(ctx)) DBG_SET_ERR(CTX(ctx), DBG_E_BADARG, "graphs[%u] belongs to another context", i);
+        gs[i] = &graphs[i]->g;
+    }
+    Graph* g = nullptr;
+    int rc = graph_combine_dev(CTX(ctx), gs.data(), n_graphs, &g);
+    if (rc == DBG_OK) *out = reinterpret_cast<dbg_graph*>(g);
+    return rc;
+}
+
+int dbg_compress_graph(dbg_ctx* ctx, const dbg_graph* graph, int stranded, int reduce_op, const uint64_t* censor_nodes,
+                       uint64_t n_censor, dbg_graph** out) {
+    if (!ctx || !out) return DBG_E_BADARG;
+    *out = nullptr;
+    NULLCHK(ctx, graph);
+    cudaSetDevice(ctx->c.device);
+    Graph* g = nullptr;
+    int rc = compress_graph_dev(CTX(ctx), &graph->g, stranded, reduce_op, (const u64*)censor_nodes, n_censor, &g);
+    if (rc == DBG_OK) *out = reinterpret_cast<dbg_graph*>(g);
+    return rc;
+}
+
 int dbg_graph_is_compressed(dbg_ctx* ctx, const dbg_graph* graph, int scmap_join_test, int64_t* pair_out) {
     if (!ctx || !pair_out) return DBG_E_BADARG;
     NULLCHK(ctx, graph);

@@ -283,6 +283,8 @@ void free_partition(Partition* P);
 int graph_edges_dev(Ctx* c, const Graph* g, u32* h_target, u8* h_flags);
 int graph_fix_exts_dev(Ctx* c, Graph* g, const u8* h_valid_nodes);
 int graph_is_compressed_dev(Ctx* c, const Graph* g, int scmap, long long* pair_out);
+int graph_combine_dev(Ctx* c, const Graph* const* gs, u32 n, Graph** out);
+int compress_graph_dev(Ctx* c, const Graph* g, int stranded, int reduce_op, const u64* h_censor, u64 n_censor, Graph** out);
 int remove_censored_exts_dev(Ctx* c, Table* t, int stranded, int sharded);
 int table_prefix_hist_dev(Ctx* c, const Table* t, int bits, u32* d_hist);
 int graph_from_device_dev(Ctx* c, int k, int stranded, u64 n_nodes, u64 n_bases, const u64* d_words, const u64* d_start,

@@ -862,200 +862,6 @@ int remove_censored_exts_dev(Ctx* c, Table* t, int stranded, int sharded) {
     return t->k <= 32 ? censor_impl<1>(c, t, stranded, sharded) : censor_impl<2>(c, t, stranded, sharded);
 }
 
-// ================================================================================================
-// BaseGraph::finish + DebruijnGraph::find_edges / find_link for every (node, side) — src/graph.rs:116-142, 223-291
-// (SURVEY §8f N1).  left_order / right_order (BoomHashMap: first / last k-mer of a node -> node id) become two
-// sorted (k-mer, node) arrays searched through a prefix LUT; one thread per (node, side) tries its <= 4 extensions.
-// Output slot (node * 2 + side) * 4 + base: target node (0xffffffff = no such extension / link not in this graph),
-// flags bit 0 = incoming side (0 Left, 1 Right), bit 1 = rc flip.
-// ================================================================================================
-template <int W>
-__device__ __forceinline__ Kmer<W> kmer_at(const KP& kp, const u64* __restrict__ words, u64 b) {   // Vmer::get_kmer
-    const int K = kp.k;
-    Kmer<W> r;
-    if constexpr (W == 1) {
-        r.lo = bases64(words, b) >> (64 - 2 * K);
-    } else {
-        const u64 H = bases64(words, b), L = bases64(words, b + 32);
-        const int sh = 128 - 2 * K;   // 0..62
-        r.hi = sh ? H >> sh : H;
-        r.lo = sh ? (L >> sh) | (H << (64 - sh)) : L;
-    }
-    return r;
-}
-
-template <int W>
-__global__ void node_term_kmers_kernel(KP kp, const u64* __restrict__ words, const u64* __restrict__ start, const u32* __restrict__ length,
-                                       u64 m, u64* __restrict__ f_lo, u64* __restrict__ f_hi, u64* __restrict__ l_lo, u64* __restrict__ l_hi,
-                                       u32* __restrict__ id_a, u32* __restrict__ id_b) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const Kmer<W> f = kmer_at<W>(kp, words, start[i]);                         // first_kmer, lib.rs:369-371
-    const Kmer<W> l = kmer_at<W>(kp, words, start[i] + length[i] - kp.k);      // last_kmer, lib.rs:374-376
-    f_lo[i] = f.lo; l_lo[i] = l.lo;
-    if constexpr (W == 2) { f_hi[i] = f.hi; l_hi[i] = l.hi; }
-    id_a[i] = (u32)i; id_b[i] = (u32)i;
-}
-
-template <int W>
-struct EndMap { const u64* lo; const u64* hi; const u32* node; const u64* lut; int shift; };
-
-template <int W>
-__device__ __forceinline__ u32 endmap_find(const EndMap<W>& mp, Kmer<W> key) {
-    const u32 j = table_find<W>(mp.lo, mp.hi, mp.lut, mp.shift, key);
-    return j == NIL ? NIL : mp.node[j];
-}
-
-template <int W>
-__global__ void graph_edges_kernel(KP kp, const u64* __restrict__ words, const u64* __restrict__ start, const u32* __restrict__ length,
-                                   const u8* __restrict__ exts, u64 m, int stranded, EndMap<W> left, EndMap<W> right,
-                                   u32* __restrict__ target, u8* __restrict__ flags) {
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * m) return;
-    const u64 n = t >> 1;
-    const int dir = (int)(t & 1);
-    const Kmer<W> kmer = kmer_at<W>(kp, words, dir ? start[n] + length[n] - kp.k : start[n]);   // term_kmer
-    const u32 e = exts[n];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        u32 tg = NIL, fl = 0;
-        if ((e >> (4 * dir + i)) & 1u) {                                            // find_edges, graph.rs:229-239
-            const Kmer<W> x = dir ? Ops<W>::ext_right(kp, kmer, i) : Ops<W>::ext_left(kp, kmer, i);
-            // find_link, graph.rs:252-291: same strand through the opposite side, else (unstranded) the rc through the same side
-            tg = endmap_find<W>(dir ? left : right, x);
-            fl = dir ? 0u : 1u;
-            if (tg == NIL && !stranded) {
-                tg = endmap_find<W>(dir ? right : left, Ops<W>::rc(kp, x));
-                fl = (dir ? 1u : 0u) | 2u;
-            }
-            if (tg == NIL) fl = 0;
-        }
-        target[t * 4 + i] = tg;
-        flags[t * 4 + i] = (u8)fl;
-    }
-}
-
-// valid_nodes (optional, host, one byte per node): fix_exts' BitSet — links into nodes marked 0 do not count
-__global__ void fix_exts_kernel(const u32* __restrict__ target, const u8* __restrict__ valid_nodes, u64 m, u8* __restrict__ exts) {
-    const u64 n = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= m) return;
-    u32 e = 0;
-#pragma unroll
-    for (int s = 0; s < 8; s++) {   // slot (n * 2 + dir) * 4 + i  <->  Exts bit 4 * dir + i
-        const u32 tg = target[n * 8 + s];
-        if (tg != NIL && (!valid_nodes || valid_nodes[tg])) e |= 1u << s;
-    }
-    exts[n] = (u8)e;
-}
-
-// DebruijnGraph::is_compressed (graph.rs:296-334): thread per (node, dir); the FIRST collapsible pair in the reference's
-// iteration order (node ascending, Left before Right) wins through an atomicMin on ((node * 2 + dir) << 32 | next).
-template <int W>
-__global__ void is_compressed_kernel(KP kp, const u64* __restrict__ words, const u64* __restrict__ start, const u32* __restrict__ length,
-                                     const u16* __restrict__ data, const u32* __restrict__ target, const u8* __restrict__ flags, u64 m,
-                                     int stranded, int scmap, u64* __restrict__ result) {
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * m) return;
-    const u64 i = t >> 1;
-    const int dir = (int)(t & 1);
-    auto single = [&](u64 n, int d, u32& nxt, int& ret) {
-        int cnt = 0;
-        for (int b = 0; b < 4; b++) {
-            const u64 s = (n * 2 + d) * 4 + b;
-            if (target[s] != NIL) { cnt++; nxt = target[s]; ret = flags[s] & 1; }
-        }
-        return cnt == 1;
-    };
-    u32 nxt = 0, back = 0;
-    int ret = 0, r2 = 0;
-    if (!single(i, dir, nxt, ret)) return;                       // dir_edges.len() == 1
-    if (!single(nxt, ret, back, r2)) return;                     // ret_edges.len() == 1
-    if (length[i] == (u32)kp.k && is_palindrome<W>(kp, kmer_at<W>(kp, words, start[i]))) return;      // we are a palindrome
-    if (length[nxt] == (u32)kp.k && is_palindrome<W>(kp, kmer_at<W>(kp, words, start[nxt]))) return;  // the neighbour is
-    if (i == nxt) return;                                        // smooth circle biting its own tail
-    if (scmap && data[i] != data[nxt]) return;                   // spec.join_test (ScmapCompress: data equality)
-    atomicMin(result, (t << 32) | nxt);
-}
-
-// h_target / h_flags != nullptr: copy the adjacency out (dbg_graph_edges); fix == 1: rewrite the graph's Exts from it
-// (DebruijnGraph::fix_exts / get_valid_exts, graph.rs:337-377); fix == 2: is_compressed, *pair_out = -1 or (node << 32 | next)
-template <int W>
-static int graph_edges_impl(Ctx* c, Graph* g, u32* h_target, u8* h_flags, int fix, const u8* h_valid_nodes, int scmap = 0, long long* pair_out = nullptr) {
-    const u64 m = g->n_nodes;
-    if (pair_out) *pair_out = -1;
-    if (m == 0) return DBG_OK;
-    if (m >= (1ull << 31)) DBG_SET_ERR(c, DBG_E_BADARG, "too many nodes for 32-bit ids");
-    TRY(arena_begin(c));
-    cudaStream_t st = c->stream;
-    KP kp = make_kp(g->k);
-    DBuf<u64> fa_lo, fa_hi, fb_lo, fb_hi, la_lo, la_hi, lb_lo, lb_hi;
-    DBuf<u32> ia, ib, ja, jb, d_target;
-    DBuf<u8> d_flags;
-    TRY(fa_lo.alloc(c, m)); TRY(fb_lo.alloc(c, m)); TRY(la_lo.alloc(c, m)); TRY(lb_lo.alloc(c, m));
-    if (W == 2) { TRY(fa_hi.alloc(c, m)); TRY(fb_hi.alloc(c, m)); TRY(la_hi.alloc(c, m)); TRY(lb_hi.alloc(c, m)); }
-    TRY(ia.alloc(c, m)); TRY(ib.alloc(c, m)); TRY(ja.alloc(c, m)); TRY(jb.alloc(c, m));
-    TRY(d_target.alloc(c, 8 * m)); TRY(d_flags.alloc(c, 8 * m));
-    node_term_kmers_kernel<W><<<grid_for(m, 256), 256, 0, st>>>(kp, g->words, g->start, g->length, m, fa_lo.p, fa_hi.p, la_lo.p, la_hi.p, ia.p, ja.p);
-    TRY(check_launch(c, "node_term_kmers"));
-    u64 *flo, *fhi, *llo, *lhi;
-    u32 *fid, *lid;
-    TRY(radix_sort_pairs(c, W, 2 * g->k, m, fa_lo.p, fa_hi.p, ia.p, fb_lo.p, fb_hi.p, ib.p, &flo, &fhi, &fid));   // left_order
-    TRY(radix_sort_pairs(c, W, 2 * g->k, m, la_lo.p, la_hi.p, ja.p, lb_lo.p, lb_hi.p, jb.p, &llo, &lhi, &lid));   // right_order
-    DBuf<u32> cnt_l, cnt_r;
-    DBuf<u64> lut_l, lut_r;
-    EndMap<W> L, R;
-    L.lo = flo; L.hi = fhi; L.node = fid;
-    R.lo = llo; R.hi = lhi; R.node = lid;
-    TRY(build_prefix_lut<W>(c, g->k, flo, fhi, m, cnt_l, lut_l, &L.shift));
-    TRY(build_prefix_lut<W>(c, g->k, llo, lhi, m, cnt_r, lut_r, &R.shift));
-    L.lut = lut_l.p; R.lut = lut_r.p;
-    graph_edges_kernel<W><<<grid_for(2 * m, 256), 256, 0, st>>>(kp, g->words, g->start, g->length, g->exts, m, g->stranded, L, R,
-                                                                d_target.p, d_flags.p);
-    TRY(check_launch(c, "graph_edges"));
-    if (h_target) {
-        CU(c, cudaMemcpyAsync(h_target, d_target.p, 8 * m * sizeof(u32), cudaMemcpyDeviceToHost, st));
-        CU(c, cudaMemcpyAsync(h_flags, d_flags.p, 8 * m, cudaMemcpyDeviceToHost, st));
-    }
-    if (fix == 2) {
-        DBuf<u64> res;
-        TRY(res.alloc(c, 1));
-        TRY(res.fill_ff());
-        is_compressed_kernel<W><<<grid_for(2 * m, 256), 256, 0, st>>>(kp, g->words, g->start, g->length, g->data, d_target.p, d_flags.p, m,
-                                                                     g->stranded, scmap, res.p);
-        TRY(check_launch(c, "is_compressed"));
-        u64 h = 0;
-        TRY(read_u64(c, res.p, &h));
-        if (h != ~0ull) *pair_out = (long long)(((h >> 33) << 32) | (h & 0xffffffffull));
-        return DBG_OK;
-    }
-    if (fix) {
-        DBuf<u8> d_valid;
-        if (h_valid_nodes) {
-            TRY(d_valid.alloc(c, m));
-            CU(c, cudaMemcpyAsync(d_valid.p, h_valid_nodes, m, cudaMemcpyHostToDevice, st));
-        }
-        fix_exts_kernel<<<grid_for(m, 256), 256, 0, st>>>(d_target.p, h_valid_nodes ? d_valid.p : nullptr, m, g->exts);
-        TRY(check_launch(c, "fix_exts"));
-        return sync(c);
-    }
-    return sync(c);
-}
-
-int graph_edges_dev(Ctx* c, const Graph* g, u32* h_target, u8* h_flags) {
-    if (!g || !h_target || !h_flags) DBG_SET_ERR(c, DBG_E_BADARG, "null argument");
-    Graph* gm = const_cast<Graph*>(g);   // not modified when fix == 0
-    return g->k <= 32 ? graph_edges_impl<1>(c, gm, h_target, h_flags, 0, nullptr) : graph_edges_impl<2>(c, gm, h_target, h_flags, 0, nullptr);
-}
-int graph_is_compressed_dev(Ctx* c, const Graph* g, int scmap, long long* pair_out) {
-    if (!g || !pair_out) DBG_SET_ERR(c, DBG_E_BADARG, "null argument");
-    Graph* gm = const_cast<Graph*>(g);   // not modified
-    return g->k <= 32 ? graph_edges_impl<1>(c, gm, nullptr, nullptr, 2, nullptr, scmap, pair_out) : graph_edges_impl<2>(c, gm, nullptr, nullptr, 2, nullptr, scmap, pair_out);
-}
-int graph_fix_exts_dev(Ctx* c, Graph* g, const u8* h_valid_nodes) {
-    if (!g) DBG_SET_ERR(c, DBG_E_BADARG, "null graph");
-    return g->k <= 32 ? graph_edges_impl<1>(c, g, nullptr, nullptr, 1, h_valid_nodes) : graph_edges_impl<2>(c, g, nullptr, nullptr, 1, h_valid_nodes);
-}
-
 // histogram of the top `bits` bits of the (ascending) keys: 2^bits u32 counters, zeroed here
 int table_prefix_hist_dev(Ctx* c, const Table* t, int bits, u32* d_hist) {
     if (!t || bits < 1 || bits > 24 || bits > 2 * t->k) DBG_SET_ERR(c, DBG_E_BADARG, "bad prefix width %d", bits);

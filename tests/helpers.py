@@ -116,3 +116,36 @@ def brute_filter_colorset(orc, k, seqs, labels, min_obs, stranded=False, seq_ext
             a[2].add(int(lab))
     keys = sorted(kk for kk, a in acc.items() if a[0] >= min_obs)
     return keys, [acc[kk][1] for kk in keys], [sorted(acc[kk][2]) for kk in keys], [min(acc[kk][0], 65535) for kk in keys]
+
+
+def canon_form(orc, g, with_data=True):
+    """Order- and strand-free form of a BaseGraph: sorted (min(seq, rc seq), Exts [rc'd with it], data)."""
+    out = []
+    L = orc.lib()
+    for i in range(int(g["n_nodes"])):
+        b = node_bases(orc, g, i)
+        r = (3 - b[::-1]).astype(np.uint8)
+        e = int(g["exts"][i])
+        if bytes(r) < bytes(b):
+            b, e = r, L.orc_exts_rc(e)
+        out.append((bytes(b), e, int(g["data"][i]) if with_data else 0))
+    return sorted(out)
+
+
+def msp_shard_graphs(orc, k, p, contigs, stranded=False, twice=True, reduce_op=0):
+    """The reference's shard_asm loop (src/test.rs:433-470): msp_sequence(rc = true) -> per-shard filter_kmers(CountFilter(2)), every
+    substring pushed twice -> per-shard compress_kmers_with_hash.  Returns the shard BaseGraphs in ascending bucket order."""
+    shards = {}
+    for c in contigs:
+        iv = orc.msp_scan(k, p, c, rc=True)
+        for st, ln, b, e in zip(iv["start"], iv["len"], iv["bucket"], iv["exts"]):
+            shards.setdefault(int(b), []).append((c[int(st):int(st) + int(ln)], int(e)))
+    graphs = []
+    for b in sorted(shards):
+        items = shards[b] * (2 if twice else 1)
+        w2, s2, l2 = orc.seqset_from_lists([x[0] for x in items])
+        t = orc.filter_kmers(k, w2, s2, l2, seq_exts=np.array([x[1] for x in items], np.uint8), min_obs=2 if twice else 1, stranded=stranded)
+        g = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], stranded=stranded, reduce_op=reduce_op)
+        assert g["error"] == 0
+        graphs.append(g)
+    return graphs

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import (assert_graphs_equal, assert_tables_equal, brute_filter_colorset, enc, random_contigs, random_dna,
+from helpers import (assert_graphs_equal, assert_tables_equal, brute_filter_colorset, enc, msp_shard_graphs, random_contigs, random_dna,
                      simple_random_contigs, small_k_contigs)
 
 pytestmark = pytest.mark.gpu
@@ -760,3 +760,139 @@ def test_fused_path_and_size_independent_properties(D, ctx, orc):
     assert orc.xor_valid(t) == orc.xor_valid(ot) and orc.mix_valid(t) == orc.mix_valid(ot)
     og = orc.compress_kmers(k, ot["lo"], ot["hi"], ot["exts"], ot["counts"])
     assert_graphs_equal(g, og)
+
+
+# ---- compress_graph / BaseGraph::combine (src/compression.rs:100-349, src/graph.rs:71-100) ------------------------
+def _spec(D, reduce_op):
+    return D.ScmapCompress() if reduce_op == 4 else D.SimpleCompress(reduce_op)
+
+
+def _cg_both(D, ctx, orc, k, host_graphs, stranded=False, reduce_op=3, censor=None):
+    dev = [D.BaseGraph.from_host(g, k, ctx=ctx) for g in host_graphs]
+    dc = D.BaseGraph.combine(dev)
+    oc = orc.combine_graphs(host_graphs)
+    assert_graphs_equal(dc.to_host(), oc)
+    assert dc.stranded == oc["stranded"]
+    og = orc.compress_graph(k, oc, stranded=stranded, reduce_op=reduce_op, censor_nodes=censor)
+    assert og["error"] == 0
+    dg = D.compress_graph(stranded, _spec(D, reduce_op), dc.finish(), censor)
+    assert_graphs_equal(dg.to_host(), og)
+    assert dg.stranded == stranded
+    return dg, og
+
+
+def _trivial_graph(orc, k, t, stranded):
+    """One node per k-mer of a table: the uncompressed graph (Exts and counts of the table)."""
+    n = len(t["lo"])
+    keys = [int(lo) | ((int(t["hi"][i]) << 64) if k > 32 else 0) for i, lo in enumerate(t["lo"])]
+    kb = np.array([[(x >> (2 * (k - 1 - j))) & 3 for j in range(k)] for x in keys], np.uint8).reshape(-1)
+    return dict(n_nodes=n, n_bases=n * k, words=orc.pack_bases(kb), start=np.arange(n, dtype=np.uint64) * np.uint64(k),
+                length=np.full(n, k, np.uint32), exts=t["exts"], data=t["counts"], stranded=stranded)
+
+
+@pytest.mark.parametrize("k", [31, 32, 47])
+def test_compress_graph_reassemble_sharded(D, ctx, orc, k):
+    """The reference's sharded flow end to end (src/test.rs:418-504): msp shards -> per-shard assemblies -> combine -> compress_graph(max);
+    combine and compress_graph on the device, bit for bit against the oracle's greedy walk; the result is_compressed."""
+    rng = np.random.default_rng(400 + k)
+    for it in range(4):
+        contigs = simple_random_contigs(rng) if it == 0 else random_contigs(rng)
+        contigs = [c for c in contigs if len(c) >= k]
+        shard_graphs = msp_shard_graphs(orc, k, 6, contigs)
+        dg, og = _cg_both(D, ctx, orc, k, shard_graphs, reduce_op=3)
+        assert dg.is_compressed(D.SimpleCompress(D.MAX)) is None
+        if it == 1:   # censored nodes (compress_graph's censor_nodes), every reduce op
+            m = sum(g["n_nodes"] for g in shard_graphs)
+            censor = sorted(set(int(x) for x in rng.integers(0, m, size=max(1, m // 10))))
+            for op in (0, 1, 2, 3, 4):
+                _cg_both(D, ctx, orc, k, shard_graphs, reduce_op=op, censor=censor)
+
+
+@pytest.mark.parametrize("k,stranded", [(4, False), (5, False), (6, False), (8, False), (5, True), (6, True), (12, False)])
+def test_compress_graph_small_k(D, ctx, orc, k, stranded):
+    """Uncompressed (one node per k-mer) graphs dense in cycles, hairpins and palindromes: compress_graph == the oracle, and without
+    censoring == compress_kmers of the same table (same rule, same seed order)."""
+    rng = np.random.default_rng(k * 13 + stranded)
+    for it in range(25):
+        contigs = [c for c in small_k_contigs(rng, alphabet=2 if it % 3 == 0 else 4) if len(c) >= k]
+        if not contigs:
+            continue
+        w, s, l = orc.seqset_from_lists(contigs)
+        t = orc.filter_kmers(k, w, s, l, min_obs=1, stranded=stranded)
+        triv = _trivial_graph(orc, k, t, stranded)
+        dg, og = _cg_both(D, ctx, orc, k, [triv], stranded=stranded, reduce_op=it % 4)
+        whole = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], stranded=stranded, reduce_op=it % 4)
+        assert_graphs_equal(og, whole)
+        n = len(t["lo"])
+        if n > 3:
+            censor = sorted(set(int(x) for x in rng.integers(0, n, size=max(1, n // 5))))
+            _cg_both(D, ctx, orc, k, [triv], stranded=stranded, reduce_op=0, censor=censor)
+
+
+def test_compress_graph_long_chains_cycles_and_long_nodes(D, ctx, orc):
+    """Chains of thousands of nodes (pointer doubling), a cycle of thousands of nodes (opened at the seed), nodes of several
+    thousand bases in both orientations (multi-chunk emission, reverse complement across word boundaries), K = 31 and 63."""
+    rng = np.random.default_rng(77)
+    for k in (31, 63):
+        genome = random_dna(rng, 6000)
+        w, s, l = orc.seqset_from_lists([genome])
+        t = orc.filter_kmers(k, w, s, l, min_obs=1)
+        whole = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"])
+        assert whole["n_nodes"] == 1
+        # (a) one node per k-mer: a chain of ~6000 nodes
+        dg, og = _cg_both(D, ctx, orc, k, [_trivial_graph(orc, k, t, False)], reduce_op=0)
+        assert_graphs_equal(og, whole)
+        # (b) a cycle: the genome closed on itself
+        circ = np.concatenate([genome, genome[:k - 1]])
+        w, s, l = orc.seqset_from_lists([circ])
+        tc = orc.filter_kmers(k, w, s, l, min_obs=1)
+        dg, og = _cg_both(D, ctx, orc, k, [_trivial_graph(orc, k, tc, False)], reduce_op=1)
+        assert og["n_nodes"] == 1 and int(og["length"][0]) == len(tc["lo"]) + k - 1
+        # (c) long partial unitigs: the k-mers split by genome position into 3 "shards", each compressed alone, then stitched
+        pos = {}
+        x, mask = 0, (1 << (2 * k)) - 1
+        for i, b in enumerate(genome):
+            x = ((x << 2) | int(b)) & mask
+            if i >= k - 1:
+                r = 0
+                y = x
+                for _ in range(k):
+                    r = (r << 2) | (3 - (y & 3)); y >>= 2
+                pos[min(x, r)] = i - k + 1
+        keys = [int(lo) | ((int(t["hi"][i]) << 64) if k > 32 else 0) for i, lo in enumerate(t["lo"])]
+        part = np.array([min(2, pos[x] // 2100) for x in keys])
+        graphs = []
+        for sh in range(3):
+            m = part == sh
+            hi = t["hi"][m] if k > 32 else t["hi"]
+            g = orc.compress_kmers(k, t["lo"][m], hi, t["exts"][m], t["counts"][m])
+            assert g["error"] == 0 and g["n_nodes"] == 1
+            graphs.append(g)
+        dg, og = _cg_both(D, ctx, orc, k, graphs, reduce_op=0)
+        assert og["n_nodes"] == 1 and int(og["length"][0]) == 6000
+        for order in ([2, 0, 1], [1, 2, 0]):
+            _cg_both(D, ctx, orc, k, [graphs[i] for i in order], reduce_op=2)
+
+
+def test_compress_graph_errors_and_empty(D, ctx, orc):
+    e = np.zeros(0, np.uint64)
+    table, _ = D.filter_kmers((e, e, np.zeros(0, np.uint32)), D.CountFilter(1), False, False, 4, k=31, ctx=ctx)
+    g0 = D.compress_kmers_with_hash(False, D.SimpleCompress(), table)
+    assert len(D.compress_graph(False, D.SimpleCompress(D.MAX), g0)) == 0
+    assert len(D.BaseGraph.combine([g0, g0])) == 0
+    ss = orc.synth_reads(500, 1, 0)
+    ta, _ = D.filter_kmers(ss, D.CountFilter(1), False, False, 4, k=31, ctx=ctx)
+    tb, _ = D.filter_kmers(ss, D.CountFilter(1), True, False, 4, k=31, ctx=ctx)
+    ga = D.compress_kmers_with_hash(False, D.SimpleCompress(), ta)
+    gb = D.compress_kmers_with_hash(True, D.SimpleCompress(), tb)
+    with pytest.raises(D.DbgError):                       # "attempted to combine stranded and unstranded graphs", graph.rs:90-92
+        D.BaseGraph.combine([ga, gb])
+    with pytest.raises(D.DbgError):
+        D.compress_graph(False, D.SimpleCompress(), ga, censor_nodes=[len(ga)])
+    # two adjacent nodes whose Exts disagree (A points to B, B has no extension back): the reference panics "unreachable"
+    a, b = enc("ACGTTGCATGCCGATAGGCT"), enc("CGTTGCATGCCGATAGGCTA")
+    g = dict(n_nodes=2, n_bases=40, words=orc.pack_bases(np.concatenate([a, b])), start=np.array([0, 20], np.uint64),
+             length=np.array([20, 20], np.uint32), exts=np.array([1 << 4, 1 << 6], np.uint8), data=np.array([1, 1], np.uint16), stranded=False)
+    assert orc.compress_graph(20, g)["error"] == 1
+    with pytest.raises(D.DbgError):
+        D.compress_graph(False, D.SimpleCompress(), D.BaseGraph.from_host(g, 20, ctx=ctx))

@@ -9,8 +9,8 @@ import os
 import numpy as np
 import pytest
 
-from helpers import (canon, dec, enc, kmers_of, node_bases, random_contigs, random_dna, rc_int, simple_random_contigs,
-                     small_k_contigs)
+from helpers import (assert_graphs_equal, canon, canon_form, dec, enc, kmers_of, msp_shard_graphs, node_bases, random_contigs,
+                     random_dna, rc_int, simple_random_contigs, small_k_contigs)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -524,3 +524,76 @@ def test_bincode_image_layout(orc):
            b"\x02" + b"\0" * 7 + b"\x12\x80" +
            b"\x02" + b"\0" * 7 + b"\x05\x00\xff\xff" + b"\x01")
     assert img == exp
+
+
+def _reassemble_sharded_props(orc, k, contigs, g):
+    """The assertions of reassemble_sharded (src/test.rs:473-503) on the stitched graph."""
+    kmer_set = set(canon(x, k) for c in contigs for x in kmers_of(c, k))
+    allc = set()
+    mask = (1 << (2 * k)) - 1
+    for i in range(g["n_nodes"]):
+        ks = kmers_of(node_bases(orc, g, i), k)
+        cs = set(canon(x, k) for x in ks)
+        assert cs <= kmer_set
+        allc |= cs
+        e = int(g["exts"][i])
+        for base in range(4):
+            if e & (1 << base):
+                assert canon((ks[0] >> 2) | (base << (2 * (k - 1))), k) in kmer_set
+            if e & (1 << (4 + base)):
+                assert canon(((ks[-1] << 2) & mask) | base, k) in kmer_set
+    assert allc == kmer_set
+
+
+@pytest.mark.parametrize("k", [31, 32])
+def test_compress_graph_reassemble_sharded(orc, k):
+    """src/test.rs:418-504: msp shards -> shard assemblies -> BaseGraph::combine -> compress_graph(max): the reference's own
+    assertions, plus: the stitched graph is compressed (compression.rs:332) and its canonical form (sequences + Exts) equals the
+    unsharded compress_kmers graph of the same contigs (every k-mer valid, so fix_exts removes nothing)."""
+    rng = np.random.default_rng(300 + k)
+    for it in range(5):
+        contigs = simple_random_contigs(rng) if it == 0 else random_contigs(rng)
+        contigs = [c for c in contigs if len(c) >= k]
+        shard_graphs = msp_shard_graphs(orc, k, 6, contigs)
+        combined = orc.combine_graphs(shard_graphs)
+        assert combined["n_nodes"] == sum(g["n_nodes"] for g in shard_graphs)
+        g = orc.compress_graph(k, combined, stranded=False, reduce_op=orc.MAX)
+        assert g["error"] == 0
+        _reassemble_sharded_props(orc, k, contigs, g)
+        assert orc.graph_edges(k, g)[2] is None
+        w, s, l = orc.seqset_from_lists(contigs + contigs)
+        t = orc.filter_kmers(k, w, s, l, min_obs=2)
+        whole = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], reduce_op=orc.MAX)
+        assert canon_form(orc, g, with_data=False) == canon_form(orc, whole, with_data=False)
+
+
+@pytest.mark.parametrize("k,stranded", [(4, False), (5, False), (6, False), (5, True), (6, True)])
+def test_compress_graph_small_k(orc, k, stranded):
+    """Per-k-mer nodes (an uncompressed graph) of cycle / hairpin / palindrome rich inputs: compress_graph of the trivial graph has the
+    canonical form of compress_kmers for acyclic components; with censored nodes the survivors still tile their k-mers."""
+    rng = np.random.default_rng(k * 11 + stranded)
+    for it in range(40):
+        contigs = [c for c in small_k_contigs(rng, alphabet=2 if it % 3 == 0 else 4) if len(c) >= k]
+        if not contigs:
+            continue
+        w, s, l = orc.seqset_from_lists(contigs)
+        t = orc.filter_kmers(k, w, s, l, min_obs=1, stranded=stranded)
+        n = len(t["lo"])
+        # one node per k-mer, Exts and counts of the table
+        kb = np.array([[(int(x) >> (2 * (k - 1 - j))) & 3 for j in range(k)] for x in t["lo"]], np.uint8).reshape(-1)
+        triv = dict(n_nodes=n, n_bases=n * k, words=orc.pack_bases(kb), start=np.arange(n, dtype=np.uint64) * k,
+                    length=np.full(n, k, np.uint32), exts=t["exts"], data=t["counts"], stranded=stranded)
+        g = orc.compress_graph(k, triv, stranded=stranded, reduce_op=orc.SAT_ADD)
+        assert g["error"] == 0
+        whole = orc.compress_kmers(k, t["lo"], t["hi"], t["exts"], t["counts"], stranded=stranded)
+        # same seed order (ascending k-mer = node order) and the same rule: identical graphs, bit for bit
+        assert_graphs_equal(g, whole)
+        if n > 3:
+            censor = sorted(set(int(x) for x in rng.integers(0, n, size=max(1, n // 5))))
+            gc = orc.compress_graph(k, triv, stranded=stranded, censor_nodes=censor)
+            assert gc["error"] == 0
+            keep = set(int(x) for i, x in enumerate(t["lo"]) if i not in censor)
+            cf = (lambda x: x) if stranded else (lambda x: canon(x, k))
+            got = [cf(x) for i in range(gc["n_nodes"]) for x in kmers_of(node_bases(orc, gc, i), k)]
+            assert sorted(got) == sorted(keep)
+            assert orc.graph_edges(k, gc, stranded=stranded)[2] is None
