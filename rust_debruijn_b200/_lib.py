@@ -6,7 +6,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdbg_b200.so")
+# DBG_B200_LIB: another build of the same library (A/B experiments, tools/build_variant.sh); never a fallback
+SO_PATH = os.environ.get("DBG_B200_LIB") or os.path.join(_HERE, "libdbg_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, E_BADARG, E_OOM, E_CUDA, E_INCONSISTENT_EXTS, E_INTERNAL = range(6)

@@ -726,6 +726,12 @@ __global__ void __launch_bounds__(256) scatter_records_kernel(const u64* __restr
 // P2: per-bucket counting in shared memory
 // ------------------------------------------------------------------------------------------------
 static const int P2_THREADS = 512;
+// P2_VLIST: a k-mer whose count crosses min_obs is appended to a shared-memory list when it happens, so the emission writes
+// the <= VL_CAP valid k-mers of a bucket without scanning the table (the scan stays for report_all and for buckets with more)
+#ifndef P2_VLIST
+#define P2_VLIST 1
+#endif
+static const int VL_CAP = 2048;
 static const int MAX_PROBE = 96;
 static const int SPLIT_STACK = 64;
 
@@ -769,10 +775,10 @@ template <int W>
 struct SmemTable {
     Kmer<W>* keys;
     u32* vals;  // count << 8 | exts
-    __device__ __forceinline__ int find_or_insert(Kmer<W> key, u32 h, int cap);
+    __device__ __forceinline__ int find_or_insert(Kmer<W> key, u32 h, int cap, u32& fresh);   // fresh += 1 when the key is new
 };
 template <>
-__device__ __forceinline__ int SmemTable<1>::find_or_insert(Kmer<1> key, u32 h, int cap) {
+__device__ __forceinline__ int SmemTable<1>::find_or_insert(Kmer<1> key, u32 h, int cap, u32& fresh) {
     u32 slot = (h >> 18) & (cap - 1);  // class selection uses the low <= 18 bits
     u64* k64 = reinterpret_cast<u64*>(keys);
     for (int pr = 0; pr < MAX_PROBE; pr++) {
@@ -780,21 +786,23 @@ __device__ __forceinline__ int SmemTable<1>::find_or_insert(Kmer<1> key, u32 h, 
         if (cur == key.lo) return (int)slot;
         if (cur == ~0ull) {
             u64 old = atomicCAS(k64 + slot, ~0ull, key.lo);
-            if (old == ~0ull || old == key.lo) return (int)slot;
+            if (old == ~0ull) { fresh++; return (int)slot; }
+            if (old == key.lo) return (int)slot;
         }
         slot = (slot + 1) & (cap - 1);
     }
     return -1;
 }
 template <>
-__device__ __forceinline__ int SmemTable<2>::find_or_insert(Kmer<2> key, u32 h, int cap) {
+__device__ __forceinline__ int SmemTable<2>::find_or_insert(Kmer<2> key, u32 h, int cap, u32& fresh) {
     u32 slot = (h >> 18) & (cap - 1);
     const Kmer<2> empty{~0ull, ~0ull};
     for (int pr = 0; pr < MAX_PROBE; pr++) {
         volatile u64* kp = reinterpret_cast<volatile u64*>(keys + slot);
         if (kp[0] == key.lo && kp[1] == key.hi) return (int)slot;  // both halves equal => not torn
         Kmer<2> old = cas128_shared(keys + slot, empty, key);
-        if ((old.lo == ~0ull && old.hi == ~0ull) || (old.lo == key.lo && old.hi == key.hi)) return (int)slot;
+        if (old.lo == ~0ull && old.hi == ~0ull) { fresh++; return (int)slot; }
+        if (old.lo == key.lo && old.hi == key.hi) return (int)slot;
         slot = (slot + 1) & (cap - 1);
     }
     return -1;
@@ -818,6 +826,11 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
     __shared__ u32 s_bucket, s_overflow, s_sp_cnt, s_sp_exts, s_nstack;
     __shared__ u64 s_base_valid, s_base_all;
     __shared__ u32 s_stack[SPLIT_STACK];  // (residue << 6) | bits ; residue < 2^26 (deeper => error)
+#if P2_VLIST
+    __shared__ u32 s_vcnt, s_na;
+    __shared__ u16 s_vlist[VL_CAP];
+    const u32 mo = a.min_obs ? a.min_obs : 1u;
+#endif
     SmemTable<W> tab{keys, vals};
     const int K = kp.k;
     const int tl = a.task_len;
@@ -866,7 +879,41 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                         reinterpret_cast<u64*>(rkeys)[2 * i + 1] = ~0ull;
                         rcnt[i] = 0;
                     }
+#if P2_VLIST
+                    if (threadIdx.x == 0) s_vcnt = 0;
+#endif
                     __syncthreads();
+#if P2_VLIST
+                    // the thread whose CAS claims an empty slot appends the slot to a list (a chunk holds <= RCAP / 2 <= VL_CAP
+                    // records): the compaction below walks the list, not the table
+                    static_assert(RCAP / 2 <= VL_CAP, "one list entry per record of a chunk");
+                    for (u32 i = threadIdx.x; i < nrc; i += P2T) {
+                        ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(a.rec + (c0 + i) * 2));
+                        Kmer<2> key{v.x, v.y};
+                        u32 slot = Ops<2>::hash32(key) >> 8 & (RCAP - 1);
+                        const Kmer<2> empty{~0ull, ~0ull};
+                        for (;;) {
+                            volatile u64* kp2 = reinterpret_cast<volatile u64*>(rkeys + slot);
+                            if (kp2[0] == key.lo && kp2[1] == key.hi) break;
+                            Kmer<2> old = cas128_shared(rkeys + slot, empty, key);
+                            if (old.lo == ~0ull && old.hi == ~0ull) { s_vlist[atomicAdd(&s_vcnt, 1u)] = (u16)slot; break; }
+                            if (old.lo == key.lo && old.hi == key.hi) break;
+                            slot = (slot + 1) & (RCAP - 1);
+                        }
+                        atomicAdd(&rcnt[slot], 1u);
+                    }
+                    __syncthreads();   // every record of the chunk has been read: the in-place writes below are safe
+                    const u32 nd = s_vcnt;
+                    for (u32 q = threadIdx.x; q < nd; q += P2T) {
+                        const int sl = s_vlist[q];
+                        const u64 o = r0 + dbase + q;
+                        *reinterpret_cast<ulonglong2*>(a.rec + o * 2) = make_ulonglong2(rkeys[sl].lo, rkeys[sl].hi);
+                        a.mult[o] = rcnt[sl];
+                    }
+                    dbase += nd;
+                    __syncthreads();
+                }
+#else
                     for (u32 i = threadIdx.x; i < nrc; i += P2T) {
                         ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(a.rec + (c0 + i) * 2));
                         Kmer<2> key{v.x, v.y};
@@ -916,6 +963,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                     }
                     __syncthreads();
                 }
+#endif
                 if (threadIdx.x == 0) { atomicAdd(&a.counters[5], dbase); a.dedup_cnt[b] = (u32)dbase; }
                 r1 = r0 + dbase;
                 __threadfence_block();
@@ -1045,6 +1093,12 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                 vals[i] = 0;
             }
             if (threadIdx.x == 0) { s_overflow = 0; s_sp_cnt = 0; s_sp_exts = 0; s_nstack--; }
+#if P2_VLIST
+            if (threadIdx.x == 32) { s_vcnt = 0; s_na = 0; }
+            u32 fresh = 0;
+#else
+            u32 fresh = 0;
+#endif
             __syncthreads();
             // ---- expand records, insert.  The bucket is processed in chunks of RC records.  Every record is cut into
             // TASKS of <= tl consecutive k-mers and the chunk's tasks are counting-sorted by length (descending) in
@@ -1155,18 +1209,18 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                         const int kk = K - 32;   // 1..32
                         NX = kk < 32 ? (u32)(((s[1] << (2 * kk)) | (s[2] >> (64 - 2 * kk))) >> 32) : (u32)(s[2] >> 32);
                     }
-                    // Exts::rc of a one-base nibble 1 << b is 1 << (3 - b); the sequence-end nibbles are complemented once
-                    const u32 ln_c = exts_complement(ln) & 0xfu, rn_c = exts_complement(rn) & 0xfu;
+                    // left nibble of the forward Exts: the record's own left mask for its first k-mer, else the base in front
+                    u32 pn = t == 0 ? ln : (1u << prev_first);
                     for (; t < tend; t++) {
                         const u32 nb = NX >> 30;   // base t+K (only meaningful when t < n-1)
                         NX <<= 2;
                         const u32 cf = PF >> 30;   // first base of this k-mer
                         PF <<= 2;
-                        const bool first = t == 0, last = t == n - 1;
                         const bool use_rc = !a.stranded && !(fwd < rcv);   // lib.rs:224-231 (equality -> flipped), filter.rs:190-196
-                        const u32 el = use_rc ? (last ? rn_c : (8u >> nb)) : (first ? ln : (1u << prev_first));
-                        const u32 er = use_rc ? (first ? ln_c : (8u >> prev_first)) : (last ? rn : (1u << nb));
-                        const u32 e = el | (er << 4);
+                        // forward Exts, then Exts::rc (lib.rs:746) when the rc is the canonical form: complement + swap of the
+                        // nibbles sends bit i to bit 7 - i, i.e. an 8-bit reversal
+                        const u32 ef = pn | ((t == n - 1 ? rn : (1u << nb)) << 4);
+                        const u32 e = use_rc ? __brev(ef) >> 24 : ef;
                         const Kmer<W> key = use_rc ? rcv : fwd;
                         const u32 h = Ops<W>::hash32(key);
                         if ((h & cmask) == cres) {
@@ -1177,7 +1231,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                                 atomicAdd(&s_sp_cnt, mcur);
                                 atomicOr(&s_sp_exts, e);
                             } else {
-                                const int slot = tab.find_or_insert(key, h, CAP);
+                                const int slot = tab.find_or_insert(key, h, CAP, fresh);
                                 if (slot < 0) {   // table full: stop everybody's claims (no flag polled in the loop), the bucket is split
                                     atomicExch(&s_overflow, 1u);
                                     atomicMax(&s_next, 0x40000000u);
@@ -1187,13 +1241,31 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                                 if (e & ~v) atomicOr(vals + slot, e);
                                 if (small_bucket) {
                                     // the bucket's total occurrences fit the 24-bit field: plain add, clamped at emission
+#if P2_VLIST
+                                    const u32 old = atomicAdd(vals + slot, mcur << 8) >> 8;
+                                    if (old < mo && old + mcur >= mo) {
+                                        const u32 qv = atomicAdd(&s_vcnt, 1u);
+                                        if (qv < VL_CAP) s_vlist[qv] = (u16)slot;
+                                    }
+#else
                                     atomicAdd(vals + slot, mcur << 8);
+#endif
                                 } else {
                                     // saturating count (filter.rs:57): stop adding once 65535 is reached; steps of <= 255
                                     // keep the transient overshoot far below the 24-bit field
                                     for (u32 rem = mcur;;) {
                                         u32 stp = min(rem, 255u);
+#if P2_VLIST
+                                        if ((v >> 8) < 65535u) {
+                                            const u32 old = atomicAdd(vals + slot, stp << 8) >> 8;
+                                            if (old < mo && old + stp >= mo) {
+                                                const u32 qv = atomicAdd(&s_vcnt, 1u);
+                                                if (qv < VL_CAP) s_vlist[qv] = (u16)slot;
+                                            }
+                                        }
+#else
                                         if ((v >> 8) < 65535u) atomicAdd(vals + slot, stp << 8);
+#endif
                                         rem -= stp;
                                         if (!rem) break;
                                         v = *reinterpret_cast<volatile u32*>(vals + slot);
@@ -1202,7 +1274,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                             }
                         }
                         // roll to the next k-mer of this record
-                        prev_first = cf;
+                        pn = 1u << cf;
                         fwd = Ops<W>::ext_right(kp, fwd, nb);
                         rcv = Ops<W>::roll_rc(kp, rcv, nb);
                     }
@@ -1211,6 +1283,9 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                 __syncthreads();
                 if (s_overflow) break;   // (uniform: every thread reads the flag after the barrier)
             }
+#if P2_VLIST
+            if (fresh) atomicAdd(&s_na, fresh);
+#endif
             __syncthreads();
             if (s_overflow) {
                 if (threadIdx.x == 0) {
@@ -1225,6 +1300,42 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                 __syncthreads();
                 continue;
             }
+#if P2_VLIST
+            if (!a.report_all && s_vcnt <= (u32)VL_CAP) {
+                // ---- emit from the list: one reservation, one k-mer per thread and round ----
+                const u32 nvl = s_vcnt;
+                if (threadIdx.x == 0) {
+                    const u32 sc = s_sp_cnt > 65535u ? 65535u : s_sp_cnt;
+                    const u32 spv = (s_sp_cnt && sc >= a.min_obs) ? 1u : 0u;
+                    const u32 tv = nvl + spv, ta = s_na + (s_sp_cnt ? 1u : 0u);
+                    s_base_valid = tv ? atomicAdd(&a.counters[1], (u64)tv) : 0;
+                    atomicAdd(&a.counters[2], (u64)ta);
+                    const bool over = s_base_valid + tv > a.cap_valid;
+                    if (over) a.counters[4] = 2;
+                    s_wr_ok = over ? 0u : 1u;
+                    if (!over && spv) {
+                        a.out_lo[s_base_valid + nvl] = ~0ull;
+                        if (W == 2) a.out_hi[s_base_valid + nvl] = ~0ull;
+                        a.out_val[s_base_valid + nvl] = (s_sp_exts & 0xffu) | (sc << 8);
+                    }
+                }
+                __syncthreads();
+                if (s_wr_ok) {
+                    const u64 pv0 = s_base_valid;
+                    for (u32 q = threadIdx.x; q < nvl; q += P2T) {
+                        const int i = s_vlist[q];
+                        const u32 v = vals[i];
+                        u32 cc = v >> 8;
+                        cc = cc > 65535u ? 65535u : cc;
+                        a.out_lo[pv0 + q] = W == 1 ? reinterpret_cast<u64*>(keys)[i] : reinterpret_cast<u64*>(keys)[2 * i];
+                        if (W == 2) a.out_hi[pv0 + q] = reinterpret_cast<u64*>(keys)[2 * i + 1];
+                        a.out_val[pv0 + q] = (v & 0xffu) | (cc << 8);
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
+#endif
             // ---- emit: count, block scan, reserve, write ----
             u32 nv = 0, na = 0;
             u32 occm = 0, valm = 0;   // bit j: slot threadIdx.x + j * P2T is occupied / valid (CAP / P2T <= 32 slots per thread)
