@@ -823,7 +823,9 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
     __shared__ u32 s_ptot, s_next, s_wr_ok, s_cnt;
     __shared__ u64 s_r0;
     __shared__ u32 s_wsum[32];
-    __shared__ u32 s_bucket, s_overflow, s_sp_cnt, s_sp_exts, s_nstack;
+    __shared__ u32 s_bucket, s_overflow, s_sp_cnt, s_sp_exts;
+    __shared__ u64 s_pf_r0;   // the NEXT bucket's records, prefetched into L2 while this bucket is expanded
+    __shared__ u32 s_pf_cnt;
     __shared__ u64 s_base_valid, s_base_all;
     __shared__ u32 s_stack[SPLIT_STACK];  // (residue << 6) | bits ; residue < 2^26 (deeper => error)
 #if P2_VLIST
@@ -844,10 +846,9 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
         if (nb_id < a.n_buckets) { nb_r0 = a.bucket_start[nb_id]; nb_cnt = a.bucket_cnt[nb_id]; }
     }
     for (;;) {
-        __syncthreads();
+        // (no barrier here: every path back to this point ends with one, after the last read of the values below)
         if (threadIdx.x == 0) {
             s_bucket = nb_id; s_r0 = nb_r0; s_cnt = nb_cnt;
-            s_nstack = 1;
             s_stack[0] = 0;
             if (nb_id < a.n_buckets) nb_id = (u32)atomicAdd(&a.counters[0], 1ull);   // result needed one bucket later
         }
@@ -857,7 +858,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
         const u64 r0 = s_r0;
         u64 r1 = r0 + s_cnt;
         if (threadIdx.x == 0 && nb_id < a.n_buckets) { nb_r0 = a.bucket_start[nb_id]; nb_cnt = a.bucket_cnt[nb_id]; }
-        if (r0 == r1) continue;
+        if (r0 == r1) { __syncthreads(); continue; }
         const bool small_bucket = (r1 - r0) * 63ull < (1ull << 24);   // no count can overflow the 24-bit field
         if constexpr (W == 1) {
             if (a.mult && a.mult_ready) {
@@ -1081,18 +1082,18 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                 __syncthreads();
             }
         }
-        while (s_nstack > 0) {
-            __syncthreads();
-            const u32 top = s_stack[s_nstack - 1];
+        // the split stack's depth is mirrored in a register by every thread (pushes and pops are uniform decisions)
+        int nstack = 1;
+        while (nstack > 0) {
+            const u32 top = s_stack[--nstack];
             const u32 cbits = top & 63u, cres = top >> 6;
             const u32 cmask = cbits ? ((1u << cbits) - 1) : 0;
-            __syncthreads();
             for (int i = threadIdx.x; i < CAP; i += P2T) {
                 if (W == 1) reinterpret_cast<u64*>(keys)[i] = ~0ull;
                 else { reinterpret_cast<u64*>(keys)[2 * i] = ~0ull; reinterpret_cast<u64*>(keys)[2 * i + 1] = ~0ull; }
                 vals[i] = 0;
             }
-            if (threadIdx.x == 0) { s_overflow = 0; s_sp_cnt = 0; s_sp_exts = 0; s_nstack--; }
+            if (threadIdx.x == 0) { s_overflow = 0; s_sp_cnt = 0; s_sp_exts = 0; }
 #if P2_VLIST
             if (threadIdx.x == 32) { s_vcnt = 0; s_na = 0; }
             u32 fresh = 0;
@@ -1126,8 +1127,15 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                     for (int l = tl; l >= 1; l--) { u32 c = s_cls[l]; s_cls[l] = acc; acc += c; }
                     s_cls[0] = acc;
                     s_next = 0;
+                    if (c0 == r0) { s_pf_r0 = nb_r0; s_pf_cnt = nb_id < a.n_buckets ? nb_cnt : 0u; }
                 }
                 __syncthreads();
+                if (c0 == r0 && cbits == 0) {
+                    // the dedup phase of the next bucket starts with one dependent load per record: pull its records into L2 now
+                    const char* pf = reinterpret_cast<const char*>(a.rec + s_pf_r0 * RW);
+                    const u32 lines = (s_pf_cnt * (u32)(RW * 8) + 127u) >> 7;
+                    for (u32 i = threadIdx.x; i < lines; i += P2T) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (u64)i * 128));
+                }
 #pragma unroll
                 for (int j = 0; j < P2_RC / P2T; j++) {   // scatter (record, first k-mer) into the class ranges
                     const u32 idx = j * P2T + threadIdx.x;
@@ -1280,23 +1288,24 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                     }
                     }
                 }
+#if P2_VLIST
+                if (fresh) { atomicAdd(&s_na, fresh); fresh = 0; }
+#endif
                 __syncthreads();
                 if (s_overflow) break;   // (uniform: every thread reads the flag after the barrier)
             }
-#if P2_VLIST
-            if (fresh) atomicAdd(&s_na, fresh);
-#endif
-            __syncthreads();
             if (s_overflow) {
+                const bool deep = cbits >= 18 || nstack + 2 > SPLIT_STACK;
                 if (threadIdx.x == 0) {
-                    if (cbits >= 18 || s_nstack + 2 > SPLIT_STACK) {
+                    if (deep) {
                         a.counters[4] = 1;  // cannot happen for distinct keys below 2^26 classes; reported as internal error
                     } else {
-                        s_stack[s_nstack++] = ((cres | (1u << cbits)) << 6) | (cbits + 1);
-                        s_stack[s_nstack++] = (cres << 6) | (cbits + 1);
+                        s_stack[nstack] = ((cres | (1u << cbits)) << 6) | (cbits + 1);
+                        s_stack[nstack + 1] = (cres << 6) | (cbits + 1);
                         atomicAdd(&a.counters[3], 1ull);
                     }
                 }
+                if (!deep) nstack += 2;
                 __syncthreads();
                 continue;
             }
