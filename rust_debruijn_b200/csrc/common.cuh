@@ -280,6 +280,27 @@ int filter_kmers_colorset_dev(Ctx* c, int k, const SeqSet* s, const u8* h_labels
 void plan_filter(const Ctx* c, int k, u64 N, int* p_out, int* bbits_out);
 int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int bbits, Partition** out);
 void free_partition(Partition* P);
+// partition of one rank's reads as bucket REGIONS (possibly with gaps) for the fused compaction + exchange of multi.cu
+struct PartRegions {
+    Ctx* ctx = nullptr;
+    int k = 0, p = 0, bbits = 0, rec_words = 2, direct = 0;
+    u64 n_input = 0, n_rec = 0;
+    const u64* rec = nullptr;     // records, bucket b = [start[b], start[b] + cnt[b])
+    const u64* start = nullptr;   // 2^bbits (+1) record offsets
+    const u32* cnt = nullptr;     // 2^bbits
+    void* holder = nullptr;       // owner of the device buffers
+};
+#ifndef DBG_MAX_RANKS
+#define DBG_MAX_RANKS 8
+#endif
+struct ScatterDst { u64* base[DBG_MAX_RANKS]; u64 bound[DBG_MAX_RANKS + 1]; int P; };
+int partition_regions_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int bbits, PartRegions** out);
+void free_part_regions(PartRegions* R);
+int bucket_totals_dev(Ctx* c, const u32* d_all_cnt, int P, int me, u32 nb, u32* d_tot, u32* d_pre);
+int local_buckets_dev(Ctx* c, const u64* d_goff, const u32* d_tot, u32 b0, u32 n, u64* d_off, u32* d_cnt);
+int scatter_buckets_dev(Ctx* c, const PartRegions* R, const u64* d_goff, const u32* d_pre, const ScatterDst& D, u64* d_sums);
+int filter_from_bucketed_dev(Ctx* c, int k, u64* d_records, u64 n_records, const u64* d_off, const u32* d_cnt, u32 n_local,
+                             u64 n_kmers_local, u64 n_input_total, u32 min_obs, int stranded, int report_all, Table** out);
 int graph_edges_dev(Ctx* c, const Graph* g, u32* h_target, u8* h_flags);
 int graph_fix_exts_dev(Ctx* c, Graph* g, const u8* h_valid_nodes);
 int graph_is_compressed_dev(Ctx* c, const Graph* g, int scmap, long long* pair_out);
@@ -301,7 +322,6 @@ void free_graph(Graph* g);
 int count_input_kmers_dev(Ctx* c, int k, const SeqSet* s, u64* N_out);
 
 // ---- sharded compression over a bucket-sharded table (shard_compress.cu; orchestrated by multi.cu) ----------------
-#define DBG_MAX_RANKS 8
 struct ShardCfg { int P, me, p, bbits, stranded, scmap; };
 // every rank's peer-mapped window: walk records (one uint4 per k-mer) and a copy of the shard's k-mers
 struct RecPeers { const uint4* rec[DBG_MAX_RANKS]; const u64* klo[DBG_MAX_RANKS]; const u64* khi[DBG_MAX_RANKS]; };

@@ -2093,6 +2093,174 @@ int partition_reads_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int
     return DBG_OK;
 }
 
+// ---- fused compaction + exchange (multi.cu): the partition's bucket regions are NOT made contiguous on the sending rank;
+// one kernel copies every bucket's records straight to their final, bucket-contiguous position in the OWNING rank's
+// receive window over peer memory (NVLink stores), so that neither a local gap-closing pass, nor a send buffer, nor a
+// per-source merge on the receiver is needed. ----
+int partition_regions_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int bbits, PartRegions** out) {
+    *out = nullptr;
+    if (k < 4 || k > 64) DBG_SET_ERR(c, DBG_E_BADARG, "k=%d outside [4,64]", k);
+    if (bbits < 0 || bbits > 20 || p < 1 || p > 16 || p > k - 3 || k - p > 63)
+        DBG_SET_ERR(c, DBG_E_BADARG, "bad MSP plan p=%d bucket_bits=%d for k=%d", p, bbits, k);
+    TRY(arena_begin(c));
+    u64 N = 0;
+    u32 max_len = 0;
+    TRY(count_input(c, k, s, &N, &max_len));
+    const u32 NB = 1u << bbits;
+    PartRegions* R = new PartRegions();
+    R->ctx = c; R->k = k; R->p = p; R->bbits = bbits; R->rec_words = k <= 32 ? 2 : 4; R->n_input = N;
+    struct Guard { PartRegions* r; ~Guard() { if (r) free_part_regions(r); } } guard{R};
+    const u64 n_tiles_all = (s->contiguous && s->total_end > s->base0) ? (s->total_end - s->base0 + TP - 1) / TP : 0;
+    if (N && k <= 32 && c->direct_partition && n_tiles_all >= c->direct_min_tiles && s->n_pending == 0) {
+        DirectOut* d = new DirectOut();
+        R->holder = d; R->direct = 1;
+        TRY(partition_direct<1>(c, k, s, stranded, N, p, bbits, *d));
+        u64 h[3] = {0, 0, 0};
+        TRY(read_u64(c, d->ctr.p, h, 3));   // [1] overflow flag, [2] records stored
+        if (!(u32)h[1]) {
+            R->rec = d->rec.p; R->start = d->bucket_start.p; R->cnt = d->cnt.p; R->n_rec = h[2];
+        } else {   // a region overflowed: staging path below
+            delete d;
+            R->holder = nullptr; R->direct = 0;
+        }
+    }
+    if (!R->rec) {
+        PartOut* po = new PartOut();
+        R->holder = po; R->direct = 0;
+        if (N) {
+            TRY(k <= 32 ? partition_stage<1>(c, k, s, stranded, N, max_len, p, bbits, 0, NB, true, *po)
+                        : partition_stage<2>(c, k, s, stranded, N, max_len, p, bbits, 0, NB, true, *po));
+        } else {
+            TRY(po->bucket_count.alloc_pool(c, NB)); TRY(po->bucket_count.zero());
+            TRY(po->bucket_off.alloc_pool(c, (u64)NB + 1)); TRY(po->bucket_off.zero());
+            TRY(po->rec.alloc_pool(c, 1));
+        }
+        R->rec = po->rec.p; R->start = po->bucket_off.p; R->cnt = po->bucket_count.p; R->n_rec = po->n_rec;
+    }
+    TRY(sync(c));
+    if (N) cudaEventElapsedTime(&c->stats.ms_k_partition, c->ev[8], c->ev[9]);
+    c->stats.n_records = R->n_rec;
+    c->stats.n_input_kmers = N;
+    guard.r = nullptr;
+    *out = R;
+    return DBG_OK;
+}
+void free_part_regions(PartRegions* R) {
+    if (!R) return;
+    if (R->holder) { if (R->direct) delete static_cast<DirectOut*>(R->holder); else delete static_cast<PartOut*>(R->holder); }
+    delete R;
+}
+
+// tot[b] = records of bucket b over all ranks, pre[b] = records of bucket b on the ranks below `me`
+__global__ void bucket_totals_kernel(const u32* __restrict__ all_cnt, int P, int me, u32 nb, u32* __restrict__ tot, u32* __restrict__ pre) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    u32 t = 0, q = 0;
+    for (int r = 0; r < P; r++) { const u32 v = all_cnt[(u64)r * nb + b]; if (r < me) q += v; t += v; }
+    tot[b] = t; pre[b] = q;
+}
+int bucket_totals_dev(Ctx* c, const u32* d_all_cnt, int P, int me, u32 nb, u32* d_tot, u32* d_pre) {
+    bucket_totals_kernel<<<grid_for(nb, 256), 256, 0, c->stream>>>(d_all_cnt, P, me, nb, d_tot, d_pre);
+    return check_launch(c, "bucket_totals");
+}
+// the owned bucket range [b0, b0 + n) in local coordinates: off[i] = goff[b0 + i] - goff[b0], cnt[i] = tot[b0 + i]
+__global__ void local_buckets_kernel(const u64* __restrict__ goff, const u32* __restrict__ tot, u32 b0, u32 n, u64* __restrict__ off,
+                                     u32* __restrict__ cnt) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    off[i] = goff[b0 + i] - goff[b0];
+    if (i < n) cnt[i] = tot[b0 + i];
+}
+int local_buckets_dev(Ctx* c, const u64* d_goff, const u32* d_tot, u32 b0, u32 n, u64* d_off, u32* d_cnt) {
+    local_buckets_kernel<<<grid_for((u64)n + 1, 256), 256, 0, c->stream>>>(d_goff, d_tot, b0, n, d_off, d_cnt);
+    return check_launch(c, "local_buckets");
+}
+
+// One warp per bucket: coalesced 16-byte copies from the bucket's region to base[owner] + (goff[b] - goff[bound[owner]] + pre[b]);
+// per destination: k-mer occurrences and records shipped (sums[r], sums[P + r]).
+template <int RW>
+__global__ void __launch_bounds__(256) scatter_buckets_kernel(const u64* __restrict__ src, const u64* __restrict__ src_start,
+                                                               const u32* __restrict__ cnt, const u64* __restrict__ goff,
+                                                               const u32* __restrict__ pre, ScatterDst D, u32 nb, u64* __restrict__ sums) {
+    __shared__ unsigned long long s_km[DBG_MAX_RANKS], s_rc[DBG_MAX_RANKS];
+    if (threadIdx.x < DBG_MAX_RANKS) { s_km[threadIdx.x] = 0; s_rc[threadIdx.x] = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (u64 b = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += ((u64)gridDim.x * blockDim.x) >> 5) {
+        const u32 n = cnt[b];
+        if (!n) continue;
+        int r = 0;
+        while (r + 1 < D.P && b >= D.bound[r + 1]) r++;
+        const u64 s0 = src_start[b], d0 = goff[b] - goff[D.bound[r]] + pre[b];
+        u64* dst = D.base[r];
+        u32 km = 0;
+        for (u32 i = lane; i < n; i += 32) {
+            const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(src + (s0 + i) * RW);
+            ulonglong2* dp = reinterpret_cast<ulonglong2*>(dst + (d0 + i) * RW);
+            const ulonglong2 v0 = sp[0];
+            dp[0] = v0;
+            if (RW == 4) { const ulonglong2 v1 = sp[1]; dp[1] = v1; km += (u32)(v1.y >> 8) & 63u; }
+            else km += (u32)(v0.y >> 8) & 63u;
+        }
+        for (int o = 16; o; o >>= 1) km += __shfl_down_sync(0xffffffffu, km, o);
+        if (lane == 0) { atomicAdd(&s_km[r], (unsigned long long)km); atomicAdd(&s_rc[r], (unsigned long long)n); }
+    }
+    __syncthreads();
+    if (threadIdx.x < D.P) {
+        if (s_km[threadIdx.x]) atomicAdd(&sums[threadIdx.x], (u64)s_km[threadIdx.x]);
+        if (s_rc[threadIdx.x]) atomicAdd(&sums[D.P + threadIdx.x], (u64)s_rc[threadIdx.x]);
+    }
+}
+int scatter_buckets_dev(Ctx* c, const PartRegions* R, const u64* d_goff, const u32* d_pre, const ScatterDst& D, u64* d_sums) {
+    const u32 nb = 1u << R->bbits;
+    const u32 grid = (u32)std::min<u64>(((u64)nb + 7) / 8, (u64)c->sm_count * 32);
+    if (R->rec_words == 2) scatter_buckets_kernel<2><<<grid, 256, 0, c->stream>>>(R->rec, R->start, R->cnt, d_goff, d_pre, D, nb, d_sums);
+    else scatter_buckets_kernel<4><<<grid, 256, 0, c->stream>>>(R->rec, R->start, R->cnt, d_goff, d_pre, D, nb, d_sums);
+    return check_launch(c, "scatter_buckets");
+}
+
+// Counting + sorting of bucket-contiguous records that are already in place (the receive window of the fused exchange).
+// d_off / d_cnt: device arrays of the n_local owned buckets (not arena memory).  n_kmers_local = k-mer occurrences held by the
+// records: the valid-k-mer buffer is sized by the exact bound, so the in-place deduplication never has to be undone.
+int filter_from_bucketed_dev(Ctx* c, int k, u64* d_records, u64 n_records, const u64* d_off, const u32* d_cnt, u32 n_local,
+                             u64 n_kmers_local, u64 n_input_total, u32 min_obs, int stranded, int report_all, Table** out) {
+    *out = nullptr;
+    if (k < 4 || k > 64 || !n_local) DBG_SET_ERR(c, DBG_E_BADARG, "bad arguments");
+    cudaStream_t st = c->stream;
+    dbg_stats& S = c->stats;
+    TRY(arena_begin(c));
+    CU(c, cudaEventRecord(c->ev[1], st));
+    Table* t = &(new dbg_kmer_table())->t;
+    t->ctx = c; t->k = k; t->n_input = n_input_total;
+    *out = t;
+    S.n_records = n_records;
+    S.n_input_kmers = n_kmers_local;
+    S.ms_k_count = 0;
+    if (n_records == 0) return DBG_OK;
+    int rc = DBG_OK;
+    {
+        CountOut co;
+        bool overflow = false;
+        if (k <= 32) {
+            rc = count_alloc<1>(c, n_kmers_local, min_obs, report_all, true, co);
+            if (rc == DBG_OK) rc = count_stage<1>(c, k, d_records, n_records, d_off, d_cnt, n_local, min_obs, stranded, report_all, co, &overflow);
+            if (rc == DBG_OK && !overflow) { cudaEventRecord(c->ev[2], st); rc = sort_stage<1>(c, k, report_all, co, t); }
+        } else {
+            rc = count_alloc<2>(c, n_kmers_local, min_obs, report_all, true, co);
+            if (rc == DBG_OK) rc = count_stage<2>(c, k, d_records, n_records, d_off, d_cnt, n_local, min_obs, stranded, report_all, co, &overflow);
+            if (rc == DBG_OK && !overflow) { cudaEventRecord(c->ev[2], st); rc = sort_stage<2>(c, k, report_all, co, t); }
+        }
+        if (rc == DBG_OK && overflow) { c->err = "valid k-mer buffer overflow with the exact bound"; rc = DBG_E_INTERNAL; }
+    }
+    if (rc != DBG_OK) { free_table(t); *out = nullptr; return rc; }
+    TRY(sync(c));
+    cudaEventElapsedTime(&S.ms_count, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&S.ms_sort, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&S.ms_k_count, c->ev[10], c->ev[11]);
+    S.gpu_launches = c->launches;
+    return DBG_OK;
+}
+
 // (defined above partition_reads_dev's first use)
 void free_partition(Partition* P) {
     if (!P) return;

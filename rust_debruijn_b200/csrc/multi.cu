@@ -364,51 +364,52 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     u64 bounds[DBG_MAX_RANKS + 1];
     owner_bounds(NB, P, bounds);
     const u64 n_own = bounds[me + 1] - bounds[me];
-    // ---- partition the own reads into bucket-ordered super-k-mer records ----
-    Partition* part = nullptr;
-    TRY(partition_reads_dev(c, k, s, stranded, p, bbits, &part));
+    // ---- partition the own reads into per-bucket regions of super-k-mer records (no compaction here) ----
+    PartRegions* part = nullptr;
+    TRY(partition_regions_dev(c, k, s, stranded, p, bbits, &part));
+    struct PartGuard { PartRegions* r; ~PartGuard() { if (r) free_part_regions(r); } } pg{part};
     tm.mark(st);   // 1
     const u32 rec_bytes = (u32)part->rec_words * 8;
-    std::vector<u32> h_cnt(NB);
-    CU(c, cudaMemcpyAsync(h_cnt.data(), part->bucket_count, NB * 4, cudaMemcpyDeviceToHost, st));
-    // per-bucket counts to the owners
-    DBuf<u32> d_rcnt;
-    TRY(d_rcnt.alloc_pool(c, (u64)P * n_own));
-    u64 so[DBG_MAX_RANKS], sc[DBG_MAX_RANKS], ro[DBG_MAX_RANKS], rc[DBG_MAX_RANKS];
-    for (int r = 0; r < P; r++) { so[r] = bounds[r] * 4; sc[r] = (bounds[r + 1] - bounds[r]) * 4; ro[r] = (u64)r * n_own * 4; rc[r] = n_own * 4; }
-    int rcode = T->all_to_all_v(part->bucket_count, so, sc, d_rcnt.p, ro, rc);
-    std::vector<u32> h_rcnt((u64)P * n_own);
-    if (rcode == DBG_OK) {
-        cudaMemcpyAsync(h_rcnt.data(), d_rcnt.p, (u64)P * n_own * 4, cudaMemcpyDeviceToHost, st);
-        rcode = sync(c);
-    }
-    if (rcode != DBG_OK) { free_partition(part); return rcode; }
-    // ---- the path's one big exchange: super-k-mer records by owning rank ----
-    u64 n_recv = 0;
-    {
-        u64 acc = 0;
-        for (int r = 0; r < P; r++) {
-            u64 t = 0;
-            for (u64 b = bounds[r]; b < bounds[r + 1]; b++) t += h_cnt[b];
-            so[r] = acc * rec_bytes; sc[r] = t * rec_bytes; acc += t;
-        }
-        for (int r = 0; r < P; r++) {
-            u64 t = 0;
-            for (u64 b = 0; b < n_own; b++) t += h_rcnt[(u64)r * n_own + b];
-            ro[r] = n_recv * rec_bytes; rc[r] = t * rec_bytes; n_recv += t;
-        }
-        for (int r = 0; r < P; r++) if (r != me) I.exchange_bytes_sent += sc[r];
-    }
-    DBuf<u64> recv;
-    rcode = recv.alloc_pool(c, n_recv * part->rec_words);
-    if (rcode == DBG_OK) rcode = T->all_to_all_v(part->rec, so, sc, recv.p, ro, rc);
-    free_partition(part);   // stream-ordered: after the sends
-    if (rcode != DBG_OK) return rcode;
+    u64 so[DBG_MAX_RANKS], sc[DBG_MAX_RANKS], ro[DBG_MAX_RANKS], rc[DBG_MAX_RANKS];   // byte offsets / counts of the later all-to-alls
+    // ---- the path's one big exchange, fused with the compaction: every rank learns every rank's per-bucket record counts (one small
+    // all-gather), so each sender knows the FINAL position of each of its buckets inside the owner's bucket-contiguous receive
+    // window, and one kernel copies the records there over peer memory (NVLink stores).  No send buffer, no gap-closing pass, no
+    // per-source merge on the receiver; the closing all-reduce is the barrier and carries the k-mer totals. ----
+    DBuf<u32> d_allcnt, d_btot, d_pre, d_cnt_loc;
+    DBuf<u64> d_goff, d_sums, d_gb, d_off_loc;
+    TRY(d_allcnt.alloc_pool(c, (u64)P * NB)); TRY(d_btot.alloc_pool(c, NB)); TRY(d_pre.alloc_pool(c, NB)); TRY(d_goff.alloc_pool(c, NB + 1));
+    TRY(d_sums.alloc_pool(c, 2 * DBG_MAX_RANKS)); TRY(d_gb.alloc_pool(c, DBG_MAX_RANKS + 1));
+    TRY(d_off_loc.alloc_pool(c, n_own + 1)); TRY(d_cnt_loc.alloc_pool(c, n_own ? n_own : 1));
+    TRY(T->all_gather(part->cnt, d_allcnt.p, NB * 4));
+    TRY(bucket_totals_dev(c, d_allcnt.p, P, me, (u32)NB, d_btot.p, d_pre.p));
+    TRY(exclusive_scan_u32_to_u64(c, d_btot.p, d_goff.p, NB, d_goff.p + NB));
+    for (int r = 0; r <= P; r++) CU(c, cudaMemcpyAsync(d_gb.p + r, d_goff.p + bounds[r], 8, cudaMemcpyDeviceToDevice, st));
+    u64 gb[DBG_MAX_RANKS + 1];
+    TRY(read_u64(c, d_gb.p, gb, P + 1));
+    const u64 n_recv = gb[me + 1] - gb[me];
+    TRY(T->ensure_window((n_recv ? n_recv : 1) * rec_bytes));
+    ScatterDst D;
+    D.P = P;
+    for (int r = 0; r < DBG_MAX_RANKS; r++) { D.base[r] = r < P ? reinterpret_cast<u64*>(T->peer_ptr[r]) : nullptr; D.bound[r] = r <= P ? bounds[r] : NB; }
+    D.bound[DBG_MAX_RANKS] = NB;
+    for (int r = P; r <= DBG_MAX_RANKS; r++) D.bound[r] = NB;
+    CU(c, cudaMemsetAsync(d_sums.p, 0, 8 * 2 * DBG_MAX_RANKS, st));
+    TRY(scatter_buckets_dev(c, part, d_goff.p, d_pre.p, D, d_sums.p));
+    u64 sent[2 * DBG_MAX_RANKS];
+    TRY(read_u64(c, d_sums.p, sent, 2 * P));
+    for (int r = 0; r < P; r++) if (r != me) I.exchange_bytes_sent += sent[P + r] * rec_bytes;
+    free_part_regions(part);   // (the scatter kernel has completed: read_u64 waited for it)
+    pg.r = nullptr;
+    TRY(T->all_reduce_sum(d_sums.p, P, true));   // every rank's stores have landed once this completes; sums[r] = k-mer occurrences rank r holds
+    u64 kin[DBG_MAX_RANKS];
+    TRY(read_u64(c, d_sums.p, kin, P));
+    TRY(local_buckets_dev(c, d_goff.p, d_btot.p, (u32)bounds[me], (u32)n_own, d_off_loc.p, d_cnt_loc.p));
     tm.mark(st);   // 2
     // ---- count the owned buckets, sort the valid k-mers: this rank's shard of the table ----
     Table* shard = nullptr;
-    TRY(filter_from_records_dev(c, k, recv.p, n_recv, h_rcnt.data(), (u32)P, (u32)n_own, tot, min_obs, stranded, 0, &shard));
-    recv.release();
+    TRY(filter_from_bucketed_dev(c, k, reinterpret_cast<u64*>(T->win), n_recv, d_off_loc.p, d_cnt_loc.p, (u32)n_own, kin[me], tot, min_obs, stranded,
+                                 0, &shard));
+    d_allcnt.release(); d_btot.release(); d_pre.release(); d_goff.release(); d_off_loc.release(); d_cnt_loc.release();
     tm.mark(st);   // 3
     struct TableGuard { Table* t; ~TableGuard() { if (t) free_table(t); } } tg{shard};
     const u64 V = shard->n;
