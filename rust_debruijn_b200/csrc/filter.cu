@@ -1711,7 +1711,13 @@ static int partition_direct(Ctx* c, int k, const SeqSet* s, int stranded, u64 N,
         CU(c, cudaStreamWaitEvent(st, sm->pend_ev[0], 0));
         t_s = tiles_upto(0);
     }
-    const u32 stride = (u32)std::max<u64>(1, t_s * 16 / ta.n_tiles);
+    // thinning: every 16th tile when the buckets are large; small buckets (many buckets per k-mer: multi-GPU jobs) need a denser
+    // sample, or the capacity of a bucket the sample happened to miss falls below its true size (measured at 2^19 buckets of
+    // ~140 records, 1 : 16: a few of the 524 288 regions overflowed on most calls and the whole partition was redone by the
+    // staging path).  >= ~32 sampled records per bucket keeps that below 1e-9 per bucket.
+    const double rec_per_bucket = 2.0 * (double)N / (double)(k - p + 2) / (double)NB;
+    const u64 thin = (u64)std::min(16.0, std::max(1.0, rec_per_bucket / 32.0));
+    const u32 stride = (u32)std::max<u64>(1, t_s * thin / ta.n_tiles);
     const u64 n_sampled = (t_s + stride - 1) / stride;
     const float scale = (float)((double)ta.n_tiles / (double)std::max<u64>(n_sampled, 1));
     {
@@ -2139,6 +2145,7 @@ int partition_regions_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, i
     }
     TRY(sync(c));
     if (N) cudaEventElapsedTime(&c->stats.ms_k_partition, c->ev[8], c->ev[9]);
+    if (getenv("DBG_MULTI_TRACE")) fprintf(stderr, "[dbg multi] partition: direct=%d records=%llu buckets=2^%d p=%d\n", R->direct, (unsigned long long)R->n_rec, bbits, p);
     c->stats.n_records = R->n_rec;
     c->stats.n_input_kmers = N;
     guard.r = nullptr;

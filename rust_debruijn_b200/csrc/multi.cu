@@ -506,7 +506,10 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
             u64 inflight = 0;
             for (u64 i = 0; i < (u64)P * P; i++) inflight += allc[i];
             if (collect) n_done = own[0]; else { n_paths = own[0]; n_cov = own[1]; }
-            if (!inflight) return DBG_OK;
+            if (!inflight) {
+                if (getenv("DBG_MULTI_TRACE") && me == 0) fprintf(stderr, "[dbg multi] %s rounds: %d\n", collect ? "collect" : "walk", round + 1);
+                return DBG_OK;
+            }
             u64 s_o[DBG_MAX_RANKS], s_c[DBG_MAX_RANKS], r_o[DBG_MAX_RANKS], r_c[DBG_MAX_RANKS];
             n_in = 0;
             for (int r = 0; r < P; r++) {
@@ -544,6 +547,8 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     }
     // ---- walk 2: the nodes themselves (finished where their right end lives) ----
     TRY(run_rounds(true));
+    EvTimer tl;   // finer timing of the layout stage (DBG_MULTI_TRACE)
+    tl.mark(st);
     obox.release(); ibox.release();
     n_paths = n_done;   // from here on: the finished nodes held by this rank
     DBuf<u64> pk_lo, pk_hi;
@@ -585,7 +590,9 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     u64 m_own = 0;
     for (int r = 0; r < P; r++) { so[r] = pbound[r] * pb; sc[r] = psend[r] * pb; ro[r] = m_own * pb; rc[r] = PM[(u64)r * P + me] * pb; m_own += PM[(u64)r * P + me]; }
     TRY(pmsg_in.alloc_pool(c, (m_own ? m_own : 1) * pb));
+    tl.mark(st);
     TRY(T->all_to_all_v(pmsg_out.p, so, sc, pmsg_in.p, ro, rc));
+    tl.mark(st);
     // ---- own seed range: sort, node lengths, offsets ----
     DBuf<u64> nk_lo, nk_hi, nk_lo_b, nk_hi_b, node_len, node_start, d_tot;
     DBuf<u32> ni_a, ni_b, olen;
@@ -597,6 +604,7 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     u64 *sk_lo = nk_lo.p, *sk_hi = nk_hi.p;
     u32* sidx = ni_a.p;
     TRY(radix_sort_pairs(c, W, 2 * k, m_own, nk_lo.p, nk_hi.p, ni_a.p, nk_lo_b.p, nk_hi_b.p, ni_b.p, &sk_lo, &sk_hi, &sidx));
+    tl.mark(st);
     TRY(ms_node_len_dev(c, k, pmsg_in.p, sidx, m_own, node_len.p, olen.p));
     u64 nb_own = 0;
     if (m_own) {
@@ -634,6 +642,13 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     I.check_ok = I.n_bases_total == I.n_valid_total + I.n_nodes_total * (u64)(k - 1);
     I.ms_partition = tm.ms(0, 1); I.ms_exchange = tm.ms(1, 2); I.ms_count_sort = tm.ms(2, 3); I.ms_links = tm.ms(3, 4);
     I.ms_discover = tm.ms(4, 5); I.ms_layout = tm.ms(5, 6); I.ms_emit = tm.ms(6, 7); I.ms_total = tm.ms(0, 8);
+    if (getenv("DBG_MULTI_TRACE") && me == 0) {
+        float t_col = 0, t_lay = 0;
+        cudaEventElapsedTime(&t_col, tm.ev[5], tl.ev[0]);
+        cudaEventElapsedTime(&t_lay, tl.ev[3], tm.ev[6]);
+        fprintf(stderr, "[dbg multi] layout: collect rounds %.2f | unpack+hist+cuts+scatter %.2f | a2a %.2f | unpack+sort %.2f | len+scan+gather %.2f ms; nodes here %llu\n",
+                t_col, tl.ms(0, 1), tl.ms(1, 2), tl.ms(2, 3), t_lay, (unsigned long long)m_own);
+    }
     c->stats.n_valid = V; c->stats.n_nodes = m_own; c->stats.n_bases = nb_own;
     c->stats.gpu_launches = c->launches;
     if (info) *info = I;
