@@ -348,13 +348,10 @@ struct WalkOut {
     int P;
 };
 int ms_count_ends_dev(Ctx* c, const uint4* d_rec, u64 n, u64* d_out);
-u32 ms_witem_bytes();
-u32 ms_entry_bytes();
-u32 ms_citem_bytes(int k);
-int ms_walk_start_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, u64 n, u32 lmax, const WalkOut& out);
-int ms_walk_continue_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, const void* inbox, u64 n_in, u32 lmax, const WalkOut& out);
-int ms_collect_start_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, const void* entries, u64 n, int reduce_op, const WalkOut& out);
-int ms_collect_continue_dev(Ctx* c, int k, const uint4* rec, int me, const void* inbox, u64 n, int reduce_op, const WalkOut& out);
+u32 ms_fitem_bytes(int k);
+int ms_fwalk_start_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, u64 n, u32 lmax, int reduce_op, const WalkOut& out);
+int ms_fwalk_continue_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, const void* inbox, u64 n_in, u32 lmax, int reduce_op,
+                          const WalkOut& out);
 int ms_scatter_nodes_dev(Ctx* c, int k, const void* nmsg, u64 m, int P, int bits, const u64* cuts, const u64* seg_off, void* out);
 int ms_unpack_nodes_dev(Ctx* c, int k, const void* in, u64 m, u64* k_lo, u64* k_hi, u32* idx);
 int ms_node_len_dev(Ctx* c, int k, const void* msgs, const u32* idx, u64 m, u64* node_len, u32* out_length);

@@ -461,42 +461,36 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     u32 lerr = 0;
     TRY(ms_link_error(c, &q, &lerr));
     tm.mark(st);   // 4
-    // ---- discover + collect: walkers that never leave their rank; a walk that must continue elsewhere is shipped there ----
+    // ---- discover + collect in ONE pass of walker rounds (shard_compress.cu, fused walk): a walker never leaves its rank — when its
+    // chain continues on another rank it is shipped there with the node collected so far; finished nodes stay where their right end lives ----
     const uint4* rec = my_rec;
-    const u32 wib = ms_witem_bytes(), enb = ms_entry_bytes(), cib = ms_citem_bytes(k), pb = ms_path_bytes(k);
+    const u32 fib = ms_fitem_bytes(k), pb = ms_path_bytes(k);
     DBuf<u64> d_ends, cur, d_allc;
     TRY(d_ends.alloc_pool(c, 1)); TRY(cur.alloc_pool(c, DBG_MAX_RANKS + 4)); TRY(d_allc.alloc_pool(c, (u64)P * P));
     TRY(ms_count_ends_dev(c, rec, V, d_ends.p));
     u64 n_ends = 0;
     TRY(read_u64(c, d_ends.p, &n_ends));
-    // capacities: a link side is crossed at most once per direction, so rank d receives at most (my link sides pointing at d)
-    // walkers from me, plus one notice per walker d ever sent me
+    // capacities: a link side is crossed at most once per direction, so rank d receives at most (my link sides pointing at d) walkers from me
     u64 ocap[DBG_MAX_RANKS + 1], ooff[DBG_MAX_RANKS + 1], icap = 0, otot = 0;
-    for (int r = 0; r < P; r++) { ocap[r] = q.n_dst[r] + M[(u64)r * P + me] + 32; ooff[r] = otot; otot += ocap[r]; icap += q.n_dst[r] + M[(u64)r * P + me] + 32; }
+    for (int r = 0; r < P; r++) { ocap[r] = q.n_dst[r] + 32; ooff[r] = otot; otot += ocap[r]; icap += M[(u64)r * P + me] + 32; }
     const u64 ecap = n_ends + 32;
-    DBuf<unsigned char> obox, ibox, entries, nmsg;
-    TRY(obox.alloc_pool(c, otot * (u64)std::max(wib, cib))); TRY(ibox.alloc_pool(c, icap * (u64)std::max(wib, cib)));
-    TRY(entries.alloc_pool(c, ecap * enb)); TRY(nmsg.alloc_pool(c, ecap * pb));
-    u64 n_paths = 0, n_cov = 0, n_done = 0;
+    DBuf<unsigned char> obox, ibox, nmsg;
+    TRY(obox.alloc_pool(c, otot * (u64)fib)); TRY(ibox.alloc_pool(c, icap * (u64)fib));
+    TRY(nmsg.alloc_pool(c, ecap * pb));
+    u64 n_paths = 0, n_cov = 0;
     std::vector<u64> allc((u64)P * P);
-    auto run_rounds = [&](bool collect) -> int {
-        // per-destination outboxes (item size isz), the rank's own list (emit entries / finished nodes) as destination P
-        const u32 isz = collect ? cib : wib;
+    auto run_rounds = [&]() -> int {
+        // per-destination outboxes, the rank's own list of finished nodes as destination P
         WalkOut wo;
-        for (int r = 0; r < P; r++) { wo.box[r] = obox.p + ooff[r] * isz; wo.cap[r] = ocap[r]; }
+        for (int r = 0; r < P; r++) { wo.box[r] = obox.p + ooff[r] * fib; wo.cap[r] = ocap[r]; }
         for (int r = P; r <= DBG_MAX_RANKS; r++) { wo.box[r] = nullptr; wo.cap[r] = 0; }
-        wo.box[P] = collect ? nmsg.p : entries.p; wo.cap[P] = ecap;
+        wo.box[P] = nmsg.p; wo.cap[P] = ecap;
         wo.cursor = cur.p; wo.P = P;
         CU(c, cudaMemsetAsync(cur.p, 0, 8 * (DBG_MAX_RANKS + 4), st));
         u64 n_in = 0;
         for (int round = 0; round < 4096; round++) {
-            if (round == 0) {
-                if (collect) TRY(ms_collect_start_dev(c, k, rec, my_klo, my_khi, me, entries.p, n_paths, reduce_op, wo));
-                else TRY(ms_walk_start_dev(c, k, rec, my_klo, my_khi, me, V, 1024u, wo));
-            } else {
-                if (collect) TRY(ms_collect_continue_dev(c, k, rec, me, ibox.p, n_in, reduce_op, wo));
-                else TRY(ms_walk_continue_dev(c, k, rec, my_klo, my_khi, me, ibox.p, n_in, 1024u, wo));
-            }
+            if (round == 0) TRY(ms_fwalk_start_dev(c, k, rec, my_klo, my_khi, me, V, 1024u, reduce_op, wo));
+            else TRY(ms_fwalk_continue_dev(c, k, rec, my_klo, my_khi, me, ibox.p, n_in, 1024u, reduce_op, wo));
             // everybody learns everybody's outbox counts: the same matrix on every rank decides when the rounds end
             TRY(T->all_gather(cur.p, d_allc.p, 8ull * P));
             u64 own[3];
@@ -505,16 +499,16 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
             if (own[2]) DBG_SET_ERR(c, DBG_E_INTERNAL, "walker buffer overflow");
             u64 inflight = 0;
             for (u64 i = 0; i < (u64)P * P; i++) inflight += allc[i];
-            if (collect) n_done = own[0]; else { n_paths = own[0]; n_cov = own[1]; }
+            n_paths = own[0]; n_cov = own[1];
             if (!inflight) {
-                if (getenv("DBG_MULTI_TRACE") && me == 0) fprintf(stderr, "[dbg multi] %s rounds: %d\n", collect ? "collect" : "walk", round + 1);
+                if (getenv("DBG_MULTI_TRACE") && me == 0) fprintf(stderr, "[dbg multi] walker rounds: %d\n", round + 1);
                 return DBG_OK;
             }
             u64 s_o[DBG_MAX_RANKS], s_c[DBG_MAX_RANKS], r_o[DBG_MAX_RANKS], r_c[DBG_MAX_RANKS];
             n_in = 0;
             for (int r = 0; r < P; r++) {
-                s_o[r] = ooff[r] * isz; s_c[r] = allc[(u64)me * P + r] * isz;
-                r_o[r] = n_in * isz; r_c[r] = allc[(u64)r * P + me] * isz; n_in += allc[(u64)r * P + me];
+                s_o[r] = ooff[r] * fib; s_c[r] = allc[(u64)me * P + r] * fib;
+                r_o[r] = n_in * fib; r_c[r] = allc[(u64)r * P + me] * fib; n_in += allc[(u64)r * P + me];
             }
             if (n_in > icap) DBG_SET_ERR(c, DBG_E_INTERNAL, "walker inbox overflow");
             TRY(T->all_to_all_v(obox.p, s_o, s_c, ibox.p, r_o, r_c));
@@ -522,7 +516,7 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
         }
         DBG_SET_ERR(c, DBG_E_INTERNAL, "walker rounds did not terminate");
     };
-    TRY(run_rounds(false));
+    TRY(run_rounds());
     u64 red[5] = {V, n_cov, n_paths, lerr == 1 ? 1ull : 0ull, lerr == 2 ? 1ull : 0ull};
     TRY(T->all_reduce_host(red, 5));
     I.n_valid_total = red[0];
@@ -545,12 +539,9 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
         *out = g;
         return DBG_OK;
     }
-    // ---- walk 2: the nodes themselves (finished where their right end lives) ----
-    TRY(run_rounds(true));
     EvTimer tl;   // finer timing of the layout stage (DBG_MULTI_TRACE)
     tl.mark(st);
     obox.release(); ibox.release();
-    n_paths = n_done;   // from here on: the finished nodes held by this rank
     DBuf<u64> pk_lo, pk_hi;
     DBuf<u32> pk_idx;
     TRY(pk_lo.alloc_pool(c, n_paths ? n_paths : 1)); TRY(pk_idx.alloc_pool(c, n_paths ? n_paths : 1));
@@ -646,7 +637,7 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
         float t_col = 0, t_lay = 0;
         cudaEventElapsedTime(&t_col, tm.ev[5], tl.ev[0]);
         cudaEventElapsedTime(&t_lay, tl.ev[3], tm.ev[6]);
-        fprintf(stderr, "[dbg multi] layout: collect rounds %.2f | unpack+hist+cuts+scatter %.2f | a2a %.2f | unpack+sort %.2f | len+scan+gather %.2f ms; nodes here %llu\n",
+        fprintf(stderr, "[dbg multi] layout: (%.2f) | unpack+hist+cuts+scatter %.2f | a2a %.2f | unpack+sort %.2f | len+scan+gather %.2f ms; nodes here %llu\n",
                 t_col, tl.ms(0, 1), tl.ms(1, 2), tl.ms(2, 3), t_lay, (unsigned long long)m_own);
     }
     c->stats.n_valid = V; c->stats.n_nodes = m_own; c->stats.n_bases = nb_own;

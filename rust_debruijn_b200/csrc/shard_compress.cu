@@ -14,15 +14,13 @@
 //   records   16 bytes per k-mer: both links (index on the owning rank, side, owner rank), count, Exts, first / last
 //             base; next to them a copy of the shard's k-mers.  This WINDOW of every rank is mapped into every rank's
 //             address space (CUDA IPC over NVLink, or plain peer access inside one process).
-//   discover  every path end walks its unitig, hopping across ranks through the peer-mapped records (one 16-byte load
-//             per k-mer), tracking the smallest K-MER (= the seed, src/compression.rs:574-575: ascending k-mer order is
-//             the seed order).  Inside one shard index order IS k-mer order, so k-mers are only fetched when the walk
-//             changes rank.  The walk that traverses the seed "leaving through R" started at the node's left end and
-//             emits one path record (seed k-mer, length, left end).
+//   discover  every path end walks its unitig tracking the smallest K-MER (= the seed, src/compression.rs:574-575: ascending
+//             k-mer order is the seed order) and collecting the node; a walk never reads another rank's records: at a rank
+//             change the walker itself is shipped (see "WALKER HAND-OFF" below).
 //   layout    path records go to the rank owning their seed's key range (quantile cuts of an all-reduced histogram,
 //             one CTA-aggregated scatter by destination): that rank sorts them and holds a contiguous run of nodes of
 //             the final order.
-//   emit      the left-end walker of discover already collected the node (bases, Exts, data) into its message, so the
+//   emit      the left-end walker already collected the node (bases, Exts, data) into its message, so the
 //             owner of the key range only copies bits into the bit-contiguous PackedDnaStringSet words; nodes too long for
 //             a message are re-walked there through the peer windows.
 // Only unitigs reachable by end walks (<= lmax k-mers) are handled here; the caller falls back to gathering the table
@@ -244,41 +242,13 @@ __global__ void ms_apply_kernel(KP kp, const u64* __restrict__ lo, const u64* __
 // through peer-mapped records took 9 ms on 2 GPUs and 412 ms on 8, against 1.7 ms on one), so a walk never leaves its
 // rank: when the next k-mer lives elsewhere the WALKER is shipped there — a 32-byte item in a per-destination outbox,
 // exchanged in bulk once per round (all-to-all) — and continues on the records of the rank that owns them.
-//   walk 1  every path end walks inwards tracking the smallest k-mer (index order = k-mer order inside a shard; k-mers are
-//           compared only at a rank change) and the side through which the walk leaves it.  The walker that reaches the
-//           far end and left the seed "through R" started at the node's LEFT end (compression.rs:574-583, ascending seed
-//           order): the left end's rank gets an emit entry (left end, seed k-mer, length) — directly or by a notice item.
-//   walk 2  every emit entry walks the node once more from its left end and collects it: bases (left-aligned words in
-//           registers), end Exts (compression.rs:513-517,534-540), reduced data (:500-511); at a rank change the partial
-//           node travels on as an 80/112-byte item.  The rank where the walk ends holds the finished NodeMsg.
+//   Every path end starts a walker that tracks the smallest k-mer (index order = k-mer order inside a shard; k-mers are compared
+//   only at a rank change) and the side through which the walk leaves it, and that collects the node as it goes: bases
+//   (left-aligned words in registers), end Exts (compression.rs:513-517,534-540), reduced data (:500-511).  The walker that
+//   reaches the far end having left the seed "through R" started at the node's LEFT end (compression.rs:574-583, ascending seed
+//   order): it holds the finished NodeMsg, which stays on the rank where the walk ended; the walker from the other end is dropped.
 // Every walker emits at most ONE thing, so outputs are appended with one reservation per (CTA, destination).
-static const u32 IT_WALK = 0, IT_NOTICE = 1;
-// info = origin rank | side through which the walk leaves the current minimum << 8 | kind << 9
-struct __align__(16) WItem { u64 lo, hi; u32 port, cnt, origin_port, info; };                       // 32 bytes
-template <int W> struct __align__(16) CItem { NodeMsg<W> node; u32 port, done; u64 acc; };          // 80 / 112 bytes
-struct __align__(16) EmitEntry { u64 lo, hi; u32 port, len; u64 pad; };   // 32 bytes: left end (port state on this rank), seed k-mer, length
-
-template <typename T>
-__device__ __forceinline__ void walk_append(const WalkOut& o, int dest, bool have, const T& item, u32 covered) {
-    __shared__ u32 s_cnt[DBG_MAX_RANKS + 1], s_cov;
-    __shared__ u64 s_base[DBG_MAX_RANKS + 1];
-    if (threadIdx.x <= DBG_MAX_RANKS) s_cnt[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_cov = 0;
-    __syncthreads();
-    u32 loc = 0;
-    if (have) { loc = atomicAdd(&s_cnt[dest], 1u); if (covered) atomicAdd(&s_cov, covered); }
-    __syncthreads();
-    if (threadIdx.x <= DBG_MAX_RANKS && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&o.cursor[threadIdx.x], (u64)s_cnt[threadIdx.x]);
-    if (threadIdx.x == 0 && s_cov) atomicAdd(&o.cursor[o.P + 1], (u64)s_cov);
-    __syncthreads();
-    if (have) {
-        const u64 pos = s_base[dest] + loc;
-        if (pos < o.cap[dest]) reinterpret_cast<T*>(o.box[dest])[pos] = item;
-        else o.cursor[o.P + 2] = 1;
-    }
-}
-
-// local part of walk 1: from port state `t` (at k-mer t >> 1 of THIS rank, about to be counted) onwards while the links
+// local part of a walk without collection: from port state `t` (at k-mer t >> 1 of THIS rank, about to be counted) onwards while the links
 // stay on this rank.  Returns the state the walk stops at: NIL (path end) or a port on rank `trank`.
 struct LocalMin { u32 idx, side; bool any; };
 __device__ __forceinline__ u32 walk_local(const uint4* __restrict__ rec, int me, u32 t, u32& trank, u32& cnt, u32 lmax, LocalMin& lm) {
@@ -298,110 +268,7 @@ __device__ __forceinline__ Kmer<W> local_key(const u64* __restrict__ klo, const 
     if constexpr (W == 1) return Kmer<1>{klo[idx]}; else return Kmer<2>{klo[idx], khi[idx]};
 }
 
-// walk 1, round 0: thread per k-mer of the shard
-template <int W>
-__global__ void __launch_bounds__(256) ms_walk_start_kernel(const uint4* __restrict__ rec, const u64* __restrict__ klo, const u64* __restrict__ khi,
-                                                             int me, u64 n, u32 lmax, WalkOut out) {
-    const u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    bool have = false, is_entry = false;
-    int dest = 0;
-    u32 covered = 0;
-    WItem it;
-    EmitEntry en;
-    it.lo = it.hi = 0; it.port = it.cnt = it.origin_port = it.info = 0;
-    en.lo = en.hi = 0; en.port = en.len = 0; en.pad = 0;
-    if (v < n) {
-        const uint4 a0 = rec[v];
-        if (a0.x == NIL && a0.y == NIL) {
-            const Kmer<W> key = local_key<W>(klo, khi, (u32)v);
-            have = is_entry = true; dest = out.P; covered = 1;
-            en.lo = key.lo; if constexpr (W == 2) en.hi = key.hi;
-            en.port = 2u * (u32)v + 1u; en.len = 1;   // stored orientation: heading right = leaving through R
-        } else if (a0.x == NIL || a0.y == NIL) {
-            const u32 d = a0.x == NIL ? 1u : 0u;   // the linked side: walk inwards through it
-            u32 cnt = 1;
-            LocalMin lm{(u32)v, d, true};
-            u32 t = d ? a0.y : a0.x;
-            u32 trank = (a0.w >> (8 * d)) & 0xffu;
-            t = walk_local(rec, me, t, trank, cnt, lmax, lm);
-            if (cnt <= lmax) {
-                const Kmer<W> key = local_key<W>(klo, khi, lm.idx);
-                if (t == NIL) {
-                    if (lm.side == 1u) {   // the whole path is local and this end is its left end
-                        have = is_entry = true; dest = out.P; covered = cnt;
-                        en.lo = key.lo; if constexpr (W == 2) en.hi = key.hi;
-                        en.port = 2u * (u32)v + d; en.len = cnt;
-                    }
-                } else {
-                    have = true; dest = (int)trank;
-                    it.lo = key.lo; if constexpr (W == 2) it.hi = key.hi;
-                    it.port = t; it.cnt = cnt; it.origin_port = 2u * (u32)v + d;
-                    it.info = (u32)me | (lm.side << 8) | (IT_WALK << 9);
-                }
-            }
-        }
-    }
-    // (both item types are 32 bytes: one append serves the outboxes and the emit list)
-    if (is_entry) it = *reinterpret_cast<WItem*>(&en);
-    walk_append<WItem>(out, dest, have, it, covered);
-}
-
-// walk 1, later rounds: thread per received item
-template <int W>
-__global__ void __launch_bounds__(256) ms_walk_continue_kernel(const uint4* __restrict__ rec, const u64* __restrict__ klo, const u64* __restrict__ khi,
-                                                                int me, const WItem* __restrict__ inbox, u64 n_in, u32 lmax, WalkOut out) {
-    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    bool have = false;
-    int dest = 0;
-    u32 covered = 0;
-    WItem it;
-    it.lo = it.hi = 0; it.port = it.cnt = it.origin_port = it.info = 0;
-    if (q < n_in) {
-        it = inbox[q];
-        const u32 kind = (it.info >> 9) & 1u;
-        if (kind == IT_NOTICE) {   // "your port origin_port is the left end of a node": becomes an emit entry here
-            EmitEntry en;
-            en.lo = it.lo; en.hi = it.hi; en.port = it.origin_port; en.len = it.cnt; en.pad = 0;
-            have = true; dest = out.P; covered = it.cnt;
-            it = *reinterpret_cast<WItem*>(&en);
-        } else {
-            u32 cnt = it.cnt, trank = (u32)me;
-            LocalMin lm{0, 0, false};
-            u32 t = walk_local(rec, me, it.port, trank, cnt, lmax, lm);
-            if (cnt <= lmax) {
-                Kmer<W> ckey;
-                if constexpr (W == 1) ckey = Kmer<1>{it.lo}; else ckey = Kmer<2>{it.lo, it.hi};
-                u32 cside = (it.info >> 8) & 1u;
-                const Kmer<W> lk = local_key<W>(klo, khi, lm.idx);   // lm.any: the item's port is a k-mer of this rank
-                if (lk < ckey) { ckey = lk; cside = lm.side; }
-                it.lo = ckey.lo; if constexpr (W == 2) it.hi = ckey.hi;
-                it.cnt = cnt;
-                const u32 origin = it.info & 0xffu;
-                if (t == NIL) {
-                    if (cside == 1u) {   // the walker started at the node's left end
-                        have = true; covered = 0;
-                        if (origin == (u32)me) {
-                            EmitEntry en;
-                            en.lo = it.lo; en.hi = it.hi; en.port = it.origin_port; en.len = cnt; en.pad = 0;
-                            dest = out.P; covered = cnt;
-                            it = *reinterpret_cast<WItem*>(&en);
-                        } else {
-                            dest = (int)origin;
-                            it.info = origin | (1u << 8) | (IT_NOTICE << 9);
-                        }
-                    }
-                } else {
-                    have = true; dest = (int)trank;
-                    it.port = t;
-                    it.info = origin | (cside << 8) | (IT_WALK << 9);
-                }
-            }
-        }
-    }
-    walk_append<WItem>(out, dest, have, it, covered);
-}
-
-// ---- walk 2: collect the node ----
+// ---- collecting a node along a walk ----
 template <int W>
 struct Collector {
     static constexpr int NBW = NodeCfg<W>::NBW;
@@ -462,103 +329,148 @@ struct Collector {
     }
 };
 
-// common tail of the two collect kernels: walk on while the links are local, then finish the node or hand it off
+// ---- fused walk: ONE pass of walker rounds instead of two (find the seed and the left end, then collect the node).  Both end
+// walkers of a path collect the node as they go (bases in their own direction of travel, Exts of their first k-mer, data); the one
+// that turns out to have started at the node's left end — it traversed the seed "leaving through R" — arrives at the far end with
+// the finished node and appends it to that rank's list, the other one is dropped there.  Half the rounds (each one a kernel, a
+// count exchange and an all-to-all), no notices, no emit entries; the price is that every walker carries a node message. ----
+// info = origin rank | side through which the walk leaves the current minimum << 8 | bases overflowed the message << 9
+template <int W> struct __align__(16) FItem { NodeMsg<W> node; u32 port, done; u64 acc; u32 origin_port, info; u64 pad; };
+
 template <int W>
-__device__ __forceinline__ void collect_run(const KP& kp, const uint4* __restrict__ rec, int me, Collector<W>& col, u32 cur, u32 crank, u32 len,
-                                            int reduce_op, Kmer<W> seed, bool active, WalkOut out) {
+__device__ __forceinline__ void fwalk_run(const KP& kp, const uint4* __restrict__ rec, const u64* __restrict__ klo, const u64* __restrict__ khi,
+                                          int me, FItem<W>& it, bool active, u32 lmax, int reduce_op, WalkOut out) {
     constexpr int NBW = NodeCfg<W>::NBW;
+    bool finished = false;
+    u32 crank = (u32)me, covered = 0;
     if (active) {
-        while (col.done < len && crank == (u32)me && cur != NIL) {
-            const uint4 r = rec[cur >> 1];
-            col.next(kp, r, cur, len, reduce_op);
-            const u32 dw = cur & 1u;
+        Collector<W> col;
+#pragma unroll
+        for (int w = 0; w < NBW; w++) col.bw[w] = it.node.b[w];
+        col.acc = it.acc; col.done = it.done; col.eb = (it.node.meta >> 16) & 0xffu;
+        bool islong = (it.info >> 9) & 1u;
+        u32 cur = it.port;
+        LocalMin lm{0, 0, false};
+        uint4 r_last = make_uint4(NIL, NIL, 0, 0);
+        u32 cur_last = 0;
+        while (cur != NIL && crank == (u32)me && col.done <= lmax) {
+            const u32 idx = cur >> 1, dw = cur & 1u;
+            const uint4 r = rec[idx];
+            if (!lm.any || idx < lm.idx) { lm.idx = idx; lm.side = dw; lm.any = true; }
+            if (col.done == 0) col.first(kp, r, local_key<W>(klo, khi, idx), cur, 0u);   // (len unknown: the right nibble is set at the end)
+            else if (islong || (u32)kp.k + col.done > 32u * NBW) { islong = true; col.done++; }
+            else col.next(kp, r, cur, 0u, reduce_op);
+            r_last = r; cur_last = cur;
             cur = dw ? r.y : r.x;
             crank = (r.w >> (8 * dw)) & 0xffu;
         }
-    }
-    CItem<W> ci;
-    ci.node.lo = seed.lo;
-    if constexpr (W == 2) ci.node.hi = seed.hi;
+        // the smallest k-mer seen so far and the side through which the walk left it
+        Kmer<W> ckey;
+        if constexpr (W == 1) ckey = Kmer<1>{it.node.lo}; else ckey = Kmer<2>{it.node.lo, it.node.hi};
+        u32 cside = (it.info >> 8) & 1u;
+        const bool had = it.done != 0;
+        if (lm.any) {
+            const Kmer<W> lk = local_key<W>(klo, khi, lm.idx);
+            if (!had || lk < ckey) { ckey = lk; cside = lm.side; }
+        }
+        it.node.lo = ckey.lo;
+        if constexpr (W == 2) it.node.hi = ckey.hi;
+        const u32 origin = it.info & 0xffu;
+        if (col.done > lmax) active = false;                    // too long for end walks: the caller falls back
+        else if (cur == NIL) {
+            if (cside != 1u) active = false;                    // started at the right end: the other walker delivers the node
+            else {
+                finished = true; covered = col.done;
+                const u32 dw = cur_last & 1u;
+                u32 rn = exts_side((r_last.z >> 16) & 0xffu, (int)dw);   // right-facing side of the last k-mer (:534-540)
+                if (dw != 1u) rn = exts_complement(rn) & 0xfu;
+                col.eb |= rn << 4;
+                if (islong) {   // the owner of the key range re-walks it from its left end through the peer windows
+                    it.node.b[0] = it.origin_port;
+                    it.node.meta = col.done | ((col.eb & 0xffu) << 16) | (NODE_LONG << 24);
+                    it.node.aux = origin << 16;
+                } else {
 #pragma unroll
-    for (int w = 0; w < NBW; w++) ci.node.b[w] = col.bw[w];
-    ci.port = cur; ci.done = col.done; ci.acc = col.acc;
-    const bool finished = active && col.done >= len;
-    ci.node.meta = len | (col.eb << 16);
-    ci.node.aux = finished ? (col.data16(len, reduce_op) | ((u32)me << 16)) : 0u;
-    // finished nodes go to the rank's own list as plain NodeMsg, unfinished ones travel on as CItem
-    __shared__ u32 s_cnt[DBG_MAX_RANKS + 1];
+                    for (int w = 0; w < NBW; w++) it.node.b[w] = col.bw[w];
+                    it.node.meta = col.done | ((col.eb & 0xffu) << 16);
+                    it.node.aux = col.data16(col.done, reduce_op) | ((u32)me << 16);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < NBW; w++) it.node.b[w] = col.bw[w];
+            it.node.meta = (col.eb & 0xffu) << 16;
+            it.node.aux = 0;
+            it.port = cur; it.done = col.done; it.acc = col.acc;
+            it.info = origin | (cside << 8) | ((islong ? 1u : 0u) << 9);
+        }
+    }
+    // finished nodes go to the rank's own list as plain NodeMsg, walkers travel on as FItem
+    __shared__ u32 s_cnt[DBG_MAX_RANKS + 1], s_cov;
     __shared__ u64 s_base[DBG_MAX_RANKS + 1];
     if (threadIdx.x <= DBG_MAX_RANKS) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_cov = 0;
     __syncthreads();
     const int dest = finished ? out.P : (int)crank;
     u32 loc = 0;
-    if (active) loc = atomicAdd(&s_cnt[dest], 1u);
+    if (active) { loc = atomicAdd(&s_cnt[dest], 1u); if (covered) atomicAdd(&s_cov, covered); }
     __syncthreads();
     if (threadIdx.x <= DBG_MAX_RANKS && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&out.cursor[threadIdx.x], (u64)s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0 && s_cov) atomicAdd(&out.cursor[out.P + 1], (u64)s_cov);
     __syncthreads();
     if (active) {
         const u64 pos = s_base[dest] + loc;
         if (pos >= out.cap[dest]) out.cursor[out.P + 2] = 1;
-        else if (finished) reinterpret_cast<NodeMsg<W>*>(out.box[dest])[pos] = ci.node;
-        else reinterpret_cast<CItem<W>*>(out.box[dest])[pos] = ci;
+        else if (finished) reinterpret_cast<NodeMsg<W>*>(out.box[dest])[pos] = it.node;
+        else reinterpret_cast<FItem<W>*>(out.box[dest])[pos] = it;
     }
 }
 
-// walk 2, round 0: thread per emit entry (a node whose left end is a k-mer of this rank)
+// round 0: thread per k-mer of the shard; path ends (and single k-mers) start a walker
 template <int W>
-__global__ void __launch_bounds__(256) ms_collect_start_kernel(KP kp, const uint4* __restrict__ rec, const u64* __restrict__ klo, const u64* __restrict__ khi,
-                                                                int me, const EmitEntry* __restrict__ entries, u64 n, int reduce_op, WalkOut out) {
+__global__ void __launch_bounds__(256) ms_fwalk_start_kernel(KP kp, const uint4* __restrict__ rec, const u64* __restrict__ klo, const u64* __restrict__ khi,
+                                                              int me, u64 n, u32 lmax, int reduce_op, WalkOut out) {
     constexpr int NBW = NodeCfg<W>::NBW;
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    Collector<W> col;
+    const u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    FItem<W> it;
+    it.node.lo = 0;
+    if constexpr (W == 2) it.node.hi = 0;
+    it.node.meta = 0; it.node.aux = 0;
 #pragma unroll
-    for (int w = 0; w < NBW; w++) col.bw[w] = 0;
-    col.acc = 0; col.eb = 0; col.done = 0;
-    u32 cur = 0, crank = (u32)me, len = 1;
-    Kmer<W> seed = Ops<W>::zero();
-    const bool active = i < n;
-    if (active) {
-        const EmitEntry en = entries[i];
-        if constexpr (W == 1) seed = Kmer<1>{en.lo}; else seed = Kmer<2>{en.lo, en.hi};
-        len = en.len;
-        cur = en.port;
-        if ((u64)len + kp.k - 1 > 32ull * NBW) {
-            // too long for a message: the owner of the key range re-walks it through the peer windows (flag LONG)
-            col.bw[0] = cur; col.done = len; col.eb = NODE_LONG << 8;   // eb << 16 lands the flag in meta bits 24..
-        } else {
-            const uint4 r = rec[cur >> 1];
-            col.first(kp, r, local_key<W>(klo, khi, cur >> 1), cur, len);
-            const u32 dw = cur & 1u;
-            cur = dw ? r.y : r.x;
-            crank = (r.w >> (8 * dw)) & 0xffu;
+    for (int w = 0; w < NBW; w++) it.node.b[w] = 0;
+    it.port = 0; it.done = 0; it.acc = 0; it.origin_port = 0; it.info = (u32)me; it.pad = 0;
+    bool active = false;
+    if (v < n) {
+        const uint4 a0 = rec[v];
+        if (a0.x == NIL || a0.y == NIL) {
+            // stored orientation for a single k-mer (heading right = leaving through R), else inwards through the linked side
+            const u32 d = (a0.x == NIL && a0.y == NIL) ? 1u : (a0.x == NIL ? 1u : 0u);
+            active = true;
+            it.port = 2u * (u32)v + d;
+            it.origin_port = it.port;
+            // a light walk first (no collection): most paths end on this rank, and half of their end walkers started at the right
+            // end — those stop here without having collected anything; only left-end walkers and walkers that leave the rank collect
+            u32 cnt = 1;
+            LocalMin lm{(u32)v, d, true};
+            u32 t = d ? a0.y : a0.x;
+            u32 trank = (a0.w >> (8 * d)) & 0xffu;
+            t = walk_local(rec, me, t, trank, cnt, lmax, lm);
+            if (cnt > lmax || (t == NIL && lm.side != 1u)) active = false;
         }
     }
-    collect_run<W>(kp, rec, me, col, cur, crank, len, reduce_op, seed, active, out);
+    fwalk_run<W>(kp, rec, klo, khi, me, it, active, lmax, reduce_op, out);
 }
 
-// walk 2, later rounds: thread per received partial node
+// later rounds: thread per received walker
 template <int W>
-__global__ void __launch_bounds__(256) ms_collect_continue_kernel(KP kp, const uint4* __restrict__ rec, int me, const CItem<W>* __restrict__ inbox, u64 n,
-                                                                   int reduce_op, WalkOut out) {
-    constexpr int NBW = NodeCfg<W>::NBW;
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    Collector<W> col;
-#pragma unroll
-    for (int w = 0; w < NBW; w++) col.bw[w] = 0;
-    col.acc = 0; col.eb = 0; col.done = 0;
-    u32 cur = 0, len = 1;
-    Kmer<W> seed = Ops<W>::zero();
-    const bool active = i < n;
-    if (active) {
-        const CItem<W> ci = inbox[i];
-        if constexpr (W == 1) seed = Kmer<1>{ci.node.lo}; else seed = Kmer<2>{ci.node.lo, ci.node.hi};
-#pragma unroll
-        for (int w = 0; w < NBW; w++) col.bw[w] = ci.node.b[w];
-        col.acc = ci.acc; col.done = ci.done; col.eb = (ci.node.meta >> 16) & 0xffu;
-        len = ci.node.meta & 0xffffu;
-        cur = ci.port;
-    }
-    collect_run<W>(kp, rec, me, col, cur, (u32)me, len, reduce_op, seed, active, out);
+__global__ void __launch_bounds__(256) ms_fwalk_continue_kernel(KP kp, const uint4* __restrict__ rec, const u64* __restrict__ klo, const u64* __restrict__ khi,
+                                                                 int me, const FItem<W>* __restrict__ inbox, u64 n_in, u32 lmax, int reduce_op, WalkOut out) {
+    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    FItem<W> it;
+    const bool active = q < n_in;
+    if (active) it = inbox[q];
+    else { it.port = NIL; it.done = 0; it.acc = 0; it.info = 0; it.origin_port = 0; it.node.meta = 0; it.node.aux = 0; it.node.lo = 0; }
+    fwalk_run<W>(kp, rec, klo, khi, me, it, active, lmax, reduce_op, out);
 }
 
 // node messages (any order) -> grouped by the rank owning the seed's key range: destination = range of the seed's top-bits
@@ -822,35 +734,21 @@ int ms_count_ends_dev(Ctx* c, const uint4* d_rec, u64 n, u64* d_out) {
     ms_count_ends_kernel<<<(u32)std::min<u64>(grid_for(n, 256), (u64)c->sm_count * 8), 256, 0, c->stream>>>(d_rec, n, d_out);
     return check_launch(c, "ms_count_ends");
 }
-u32 ms_witem_bytes() { return (u32)sizeof(WItem); }
-u32 ms_entry_bytes() { return (u32)sizeof(EmitEntry); }
-u32 ms_citem_bytes(int k) { return k <= 32 ? (u32)sizeof(CItem<1>) : (u32)sizeof(CItem<2>); }
-
-int ms_walk_start_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, u64 n, u32 lmax, const WalkOut& out) {
+u32 ms_fitem_bytes(int k) { return k <= 32 ? (u32)sizeof(FItem<1>) : (u32)sizeof(FItem<2>); }
+int ms_fwalk_start_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, u64 n, u32 lmax, int reduce_op, const WalkOut& out) {
     if (!n) return DBG_OK;
-    if (k <= 32) ms_walk_start_kernel<1><<<grid_for(n, 256), 256, 0, c->stream>>>(rec, klo, khi, me, n, lmax, out);
-    else ms_walk_start_kernel<2><<<grid_for(n, 256), 256, 0, c->stream>>>(rec, klo, khi, me, n, lmax, out);
-    return check_launch(c, "ms_walk_start");
+    KP kp = make_kp(k);
+    if (k <= 32) ms_fwalk_start_kernel<1><<<grid_for(n, 256), 256, 0, c->stream>>>(kp, rec, klo, khi, me, n, lmax, reduce_op, out);
+    else ms_fwalk_start_kernel<2><<<grid_for(n, 256), 256, 0, c->stream>>>(kp, rec, klo, khi, me, n, lmax, reduce_op, out);
+    return check_launch(c, "ms_fwalk_start");
 }
-int ms_walk_continue_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, const void* inbox, u64 n_in, u32 lmax, const WalkOut& out) {
+int ms_fwalk_continue_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, const void* inbox, u64 n_in, u32 lmax, int reduce_op,
+                          const WalkOut& out) {
     if (!n_in) return DBG_OK;
-    if (k <= 32) ms_walk_continue_kernel<1><<<grid_for(n_in, 256), 256, 0, c->stream>>>(rec, klo, khi, me, reinterpret_cast<const WItem*>(inbox), n_in, lmax, out);
-    else ms_walk_continue_kernel<2><<<grid_for(n_in, 256), 256, 0, c->stream>>>(rec, klo, khi, me, reinterpret_cast<const WItem*>(inbox), n_in, lmax, out);
-    return check_launch(c, "ms_walk_continue");
-}
-int ms_collect_start_dev(Ctx* c, int k, const uint4* rec, const u64* klo, const u64* khi, int me, const void* entries, u64 n, int reduce_op, const WalkOut& out) {
-    if (!n) return DBG_OK;
     KP kp = make_kp(k);
-    if (k <= 32) ms_collect_start_kernel<1><<<grid_for(n, 256), 256, 0, c->stream>>>(kp, rec, klo, khi, me, reinterpret_cast<const EmitEntry*>(entries), n, reduce_op, out);
-    else ms_collect_start_kernel<2><<<grid_for(n, 256), 256, 0, c->stream>>>(kp, rec, klo, khi, me, reinterpret_cast<const EmitEntry*>(entries), n, reduce_op, out);
-    return check_launch(c, "ms_collect_start");
-}
-int ms_collect_continue_dev(Ctx* c, int k, const uint4* rec, int me, const void* inbox, u64 n, int reduce_op, const WalkOut& out) {
-    if (!n) return DBG_OK;
-    KP kp = make_kp(k);
-    if (k <= 32) ms_collect_continue_kernel<1><<<grid_for(n, 256), 256, 0, c->stream>>>(kp, rec, me, reinterpret_cast<const CItem<1>*>(inbox), n, reduce_op, out);
-    else ms_collect_continue_kernel<2><<<grid_for(n, 256), 256, 0, c->stream>>>(kp, rec, me, reinterpret_cast<const CItem<2>*>(inbox), n, reduce_op, out);
-    return check_launch(c, "ms_collect_continue");
+    if (k <= 32) ms_fwalk_continue_kernel<1><<<grid_for(n_in, 256), 256, 0, c->stream>>>(kp, rec, klo, khi, me, reinterpret_cast<const FItem<1>*>(inbox), n_in, lmax, reduce_op, out);
+    else ms_fwalk_continue_kernel<2><<<grid_for(n_in, 256), 256, 0, c->stream>>>(kp, rec, klo, khi, me, reinterpret_cast<const FItem<2>*>(inbox), n_in, lmax, reduce_op, out);
+    return check_launch(c, "ms_fwalk_continue");
 }
 
 // cuts: P + 1 bin indices over the top `bits` key bits; seg_off: P + 1 message offsets (prefix sums of the per-destination
