@@ -293,7 +293,7 @@ struct PartRegions {
 #ifndef DBG_MAX_RANKS
 #define DBG_MAX_RANKS 8
 #endif
-struct ScatterDst { u64* base[DBG_MAX_RANKS]; u64 bound[DBG_MAX_RANKS + 1]; int P; };
+struct ScatterDst { u64* base[DBG_MAX_RANKS]; u64 bound[DBG_MAX_RANKS + 1]; int P, me; };
 int partition_regions_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, int bbits, PartRegions** out);
 void free_part_regions(PartRegions* R);
 int bucket_totals_dev(Ctx* c, const u32* d_all_cnt, int P, int me, u32 nb, u32* d_tot, u32* d_pre);

@@ -2193,21 +2193,44 @@ __global__ void __launch_bounds__(256) scatter_buckets_kernel(const u64* __restr
     if (threadIdx.x < DBG_MAX_RANKS) { s_km[threadIdx.x] = 0; s_rc[threadIdx.x] = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    for (u64 b = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += ((u64)gridDim.x * blockDim.x) >> 5) {
+    // Work item j -> destination (j + me) mod P, bucket j / P of that destination's range: at any moment a sender writes to ALL
+    // destinations, and the senders are rotated against each other.  (Sweeping the buckets in order sends the whole GPU — and every
+    // other GPU at the same time — to one destination after the other: 8 senders queueing on one NVLink ingress, the other 7 idle.)
+    u64 max_n = 0;
+    for (int r = 0; r < D.P; r++) max_n = max(max_n, D.bound[r + 1] - D.bound[r]);
+    const u64 n_items = max_n * (u64)D.P;
+    for (u64 j = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_items; j += ((u64)gridDim.x * blockDim.x) >> 5) {
+        const int r = (int)((j + (u64)D.me) % (u64)D.P);
+        const u64 bi = j / (u64)D.P;
+        if (bi >= D.bound[r + 1] - D.bound[r]) continue;
+        const u64 b = D.bound[r] + bi;
         const u32 n = cnt[b];
         if (!n) continue;
-        int r = 0;
-        while (r + 1 < D.P && b >= D.bound[r + 1]) r++;
         const u64 s0 = src_start[b], d0 = goff[b] - goff[D.bound[r]] + pre[b];
         u64* dst = D.base[r];
         u32 km = 0;
-        for (u32 i = lane; i < n; i += 32) {
-            const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(src + (s0 + i) * RW);
-            ulonglong2* dp = reinterpret_cast<ulonglong2*>(dst + (d0 + i) * RW);
-            const ulonglong2 v0 = sp[0];
-            dp[0] = v0;
-            if (RW == 4) { const ulonglong2 v1 = sp[1]; dp[1] = v1; km += (u32)(v1.y >> 8) & 63u; }
-            else km += (u32)(v0.y >> 8) & 63u;
+        // four records per lane in flight: the stores are posted, the loads in front of them are what a warp waits for
+        for (u32 i0 = 0; i0 < n; i0 += 128) {
+            ulonglong2 v[4][RW / 2];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const u32 i = i0 + 32 * u + lane;
+                if (i < n) {
+                    const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(src + (s0 + i) * RW);
+                    v[u][0] = sp[0];
+                    if (RW == 4) v[u][RW / 2 - 1] = sp[1];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const u32 i = i0 + 32 * u + lane;
+                if (i < n) {
+                    ulonglong2* dp = reinterpret_cast<ulonglong2*>(dst + (d0 + i) * RW);
+                    dp[0] = v[u][0];
+                    if (RW == 4) dp[1] = v[u][RW / 2 - 1];
+                    km += (u32)(v[u][RW / 2 - 1].y >> 8) & 63u;
+                }
+            }
         }
         for (int o = 16; o; o >>= 1) km += __shfl_down_sync(0xffffffffu, km, o);
         if (lane == 0) { atomicAdd(&s_km[r], (unsigned long long)km); atomicAdd(&s_rc[r], (unsigned long long)n); }

@@ -389,12 +389,15 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     const u64 n_recv = gb[me + 1] - gb[me];
     TRY(T->ensure_window((n_recv ? n_recv : 1) * rec_bytes));
     ScatterDst D;
-    D.P = P;
+    D.P = P; D.me = me;
     for (int r = 0; r < DBG_MAX_RANKS; r++) { D.base[r] = r < P ? reinterpret_cast<u64*>(T->peer_ptr[r]) : nullptr; D.bound[r] = r <= P ? bounds[r] : NB; }
     D.bound[DBG_MAX_RANKS] = NB;
     for (int r = P; r <= DBG_MAX_RANKS; r++) D.bound[r] = NB;
     CU(c, cudaMemsetAsync(d_sums.p, 0, 8 * 2 * DBG_MAX_RANKS, st));
+    EvTimer tx;   // the scatter kernel alone (DBG_MULTI_TRACE)
+    tx.mark(st);
     TRY(scatter_buckets_dev(c, part, d_goff.p, d_pre.p, D, d_sums.p));
+    tx.mark(st);
     u64 sent[2 * DBG_MAX_RANKS];
     TRY(read_u64(c, d_sums.p, sent, 2 * P));
     for (int r = 0; r < P; r++) if (r != me) I.exchange_bytes_sent += sent[P + r] * rec_bytes;
@@ -634,6 +637,7 @@ static int multi_reads_to_graph(Transport* T, int k, const SeqSet* s, u32 min_ob
     I.ms_partition = tm.ms(0, 1); I.ms_exchange = tm.ms(1, 2); I.ms_count_sort = tm.ms(2, 3); I.ms_links = tm.ms(3, 4);
     I.ms_discover = tm.ms(4, 5); I.ms_layout = tm.ms(5, 6); I.ms_emit = tm.ms(6, 7); I.ms_total = tm.ms(0, 8);
     if (getenv("DBG_MULTI_TRACE") && me == 0) {
+        fprintf(stderr, "[dbg multi] exchange: scatter kernel %.2f ms for %.0f MB received here\n", tx.ms(0, 1), (double)n_recv * rec_bytes / 1e6);
         float t_col = 0, t_lay = 0;
         cudaEventElapsedTime(&t_col, tm.ev[5], tl.ev[0]);
         cudaEventElapsedTime(&t_lay, tl.ev[3], tm.ev[6]);
