@@ -158,6 +158,34 @@ class SeqSet:
         return ss
 
     @staticmethod
+    def parse_fastq(data):
+        """4-line FASTQ records (bytes or a path) -> (read names without '@' up to the first blank, sequence lines).  The crate has no
+        FASTQ reader of its own: this is the caller-side loop that feeds DnaString::from_acgt_bytes[_hashn] (SURVEY §8f N3)."""
+        if not isinstance(data, (bytes, bytearray)):
+            with open(data, "rb") as f:
+                data = f.read()
+        lines = bytes(data).split(b"\n")
+        if lines and lines[-1] == b"":
+            lines.pop()
+        if len(lines) % 4:
+            raise ValueError("FASTQ: number of lines is not a multiple of 4")
+        names, seqs = [], []
+        for i in range(0, len(lines), 4):
+            h, sq, plus = lines[i].rstrip(b"\r"), lines[i + 1].rstrip(b"\r"), lines[i + 2]
+            if not h.startswith(b"@") or not plus.startswith(b"+"):
+                raise ValueError("FASTQ: malformed record at line %d" % (i + 1))
+            names.append(h[1:].split(None, 1)[0] if len(h) > 1 else b"")
+            seqs.append(sq)
+        return names, seqs
+
+    @staticmethod
+    def from_fastq(ctx, data, hashn=True):
+        """A FASTQ file (path or bytes) as a device sequence set: sequences packed on the device, non-ACGT characters replaced as in
+        DnaString::from_acgt_bytes_hashn (hash of read name + position; hashn=False: from_acgt_bytes, 'A')."""
+        names, seqs = SeqSet.parse_fastq(data)
+        return SeqSet.from_ascii_hashn(ctx, seqs, names) if hashn else SeqSet.from_ascii(ctx, seqs)
+
+    @staticmethod
     def upload_uniform(ctx, words, n_seqs, read_len, seq_exts=None, pipelined=False):
         """pipelined=True: asynchronous chunked upload overlapping the partition stage of the next call; `words` (pinned
         for real overlap) must stay untouched until that call has returned (the SeqSet keeps a reference)."""

@@ -745,7 +745,13 @@ template <int W> struct P2Cfg;
 // K <= 32: 8 B key + 4 B val = 96 KB tables, 2 CTAs/SM of 512 threads (4 x 256 threads with 48 KB tables measured 5% slower:
 // more bucket splits).  RC = records per chunk.
 template <> struct P2Cfg<1> { static const int CAP = P2_CAP1; static const int THREADS = P2_THR1; static const int CTAS = P2_CTA1; static const int RC = P2_RC1; };
-template <> struct P2Cfg<2> { static const int CAP = 8192; static const int THREADS = 1024; static const int CTAS = 1; static const int RC = 1024; };  // 16 B key + 4 B val = 160 KB, 1 CTA/SM
+#ifndef P2_CAP2
+#define P2_CAP2 8192
+#define P2_THR2 1024
+#define P2_CTA2 1
+#define P2_RC2 1024
+#endif
+template <> struct P2Cfg<2> { static const int CAP = P2_CAP2; static const int THREADS = P2_THR2; static const int CTAS = P2_CTA2; static const int RC = P2_RC2; };  // 16 B key + 4 B val = 160 KB, 1 CTA/SM
 
 struct P2Args {
     u64* rec; u32* mult;  // records (deduplicated in place per bucket when mult != nullptr) and their multiplicities
@@ -975,8 +981,8 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                 // ---- P2a for 32-byte records: the table is keyed by a 128-bit hash of the record (one ATOMS.CAS.128);
                 // the slot owner stores the full record, everybody else verifies it before adding to the multiplicity.
                 // A mismatch (128-bit hash collision) only disables deduplication for that chunk. ----
-                constexpr int RCAP = 2048;
-                static_assert(W == 1 || RCAP / 2 == P2Cfg<2>::THREADS, "one record per thread");
+                constexpr int RCAP = 2 * P2T;   // one record per thread and chunk, table at most half full
+                static_assert(W == 1 || 52 * RCAP <= (int)(sizeof(Kmer<2>) + 4) * CAP, "dedup table fits the k-mer table memory");
                 Kmer<2>* hkeys = reinterpret_cast<Kmer<2>*>(smem_raw);
                 u64* srec = reinterpret_cast<u64*>(smem_raw + sizeof(Kmer<2>) * RCAP);
                 u32* rcnt = reinterpret_cast<u32*>(smem_raw + (sizeof(Kmer<2>) + 32) * RCAP);

@@ -43,3 +43,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "import oracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, f
+
+
+def test_integration_md_lists_every_entry_point():
+    """INTEGRATION.md's Rust extern block is generated from the header (tools/gen_rust_extern.py) and must stay in step with it;
+    dbg_stats / dbg_multi_info are declared field for field (a zero-sized placeholder would let dbg_stats_get write past it)."""
+    import subprocess
+    import sys
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for s in header_symbols():
+        assert f"pub fn {s}(" in doc, f"{s} missing from INTEGRATION.md"
+    gen = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "gen_rust_extern.py")]).decode()
+    assert gen in doc, "INTEGRATION.md extern block is stale: regenerate with tools/gen_rust_extern.py"
+    assert "pub struct dbg_stats { pub n_seqs: u64" in doc and "pub struct dbg_multi_info { pub n_ranks: u32" in doc

@@ -509,6 +509,27 @@ def test_from_ascii_hashn_on_device(D, ctx, orc):
     assert g["n_nodes"] > 0
 
 
+def test_fastq_feeding(D, ctx, orc, tmp_path):
+    """FASTQ -> device sequence set (SeqSet.from_fastq: host-side record split, device-side packing with the hashn policy) equals the
+    oracle's from_acgt_bytes_hashn on the same records; CRLF line ends, an empty read and a path argument included."""
+    rng = np.random.default_rng(23)
+    alpha = np.frombuffer(b"ACGTACGTACGTNn", np.uint8)
+    seqs = [bytes(rng.choice(alpha, size=n)) for n in (150, 0, 151, 76, 33)]
+    names = [b"r%d" % i for i in range(len(seqs))]
+    fq = b"".join(b"@" + n + b" extra field\n" + s + (b"\r\n" if i == 2 else b"\n") + b"+\n" + b"I" * len(s) + b"\n"
+                  for i, (n, s) in enumerate(zip(names, seqs)))
+    path = tmp_path / "reads.fastq"
+    path.write_bytes(fq)
+    ow, ost, oln, obad = orc.from_acgt_bytes_hashn(seqs, names)
+    for src in (fq, str(path)):
+        ss = D.SeqSet.from_fastq(ctx, src)
+        w, s_, l = ss.copy_out()
+        assert np.array_equal(w, ow) and np.array_equal(s_, ost) and np.array_equal(l, oln) and ss.n_invalid == obad
+    assert D.SeqSet.parse_fastq(fq) == (names, seqs)
+    with pytest.raises(ValueError):
+        D.SeqSet.parse_fastq(fq[:-20] + b"\nxx")
+
+
 def test_bincode_image_round_trip(D, ctx, orc):
     """dbg_graph_serialize / dbg_graph_deserialize: the bincode image of BaseGraph<K, u16> equals the oracle's (hand-checked layout,
     tests/test_oracle.py::test_bincode_image_layout) and reads back to the same arrays."""

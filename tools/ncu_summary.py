@@ -20,11 +20,12 @@ for r in rows:
             agg.setdefault(name, [0, 0.0])
             agg[name][0] += 1
             agg[name][1] += float(d["Metric Value"].replace(",", "")) / 1e6
-steps = 2
+steps = int(sys.argv[6]) if len(sys.argv) > 6 else 2
+cmd = sys.argv[7] if len(sys.argv) > 7 else f"python tools/profile_step.py --steps {steps}"
 synth = agg.pop("synth_reads_kernel", [0, 0.0])
 tot = sum(v[1] for v in agg.values())
 out = [f"# {title}\n", "## Launch list (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised: compare SHARES)\n",
-       f"`python tools/profile_step.py --steps {steps}` (configs[1]: 10M x 150bp noisy, K=31); synth_reads_kernel ({synth[1]:.2f} ms, input generation) excluded.\n",
+       f"`{cmd}` (configs[1]: 10M x 150bp noisy, K=31); synth_reads_kernel ({synth[1]:.2f} ms, input generation) excluded.\n",
        "| kernel | launches/step | ms/step | share |", "|---|---|---|---|"]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"| {k} | {v[0] / steps:g} | {v[1] / steps:.3f} | {v[1] / tot * 100:.1f}% |")

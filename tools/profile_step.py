@@ -14,12 +14,15 @@ ap.add_argument("--clean", action="store_true")
 ap.add_argument("--p", type=int, default=0)
 ap.add_argument("--bucket-occ", type=int, default=0)
 ap.add_argument("--no-direct", action="store_true")
+ap.add_argument("--dedup", type=int, default=-1)
 a = ap.parse_args()
 ctx = D.Context(0)
 if a.p:
     ctx.set_param("msp_p", a.p)
 if a.no_direct:
     ctx.set_param("direct_partition", 0)
+if a.dedup >= 0:
+    ctx.set_param("dedup", a.dedup)
 if a.bucket_occ:
     ctx.set_param("bucket_occ", a.bucket_occ)
 ss = D.SeqSet.synth(ctx, a.reads, 1, 0 if a.clean else 83886)
