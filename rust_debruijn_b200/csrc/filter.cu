@@ -824,7 +824,8 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
     Kmer<W>* keys = reinterpret_cast<Kmer<W>*>(smem_raw);
     u32* vals = reinterpret_cast<u32*>(smem_raw + sizeof(Kmer<W>) * CAP);
     __shared__ u64 s_scan[33];
-    __shared__ u16 s_task[P2_RC * 4];     // (record in chunk) | (task in record << 10), sorted by task length
+    constexpr int MAXT = W == 1 ? 4 : 8;   // tasks per record: 4 x 8 k-mers (<= 32 k-mers per 16-byte record), 8 x 8 (<= 59 per 32-byte record)
+    __shared__ u16 s_task[P2_RC * MAXT];  // (record in chunk) | (task in record << 10), sorted by task length
     __shared__ u32 s_cls[17];             // per task length: counter / cursor; [0] = number of tasks
     __shared__ u32 s_ptot, s_next, s_wr_ok, s_cnt;
     __shared__ u64 s_r0;
@@ -1146,7 +1147,7 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                 for (int j = 0; j < P2_RC / P2T; j++) {   // scatter (record, first k-mer) into the class ranges
                     const u32 idx = j * P2T + threadIdx.x;
                     const u32 n = myn[j];
-                    for (u32 jt = 0; jt < 4; jt++) {
+                    for (u32 jt = 0; jt < (u32)MAXT; jt++) {
                         const u32 t0 = jt * tl;
                         const bool has = t0 < n;
                         if (!__any_sync(0xffffffffu, has)) break;
@@ -1811,7 +1812,9 @@ static int count_stage(Ctx* c, int k, u64* rec, u64 n_rec, const u64* bucket_sta
     a.rec = rec; a.mult = dedup ? mult.p : nullptr; a.mult_ready = 0; a.dedup_cnt = dedup_cnt.p;
     a.bucket_start = bucket_start; a.bucket_cnt = bucket_cnt; a.n_buckets = NB;
     a.min_obs = min_obs; a.stranded = stranded; a.report_all = report_all;
-    a.task_len = rec_max_kmers(RecLayout<W>::WORDS, k) <= 32 ? 8 : 16;
+    // k-mers per task: 8 keeps ~one task per thread and chunk for both record sizes (32-byte records hold up to 59 k-mers; tasks of 16
+    // left half of the 1024 threads of a K > 32 CTA without work: buckets of ~350 records); records longer than 8 tasks fall back to 16
+    a.task_len = rec_max_kmers(RecLayout<W>::WORDS, k) <= (W == 1 ? 32 : 64) ? 8 : 16;
     a.out_lo = co.v_lo.p; a.out_hi = co.v_hi.p; a.out_val = co.v_val.p; a.cap_valid = co.cap_valid;
     a.all_lo = co.a_lo.p; a.all_hi = co.a_hi.p; a.cap_all = co.cap_all;
     a.counters = co.ctr.p;
