@@ -7,6 +7,10 @@
  * crate root).  Plain pointers and sizes only; no exceptions or unwinding cross this ABI; every call
  * returns a dbg_status and leaves a message retrievable with dbg_last_error().
  *
+ * Limits: k-mer / node indices are 32-bit inside one table or graph (fewer than 2^31 valid k-mers per GPU — per rank's shard in
+ * the multi-GPU calls — and fewer than 2^31 nodes per graph; larger inputs return DBG_E_BADARG), K in [4, 64], counts saturate at
+ * 65 535 as in the crate (src/filter.rs:57).
+ *
  * Threading: calls block.  One dbg_ctx = one CUDA device + one stream; a ctx is used by one caller at
  * a time; several ctxs (one per GPU / per process) may coexist.  There is NO CPU fallback: without a
  * CUDA device dbg_ctx_create fails with DBG_E_CUDA.

@@ -28,6 +28,7 @@ struct Ctx {
     int dedup = 1;             // deduplicate super-k-mer records per bucket before counting (K <= 32)
     int direct_partition = 1;  // records straight into per-bucket regions sized by a sampling pass (0 = always stage + scatter)
     u64 direct_min_tiles = 2048;  // ... only for inputs of at least this many 4096-base tiles
+    int pipelined_direct_failed = 0;  // a direct partition sized from the first upload chunk overflowed once: keep pipelined inputs on staging
     int no_fast_compress = 0;  // testing: 1 = always take the general (per-k-mer rank + emit) compression path
     u64 valid_est_div = 0;     // testing: size the valid-k-mer buffer as N / div (0 = default estimate N/8 + 2^20)
     u64 mem_budget_bytes = 0;  // scratch budget for the pass planner (0 = 60% of free device memory, capped by memory_size)

@@ -1948,10 +1948,14 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     float ms_part = 0, ms_cnt = 0;
     // direct partition (no staging, no scatter pass): contiguous layouts, one pass, enough tiles for the sampling pass
     const u64 n_tiles_all = (s->contiguous && s->total_end > s->base0) ? (s->total_end - s->base0 + TP - 1) / TP : 0;
-    // (a pipelined upload keeps the staging path: its sampling pass could only look at the first chunk, which is not a
-    // uniform sample of position-sorted input, and a mispredicted region costs a second partition + count)
+    // A pipelined upload can only sample its FIRST chunk (the main pass must start before the rest has arrived).  Reads as a
+    // sequencer writes them are in no genomic order, so the first eighth is as good a sample as every 16th tile; position-sorted
+    // input is not, and there a mispredicted region costs a second partition + count: the context remembers a failed attempt and
+    // keeps such callers on the staging path afterwards.
     // Two-word keys keep staging as well: their buckets hold ~340 records, too few for a 1/16 sample to size tightly.
-    bool use_direct = c->direct_partition && W == 1 && n_pass == 1 && n_tiles_all >= c->direct_min_tiles && s->n_pending == 0;
+    const bool pipelined = s->n_pending > 0;
+    bool use_direct = c->direct_partition && W == 1 && n_pass == 1 && n_tiles_all >= c->direct_min_tiles &&
+                      (!pipelined || !c->pipelined_direct_failed);
     S.direct_partition = 0;
     for (int attempt = 0;; attempt++) {
         c->arena_off = 0;
@@ -1994,7 +1998,10 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
             }
             c->arena_off = mark;  // every per-pass buffer is gone
         }
-        if (direct_failed) { use_direct = false; attempt--; continue; }
+        if (direct_failed) {
+            if (pipelined) c->pipelined_direct_failed = 1;
+            use_direct = false; attempt--; continue;
+        }
         if (!overflow) {
             CU(c, cudaEventRecord(c->ev[2], st));
             TRY(sort_stage<W>(c, k, report_all, co, t));

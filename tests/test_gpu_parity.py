@@ -181,6 +181,35 @@ def test_pipelined_upload_matches_oracle(D, ctx, orc):
     assert_graphs_equal(D.BaseGraph(ctx, gh).to_host(), og)
 
 
+def test_pipelined_upload_direct_partition_and_its_fallback(D, orc):
+    """A pipelined upload takes the direct partition sized from its FIRST chunk.  Reads in sequencer order: it holds
+    (direct_partition == 1).  An input whose first chunk says nothing about the rest (an eighth of identical low-complexity reads,
+    then random ones): regions overflow, the call falls back to staging, the result is still the oracle's, and the context keeps
+    later pipelined inputs on the staging path."""
+    c2 = D.Context(0)
+    R = 900_000
+    w, s, l = orc.synth_reads(R, 5, orc.ERR_THR_NOISY)
+    ot = orc.filter_kmers(31, w, s, l, min_obs=2, threads=os.cpu_count() or 1)
+    table, _ = D.filter_kmers(D.SeqSet.upload_uniform(c2, w, R, 150, pipelined=True), D.CountFilter(2), False, False, 4, k=31)
+    assert_tables_equal(table.to_host(), ot)
+    assert c2.stats()["direct_partition"] == 1
+    # first eighth: the same read over and over (16-read period keeps the packed words periodic); rest: the synthetic reads
+    w2 = w.copy()
+    n8 = (R // 8 // 16) * 16
+    period = 16 * 150 // 32                                   # 16 reads = 75 words
+    w2[:n8 * 150 // 32] = np.tile(w[:period], n8 // 16)
+    ot2 = orc.filter_kmers(31, w2, s, l, min_obs=2, threads=os.cpu_count() or 1)
+    table2, _ = D.filter_kmers(D.SeqSet.upload_uniform(c2, w2, R, 150, pipelined=True), D.CountFilter(2), False, False, 4, k=31)
+    assert_tables_equal(table2.to_host(), ot2)
+    assert c2.stats()["direct_partition"] == 0                 # fell back
+    table3, _ = D.filter_kmers(D.SeqSet.upload_uniform(c2, w, R, 150, pipelined=True), D.CountFilter(2), False, False, 4, k=31)
+    assert_tables_equal(table3.to_host(), ot)
+    assert c2.stats()["direct_partition"] == 0                 # remembered: staging from the start
+    table4, _ = D.filter_kmers(D.SeqSet.upload_uniform(c2, w, R, 150), D.CountFilter(2), False, False, 4, k=31)
+    assert c2.stats()["direct_partition"] == 1                 # resident inputs still sample the whole input
+    assert_tables_equal(table4.to_host(), ot)
+
+
 def test_from_ascii_ingest(D, ctx, orc):
     """dbg_seqset_from_ascii = DnaString::from_acgt_bytes + PackedDnaStringSet::add on the device: packed words, offsets,
     lengths and the invalid-character count identical to the oracle; the packed set then feeds filter_kmers."""

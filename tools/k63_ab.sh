@@ -1,3 +1,4 @@
-echo "== K=63"; python tools/profile_step.py --steps 3 --k 63 2>&1 | tail -n 1 | cut -c1-900
-echo "== K=47"; python tools/profile_step.py --steps 3 --k 47 2>&1 | tail -n 1 | cut -c1-900
-python -m pytest tests -m gpu -x -q -k "not full_size and not fullsize and not multi" 2>&1 | tail -n 2
+export DBG_B200_LIB=$PWD/rust_debruijn_b200/variants/libdbg_w2half.so
+echo "== K=63 w2half occ 3300"; python tools/profile_step.py --steps 3 --k 63 --bucket-occ 3300 2>&1 | tail -n 1 | cut -c1-900
+unset DBG_B200_LIB
+echo "== K=63 base dedup 2"; python tools/profile_step.py --steps 3 --k 63 --dedup 2 2>&1 | tail -n 1 | cut -c1-900
