@@ -207,6 +207,9 @@ static const int WSC = WP + 64 + 8;                  // p-mer scores per warp ti
 static const int WBK = WP + WP / 16 + 8;             // bucket of every examined position, padded (bkpad)
 static const int WBM = 24;                           // bitmap words per warp tile (>= (31 + WP + 64 + 2) / 32 + 3)
 static const int NST = 4;                            // ring depth
+#ifndef PRODUCER_NAP_NS
+#define PRODUCER_NAP_NS 256
+#endif
 static const int SB_BYTES = 1088;                    // bytes staged per block (8 warp tiles + flanks), multiple of 16
 static const int SBW = 288;                          // u32 words per ring slot
 static const int TP = 4096;                          // (size unit of the direct_min_tiles parameter only)
@@ -251,6 +254,9 @@ __device__ __forceinline__ void mbar_wait_suspended(u64* bar, u32 parity) {
     do {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(ok) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+        // (the hint alone still returned every ~50 cycles: 12 % of the kernel's executed instructions were this loop; the ring is
+        // 4 blocks deep, a refill that starts a few hundred ns late is never waited for)
+        if (!ok) __nanosleep(PRODUCER_NAP_NS);
     } while (!ok);
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
