@@ -105,7 +105,8 @@ def hbm_peak():
 
 
 def ncu_traffic():
-    """dram bytes per launch of the dominant kernels from the committed ncu --set full captures, if any."""
+    """dram bytes per launch of the dominant kernels from the committed ncu --set full captures (configs[1] launches:
+    profiles/traffic.json, details of the round-2 captures in profiles/traffic_r02.json), if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
