@@ -165,8 +165,10 @@ __global__ void rs_hist_scan_kernel(u64* ghist, int passes) {  // one warp per p
     }
 }
 
+// resident CTAs per SM: 3 for one-word keys (40 registers, a few spilled words; 67 KB of shared memory each), 2 for two-word keys
+// (measured: 2.39 -> 2.11 ms at K=31 with 3; K=63: 2.9 ms with 2, 3.1 ms with 3)
 template <int W>
-__global__ void __launch_bounds__(OS_THREADS) rs_onesweep(const u64* __restrict__ lo, const u64* __restrict__ hi,
+__global__ void __launch_bounds__(OS_THREADS, W == 1 ? 3 : 2) rs_onesweep(const u64* __restrict__ lo, const u64* __restrict__ hi,
                                                           const u32* __restrict__ val, u64* __restrict__ olo,
                                                           u64* __restrict__ ohi, u32* __restrict__ oval, u64 n, int d,
                                                           const u64* __restrict__ gbase, u64* status, u32* tile_counter) {
@@ -188,13 +190,20 @@ __global__ void __launch_bounds__(OS_THREADS) rs_onesweep(const u64* __restrict_
     const u64 tbase = (u64)tile * OS_TILE, wbase = tbase + (u64)warp * OS_SEG;
     u64 klo[OS_ITEMS], khi[OS_ITEMS];
     u32 kv[OS_ITEMS], rank[OS_ITEMS], dgt[OS_ITEMS];
+    // all loads first: the ranking rounds below are separated by __syncwarp (a memory fence the loads cannot be hoisted over), so
+    // loading inside them paid one global-memory latency per item instead of one per thread
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; r++) {
+        const u64 i = wbase + r * 32 + lane;
+        const bool act = i < n;
+        klo[r] = act ? lo[i] : 0;
+        khi[r] = (W == 2 && act) ? hi[i] : 0;
+        kv[r] = act ? val[i] : 0;
+    }
 #pragma unroll
     for (int r = 0; r < OS_ITEMS; r++) {
         u64 i = wbase + r * 32 + lane;
         bool act = i < n;
-        klo[r] = act ? lo[i] : 0;
-        khi[r] = (W == 2 && act) ? hi[i] : 0;
-        kv[r] = act ? val[i] : 0;
         u32 dg = act ? (d < 8 ? (u32)(klo[r] >> (8 * d)) & 0xffu : (u32)(khi[r] >> (8 * (d - 8))) & 0xffu) : 0xffffffffu;
         dgt[r] = dg;
         u32 peers = __match_any_sync(0xffffffffu, dg);
