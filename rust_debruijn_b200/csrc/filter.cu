@@ -888,6 +888,17 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                 u64 dbase = 0;
                 for (u64 c0 = r0; c0 < r1; c0 += RCAP / 2) {
                     const u32 nrc = (u32)min((u64)(RCAP / 2), r1 - c0);
+#if P2_VLIST
+                    // the chunk's records of this thread are loaded up front, under the table clear: the probe loop's atomics are
+                    // fences the next load could not be hoisted over (one L2 round trip per record otherwise)
+                    constexpr int RPT = RCAP / 2 / P2T;
+                    ulonglong2 vv[RPT];
+#pragma unroll
+                    for (int u = 0; u < RPT; u++) {
+                        const u32 i = threadIdx.x + u * P2T;
+                        vv[u] = i < nrc ? __ldcg(reinterpret_cast<const ulonglong2*>(a.rec + (c0 + i) * 2)) : make_ulonglong2(0, 0);
+                    }
+#endif
                     for (int i = threadIdx.x; i < RCAP; i += P2T) {
                         reinterpret_cast<u64*>(rkeys)[2 * i] = ~0ull;
                         reinterpret_cast<u64*>(rkeys)[2 * i + 1] = ~0ull;
@@ -901,9 +912,11 @@ __global__ void __launch_bounds__(P2Cfg<W>::THREADS, P2Cfg<W>::CTAS) count_kerne
                     // the thread whose CAS claims an empty slot appends the slot to a list (a chunk holds <= RCAP / 2 <= VL_CAP
                     // records): the compaction below walks the list, not the table
                     static_assert(RCAP / 2 <= VL_CAP, "one list entry per record of a chunk");
-                    for (u32 i = threadIdx.x; i < nrc; i += P2T) {
-                        ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(a.rec + (c0 + i) * 2));
-                        Kmer<2> key{v.x, v.y};
+#pragma unroll
+                    for (int u = 0; u < RPT; u++) {
+                        const u32 i = threadIdx.x + u * P2T;
+                        if (i >= nrc) break;
+                        Kmer<2> key{vv[u].x, vv[u].y};
                         u32 slot = Ops<2>::hash32(key) >> 8 & (RCAP - 1);
                         const Kmer<2> empty{~0ull, ~0ull};
                         for (;;) {
