@@ -207,6 +207,9 @@ static const int WSC = WP + 64 + 8;                  // p-mer scores per warp ti
 static const int WBK = WP + WP / 16 + 8;             // bucket of every examined position, padded (bkpad)
 static const int WBM = 24;                           // bitmap words per warp tile (>= (31 + WP + 64 + 2) / 32 + 3)
 static const int NST = 4;                            // ring depth
+#ifndef W2_DIRECT
+#define W2_DIRECT 1
+#endif
 #ifndef PRODUCER_NAP_NS
 #define PRODUCER_NAP_NS 256
 #endif
@@ -1971,9 +1974,10 @@ static int filter_impl(Ctx* c, int k, const SeqSet* s, u32 min_obs, int stranded
     // sequencer writes them are in no genomic order, so the first eighth is as good a sample as every 16th tile; position-sorted
     // input is not, and there a mispredicted region costs a second partition + count: the context remembers a failed attempt and
     // keeps such callers on the staging path afterwards.
-    // Two-word keys keep staging as well: their buckets hold ~340 records, too few for a 1/16 sample to size tightly.
+    // (Two-word keys used to keep staging: their buckets hold ~340 records, too few for a 1 : 16 sample; the sampling density now
+    // follows the bucket size.)
     const bool pipelined = s->n_pending > 0;
-    bool use_direct = c->direct_partition && W == 1 && n_pass == 1 && n_tiles_all >= c->direct_min_tiles &&
+    bool use_direct = c->direct_partition && (W == 1 || W2_DIRECT) && n_pass == 1 && n_tiles_all >= c->direct_min_tiles &&
                       (!pipelined || !c->pipelined_direct_failed);
     S.direct_partition = 0;
     for (int attempt = 0;; attempt++) {
