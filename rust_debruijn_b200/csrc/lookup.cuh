@@ -49,10 +49,13 @@ __device__ __forceinline__ u32 table_find(const u64* __restrict__ lo, const u64*
     return NIL;
 }
 
+#ifndef LUT_KEYS_LOG2
+#define LUT_KEYS_LOG2 4   // ~2^4 keys per prefix: the binary search ends inside one 128-byte line
+#endif
 template <int W>
 static inline int build_prefix_lut(Ctx* c, int k, const u64* lo, const u64* hi, u64 n, DBuf<u32>& cnt, DBuf<u64>& lut, int* shift_out) {
     int lb = 8;
-    while ((1ull << (lb + 4)) <= n && lb < 24) lb++;
+    while ((1ull << (lb + LUT_KEYS_LOG2)) <= n && lb < 24) lb++;
     if (lb > 2 * k) lb = 2 * k;
     const int shift = 2 * k - lb;
     const u64 n_pfx = 1ull << lb;
