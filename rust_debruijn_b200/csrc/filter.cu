@@ -2156,7 +2156,8 @@ int partition_regions_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, i
     R->ctx = c; R->k = k; R->p = p; R->bbits = bbits; R->rec_words = k <= 32 ? 2 : 4; R->n_input = N;
     struct Guard { PartRegions* r; ~Guard() { if (r) free_part_regions(r); } } guard{R};
     const u64 n_tiles_all = (s->contiguous && s->total_end > s->base0) ? (s->total_end - s->base0 + TP - 1) / TP : 0;
-    if (N && k <= 32 && c->direct_partition && n_tiles_all >= c->direct_min_tiles && s->n_pending == 0) {
+    const bool pipelined = s->n_pending > 0;   // (first-chunk sampling, remembered fallback: see filter_impl)
+    if (N && k <= 32 && c->direct_partition && n_tiles_all >= c->direct_min_tiles && (!pipelined || !c->pipelined_direct_failed)) {
         DirectOut* d = new DirectOut();
         R->holder = d; R->direct = 1;
         TRY(partition_direct<1>(c, k, s, stranded, N, p, bbits, *d));
@@ -2167,6 +2168,7 @@ int partition_regions_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, i
         } else {   // a region overflowed: staging path below
             delete d;
             R->holder = nullptr; R->direct = 0;
+            if (pipelined) c->pipelined_direct_failed = 1;
         }
     }
     if (!R->rec) {
