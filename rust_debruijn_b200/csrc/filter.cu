@@ -210,9 +210,6 @@ static const int NST = 4;                            // ring depth
 #ifndef W2_DIRECT
 #define W2_DIRECT 1
 #endif
-#ifndef PRODUCER_NAP_NS
-#define PRODUCER_NAP_NS 256
-#endif
 static const int SB_BYTES = 1088;                    // bytes staged per block (8 warp tiles + flanks), multiple of 16
 static const int SBW = 288;                          // u32 words per ring slot
 static const int TP = 4096;                          // (size unit of the direct_min_tiles parameter only)
@@ -257,9 +254,8 @@ __device__ __forceinline__ void mbar_wait_suspended(u64* bar, u32 parity) {
     do {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(ok) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
-        // (the hint alone still returned every ~50 cycles: 12 % of the kernel's executed instructions were this loop; the ring is
-        // 4 blocks deep, a refill that starts a few hundred ns late is never waited for)
-        if (!ok) __nanosleep(PRODUCER_NAP_NS);
+        // (12-15 % of the kernel's executed instructions are this loop; an added __nanosleep between polls changed neither that
+        // share nor the kernel time: the polls take issue slots nobody else wanted)
     } while (!ok);
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
