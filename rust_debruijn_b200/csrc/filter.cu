@@ -660,10 +660,14 @@ __global__ void __launch_bounds__(WT_THREADS, WT_CTAS) msp_tile_kernel(KP kp, P1
 __global__ void bucket_caps_kernel(const u32* __restrict__ sample, u32 nb, float scale, u32* __restrict__ cap) {
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
-    // thinning 1 : scale leaves Poisson-like noise of variance ~ scale * count; "+ scale" keeps the bound honest when the
-    // sample saw (almost) nothing of a small bucket
-    float est = (float)sample[b] * scale;
-    cap[b] = (u32)(est + 6.0f * sqrtf(scale * (est + scale)) + 64.0f);
+    // The sample saw s of the bucket's T records (s ~ Poisson(T / scale)).  The capacity is scale x an UPPER confidence bound of
+    // the Poisson mean given s (z = 6.5: about 1e-10 per bucket), not "estimate + 6 sigma of the estimate": a bucket whose sample
+    // came out low has a low estimate AND a low sigma, and with 2^18 buckets one such bucket per call is the rule, not the
+    // exception (measured: region 109792, 331 records, 4 sampled of 22 expected -> capacity 325 -> the whole partition redone by
+    // the staging path, 18 ms instead of 8 on one of four ranks).
+    const float z = 6.5f, sf = (float)sample[b];
+    const float lam = sf + z * sqrtf(sf + 0.25f * z * z) + 0.5f * z * z;
+    cap[b] = (u32)(lam * scale) + 64u;
 }
 // after the main pass: records actually stored per bucket (cursor clipped to the capacity) and their total
 __global__ void __launch_bounds__(256) bucket_fill_final_kernel(const u32* __restrict__ fill, const u32* __restrict__ cap,
@@ -2162,6 +2166,20 @@ int partition_regions_dev(Ctx* c, int k, const SeqSet* s, int stranded, int p, i
         if (!(u32)h[1]) {
             R->rec = d->rec.p; R->start = d->bucket_start.p; R->cnt = d->cnt.p; R->n_rec = h[2];
         } else {   // a region overflowed: staging path below
+            if (getenv("DBG_MULTI_TRACE")) {   // which regions, and by how much
+                std::vector<u32> hf(NB), hc(NB);
+                std::vector<u64> hs(NB + 1);
+                cudaMemcpy(hf.data(), d->fill.p, (u64)NB * 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(hc.data(), d->cap.p, (u64)NB * 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(hs.data(), d->bucket_start.p, ((u64)NB + 1) * 8, cudaMemcpyDeviceToHost);
+                u64 nover = 0, sumcap = 0, sumfill = 0;
+                for (u32 b = 0; b < NB; b++) {
+                    sumcap += hc[b]; sumfill += hf[b];
+                    if (hf[b] > hc[b] && nover++ < 8) fprintf(stderr, "[dbg multi] region %u: fill %u > cap %u\n", b, hf[b], hc[b]);
+                }
+                fprintf(stderr, "[dbg multi] direct partition overflow: %llu regions over, sum cap %llu (bound %llu), records %llu, flag %llu\n",
+                        (unsigned long long)nover, (unsigned long long)sumcap, (unsigned long long)d->rec_bound, (unsigned long long)sumfill, (unsigned long long)h[1]);
+            }
             delete d;
             R->holder = nullptr; R->direct = 0;
             if (pipelined) c->pipelined_direct_failed = 1;
