@@ -271,7 +271,8 @@ int dbg_graph_from_device(dbg_ctx* ctx, int k, int stranded, uint64_t n_nodes, u
  * A communicator is one rank: one process per GPU (dbg_comm_create; every rank passes the same 128-byte id obtained from
  * dbg_comm_unique_id on one rank and distributed by the caller's own rendezvous), or one process driving several GPUs with one
  * host thread per rank (dbg_multi_*; the communicators are owned by the handle).  Calls are collective: every rank must make
- * the same call.  Transport "nccl" = grouped ncclSend/ncclRecv + all-reduce on the ctx stream; "local" (dbg_multi_* only, when
+ * the same call.  Transport "nccl" = peer windows (CUDA IPC) written directly by the exchange kernel over NVLink, grouped
+ * ncclSend/ncclRecv for the small exchanges, all-gather / all-reduce on the ctx stream; "local" (dbg_multi_* only, when
  * the device list repeats a device, NCCL is missing, or DBG_MULTI_TRANSPORT=local) stages through cudaMemcpy between the ranks'
  * buffers and exists so that the multi-rank logic can be exercised on ONE GPU. */
 typedef struct dbg_comm dbg_comm;
@@ -283,7 +284,7 @@ typedef struct {
     uint64_t n_nodes_total, n_bases_total;   /* the complete BaseGraph */
     uint64_t node0, base0;   /* position of this rank's run of nodes in the complete graph (0 when replicated) */
     uint64_t n_queries_sent; /* neighbour lookups this rank had to send to other ranks */
-    uint64_t exchange_bytes_sent; /* super-k-mer record bytes this rank sent in the all-to-all */
+    uint64_t exchange_bytes_sent; /* super-k-mer record bytes this rank stored into other ranks' windows (the path's one big exchange) */
     uint32_t replicated;     /* 1 = long unitigs / cycles: the table was gathered and every rank returns the COMPLETE graph */
     uint32_t check_ok;       /* n_bases_total == n_valid_total + n_nodes_total * (k - 1) and every k-mer was covered */
     uint32_t msp_p, bucket_bits;

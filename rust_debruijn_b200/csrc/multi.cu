@@ -3,12 +3,15 @@
 // process driving several GPUs with one host thread per rank (dbg_multi_create).  No torch, no Python in the data path.
 //
 //   filter_kmers   shards by MSP bucket — the reference's own sharded flow (src/test.rs:433-456: msp_sequence -> per-shard
-//                  filter_kmers): every rank cuts ITS reads into super-k-mer records with the same plan, ONE all-to-all
-//                  ships each bucket range to its owner (NCCL grouped send / recv over NVLink), the owner counts its buckets.
-//   compress_kmers the table STAYS sharded (shard_compress.cu): remote neighbour queries by a second, small all-to-all,
-//                  unitig walks over peer-mapped walk records (CUDA IPC / peer access: NVLink loads), path records shipped
-//                  to the rank that owns their seed's key range; every rank ends with a contiguous run of nodes of the
-//                  complete BaseGraph (runs concatenated in rank order = the single-GPU graph, bit for bit).
+//                  filter_kmers): every rank cuts ITS reads into per-bucket regions of super-k-mer records with the same plan;
+//                  the per-bucket counts are all-gathered, so every sender knows the final position of each of its buckets in
+//                  the owner's bucket-contiguous receive window, and ONE kernel stores the records there over peer memory
+//                  (NVLink; compaction + exchange fused, no send buffer, no merge on the receiver); the owner counts its buckets.
+//   compress_kmers the table STAYS sharded (shard_compress.cu): remote neighbour queries by a small all-to-all; unitig walkers
+//                  never read another rank's records — a walker whose chain continues elsewhere is shipped there (bulk all-to-all
+//                  per round) with the node it has collected so far; finished nodes go to the rank that owns their seed's key
+//                  range; every rank ends with a contiguous run of nodes of the complete BaseGraph (runs concatenated in rank
+//                  order = the single-GPU graph, bit for bit).
 //
 // Transports: NCCL (+ CUDA IPC for the peer windows) is the product path; a host-staged "local" transport connects ranks
 // living in one process without NCCL — it lets several ranks share ONE device, which is how the multi-rank logic is

@@ -2,8 +2,8 @@
 flow (src/test.rs:418-470: msp_sequence -> per-shard filter_kmers -> compress -> combine + compress_graph) as ONE collective
 call whose per-rank outputs, concatenated in rank order, are the single-GPU BaseGraph bit for bit.
 
-All data-path communication (NCCL all-to-all of super-k-mer records, neighbour queries, path records; NVLink peer loads of
-the walk records) happens inside libdbg_b200.so.  Python only hands every rank the same NCCL unique id:
+All data-path communication (super-k-mer records stored straight into the owners' peer-mapped windows over NVLink; NCCL
+all-to-alls of neighbour queries, walkers and finished nodes) happens inside libdbg_b200.so.  Python only hands every rank the same NCCL unique id:
 
     comm = Comm.from_torch(ctx)          # one process per GPU under torchrun: id broadcast through torch.distributed
     g = comm.reads_to_graph(seqs, CountFilter(2), SimpleCompress(SAT_ADD), k=31)
