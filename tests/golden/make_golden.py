@@ -36,6 +36,25 @@ def rows():
                         edges=sha(target, flags), n_edges=int((target != 0xffffffff).sum()), is_compressed=pair is None,
                         fix_exts=sha(O.graph_fix_exts(k, g0, stranded=stranded)), gfa=sha(O.write_gfa(k, g, stranded=stranded).encode()),
                         scmap_nodes=int(gs["n_nodes"]), scmap_graph=sha(gs["words"], gs["start"], gs["length"], gs["exts"], gs["data"])))
+    # round 2: compress_graph / combine over the reference's sharded flow (src/test.rs:418-504), hashn ingest, bincode image
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import msp_shard_graphs, random_contigs   # noqa: E402
+    rng = np.random.default_rng(2024)
+    for k in (31, 47):
+        contigs = [c for c in random_contigs(rng) if len(c) >= k]
+        shard_graphs = msp_shard_graphs(O, k, 6, contigs)
+        comb = O.combine_graphs(shard_graphs)
+        m = int(comb["n_nodes"])
+        censor = sorted(set(int(x) for x in rng.integers(0, m, size=max(1, m // 10))))
+        cg = O.compress_graph(k, comb, reduce_op=O.MAX)
+        cgc = O.compress_graph(k, comb, reduce_op=O.SAT_ADD, censor_nodes=censor)
+        out.append(dict(compress_graph=True, k=k, n_shards=len(shard_graphs), combined_nodes=m,
+                        combined=sha(comb["words"], comb["start"], comb["length"], comb["exts"], comb["data"]),
+                        nodes=int(cg["n_nodes"]), graph=sha(cg["words"], cg["start"], cg["length"], cg["exts"], cg["data"]),
+                        censored_nodes=int(cgc["n_nodes"]), censored_graph=sha(cgc["words"], cgc["start"], cgc["length"], cgc["exts"], cgc["data"]),
+                        bincode=sha(O.graph_to_bincode(cg))))
+    hw, hst, hln, hbad = O.from_acgt_bytes_hashn([b"ACGTNNacgtXy-", b"NNNN", b""], [b"read/1", b"r2", b"empty"])
+    out.append(dict(hashn=True, words=sha(hw), n_invalid=int(hbad), siphash13_abc=int(O.siphash13(b"abc"))))
     ascii_reads = [b"ACGTNNacgtXy-", b"", b"TTTTTGGGGGCCCCCAAAAATTTTTGGGGGCCCCCAAAAAT", b"g"]
     aw, ast_, aln, abad = O.from_acgt_bytes(ascii_reads)
     out.append(dict(ascii=True, words=sha(aw), start=[int(x) for x in ast_], length=[int(x) for x in aln], n_invalid=int(abad)))

@@ -946,3 +946,31 @@ def test_compress_graph_errors_and_empty(D, ctx, orc):
     assert orc.compress_graph(20, g)["error"] == 1
     with pytest.raises(D.DbgError):
         D.compress_graph(False, D.SimpleCompress(), D.BaseGraph.from_host(g, 20, ctx=ctx))
+
+
+def test_compress_graph_golden_vectors(D, ctx, orc):
+    """The device's combine / compress_graph outputs hash to the committed vectors of tests/golden/widened.json (inputs regenerated
+    from the same seeds as tests/golden/make_golden.py; the vectors are the oracle's — see that script's header)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    want = [r for r in json.load(open(os.path.join(HERE, "golden", "widened.json")))["rows"] if r.get("compress_graph")]
+    rng = np.random.default_rng(2024)
+    assert [r["k"] for r in want] == [31, 47]
+    for row in want:
+        k = row["k"]
+        contigs = [c for c in random_contigs(rng) if len(c) >= k]
+        shard_graphs = msp_shard_graphs(orc, k, 6, contigs)
+        comb = D.BaseGraph.combine([D.BaseGraph.from_host(g, k, ctx=ctx) for g in shard_graphs])
+        ch = comb.to_host()
+        m = len(comb)
+        censor = sorted(set(int(x) for x in rng.integers(0, m, size=max(1, m // 10))))
+        assert m == row["combined_nodes"] and mg.sha(ch["words"], ch["start"], ch["length"], ch["exts"], ch["data"]) == row["combined"]
+        cg = D.compress_graph(False, D.SimpleCompress(D.MAX), comb)
+        gh = cg.to_host()
+        assert len(cg) == row["nodes"] and mg.sha(gh["words"], gh["start"], gh["length"], gh["exts"], gh["data"]) == row["graph"]
+        assert mg.sha(cg.to_bincode()) == row["bincode"]
+        cgc = D.compress_graph(False, D.SimpleCompress(D.SAT_ADD), comb, censor).to_host()
+        assert cgc["n_nodes"] == row["censored_nodes"]
+        assert mg.sha(cgc["words"], cgc["start"], cgc["length"], cgc["exts"], cgc["data"]) == row["censored_graph"]
