@@ -441,15 +441,20 @@ class BaseGraph:
         return BaseGraph(ctx, h)
 
     @staticmethod
-    def from_host(g, k, ctx=None):
-        """A device BaseGraph from host arrays (dict with words / start / length / exts / data / stranded), through the bincode image."""
+    def host_image(g):
+        """bincode 1.x image (serde field order of the crate's BaseGraph<K, u16>, src/graph.rs:43-50) of host arrays: dict with words /
+        start / length / exts / data / n_bases / stranded.  Pure host code."""
         def vec(x, dt):
             x = np.ascontiguousarray(x, dt)
             return np.uint64(len(x)).tobytes() + x.tobytes()
         nw = (int(g["n_bases"]) + 31) // 32
-        img = (vec(np.asarray(g["words"])[:nw], "<u8") + np.uint64(int(g["n_bases"])).tobytes() + vec(g["start"], "<u8") + vec(g["length"], "<u4") +
-               vec(g["exts"], "u1") + vec(g["data"], "<u2") + bytes([1 if g.get("stranded") else 0]))
-        return BaseGraph.from_bincode(img, k, ctx=ctx)
+        return (vec(np.asarray(g["words"])[:nw], "<u8") + np.uint64(int(g["n_bases"])).tobytes() + vec(g["start"], "<u8") +
+                vec(g["length"], "<u4") + vec(g["exts"], "u1") + vec(g["data"], "<u2") + bytes([1 if g.get("stranded") else 0]))
+
+    @staticmethod
+    def from_host(g, k, ctx=None):
+        """A device BaseGraph from host arrays, through the bincode image."""
+        return BaseGraph.from_bincode(BaseGraph.host_image(g), k, ctx=ctx)
 
     def write_gfa(self, out):
         """DebruijnGraph::write_gfa (src/graph.rs:538-614): header, one S line per node, L lines for the left edges with
