@@ -14,6 +14,11 @@
 // determined by src/filter.rs:205-219: ascending, unique), and the model-derived anchors of
 // SURVEY.md Appendix B (an independent second restatement).  Seed order used here: ascending
 // canonical k-mer (= order of valid_kmers before BoomHashMap2::new permutes them).
+// compress_graph (CompressFromGraph, src/compression.rs:100-349) has no such caveat — its seeds are taken
+// in node order (:322-327) — and is pinned by the assertions of the reference's own sharded test
+// (src/test.rs:418-504) and by bit-equality with compress_kmers on one-node-per-k-mer graphs.
+// Restated here: filter_kmers (+ threaded variant), CompressFromHash, CompressFromGraph, finish /
+// find_edges / is_compressed, remove_censored_exts[_sharded], Scanner::scan / msp_sequence, synth-v1.
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
