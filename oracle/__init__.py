@@ -78,7 +78,7 @@ def lib():
         L.orc_compress_kmers.argtypes = [C.c_int, C.c_uint64, u64p, u64p, u8p, u16p, C.c_int, C.c_int, u32p]
         L.orc_graph_error.argtypes = [C.c_void_p]
         L.orc_compress_graph.restype = C.c_void_p
-        L.orc_compress_graph.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, u64p, u32p, u8p, u16p, u8p]
+        L.orc_compress_graph.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, u64p, u32p, u8p, u16p, u8p]
         for f in ("orc_graph_n_nodes", "orc_graph_n_bases"):
             getattr(L, f).restype = C.c_uint64
             getattr(L, f).argtypes = [C.c_void_p]
@@ -369,7 +369,7 @@ def compress_graph(k, g, stranded=False, reduce_op=SAT_ADD, censor_nodes=None):
     if censor_nodes is not None:
         censor = np.zeros(m, np.uint8)
         censor[np.asarray(list(censor_nodes), np.int64)] = 1
-    h = L.orc_compress_graph(k, int(stranded), reduce_op, m, _p(words, C.c_uint64), _p(start, C.c_uint64), _p(length, C.c_uint32),
+    h = L.orc_compress_graph(k, int(stranded), int(bool(g.get("stranded", stranded))), reduce_op, m, _p(words, C.c_uint64), _p(start, C.c_uint64), _p(length, C.c_uint32),
                              _p(exts, C.c_uint8), _p(data, C.c_uint16), _p(censor, C.c_uint8))
     return _graph_out(h, stranded)
 

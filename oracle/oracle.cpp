@@ -673,10 +673,12 @@ struct GraphCompressor {
     int error = 0;
     struct Step { uint32_t node; int dir; };
 
-    GraphCompressor(int k_, int stranded_, int op_, uint64_t m_, const uint64_t* w, const uint64_t* st, const uint32_t* len,
+    // stranded_: the function's argument (palindrome rule, flag of the result); graph_stranded: old_graph.base.stranded, which is
+    // what DebruijnGraph::find_link consults (graph.rs:268, 281)
+    GraphCompressor(int k_, int stranded_, int graph_stranded, int op_, uint64_t m_, const uint64_t* w, const uint64_t* st, const uint32_t* len,
                     const uint8_t* e, const uint16_t* d, const uint8_t* censor /* one byte per node, may be null */)
         : k(k_), stranded(stranded_), op(op_), m(m_), words(w), start(st), length(len), data(d), exts(e, e + m_), avail(m_, 1),
-          ix(k_, stranded_, m_, w, st, len) {
+          ix(k_, graph_stranded, m_, w, st, len) {
         if (censor) for (uint64_t i = 0; i < m; i++) if (censor[i]) avail[i] = 0;
         fix_exts(ix, exts, avail.data());
     }
@@ -874,11 +876,11 @@ void* orc_compress_kmers(int k, uint64_t n, const uint64_t* lo, const uint64_t* 
     return g;
 }
 // compress_graph(stranded, spec, old_graph, censor_nodes): censor = one byte per node (non-zero = in censor_nodes) or null.
-void* orc_compress_graph(int k, int stranded, int reduce_op, uint64_t m, const uint64_t* words, const uint64_t* start,
+void* orc_compress_graph(int k, int stranded, int graph_stranded, int reduce_op, uint64_t m, const uint64_t* words, const uint64_t* start,
                          const uint32_t* length, const uint8_t* exts, const uint16_t* data, const uint8_t* censor) {
     GraphOut* g = new GraphOut();
-    if (k <= 32) { GraphCompressor<uint64_t> c(k, stranded, reduce_op, m, words, start, length, exts, data, censor); c.run(*g); }
-    else { GraphCompressor<u128> c(k, stranded, reduce_op, m, words, start, length, exts, data, censor); c.run(*g); }
+    if (k <= 32) { GraphCompressor<uint64_t> c(k, stranded, graph_stranded, reduce_op, m, words, start, length, exts, data, censor); c.run(*g); }
+    else { GraphCompressor<u128> c(k, stranded, graph_stranded, reduce_op, m, words, start, length, exts, data, censor); c.run(*g); }
     return g;
 }
 int orc_graph_error(void* h) { return ((GraphOut*)h)->error; }
