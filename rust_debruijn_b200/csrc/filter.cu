@@ -734,7 +734,6 @@ __global__ void __launch_bounds__(256) scatter_records_kernel(const u64* __restr
 // ------------------------------------------------------------------------------------------------
 // P2: per-bucket counting in shared memory
 // ------------------------------------------------------------------------------------------------
-static const int P2_THREADS = 512;
 // P2_VLIST: a k-mer whose count crosses min_obs is appended to a shared-memory list when it happens, so the emission writes
 // the <= VL_CAP valid k-mers of a bucket without scanning the table (the scan stays for report_all and for buckets with more)
 #ifndef P2_VLIST
