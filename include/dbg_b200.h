@@ -311,6 +311,12 @@ int dbg_multi_reads_to_graph(dbg_multi* m, int k, const dbg_seqset* const* seqs,
 /* pure host helpers of the plan (no GPU): bucket ownership (rank r owns [bounds[r], bounds[r+1])) and quantile cuts of a histogram */
 int dbg_plan_owner_bounds(uint64_t n_buckets, int n_ranks, uint64_t* bounds_out /* n_ranks + 1 */);
 int dbg_plan_quantile_cuts(const uint64_t* hist, uint64_t n_bins, int n_ranks, uint64_t* cuts_out /* n_ranks + 1 */);
+/* Layout of the fused record exchange of dbg_reads_to_graph_multi, as a pure host function (the device computes the same from the
+ * all-gathered counts): all_counts[s * n_buckets + b] = records of bucket b on rank s; dst_off[b] = where sender `me` stores its
+ * records of bucket b inside the window of the bucket's owner (in records; buckets contiguous, senders in rank order inside a
+ * bucket); recv_total[r] = records rank r ends up with. */
+int dbg_plan_exchange_layout(const uint32_t* all_counts, int n_ranks, int me, uint64_t n_buckets, uint64_t* dst_off /* n_buckets */,
+                             uint64_t* recv_total /* n_ranks */);
 
 /* ---- msp::msp_sequence bucket assignment — src/msp.rs:279-324, 115-117 -----------------------------
  * For every k-mer start position j of every sequence: the MSP bucket of that k-mer under the

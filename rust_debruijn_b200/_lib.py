@@ -146,6 +146,7 @@ SIGNATURES = {
     "dbg_multi_reads_to_graph": (C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_int, C.c_int, vp, vp]),
     "dbg_plan_owner_bounds": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     "dbg_plan_quantile_cuts": (C.c_int, [C.POINTER(C.c_uint64), C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
+    "dbg_plan_exchange_layout": (C.c_int, [vp, C.c_int, C.c_int, C.c_uint64, vp, vp]),
 }
 
 _lib = None

@@ -807,4 +807,30 @@ int dbg_plan_quantile_cuts(const uint64_t* hist, uint64_t n_bins, int n_ranks, u
     return DBG_OK;
 }
 
+/* Layout of the fused exchange (scatter_buckets_kernel + bucket_totals_kernel + the scan, restated on the host for the CPU tests):
+ * all_counts[s * n_buckets + b] = records of bucket b on rank s.  For sender `me`: dst_off[b] = position (in records) of its chunk of
+ * bucket b inside the window of the bucket's owner = (records of the owner's buckets below b, all senders) + (records of bucket b
+ * on the senders below me).  recv_total[r] = records rank r receives. */
+int dbg_plan_exchange_layout(const uint32_t* all_counts, int n_ranks, int me, uint64_t n_buckets, uint64_t* dst_off /* n_buckets */,
+                             uint64_t* recv_total /* n_ranks */) {
+    if (!all_counts || !dst_off || !recv_total || n_ranks < 1 || n_ranks > DBG_MAX_RANKS || me < 0 || me >= n_ranks) return DBG_E_BADARG;
+    u64 bounds[DBG_MAX_RANKS + 1];
+    owner_bounds(n_buckets, n_ranks, bounds);
+    for (int r = 0; r < n_ranks; r++) {
+        u64 goff = 0;   // goff[b] - goff[bounds[r]] of the device code
+        for (u64 b = bounds[r]; b < bounds[r + 1]; b++) {
+            u64 tot = 0, pre = 0;
+            for (int s2 = 0; s2 < n_ranks; s2++) {
+                const u64 v = all_counts[(u64)s2 * n_buckets + b];
+                if (s2 < me) pre += v;
+                tot += v;
+            }
+            dst_off[b] = goff + pre;
+            goff += tot;
+        }
+        recv_total[r] = goff;
+    }
+    return DBG_OK;
+}
+
 }  // extern "C"

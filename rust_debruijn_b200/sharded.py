@@ -82,3 +82,17 @@ def reads_to_graph_sharded(seqs, summarizer, spec, stranded=False, k=31, group=N
     finally:
         if own:
             comm.close()
+
+
+def exchange_layout(all_counts, me):
+    """Where sender `me` stores its records of every bucket inside the owners' windows (dbg_plan_exchange_layout): all_counts is the
+    all-gathered [world, n_buckets] uint32 matrix.  Returns (dst_off[n_buckets] in records, recv_total[world])."""
+    all_counts = np.ascontiguousarray(all_counts, np.uint32)
+    world, nb = all_counts.shape
+    dst_off = np.zeros(nb, np.uint64)
+    recv_total = np.zeros(world, np.uint64)
+    st = _lib.lib().dbg_plan_exchange_layout(all_counts.ctypes.data_as(C.c_void_p), world, me, nb, dst_off.ctypes.data_as(C.c_void_p),
+                                             recv_total.ctypes.data_as(C.c_void_p))
+    if st != 0:
+        raise ValueError("bad arguments")
+    return dst_off, recv_total

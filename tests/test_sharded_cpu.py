@@ -129,3 +129,53 @@ def test_seed_key_ranges_gloo(world):
         assert lo[d] > max(hi[:d])
     total = per_dst.sum()
     assert per_dst.max() - per_dst.min() <= 0.1 * total / world + 4096   # quantile cuts at 2^16-bin granularity
+
+
+def _layout_worker(rank, world, port, nb, out):
+    import torch
+    import torch.distributed as dist
+
+    from rust_debruijn_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(500 + rank)
+    counts = rng.integers(0, 40, size=nb).astype(np.int32)
+    counts[rng.integers(0, nb, size=max(1, nb // 4))] = 0                 # empty buckets on some ranks
+    gathered = [torch.zeros(nb, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(counts))                   # the library all-gathers the same matrix (NCCL, on the device)
+    allc = np.stack([g.numpy() for g in gathered]).astype(np.uint32)
+    dst_off, recv_total = sharded.exchange_layout(allc, rank)
+    out[rank] = (counts.astype(np.uint32), dst_off, recv_total)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nb", [(2, 64), (3, 50), (2, 2)])
+def test_fused_exchange_layout_gloo(world, nb):
+    """The layout every sender derives from the all-gathered per-bucket counts (dbg_plan_exchange_layout, the host restatement of what
+    bucket_totals_kernel + the scan + scatter_buckets_kernel compute): all ranks agree on the receive totals, and the senders' chunks
+    tile every owner's window exactly — buckets contiguous and ascending, senders in rank order inside a bucket, no gap, no overlap."""
+    import torch.multiprocessing as mp
+
+    from rust_debruijn_b200 import sharded
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_layout_worker, args=(world, port, nb, out), nprocs=world, join=True)
+    bounds = sharded.owner_bounds(nb, world)
+    for r in range(1, world):
+        assert np.array_equal(out[r][2], out[0][2])                       # everybody computed the same receive totals
+    for dst in range(world):
+        total = int(out[0][2][dst])
+        assert total == sum(int(out[s][0][bounds[dst]:bounds[dst + 1]].sum()) for s in range(world))
+        cover = np.zeros(total, np.int32)
+        pos = 0
+        for b in range(bounds[dst], bounds[dst + 1]):
+            for s in range(world):                                        # expected order: bucket-major, sender-minor
+                n, off = int(out[s][0][b]), int(out[s][1][b])
+                if n:
+                    assert off == pos, (dst, b, s)
+                cover[off:off + n] += 1
+                pos += n
+        assert pos == total and (cover == 1).all()
